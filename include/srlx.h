@@ -1,0 +1,225 @@
+/*
+ * srlx.h -- C ABI of libsrlx.so: the B200 (sm_100a) rollout -> replay -> PER sample -> TD/Adam update path
+ * behind the SRL (pocokhc/simple_distributed_rl v1.4.5) plugin API.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes only.  No torch / Python types cross this boundary.
+ *   - Every buffer is CALLER-OWNED device memory (the Python host side allocates torch CUDA tensors and passes
+ *     data_ptr()).  The library keeps no state between calls except the thread-local error string.
+ *   - Every call takes the CUDA stream as a uintptr_t-sized handle and is asynchronous on it unless noted "sync".
+ *   - Return value: 0 = ok, <0 = error; srlx_last_error() returns a thread-local message.
+ *   - One set of buffers is driven from one host thread at a time (documented, not locked), like the reference's
+ *     GIL-serialised pybind11 module (srl/rl/memories/priority_memories/cpp_module/src/proportional_memory.cpp).
+ *
+ * Reference interfaces replaced (paths relative to the reference root):
+ *   srlx_tree_*      <- ProportionalMemory / SumTree: srl/rl/memories/priority_memories/proportional_memory.py:13-205
+ *                       and its pybind11 twin cpp_module/src/proportional_memory.cpp:14-275
+ *   srlx_vec_step    <- core_play.play loop body srl/base/run/core_play.py:115-214 (policy -> env.step -> on_step),
+ *                       EnvRun.step srl/base/env/env_run.py:254-366, WorkerRun srl/base/rl/worker_run.py:310-401,
+ *                       Grid srl/envs/grid.py:173-208,340-378, dqn.Worker.policy/on_step srl/algorithms/dqn/dqn.py:192-246,
+ *                       rainbow.Worker srl/algorithms/rainbow/rainbow.py:301-400
+ *   srlx_learn       <- dqn Trainer.train srl/algorithms/dqn/model_torch.py:90-132, rainbow Trainer.train
+ *                       srl/algorithms/rainbow/model_torch.py:85-122, calc_target_q dqn.py:144-176,
+ *                       rainbow.py:185-287, rainbow_nomultisteps.py:10-43, PriorityReplayBuffer.sample/update
+ *                       srl/rl/memories/priority_replay_buffer.py:228-250, ReplayBuffer.sample
+ *                       srl/rl/memories/priority_memories/replay_buffer.py:34-36
+ *   srlx_qnet_forward<- RLParameter.pred_q / pred_target_q srl/algorithms/dqn/model_torch.py:58-70
+ */
+#ifndef SRLX_H_
+#define SRLX_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SRLX_VERSION 100 /* 0.1.0 */
+
+#define SRLX_MAX_LAYERS 6   /* dense layers incl. the output layer */
+#define SRLX_MAX_OBS 16     /* observation floats per env step */
+#define SRLX_MAX_ACTIONS 16 /* discrete actions */
+#define SRLX_MAX_MULTISTEPS 8
+#define SRLX_MAX_BATCH 256
+
+/* ---- environments (closed-form, stepped on device) ------------------------------------------------------ */
+enum { SRLX_ENV_GRID = 0, SRLX_ENV_CARTPOLE = 1 };
+
+/* dueling combine: srl/rl/torch_/blocks/dueling_network.py:51-58 */
+enum { SRLX_DUEL_NONE = 0, SRLX_DUEL_AVERAGE = 1, SRLX_DUEL_MAX = 2, SRLX_DUEL_NAIVE = 3 };
+
+/* replay kind: srl/rl/memories/priority_replay_buffer.py:119-152 */
+enum { SRLX_MEM_UNIFORM = 0, SRLX_MEM_PROPORTIONAL = 1 };
+
+/* Q-network: a stack of dense layers (ReLU between, last one linear).  Flat parameter layout, fp32:
+ *   for l in 0..n_layers-1:  W_l [out_l][in_l] row-major (torch nn.Linear layout) at w_off[l], b_l [out_l] at b_off[l].
+ * Dueling head (srl/rl/torch_/blocks/dueling_network.py:8-59): the LAST HIDDEN layer is the concatenation
+ * [value-hidden(H) ; advantage-hidden(H)] (width 2H) and the output layer has 1+A rows of H inputs each:
+ * row 0 (V) reads hidden[0:H], rows 1..A (advantages) read hidden[H:2H].
+ * Noisy layers (srl/rl/torch_/modules/noisy_linear.py:8-52): a second flat buffer "sigma" with the same layout;
+ * effective weight = mu + sigma * N(0,1), noise re-drawn per forward call. */
+typedef struct srlx_net {
+  int32_t n_layers;
+  int32_t in_dim;
+  int32_t out_dim[SRLX_MAX_LAYERS]; /* rows of W_l; last = n_actions (plain) or 1+n_actions (dueling) */
+  int32_t k_dim[SRLX_MAX_LAYERS];   /* columns of W_l (in_l; for the dueling output layer this is H) */
+  int32_t w_off[SRLX_MAX_LAYERS];
+  int32_t b_off[SRLX_MAX_LAYERS];
+  int32_t n_params; /* floats in one flat buffer */
+  int32_t n_actions;
+  int32_t dueling; /* SRLX_DUEL_* */
+  int32_t noisy;   /* 0/1: any layer is a NoisyLinear */
+  int32_t layer_noisy[SRLX_MAX_LAYERS]; /* per layer: the plain out Linear of a noisy rainbow MLP is NOT noisy
+                                           (srl/rl/models/config/dueling_network.py:125-127) */
+} srlx_net;
+
+/* Device-resident counters / scalars shared by the kernels (one per engine, 256-byte aligned). */
+typedef struct srlx_state {
+  uint64_t vec_steps;     /* g: vector steps executed so far */
+  uint64_t total_step;    /* RunState.total_step  (srl/base/context.py:297-343): env steps = vec_steps * n_envs */
+  uint64_t train_count;   /* RLTrainer.train_count (srl/base/rl/trainer.py:14-62) */
+  uint64_t episode_count; /* RunState.episode_count */
+  uint64_t sync_count;    /* trainer.info["sync"] */
+  uint64_t adam_step;     /* torch.optim.Adam state["step"] */
+  uint64_t mem_size;      /* items currently sampleable (ProportionalMemory.size / len(ReplayBuffer.memory)) */
+  uint64_t sample_retries;/* PER rejections (priority==0 or duplicate), diagnostics */
+  double max_priority;    /* ProportionalMemory.max_priority (proportional_memory.py:116) */
+  double episode_reward_sum;   /* sum of finished-episode rewards (for mean reward reporting) */
+  double last_loss;       /* trainer.info["loss"] of the last update */
+  double loss_sum;        /* sum of losses since last host reset */
+  uint64_t episode_len_sum;
+  uint64_t reserved[3];
+} srlx_state;
+
+/* Engine configuration: dimensions, hyper-parameters and the device pointers of every caller-owned buffer. */
+typedef struct srlx_engine {
+  /* ---- sizes ---- */
+  int32_t env_id;          /* SRLX_ENV_* */
+  int32_t n_envs;          /* E */
+  int32_t obs_dim;         /* D */
+  int32_t n_actions;       /* A */
+  int32_t ring_rows;       /* R: ring capacity = R*E slots; slot(g,e) = (g % R)*E + e */
+  int32_t multisteps;      /* M >= 1 (rainbow.Config.multisteps) */
+  int32_t batch_size;      /* B */
+  int32_t mem_kind;        /* SRLX_MEM_* */
+  /* ---- algorithm switches (dqn.py:50-103, rainbow.py:57-108) ---- */
+  int32_t enable_double_dqn;
+  int32_t enable_rescale;
+  int32_t enable_reward_clip;
+  int32_t has_duplicate;   /* ProportionalMemory.has_duplicate */
+  int32_t target_update_interval;
+  int32_t trunc_limit;     /* episode is truncated when step_num reaches this (CartPole 500; Grid 51 = max_episode_steps+1) */
+  int32_t trunc_overrides_term; /* gymnasium TimeLimit semantics: truncated wins over terminated */
+  int32_t reserved_i;
+  uint64_t seed;
+  uint64_t warmup_size;
+  /* ---- hyper-parameters ---- */
+  double epsilon;          /* epsilon-greedy (ignored when net.noisy, rainbow.py:305-309) */
+  double discount;
+  double lr;
+  double adam_beta1, adam_beta2, adam_eps;
+  double retrace_h;
+  double per_alpha, per_beta_initial, per_beta_steps, per_epsilon;
+  double reward_shift, reward_scale; /* WorkerRun: (r + shift) * scale, worker_run.py:348 */
+  double huber_delta;
+  /* ---- Grid env tables (srl/envs/grid.py) ---- */
+  int32_t grid_w, grid_h;
+  int8_t grid_field[64];       /* row-major [h][w]; 9 wall, 1 goal, -1 hole, 2 start, 0 road */
+  int32_t grid_n_starts;
+  int32_t grid_starts[16];     /* x | y<<8 */
+  double grid_slip_cdf[16];    /* [chosen action][4] normalised cdf in the order np.random.choice sees (UP,DOWN,RIGHT,LEFT) */
+  int32_t grid_slip_action[4]; /* executed action for each cdf slot: {3,1,2,0} */
+  double grid_move_reward, grid_goal_reward, grid_hole_reward;
+  /* ---- network ---- */
+  srlx_net net;
+  /* ---- device buffers (caller-owned) ---- */
+  srlx_state* state;        /* 1 */
+  double* env_state;        /* [E][4] f64 (CartPole x,x_dot,theta,theta_dot; Grid x,y in [0],[1]) */
+  int32_t* env_step_num;    /* [E] EnvRun._step_num */
+  uint32_t* env_episode;    /* [E] episodes started by this env (RNG counter) */
+  double* env_ep_reward;    /* [E] EnvRun._episode_rewards */
+  uint8_t* env_needs_reset; /* [E] */
+  float* ring_obs;          /* [R*E][D] state            */
+  float* ring_next_obs;     /* [R*E][D] next_state       */
+  int32_t* ring_action;     /* [R*E] action index (one-hot in the reference record) */
+  float* ring_reward;       /* [R*E] */
+  uint8_t* ring_term;       /* [R*E] worker.terminated (NOT truncated) */
+  uint8_t* ring_done;       /* [R*E] episode ended at this step (terminated or truncated) */
+  double* tree;             /* [2*R*E-1] SumTree nodes, leaf j at j + R*E - 1 (proportional_memory.py:13-47); NULL for uniform */
+  float* params;            /* [n_params] online mu */
+  float* params_sigma;      /* [n_params] online sigma (noisy) or NULL */
+  float* target;            /* [n_params] target mu */
+  float* target_sigma;      /* [n_params] or NULL */
+  float* adam_m;            /* [n_params * (1+noisy)] exp_avg   (mu block then sigma block) */
+  float* adam_v;            /* [n_params * (1+noisy)] exp_avg_sq */
+  /* ---- optional debug taps (NULL in production) ---- */
+  float* dbg_q;             /* [E][A] Q values the policy saw in the last vector step */
+  int32_t* dbg_action;      /* [E] */
+  int64_t* dbg_sample_idx;  /* [B] tree indices (PER) or slots (uniform) of the last update */
+  float* dbg_weights;       /* [B] IS weights of the last update */
+  float* dbg_target_q;      /* [B] */
+  float* dbg_q_sa;          /* [B] */
+  float* dbg_grads;         /* [n_params*(1+noisy)] gradient of the last update */
+  float* dbg_windows;       /* [B][M+1][D] states, then [B][M] (action, reward, term) as floats */
+} srlx_engine;
+
+/* ---- library ------------------------------------------------------------------------------------------ */
+int srlx_version(void);
+const char* srlx_last_error(void);
+size_t srlx_sizeof_engine(void);
+size_t srlx_sizeof_state(void);
+size_t srlx_sizeof_net(void);
+/* Number of kernels launched by this library in this process since load (bench.py "gpu_launches"). */
+uint64_t srlx_launch_count(void);
+
+/* ---- RNG taps (parity of the device Philox4x32-10 streams with oracle/philox.py) ------------------------- */
+/* out[i*4..i*4+3] = philox4x32-10(ctr = (a0+i, b, c, stream), key = seed) for i < n. */
+int srlx_philox_words(uint64_t seed, uint32_t stream, uint32_t a0, uint32_t b, uint32_t c, uint32_t* out_dev,
+                      size_t n, uintptr_t cuda_stream);
+/* The N(0,1) noise tensor a NoisyLinear forward call `call_id` of kind `kind` uses (flat param layout). */
+int srlx_noise_fill(uint64_t seed, uint32_t kind, uint64_t call_id, float* out_dev, size_t n_params,
+                    uintptr_t cuda_stream);
+
+/* ---- SumTree / ProportionalMemory (R7) -- narrow seam, mirrors the pybind11 class method by method -------- */
+/* tree: [2*capacity-1] doubles; meta: srlx_state (uses mem_size, max_priority, vec_steps as the ring `write`). */
+int srlx_tree_clear(double* tree, uint64_t capacity, srlx_state* meta, uintptr_t cuda_stream);
+/* add n items at ring positions write, write+1, ... (mod capacity).  priorities_dev == NULL -> max_priority
+ * (proportional_memory.py:120-129); restore_skip != 0 -> priorities are used as-is. */
+int srlx_tree_add(double* tree, uint64_t capacity, srlx_state* meta, const double* priorities_dev, uint64_t n,
+                  double alpha, double epsilon, int restore_skip, uintptr_t cuda_stream);
+/* sample `batch` leaves.  If u01_dev != NULL it holds pre-drawn uniforms [batch][max_tries] (row i, attempt k) so the
+ * oracle can replay the identical draw; otherwise Philox(seed, STREAM_SAMPLE, (i | k<<16, step_lo, step_hi)).
+ * out_tree_idx: tree indices (leaf + capacity - 1), the `indices` the reference returns; out_weights fp32 IS weights
+ * normalised by their max; out_priority (optional) the leaf priorities. */
+int srlx_tree_sample(const double* tree, uint64_t capacity, srlx_state* meta, uint32_t batch, uint64_t step,
+                     double beta_initial, double beta_steps, int has_duplicate, uint64_t seed,
+                     const double* u01_dev, uint32_t max_tries, int64_t* out_tree_idx, float* out_weights,
+                     double* out_priority, uintptr_t cuda_stream);
+/* update(indices, priorities): leaf <- (|p|+eps)^alpha, propagate the change to the root in index order, track
+ * max_priority (proportional_memory.py:171-177). */
+int srlx_tree_update(double* tree, uint64_t capacity, srlx_state* meta, const int64_t* tree_idx_dev,
+                     const float* priorities_dev, uint32_t n, double alpha, double epsilon, uintptr_t cuda_stream);
+/* descend only: out_tree_idx[i] = SumTree._retrieve(tree, 0, vals[i]) (proportional_memory.py:57-66). */
+int srlx_tree_retrieve(const double* tree, uint64_t capacity, const double* vals_dev, uint32_t n,
+                       int64_t* out_tree_idx, uintptr_t cuda_stream);
+
+/* ---- engine (R1-R6, R8-R12) ------------------------------------------------------------------------------ */
+/* Zero the counters, mark every env for reset, clear ring flags and the tree. */
+int srlx_engine_reset(const srlx_engine* eng, uintptr_t cuda_stream);
+/* n_steps x { one vector step of all E envs (policy -> env.step -> ring write -> replay add) followed by
+ * updates_per_step trainer updates }.  training==0: evaluation rollouts (test_epsilon in eng->epsilon, nothing stored). */
+int srlx_engine_run(const srlx_engine* eng, uint32_t n_steps, uint32_t updates_per_step, int training,
+                    uintptr_t cuda_stream);
+/* The two halves separately (parity tests drive them one at a time). */
+int srlx_vec_step(const srlx_engine* eng, int training, uintptr_t cuda_stream);
+int srlx_learn(const srlx_engine* eng, uint32_t n_updates, uintptr_t cuda_stream);
+/* Inference seam: q_out[n][A] = Q(obs[n][D]) with `params` (pred_q) or `target` (pred_target_q); noise_call_id is the
+ * NoisyLinear draw to use (ignored when !noisy; kind = 3). */
+int srlx_qnet_forward(const srlx_engine* eng, int use_target, const float* obs_dev, uint32_t n, uint64_t noise_call_id,
+                      float* q_out_dev, uintptr_t cuda_stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SRLX_H_ */

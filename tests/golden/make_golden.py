@@ -1,0 +1,322 @@
+"""Generate the golden vectors under tests/golden/ by EXECUTING THE REFERENCE (pocokhc/simple_distributed_rl v1.4.5).
+
+Run in the build container only (the reference tree does not exist on the GPU box):
+
+    PYTHONPATH=/root/reference python tests/golden/make_golden.py
+
+Outputs (committed):
+    grid_transitions.npz   Grid.step / _move / reward_done_func of srl/envs/grid.py driven with known np.random uniforms,
+                           plus the EnvRun truncation length (srl/base/env/env_run.py:360-362)
+    sumtree.npz            srl/rl/memories/priority_memories/proportional_memory.py ProportionalMemory driven with injected
+                           uniforms: tree arrays, sampled indices, IS weights, max_priority after add/sample/update sequences
+    trainer_<case>.npz     srl/algorithms/{dqn,rainbow}/model_torch.py Trainer.train() on frozen batches with injected
+                           NoisyLinear noise: target_q, q, loss, priorities, parameters before/after two updates
+    functions.npz          srl/rl/functions.py rescaling / inverse_rescaling / create_epsilon_list
+"""
+import os
+import random
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "..", ".."))
+
+import srl  # noqa: E402  (the reference)
+from srl.algorithms import dqn, rainbow  # noqa: E402
+from srl.envs import grid as ref_grid  # noqa: E402
+from srl.rl import functions as ref_funcs  # noqa: E402
+from srl.rl.memories.priority_memories import proportional_memory as ref_pm  # noqa: E402
+
+from oracle import nets  # noqa: E402
+
+
+# --------------------------------------------------------------------------------------------------------
+def gen_grid():
+    env = ref_grid.Grid()
+    recs = []
+    cells = [(x, y) for y in range(env.H) for x in range(env.W) if env.field[y][x] != 9]
+    for x, y in cells:
+        for a in range(4):
+            for seed in range(48):
+                np.random.seed(seed * 7919 + a)
+                u = np.random.random_sample()
+                np.random.seed(seed * 7919 + a)
+                env.player_pos = (x, y)
+                st, r, done, trunc = env.step(a)
+                assert trunc is False
+                recs.append((x, y, a, u, st[0], st[1], r, int(done), env.action.value))
+    recs = np.array(recs, dtype=np.float64)
+    # start position
+    st = env.reset()
+    # EnvRun truncation: bump into the left wall from the start cell forever (move_prob=1 so no slip)
+    e2 = srl.make_env(srl.EnvConfig("Grid", kwargs=dict(move_prob=1.0)))
+    e2.setup()
+    e2.reset()
+    n = 0
+    while not e2.done:
+        e2.step(0)
+        n += 1
+    np.savez(os.path.join(HERE, "grid_transitions.npz"), recs=recs, start=np.array(st), trunc_steps=n,
+             trunc_done_type=str(e2.done_type.name) if hasattr(e2, "done_type") else "")
+    print("grid:", recs.shape, "start", st, "episode length when never terminating:", n)
+
+
+# --------------------------------------------------------------------------------------------------------
+class _Uniforms:
+    def __init__(self, seed):
+        self.rng = np.random.default_rng(seed)
+        self.log = []
+
+    def __call__(self):
+        u = float(self.rng.random())
+        self.log.append(u)
+        return u
+
+
+def gen_sumtree():
+    out = {}
+    for case, (cap, alpha, beta0, bsteps, dup) in enumerate(
+        [(10, 0.8, 1.0, 10, True), (10, 0.6, 0.4, 1000, False), (37, 0.6, 0.4, 1_000_000, True), (64, 0.5, 0.4, 100, True)]
+    ):
+        mem = ref_pm.ProportionalMemory(cap, alpha, beta0, bsteps, has_duplicate=dup)
+        uni = _Uniforms(100 + case)
+        ref_pm.random.random = uni
+        rng = np.random.default_rng(case)
+        n_add = cap + cap // 2
+        add_pri = rng.random(n_add) * 3.0
+        use_none = rng.random(n_add) < 0.3
+        for i in range(n_add):
+            mem.add(i, None if use_none[i] else float(add_pri[i]))
+        out[f"c{case}_cfg"] = np.array([cap, alpha, beta0, bsteps, int(dup)], dtype=np.float64)
+        out[f"c{case}_add_pri"] = add_pri
+        out[f"c{case}_add_none"] = use_none
+        out[f"c{case}_tree_after_add"] = np.array(mem.tree.tree, dtype=np.float64)
+        out[f"c{case}_maxp_after_add"] = mem.max_priority
+        B = 5
+        n_iter = 6
+        idxs, ws, ups, trees, maxps, ulogs, steps = [], [], [], [], [], [], []
+        for it in range(n_iter):
+            step = it * 3
+            uni.log = []
+            batches, weights, indices = mem.sample(B, step)
+            ulogs.append(list(uni.log) + [np.nan] * (64 - len(uni.log)))
+            idxs.append(indices)
+            ws.append(weights)
+            up = rng.standard_normal(B) * 2.0
+            mem.update(indices, up)
+            ups.append(up)
+            trees.append(np.array(mem.tree.tree, dtype=np.float64))
+            maxps.append(mem.max_priority)
+            steps.append(step)
+        out[f"c{case}_idx"] = np.array(idxs, dtype=np.int64)
+        out[f"c{case}_weights"] = np.array(ws, dtype=np.float64)
+        out[f"c{case}_upd"] = np.array(ups, dtype=np.float64)
+        out[f"c{case}_trees"] = np.array(trees)
+        out[f"c{case}_maxp"] = np.array(maxps)
+        out[f"c{case}_uniforms"] = np.array(ulogs, dtype=np.float64)
+        out[f"c{case}_steps"] = np.array(steps)
+        out[f"c{case}_size"] = mem.size
+        out[f"c{case}_write"] = mem.tree.write
+    ref_pm.random.random = random.random
+    out["n_cases"] = 4
+    np.savez(os.path.join(HERE, "sumtree.npz"), **out)
+    print("sumtree: cases", out["n_cases"])
+
+
+# --------------------------------------------------------------------------------------------------------
+def gen_functions():
+    x = np.concatenate([np.linspace(-50, 50, 41), [-1e-3, 0.0, 1e-3, 123.456]]).astype(np.float32)
+    np.savez(
+        os.path.join(HERE, "functions.npz"),
+        x=x,
+        rescaling=ref_funcs.rescaling(x),
+        inverse_rescaling=ref_funcs.inverse_rescaling(x),
+        eps_list_8=np.array(ref_funcs.create_epsilon_list(8, 0.4, 7.0)),
+        eps_list_1=np.array(ref_funcs.create_epsilon_list(1, 0.4, 7.0)),
+    )
+    print("functions ok")
+
+
+# --------------------------------------------------------------------------------------------------------
+class _StubMemory:
+    """Stands in for RLPriorityReplayBuffer: returns the frozen batch, records the priorities written back."""
+
+    def __init__(self, batches_list, weights_list):
+        self.batches_list = batches_list
+        self.weights_list = weights_list
+        self.i = 0
+        self.updates = []
+
+    def sample(self):
+        b, w = self.batches_list[self.i], self.weights_list[self.i]
+        self.i += 1
+        return b, w, list(range(len(b)))
+
+    def update(self, update_args, priorities, step):
+        self.updates.append((np.array(priorities).copy(), step))
+
+    def length(self):
+        return 10**6
+
+
+def _noise_schedule(spec, model):
+    """flat-layout slices in the order NoisyLinear.forward draws them (w then b per module, modules in forward order)."""
+    from srl.rl.torch_.modules.noisy_linear import NoisyLinear
+
+    key2off = {}
+    for off, shape, kmu, ksig in spec._keys("rainbow"):
+        key2off[kmu] = (off, int(np.prod(shape)), shape)
+    sched = []
+    for name, mod in model.named_modules():
+        if isinstance(mod, NoisyLinear):
+            sched.append(key2off[name + ".w_mu"])
+            sched.append(key2off[name + ".b_mu"])
+    return sched
+
+
+def gen_trainer(case, algo, hidden, dueling, noisy, multisteps, double, rescale, B=8, n_updates=2, retrace_h=1.0,
+                seed=0):
+    torch.manual_seed(seed)
+    rng = np.random.default_rng(seed)
+    if algo == "dqn":
+        cfg = dqn.Config(batch_size=B, enable_double_dqn=double, enable_rescale=rescale, target_model_update_interval=1000)
+        cfg.hidden_block.set(hidden)
+    else:
+        cfg = rainbow.Config(batch_size=B, enable_double_dqn=double, enable_rescale=rescale, multisteps=multisteps,
+                             enable_noisy_dense=noisy, retrace_h=retrace_h, target_model_update_interval=1000)
+        if dueling is None:
+            cfg.hidden_block.set(hidden)
+        else:
+            cfg.hidden_block.set_dueling_network(hidden, dueling_type=dueling)
+    cfg.memory.compress = False
+    cfg.memory.warmup_size = B
+    runner = srl.Runner("Grid", cfg)
+    runner.set_device("CPU")
+    parameter = runner.make_parameter()
+    D, A = 2, 4
+    spec = nets.NetSpec(D, tuple(hidden), A, dueling, noisy)
+    # de-synchronise target from online so the two nets differ
+    with torch.no_grad():
+        for p in parameter.q_target.parameters():
+            p.add_(torch.randn_like(p) * 0.05)
+    mu0, sig0 = spec.from_state_dict(parameter.q_online.state_dict(), algo)
+    tmu0, tsig0 = spec.from_state_dict(parameter.q_target.state_dict(), algo)
+    assert spec.n_params == sum(p.numel() for n, p in parameter.q_online.named_parameters() if "sigma" not in n), (
+        spec.n_params, [(n, p.shape) for n, p in parameter.q_online.named_parameters()])
+
+    M = multisteps
+    states = rng.uniform(0, 5, size=(n_updates, B, M + 1, D)).astype(np.float32)
+    actions = rng.integers(0, A, size=(n_updates, B, M))
+    rewards = rng.normal(0, 1, size=(n_updates, B, M)).astype(np.float32)
+    terms = (rng.random((n_updates, B, M)) < 0.25).astype(np.int64)
+    weights = rng.uniform(0.3, 1.0, size=(n_updates, B)).astype(np.float32)
+    # make a few windows greedy-consistent is not needed: random actions already hit both retrace branches for A=4
+    batches_list = []
+    for u in range(n_updates):
+        bl = []
+        for i in range(B):
+            if algo == "rainbow" and M > 1:
+                steps = [[states[u, i, 0], None, None, None, None]]
+                for k in range(M):
+                    steps.append([states[u, i, k + 1], np.eye(A, dtype=np.float32)[actions[u, i, k]].tolist(),
+                                  float(rewards[u, i, k]), int(terms[u, i, k]), []])
+                bl.append(steps)
+            else:
+                bl.append([states[u, i, 0], states[u, i, 1], np.eye(A, dtype=np.float32)[actions[u, i, 0]].tolist(),
+                           float(rewards[u, i, 0]), int(1 - terms[u, i, 0]), []])
+        batches_list.append(bl)
+    memory = _StubMemory(batches_list, [w for w in weights])
+    trainer = cfg.make_trainer(parameter, memory)
+    trainer.on_setup()
+
+    # noise injection: pass order inside Trainer.train is online(s') [1], target(s') [2], online(s) [0]
+    noise = rng.standard_normal((n_updates, 3, spec.n_params)).astype(np.float32)
+    real_randn = torch.randn
+    if noisy:
+        import srl.rl.torch_.modules.noisy_linear as nl
+
+        sched = _noise_schedule(spec, parameter.q_online)
+        state = {"u": 0, "call": 0}
+        if algo == "rainbow" and M > 1 and not double:
+            order = [1, 2, 0]
+        else:
+            order = [2, 1, 0] if (algo == "rainbow" and M == 1) or algo == "dqn" else [1, 2, 0]
+        # rainbow n-step: pred_q(online) first then pred_target_q (rainbow.py:219-220);
+        # 1-step variants: pred_target_q first then pred_q (rainbow_nomultisteps.py:22-26, dqn.py:155-159)
+
+        def fake_randn(size, **kw):
+            per_pass = len(sched)
+            c = state["call"]
+            p = order[c // per_pass]
+            off, n, shape = sched[c % per_pass]
+            assert tuple(size) == tuple(shape), (size, shape)
+            state["call"] += 1
+            return torch.tensor(noise[state["u"], p, off : off + n].reshape(shape))
+
+        nl.torch.randn = fake_randn
+
+    # capture target_q
+    captured = []
+    if algo == "rainbow" and M == 1:
+        import srl.algorithms.rainbow.model_torch as mt
+
+        orig = mt.calc_target_q
+
+        def wrap(*a, **k):
+            r = orig(*a, **k)
+            captured.append(np.array(r[0]).copy())
+            return r
+
+        mt.calc_target_q = wrap
+    else:
+        orig = parameter.calc_target_q
+
+        def wrap(*a, **k):
+            r = orig(*a, **k)
+            captured.append(np.array(r[0] if isinstance(r, tuple) else r).copy())
+            return r
+
+        parameter.calc_target_q = wrap
+
+    losses, mus, sigs, tmus = [], [], [], []
+    for u in range(n_updates):
+        if noisy:
+            state["u"], state["call"] = u, 0
+        trainer.train()
+        losses.append(trainer.info["loss"])
+        m_, s_ = spec.from_state_dict(parameter.q_online.state_dict(), algo)
+        mus.append(m_)
+        sigs.append(s_ if s_ is not None else np.zeros(0, np.float32))
+        tmus.append(spec.from_state_dict(parameter.q_target.state_dict(), algo)[0])
+    if noisy:
+        nl.torch.randn = real_randn
+    if algo == "rainbow" and M == 1:
+        mt.calc_target_q = orig
+
+    np.savez(
+        os.path.join(HERE, f"trainer_{case}.npz"),
+        algo=algo, hidden=np.array(hidden), dueling="none" if dueling is None else dueling, noisy=int(noisy),
+        multisteps=M, double=int(double), rescale=int(rescale), retrace_h=retrace_h, discount=cfg.discount, lr=cfg.lr,
+        mu0=mu0, sigma0=sig0 if sig0 is not None else np.zeros(0, np.float32),
+        tmu0=tmu0, tsigma0=tsig0 if tsig0 is not None else np.zeros(0, np.float32),
+        states=states, actions=actions, rewards=rewards, terms=terms, weights=weights, noise=noise if noisy else np.zeros(0),
+        target_q=np.array(captured), losses=np.array(losses), priorities=np.array([p for p, s in memory.updates]),
+        update_steps=np.array([s for p, s in memory.updates]), mu_after=np.array(mus), sigma_after=np.array(sigs),
+        tmu_after=np.array(tmus), train_count=trainer.train_count, sync_count=trainer.sync_count,
+    )
+    print(f"trainer_{case}: n_params={spec.n_params} losses={losses}")
+
+
+if __name__ == "__main__":
+    gen_grid()
+    gen_sumtree()
+    gen_functions()
+    gen_trainer("dqn_mlp64x64_double", "dqn", (64, 64), None, False, 1, True, False)
+    gen_trainer("dqn_mlp32_plain_rescale", "dqn", (32,), None, False, 1, False, True)
+    gen_trainer("rainbow_default_noisy_m3", "rainbow", (512,), "average", True, 3, True, False)
+    gen_trainer("rainbow_duel64x64_m3", "rainbow", (64, 64), "average", False, 3, True, False)
+    gen_trainer("rainbow_duelmax_m2_nodouble", "rainbow", (32,), "max", False, 2, False, False, retrace_h=0.9)
+    gen_trainer("rainbow_naive_noisy_m1", "rainbow", (32,), "", True, 1, True, False)
+    gen_trainer("rainbow_mlp_noisy_m3_rescale", "rainbow", (32, 16), None, True, 3, True, True)

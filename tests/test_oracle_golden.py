@@ -1,0 +1,187 @@
+"""The oracle restatements vs. the golden vectors produced by executing the reference (tests/golden/make_golden.py)
+and vs. the reference's own known-answer tests (tests/quick/rl/memories/test_priority_memories.py)."""
+import collections
+import glob
+import math
+import os
+
+import numpy as np
+import pytest
+
+from oracle import envs, nets, philox, sumtree, targets
+
+
+def test_philox_kat():
+    # Random123 known-answer vectors for philox4x32-10
+    f = lambda *a: [int(x) for x in philox.philox4x32(*a)]
+    assert f(0, 0, 0, 0, 0, 0) == [0x6627E8D5, 0xE169C58D, 0xBC57AC4C, 0x9B00DBD8]
+    assert f(*([0xFFFFFFFF] * 6)) == [0x408F276D, 0x41C83B0E, 0xA20BC7C6, 0x6D5451FD]
+    assert f(0x243F6A88, 0x85A308D3, 0x13198A2E, 0x03707344, 0xA4093822, 0x299F31D0) == [0xD16CFE09, 0x94FDCCEB, 0x5001E420, 0x24126EA1]
+
+
+def test_uniform_conversions():
+    assert philox.u01_f32(0xFFFFFFFF) < 1.0 and philox.u01_f32(0) == 0.0
+    assert philox.u01_f64(0xFFFFFFFF, 0xFFFFFFFF) < 1.0 and philox.u01_f64(0, 0) == 0.0
+
+
+# ---- Grid ----------------------------------------------------------------------------------------------
+def test_grid_transitions_match_reference(golden_dir):
+    g = np.load(os.path.join(golden_dir, "grid_transitions.npz"))
+    spec = envs.GridSpec()
+    assert list(g["start"]) == [1, 3] and spec.starts == [(1, 3)]
+    assert int(g["trunc_steps"]) == spec.trunc_limit == 51
+    seen_slip = set()
+    for x, y, a, u, nx, ny, r, done, executed in g["recs"]:
+        ea = spec.slip(int(a), float(u))
+        assert ea == int(executed)
+        seen_slip.add((int(a), ea))
+        mx, my = spec.move(int(x), int(y), ea)
+        assert (mx, my) == (int(nx), int(ny))
+        rr, dd = spec.reward_done(mx, my)
+        assert rr == r and int(dd) == int(done)
+    assert len(seen_slip) == 12  # every (chosen, executed) pair with non-zero probability was exercised
+
+
+# ---- CartPole (unpinned vs gymnasium; the polynomial must track libm) --------------------------------------
+def test_cartpole_poly_sincos_close_to_libm():
+    x = np.linspace(-0.6, 0.6, 4001)
+    s = np.array([envs.poly_sin(v) for v in x])
+    c = np.array([envs.poly_cos(v) for v in x])
+    assert np.max(np.abs(s - np.sin(x))) < 4e-16
+    assert np.max(np.abs(c - np.cos(x))) < 4e-16
+
+
+def test_cartpole_physics_matches_textbook_euler():
+    """Independent restatement of the published gymnasium CartPole equations with libm sin/cos."""
+    spec = envs.CartPoleSpec()
+    rng = np.random.default_rng(0)
+    for _ in range(200):
+        st = rng.uniform(-0.2, 0.2, 4)
+        a = int(rng.integers(0, 2))
+        x, xd, th, thd = st
+        force = 10.0 if a == 1 else -10.0
+        ct, sn = math.cos(th), math.sin(th)
+        temp = (force + 0.05 * thd * thd * sn) / 1.1
+        thacc = (9.8 * sn - ct * temp) / (0.5 * (4.0 / 3.0 - 0.1 * ct * ct / 1.1))
+        xacc = temp - 0.05 * thacc * ct / 1.1
+        want = np.array([x + 0.02 * xd, xd + 0.02 * xacc, th + 0.02 * thd, thd + 0.02 * thacc])
+        got, r, term = spec.step(st, a)
+        np.testing.assert_allclose(got, want, rtol=0, atol=1e-14)
+        assert r == 1.0
+        assert term == bool(abs(want[0]) > 2.4 or abs(want[2]) > 12 * 2 * math.pi / 360)
+
+
+# ---- SumTree / ProportionalMemory -------------------------------------------------------------------------
+def test_sumtree_matches_reference_golden(golden_dir):
+    g = np.load(os.path.join(golden_dir, "sumtree.npz"))
+    for case in range(int(g["n_cases"])):
+        cap, alpha, beta0, bsteps, dup = g[f"c{case}_cfg"]
+        mem = sumtree.ProportionalMemory(int(cap), alpha, beta0, bsteps, has_duplicate=bool(dup))
+        for p, none in zip(g[f"c{case}_add_pri"], g[f"c{case}_add_none"]):
+            mem.add(None if none else float(p))
+        np.testing.assert_array_equal(mem.tree.tree, g[f"c{case}_tree_after_add"])
+        assert mem.max_priority == float(g[f"c{case}_maxp_after_add"])
+        for it, step in enumerate(g[f"c{case}_steps"]):
+            us = g[f"c{case}_uniforms"][it]
+            cursor = {"n": 0}
+
+            def uniforms(i, k):
+                u = us[cursor["n"]]
+                cursor["n"] += 1
+                return float(u)
+
+            idx, w, pri, _ = mem.sample(5, int(step), uniforms)
+            np.testing.assert_array_equal(idx, g[f"c{case}_idx"][it])
+            np.testing.assert_allclose(w, g[f"c{case}_weights"][it], rtol=1e-15)
+            mem.update(idx, g[f"c{case}_upd"][it])
+            np.testing.assert_array_equal(mem.tree.tree, g[f"c{case}_trees"][it])
+            assert mem.max_priority == float(g[f"c{case}_maxp"][it])
+        assert mem.size == int(g[f"c{case}_size"]) and mem.tree.write == int(g[f"c{case}_write"])
+
+
+@pytest.mark.parametrize("alpha", [0, 0.2, 0.5, 0.8, 1.0])
+def test_IS_Proportional_kat(alpha):
+    """tests/quick/rl/memories/test_priority_memories.py:97-117,150-176 restated for the oracle."""
+    epsilon = 0.0001
+    mem = sumtree.ProportionalMemory(10, alpha=alpha, beta_initial=1, epsilon=epsilon, has_duplicate=False)
+    priorities = [1, 2, 4, 3]
+    true_p = [(t + epsilon) ** alpha for t in priorities]
+    N = 4
+    probs = [p / sum(true_p) for p in true_p]
+    tw = np.array([(N * p) ** -1 for p in probs])
+    tw /= tw.max()
+    for p in priorities:
+        mem.add(p)
+    idx, w, _, _ = mem.sample(N, 1, sumtree.philox_uniforms(3, 0))
+    for i, ti in enumerate(idx):
+        assert math.isclose(w[i], tw[ti - 9], rel_tol=1e-7)
+    assert len(set(idx.tolist())) == N
+
+
+def test_priority_memory_monotone_counts():
+    """tests/quick/rl/memories/test_priority_memories.py:17-91 (2 000 iterations instead of 20 000 for CPU time)."""
+    cap = 10
+    mem = sumtree.ProportionalMemory(cap, 0.8, 1, 10, has_duplicate=False)
+    for i in range(100):
+        mem.add(0)
+    assert mem.length() == cap
+    for i in range(1, 11):
+        mem.add(i)
+    counter = collections.Counter()
+    for it in range(2000):
+        idx, w, pri, _ = mem.sample(5, 1, sumtree.philox_uniforms(11, it))
+        assert len(set(idx.tolist())) == 5
+        for j in idx:
+            counter[int(j) - (cap - 1)] += 1
+        mem.update(idx, np.array([((int(j) - (cap - 1)) - mem.tree.write) % cap + 1 for j in idx], dtype=np.float64))
+    slot_pri = {(mem.tree.write + k) % cap: k + 1 for k in range(cap)}
+    vals = [counter[s] for s, _ in sorted(slot_pri.items(), key=lambda kv: kv[1])]
+    assert all(vals[i] < vals[i + 1] for i in range(cap - 1)), vals
+
+
+def test_uniform_sample_distinct():
+    idx = sumtree.uniform_sample_distinct(40, 32, 5, 9)
+    assert len(set(idx.tolist())) == 32 and idx.min() >= 0 and idx.max() < 40
+
+
+# ---- functions ---------------------------------------------------------------------------------------------
+def test_rescaling_golden(golden_dir):
+    g = np.load(os.path.join(golden_dir, "functions.npz"))
+    np.testing.assert_array_equal(targets.rescaling(g["x"]), g["rescaling"])
+    np.testing.assert_array_equal(targets.inverse_rescaling(g["x"]), g["inverse_rescaling"])
+    x = g["x"].astype(np.float64)
+    np.testing.assert_allclose(targets.inverse_rescaling(targets.rescaling(x)), x, rtol=1e-3, atol=1e-6)
+
+
+# ---- trainer update ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "trainer_*.npz"))))
+def test_trainer_update_matches_reference(path):
+    g = np.load(path)
+    algo = str(g["algo"])
+    dueling = None if str(g["dueling"]) == "none" else str(g["dueling"])
+    noisy = bool(g["noisy"])
+    spec = nets.NetSpec(2, tuple(int(h) for h in g["hidden"]), 4, dueling, noisy)
+    assert spec.n_params == len(g["mu0"])
+    sigma0 = g["sigma0"] if noisy else None
+    st = nets.AdamState(spec, g["mu0"], sigma0, lr=float(g["lr"]))
+    tmu = g["tmu0"].copy()
+    tsig = g["tsigma0"].copy() if noisy else None
+    mask = spec.sigma_mask(algo) if noisy else None
+    for u in range(len(g["losses"])):
+        noise = tuple(g["noise"][u]) if noisy else (None, None, None)
+        res = nets.train_update(
+            spec, st, tmu, tsig, algo=algo, states=g["states"][u], actions=g["actions"][u], rewards=g["rewards"][u],
+            dones=g["terms"][u], weights=g["weights"][u], discount=float(g["discount"]), multisteps=int(g["multisteps"]),
+            retrace_h=float(g["retrace_h"]), enable_double_dqn=bool(g["double"]), enable_rescale=bool(g["rescale"]),
+            noise=noise, sigma_mask=mask)
+        np.testing.assert_allclose(res["target_q"], g["target_q"][u], rtol=1e-6, atol=1e-6)
+        assert abs(res["loss"] - g["losses"][u]) <= 1e-6 * max(1, abs(g["losses"][u]))
+        np.testing.assert_allclose(res["priorities"], g["priorities"][u], rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose(st.mu.detach().numpy(), g["mu_after"][u], rtol=1e-5, atol=1e-7)
+        if noisy:
+            np.testing.assert_allclose(st.sigma.detach().numpy(), g["sigma_after"][u], rtol=1e-5, atol=1e-7)
+        if u % 1000 == 0:  # first update syncs the target (train_count % interval == 0 before the increment)
+            tmu = st.mu.detach().numpy().copy()
+            tsig = st.sigma.detach().numpy().copy() if noisy else None
+        np.testing.assert_allclose(tmu, g["tmu_after"][u], rtol=1e-5, atol=1e-7)
+    assert list(g["update_steps"]) == list(range(len(g["losses"])))
