@@ -147,6 +147,7 @@ typedef struct srlx_engine {
   uint8_t* ring_term;       /* [R*E] worker.terminated (NOT truncated) */
   uint8_t* ring_done;       /* [R*E] episode ended at this step (terminated or truncated) */
   double* tree;             /* [2*R*E-1] SumTree nodes, leaf j at j + R*E - 1 (proportional_memory.py:13-47); NULL for uniform */
+  double* tree_scratch;     /* [2*(E+2)] scratch for the per-step bulk add; NULL for uniform */
   float* params;            /* [n_params] online mu */
   float* params_sigma;      /* [n_params] online sigma (noisy) or NULL */
   float* target;            /* [n_params] target mu */

@@ -154,7 +154,7 @@ class OracleEngine:
             a, b, change = pa, pb, pc
 
     # ---- one vector step ---------------------------------------------------------------------------------
-    def vec_step(self, training=True):
+    def vec_step(self, training=True, q_override=None):
         cfg, env, E = self.cfg, self.env, self.E
         g = self.vec_steps
         row = g % self.R
@@ -169,6 +169,9 @@ class OracleEngine:
             obs[e] = env.obs(self.env_state[e])
         noise = self.noise_fn(nets.NOISE_KIND_ROLLOUT, g) if cfg.noisy else None
         q = nets.np_forward(self.spec, self.mu, self.sigma, noise, obs)
+        q_own = q
+        if q_override is not None:  # drive the policy with the device's Q so the action indices are comparable bit for bit
+            q = np.asarray(q_override, dtype=np.float32)
         actions = np.zeros(E, dtype=np.int32)
         for e in range(E):
             w = philox.words(cfg.seed, philox.STREAM_POLICY, e, g & 0xFFFFFFFF, g >> 32)
@@ -219,7 +222,7 @@ class OracleEngine:
             self.per.size = self.mem_size
             self.vec_steps += 1
             self.total_step += E
-        return dict(q=q, actions=actions, obs=obs)
+        return dict(q=q_own, actions=actions, obs=obs)
 
     # ---- window rebuild ----------------------------------------------------------------------------------
     def window(self, slot):

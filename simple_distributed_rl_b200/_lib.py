@@ -1,0 +1,142 @@
+"""ctypes binding of libsrlx.so (C ABI: include/srlx.h).  No CPU fallback: a missing library is an error."""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsrlx.so")
+
+SRLX_MAX_LAYERS = 6
+ENV_GRID, ENV_CARTPOLE = 0, 1
+DUEL_NONE, DUEL_AVERAGE, DUEL_MAX, DUEL_NAIVE = 0, 1, 2, 3
+MEM_UNIFORM, MEM_PROPORTIONAL = 0, 1
+NOISE_KIND_ROLLOUT, NOISE_KIND_TRAIN, NOISE_KIND_PRED = 0, 1, 3
+STREAM_ENV_RESET, STREAM_ENV_STEP, STREAM_POLICY, STREAM_NOISE, STREAM_SAMPLE, STREAM_PAD_ACTION, STREAM_UNIFORM_SAMPLE = 1, 2, 3, 4, 5, 6, 7
+
+
+class SrlxNet(C.Structure):
+    _fields_ = [
+        ("n_layers", C.c_int32),
+        ("in_dim", C.c_int32),
+        ("out_dim", C.c_int32 * SRLX_MAX_LAYERS),
+        ("k_dim", C.c_int32 * SRLX_MAX_LAYERS),
+        ("w_off", C.c_int32 * SRLX_MAX_LAYERS),
+        ("b_off", C.c_int32 * SRLX_MAX_LAYERS),
+        ("n_params", C.c_int32),
+        ("n_actions", C.c_int32),
+        ("dueling", C.c_int32),
+        ("noisy", C.c_int32),
+        ("layer_noisy", C.c_int32 * SRLX_MAX_LAYERS),
+    ]
+
+
+class SrlxState(C.Structure):
+    _fields_ = [
+        ("vec_steps", C.c_uint64),
+        ("total_step", C.c_uint64),
+        ("train_count", C.c_uint64),
+        ("episode_count", C.c_uint64),
+        ("sync_count", C.c_uint64),
+        ("adam_step", C.c_uint64),
+        ("mem_size", C.c_uint64),
+        ("sample_retries", C.c_uint64),
+        ("max_priority", C.c_double),
+        ("episode_reward_sum", C.c_double),
+        ("last_loss", C.c_double),
+        ("loss_sum", C.c_double),
+        ("episode_len_sum", C.c_uint64),
+        ("reserved", C.c_uint64 * 3),
+    ]
+
+
+_P = C.c_void_p
+
+
+class SrlxEngine(C.Structure):
+    _fields_ = [
+        ("env_id", C.c_int32), ("n_envs", C.c_int32), ("obs_dim", C.c_int32), ("n_actions", C.c_int32),
+        ("ring_rows", C.c_int32), ("multisteps", C.c_int32), ("batch_size", C.c_int32), ("mem_kind", C.c_int32),
+        ("enable_double_dqn", C.c_int32), ("enable_rescale", C.c_int32), ("enable_reward_clip", C.c_int32),
+        ("has_duplicate", C.c_int32), ("target_update_interval", C.c_int32), ("trunc_limit", C.c_int32),
+        ("trunc_overrides_term", C.c_int32), ("reserved_i", C.c_int32),
+        ("seed", C.c_uint64), ("warmup_size", C.c_uint64),
+        ("epsilon", C.c_double), ("discount", C.c_double), ("lr", C.c_double),
+        ("adam_beta1", C.c_double), ("adam_beta2", C.c_double), ("adam_eps", C.c_double),
+        ("retrace_h", C.c_double),
+        ("per_alpha", C.c_double), ("per_beta_initial", C.c_double), ("per_beta_steps", C.c_double), ("per_epsilon", C.c_double),
+        ("reward_shift", C.c_double), ("reward_scale", C.c_double), ("huber_delta", C.c_double),
+        ("grid_w", C.c_int32), ("grid_h", C.c_int32),
+        ("grid_field", C.c_int8 * 64),
+        ("grid_n_starts", C.c_int32),
+        ("grid_starts", C.c_int32 * 16),
+        ("grid_slip_cdf", C.c_double * 16),
+        ("grid_slip_action", C.c_int32 * 4),
+        ("grid_move_reward", C.c_double), ("grid_goal_reward", C.c_double), ("grid_hole_reward", C.c_double),
+        ("net", SrlxNet),
+        ("state", _P), ("env_state", _P), ("env_step_num", _P), ("env_episode", _P), ("env_ep_reward", _P),
+        ("env_needs_reset", _P),
+        ("ring_obs", _P), ("ring_next_obs", _P), ("ring_action", _P), ("ring_reward", _P), ("ring_term", _P),
+        ("ring_done", _P),
+        ("tree", _P), ("tree_scratch", _P),
+        ("params", _P), ("params_sigma", _P), ("target", _P), ("target_sigma", _P), ("adam_m", _P), ("adam_v", _P),
+        ("dbg_q", _P), ("dbg_action", _P), ("dbg_sample_idx", _P), ("dbg_weights", _P), ("dbg_target_q", _P),
+        ("dbg_q_sa", _P), ("dbg_grads", _P), ("dbg_windows", _P),
+    ]
+
+
+class SrlxError(RuntimeError):
+    pass
+
+
+# every symbol include/srlx.h declares: (name, restype, argtypes)
+_u64, _u32, _i32, _dbl, _sz, _uptr = C.c_uint64, C.c_uint32, C.c_int, C.c_double, C.c_size_t, C.c_size_t
+SYMBOLS = [
+    ("srlx_version", C.c_int, []),
+    ("srlx_last_error", C.c_char_p, []),
+    ("srlx_sizeof_engine", _sz, []),
+    ("srlx_sizeof_state", _sz, []),
+    ("srlx_sizeof_net", _sz, []),
+    ("srlx_launch_count", _u64, []),
+    ("srlx_philox_words", C.c_int, [_u64, _u32, _u32, _u32, _u32, _P, _sz, _uptr]),
+    ("srlx_noise_fill", C.c_int, [_u64, _u32, _u64, _P, _sz, _uptr]),
+    ("srlx_tree_clear", C.c_int, [_P, _u64, _P, _uptr]),
+    ("srlx_tree_add", C.c_int, [_P, _u64, _P, _P, _u64, _dbl, _dbl, _i32, _uptr]),
+    ("srlx_tree_sample", C.c_int, [_P, _u64, _P, _u32, _u64, _dbl, _dbl, _i32, _u64, _P, _u32, _P, _P, _P, _uptr]),
+    ("srlx_tree_update", C.c_int, [_P, _u64, _P, _P, _P, _u32, _dbl, _dbl, _uptr]),
+    ("srlx_tree_retrieve", C.c_int, [_P, _u64, _P, _u32, _P, _uptr]),
+    ("srlx_engine_reset", C.c_int, [C.POINTER(SrlxEngine), _uptr]),
+    ("srlx_engine_run", C.c_int, [C.POINTER(SrlxEngine), _u32, _u32, _i32, _uptr]),
+    ("srlx_vec_step", C.c_int, [C.POINTER(SrlxEngine), _i32, _uptr]),
+    ("srlx_learn", C.c_int, [C.POINTER(SrlxEngine), _u32, _uptr]),
+    ("srlx_qnet_forward", C.c_int, [C.POINTER(SrlxEngine), _i32, _P, _u32, _u64, _P, _uptr]),
+]
+
+_lib = None
+
+
+def load():
+    """Load libsrlx.so (built by `make -C simple_distributed_rl_b200/csrc` / __graft_entry__.build())."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise SrlxError(
+            f"{LIB_PATH} not found: the CUDA extension is required (there is no CPU fallback). "
+            "Build it with `python -c 'import __graft_entry__ as g; g.build()'` or `make -C simple_distributed_rl_b200/csrc`."
+        )
+    lib = C.CDLL(LIB_PATH)
+    for name, res, args in SYMBOLS:
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    if lib.srlx_sizeof_engine() != C.sizeof(SrlxEngine) or lib.srlx_sizeof_state() != C.sizeof(SrlxState) or lib.srlx_sizeof_net() != C.sizeof(SrlxNet):
+        raise SrlxError(
+            f"ABI mismatch: C sizes engine/state/net = {lib.srlx_sizeof_engine()}/{lib.srlx_sizeof_state()}/{lib.srlx_sizeof_net()}, "
+            f"ctypes = {C.sizeof(SrlxEngine)}/{C.sizeof(SrlxState)}/{C.sizeof(SrlxNet)}"
+        )
+    _lib = lib
+    return lib
+
+
+def check(rc):
+    if rc != 0:
+        raise SrlxError(f"libsrlx call failed ({rc}): {load().srlx_last_error().decode()}")

@@ -1,0 +1,187 @@
+// tree.cuh -- device SumTree: binary tree in the reference's own flat layout (2N-1 doubles, leaf j at j+N-1, children
+// 2i+1 / 2i+2; srl/rl/memories/priority_memories/proportional_memory.py:13-47), so backup()/restore() interchange with
+// the reference and the descent makes the identical "<=" decisions on identical node values.  CPU twin: oracle/sumtree.py.
+#pragma once
+#include "philox.cuh"
+
+namespace srlx {
+
+// SumTree._retrieve (proportional_memory.py:57-66): walk down from the root.
+// Five levels are resolved per memory round trip: the 62 descendants of the current node down to depth +5 sit in five
+// contiguous runs of the BFS array (2,4,8,16,32 doubles), the warp fetches them with independent coalesced loads and
+// then replays the five "val <= tree[left]" decisions out of registers with shuffles -- same comparisons on the same
+// stored values as the sequential walk, but ~4 dependent L2 latencies for a 2M-leaf tree instead of 21.
+__device__ inline int64_t tree_retrieve_warp(const double* __restrict__ tree, int64_t n_nodes, double val) {
+  const int lane = threadIdx.x & 31;
+  int64_t idx = 0;
+  while (true) {
+    // level k (1..5) of the subtree rooted at idx occupies [(idx+1)*2^k - 1, (idx+1)*2^k - 1 + 2^k)
+    // lane l loads: k=1: l<2, k=2: l<4, k=3: l<8, k=4: l<16, k=5: all 32
+    double v1 = 0, v2 = 0, v3 = 0, v4 = 0, v5 = 0;
+    const int64_t b1 = (idx + 1) * 2 - 1, b2 = (idx + 1) * 4 - 1, b3 = (idx + 1) * 8 - 1, b4 = (idx + 1) * 16 - 1,
+                  b5 = (idx + 1) * 32 - 1;
+    if (lane < 2 && b1 + lane < n_nodes) v1 = __ldcg(tree + b1 + lane);
+    if (lane < 4 && b2 + lane < n_nodes) v2 = __ldcg(tree + b2 + lane);
+    if (lane < 8 && b3 + lane < n_nodes) v3 = __ldcg(tree + b3 + lane);
+    if (lane < 16 && b4 + lane < n_nodes) v4 = __ldcg(tree + b4 + lane);
+    if (b5 + lane < n_nodes) v5 = __ldcg(tree + b5 + lane);
+    int rel = 0;  // position of the current node inside its level of the subtree
+    bool leaf = false;
+#pragma unroll
+    for (int k = 1; k <= 5; ++k) {
+      const int64_t left = 2 * idx + 1;
+      if (left >= n_nodes) { leaf = true; break; }
+      const double vk = (k == 1) ? v1 : (k == 2) ? v2 : (k == 3) ? v3 : (k == 4) ? v4 : v5;
+      const double tl = __shfl_sync(0xffffffffu, vk, 2 * rel);
+      if (val <= tl) {
+        idx = left;
+        rel = 2 * rel;
+      } else {
+        idx = left + 1;
+        val -= tl;
+        rel = 2 * rel + 1;
+      }
+    }
+    if (leaf) return idx;
+    if (2 * idx + 1 >= n_nodes) return idx;
+  }
+}
+
+// single-thread walk (used by the sequential no-duplicate path and as the reference for the warp version)
+__device__ inline int64_t tree_retrieve_seq(const double* __restrict__ tree, int64_t n_nodes, double val) {
+  int64_t idx = 0;
+  while (true) {
+    const int64_t left = 2 * idx + 1;
+    if (left >= n_nodes) return idx;
+    const double tl = __ldcg(tree + left);
+    if (val <= tl) idx = left;
+    else { idx = left + 1; val -= tl; }
+  }
+}
+
+// true iff `node` is a proper ancestor of tree index x (heap numbering: parent(i) = (i-1)/2)
+__device__ inline bool tree_is_ancestor(int64_t node, int64_t x) {
+  const int dn = 63 - __clzll((long long)(node + 1));
+  const int dx = 63 - __clzll((long long)(x + 1));
+  const int l = dx - dn;
+  return l >= 1 && ((x + 1) >> l) == node + 1;
+}
+
+// ProportionalMemory.update for a batch (proportional_memory.py:171-177), executed by one thread block.
+// The reference applies the items one after the other: leaf <- p_i, every ancestor += (p_i - old leaf).  To stay
+// bit-identical in fp64 each node's additions are applied in item order by ONE thread (the "leader": the first item
+// that touches the node), while all nodes proceed in parallel -> one memory round trip instead of n*depth.
+//   idx[i]   tree index of item i (leaf + capacity - 1)
+//   pri[i]   final priority (already (|td|+eps)^alpha)
+//   change[] scratch (n doubles, shared memory)
+// Requires blockDim-wide participation; ends with __syncthreads().
+__device__ inline void tree_update_batch(double* __restrict__ tree, const int64_t* idx, const double* pri, double* change,
+                                         int n) {
+  const int tid = threadIdx.x, nt = blockDim.x;
+  // 1) per-item change, in item order for duplicate leaves
+  for (int i = tid; i < n; i += nt) {
+    const int64_t li = idx[i];
+    double prev = 0.0;
+    bool found = false;
+    for (int j = i - 1; j >= 0; --j)
+      if (idx[j] == li) { prev = pri[j]; found = true; break; }
+    if (!found) prev = __ldcg(tree + li);
+    change[i] = pri[i] - prev;
+  }
+  __syncthreads();
+  // 2) leaves: the last item touching a leaf wins
+  for (int i = tid; i < n; i += nt) {
+    const int64_t li = idx[i];
+    bool last = true;
+    for (int j = i + 1; j < n; ++j)
+      if (idx[j] == li) { last = false; break; }
+    if (last) __stcg(tree + li, pri[i]);
+  }
+  // 3) ancestors: work item = (item i, level l); leader applies all changes to that node in item order.
+  //    (leaves of a non-power-of-two tree sit at two depths, so "same node" is tested by ancestry, not by level.)
+  const int max_levels = 48;
+  for (int w = tid; w < n * max_levels; w += nt) {
+    const int i = w / max_levels, l = w % max_levels + 1;
+    const int64_t ip1 = idx[i] + 1;
+    if ((ip1 >> l) == 0) continue;  // above the root
+    const int64_t node = (ip1 >> l) - 1;
+    bool leader = true;
+    for (int j = 0; j < i; ++j)
+      if (tree_is_ancestor(node, idx[j])) { leader = false; break; }
+    if (!leader) continue;
+    double v = __ldcg(tree + node);
+    for (int j = i; j < n; ++j)
+      if (tree_is_ancestor(node, idx[j])) v += change[j];
+    __stcg(tree + node, v);
+  }
+  __syncthreads();
+}
+
+// ProportionalMemory.sample draw for a whole batch (proportional_memory.py:142-157), executed by one thread block.
+// Attempt k of sample i uses uniform u(i,k): injected (u01 != NULL, row-major [B][max_tries]) or
+// Philox(seed, STREAM_SAMPLE, (i | k<<16, rng_step_lo, rng_step_hi)).  An attempt is rejected when the leaf priority is 0
+// or, with has_duplicate == 0, when the leaf was already picked by an earlier sample -- evaluated in sample order, so
+// the result equals the reference's sequential loop.  One warp walks one sample (tree_retrieve_warp).
+// Outputs (shared memory): s_idx tree indices, s_pri leaf priorities, s_att scratch; *retries accumulates rejections.
+__device__ inline void per_sample_block(const double* __restrict__ tree, int64_t n_nodes, double total, int B,
+                                        uint64_t seed, uint64_t rng_step, const double* __restrict__ u01, int max_tries,
+                                        int has_duplicate, int64_t* s_idx, double* s_pri, double* s_att,
+                                        unsigned long long* retries) {
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nwarps = blockDim.x >> 5;
+  auto draw = [&](int i, int k) -> double {
+    if (u01) return u01[(size_t)i * max_tries + k];
+    const uint4 w = philox(seed, STREAM_SAMPLE, (uint32_t)i | ((uint32_t)k << 16), (uint32_t)rng_step, (uint32_t)(rng_step >> 32));
+    return u01_f64(w.x, w.y);
+  };
+  for (int i = warp; i < B; i += nwarps) {
+    int64_t idx = 0;
+    double p = 0.0;
+    int k = 0;
+    for (; k < max_tries; ++k) {
+      const double r = draw(i, k) * total;
+      idx = tree_retrieve_warp(tree, n_nodes, r);
+      p = __ldcg(tree + idx);
+      if (p != 0.0) break;
+    }
+    if (lane == 0) {
+      s_idx[i] = idx;
+      s_pri[i] = p;
+      s_att[i] = (double)k;
+      if (k) atomicAdd(retries, (unsigned long long)k);
+    }
+  }
+  __syncthreads();
+  if (!has_duplicate && tid == 0) {
+    for (int i = 1; i < B; ++i) {
+      int k = (int)s_att[i];
+      while (k < max_tries) {
+        bool dup = false;
+        for (int j = 0; j < i; ++j) dup |= (s_idx[j] == s_idx[i]);
+        if (!dup && s_pri[i] != 0.0) break;
+        ++k;
+        *retries += 1;
+        if (k >= max_tries) break;
+        s_idx[i] = tree_retrieve_seq(tree, n_nodes, draw(i, k) * total);
+        s_pri[i] = __ldcg(tree + s_idx[i]);
+      }
+    }
+  }
+  __syncthreads();
+}
+
+// IS weights (proportional_memory.py:159-167): w_i = (size * p_i / total)^-beta, divided by the batch max, as float32.
+__device__ inline void per_weights_block(double total, double size, double beta, int B, const double* s_pri, double* s_tmp,
+                                         float* s_w) {
+  const int tid = threadIdx.x, lane = tid & 31;
+  for (int i = tid; i < B; i += blockDim.x) s_tmp[i] = pow(size * (s_pri[i] / total), -beta);
+  __syncthreads();
+  if (tid < 32) {
+    double mx = 0.0;
+    for (int i = lane; i < B; i += 32) mx = fmax(mx, s_tmp[i]);
+    for (int s = 16; s > 0; s >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, s));
+    for (int i = lane; i < B; i += 32) s_w[i] = (float)(s_tmp[i] / mx);
+  }
+  __syncthreads();
+}
+
+}  // namespace srlx

@@ -1,0 +1,214 @@
+"""DeviceEngine: owns the HBM-resident buffers (torch CUDA tensors) and drives the libsrlx.so kernels.
+
+Data layout in HBM (one engine per GPU; E = n_envs, R = ring_rows, D = obs_dim, P = n_params):
+  env_state      f64 [E,4]     environment state (CartPole x,x_dot,theta,theta_dot; Grid x,y)
+  env_*          i32/u32/f64/u8 [E]  EnvRun counters (step_num, episodes started, episode reward, needs_reset)
+  ring_obs       f32 [R*E, D]  state            slot(g, e) = (g % R) * E + e  (time-major: one vector step = one row,
+  ring_next_obs  f32 [R*E, D]  next_state       so the E writes of a step are one contiguous, coalesced run)
+  ring_action    i32 [R*E]     action index
+  ring_reward    f32 [R*E]     reward after shift/scale/clip
+  ring_term/done u8  [R*E]     worker.terminated / episode ended
+  tree           f64 [2*R*E-1] SumTree in the reference's own flat layout (proportional only)
+  params/target  f32 [P] (+ sigma [P] when noisy), adam_m/adam_v f32 [P*(1+noisy)]
+  state          srlx_state    device-resident counters (RunState / trainer / memory scalars)
+PyTorch is used for allocation, streams and host<->device copies only; every computation is a libsrlx kernel.
+"""
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+from .envspec import make_env_spec
+from .netspec import NetSpec
+
+
+@dataclass
+class EngineConfig:
+    env: str = "CartPole-v1"
+    n_envs: int = 8192
+    ring_rows: int = 256
+    multisteps: int = 1
+    batch_size: int = 32
+    mem_kind: int = _lib.MEM_PROPORTIONAL
+    algo: str = "dqn"
+    enable_double_dqn: bool = True
+    enable_rescale: bool = False
+    enable_reward_clip: bool = False
+    has_duplicate: bool = True
+    target_update_interval: int = 1000
+    seed: int = 0
+    warmup_size: int = 1000
+    epsilon: float = 0.1
+    discount: float = 0.99
+    lr: float = 1e-3
+    adam_beta1: float = 0.9
+    adam_beta2: float = 0.999
+    adam_eps: float = 1e-8
+    retrace_h: float = 1.0
+    per_alpha: float = 0.6
+    per_beta_initial: float = 0.4
+    per_beta_steps: float = 1_000_000
+    per_epsilon: float = 1e-4
+    reward_shift: float = 0.0
+    reward_scale: float = 1.0
+    huber_delta: float = 1.0
+    hidden: tuple = (64, 64)
+    dueling: Optional[str] = None
+    noisy: bool = False
+    env_kwargs: dict = field(default_factory=dict)
+
+
+class DeviceEngine:
+    def __init__(self, cfg: EngineConfig, device="cuda:0", debug: bool = False, params=None, stream=None):
+        self.lib = _lib.load()
+        if not torch.cuda.is_available():
+            raise _lib.SrlxError("DeviceEngine needs a CUDA device (no CPU fallback)")
+        self.cfg = cfg
+        self.device = torch.device(device)
+        self.env = make_env_spec(cfg.env, **cfg.env_kwargs)
+        self.spec = NetSpec(self.env.obs_dim, tuple(cfg.hidden), self.env.n_actions, cfg.dueling, cfg.noisy, cfg.algo)
+        self.E, self.R, self.D, self.A, self.M, self.B = cfg.n_envs, cfg.ring_rows, self.env.obs_dim, self.env.n_actions, cfg.multisteps, cfg.batch_size
+        self.cap = self.E * self.R
+        self.per = cfg.mem_kind == _lib.MEM_PROPORTIONAL
+        self.debug = debug
+        self.stream = stream
+        dev = self.device
+        z = lambda shape, dt: torch.zeros(shape, dtype=dt, device=dev)
+        P, noisy = self.spec.n_params, cfg.noisy
+        self.t = dict(
+            state=z(C.sizeof(_lib.SrlxState), torch.uint8),
+            env_state=z((self.E, 4), torch.float64),
+            env_step_num=z(self.E, torch.int32),
+            env_episode=z(self.E, torch.int32),
+            env_ep_reward=z(self.E, torch.float64),
+            env_needs_reset=z(self.E, torch.uint8),
+            ring_obs=z((self.cap, self.D), torch.float32),
+            ring_next_obs=z((self.cap, self.D), torch.float32),
+            ring_action=z(self.cap, torch.int32),
+            ring_reward=z(self.cap, torch.float32),
+            ring_term=z(self.cap, torch.uint8),
+            ring_done=z(self.cap, torch.uint8),
+            params=z(P, torch.float32),
+            target=z(P, torch.float32),
+            adam_m=z(P * (2 if noisy else 1), torch.float32),
+            adam_v=z(P * (2 if noisy else 1), torch.float32),
+        )
+        if self.per:
+            self.t["tree"] = z(2 * self.cap - 1, torch.float64)
+            self.t["tree_scratch"] = z(2 * (self.E + 2), torch.float64)
+        if noisy:
+            self.t["params_sigma"] = z(P, torch.float32)
+            self.t["target_sigma"] = z(P, torch.float32)
+        if debug:
+            B, M, D, A = self.B, self.M, self.D, self.A
+            self.t.update(
+                dbg_q=z((self.E, A), torch.float32), dbg_action=z(self.E, torch.int32), dbg_sample_idx=z(B, torch.int64),
+                dbg_weights=z(B, torch.float32), dbg_target_q=z(B, torch.float32), dbg_q_sa=z(B, torch.float32),
+                dbg_grads=z(P * (2 if noisy else 1), torch.float32), dbg_windows=z(B * (M + 1) * D + 3 * B * M, torch.float32),
+            )
+        self.c = self._build_struct()
+        # pinned host mirror of the device counters (one small D2H per read)
+        self._state_host = torch.zeros(C.sizeof(_lib.SrlxState), dtype=torch.uint8).pin_memory()
+        self.reset()
+        if params is None:
+            mu, sigma = self.spec.init_params(cfg.seed)
+        else:
+            mu, sigma = params
+        self.set_params(mu, sigma, also_target=True)
+
+    # ---- struct ---------------------------------------------------------------------------------------------
+    def _build_struct(self):
+        cfg, c = self.cfg, _lib.SrlxEngine()
+        self.env.fill(c)
+        c.n_envs, c.ring_rows, c.multisteps, c.batch_size, c.mem_kind = self.E, self.R, self.M, self.B, cfg.mem_kind
+        c.enable_double_dqn, c.enable_rescale, c.enable_reward_clip = int(cfg.enable_double_dqn), int(cfg.enable_rescale), int(cfg.enable_reward_clip)
+        c.has_duplicate, c.target_update_interval = int(cfg.has_duplicate), int(cfg.target_update_interval)
+        c.seed, c.warmup_size = int(cfg.seed) & 0xFFFFFFFFFFFFFFFF, int(cfg.warmup_size)
+        for k in ("epsilon", "discount", "lr", "adam_beta1", "adam_beta2", "adam_eps", "retrace_h", "per_alpha", "per_beta_initial",
+                  "per_beta_steps", "per_epsilon", "reward_shift", "reward_scale", "huber_delta"):
+            setattr(c, k, float(getattr(cfg, k)))
+        c.net = self.spec.to_c()
+        for name, _ in _lib.SrlxEngine._fields_:
+            if name in self.t:
+                setattr(c, name, self.t[name].data_ptr())
+        return c
+
+    def _stream(self):
+        s = self.stream if self.stream is not None else torch.cuda.current_stream(self.device)
+        return s.cuda_stream
+
+    # ---- control ---------------------------------------------------------------------------------------------
+    def reset(self):
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.srlx_engine_reset(C.byref(self.c), self._stream()))
+
+    def set_epsilon(self, eps: float):
+        self.c.epsilon = float(eps)
+
+    def vec_step(self, training=True):
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.srlx_vec_step(C.byref(self.c), int(training), self._stream()))
+
+    def learn(self, n_updates=1):
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.srlx_learn(C.byref(self.c), int(n_updates), self._stream()))
+
+    def run(self, n_steps, updates_per_step, training=True):
+        """n_steps x (one vector step of all E envs + updates_per_step trainer updates), no host sync in between."""
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.srlx_engine_run(C.byref(self.c), int(n_steps), int(updates_per_step), int(training), self._stream()))
+
+    def pred_q(self, obs: np.ndarray, target=False, noise_call_id=0) -> np.ndarray:
+        """RLParameter.pred_q / pred_target_q (srl/algorithms/dqn/model_torch.py:58-70)."""
+        x = torch.as_tensor(np.ascontiguousarray(obs, dtype=np.float32)).reshape(-1, self.D).to(self.device)
+        q = torch.empty((x.shape[0], self.A), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.srlx_qnet_forward(C.byref(self.c), int(target), x.data_ptr(), x.shape[0], int(noise_call_id), q.data_ptr(), self._stream()))
+        return q.cpu().numpy()
+
+    def noise(self, kind: int, call_id: int) -> np.ndarray:
+        out = torch.empty(self.spec.n_params, dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.srlx_noise_fill(int(self.cfg.seed) & 0xFFFFFFFFFFFFFFFF, int(kind), int(call_id), out.data_ptr(), self.spec.n_params, self._stream()))
+        return out.cpu().numpy()
+
+    # ---- state / parameters -------------------------------------------------------------------------------------
+    def read_state(self) -> "_lib.SrlxState":
+        self._state_host.copy_(self.t["state"], non_blocking=False)
+        return _lib.SrlxState.from_buffer_copy(self._state_host.numpy().tobytes())
+
+    def write_state(self, st: "_lib.SrlxState"):
+        self.t["state"].copy_(torch.frombuffer(bytearray(bytes(st)), dtype=torch.uint8))
+
+    def set_params(self, mu, sigma=None, also_target=False):
+        self.t["params"].copy_(torch.as_tensor(np.asarray(mu, dtype=np.float32)))
+        if self.cfg.noisy:
+            self.t["params_sigma"].copy_(torch.as_tensor(np.asarray(sigma, dtype=np.float32)))
+        if also_target:
+            self.set_target(mu, sigma)
+
+    def set_target(self, mu, sigma=None):
+        self.t["target"].copy_(torch.as_tensor(np.asarray(mu, dtype=np.float32)))
+        if self.cfg.noisy:
+            self.t["target_sigma"].copy_(torch.as_tensor(np.asarray(sigma, dtype=np.float32)))
+
+    def get_params(self):
+        return self.t["params"].cpu().numpy(), (self.t["params_sigma"].cpu().numpy() if self.cfg.noisy else None)
+
+    def get_target(self):
+        return self.t["target"].cpu().numpy(), (self.t["target_sigma"].cpu().numpy() if self.cfg.noisy else None)
+
+    def state_dict(self):
+        """The reference-compatible state_dict of the online network (RLParameter.call_backup)."""
+        mu, sigma = self.get_params()
+        return self.spec.to_state_dict(mu, sigma)
+
+    def load_state_dict(self, sd, also_target=True):
+        mu, sigma = self.spec.from_state_dict(sd)
+        self.set_params(mu, sigma, also_target=also_target)
+
+    def hbm_bytes(self):
+        return sum(t.numel() * t.element_size() for t in self.t.values())

@@ -1,0 +1,122 @@
+"""DeviceProportionalMemory: the reference's IPriorityMemory interface over the device SumTree.
+
+Drop-in for srl/rl/memories/priority_memories/proportional_memory.py::ProportionalMemory and its pybind11 twin
+(cpp_module/src/proportional_memory.cpp:87-275): same constructor arguments, same methods
+(clear / length / add / sample / update / backup / restore), `sample` returns (batches, weights, tree indices) and the
+indices are handed back verbatim to `update`; `backup()` returns the same 6-element list
+[capacity, max_priority, size, write, tree[:], data[:]] so memories interchange with the reference.
+Use it through `PriorityReplayBufferConfig.set_custom("simple_distributed_rl_b200.memory:DeviceProportionalMemory", {...})`
+(srl/rl/memories/priority_replay_buffer.py:111-117,149-152).
+
+The python payloads stay in a host list (the reference's C++ module also keeps py::object payloads); only the priority
+arithmetic lives on the GPU.  This seam exists for parity (the reference's own KATs run against it); the fast path is
+the fused engine (engine.py), where payloads never leave HBM.
+"""
+import ctypes as C
+from typing import Any, List, Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+
+
+class DeviceProportionalMemory:
+    def __init__(self, capacity: int, alpha: float = 0.6, beta_initial: float = 0.4, beta_steps: int = 1_000_000,
+                 has_duplicate: bool = True, epsilon: float = 0.0001, device="cuda:0", seed: int = 0):
+        self.lib = _lib.load()
+        if not torch.cuda.is_available():
+            raise _lib.SrlxError("DeviceProportionalMemory needs a CUDA device (no CPU fallback)")
+        self.capacity = int(capacity)
+        self.alpha, self.beta_initial, self.beta_steps = float(alpha), float(beta_initial), float(beta_steps)
+        self.has_duplicate, self.epsilon = bool(has_duplicate), float(epsilon)
+        self.device = torch.device(device)
+        self.seed = int(seed)
+        self._tree = torch.zeros(2 * self.capacity - 1, dtype=torch.float64, device=self.device)
+        self._meta = torch.zeros(C.sizeof(_lib.SrlxState), dtype=torch.uint8, device=self.device)
+        self._draws = 0
+        self.clear()
+
+    # -- helpers
+    def _s(self):
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def _read_meta(self) -> "_lib.SrlxState":
+        return _lib.SrlxState.from_buffer_copy(self._meta.cpu().numpy().tobytes())
+
+    def _write_meta(self, st):
+        self._meta.copy_(torch.frombuffer(bytearray(bytes(st)), dtype=torch.uint8))
+
+    # -- IPriorityMemory (imemory.py:7-34)
+    def clear(self) -> None:
+        _lib.check(self.lib.srlx_tree_clear(self._tree.data_ptr(), self.capacity, self._meta.data_ptr(), self._s()))
+        self.data: List[Any] = [None] * self.capacity
+        self._write = 0
+        self._size = 0
+
+    def length(self) -> int:
+        return self._size
+
+    def add(self, batch: Any, priority: Optional[float] = None, _restore_skip: bool = False) -> None:
+        pr = None
+        ptr = None
+        if priority is not None:
+            pr = torch.tensor([float(priority)], dtype=torch.float64, device=self.device)
+            ptr = pr.data_ptr()
+        _lib.check(self.lib.srlx_tree_add(self._tree.data_ptr(), self.capacity, self._meta.data_ptr(), ptr, 1, self.alpha,
+                                          self.epsilon, int(_restore_skip), self._s()))
+        self.data[self._write] = batch
+        self._write = (self._write + 1) % self.capacity
+        self._size = min(self._size + 1, self.capacity)
+
+    def sample(self, batch_size: int, step: int, uniforms: Optional[np.ndarray] = None):
+        idx = torch.empty(batch_size, dtype=torch.int64, device=self.device)
+        w = torch.empty(batch_size, dtype=torch.float32, device=self.device)
+        u_ptr, max_tries = None, 9999
+        if uniforms is not None:
+            u = torch.as_tensor(np.ascontiguousarray(uniforms, dtype=np.float64)).to(self.device)
+            u_ptr, max_tries = u.data_ptr(), int(u.shape[1])
+        # the Philox stream is keyed by (seed, draw counter) so consecutive sample() calls are independent draws
+        self._draws += 1
+        seed = (self.seed * 0x9E3779B97F4A7C15 + self._draws) & 0xFFFFFFFFFFFFFFFF
+        _lib.check(self.lib.srlx_tree_sample(self._tree.data_ptr(), self.capacity, self._meta.data_ptr(), batch_size, max(int(step), 0),
+                                             self.beta_initial, self.beta_steps, int(self.has_duplicate), seed, u_ptr, max_tries,
+                                             idx.data_ptr(), w.data_ptr(), None, self._s()))
+        indices = idx.cpu().numpy().tolist()
+        batches = [self.data[i - (self.capacity - 1)] for i in indices]
+        return batches, w.cpu().numpy(), indices
+
+    def update(self, indices: List[Any], priorities: np.ndarray) -> None:
+        n = len(indices)
+        if n == 0:
+            return
+        idx = torch.as_tensor(np.asarray(indices, dtype=np.int64)).to(self.device)
+        pr = torch.as_tensor(np.asarray(priorities, dtype=np.float32)).to(self.device)
+        _lib.check(self.lib.srlx_tree_update(self._tree.data_ptr(), self.capacity, self._meta.data_ptr(), idx.data_ptr(),
+                                             pr.data_ptr(), n, self.alpha, self.epsilon, self._s()))
+
+    def backup(self):
+        st = self._read_meta()
+        return [self.capacity, float(st.max_priority), int(st.mem_size), int(st.vec_steps), self._tree.cpu().numpy().tolist(), self.data[:]]
+
+    def restore(self, data) -> None:
+        if self.capacity == data[0]:
+            st = self._read_meta()
+            st.max_priority, st.mem_size, st.vec_steps = float(data[1]), int(data[2]), int(data[3])
+            self._write_meta(st)
+            self._tree.copy_(torch.as_tensor(np.asarray(data[4], dtype=np.float64)))
+            self.data = list(data[5][:])
+            self._size, self._write = int(data[2]), int(data[3])
+        else:  # different capacity: re-add item by item with the stored priorities (proportional_memory.py:196-205)
+            self.clear()
+            capacity, size, tree, tree_data = data[0], data[2], data[4], data[5]
+            for i in range(size):
+                self.add(tree_data[i], tree[i + capacity - 1], _restore_skip=True)
+
+    # -- extras used by the parity tests
+    @property
+    def max_priority(self) -> float:
+        return float(self._read_meta().max_priority)
+
+    def tree_array(self) -> np.ndarray:
+        return self._tree.cpu().numpy()
