@@ -339,8 +339,10 @@ def test_engine_lockstep(name):
             np.testing.assert_allclose(tm_d, orc.tgt_mu, rtol=1e-4, atol=2e-5)
             assert st.sync_count == orc.sync_count and st.adam_step == orc.train_count
             if dev.per:
-                np.testing.assert_allclose(dev.t["tree"].cpu().numpy(), orc.per.tree.tree, rtol=1e-4, atol=1e-7)
-                assert math.isclose(st.max_priority, orc.per.max_priority, rel_tol=1e-4)
+                # priorities are (|td| + 1e-4)^alpha of a DIFFERENCE of two Q values: an fp32 ulp of Q (1e-7 abs) moves a
+                # near-zero |td| by up to ~1e-3 relative, hence the absolute term
+                np.testing.assert_allclose(dev.t["tree"].cpu().numpy(), orc.per.tree.tree, rtol=1e-3, atol=1e-5)
+                assert math.isclose(st.max_priority, orc.per.max_priority, rel_tol=1e-3)
                 # keep the two trees bit-identical so the next leaf selection is comparable (fp32 |td| differs in ulps)
                 orc.per.tree.tree[:] = dev.t["tree"].cpu().numpy()
                 orc.per.max_priority = st.max_priority
