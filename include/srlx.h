@@ -140,6 +140,8 @@ typedef struct srlx_engine {
   uint32_t* env_episode;    /* [E] episodes started by this env (RNG counter) */
   double* env_ep_reward;    /* [E] EnvRun._episode_rewards */
   uint8_t* env_needs_reset; /* [E] */
+  double* env_first_ep_reward; /* [E] optional (NULL ok): reward of the FIRST episode env e finished (Runner.evaluate) */
+  int32_t* env_last_ep_len;    /* [E] optional: length of the last finished episode, 0 = none finished yet */
   float* ring_obs;          /* [R*E][D] state            */
   float* ring_next_obs;     /* [R*E][D] next_state       */
   int32_t* ring_action;     /* [R*E] action index (one-hot in the reference record) */

@@ -73,7 +73,7 @@ class SrlxEngine(C.Structure):
         ("grid_move_reward", C.c_double), ("grid_goal_reward", C.c_double), ("grid_hole_reward", C.c_double),
         ("net", SrlxNet),
         ("state", _P), ("env_state", _P), ("env_step_num", _P), ("env_episode", _P), ("env_ep_reward", _P),
-        ("env_needs_reset", _P),
+        ("env_needs_reset", _P), ("env_first_ep_reward", _P), ("env_last_ep_len", _P),
         ("ring_obs", _P), ("ring_next_obs", _P), ("ring_action", _P), ("ring_reward", _P), ("ring_term", _P),
         ("ring_done", _P),
         ("tree", _P), ("tree_scratch", _P),

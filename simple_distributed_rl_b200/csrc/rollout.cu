@@ -122,6 +122,10 @@ rollout_kernel(const __grid_constant__ srlx_engine eng, const int envs_per_cta, 
       }
       if (done) {
         eng.env_needs_reset[e] = 1;
+        if (eng.env_last_ep_len) {
+          if (eng.env_first_ep_reward && eng.env_last_ep_len[e] == 0) eng.env_first_ep_reward[e] = ep_reward;
+          eng.env_last_ep_len[e] = step_num;
+        }
         atomicAdd(&s_episodes, 1ull);
         atomicAdd(&s_eplen, (unsigned long long)step_num);
         atomicAdd(&s_epreward, ep_reward);
@@ -216,6 +220,8 @@ __global__ void engine_reset_kernel(const __grid_constant__ srlx_engine eng) {
     eng.env_episode[i] = 0;
     eng.env_step_num[i] = 0;
     eng.env_ep_reward[i] = 0.0;
+    if (eng.env_last_ep_len) eng.env_last_ep_len[i] = 0;
+    if (eng.env_first_ep_reward) eng.env_first_ep_reward[i] = 0.0;
     for (int d = 0; d < 4; ++d) eng.env_state[i * 4 + d] = 0.0;
   }
   for (size_t i = i0; i < cap; i += stride) {

@@ -62,7 +62,7 @@ class EngineConfig:
 
 
 class DeviceEngine:
-    def __init__(self, cfg: EngineConfig, device="cuda:0", debug: bool = False, params=None, stream=None):
+    def __init__(self, cfg: EngineConfig, device="cuda:0", debug: bool = False, params=None, stream=None, track_episodes: bool = False):
         self.lib = _lib.load()
         if not torch.cuda.is_available():
             raise _lib.SrlxError("DeviceEngine needs a CUDA device (no CPU fallback)")
@@ -99,6 +99,9 @@ class DeviceEngine:
         if self.per:
             self.t["tree"] = z(2 * self.cap - 1, torch.float64)
             self.t["tree_scratch"] = z(2 * (self.E + 2), torch.float64)
+        if track_episodes:
+            self.t["env_first_ep_reward"] = z(self.E, torch.float64)
+            self.t["env_last_ep_len"] = z(self.E, torch.int32)
         if noisy:
             self.t["params_sigma"] = z(P, torch.float32)
             self.t["target_sigma"] = z(P, torch.float32)
