@@ -42,7 +42,9 @@ def workload_config(args, world):
             "n_envs_per_gpu": args.envs, "replay_capacity_per_gpu": args.envs * args.ring_rows, "batch_size": 32,
             "multisteps": 3, "train_interval": args.train_interval,
             "updates_per_step_per_gpu": args.envs // args.train_interval,
-            "env_steps_per_step": args.envs * world, "parallelism": f"shard{world}" if world > 1 else "single",
+            "env_steps_per_step": args.envs * world,
+            "parallelism": (f"shard{world}: env/replay/SumTree shards + learner replica per GPU, parameters averaged by one "
+                            f"NCCL all-reduce per step") if world > 1 else "single",
             "l2": "flushed between timed steps (256 MiB write)"}
 
 
@@ -181,7 +183,7 @@ def own_arm(args):
     import torch
     import torch.distributed as dist
 
-    from simple_distributed_rl_b200 import _lib
+    from simple_distributed_rl_b200 import _lib, parallel
     from simple_distributed_rl_b200.engine import EngineConfig
     from simple_distributed_rl_b200.runner import VecRunner
 
@@ -205,6 +207,8 @@ def own_arm(args):
     P_total = eng.spec.n_params * 2  # mu + sigma
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
+    sync_tensors = [eng.t["params"]] + ([eng.t["params_sigma"]] if "params_sigma" in eng.t else [])
+
     def barrier():
         if world > 1:
             dist.barrier()
@@ -215,6 +219,8 @@ def own_arm(args):
     for _ in range(max(3, args.warmup)):
         eng.vec_step()
         eng.learn(U)
+        if world > 1:
+            parallel.average_parameters(sync_tensors)
     barrier()
 
     # ---- timed region: K steps, device-timed per phase, L2 flushed between steps ------------------------------
@@ -233,6 +239,8 @@ def own_arm(args):
         eng.vec_step()
         ev[k][1].record()
         eng.learn(U)
+        if world > 1:  # replicas' online parameters averaged over NVLink once per step (parallel.py)
+            parallel.average_parameters(sync_tensors)
         ev[k][2].record()
     barrier()
     t_wall = time.perf_counter() - t_wall0

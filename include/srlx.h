@@ -165,6 +165,8 @@ typedef struct srlx_engine {
   float* dbg_q_sa;          /* [B] */
   float* dbg_grads;         /* [n_params*(1+noisy)] gradient of the last update */
   float* dbg_windows;       /* [B][M+1][D] states, then [B][M] (action, reward, term) as floats */
+  long long* dbg_clock;     /* [32] clock64() stamps of the learner phases of the second-to-last update of a launch (CTA 0):
+                               [0..7] compute warps, [16..24] aux warps; see learner.cu */
 } srlx_engine;
 
 /* ---- library ------------------------------------------------------------------------------------------ */

@@ -1,16 +1,12 @@
-timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_r1_b.json 2> gpurun_out/bench_r1_b.err; python -c "
-import json; d=json.load(open('gpurun_out/bench_r1_b.json')); print(d['value'], d['trainer_updates_per_sec'], d['roofline']['us_per_update'], d['roofline_rollout']['launch_ms'], d['e2e']['value'], d['final_loss'], d['mean_episode_len'])"
-tail -3 gpurun_out/bench_r1_b.err
-cat > /tmp/san.py <<'PY'
+cat > /tmp/prof.py <<'PY'
 import sys; sys.path.insert(0,'.')
 from simple_distributed_rl_b200.engine import DeviceEngine, EngineConfig
 import torch
-for kw in [dict(env="CartPole-v1", algo="rainbow", hidden=(512,), dueling="average", noisy=True, mem_kind=1, multisteps=3, n_envs=48, ring_rows=12, batch_size=32, warmup_size=96),
-           dict(env="CartPole-v1", algo="rainbow", hidden=(64, 64), dueling="average", noisy=False, mem_kind=1, multisteps=3, n_envs=32, ring_rows=9, batch_size=16, warmup_size=64, has_duplicate=False, epsilon=0.25)]:
-    d = DeviceEngine(EngineConfig(**kw))
-    d.run(6, 3)
-    torch.cuda.synchronize()
-    print(d.read_state().train_count)
+kw = dict(env="CartPole-v1", algo="rainbow", hidden=(512,), dueling="average", noisy=True, mem_kind=1, multisteps=3, n_envs=8192, ring_rows=256, batch_size=32, warmup_size=1000, seed=1)
+d = DeviceEngine(EngineConfig(**kw))
+d.run(256, 0)
+for rep in range(3):
+    d.learn(128)
+torch.cuda.synchronize()
 PY
-timeout 900 compute-sanitizer --tool racecheck python /tmp/san.py 2>&1 | tail -8
-timeout 900 compute-sanitizer --tool memcheck python /tmp/san.py 2>&1 | tail -8
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:learner_kernel -s 2 -c 1 -o gpurun_out/prof_learner_r1_b -f python /tmp/prof.py > gpurun_out/ncu_c.log 2>&1; tail -3 gpurun_out/ncu_c.log

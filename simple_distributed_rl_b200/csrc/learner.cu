@@ -165,6 +165,11 @@ __host__ __device__ inline LPlan make_lplan(const srlx_engine& eng, int C, int m
   return p;
 }
 
+#define SRLX_STAMP(cond, slot)                                                        \
+  do {                                                                                \
+    if (eng.dbg_clock && rank == 0 && (cond) && upd + 2 == n_updates) eng.dbg_clock[slot] = clock64(); \
+  } while (0)
+
 struct LScal {
   double total, beta, max_priority, loss_sum, last_loss;
   unsigned long long retries;
@@ -482,6 +487,7 @@ learner_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_updates
       const int parb = upd & 1;
       const float* x_cur = xin + (size_t)parb * pl.NX * pl.ldx0;
       named_bar_sync(BAR_X, kLearnThreads);  // x(t) gathered by the aux warps
+      SRLX_STAMP(ct == 0, 0);
 
       // ---------------------------------------------------------------- trunk forward: warp per row tile, lane per row
       if (lw > 0) {
@@ -503,6 +509,7 @@ learner_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_updates
         }
         named_bar_sync(BAR_CMP, NCP);
       }
+      SRLX_STAMP(ct == 0, 1);
       // ---------------------------------------------------------------- wide layer + partial outputs: (tile, unit chunk)
       {
         const int usub = (Us + NSUB - 1) / NSUB;
@@ -530,6 +537,7 @@ learner_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_updates
         }
       }
       named_bar_sync(BAR_CMP, NCP);
+      SRLX_STAMP(ct == 0, 2);
       // ---------------------------------------------------------------- push this CTA's partial sums to every CTA
       {
         const int row_lo = need_online_next ? 0 : 0;
@@ -550,8 +558,10 @@ learner_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_updates
         fence_cluster();
         mbar_arrive_remote(&mbar[0], lane);
       }
+      SRLX_STAMP(ct == 0, 3);
       // ---------------------------------------------------------------- wait for d(raw outputs) from the aux warps
       named_bar_sync(BAR_D, kLearnThreads);
+      SRLX_STAMP(ct == 0, 4);
       // ---------------------------------------------------------------- backward of this CTA's slice
       for (int i = ct; i < pl.Pl; i += NCP) G[i] = 0.f;
       const float* wS = weff;  // the online(s) set
@@ -680,6 +690,7 @@ learner_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_updates
           }
         }
       }
+      SRLX_STAMP(ct == 0, 5);
       // ---------------------------------------------------------------- Adam + target sync + next effective weights
       if (ct == 0) {
         const double t = (double)(adam0 + upd + 1);
@@ -690,6 +701,7 @@ learner_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_updates
       finish(true, tc, tc + 1);
       if (ct == 0 && (tc % (uint64_t)eng.target_update_interval) == 0) sc->sync_count += 1;
       named_bar_sync(BAR_CMP, NCP);
+      SRLX_STAMP(ct == 0, 6);
     }
   } else {
     // ================================================== AUX WARPS ==================================================
@@ -855,6 +867,7 @@ learner_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_updates
       const int* slot = samp_slot + parb * B;
       const float* s_w = samp_w + parb * B;
       mbar_wait(&mbar[2], upd & 1);  // sample(t) has arrived from CTA 0
+      SRLX_STAMP(at == 0, 16);
       // ---------------------------------------------------------------- gather the windows (one L2 round trip)
       for (int w = at; w < BM; w += NA) {
         const int i = w / M, k = w - i * M;
@@ -903,9 +916,11 @@ learner_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_updates
       }
       named_bar_sync(BAR_AUX, NA);
       named_bar_arrive(BAR_X, kLearnThreads);  // x(t) ready for the compute warps
+      SRLX_STAMP(at == 0, 17);
 
       // ---------------------------------------------------------------- reduce the partial sums, dueling combine
       mbar_wait(&mbar[0], upd & 1);
+      SRLX_STAMP(at == 0, 18);
       {
         const int n_vals = pl.NRq * nout;
         const float* pb = part + (size_t)parb * C * n_vals;
@@ -939,6 +954,7 @@ learner_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_updates
         }
       }
       named_bar_sync(BAR_AUX, NA);
+      SRLX_STAMP(at == 0, 19);
       // ---------------------------------------------------------------- targets, Huber gradient (thread per sample)
       {
         const float* qon = Q + B * A;          // online(s')  [BM][A]
@@ -1003,6 +1019,7 @@ learner_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_updates
       }
       named_bar_sync(BAR_AUX, NA);
       named_bar_arrive(BAR_D, kLearnThreads);  // d(raw) ready: the compute warps start backward
+      SRLX_STAMP(at == 0, 20);
       if (rank == 0 && at == 0) {
         double l = 0.0;
         for (int w = 0; w < kAuxWarps; ++w) l += s_tmp[w];
@@ -1035,6 +1052,7 @@ learner_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_updates
         }
       }
       named_bar_sync(BAR_AUX, NA);  // s_tmp / loss consumed before the sampler reuses the scratch
+      SRLX_STAMP(at == 0, 21);
       // ---------------------------------------------------------------- CTA 0: priorities -> tree, then sample t+1
       if (rank == 0) {
         if (per) {
@@ -1088,7 +1106,9 @@ learner_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_updates
           }
           named_bar_sync(BAR_AUX, NA);
         }
+        SRLX_STAMP(at == 0, 22);
         if (upd + 1 < n_updates) sample_and_broadcast(tc + 1, parb ^ 1);
+        SRLX_STAMP(at == 0, 23);
       }
     }
   }

@@ -111,6 +111,7 @@ class DeviceEngine:
                 dbg_q=z((self.E, A), torch.float32), dbg_action=z(self.E, torch.int32), dbg_sample_idx=z(B, torch.int64),
                 dbg_weights=z(B, torch.float32), dbg_target_q=z(B, torch.float32), dbg_q_sa=z(B, torch.float32),
                 dbg_grads=z(P * (2 if noisy else 1), torch.float32), dbg_windows=z(B * (M + 1) * D + 3 * B * M, torch.float32),
+                dbg_clock=z(32, torch.int64),
             )
         self.c = self._build_struct()
         # pinned host mirror of the device counters (one small D2H per read)

@@ -1,0 +1,130 @@
+"""Drop-in glue for an installed `srl` (pocokhc/simple_distributed_rl): existing `srl.algorithms.dqn.Config` /
+`srl.algorithms.rainbow.Config` objects are read field by field and mapped onto the device engine, unchanged.
+
+    import srl
+    from srl.algorithms import rainbow
+    from simple_distributed_rl_b200 import srl_plugin
+
+    rl_config = rainbow.Config(multisteps=3, enable_noisy_dense=True)          # the user's existing config
+    rl_config.memory.set_proportional(); rl_config.memory.capacity = 2_000_000
+    runner = srl_plugin.DeviceRunner("CartPole-v1", rl_config, num_envs=8192)  # instead of srl.Runner(...)
+    runner.train(max_steps=10_000_000)                                         # same stop arguments as srl.Runner.train
+    rewards = runner.evaluate(max_episodes=100)
+    runner.save_parameter_state_dict()  -> reference-compatible state_dict (srl/rl/torch_/helper.py:60-93)
+
+Fields honoured (reference: srl/algorithms/dqn/dqn.py:50-103, srl/algorithms/rainbow/rainbow.py:57-108,
+srl/rl/memories/priority_replay_buffer.py:17-117, srl/base/rl/config.py:41-107): batch_size, memory.{capacity,
+warmup_size, name, kwargs}, epsilon, test_epsilon, lr, discount, target_model_update_interval, enable_reward_clip,
+enable_double_dqn, enable_rescale, enable_noisy_dense, multisteps, retrace_h, hidden_block (MLP / DuelingNetwork layer
+sizes + dueling_type), and, when present, reward_scale / reward_shift ... everything else (schedulers, image blocks,
+window_length > 1, frameskip, demo memory, rank-based memories) raises NotImplementedError instead of being silently ignored.
+
+`register_memory(rl_config)` alone swaps only the SumTree: `rl_config.memory.set_custom(ENTRY_POINT, kwargs)`
+(srl/rl/memories/priority_replay_buffer.py:111-117,149-152) so the reference's own Runner / Trainer drive the device tree.
+"""
+from typing import Any, List, Optional
+
+from . import _lib
+from .engine import EngineConfig
+from .runner import VecRunner
+
+MEMORY_ENTRY_POINT = "simple_distributed_rl_b200.memory:DeviceProportionalMemory"
+
+
+def _get(obj, name, default=None):
+    return getattr(obj, name, default)
+
+
+def _algo_of(rl_config) -> str:
+    name = rl_config.get_name() if hasattr(rl_config, "get_name") else type(rl_config).__module__
+    name = str(name).split(":")[0]
+    if name == "DQN":
+        return "dqn"
+    if name in ("Rainbow", "Rainbow_no_multisteps"):
+        return "rainbow"
+    raise NotImplementedError(f"algorithm {name!r} is not on the device path (supported: DQN, Rainbow)")
+
+
+def engine_config_from_srl(env: Any, rl_config: Any, num_envs: int, seed: int = 0, ring_rows: Optional[int] = None) -> EngineConfig:
+    """Map (env id or EnvConfig, dqn/rainbow Config) -> EngineConfig.  Unsupported settings raise."""
+    env_name = env if isinstance(env, str) else _get(env, "name", _get(env, "id", None))
+    env_kwargs = {} if isinstance(env, str) else dict(_get(env, "kwargs", {}) or {})
+    algo = _algo_of(rl_config)
+    # ---- things the device path does not implement: refuse loudly
+    if _get(rl_config, "window_length", 1) not in (0, 1):
+        raise NotImplementedError("window_length > 1 is not supported on the device path")
+    if _get(rl_config, "frameskip", 0) not in (0, None):
+        raise NotImplementedError("frameskip is not supported on the device path")
+    for sched in ("epsilon_scheduler", "lr_scheduler"):
+        s = _get(rl_config, sched)
+        if s is not None and (getattr(s, "schedulers", None) or getattr(s, "schedule_type", "") not in ("", None)):
+            raise NotImplementedError(f"{sched} with phases is not supported on the device path (constant rates only)")
+    mem = rl_config.memory
+    if _get(mem, "enable_demo_memory", False):
+        raise NotImplementedError("demo memory is not supported on the device path")
+    mk = dict(_get(mem, "kwargs", {}) or {})
+    if mem.name == "ReplayBuffer":
+        mem_kind, per = _lib.MEM_UNIFORM, {}
+    elif mem.name in ("Proportional", "Proportional_cpp"):
+        mem_kind = _lib.MEM_PROPORTIONAL
+        per = dict(per_alpha=mk.get("alpha", 0.6), per_beta_initial=mk.get("beta_initial", 0.4),
+                   per_beta_steps=mk.get("beta_steps", 1_000_000), per_epsilon=mk.get("epsilon", 0.0001),
+                   has_duplicate=mk.get("has_duplicate", True))
+    else:
+        raise NotImplementedError(f"memory {mem.name!r} is not supported on the device path (ReplayBuffer, Proportional)")
+    # ---- network
+    hb = rl_config.hidden_block
+    hk = dict(_get(hb, "kwargs", {}) or {})
+    noisy = bool(_get(rl_config, "enable_noisy_dense", False))
+    if hb.name == "MLP":
+        hidden, dueling = tuple(hk["layer_sizes"]), None
+        if hk.get("activation", "relu") != "relu":
+            raise NotImplementedError("only relu activations are supported on the device path")
+    elif hb.name == "DuelingNetwork":
+        hidden = tuple(hk["layer_sizes"])
+        dueling = hk.get("dueling_kwargs", {}).get("dueling_type", "average")
+        if hk.get("mlp_kwargs", {}).get("activation", "relu") != "relu":
+            raise NotImplementedError("only relu activations are supported on the device path")
+    else:
+        raise NotImplementedError(f"hidden block {hb.name!r} is not supported on the device path")
+    multisteps = int(_get(rl_config, "multisteps", 1)) if algo == "rainbow" else 1
+    if _algo_of(rl_config) == "rainbow" and str(rl_config.get_name()).startswith("Rainbow_no_multisteps"):
+        multisteps = 1
+    cap = int(mem.capacity)
+    rows = ring_rows if ring_rows is not None else max(multisteps, -(-cap // int(num_envs)))
+    return EngineConfig(
+        env=env_name, n_envs=int(num_envs), ring_rows=int(rows), multisteps=multisteps, batch_size=int(rl_config.batch_size),
+        mem_kind=mem_kind, algo=algo, enable_double_dqn=bool(rl_config.enable_double_dqn),
+        enable_rescale=bool(rl_config.enable_rescale), enable_reward_clip=bool(rl_config.enable_reward_clip),
+        target_update_interval=int(rl_config.target_model_update_interval), seed=int(seed),
+        warmup_size=int(mem.warmup_size), epsilon=float(rl_config.epsilon), discount=float(rl_config.discount),
+        lr=float(rl_config.lr), retrace_h=float(_get(rl_config, "retrace_h", 1.0)),
+        reward_shift=float(_get(rl_config, "reward_shift", 0.0) or 0.0), reward_scale=float(_get(rl_config, "reward_scale", 1.0) or 1.0),
+        hidden=hidden, dueling=dueling, noisy=noisy, env_kwargs=env_kwargs, **per)
+
+
+class DeviceRunner(VecRunner):
+    """`srl.Runner(env, rl_config)`-shaped constructor over the device engine."""
+
+    def __init__(self, env: Any, rl_config: Any, num_envs: int = 4096, seed: int = 0, device="cuda:0", ring_rows=None):
+        self.rl_config = rl_config
+        super().__init__(engine_config_from_srl(env, rl_config, num_envs, seed, ring_rows), device=device)
+
+    def evaluate(self, max_episodes: int = 10, **kw) -> List[float]:
+        return super().evaluate(max_episodes=max_episodes, test_epsilon=float(_get(self.rl_config, "test_epsilon", 0.0)), **kw)
+
+    # RLParameter.call_backup / call_restore interchange (srl/algorithms/dqn/model_torch.py:47-52)
+    def save_parameter_state_dict(self):
+        return self.state_dict()
+
+    def load_parameter_state_dict(self, sd):
+        self.load_state_dict(sd)
+
+
+def register_memory(rl_config: Any, device: str = "cuda:0", seed: int = 0) -> Any:
+    """Keep the reference Runner/Trainer/Worker, swap only the priority memory for the device SumTree."""
+    mk = dict(_get(rl_config.memory, "kwargs", {}) or {})
+    kw = dict(alpha=mk.get("alpha", 0.6), beta_initial=mk.get("beta_initial", 0.4), beta_steps=mk.get("beta_steps", 1_000_000),
+              has_duplicate=mk.get("has_duplicate", True), epsilon=mk.get("epsilon", 0.0001), device=device, seed=seed)
+    rl_config.memory.set_custom(MEMORY_ENTRY_POINT, kw)
+    return rl_config

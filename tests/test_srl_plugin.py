@@ -1,0 +1,70 @@
+"""The device path reads the reference's own config objects unchanged (srl_plugin.engine_config_from_srl).
+Needs the reference importable (/root/reference: present in the build container only) -> skipped elsewhere."""
+import os
+import sys
+
+import pytest
+
+REF = "/root/reference"
+
+
+@pytest.fixture(scope="module")
+def srl_mod():
+    if not os.path.isdir(os.path.join(REF, "srl")):
+        pytest.skip("reference not present")
+    sys.path.insert(0, REF)
+    try:
+        import srl  # noqa: F401
+        from srl.algorithms import dqn, rainbow
+    finally:
+        sys.path.remove(REF)
+    return dqn, rainbow
+
+
+def test_rainbow_config_maps_field_by_field(srl_mod):
+    from simple_distributed_rl_b200 import _lib
+    from simple_distributed_rl_b200.srl_plugin import engine_config_from_srl
+
+    _, rainbow = srl_mod
+    cfg = rainbow.Config(multisteps=3, enable_noisy_dense=True, lr=5e-4, discount=0.97, retrace_h=0.8, batch_size=64)
+    cfg.memory.set_proportional(alpha=0.7, beta_initial=0.5, beta_steps=1234, has_duplicate=False, epsilon=1e-3)
+    cfg.memory.capacity = 2_000_000
+    cfg.memory.warmup_size = 5000
+    cfg.set_torch() if hasattr(cfg, "set_torch") else None
+    e = engine_config_from_srl("CartPole-v1", cfg, num_envs=8192)
+    assert (e.algo, e.multisteps, e.noisy, e.dueling, e.hidden) == ("rainbow", 3, True, "average", (512,))
+    assert (e.n_envs, e.ring_rows, e.batch_size, e.warmup_size) == (8192, 245, 64, 5000)
+    assert e.mem_kind == _lib.MEM_PROPORTIONAL and not e.has_duplicate
+    assert (e.per_alpha, e.per_beta_initial, e.per_beta_steps, e.per_epsilon) == (0.7, 0.5, 1234, 1e-3)
+    assert (e.lr, e.discount, e.retrace_h, e.target_update_interval) == (5e-4, 0.97, 0.8, 1000)
+
+
+def test_dqn_config_maps_and_unsupported_raises(srl_mod):
+    from simple_distributed_rl_b200 import _lib
+    from simple_distributed_rl_b200.srl_plugin import engine_config_from_srl
+
+    dqn, rainbow = srl_mod
+    cfg = dqn.Config(epsilon=0.05, enable_double_dqn=False, enable_rescale=True)
+    cfg.hidden_block.set((64, 64))
+    cfg.memory.capacity = 1_000_000
+    e = engine_config_from_srl("Grid", cfg, num_envs=4096)
+    assert (e.algo, e.hidden, e.dueling, e.noisy, e.multisteps) == ("dqn", (64, 64), None, False, 1)
+    assert e.mem_kind == _lib.MEM_UNIFORM and e.ring_rows == 245 and not e.enable_double_dqn and e.enable_rescale
+    cfg.memory.set_rankbased()
+    with pytest.raises(NotImplementedError):
+        engine_config_from_srl("Grid", cfg, num_envs=64)
+    cfg2 = rainbow.Config()
+    cfg2.epsilon_scheduler.set_linear(1.0, 0.1, 1000)
+    with pytest.raises(NotImplementedError):
+        engine_config_from_srl("Grid", cfg2, num_envs=64)
+
+
+def test_register_memory_uses_reference_custom_seam(srl_mod):
+    from simple_distributed_rl_b200.srl_plugin import MEMORY_ENTRY_POINT, register_memory
+
+    dqn, _ = srl_mod
+    cfg = dqn.Config()
+    cfg.memory.set_proportional(alpha=0.5)
+    register_memory(cfg)
+    assert cfg.memory.name == "custom" and cfg.memory.kwargs["entry_point"] == MEMORY_ENTRY_POINT
+    assert cfg.memory.kwargs["kwargs"]["alpha"] == 0.5
