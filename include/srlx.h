@@ -166,7 +166,11 @@ typedef struct srlx_engine {
   float* dbg_grads;         /* [n_params*(1+noisy)] gradient of the last update */
   float* dbg_windows;       /* [B][M+1][D] states, then [B][M] (action, reward, term) as floats */
   long long* dbg_clock;     /* [32] clock64() stamps of the learner phases of the second-to-last update of a launch (CTA 0):
-                               [0..7] compute warps, [16..24] aux warps; see learner.cu */
+                               [0..7] compute warps, [16..24] aux / memory warps; see learner.cu, learner_fast.cu */
+  /* ---- scratch (caller-owned) ---- */
+  float* noise_scratch;     /* NoisyNet draws of a chunk of updates, precomputed by all SMs and streamed by the learner
+                               (learner_fast.cu); NULL -> the generic learner draws in-kernel */
+  uint64_t noise_scratch_bytes;
 } srlx_engine;
 
 /* ---- library ------------------------------------------------------------------------------------------ */

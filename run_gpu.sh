@@ -1,12 +1,6 @@
-cat > /tmp/prof.py <<'PY'
-import sys; sys.path.insert(0,'.')
-from simple_distributed_rl_b200.engine import DeviceEngine, EngineConfig
-import torch
-kw = dict(env="CartPole-v1", algo="rainbow", hidden=(512,), dueling="average", noisy=True, mem_kind=1, multisteps=3, n_envs=8192, ring_rows=256, batch_size=32, warmup_size=1000, seed=1)
-d = DeviceEngine(EngineConfig(**kw))
-d.run(256, 0)
-for rep in range(3):
-    d.learn(128)
-torch.cuda.synchronize()
-PY
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:learner_kernel -s 2 -c 1 -o gpurun_out/prof_learner_r1_b -f python /tmp/prof.py > gpurun_out/ncu_c.log 2>&1; tail -3 gpurun_out/ncu_c.log
+set -x
+mkdir -p gpurun_out
+make -C simple_distributed_rl_b200/csrc 2>&1 | tail -2
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -8
+timeout 300 python tools/phase_clocks.py 2>&1 | tail -3 | tee gpurun_out/phase_r1_c.json
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:learner_fast_kernel -s 1 -c 1 -o gpurun_out/prof_fast_r1_c -f python tools/prof_learner.py > gpurun_out/ncu_c.log 2>&1; tail -3 gpurun_out/ncu_c.log

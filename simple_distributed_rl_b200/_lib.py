@@ -80,6 +80,7 @@ class SrlxEngine(C.Structure):
         ("params", _P), ("params_sigma", _P), ("target", _P), ("target_sigma", _P), ("adam_m", _P), ("adam_v", _P),
         ("dbg_q", _P), ("dbg_action", _P), ("dbg_sample_idx", _P), ("dbg_weights", _P), ("dbg_target_q", _P),
         ("dbg_q_sa", _P), ("dbg_grads", _P), ("dbg_windows", _P), ("dbg_clock", _P),
+        ("noise_scratch", _P), ("noise_scratch_bytes", C.c_uint64),
     ]
 
 

@@ -1144,10 +1144,14 @@ learner_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_updates
   cluster.sync();  // no CTA may exit while a peer can still address its shared memory
 }
 
+int learn_generic(const srlx_engine* eng, uint32_t n_updates, uintptr_t cuda_stream);
+
 }  // namespace srlx
 
 // ---- host side ---------------------------------------------------------------------------------------------------
-extern "C" int srlx_learn(const srlx_engine* eng, uint32_t n_updates, uintptr_t cuda_stream) {
+// generic kernel (any MLP depth); srlx_learn (learner_fast.cu) dispatches here when the short-critical-path kernel does
+// not apply
+int srlx::learn_generic(const srlx_engine* eng, uint32_t n_updates, uintptr_t cuda_stream) {
   using namespace srlx;
   SRLX_REQUIRE(eng != nullptr, "srlx_learn: eng is NULL");
   SRLX_REQUIRE(eng->batch_size >= 1 && eng->batch_size <= SRLX_MAX_BATCH, "batch_size %d out of range [1,%d]", eng->batch_size, SRLX_MAX_BATCH);

@@ -1,0 +1,1144 @@
+// learner_fast.cu -- the trainer inner step for SINGLE-HIDDEN-LAYER Q-networks (the reference's Rainbow default: dueling
+// (512,) head on a <= 4-float observation; srl/algorithms/rainbow/rainbow.py:57-108, dueling_network.py:12-14), as one
+// persistent thread-block-cluster kernel whose critical path per update is a handful of dependent hops:
+//
+//   forward (all rows, units sharded over the C CTAs, weights in registers, packed FFMA2)
+//     -> reduce-scatter of the partial output sums to the CTA that OWNS the batch item   (st.async + mbarrier tx, DSMEM)
+//     -> owner: dueling combine, n-step/Retrace target, Huber gradient                    (B/C items per CTA)
+//     -> all-gather of d(raw outputs) + (target, q)                                        (st.async + mbarrier tx)
+//     -> backward + Adam + next effective weights (every CTA, its slice)      ||   CTA 0: priorities -> SumTree update
+//                                                                                   -> PER sample(t+1) -> slots to all
+//                                                                                   CTAs -> every CTA gathers x(t+1)
+//
+// What is NOT on the critical path any more (compared with learner.cu, which stays as the generic kernel for deeper nets):
+//   * NoisyNet draws: noise_precompute_kernel fills HBM with the N(0,1) tensors of a whole chunk of updates using all
+//     148 SMs (3 x P Gaussians per update; Philox + Box-Muller is ~150 instructions per 4 values), laid out per CTA in
+//     CTA-local parameter order; the learner streams its slice with one cp.async.bulk (TMA, mbarrier complete_tx) per
+//     update, two updates ahead, into a 3-deep shared-memory ring.
+//   * Adam bias-correction pow()s: tabulated per launch.
+//   * IS weights: sent after the sampled slots (only the Huber step needs them).
+// 16 compute warps + 4 memory warps per CTA; the memory warps run one update ahead (sample/gather of t+1 overlaps
+// backward + Adam of t).  Same arithmetic, reference line citations and CPU twin (oracle/engine.py::OracleEngine.learn)
+// as learner.cu.
+#include <stdlib.h>
+
+#include "cluster.cuh"
+#include "net.cuh"
+#include "tree.cuh"
+
+namespace srlx {
+
+int learn_generic(const srlx_engine* eng, uint32_t n_updates, uintptr_t cuda_stream);  // learner.cu
+
+constexpr int kFCmpWarps = 16, kFMemWarps = 4;
+constexpr int FNC = kFCmpWarps * 32, FNM = kFMemWarps * 32, FNT = FNC + FNM;
+constexpr int kFMaxC = 16, kFMaxSeg = 8, kFCacheLevels = 11, kFMaxChunk = 512, kFHld = 33, kFSubLd = 66;
+enum { FBAR_CMP = 1, FBAR_MEM = 2 };
+enum { FSEG_W = 0, FSEG_B = 1, FSEG_O = 2, FSEG_OB = 3 };
+enum { MB_RS = 0, MB_AG, MB_S, MB_WT, MB_XR, MB_NZ0, MB_NZ1, MB_NZ2, MB_COUNT };
+
+// A contiguous run of the flat (global) parameter vector held by one CTA.
+struct FSeg {
+  int g0, n, l0;  // global flat offset, length, offset in the CTA-local parameter arrays
+  int kind, o;    // FSEG_*; output row for FSEG_O
+  int ulo;        // FSEG_O: first local unit the run covers
+  int noisy, replicated;
+};
+
+struct FPlan {
+  int C, B, M, A, D, K, nout, Uh, Us, nCh, BM, NX, NRq, ipc, rpi, nOwn, Pl, WS, nRG, rpg, B4, n_cache;
+  size_t off_mbar, off_seg, off_scal, off_adam, off_gpow, off_gidx, off_slot, off_par, off_nz, off_weff, off_xin, off_meta,
+      off_g, off_hS, off_part, off_rs, off_ag, off_qown, off_rawown, off_samp_slot, off_samp_w, off_sdbl, off_sub, off_cache, total;
+};
+
+__host__ __device__ inline int fast_pick_cluster(const srlx_net& net, int want) {
+  const int Uh = net.out_dim[0];
+  int c = want > 0 ? want : 8;
+  if (c > kFMaxC) c = kFMaxC;
+  while (c > 1 && (Uh % c != 0 || (Uh / c) % 4 != 0)) c >>= 1;
+  if (Uh % c != 0 || (Uh / c) % 4 != 0) return 0;
+  return c;
+}
+
+// the runs of CTA `rank`; returns their number
+__host__ __device__ inline int fast_segs(const srlx_net& net, int C, int rank, FSeg* out) {
+  const int K = net.k_dim[0], Uh = net.out_dim[0], Us = Uh / C, u0 = rank * Us, nout = net.out_dim[1], Ko = net.k_dim[1];
+  int ns = 0, l0 = 0;
+  auto add = [&](int g0, int n, int kind, int o, int ulo, int nz, int rep) {
+    if (n <= 0) return;
+    FSeg s;
+    s.g0 = g0; s.n = n; s.l0 = l0; s.kind = kind; s.o = o; s.ulo = ulo; s.noisy = nz; s.replicated = rep;
+    out[ns++] = s;
+    l0 += n;
+  };
+  add(net.w_off[0] + u0 * K, Us * K, FSEG_W, 0, 0, net.layer_noisy[0], 0);
+  add(net.b_off[0] + u0, Us, FSEG_B, 0, 0, net.layer_noisy[0], 0);
+  for (int o = 0; o < nout; ++o) {
+    const int koff = (net.dueling != SRLX_DUEL_NONE && o > 0) ? Ko : 0;  // output row o reads wide units [koff, koff+Ko)
+    const int lo_u = u0 > koff ? u0 : koff, hi_u = (u0 + Us) < (koff + Ko) ? (u0 + Us) : (koff + Ko);
+    add(net.w_off[1] + o * Ko + (lo_u - koff), hi_u - lo_u, FSEG_O, o, lo_u - u0, net.layer_noisy[1], 0);
+  }
+  add(net.b_off[1], nout, FSEG_OB, 0, 0, net.layer_noisy[1], 1);
+  return ns;
+}
+
+__host__ __device__ inline bool fast_shape_ok(const srlx_engine& eng) {
+  const srlx_net& net = eng.net;
+  return net.n_layers == 2 && eng.obs_dim >= 1 && eng.obs_dim <= 4 && net.k_dim[0] == eng.obs_dim && net.out_dim[1] <= 4 &&
+         eng.n_actions <= 4 && eng.batch_size >= 1 && eng.batch_size <= 32 && eng.multisteps >= 1 &&
+         eng.multisteps <= SRLX_MAX_MULTISTEPS && (2ll * eng.ring_rows * eng.n_envs) < (1ll << 31);
+}
+
+__host__ __device__ inline FPlan make_fplan(const srlx_engine& eng, int C, long long n_tree_nodes) {
+  FPlan p;
+  const srlx_net& net = eng.net;
+  p.C = C;
+  p.B = eng.batch_size;
+  p.M = eng.multisteps;
+  p.A = eng.n_actions;
+  p.D = eng.obs_dim;
+  p.K = net.k_dim[0];
+  p.nout = net.out_dim[1];
+  p.Uh = net.out_dim[0];
+  p.Us = p.Uh / C;
+  p.nCh = p.Us / 4;
+  p.BM = p.B * p.M;
+  p.NX = p.B + p.BM;
+  p.NRq = p.B + 2 * p.BM;
+  p.ipc = (p.B + C - 1) / C;
+  p.rpi = 1 + 2 * p.M;
+  p.nOwn = p.ipc * p.rpi;
+  p.Pl = round_up(p.Us * (p.K + 1) + p.nout * p.Us + p.nout, 4);
+  p.WS = p.nCh * 36 + 4;
+  p.nRG = 1;
+  while (p.nRG * 2 * p.Us <= FNC && p.nRG * 2 <= 32) p.nRG *= 2;
+  p.rpg = (p.B + p.nRG - 1) / p.nRG;
+  p.B4 = round_up(p.B, 4);
+  size_t o = 0;
+  auto take = [&](size_t bytes) { size_t r = o; o += (bytes + 15) / 16 * 16; return r; };
+  p.off_mbar = take(8 * MB_COUNT);
+  p.off_seg = take(sizeof(FSeg) * kFMaxSeg);
+  p.off_scal = take(256);
+  p.off_adam = take((size_t)2 * kFMaxChunk * 4);
+  p.off_gpow = take((size_t)SRLX_MAX_MULTISTEPS * 4);
+  p.off_gidx = take((size_t)p.Pl * 4);
+  p.off_slot = take((size_t)p.Pl * 4);
+  p.off_par = take((size_t)8 * p.Pl * 4);
+  p.off_nz = take(net.noisy ? (size_t)9 * p.Pl * 4 : 0);
+  p.off_weff = take((size_t)3 * p.WS * 4);
+  p.off_xin = take((size_t)2 * p.NX * 16);
+  p.off_meta = take((size_t)2 * 3 * p.BM * 4);  // [2][act, rew, term][BM]
+  p.off_g = take((size_t)4 * p.BM * 4);         // gathered act / rew / term / done before the padding pass
+  p.off_hS = take((size_t)p.Us * kFHld * 4);
+  {
+    const size_t a = (size_t)kFCmpWarps * p.NRq * 16, b = (size_t)p.nRG * p.Pl * 4;
+    p.off_part = take(a > b ? a : b);
+  }
+  p.off_rs = take((size_t)2 * C * p.nOwn * 16);
+  p.off_ag = take((size_t)2 * p.B * 32);
+  p.off_qown = take((size_t)p.nOwn * 16);
+  p.off_rawown = take((size_t)p.ipc * 16);
+  p.off_samp_slot = take((size_t)2 * p.B4 * 4);
+  p.off_samp_w = take((size_t)2 * p.B4 * 4);
+  p.off_sdbl = take((size_t)6 * 32 * 8);  // s_idx (i64), s_pri, s_new, s_chg, s_val, s_tmp
+  p.n_cache = 0;
+  if (eng.mem_kind == SRLX_MEM_PROPORTIONAL) {
+    p.off_sub = take((size_t)kFMemWarps * 8 * kFSubLd * 8);
+    int lev = 0;
+    while (lev < kFCacheLevels && ((1ll << (lev + 1)) - 1) <= n_tree_nodes) ++lev;
+    p.n_cache = (int)((1ll << lev) - 1);
+  } else {
+    p.off_sub = take(0);
+  }
+  p.off_cache = take((size_t)p.n_cache * 8);
+  p.total = o;
+  return p;
+}
+
+// ---- PTX helpers: DSMEM stores that complete a transaction count on the destination CTA's mbarrier, TMA bulk copy ------
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t saddr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void st_async_f4(uint32_t raddr, float4 v, uint32_t rmbar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.f32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(raddr),
+               "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "r"(rmbar)
+               : "memory");
+}
+__device__ __forceinline__ void st_async_i4(uint32_t raddr, int4 v, uint32_t rmbar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.s32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(raddr),
+               "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "r"(rmbar)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.release.cta.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_local(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ float2 f2(float a, float b) { return make_float2(a, b); }
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+
+struct FScal {
+  double max_priority, loss_sum, last_loss;
+  unsigned long long retries;
+  unsigned int sync_count;
+};
+
+#define SRLX_FSTAMP(cond, slot)                                                                                    \
+  do {                                                                                                             \
+    if (eng.dbg_clock && rank == 0 && (cond) && upd + 2 == n_updates) eng.dbg_clock[slot] = clock64();             \
+  } while (0)
+
+// =====================================================================================================================
+// N(0,1) tensors of `n_updates` consecutive updates, CTA-local order: out[((u * C + rank) * 3 + set) * Pl + i].
+// set 0 = online(s), 1 = online(s'), 2 = target(s'): NoisyLinear draws per forward call (noisy_linear.py:35-52), call ids
+// as in learner.cu (train_count * 3 + set).
+__global__ void __launch_bounds__(128) noise_precompute_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_updates,
+                                                               const int C, const int Pl, float* __restrict__ out) {
+  __shared__ FSeg segs[kFMaxSeg];
+  __shared__ int n_seg_s;
+  const int u = blockIdx.x / C, rank = blockIdx.x - u * C;
+  if (threadIdx.x == 0) n_seg_s = fast_segs(eng.net, C, rank, segs);
+  __syncthreads();
+  const uint64_t tc = eng.state->train_count + (uint64_t)u;
+  float* dst = out + (size_t)blockIdx.x * 3 * Pl;
+  for (int s = 0; s < n_seg_s; ++s) {
+    const FSeg sg = segs[s];
+    const int blk0 = sg.g0 >> 2, blk1 = (sg.g0 + sg.n - 1) >> 2;
+    for (int blk = blk0 + (int)threadIdx.x; blk <= blk1; blk += (int)blockDim.x) {
+      float z[3][4] = {};
+      if (sg.noisy) {
+#pragma unroll
+        for (int set = 0; set < 3; ++set) {
+          const float4 a = noise4(eng.seed, NOISE_KIND_TRAIN, tc * 3 + set, (uint32_t)blk);
+          z[set][0] = a.x; z[set][1] = a.y; z[set][2] = a.z; z[set][3] = a.w;
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int p = 4 * blk + q;
+        if (p < sg.g0 || p >= sg.g0 + sg.n) continue;
+        const int i = sg.l0 + (p - sg.g0);
+#pragma unroll
+        for (int set = 0; set < 3; ++set) dst[(size_t)set * Pl + i] = z[set][q];
+      }
+    }
+  }
+}
+
+// =====================================================================================================================
+__global__ void __launch_bounds__(FNT, 1)
+learner_fast_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_updates, const float* __restrict__ noise) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  cg::cluster_group cluster = cg::this_cluster();
+  const int C = (int)cluster.num_blocks();
+  const int rank = (int)cluster.block_rank();
+  const srlx_net& net = eng.net;
+  const int64_t cap = (int64_t)eng.ring_rows * eng.n_envs, n_nodes = 2 * cap - 1;
+  const FPlan pl = make_fplan(eng, C, n_nodes);
+
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(smem + pl.off_mbar);
+  FSeg* segs = reinterpret_cast<FSeg*>(smem + pl.off_seg);
+  FScal* sc = reinterpret_cast<FScal*>(smem + pl.off_scal);
+  int* n_seg_p = reinterpret_cast<int*>(smem + pl.off_scal + 128);
+  int* n_used_p = n_seg_p + 1;
+  float* adam_ss = reinterpret_cast<float*>(smem + pl.off_adam);  // step_size per update of this launch
+  float* adam_bc = adam_ss + kFMaxChunk;                          // sqrt(bias_correction2)
+  float* gpow = reinterpret_cast<float*>(smem + pl.off_gpow);
+  int* gidx = reinterpret_cast<int*>(smem + pl.off_gidx);
+  int* slot_t = reinterpret_cast<int*>(smem + pl.off_slot);
+  float* par = reinterpret_cast<float*>(smem + pl.off_par);
+  float *p_mu = par, *p_sg = par + pl.Pl, *p_m1 = par + 2 * pl.Pl, *p_v1 = par + 3 * pl.Pl, *p_m2 = par + 4 * pl.Pl,
+        *p_v2 = par + 5 * pl.Pl, *p_tmu = par + 6 * pl.Pl, *p_tsg = par + 7 * pl.Pl;
+  float* nzr = reinterpret_cast<float*>(smem + pl.off_nz);      // [3 ring][3 set][Pl]
+  float* weff = reinterpret_cast<float*>(smem + pl.off_weff);   // [3][WS]
+  float* xin = reinterpret_cast<float*>(smem + pl.off_xin);     // [2][NX][4]
+  float* meta = reinterpret_cast<float*>(smem + pl.off_meta);   // [2][3][BM]
+  int* g_act = reinterpret_cast<int*>(smem + pl.off_g);
+  float* g_rew = reinterpret_cast<float*>(smem + pl.off_g) + pl.BM;
+  float* g_term = g_rew + pl.BM;
+  int* g_done = reinterpret_cast<int*>(g_term + pl.BM);
+  float* hS = reinterpret_cast<float*>(smem + pl.off_hS);       // [Us][33]
+  float* part = reinterpret_cast<float*>(smem + pl.off_part);   // [16][NRq][4]  (forward)  /  [nRG][Pl] (backward)
+  float* rs = reinterpret_cast<float*>(smem + pl.off_rs);       // [2][C][nOwn][4]
+  float* ag = reinterpret_cast<float*>(smem + pl.off_ag);       // [2][B][8]: d(raw)[4], target, q, loss term, -
+  float* qown = reinterpret_cast<float*>(smem + pl.off_qown);   // [nOwn][4]
+  float* rawown = reinterpret_cast<float*>(smem + pl.off_rawown);
+  int* samp_slot = reinterpret_cast<int*>(smem + pl.off_samp_slot);
+  float* samp_w = reinterpret_cast<float*>(smem + pl.off_samp_w);
+  int64_t* s_idx = reinterpret_cast<int64_t*>(smem + pl.off_sdbl);
+  double* s_pri = reinterpret_cast<double*>(smem + pl.off_sdbl) + 32;
+  double *s_new = s_pri + 32, *s_chg = s_pri + 64, *s_val = s_pri + 96, *s_tmp = s_pri + 128;
+  double* sub = reinterpret_cast<double*>(smem + pl.off_sub);
+  double* cache = reinterpret_cast<double*>(smem + pl.off_cache);
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int B = pl.B, M = pl.M, A = pl.A, D = pl.D, K = pl.K, E = eng.n_envs, R = eng.ring_rows, BM = pl.BM;
+  const int Us = pl.Us, nout = pl.nout, nCh = pl.nCh, Pl = pl.Pl, WS = pl.WS, rpi = pl.rpi, ipc = pl.ipc;
+  const int u0 = rank * Us;
+  const bool per = eng.mem_kind == SRLX_MEM_PROPORTIONAL;
+  const bool noisy = net.noisy != 0;
+  const bool need_online_next = eng.enable_double_dqn || M > 1;
+  const int rows_sent_per_item = 1 + M + (need_online_next ? M : 0);
+  const int nIt = max(0, min(ipc, B - rank * ipc));  // batch items this CTA owns: [rank*ipc, rank*ipc + nIt)
+  srlx_state* st = eng.state;
+
+  const uint64_t tc0 = st->train_count, mem_size = st->mem_size, vec_steps = st->vec_steps, adam0 = st->adam_step;
+  const bool go = mem_size >= eng.warmup_size && mem_size >= (uint64_t)B;
+  if (!go) return;  // still warming up (uniform across the cluster)
+
+  const size_t nz_bytes = (size_t)3 * Pl * 4;
+  auto nz_src = [&](uint32_t u) { return noise + ((size_t)u * C + rank) * 3 * Pl; };
+
+  // ---- one-time setup ---------------------------------------------------------------------------------------------
+  if (tid == 0) {
+    mbar_init(&mbar[MB_RS], 1);
+    mbar_init(&mbar[MB_AG], 1);
+    mbar_init(&mbar[MB_S], 1);
+    mbar_init(&mbar[MB_WT], 1);
+    mbar_init(&mbar[MB_XR], 1);
+    mbar_init(&mbar[MB_NZ0], 1);
+    mbar_init(&mbar[MB_NZ1], 1);
+    mbar_init(&mbar[MB_NZ2], 1);
+    fence_mbar_init();
+    mbar_expect_tx(&mbar[MB_S], (uint32_t)pl.B4 * 4);
+    mbar_expect_tx(&mbar[MB_WT], (uint32_t)pl.B4 * 4);
+    if (noisy) {
+      mbar_expect_tx(&mbar[MB_NZ0], (uint32_t)nz_bytes);
+      bulk_g2s(nzr, nz_src(0), (uint32_t)nz_bytes, &mbar[MB_NZ0]);
+      if (n_updates > 1) {
+        mbar_expect_tx(&mbar[MB_NZ1], (uint32_t)nz_bytes);
+        bulk_g2s(nzr + 3 * Pl, nz_src(1), (uint32_t)nz_bytes, &mbar[MB_NZ1]);
+      }
+    }
+    const int ns = fast_segs(net, C, rank, segs);
+    *n_seg_p = ns;
+    *n_used_p = segs[ns - 1].l0 + segs[ns - 1].n;
+    sc->loss_sum = 0.0;
+    sc->last_loss = 0.0;
+    sc->retries = 0;
+    sc->sync_count = 0;
+    sc->max_priority = st->max_priority;
+  }
+  for (int i = tid; i < 3 * WS; i += FNT) weff[i] = 0.f;
+  for (int i = tid; i < 2 * pl.NX * 4; i += FNT) xin[i] = 0.f;
+  for (int i = tid; i < 8 * Pl; i += FNT) par[i] = 0.f;
+  for (int i = tid; i < Us * kFHld; i += FNT) hS[i] = 0.f;
+  for (int i = tid; i < (int)n_updates && i < kFMaxChunk; i += FNT) {
+    const double t = (double)(adam0 + (uint64_t)i + 1);
+    adam_ss[i] = (float)(eng.lr / (1.0 - pow(eng.adam_beta1, t)));
+    adam_bc[i] = (float)sqrt(1.0 - pow(eng.adam_beta2, t));
+  }
+  if (tid < M) gpow[tid] = (float)pow(eng.discount, (double)tid);
+  if (rank == 0)
+    for (int i = tid; i < pl.n_cache; i += FNT) cache[i] = __ldcg(eng.tree + i);
+  __syncthreads();
+  const int n_seg = *n_seg_p, n_used = *n_used_p;
+  for (int s = 0; s < n_seg; ++s) {
+    const FSeg sg = segs[s];
+    for (int j = tid; j < sg.n; j += FNT) {
+      const int p = sg.g0 + j, i = sg.l0 + j;
+      int sl;
+      if (sg.kind == FSEG_W) {
+        const int u = j / K, k = j - u * K;
+        sl = (u >> 2) * 16 + k * 4 + (u & 3);
+      } else if (sg.kind == FSEG_B) {
+        sl = nCh * 16 + j;
+      } else if (sg.kind == FSEG_O) {
+        const int u = sg.ulo + j;
+        sl = nCh * 20 + (u >> 2) * 16 + sg.o * 4 + (u & 3);
+      } else {
+        sl = nCh * 36 + j;
+      }
+      gidx[i] = p;
+      slot_t[i] = sl | ((noisy && sg.noisy) ? (1 << 29) : 0) | (sg.replicated ? (1 << 30) : 0);
+      p_mu[i] = __ldcg(eng.params + p);
+      p_tmu[i] = __ldcg(eng.target + p);
+      p_m1[i] = __ldcg(eng.adam_m + p);
+      p_v1[i] = __ldcg(eng.adam_v + p);
+      if (noisy) {
+        p_sg[i] = __ldcg(eng.params_sigma + p);
+        p_tsg[i] = __ldcg(eng.target_sigma + p);
+        p_m2[i] = __ldcg(eng.adam_m + net.n_params + p);
+        p_v2[i] = __ldcg(eng.adam_v + net.n_params + p);
+      }
+    }
+  }
+  cluster.sync();  // mbarriers initialised + everyone's shared memory ready before any remote access
+
+  const uint32_t mb_rs = smem_u32(&mbar[MB_RS]), mb_ag = smem_u32(&mbar[MB_AG]), mb_s = smem_u32(&mbar[MB_S]),
+                 mb_wt = smem_u32(&mbar[MB_WT]);
+
+  // ==================================================================================================================
+  if (warp < kFCmpWarps) {
+    // ================================================ COMPUTE WARPS ================================================
+    const int ct = tid, cw = warp;
+    const float b1 = (float)eng.adam_beta1, b2 = (float)eng.adam_beta2, aeps = (float)eng.adam_eps;
+
+    // Adam (update `upd`, if do_adam) + target sync + effective weights of the next update: one pass over the CTA's parameters
+    auto finish = [&](bool do_adam, uint32_t upd, bool build_next) {
+      const uint64_t tc_done = tc0 + upd;
+      const float step_size = do_adam ? adam_ss[upd] : 0.f, bc2_sqrt = do_adam ? adam_bc[upd] : 1.f;
+      const bool do_sync = do_adam && (tc_done % (uint64_t)eng.target_update_interval) == 0;
+      const uint32_t un = do_adam ? upd + 1 : 0;  // update whose weights are built
+      const float* z_cur = nzr + (size_t)(upd % 3) * 3 * Pl;   // noise of update `upd` (set 0 = the eps of online(s))
+      const float* z_nxt = nzr + (size_t)(un % 3) * 3 * Pl;
+      for (int i = ct; i < n_used; i += FNC) {
+        const int sl = slot_t[i];
+        const bool nz = (sl >> 29) & 1;
+        const int slot = sl & 0x1fffffff;
+        float mu = p_mu[i], sgm = nz ? p_sg[i] : 0.f;
+        if (do_adam) {
+          float g = 0.f;
+          for (int rg = 0; rg < pl.nRG; ++rg) g += part[(size_t)rg * Pl + i];
+          float m = p_m1[i], v = p_v1[i];
+          // torch/optim/adam.py _single_tensor_adam: lerp, mul_/addcmul_, sqrt/div/add_, addcdiv_
+          m = m + (g - m) * (1.0f - b1);
+          v = v * b2 + (1.0f - b2) * g * g;
+          mu = mu - step_size * (m / (sqrtf(v) / bc2_sqrt + aeps));
+          p_mu[i] = mu; p_m1[i] = m; p_v1[i] = v;
+          const bool wr = eng.dbg_grads && (!((sl >> 30) & 1) || rank == 0);
+          if (wr) eng.dbg_grads[gidx[i]] = g;
+          if (noisy) {
+            float gs = 0.f;
+            if (nz) {
+              gs = g * z_cur[i];
+              float m2 = p_m2[i], v2 = p_v2[i];
+              m2 = m2 + (gs - m2) * (1.0f - b1);
+              v2 = v2 * b2 + (1.0f - b2) * gs * gs;
+              sgm = sgm - step_size * (m2 / (sqrtf(v2) / bc2_sqrt + aeps));
+              p_sg[i] = sgm; p_m2[i] = m2; p_v2[i] = v2;
+            }
+            if (wr) eng.dbg_grads[net.n_params + gidx[i]] = gs;
+          }
+          if (do_sync) { p_tmu[i] = mu; if (nz) p_tsg[i] = sgm; }
+        }
+        if (build_next) {
+          const float tmu = p_tmu[i];
+          float zS = 0.f, zN = 0.f, zT = 0.f, tsg = 0.f;
+          if (nz) { zS = z_nxt[i]; zN = z_nxt[Pl + i]; zT = z_nxt[2 * Pl + i]; tsg = p_tsg[i]; }
+          weff[slot] = fmaf(sgm, zS, mu);
+          weff[WS + slot] = fmaf(sgm, zN, mu);
+          weff[2 * WS + slot] = fmaf(tsg, zT, tmu);
+        }
+      }
+    };
+
+    if (noisy) mbar_wait(&mbar[MB_NZ0], 0);
+    finish(false, 0, true);
+    named_bar_sync(FBAR_CMP, FNC);
+
+    const int nActive = min(kFCmpWarps, nCh);
+    for (uint32_t upd = 0; upd < n_updates; ++upd) {
+      const int parb = upd & 1;
+      const float* x_cur = xin + (size_t)parb * pl.NX * 4;
+      const int* w_act = reinterpret_cast<const int*>(meta + (size_t)parb * 3 * BM);
+      const float* w_rew = meta + (size_t)parb * 3 * BM + BM;
+      const float* w_term = w_rew + BM;
+      if (ct == 0) {
+        mbar_expect_tx(&mbar[MB_RS], (uint32_t)(C * nIt * rows_sent_per_item * 16));
+        mbar_expect_tx(&mbar[MB_AG], (uint32_t)(B * 32));
+      }
+      mbar_wait(&mbar[MB_XR], parb);  // x(t) gathered by the memory warps
+      SRLX_FSTAMP(ct == 0, 0);
+
+      // ---------------------------------------------------------------- forward: warp = 4-unit chunk(s), lane = row
+      for (int ch = cw; ch < nCh; ch += kFCmpWarps) {
+        const bool first = ch < kFCmpWarps;
+        float* mypart = part + (size_t)cw * pl.NRq * 4;
+        unsigned omask = 0;
+        {
+          const int ua = u0 + ch * 4, ub = ua + 4;
+          for (int o = 0; o < nout; ++o) {
+            const int koff = (net.dueling != SRLX_DUEL_NONE && o > 0) ? net.k_dim[1] : 0;
+            if (ua < koff + net.k_dim[1] && ub > koff) omask |= 1u << o;
+          }
+        }
+        for (int set = 0; set < 3; ++set) {
+          if (set == 1 && !need_online_next) continue;
+          const float* ws = weff + set * WS;
+          const float4 W0 = ld4(ws + ch * 16), W1 = ld4(ws + ch * 16 + 4), W2 = ld4(ws + ch * 16 + 8), W3 = ld4(ws + ch * 16 + 12);
+          const float4 Bv = ld4(ws + nCh * 16 + ch * 4);
+          const float* wo = ws + nCh * 20 + ch * 16;
+          const float4 O0 = ld4(wo), O1 = ld4(wo + 4), O2 = ld4(wo + 8), O3 = ld4(wo + 12);
+          const int nrows = set == 0 ? B : BM, row_base = set == 0 ? 0 : (set == 1 ? B : B + BM), xbase = set == 0 ? 0 : B;
+          for (int j0 = 0; j0 < nrows; j0 += 32) {
+            const int r = j0 + lane;
+            const bool valid = r < nrows;
+            const float4 x = ld4(x_cur + (size_t)(xbase + min(r, nrows - 1)) * 4);
+            float2 a01 = f2(Bv.x, Bv.y), a23 = f2(Bv.z, Bv.w);
+            a01 = __ffma2_rn(f2(W0.x, W0.y), f2(x.x, x.x), a01); a23 = __ffma2_rn(f2(W0.z, W0.w), f2(x.x, x.x), a23);
+            a01 = __ffma2_rn(f2(W1.x, W1.y), f2(x.y, x.y), a01); a23 = __ffma2_rn(f2(W1.z, W1.w), f2(x.y, x.y), a23);
+            a01 = __ffma2_rn(f2(W2.x, W2.y), f2(x.z, x.z), a01); a23 = __ffma2_rn(f2(W2.z, W2.w), f2(x.z, x.z), a23);
+            a01 = __ffma2_rn(f2(W3.x, W3.y), f2(x.w, x.w), a01); a23 = __ffma2_rn(f2(W3.z, W3.w), f2(x.w, x.w), a23);
+            const float2 h01 = f2(fmaxf(a01.x, 0.f), fmaxf(a01.y, 0.f)), h23 = f2(fmaxf(a23.x, 0.f), fmaxf(a23.y, 0.f));
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (omask & 1u) { float2 t = __ffma2_rn(h01, f2(O0.x, O0.y), f2(0.f, 0.f)); t = __ffma2_rn(h23, f2(O0.z, O0.w), t); acc.x = t.x + t.y; }
+            if (omask & 2u) { float2 t = __ffma2_rn(h01, f2(O1.x, O1.y), f2(0.f, 0.f)); t = __ffma2_rn(h23, f2(O1.z, O1.w), t); acc.y = t.x + t.y; }
+            if (omask & 4u) { float2 t = __ffma2_rn(h01, f2(O2.x, O2.y), f2(0.f, 0.f)); t = __ffma2_rn(h23, f2(O2.z, O2.w), t); acc.z = t.x + t.y; }
+            if (omask & 8u) { float2 t = __ffma2_rn(h01, f2(O3.x, O3.y), f2(0.f, 0.f)); t = __ffma2_rn(h23, f2(O3.z, O3.w), t); acc.w = t.x + t.y; }
+            if (valid) {
+              if (set == 0) {
+                float* hp = hS + (size_t)(ch * 4) * kFHld + r;
+                hp[0] = h01.x; hp[kFHld] = h01.y; hp[2 * kFHld] = h23.x; hp[3 * kFHld] = h23.y;
+              }
+              float4* dst = reinterpret_cast<float4*>(mypart + (size_t)(row_base + r) * 4);
+              if (!first) { const float4 o = *dst; acc.x += o.x; acc.y += o.y; acc.z += o.z; acc.w += o.w; }
+              *dst = acc;
+            }
+          }
+        }
+      }
+      named_bar_sync(FBAR_CMP, FNC);
+      SRLX_FSTAMP(ct == 0, 1);
+      // ---------------------------------------------------------------- reduce over warps, scatter to the owning CTA
+      for (int row = ct; row < pl.NRq; row += FNC) {
+        int item, j;
+        if (row < B) { item = row; j = 0; }
+        else if (row < B + BM) {
+          if (!need_online_next) continue;
+          const int w = row - B; item = w / M; j = 1 + (w - item * M);
+        } else { const int w = row - B - BM; item = w / M; j = 1 + M + (w - item * M); }
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int w = 0; w < nActive; ++w) {
+          const float4 o = ld4(part + ((size_t)w * pl.NRq + row) * 4);
+          v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
+        }
+        const int c = item / ipc, ii = item - c * ipc;
+        const float* dst = rs + (((size_t)parb * C + rank) * pl.nOwn + ii * rpi + j) * 4;
+        st_async_f4(mapa_u32(smem_u32(dst), (uint32_t)c), v, mapa_u32(mb_rs, (uint32_t)c));
+      }
+      mbar_wait(&mbar[MB_RS], parb);
+      SRLX_FSTAMP(ct == 0, 2);
+      // ---------------------------------------------------------------- owner: sum the C partials, dueling combine
+      for (int w = ct; w < nIt * rpi; w += FNC) {
+        const int ii = w / rpi, j = w - ii * rpi;
+        const int set = j == 0 ? 0 : (j <= M ? 1 : 2);
+        if (set == 1 && !need_online_next) continue;
+        float4 v = ld4(weff + set * WS + nCh * 36);  // effective output bias of this forward call
+        for (int c = 0; c < C; ++c) {
+          const float4 o = ld4(rs + (((size_t)parb * C + c) * pl.nOwn + w) * 4);
+          v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
+        }
+        const float raw[4] = {v.x, v.y, v.z, v.w};
+        float q[4] = {0.f, 0.f, 0.f, 0.f};
+        if (net.dueling == SRLX_DUEL_NONE) {
+          for (int a = 0; a < A; ++a) q[a] = raw[a];
+        } else {
+          float red = 0.f;
+          if (net.dueling == SRLX_DUEL_AVERAGE) {
+            for (int a = 0; a < A; ++a) red += raw[1 + a];
+            red = red / (float)A;
+          } else if (net.dueling == SRLX_DUEL_MAX) {
+            red = raw[1];
+            for (int a = 1; a < A; ++a) red = fmaxf(red, raw[1 + a]);
+          }
+          for (int a = 0; a < A; ++a) q[a] = raw[0] + raw[1 + a] - red;
+        }
+        *reinterpret_cast<float4*>(qown + (size_t)w * 4) = make_float4(q[0], q[1], q[2], q[3]);
+        if (set == 0) *reinterpret_cast<float4*>(rawown + (size_t)ii * 4) = v;
+      }
+      named_bar_sync(FBAR_CMP, FNC);
+      SRLX_FSTAMP(ct == 0, 6);
+      mbar_wait(&mbar[MB_WT], parb);  // IS weights of this batch
+      SRLX_FSTAMP(ct == 0, 7);
+      if (ct == 0 && upd + 1 < n_updates) mbar_expect_tx(&mbar[MB_WT], (uint32_t)pl.B4 * 4);
+      // ---------------------------------------------------------------- owner: targets, Huber gradient (thread per item)
+      if (ct < nIt) {
+        const int ii = ct, i = rank * ipc + ii;
+        const float* qs = qown + (size_t)(ii * rpi) * 4;
+        const float* qon = qs + 4;             // online(s')  [M][4]
+        const float* qtg = qs + 4 * (1 + M);   // target(s')  [M][4]
+        const float gamma = (float)eng.discount;
+        float target = 0.f, retrace = 1.f;
+        for (int k = 0; k < M; ++k) {
+          const float* qo = qon + k * 4;
+          const float* qt = qtg + k * 4;
+          const float* qsel = eng.enable_double_dqn ? qo : qt;
+          int am = 0;
+          float best = qsel[0];
+          for (int a = 1; a < A; ++a)
+            if (qsel[a] > best) { best = qsel[a]; am = a; }  // np.argmax: first max wins
+          // Retrace with the reference's index shift (rainbow.py:267): action taken at s_k vs greedy action at s_{k+1}
+          if (k >= 1) retrace = retrace * ((float)eng.retrace_h * ((w_act[i * M + k] == am) ? 1.f : 0.f));
+          float maxq = qt[am];
+          if (eng.enable_rescale) maxq = inverse_rescaling_f(maxq);
+          float gain = w_rew[i * M + k] + ((1.0f - w_term[i * M + k]) * gamma) * maxq;
+          if (eng.enable_rescale) gain = rescaling_f(gain);
+          float qk = 0.f;  // the first step is learnt by the trainer itself (rainbow.py:232-234)
+          if (k >= 1) qk = qon[(k - 1) * 4 + w_act[i * M + k]];
+          const float td = gain - qk;
+          target += (td * gpow[k]) * retrace;
+        }
+        const int a0 = w_act[i * M + 0];
+        const float q = qs[a0];
+        const float w = samp_w[parb * pl.B4 + i];
+        const float d = q * w - target * w;
+        const float ad = fabsf(d);
+        const float delta = (float)eng.huber_delta;
+        const float lterm = (ad <= delta) ? 0.5f * d * d : delta * (ad - 0.5f * delta);
+        const float dq = fminf(fmaxf(d, -delta), delta) * w / (float)B;
+        float dr[4] = {0.f, 0.f, 0.f, 0.f};
+        if (net.dueling == SRLX_DUEL_NONE) {
+          dr[a0] = dq;
+        } else {  // dueling combine backward (dueling_network.py:51-58)
+          int amax = 0;
+          if (net.dueling == SRLX_DUEL_MAX) {
+            const float* rw = rawown + ii * 4;
+            float bestr = rw[1];
+            for (int a = 1; a < A; ++a)
+              if (rw[1 + a] > bestr) { bestr = rw[1 + a]; amax = a; }
+          }
+          for (int a = 0; a < A; ++a) {
+            float dd = (a == a0) ? dq : 0.f;
+            if (net.dueling == SRLX_DUEL_AVERAGE) dd -= dq / (float)A;
+            else if (net.dueling == SRLX_DUEL_MAX && a == amax) dd -= dq;
+            dr[1 + a] = dd;
+          }
+          dr[0] = dq;
+        }
+        const float4 v0 = make_float4(dr[0], dr[1], dr[2], dr[3]), v1 = make_float4(target, q, lterm, 0.f);
+        const uint32_t dst = smem_u32(ag + ((size_t)parb * B + i) * 8);
+        for (int c = 0; c < C; ++c) {
+          const uint32_t rb = mapa_u32(mb_ag, (uint32_t)c);
+          st_async_f4(mapa_u32(dst, (uint32_t)c), v0, rb);
+          st_async_f4(mapa_u32(dst + 16, (uint32_t)c), v1, rb);
+        }
+      }
+      SRLX_FSTAMP(ct == 0, 8);
+      mbar_wait(&mbar[MB_AG], parb);
+      SRLX_FSTAMP(ct == 0, 3);
+      // ---------------------------------------------------------------- backward of this CTA's slice: thread = (unit, row group)
+      {
+        const float* agb = ag + (size_t)parb * B * 8;
+        const float* wS = weff;  // online(s)
+        for (int it = ct; it < Us * pl.nRG; it += FNC) {
+          const int rg = it / Us, u = it - rg * Us;
+          const float* wo = wS + nCh * 20 + (u >> 2) * 16 + (u & 3);
+          const float wo0 = wo[0], wo1 = wo[4], wo2 = wo[8], wo3 = wo[12];
+          float gW0 = 0.f, gW1 = 0.f, gW2 = 0.f, gW3 = 0.f, gb = 0.f, gO0 = 0.f, gO1 = 0.f, gO2 = 0.f, gO3 = 0.f;
+          const int r0 = rg * pl.rpg, r1 = min(B, r0 + pl.rpg);
+          for (int r = r0; r < r1; ++r) {
+            const float4 dr = ld4(agb + (size_t)r * 8);
+            const float h = hS[(size_t)u * kFHld + r];
+            const float4 x = ld4(x_cur + (size_t)r * 4);
+            float d = dr.x * wo0;
+            d = fmaf(dr.y, wo1, d); d = fmaf(dr.z, wo2, d); d = fmaf(dr.w, wo3, d);
+            const float dh = h > 0.f ? d : 0.f;
+            gO0 = fmaf(dr.x, h, gO0); gO1 = fmaf(dr.y, h, gO1); gO2 = fmaf(dr.z, h, gO2); gO3 = fmaf(dr.w, h, gO3);
+            gb += dh;
+            gW0 = fmaf(dh, x.x, gW0); gW1 = fmaf(dh, x.y, gW1); gW2 = fmaf(dh, x.z, gW2); gW3 = fmaf(dh, x.w, gW3);
+          }
+          float* g = part + (size_t)rg * Pl;
+          const float gW[4] = {gW0, gW1, gW2, gW3}, gO[4] = {gO0, gO1, gO2, gO3};
+          for (int k = 0; k < K; ++k) g[u * K + k] = gW[k];
+          g[Us * K + u] = gb;
+          for (int s = 2; s < n_seg; ++s) {
+            const FSeg& sg = segs[s];
+            if (sg.kind == FSEG_O && u >= sg.ulo && u < sg.ulo + sg.n) g[sg.l0 + (u - sg.ulo)] = gO[sg.o];
+          }
+        }
+        // output bias (replicated parameter, identical on every CTA): row group 0 holds the sum, the others zero
+        if (ct < nout * pl.nRG) {
+          const int rg = ct / nout, o = ct - rg * nout;
+          float a = 0.f;
+          if (rg == 0)
+            for (int r = 0; r < B; ++r) a += agb[(size_t)r * 8 + o];
+          part[(size_t)rg * Pl + segs[n_seg - 1].l0 + o] = a;
+        }
+      }
+      named_bar_sync(FBAR_CMP, FNC);
+      SRLX_FSTAMP(ct == 0, 4);
+      // ---------------------------------------------------------------- Adam + target sync + next effective weights
+      const bool more = upd + 1 < n_updates;
+      if (noisy && more) mbar_wait(&mbar[MB_NZ0 + (upd + 1) % 3], ((upd + 1) / 3) & 1);
+      finish(true, upd, more);
+      named_bar_sync(FBAR_CMP, FNC);
+      SRLX_FSTAMP(ct == 0, 5);
+    }
+  } else {
+    // ================================================= MEMORY WARPS =================================================
+    const int mt = tid - FNC, mw = warp - kFCmpWarps;
+    const int64_t cap1 = cap - 1;
+    const unsigned FULL = 0xffffffffu;
+
+    // ---- sample of update `tc` (CTA 0): slots, then IS weights, into buffer `pb` of every CTA ---------------------------
+    auto sample_and_send = [&](uint64_t tc, int pb, uint32_t upd) {
+#define SRLX_SSTAMP(slot)                                                                                  \
+  do {                                                                                                     \
+    if (eng.dbg_clock && mt == 0 && upd + 1 == n_updates) eng.dbg_clock[slot] = clock64();                 \
+  } while (0)
+      double total = 0.0, beta = 1.0;
+      auto draw = [&](int i, int k) -> double {
+        const uint4 w = philox(eng.seed, STREAM_SAMPLE, (uint32_t)i | ((uint32_t)k << 16), (uint32_t)tc, (uint32_t)(tc >> 32));
+        return u01_f64(w.x, w.y);
+      };
+      if (per) {
+        total = cache[0];
+        // PriorityReplayBuffer.step is the train_count of the PREVIOUS update() call (priority_replay_buffer.py:232,250)
+        const double stepd = (tc > 0) ? (double)(tc - 1) : 0.0;
+        beta = eng.per_beta_initial + (1.0 - eng.per_beta_initial) * stepd / eng.per_beta_steps;
+        beta = beta > 1.0 ? 1.0 : beta;
+        // lane g < 8 of memory warp mw owns sample mw*8+g
+        const int i = mw * 8 + lane;
+        const bool own = lane < 8 && i < B;
+        int idx = 0;
+        double val = 0.0, pcur = 0.0;
+        if (own) {  // (a) the cached top levels, out of shared memory
+          val = draw(i, 0) * total;
+          while (2 * idx + 1 < pl.n_cache) {
+            const double tl = cache[2 * idx + 1];
+            if (val <= tl) idx = 2 * idx + 1;
+            else { val -= tl; idx = 2 * idx + 2; }
+          }
+          pcur = cache[idx];
+        }
+        SRLX_SSTAMP(22);
+        bool done = !own || (2 * (int64_t)idx + 1 >= n_nodes);
+        // (b) the remaining levels, five per L2 round trip: 31 lanes fetch both children of every node of the 5-level
+        //     subtree below each of the warp's 8 samples, the owner lanes replay the "val <= tree[left]" walk out of smem
+        double* wsub = sub + (size_t)mw * 8 * kFSubLd;
+        const int k_l = 32 - __clz(lane + 1);         // level (1..5) whose nodes this lane fetches; lane 31 idles
+        const int q_l = lane + 1 - (1 << (k_l - 1));  // parent position inside level k_l - 1
+        const int pos_l = (1 << k_l) - 2 + 2 * q_l;
+        while (__any_sync(FULL, !done)) {
+          double v0[8], v1[8];
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            const int ig = __shfl_sync(FULL, idx, g);
+            const int dg = __shfl_sync(FULL, (int)done, g);
+            const int64_t node = (((int64_t)ig + 1) << k_l) - 1 + 2 * q_l;
+            const bool ld = lane < 31 && !dg;
+            v0[g] = (ld && node < n_nodes) ? __ldcg(eng.tree + node) : 0.0;
+            v1[g] = (ld && node + 1 < n_nodes) ? __ldcg(eng.tree + node + 1) : 0.0;
+          }
+          if (lane < 31) {
+#pragma unroll
+            for (int g = 0; g < 8; ++g) *reinterpret_cast<double2*>(wsub + g * kFSubLd + pos_l) = make_double2(v0[g], v1[g]);
+          }
+          __syncwarp();
+          if (!done) {
+            const double* ms = wsub + lane * kFSubLd;
+            int rel = 0;
+#pragma unroll
+            for (int k = 1; k <= 5; ++k) {
+              const int64_t left = 2 * (int64_t)idx + 1;
+              if (left < n_nodes) {
+                const int base = (1 << k) - 2 + 2 * rel;
+                const double tl = ms[base];
+                if (val <= tl) { idx = (int)left; rel = 2 * rel; pcur = tl; }
+                else { val -= tl; pcur = ms[base + 1]; idx = (int)left + 1; rel = 2 * rel + 1; }
+              }
+            }
+            done = 2 * (int64_t)idx + 1 >= n_nodes;
+          }
+          __syncwarp();
+        }
+        SRLX_SSTAMP(23);
+        if (own) {  // a zero-priority leaf is re-drawn (proportional_memory.py:150-152), sequentially
+          int64_t li = idx;
+          double p = pcur;
+          int k = 0;
+          while (p == 0.0 && k + 1 < 9999) {
+            ++k;
+            li = tree_retrieve_seq(eng.tree, n_nodes, draw(i, k) * total);
+            p = __ldcg(eng.tree + li);
+          }
+          s_idx[i] = li;
+          s_pri[i] = p;
+          s_tmp[i] = (double)k;
+          if (k) atomicAdd(&sc->retries, (unsigned long long)k);
+        }
+        named_bar_sync(FBAR_MEM, FNM);
+        if (!eng.has_duplicate) {
+          if (mt == 0) {
+            for (int i2 = 1; i2 < B; ++i2) {
+              int k = (int)s_tmp[i2];
+              while (k < 9999) {
+                bool dup = false;
+                for (int j = 0; j < i2; ++j) dup |= (s_idx[j] == s_idx[i2]);
+                if (!dup && s_pri[i2] != 0.0) break;
+                ++k;
+                sc->retries += 1;
+                if (k >= 9999) break;
+                s_idx[i2] = tree_retrieve_seq(eng.tree, n_nodes, draw(i2, k) * total);
+                s_pri[i2] = __ldcg(eng.tree + s_idx[i2]);
+              }
+            }
+          }
+          named_bar_sync(FBAR_MEM, FNM);
+        }
+      } else {
+        // uniform replay: B distinct items (replay_buffer.py:34-36), sequential rejection
+        if (mt == 0) {
+          const uint64_t g_next = vec_steps;
+          const uint64_t g_lo = g_next > (uint64_t)R ? g_next - R : 0;
+          const uint64_t n_g = g_next - (uint64_t)(M - 1) - g_lo;
+          const uint32_t n_valid = (uint32_t)(n_g * E);
+          for (int i = 0; i < B; ++i) {
+            uint32_t pick = 0;
+            for (int k = 0; k < 65536; ++k) {
+              const uint4 w = philox(eng.seed, STREAM_UNIFORM_SAMPLE, (uint32_t)i | ((uint32_t)k << 16), (uint32_t)tc, (uint32_t)(tc >> 32));
+              pick = u_below(w.x, n_valid);
+              bool dup = false;
+              for (int j = 0; j < i; ++j) dup |= (s_idx[j] == (int64_t)pick);
+              if (!dup) break;
+            }
+            s_idx[i] = pick;
+          }
+          for (int i = 0; i < B; ++i) {
+            const uint64_t pick = (uint64_t)s_idx[i];
+            const uint64_t g = g_lo + pick / E;
+            s_idx[i] = (int64_t)((g % R) * E + pick % E) + cap1;  // stored as if it were a tree index
+          }
+        }
+        named_bar_sync(FBAR_MEM, FNM);
+      }
+      SRLX_SSTAMP(24);
+      // slots to every CTA (4 per store)
+      {
+        const int nq = pl.B4 / 4;
+        const uint32_t dst = smem_u32(samp_slot + pb * pl.B4);
+        for (int w = mt; w < nq * C; w += FNM) {
+          const int c = w / nq, q = w - c * nq;
+          int v[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) v[e] = (4 * q + e < B) ? (int)(s_idx[4 * q + e] - cap1) : 0;
+          st_async_i4(mapa_u32(dst + 16 * q, (uint32_t)c), make_int4(v[0], v[1], v[2], v[3]), mapa_u32(mb_s, (uint32_t)c));
+        }
+      }
+      SRLX_SSTAMP(25);
+      // IS weights (proportional_memory.py:159-167): only the Huber step needs them, so they follow the slots
+      if (per) {
+        if (mt < B) s_tmp[mt] = pow((double)mem_size * (s_pri[mt] / total), -beta);
+        named_bar_sync(FBAR_MEM, FNM);
+        SRLX_SSTAMP(26);
+        if (mw == 0) {
+          double mx = 0.0;
+          for (int i = lane; i < B; i += 32) mx = fmax(mx, s_tmp[i]);
+          for (int s = 16; s > 0; s >>= 1) mx = fmax(mx, __shfl_xor_sync(FULL, mx, s));
+          for (int i = lane; i < B; i += 32) s_val[i] = s_tmp[i] / mx;
+        }
+      } else {
+        if (mt < B) s_val[mt] = 1.0;
+      }
+      named_bar_sync(FBAR_MEM, FNM);
+      {
+        const int nq = pl.B4 / 4;
+        const uint32_t dst = smem_u32(samp_w + pb * pl.B4);
+        for (int w = mt; w < nq * C; w += FNM) {
+          const int c = w / nq, q = w - c * nq;
+          float v[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) v[e] = (4 * q + e < B) ? (float)s_val[4 * q + e] : 0.f;
+          st_async_f4(mapa_u32(dst + 16 * q, (uint32_t)c), make_float4(v[0], v[1], v[2], v[3]), mapa_u32(mb_wt, (uint32_t)c));
+        }
+      }
+    };
+
+    if (rank == 0) sample_and_send(tc0, 0, 0);
+
+    for (uint32_t upd = 0; upd < n_updates; ++upd) {
+      const uint64_t tc = tc0 + upd;
+      const int parb = upd & 1;
+      float* x_cur = xin + (size_t)parb * pl.NX * 4;
+      int* w_act = reinterpret_cast<int*>(meta + (size_t)parb * 3 * BM);
+      float* w_rew = meta + (size_t)parb * 3 * BM + BM;
+      float* w_term = w_rew + BM;
+      const int* slot = samp_slot + parb * pl.B4;
+      mbar_wait(&mbar[MB_S], parb);  // slots of update t have arrived from CTA 0
+      SRLX_FSTAMP(mt == 0, 16);
+      // ---------------------------------------------------------------- gather the windows (one memory round trip)
+      for (int w = mt; w < BM; w += FNM) {
+        const int i = w / M, k = w - i * M;
+        const int s0 = slot[i];
+        const int rho = s0 / E, e = s0 - rho * E;
+        const int sk = ((rho + k) % R) * E + e;
+        g_act[w] = __ldcg(eng.ring_action + sk);
+        g_rew[w] = __ldcg(eng.ring_reward + sk);
+        g_term[w] = (float)__ldcg(eng.ring_term + sk);
+        g_done[w] = (int)__ldcg(eng.ring_done + sk);
+        float* xr = x_cur + (size_t)(B + w) * 4;
+        if (D == 4) {
+          *reinterpret_cast<float4*>(xr) = __ldcg(reinterpret_cast<const float4*>(eng.ring_next_obs + (size_t)sk * 4));
+        } else {
+          for (int d = 0; d < D; ++d) xr[d] = __ldcg(eng.ring_next_obs + (size_t)sk * D + d);
+        }
+      }
+      for (int i = mt; i < B; i += FNM) {
+        float* xr = x_cur + (size_t)i * 4;
+        if (D == 4) {
+          *reinterpret_cast<float4*>(xr) = __ldcg(reinterpret_cast<const float4*>(eng.ring_obs + (size_t)slot[i] * 4));
+        } else {
+          for (int d = 0; d < D; ++d) xr[d] = __ldcg(eng.ring_obs + (size_t)slot[i] * D + d);
+        }
+      }
+      named_bar_sync(FBAR_MEM, FNM);
+      for (int i = mt; i < B; i += FNM) {
+        const int s0 = slot[i];
+        const int rho = s0 / E, e = s0 - rho * E;
+        const uint64_t g_last = vec_steps - 1;
+        const uint64_t g_item = g_last - ((g_last + (uint64_t)R - (uint64_t)rho) % (uint64_t)R);
+        bool ended = false;
+        int last_k = 0;
+        for (int k = 0; k < M; ++k) {
+          const int w = i * M + k;
+          if (!ended) {
+            w_act[w] = g_act[w];
+            w_rew[w] = g_rew[w];
+            w_term[w] = g_term[w];
+            last_k = k;
+            if (g_done[w]) ended = true;
+          } else {
+            // padded tail record: random action, reward 0, terminated 1, state = last next_state (rainbow.py:358-371)
+            const uint64_t gp = g_item + (uint64_t)k;
+            const uint4 pw = philox(eng.seed, STREAM_PAD_ACTION, (uint32_t)e, (uint32_t)gp, (uint32_t)(gp >> 32));
+            w_act[w] = (int)u_below(pw.x, (uint32_t)A);
+            w_rew[w] = 0.f;
+            w_term[w] = 1.f;
+            *reinterpret_cast<float4*>(x_cur + (size_t)(B + w) * 4) = ld4(x_cur + (size_t)(B + i * M + last_k) * 4);
+          }
+        }
+      }
+      named_bar_sync(FBAR_MEM, FNM);
+      if (mt == 0) {
+        mbar_arrive_local(&mbar[MB_XR]);  // x(t) ready for the compute warps
+        if (upd + 1 < n_updates) mbar_expect_tx(&mbar[MB_S], (uint32_t)pl.B4 * 4);
+      }
+      SRLX_FSTAMP(mt == 0, 17);
+
+      mbar_wait(&mbar[MB_AG], parb);  // update t's targets are known everywhere: forward(t) is over in every CTA
+      SRLX_FSTAMP(mt == 0, 18);
+      if (mt == 0 && noisy && upd + 2 < n_updates) {  // ring slot (t+2)%3 was last read by Adam(t-1)
+        uint64_t* nb = &mbar[MB_NZ0 + (upd + 2) % 3];
+        mbar_expect_tx(nb, (uint32_t)nz_bytes);
+        bulk_g2s(nzr + (size_t)((upd + 2) % 3) * 3 * Pl, nz_src(upd + 2), (uint32_t)nz_bytes, nb);
+      }
+      if (rank == 0) {
+        const float* agb = ag + (size_t)parb * B * 8;
+        if (eng.dbg_sample_idx)  // before the sampler reuses s_idx for update t+1
+          for (int i = mt; i < B; i += FNM) eng.dbg_sample_idx[i] = per ? s_idx[i] : (s_idx[i] - cap1);
+        if (per) {
+          // ProportionalMemory.update (proportional_memory.py:171-177), bit-identical to the sequential loop:
+          // per-item change in item order for duplicate leaves ...
+          if (mw == 0) {
+            const bool v = lane < B;
+            const int li = v ? (int)s_idx[lane] : -1 - lane;
+            double pnew = 0.0;
+            if (v) pnew = pow(fabs((double)fabsf(agb[lane * 8 + 4] - agb[lane * 8 + 5])) + eng.per_epsilon, eng.per_alpha);
+            const unsigned mask = __match_any_sync(FULL, li);
+            const unsigned lower = mask & ((1u << lane) - 1u);
+            const int j = lower ? 31 - __clz(lower) : -1;
+            const double prevnew = __shfl_sync(FULL, pnew, j < 0 ? 0 : j);
+            if (v) {
+              const double prev = j >= 0 ? prevnew : s_pri[lane];
+              s_new[lane] = pnew;
+              s_chg[lane] = pnew - prev;
+              if (((mask >> lane) >> 1) == 0) {  // the last item touching a leaf wins
+                __stcg(eng.tree + li, pnew);
+                if (li < pl.n_cache) cache[li] = pnew;
+              }
+            }
+            double mx = pnew;
+            for (int s = 16; s > 0; s >>= 1) mx = fmax(mx, __shfl_xor_sync(FULL, mx, s));
+            if (lane == 0 && mx > sc->max_priority) sc->max_priority = mx;
+          }
+          named_bar_sync(FBAR_MEM, FNM);
+          SRLX_FSTAMP(mt == 0, 19);
+          // ... and every ancestor receives the changes of the items below it in item order: warp per tree level,
+          // lane per item, the first lane of each group of equal nodes applies the whole group.  All loads first.
+          {
+            const int dmax = 63 - __clzll((long long)n_nodes);  // depth of the deepest leaf
+            const bool valid = lane < B;
+            const long long ip1 = valid ? (long long)s_idx[lane] + 1 : 1;
+            const int d = 63 - __clzll(ip1);
+            double v[8];
+            unsigned msk[8];
+            long long nd[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const int a = mw + kFMemWarps * q;
+              nd[q] = -1;
+              msk[q] = 0;
+              v[q] = 0.0;
+              if (a < dmax) {
+                const bool has = valid && d > a;
+                const long long node = has ? (ip1 >> (d - a)) - 1 : -1 - (long long)lane;
+                const unsigned mask = __match_any_sync(FULL, node);
+                if (has && lane == __ffs(mask) - 1) {
+                  nd[q] = node;
+                  msk[q] = mask;
+                  v[q] = (node < (long long)pl.n_cache) ? cache[node] : __ldcg(eng.tree + node);
+                }
+              }
+            }
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              if (nd[q] >= 0) {
+                unsigned m = msk[q];
+                double a = v[q];
+                while (m) {
+                  const int j = __ffs(m) - 1;
+                  m &= m - 1;
+                  a += s_chg[j];
+                }
+                __stcg(eng.tree + nd[q], a);
+                if (nd[q] < (long long)pl.n_cache) cache[nd[q]] = a;
+              }
+            }
+          }
+          named_bar_sync(FBAR_MEM, FNM);
+        }
+        SRLX_FSTAMP(mt == 0, 20);
+        if (upd + 1 < n_updates) sample_and_send(tc + 1, parb ^ 1, upd + 1);
+        SRLX_FSTAMP(mt == 0, 21);
+        // loss, counters, debug taps (off the critical path)
+        if (mt == 0) {
+          float l = 0.f;
+          for (int i = 0; i < B; ++i) l += agb[i * 8 + 6];
+          const double ld = (double)l / (double)B;
+          sc->last_loss = ld;
+          sc->loss_sum += ld;
+          if ((tc % (uint64_t)eng.target_update_interval) == 0) sc->sync_count += 1;
+        }
+        if (eng.dbg_target_q)
+          for (int i = mt; i < B; i += FNM) eng.dbg_target_q[i] = agb[i * 8 + 4];
+        if (eng.dbg_q_sa)
+          for (int i = mt; i < B; i += FNM) eng.dbg_q_sa[i] = agb[i * 8 + 5];
+        if (eng.dbg_weights)
+          for (int i = mt; i < B; i += FNM) eng.dbg_weights[i] = samp_w[parb * pl.B4 + i];
+        if (eng.dbg_windows) {
+          float* dw = eng.dbg_windows;
+          const int n_states = B * (M + 1) * D;
+          for (int w = mt; w < n_states; w += FNM) {
+            const int i = w / ((M + 1) * D), rem = w - i * (M + 1) * D, k = rem / D, d = rem - k * D;
+            dw[w] = (k == 0) ? x_cur[(size_t)i * 4 + d] : x_cur[(size_t)(B + i * M + k - 1) * 4 + d];
+          }
+          for (int w = mt; w < BM; w += FNM) {
+            dw[n_states + w] = (float)w_act[w];
+            dw[n_states + BM + w] = w_rew[w];
+            dw[n_states + 2 * BM + w] = w_term[w];
+          }
+        }
+      }
+    }
+  }
+
+  // ---- write back: parameters, Adam moments, target copy, counters ----------------------------------------------------
+  __syncthreads();
+  for (int s = 0; s < n_seg; ++s) {
+    const FSeg sg = segs[s];
+    if (sg.replicated && rank != 0) continue;
+    for (int j = tid; j < sg.n; j += FNT) {
+      const int p = sg.g0 + j, i = sg.l0 + j;
+      __stcg(eng.params + p, p_mu[i]);
+      __stcg(eng.target + p, p_tmu[i]);
+      __stcg(eng.adam_m + p, p_m1[i]);
+      __stcg(eng.adam_v + p, p_v1[i]);
+      if (noisy) {
+        __stcg(eng.params_sigma + p, p_sg[i]);
+        __stcg(eng.target_sigma + p, p_tsg[i]);
+        __stcg(eng.adam_m + net.n_params + p, p_m2[i]);
+        __stcg(eng.adam_v + net.n_params + p, p_v2[i]);
+      }
+    }
+  }
+  if (rank == 0 && tid == 0) {
+    st->train_count = tc0 + n_updates;
+    st->adam_step = adam0 + n_updates;
+    st->max_priority = sc->max_priority;
+    st->sample_retries += sc->retries;
+    st->last_loss = sc->last_loss;
+    st->loss_sum += sc->loss_sum;
+    st->sync_count += sc->sync_count;
+  }
+  cluster.sync();  // no CTA may exit while a peer can still address its shared memory
+}
+
+// ---- host side ---------------------------------------------------------------------------------------------------
+static int learn_fast(const srlx_engine* eng, uint32_t n_updates, uintptr_t cuda_stream, int C, int max_smem) {
+  const long long n_nodes = 2ll * eng->ring_rows * eng->n_envs - 1;
+  const FPlan pl = make_fplan(*eng, C, n_nodes);
+  (void)max_smem;
+  SRLX_CHECK_CUDA(cudaFuncSetAttribute(learner_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.total));
+  if (C > 8) SRLX_CHECK_CUDA(cudaFuncSetAttribute(learner_fast_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+  const size_t per_update = (size_t)C * 3 * pl.Pl * 4;
+  uint32_t chunk = kFMaxChunk;
+  if (eng->net.noisy) {
+    const uint64_t fit = eng->noise_scratch_bytes / per_update;
+    if (fit < chunk) chunk = (uint32_t)fit;
+  }
+  if (const char* e = getenv("SRLX_CHUNK")) {
+    const int v = atoi(e);
+    if (v >= 1 && (uint32_t)v < chunk) chunk = (uint32_t)v;
+  }
+  cudaStream_t stream = (cudaStream_t)cuda_stream;
+  for (uint32_t done = 0; done < n_updates;) {
+    const uint32_t n = (n_updates - done) < chunk ? (n_updates - done) : chunk;
+    if (eng->net.noisy) {
+      noise_precompute_kernel<<<n * C, 128, 0, stream>>>(*eng, n, C, pl.Pl, eng->noise_scratch);
+      count_launch();
+      SRLX_CHECK_CUDA(cudaGetLastError());
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)C, 1, 1);
+    cfg.blockDim = dim3(FNT, 1, 1);
+    cfg.dynamicSmemBytes = pl.total;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)C;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    SRLX_CHECK_CUDA(cudaLaunchKernelEx(&cfg, learner_fast_kernel, *eng, n, (const float*)eng->noise_scratch));
+    count_launch();
+    SRLX_CHECK_CUDA(cudaGetLastError());
+    done += n;
+  }
+  return 0;
+}
+
+}  // namespace srlx
+
+extern "C" int srlx_learn(const srlx_engine* eng, uint32_t n_updates, uintptr_t cuda_stream) {
+  using namespace srlx;
+  SRLX_REQUIRE(eng != nullptr, "srlx_learn: eng is NULL");
+  SRLX_REQUIRE(eng->batch_size >= 1 && eng->batch_size <= SRLX_MAX_BATCH, "batch_size %d out of range [1,%d]", eng->batch_size, SRLX_MAX_BATCH);
+  SRLX_REQUIRE(eng->multisteps >= 1 && eng->multisteps <= SRLX_MAX_MULTISTEPS, "multisteps %d out of range", eng->multisteps);
+  SRLX_REQUIRE(eng->n_actions >= 1 && eng->n_actions <= SRLX_MAX_ACTIONS, "n_actions %d out of range", eng->n_actions);
+  SRLX_REQUIRE(eng->net.n_layers >= 2 && eng->net.n_layers <= SRLX_MAX_LAYERS,
+               "the fused learner needs at least one hidden layer (n_layers = %d)", eng->net.n_layers);
+  SRLX_REQUIRE(eng->mem_kind == SRLX_MEM_UNIFORM || eng->tree != nullptr, "proportional memory needs a tree buffer");
+  SRLX_REQUIRE(!eng->net.noisy || (eng->params_sigma && eng->target_sigma), "noisy net needs sigma buffers");
+  SRLX_REQUIRE(eng->state && eng->params && eng->target && eng->adam_m && eng->adam_v, "srlx_learn: parameter buffer is NULL");
+  SRLX_REQUIRE(eng->ring_obs && eng->ring_next_obs && eng->ring_action && eng->ring_reward && eng->ring_term && eng->ring_done,
+               "srlx_learn: ring buffer pointer is NULL");
+  if (n_updates == 0) return 0;
+  // single-hidden-layer networks on small observations take the short-critical-path kernel; everything else the generic one
+  const char* force = getenv("SRLX_LEARNER");
+  const bool want_generic = force && force[0] == 'g';
+  if (!want_generic && fast_shape_ok(*eng)) {
+    int want = 0;
+    if (const char* e = getenv("SRLX_CLUSTER")) want = atoi(e);
+    const int C = fast_pick_cluster(eng->net, want);
+    if (C >= 1) {
+      int dev = 0, max_smem = 0;
+      SRLX_CHECK_CUDA(cudaGetDevice(&dev));
+      SRLX_CHECK_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+      const FPlan pl = make_fplan(*eng, C, 2ll * eng->ring_rows * eng->n_envs - 1);
+      const bool noise_ok = !eng->net.noisy || (eng->noise_scratch && eng->noise_scratch_bytes >= (uint64_t)C * 3 * pl.Pl * 4);
+      if ((long long)pl.total + 1024 <= max_smem && noise_ok) return learn_fast(eng, n_updates, cuda_stream, C, max_smem);
+    }
+  }
+  return learn_generic(eng, n_updates, cuda_stream);
+}

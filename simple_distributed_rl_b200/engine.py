@@ -105,6 +105,9 @@ class DeviceEngine:
         if noisy:
             self.t["params_sigma"] = z(P, torch.float32)
             self.t["target_sigma"] = z(P, torch.float32)
+            # NoisyNet draws of a chunk of trainer updates (csrc/learner_fast.cu): 3 forward calls x P values per update,
+            # sized for 256 updates at a time (L2-resident at the default network)
+            self.t["noise_scratch"] = torch.empty(max(1 << 20, 256 * 3 * (P + 64 * 16)), dtype=torch.float32, device=dev)
         if debug:
             B, M, D, A = self.B, self.M, self.D, self.A
             self.t.update(
@@ -135,6 +138,8 @@ class DeviceEngine:
                   "per_beta_steps", "per_epsilon", "reward_shift", "reward_scale", "huber_delta"):
             setattr(c, k, float(getattr(cfg, k)))
         c.net = self.spec.to_c()
+        if "noise_scratch" in self.t:
+            c.noise_scratch_bytes = self.t["noise_scratch"].numel() * 4
         for name, _ in _lib.SrlxEngine._fields_:
             if name in self.t:
                 setattr(c, name, self.t[name].data_ptr())
