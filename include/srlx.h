@@ -165,7 +165,7 @@ typedef struct srlx_engine {
   float* dbg_q_sa;          /* [B] */
   float* dbg_grads;         /* [n_params*(1+noisy)] gradient of the last update */
   float* dbg_windows;       /* [B][M+1][D] states, then [B][M] (action, reward, term) as floats */
-  long long* dbg_clock;     /* [32] clock64() stamps of the learner phases of the second-to-last update of a launch (CTA 0):
+  long long* dbg_clock;     /* [64] clock64() stamps of the learner phases of the second-to-last update of a launch (CTA 0):
                                [0..7] compute warps, [16..24] aux / memory warps; see learner.cu, learner_fast.cu */
   /* ---- scratch (caller-owned) ---- */
   float* noise_scratch;     /* NoisyNet draws of a chunk of updates, precomputed by all SMs and streamed by the learner
@@ -220,6 +220,9 @@ int srlx_engine_reset(const srlx_engine* eng, uintptr_t cuda_stream);
  * updates_per_step trainer updates }.  training==0: evaluation rollouts (test_epsilon in eng->epsilon, nothing stored). */
 int srlx_engine_run(const srlx_engine* eng, uint32_t n_steps, uint32_t updates_per_step, int training,
                     uintptr_t cuda_stream);
+/* Which kernel srlx_learn runs for this engine: 1 = the short-critical-path kernel for single-hidden-layer networks
+ * (csrc/learner_fast.cu; *cluster_size CTAs, *smem_bytes of shared memory each), 0 = the generic kernel (csrc/learner.cu). */
+int srlx_learner_info(const srlx_engine* eng, int* cluster_size, size_t* smem_bytes);
 /* The two halves separately (parity tests drive them one at a time). */
 int srlx_vec_step(const srlx_engine* eng, int training, uintptr_t cuda_stream);
 int srlx_learn(const srlx_engine* eng, uint32_t n_updates, uintptr_t cuda_stream);

@@ -108,6 +108,7 @@ SYMBOLS = [
     ("srlx_engine_run", C.c_int, [C.POINTER(SrlxEngine), _u32, _u32, _i32, _uptr]),
     ("srlx_vec_step", C.c_int, [C.POINTER(SrlxEngine), _i32, _uptr]),
     ("srlx_learn", C.c_int, [C.POINTER(SrlxEngine), _u32, _uptr]),
+    ("srlx_learner_info", C.c_int, [C.POINTER(SrlxEngine), C.POINTER(C.c_int), C.POINTER(C.c_size_t)]),
     ("srlx_qnet_forward", C.c_int, [C.POINTER(SrlxEngine), _i32, _P, _u32, _u64, _P, _uptr]),
 ]
 

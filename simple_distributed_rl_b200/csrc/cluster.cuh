@@ -43,6 +43,23 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
   }
 }
+// try_wait with a suspend-time hint: the warp sleeps in hardware until the phase completes (or the hint expires) instead
+// of re-issuing the poll every few dozen cycles -- pollers share the MIO queue with the warps doing the actual work.
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity) {
+  uint32_t ok = 0;
+  const uint32_t addr = smem_u32(bar);
+  do {
+    asm volatile(
+        "{\n"
+        "  .reg .pred p;\n"
+        "  mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2, %3;\n"
+        "  selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity), "r"(20000u)
+        : "memory");
+  } while (!ok);
+}
 
 // generic pointer to the same shared-memory object in CTA `rank` of the cluster
 template <class T>

@@ -32,7 +32,7 @@ int learn_generic(const srlx_engine* eng, uint32_t n_updates, uintptr_t cuda_str
 
 constexpr int kFCmpWarps = 16, kFMemWarps = 4;
 constexpr int FNC = kFCmpWarps * 32, FNM = kFMemWarps * 32, FNT = FNC + FNM;
-constexpr int kFMaxC = 16, kFMaxSeg = 8, kFCacheLevels = 11, kFMaxChunk = 512, kFHld = 33, kFSubLd = 66;
+constexpr int kFMaxC = 16, kFMaxSeg = 8, kFCacheLevels = 12, kFMaxChunk = 512, kFSubLd = 66;
 enum { FBAR_CMP = 1, FBAR_MEM = 2 };
 enum { FSEG_W = 0, FSEG_B = 1, FSEG_O = 2, FSEG_OB = 3 };
 enum { MB_RS = 0, MB_AG, MB_S, MB_WT, MB_XR, MB_NZ0, MB_NZ1, MB_NZ2, MB_COUNT };
@@ -48,7 +48,7 @@ struct FSeg {
 struct FPlan {
   int C, B, M, A, D, K, nout, Uh, Us, nCh, BM, NX, NRq, ipc, rpi, nOwn, Pl, WS, nRG, rpg, B4, n_cache;
   size_t off_mbar, off_seg, off_scal, off_adam, off_gpow, off_gidx, off_slot, off_par, off_nz, off_weff, off_xin, off_meta,
-      off_g, off_hS, off_part, off_rs, off_ag, off_qown, off_rawown, off_samp_slot, off_samp_w, off_sdbl, off_sub, off_cache, total;
+      off_g, off_part, off_rs, off_ag, off_qown, off_rawown, off_samp_slot, off_samp_w, off_sdbl, off_sub, off_cache, total;
 };
 
 __host__ __device__ inline int fast_pick_cluster(const srlx_net& net, int want) {
@@ -129,7 +129,6 @@ __host__ __device__ inline FPlan make_fplan(const srlx_engine& eng, int C, long 
   p.off_xin = take((size_t)2 * p.NX * 16);
   p.off_meta = take((size_t)2 * 3 * p.BM * 4);  // [2][act, rew, term][BM]
   p.off_g = take((size_t)4 * p.BM * 4);         // gathered act / rew / term / done before the padding pass
-  p.off_hS = take((size_t)p.Us * kFHld * 4);
   {
     const size_t a = (size_t)kFCmpWarps * p.NRq * 16, b = (size_t)p.nRG * p.Pl * 4;
     p.off_part = take(a > b ? a : b);
@@ -266,7 +265,6 @@ learner_fast_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_up
   float* g_rew = reinterpret_cast<float*>(smem + pl.off_g) + pl.BM;
   float* g_term = g_rew + pl.BM;
   int* g_done = reinterpret_cast<int*>(g_term + pl.BM);
-  float* hS = reinterpret_cast<float*>(smem + pl.off_hS);       // [Us][33]
   float* part = reinterpret_cast<float*>(smem + pl.off_part);   // [16][NRq][4]  (forward)  /  [nRG][Pl] (backward)
   float* rs = reinterpret_cast<float*>(smem + pl.off_rs);       // [2][C][nOwn][4]
   float* ag = reinterpret_cast<float*>(smem + pl.off_ag);       // [2][B][8]: d(raw)[4], target, q, loss term, -
@@ -331,7 +329,6 @@ learner_fast_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_up
   for (int i = tid; i < 3 * WS; i += FNT) weff[i] = 0.f;
   for (int i = tid; i < 2 * pl.NX * 4; i += FNT) xin[i] = 0.f;
   for (int i = tid; i < 8 * Pl; i += FNT) par[i] = 0.f;
-  for (int i = tid; i < Us * kFHld; i += FNT) hS[i] = 0.f;
   for (int i = tid; i < (int)n_updates && i < kFMaxChunk; i += FNT) {
     const double t = (double)(adam0 + (uint64_t)i + 1);
     adam_ss[i] = (float)(eng.lr / (1.0 - pow(eng.adam_beta1, t)));
@@ -432,8 +429,12 @@ learner_fast_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_up
       }
     };
 
-    if (noisy) mbar_wait(&mbar[MB_NZ0], 0);
+    // Only warp 0 of a group ever polls an mbarrier; the rest of the group blocks on a named barrier (hardware-blocked,
+    // no polling), so waiting warps do not compete with working warps for the MIO queue.
+    if (noisy && cw == 0) mbar_wait_sleep(&mbar[MB_NZ0], 0);
+    named_bar_sync(FBAR_CMP, FNC);
     finish(false, 0, true);
+    if (cw == 0) mbar_wait_sleep(&mbar[MB_XR], 0);  // x(0) gathered by the memory warps
     named_bar_sync(FBAR_CMP, FNC);
 
     const int nActive = min(kFCmpWarps, nCh);
@@ -447,7 +448,6 @@ learner_fast_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_up
         mbar_expect_tx(&mbar[MB_RS], (uint32_t)(C * nIt * rows_sent_per_item * 16));
         mbar_expect_tx(&mbar[MB_AG], (uint32_t)(B * 32));
       }
-      mbar_wait(&mbar[MB_XR], parb);  // x(t) gathered by the memory warps
       SRLX_FSTAMP(ct == 0, 0);
 
       // ---------------------------------------------------------------- forward: warp = 4-unit chunk(s), lane = row
@@ -486,10 +486,6 @@ learner_fast_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_up
             if (omask & 4u) { float2 t = __ffma2_rn(h01, f2(O2.x, O2.y), f2(0.f, 0.f)); t = __ffma2_rn(h23, f2(O2.z, O2.w), t); acc.z = t.x + t.y; }
             if (omask & 8u) { float2 t = __ffma2_rn(h01, f2(O3.x, O3.y), f2(0.f, 0.f)); t = __ffma2_rn(h23, f2(O3.z, O3.w), t); acc.w = t.x + t.y; }
             if (valid) {
-              if (set == 0) {
-                float* hp = hS + (size_t)(ch * 4) * kFHld + r;
-                hp[0] = h01.x; hp[kFHld] = h01.y; hp[2 * kFHld] = h23.x; hp[3 * kFHld] = h23.y;
-              }
               float4* dst = reinterpret_cast<float4*>(mypart + (size_t)(row_base + r) * 4);
               if (!first) { const float4 o = *dst; acc.x += o.x; acc.y += o.y; acc.z += o.z; acc.w += o.w; }
               *dst = acc;
@@ -516,10 +512,11 @@ learner_fast_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_up
         const float* dst = rs + (((size_t)parb * C + rank) * pl.nOwn + ii * rpi + j) * 4;
         st_async_f4(mapa_u32(smem_u32(dst), (uint32_t)c), v, mapa_u32(mb_rs, (uint32_t)c));
       }
-      mbar_wait(&mbar[MB_RS], parb);
+      if (cw == 0) {  // the owner work is one warp's worth: warp 0 does it, the other warps go straight to the AG barrier
+      mbar_wait_sleep(&mbar[MB_RS], parb);
       SRLX_FSTAMP(ct == 0, 2);
       // ---------------------------------------------------------------- owner: sum the C partials, dueling combine
-      for (int w = ct; w < nIt * rpi; w += FNC) {
+      for (int w = lane; w < nIt * rpi; w += 32) {
         const int ii = w / rpi, j = w - ii * rpi;
         const int set = j == 0 ? 0 : (j <= M ? 1 : 2);
         if (set == 1 && !need_online_next) continue;
@@ -528,32 +525,40 @@ learner_fast_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_up
           const float4 o = ld4(rs + (((size_t)parb * C + c) * pl.nOwn + w) * 4);
           v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
         }
+        // (fixed-bound unrolled loops keep raw/q in registers: A <= 4, nout <= 4)
         const float raw[4] = {v.x, v.y, v.z, v.w};
         float q[4] = {0.f, 0.f, 0.f, 0.f};
         if (net.dueling == SRLX_DUEL_NONE) {
-          for (int a = 0; a < A; ++a) q[a] = raw[a];
+#pragma unroll
+          for (int a = 0; a < 4; ++a) q[a] = raw[a];
         } else {
           float red = 0.f;
           if (net.dueling == SRLX_DUEL_AVERAGE) {
-            for (int a = 0; a < A; ++a) red += raw[1 + a];
+#pragma unroll
+            for (int a = 0; a < 3; ++a)
+              if (a < A) red += raw[1 + a];
             red = red / (float)A;
           } else if (net.dueling == SRLX_DUEL_MAX) {
             red = raw[1];
-            for (int a = 1; a < A; ++a) red = fmaxf(red, raw[1 + a]);
+#pragma unroll
+            for (int a = 1; a < 3; ++a)
+              if (a < A) red = fmaxf(red, raw[1 + a]);
           }
-          for (int a = 0; a < A; ++a) q[a] = raw[0] + raw[1 + a] - red;
+#pragma unroll
+          for (int a = 0; a < 3; ++a)
+            if (a < A) q[a] = raw[0] + raw[1 + a] - red;
         }
         *reinterpret_cast<float4*>(qown + (size_t)w * 4) = make_float4(q[0], q[1], q[2], q[3]);
         if (set == 0) *reinterpret_cast<float4*>(rawown + (size_t)ii * 4) = v;
       }
-      named_bar_sync(FBAR_CMP, FNC);
+      __syncwarp();
       SRLX_FSTAMP(ct == 0, 6);
-      mbar_wait(&mbar[MB_WT], parb);  // IS weights of this batch
+      mbar_wait_sleep(&mbar[MB_WT], parb);  // IS weights of this batch
       SRLX_FSTAMP(ct == 0, 7);
       if (ct == 0 && upd + 1 < n_updates) mbar_expect_tx(&mbar[MB_WT], (uint32_t)pl.B4 * 4);
       // ---------------------------------------------------------------- owner: targets, Huber gradient (thread per item)
-      if (ct < nIt) {
-        const int ii = ct, i = rank * ipc + ii;
+      for (int ii = lane; ii < nIt; ii += 32) {
+        const int i = rank * ipc + ii;
         const float* qs = qown + (size_t)(ii * rpi) * 4;
         const float* qon = qs + 4;             // online(s')  [M][4]
         const float* qtg = qs + 4 * (1 + M);   // target(s')  [M][4]
@@ -588,7 +593,8 @@ learner_fast_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_up
         const float dq = fminf(fmaxf(d, -delta), delta) * w / (float)B;
         float dr[4] = {0.f, 0.f, 0.f, 0.f};
         if (net.dueling == SRLX_DUEL_NONE) {
-          dr[a0] = dq;
+#pragma unroll
+          for (int a = 0; a < 4; ++a) dr[a] = (a == a0) ? dq : 0.f;
         } else {  // dueling combine backward (dueling_network.py:51-58)
           int amax = 0;
           if (net.dueling == SRLX_DUEL_MAX) {
@@ -597,11 +603,14 @@ learner_fast_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_up
             for (int a = 1; a < A; ++a)
               if (rw[1 + a] > bestr) { bestr = rw[1 + a]; amax = a; }
           }
-          for (int a = 0; a < A; ++a) {
-            float dd = (a == a0) ? dq : 0.f;
-            if (net.dueling == SRLX_DUEL_AVERAGE) dd -= dq / (float)A;
-            else if (net.dueling == SRLX_DUEL_MAX && a == amax) dd -= dq;
-            dr[1 + a] = dd;
+#pragma unroll
+          for (int a = 0; a < 3; ++a) {
+            if (a < A) {
+              float dd = (a == a0) ? dq : 0.f;
+              if (net.dueling == SRLX_DUEL_AVERAGE) dd -= dq / (float)A;
+              else if (net.dueling == SRLX_DUEL_MAX && a == amax) dd -= dq;
+              dr[1 + a] = dd;
+            }
           }
           dr[0] = dq;
         }
@@ -614,7 +623,9 @@ learner_fast_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_up
         }
       }
       SRLX_FSTAMP(ct == 0, 8);
-      mbar_wait(&mbar[MB_AG], parb);
+      mbar_wait_sleep(&mbar[MB_AG], parb);
+      }
+      named_bar_sync(FBAR_CMP, FNC);
       SRLX_FSTAMP(ct == 0, 3);
       // ---------------------------------------------------------------- backward of this CTA's slice: thread = (unit, row group)
       {
@@ -624,12 +635,17 @@ learner_fast_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_up
           const int rg = it / Us, u = it - rg * Us;
           const float* wo = wS + nCh * 20 + (u >> 2) * 16 + (u & 3);
           const float wo0 = wo[0], wo1 = wo[4], wo2 = wo[8], wo3 = wo[12];
+          // the hidden activation is recomputed (4 FMAs) instead of being staged through shared memory by the forward
+          const float* wi = wS + (u >> 2) * 16 + (u & 3);
+          const float wi0 = wi[0], wi1 = wi[4], wi2 = wi[8], wi3 = wi[12], bi = wS[nCh * 16 + u];
           float gW0 = 0.f, gW1 = 0.f, gW2 = 0.f, gW3 = 0.f, gb = 0.f, gO0 = 0.f, gO1 = 0.f, gO2 = 0.f, gO3 = 0.f;
           const int r0 = rg * pl.rpg, r1 = min(B, r0 + pl.rpg);
           for (int r = r0; r < r1; ++r) {
             const float4 dr = ld4(agb + (size_t)r * 8);
-            const float h = hS[(size_t)u * kFHld + r];
             const float4 x = ld4(x_cur + (size_t)r * 4);
+            float h = fmaf(wi0, x.x, bi);  // same operation order as the forward (FFMA2 lanes are plain fp32 FMAs)
+            h = fmaf(wi1, x.y, h); h = fmaf(wi2, x.z, h); h = fmaf(wi3, x.w, h);
+            h = fmaxf(h, 0.f);
             float d = dr.x * wo0;
             d = fmaf(dr.y, wo1, d); d = fmaf(dr.z, wo2, d); d = fmaf(dr.w, wo3, d);
             const float dh = h > 0.f ? d : 0.f;
@@ -655,14 +671,15 @@ learner_fast_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_up
           part[(size_t)rg * Pl + segs[n_seg - 1].l0 + o] = a;
         }
       }
+      const bool more = upd + 1 < n_updates;
+      if (noisy && more && cw == 0) mbar_wait_sleep(&mbar[MB_NZ0 + (upd + 1) % 3], ((upd + 1) / 3) & 1);
       named_bar_sync(FBAR_CMP, FNC);
       SRLX_FSTAMP(ct == 0, 4);
       // ---------------------------------------------------------------- Adam + target sync + next effective weights
-      const bool more = upd + 1 < n_updates;
-      if (noisy && more) mbar_wait(&mbar[MB_NZ0 + (upd + 1) % 3], ((upd + 1) / 3) & 1);
       finish(true, upd, more);
-      named_bar_sync(FBAR_CMP, FNC);
       SRLX_FSTAMP(ct == 0, 5);
+      if (more && cw == 0) mbar_wait_sleep(&mbar[MB_XR], parb ^ 1);  // x(t+1) gathered by the memory warps
+      named_bar_sync(FBAR_CMP, FNC);
     }
   } else {
     // ================================================= MEMORY WARPS =================================================
@@ -709,22 +726,26 @@ learner_fast_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_up
         const int k_l = 32 - __clz(lane + 1);         // level (1..5) whose nodes this lane fetches; lane 31 idles
         const int q_l = lane + 1 - (1 << (k_l - 1));  // parent position inside level k_l - 1
         const int pos_l = (1 << k_l) - 2 + 2 * q_l;
+        int rnd = 0;
         while (__any_sync(FULL, !done)) {
           double v0[8], v1[8];
+          // unconditional loads from clamped addresses (a predicated load + select makes ptxas wait for every load in
+          // turn): nodes past the end of the tree or below finished samples are fetched but never looked at
 #pragma unroll
           for (int g = 0; g < 8; ++g) {
             const int ig = __shfl_sync(FULL, idx, g);
-            const int dg = __shfl_sync(FULL, (int)done, g);
-            const int64_t node = (((int64_t)ig + 1) << k_l) - 1 + 2 * q_l;
-            const bool ld = lane < 31 && !dg;
-            v0[g] = (ld && node < n_nodes) ? __ldcg(eng.tree + node) : 0.0;
-            v1[g] = (ld && node + 1 < n_nodes) ? __ldcg(eng.tree + node + 1) : 0.0;
+            int64_t node = (((int64_t)ig + 1) << k_l) - 1 + 2 * q_l;
+            node = node < n_nodes - 1 ? node : (n_nodes > 1 ? n_nodes - 2 : 0);
+            v0[g] = __ldcg(eng.tree + node);
+            v1[g] = __ldcg(eng.tree + (n_nodes > 1 ? node + 1 : 0));
           }
+          if (rnd < 3) SRLX_SSTAMP(32 + rnd * 4);
           if (lane < 31) {
 #pragma unroll
             for (int g = 0; g < 8; ++g) *reinterpret_cast<double2*>(wsub + g * kFSubLd + pos_l) = make_double2(v0[g], v1[g]);
           }
           __syncwarp();
+          if (rnd < 3) SRLX_SSTAMP(33 + rnd * 4);
           if (!done) {
             const double* ms = wsub + lane * kFSubLd;
             int rel = 0;
@@ -741,6 +762,8 @@ learner_fast_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_up
             done = 2 * (int64_t)idx + 1 >= n_nodes;
           }
           __syncwarp();
+          if (rnd < 3) SRLX_SSTAMP(34 + rnd * 4);
+          ++rnd;
         }
         SRLX_SSTAMP(23);
         if (own) {  // a zero-priority leaf is re-drawn (proportional_memory.py:150-152), sequentially
@@ -854,31 +877,46 @@ learner_fast_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_up
       float* w_rew = meta + (size_t)parb * 3 * BM + BM;
       float* w_term = w_rew + BM;
       const int* slot = samp_slot + parb * pl.B4;
-      mbar_wait(&mbar[MB_S], parb);  // slots of update t have arrived from CTA 0
+      if (mw == 0) mbar_wait_sleep(&mbar[MB_S], parb);  // slots of update t have arrived from CTA 0
+      named_bar_sync(FBAR_MEM, FNM);
       SRLX_FSTAMP(mt == 0, 16);
       // ---------------------------------------------------------------- gather the windows (one memory round trip)
-      for (int w = mt; w < BM; w += FNM) {
-        const int i = w / M, k = w - i * M;
-        const int s0 = slot[i];
-        const int rho = s0 / E, e = s0 - rho * E;
-        const int sk = ((rho + k) % R) * E + e;
-        g_act[w] = __ldcg(eng.ring_action + sk);
-        g_rew[w] = __ldcg(eng.ring_reward + sk);
-        g_term[w] = (float)__ldcg(eng.ring_term + sk);
-        g_done[w] = (int)__ldcg(eng.ring_done + sk);
-        float* xr = x_cur + (size_t)(B + w) * 4;
-        if (D == 4) {
-          *reinterpret_cast<float4*>(xr) = __ldcg(reinterpret_cast<const float4*>(eng.ring_next_obs + (size_t)sk * 4));
+      for (int w = mt; w < BM + B; w += FNM) {
+        if (w < BM) {
+          const int i = w / M, k = w - i * M;
+          const int s0 = slot[i];
+          const int rho = s0 / E, e = s0 - rho * E;
+          const int sk = ((rho + k) % R) * E + e;
+          // every load of this thread is issued before the first dependent store
+          const int a = __ldcg(eng.ring_action + sk);
+          const float rw = __ldcg(eng.ring_reward + sk);
+          const unsigned char tm = __ldcg(eng.ring_term + sk), dn = __ldcg(eng.ring_done + sk);
+          float4 xv = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (D == 4) {
+            xv = __ldcg(reinterpret_cast<const float4*>(eng.ring_next_obs + (size_t)sk * 4));
+          } else {
+            const float* src = eng.ring_next_obs + (size_t)sk * D;
+            xv.x = __ldcg(src);
+            if (D > 1) xv.y = __ldcg(src + 1);
+            if (D > 2) xv.z = __ldcg(src + 2);
+          }
+          g_act[w] = a;
+          g_rew[w] = rw;
+          g_term[w] = (float)tm;
+          g_done[w] = (int)dn;
+          *reinterpret_cast<float4*>(x_cur + (size_t)(B + w) * 4) = xv;
         } else {
-          for (int d = 0; d < D; ++d) xr[d] = __ldcg(eng.ring_next_obs + (size_t)sk * D + d);
-        }
-      }
-      for (int i = mt; i < B; i += FNM) {
-        float* xr = x_cur + (size_t)i * 4;
-        if (D == 4) {
-          *reinterpret_cast<float4*>(xr) = __ldcg(reinterpret_cast<const float4*>(eng.ring_obs + (size_t)slot[i] * 4));
-        } else {
-          for (int d = 0; d < D; ++d) xr[d] = __ldcg(eng.ring_obs + (size_t)slot[i] * D + d);
+          const int i = w - BM;
+          float4 xv = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (D == 4) {
+            xv = __ldcg(reinterpret_cast<const float4*>(eng.ring_obs + (size_t)slot[i] * 4));
+          } else {
+            const float* src = eng.ring_obs + (size_t)slot[i] * D;
+            xv.x = __ldcg(src);
+            if (D > 1) xv.y = __ldcg(src + 1);
+            if (D > 2) xv.z = __ldcg(src + 2);
+          }
+          *reinterpret_cast<float4*>(x_cur + (size_t)i * 4) = xv;
         }
       }
       named_bar_sync(FBAR_MEM, FNM);
@@ -915,7 +953,8 @@ learner_fast_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_up
       }
       SRLX_FSTAMP(mt == 0, 17);
 
-      mbar_wait(&mbar[MB_AG], parb);  // update t's targets are known everywhere: forward(t) is over in every CTA
+      if (mw == 0) mbar_wait_sleep(&mbar[MB_AG], parb);  // update t's targets are known everywhere: forward(t) is over in every CTA
+      named_bar_sync(FBAR_MEM, FNM);
       SRLX_FSTAMP(mt == 0, 18);
       if (mt == 0 && noisy && upd + 2 < n_updates) {  // ring slot (t+2)%3 was last read by Adam(t-1)
         uint64_t* nb = &mbar[MB_NZ0 + (upd + 2) % 3];
@@ -976,9 +1015,10 @@ learner_fast_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_up
                 if (has && lane == __ffs(mask) - 1) {
                   nd[q] = node;
                   msk[q] = mask;
-                  v[q] = (node < (long long)pl.n_cache) ? cache[node] : __ldcg(eng.tree + node);
                 }
               }
+              // unconditional load (node 0 for non-leaders): the global tree is write-through, so it is current
+              v[q] = __ldcg(eng.tree + (nd[q] >= 0 ? nd[q] : 0));
             }
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
@@ -1110,6 +1150,31 @@ static int learn_fast(const srlx_engine* eng, uint32_t n_updates, uintptr_t cuda
 
 }  // namespace srlx
 
+// Which kernel srlx_learn will run for this engine: 1 = learner_fast_kernel (single hidden layer, <= 4 observation floats,
+// <= 4 outputs, batch <= 32), 0 = the generic learner_kernel; negative = error.
+extern "C" int srlx_learner_info(const srlx_engine* eng, int* cluster_size, size_t* smem_bytes) {
+  using namespace srlx;
+  SRLX_REQUIRE(eng != nullptr, "srlx_learner_info: eng is NULL");
+  if (cluster_size) *cluster_size = 0;
+  if (smem_bytes) *smem_bytes = 0;
+  const char* force = getenv("SRLX_LEARNER");
+  const bool want_generic = force && force[0] == 'g';
+  if (want_generic || !fast_shape_ok(*eng)) return 0;
+  int want = 0;
+  if (const char* e = getenv("SRLX_CLUSTER")) want = atoi(e);
+  const int C = fast_pick_cluster(eng->net, want);
+  if (C < 1) return 0;
+  int dev = 0, max_smem = 0;
+  SRLX_CHECK_CUDA(cudaGetDevice(&dev));
+  SRLX_CHECK_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+  const FPlan pl = make_fplan(*eng, C, 2ll * eng->ring_rows * eng->n_envs - 1);
+  const bool noise_ok = !eng->net.noisy || (eng->noise_scratch && eng->noise_scratch_bytes >= (uint64_t)C * 3 * pl.Pl * 4);
+  if ((long long)pl.total + 1024 > max_smem || !noise_ok) return 0;
+  if (cluster_size) *cluster_size = C;
+  if (smem_bytes) *smem_bytes = pl.total;
+  return 1;
+}
+
 extern "C" int srlx_learn(const srlx_engine* eng, uint32_t n_updates, uintptr_t cuda_stream) {
   using namespace srlx;
   SRLX_REQUIRE(eng != nullptr, "srlx_learn: eng is NULL");
@@ -1124,21 +1189,8 @@ extern "C" int srlx_learn(const srlx_engine* eng, uint32_t n_updates, uintptr_t 
   SRLX_REQUIRE(eng->ring_obs && eng->ring_next_obs && eng->ring_action && eng->ring_reward && eng->ring_term && eng->ring_done,
                "srlx_learn: ring buffer pointer is NULL");
   if (n_updates == 0) return 0;
-  // single-hidden-layer networks on small observations take the short-critical-path kernel; everything else the generic one
-  const char* force = getenv("SRLX_LEARNER");
-  const bool want_generic = force && force[0] == 'g';
-  if (!want_generic && fast_shape_ok(*eng)) {
-    int want = 0;
-    if (const char* e = getenv("SRLX_CLUSTER")) want = atoi(e);
-    const int C = fast_pick_cluster(eng->net, want);
-    if (C >= 1) {
-      int dev = 0, max_smem = 0;
-      SRLX_CHECK_CUDA(cudaGetDevice(&dev));
-      SRLX_CHECK_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-      const FPlan pl = make_fplan(*eng, C, 2ll * eng->ring_rows * eng->n_envs - 1);
-      const bool noise_ok = !eng->net.noisy || (eng->noise_scratch && eng->noise_scratch_bytes >= (uint64_t)C * 3 * pl.Pl * 4);
-      if ((long long)pl.total + 1024 <= max_smem && noise_ok) return learn_fast(eng, n_updates, cuda_stream, C, max_smem);
-    }
-  }
+  int C = 0;
+  size_t smem_bytes = 0;
+  if (srlx_learner_info(eng, &C, &smem_bytes) == 1) return learn_fast(eng, n_updates, cuda_stream, C, 0);
   return learn_generic(eng, n_updates, cuda_stream);
 }

@@ -114,7 +114,7 @@ class DeviceEngine:
                 dbg_q=z((self.E, A), torch.float32), dbg_action=z(self.E, torch.int32), dbg_sample_idx=z(B, torch.int64),
                 dbg_weights=z(B, torch.float32), dbg_target_q=z(B, torch.float32), dbg_q_sa=z(B, torch.float32),
                 dbg_grads=z(P * (2 if noisy else 1), torch.float32), dbg_windows=z(B * (M + 1) * D + 3 * B * M, torch.float32),
-                dbg_clock=z(32, torch.int64),
+                dbg_clock=z(64, torch.int64),
             )
         self.c = self._build_struct()
         # pinned host mirror of the device counters (one small D2H per read)
@@ -164,6 +164,15 @@ class DeviceEngine:
     def learn(self, n_updates=1):
         with torch.cuda.device(self.device):
             _lib.check(self.lib.srlx_learn(C.byref(self.c), int(n_updates), self._stream()))
+
+    def learner_info(self):
+        """(kernel, cluster size, shared-memory bytes per CTA) srlx_learn uses for this engine."""
+        cs, sm = C.c_int(0), C.c_size_t(0)
+        with torch.cuda.device(self.device):
+            rc = self.lib.srlx_learner_info(C.byref(self.c), C.byref(cs), C.byref(sm))
+        if rc < 0:
+            _lib.check(rc)
+        return ("learner_fast_kernel" if rc == 1 else "learner_kernel", cs.value, sm.value)
 
     def run(self, n_steps, updates_per_step, training=True):
         """n_steps x (one vector step of all E envs + updates_per_step trainer updates), no host sync in between."""

@@ -28,8 +28,8 @@ def main():
     ms = e0.elapsed_time(e1)
     c = d.t["dbg_clock"].cpu().numpy().astype("int64")
     base = min(int(x) for x in c if x > 0)
-    rel = {i: int(c[i] - base) for i in range(32) if c[i] > 0}
-    out = {"us_per_update": 1e3 * ms / 1024, "stamps_cycles_rel": rel}
+    rel = {i: int(c[i] - base) for i in range(64) if c[i] > 0}
+    out = {"us_per_update": 1e3 * ms / 1024, "learner": d.learner_info(), "stamps_cycles_rel": rel}
     print(json.dumps(out))
 
 
