@@ -48,7 +48,7 @@ struct FSeg {
 struct FPlan {
   int C, B, M, A, D, K, nout, Uh, Us, nCh, BM, NX, NRq, ipc, rpi, nOwn, Pl, WS, nRG, rpg, B4, n_cache;
   size_t off_mbar, off_seg, off_scal, off_adam, off_gpow, off_gidx, off_slot, off_par, off_nz, off_weff, off_xin, off_meta,
-      off_g, off_part, off_rs, off_ag, off_qown, off_rawown, off_samp_slot, off_samp_w, off_sdbl, off_sub, off_cache, total;
+      off_part, off_rs, off_ag, off_qown, off_rawown, off_samp_slot, off_samp_w, off_sdbl, off_sub, off_cache, total;
 };
 
 __host__ __device__ inline int fast_pick_cluster(const srlx_net& net, int want) {
@@ -86,7 +86,7 @@ __host__ __device__ inline bool fast_shape_ok(const srlx_engine& eng) {
   const srlx_net& net = eng.net;
   return net.n_layers == 2 && eng.obs_dim >= 1 && eng.obs_dim <= 4 && net.k_dim[0] == eng.obs_dim && net.out_dim[1] <= 4 &&
          eng.n_actions <= 4 && eng.batch_size >= 1 && eng.batch_size <= 32 && eng.multisteps >= 1 &&
-         eng.multisteps <= SRLX_MAX_MULTISTEPS && (2ll * eng.ring_rows * eng.n_envs) < (1ll << 31);
+         eng.multisteps <= SRLX_MAX_MULTISTEPS && (2ll * eng.ring_rows * eng.n_envs) < (1ll << 27);
 }
 
 __host__ __device__ inline FPlan make_fplan(const srlx_engine& eng, int C, long long n_tree_nodes) {
@@ -128,7 +128,6 @@ __host__ __device__ inline FPlan make_fplan(const srlx_engine& eng, int C, long 
   p.off_weff = take((size_t)3 * p.WS * 4);
   p.off_xin = take((size_t)2 * p.NX * 16);
   p.off_meta = take((size_t)2 * 3 * p.BM * 4);  // [2][act, rew, term][BM]
-  p.off_g = take((size_t)4 * p.BM * 4);         // gathered act / rew / term / done before the padding pass
   {
     const size_t a = (size_t)kFCmpWarps * p.NRq * 16, b = (size_t)p.nRG * p.Pl * 4;
     p.off_part = take(a > b ? a : b);
@@ -139,7 +138,7 @@ __host__ __device__ inline FPlan make_fplan(const srlx_engine& eng, int C, long 
   p.off_rawown = take((size_t)p.ipc * 16);
   p.off_samp_slot = take((size_t)2 * p.B4 * 4);
   p.off_samp_w = take((size_t)2 * p.B4 * 4);
-  p.off_sdbl = take((size_t)6 * 32 * 8);  // s_idx (i64), s_pri, s_new, s_chg, s_val, s_tmp
+  p.off_sdbl = take(2048);  // s_idx, s_att, sperm[4][32] (int), then s_pri, s_tmp (double)
   p.n_cache = 0;
   if (eng.mem_kind == SRLX_MEM_PROPORTIONAL) {
     p.off_sub = take((size_t)kFMemWarps * 8 * kFSubLd * 8);
@@ -234,14 +233,17 @@ __global__ void __launch_bounds__(128) noise_precompute_kernel(const __grid_cons
 }
 
 // =====================================================================================================================
+// FLAG = true: the reference's Rainbow default shape (batch 32, 3-step, 2 actions, 4 observation floats, dueling-average
+// head of 2 x 512 units over 8 CTAs) with every loop bound a compile-time constant; FLAG = false: same code, run-time bounds.
+template <bool FLAG>
 __global__ void __launch_bounds__(FNT, 1)
 learner_fast_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_updates, const float* __restrict__ noise) {
   extern __shared__ __align__(16) unsigned char smem[];
   cg::cluster_group cluster = cg::this_cluster();
-  const int C = (int)cluster.num_blocks();
+  const int C = FLAG ? 8 : (int)cluster.num_blocks();
   const int rank = (int)cluster.block_rank();
   const srlx_net& net = eng.net;
-  const int64_t cap = (int64_t)eng.ring_rows * eng.n_envs, n_nodes = 2 * cap - 1;
+  const int cap = eng.ring_rows * eng.n_envs, n_nodes = 2 * cap - 1, cap1 = cap - 1;
   const FPlan pl = make_fplan(eng, C, n_nodes);
 
   uint64_t* mbar = reinterpret_cast<uint64_t*>(smem + pl.off_mbar);
@@ -255,16 +257,13 @@ learner_fast_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_up
   int* gidx = reinterpret_cast<int*>(smem + pl.off_gidx);
   int* slot_t = reinterpret_cast<int*>(smem + pl.off_slot);
   float* par = reinterpret_cast<float*>(smem + pl.off_par);
-  float *p_mu = par, *p_sg = par + pl.Pl, *p_m1 = par + 2 * pl.Pl, *p_v1 = par + 3 * pl.Pl, *p_m2 = par + 4 * pl.Pl,
-        *p_v2 = par + 5 * pl.Pl, *p_tmu = par + 6 * pl.Pl, *p_tsg = par + 7 * pl.Pl;
+  const int Pl = FLAG ? 1028 : pl.Pl;
+  float *p_mu = par, *p_sg = par + Pl, *p_m1 = par + 2 * Pl, *p_v1 = par + 3 * Pl, *p_m2 = par + 4 * Pl,
+        *p_v2 = par + 5 * Pl, *p_tmu = par + 6 * Pl, *p_tsg = par + 7 * Pl;
   float* nzr = reinterpret_cast<float*>(smem + pl.off_nz);      // [3 ring][3 set][Pl]
   float* weff = reinterpret_cast<float*>(smem + pl.off_weff);   // [3][WS]
   float* xin = reinterpret_cast<float*>(smem + pl.off_xin);     // [2][NX][4]
   float* meta = reinterpret_cast<float*>(smem + pl.off_meta);   // [2][3][BM]
-  int* g_act = reinterpret_cast<int*>(smem + pl.off_g);
-  float* g_rew = reinterpret_cast<float*>(smem + pl.off_g) + pl.BM;
-  float* g_term = g_rew + pl.BM;
-  int* g_done = reinterpret_cast<int*>(g_term + pl.BM);
   float* part = reinterpret_cast<float*>(smem + pl.off_part);   // [16][NRq][4]  (forward)  /  [nRG][Pl] (backward)
   float* rs = reinterpret_cast<float*>(smem + pl.off_rs);       // [2][C][nOwn][4]
   float* ag = reinterpret_cast<float*>(smem + pl.off_ag);       // [2][B][8]: d(raw)[4], target, q, loss term, -
@@ -272,19 +271,25 @@ learner_fast_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_up
   float* rawown = reinterpret_cast<float*>(smem + pl.off_rawown);
   int* samp_slot = reinterpret_cast<int*>(smem + pl.off_samp_slot);
   float* samp_w = reinterpret_cast<float*>(smem + pl.off_samp_w);
-  int64_t* s_idx = reinterpret_cast<int64_t*>(smem + pl.off_sdbl);
-  double* s_pri = reinterpret_cast<double*>(smem + pl.off_sdbl) + 32;
-  double *s_new = s_pri + 32, *s_chg = s_pri + 64, *s_val = s_pri + 96, *s_tmp = s_pri + 128;
+  int* s_idx = reinterpret_cast<int*>(smem + pl.off_sdbl);  // tree index of each sampled item (slot + cap - 1)
+  int* s_att = s_idx + 32;
+  int* sperm = s_idx + 64;                                  // [4 warps][32]
+  double* s_pri = reinterpret_cast<double*>(smem + pl.off_sdbl + 1024);
+  double* s_tmp = s_pri + 32;
   double* sub = reinterpret_cast<double*>(smem + pl.off_sub);
   double* cache = reinterpret_cast<double*>(smem + pl.off_cache);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int B = pl.B, M = pl.M, A = pl.A, D = pl.D, K = pl.K, E = eng.n_envs, R = eng.ring_rows, BM = pl.BM;
-  const int Us = pl.Us, nout = pl.nout, nCh = pl.nCh, Pl = pl.Pl, WS = pl.WS, rpi = pl.rpi, ipc = pl.ipc;
+  const int B = FLAG ? 32 : pl.B, M = FLAG ? 3 : pl.M, A = FLAG ? 2 : pl.A, D = FLAG ? 4 : pl.D, K = D;
+  const int E = eng.n_envs, R = eng.ring_rows, BM = B * M, NRq = B + 2 * BM, NX = B + BM, B4 = FLAG ? 32 : pl.B4;
+  const int Us = FLAG ? 128 : pl.Us, nout = FLAG ? 3 : pl.nout, nCh = Us / 4, WS = nCh * 36 + 4, rpi = 1 + 2 * M;
+  const int ipc = FLAG ? 4 : pl.ipc, nOwn = ipc * rpi, nRG = FLAG ? 4 : pl.nRG, rpg = FLAG ? 8 : pl.rpg;
+  const int dueling = FLAG ? (int)SRLX_DUEL_AVERAGE : net.dueling;
+  const int n_cache = pl.n_cache;
   const int u0 = rank * Us;
   const bool per = eng.mem_kind == SRLX_MEM_PROPORTIONAL;
   const bool noisy = net.noisy != 0;
-  const bool need_online_next = eng.enable_double_dqn || M > 1;
+  const bool need_online_next = FLAG ? true : (eng.enable_double_dqn || M > 1);
   const int rows_sent_per_item = 1 + M + (need_online_next ? M : 0);
   const int nIt = max(0, min(ipc, B - rank * ipc));  // batch items this CTA owns: [rank*ipc, rank*ipc + nIt)
   srlx_state* st = eng.state;
@@ -307,8 +312,8 @@ learner_fast_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_up
     mbar_init(&mbar[MB_NZ1], 1);
     mbar_init(&mbar[MB_NZ2], 1);
     fence_mbar_init();
-    mbar_expect_tx(&mbar[MB_S], (uint32_t)pl.B4 * 4);
-    mbar_expect_tx(&mbar[MB_WT], (uint32_t)pl.B4 * 4);
+    mbar_expect_tx(&mbar[MB_S], (uint32_t)B4 * 4);
+    mbar_expect_tx(&mbar[MB_WT], (uint32_t)B4 * 4);
     if (noisy) {
       mbar_expect_tx(&mbar[MB_NZ0], (uint32_t)nz_bytes);
       bulk_g2s(nzr, nz_src(0), (uint32_t)nz_bytes, &mbar[MB_NZ0]);
@@ -327,7 +332,7 @@ learner_fast_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_up
     sc->max_priority = st->max_priority;
   }
   for (int i = tid; i < 3 * WS; i += FNT) weff[i] = 0.f;
-  for (int i = tid; i < 2 * pl.NX * 4; i += FNT) xin[i] = 0.f;
+  for (int i = tid; i < 2 * NX * 4; i += FNT) xin[i] = 0.f;
   for (int i = tid; i < 8 * Pl; i += FNT) par[i] = 0.f;
   for (int i = tid; i < (int)n_updates && i < kFMaxChunk; i += FNT) {
     const double t = (double)(adam0 + (uint64_t)i + 1);
@@ -336,7 +341,7 @@ learner_fast_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_up
   }
   if (tid < M) gpow[tid] = (float)pow(eng.discount, (double)tid);
   if (rank == 0)
-    for (int i = tid; i < pl.n_cache; i += FNT) cache[i] = __ldcg(eng.tree + i);
+    for (int i = tid; i < n_cache; i += FNT) cache[i] = __ldcg(eng.tree + i);
   __syncthreads();
   const int n_seg = *n_seg_p, n_used = *n_used_p;
   for (int s = 0; s < n_seg; ++s) {
@@ -373,6 +378,7 @@ learner_fast_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_up
 
   const uint32_t mb_rs = smem_u32(&mbar[MB_RS]), mb_ag = smem_u32(&mbar[MB_AG]), mb_s = smem_u32(&mbar[MB_S]),
                  mb_wt = smem_u32(&mbar[MB_WT]);
+  const unsigned FULL = 0xffffffffu;
 
   // ==================================================================================================================
   if (warp < kFCmpWarps) {
@@ -395,7 +401,7 @@ learner_fast_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_up
         float mu = p_mu[i], sgm = nz ? p_sg[i] : 0.f;
         if (do_adam) {
           float g = 0.f;
-          for (int rg = 0; rg < pl.nRG; ++rg) g += part[(size_t)rg * Pl + i];
+          for (int rg = 0; rg < nRG; ++rg) g += part[(size_t)rg * Pl + i];
           float m = p_m1[i], v = p_v1[i];
           // torch/optim/adam.py _single_tensor_adam: lerp, mul_/addcmul_, sqrt/div/add_, addcdiv_
           m = m + (g - m) * (1.0f - b1);
@@ -440,7 +446,7 @@ learner_fast_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_up
     const int nActive = min(kFCmpWarps, nCh);
     for (uint32_t upd = 0; upd < n_updates; ++upd) {
       const int parb = upd & 1;
-      const float* x_cur = xin + (size_t)parb * pl.NX * 4;
+      const float* x_cur = xin + (size_t)parb * NX * 4;
       const int* w_act = reinterpret_cast<const int*>(meta + (size_t)parb * 3 * BM);
       const float* w_rew = meta + (size_t)parb * 3 * BM + BM;
       const float* w_term = w_rew + BM;
@@ -453,12 +459,12 @@ learner_fast_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_up
       // ---------------------------------------------------------------- forward: warp = 4-unit chunk(s), lane = row
       for (int ch = cw; ch < nCh; ch += kFCmpWarps) {
         const bool first = ch < kFCmpWarps;
-        float* mypart = part + (size_t)cw * pl.NRq * 4;
+        float* mypart = part + (size_t)cw * NRq * 4;
         unsigned omask = 0;
         {
           const int ua = u0 + ch * 4, ub = ua + 4;
           for (int o = 0; o < nout; ++o) {
-            const int koff = (net.dueling != SRLX_DUEL_NONE && o > 0) ? net.k_dim[1] : 0;
+            const int koff = (dueling != SRLX_DUEL_NONE && o > 0) ? net.k_dim[1] : 0;
             if (ua < koff + net.k_dim[1] && ub > koff) omask |= 1u << o;
           }
         }
@@ -496,134 +502,160 @@ learner_fast_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_up
       named_bar_sync(FBAR_CMP, FNC);
       SRLX_FSTAMP(ct == 0, 1);
       // ---------------------------------------------------------------- reduce over warps, scatter to the owning CTA
-      for (int row = ct; row < pl.NRq; row += FNC) {
+      // two threads per row (each sums half of the warp copies), combined with one shuffle
+      for (int wb = cw * 32; wb < 2 * NRq; wb += FNC) {  // whole warps iterate (shuffles below); NRq <= 288 -> one pass
+        const int w2 = wb + lane;
+        const int row = min(w2 >> 1, NRq - 1), half = w2 & 1;  // an (even, odd) lane pair shares a row
         int item, j;
+        bool send = w2 < 2 * NRq;
         if (row < B) { item = row; j = 0; }
         else if (row < B + BM) {
-          if (!need_online_next) continue;
+          send = send && need_online_next;
           const int w = row - B; item = w / M; j = 1 + (w - item * M);
         } else { const int w = row - B - BM; item = w / M; j = 1 + M + (w - item * M); }
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int w = 0; w < nActive; ++w) {
-          const float4 o = ld4(part + ((size_t)w * pl.NRq + row) * 4);
+        for (int w = half; w < nActive; w += 2) {
+          const float4 o = ld4(part + ((size_t)w * NRq + row) * 4);
           v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
         }
-        const int c = item / ipc, ii = item - c * ipc;
-        const float* dst = rs + (((size_t)parb * C + rank) * pl.nOwn + ii * rpi + j) * 4;
-        st_async_f4(mapa_u32(smem_u32(dst), (uint32_t)c), v, mapa_u32(mb_rs, (uint32_t)c));
+        v.x += __shfl_xor_sync(FULL, v.x, 1); v.y += __shfl_xor_sync(FULL, v.y, 1);
+        v.z += __shfl_xor_sync(FULL, v.z, 1); v.w += __shfl_xor_sync(FULL, v.w, 1);
+        if (half == 0 && send) {
+          const int c = item / ipc, ii = item - c * ipc;
+          const float* dst = rs + (((size_t)parb * C + rank) * nOwn + ii * rpi + j) * 4;
+          st_async_f4(mapa_u32(smem_u32(dst), (uint32_t)c), v, mapa_u32(mb_rs, (uint32_t)c));
+        }
       }
       if (cw == 0) {  // the owner work is one warp's worth: warp 0 does it, the other warps go straight to the AG barrier
-      mbar_wait_sleep(&mbar[MB_RS], parb);
-      SRLX_FSTAMP(ct == 0, 2);
-      // ---------------------------------------------------------------- owner: sum the C partials, dueling combine
-      for (int w = lane; w < nIt * rpi; w += 32) {
-        const int ii = w / rpi, j = w - ii * rpi;
-        const int set = j == 0 ? 0 : (j <= M ? 1 : 2);
-        if (set == 1 && !need_online_next) continue;
-        float4 v = ld4(weff + set * WS + nCh * 36);  // effective output bias of this forward call
-        for (int c = 0; c < C; ++c) {
-          const float4 o = ld4(rs + (((size_t)parb * C + c) * pl.nOwn + w) * 4);
-          v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
-        }
-        // (fixed-bound unrolled loops keep raw/q in registers: A <= 4, nout <= 4)
-        const float raw[4] = {v.x, v.y, v.z, v.w};
-        float q[4] = {0.f, 0.f, 0.f, 0.f};
-        if (net.dueling == SRLX_DUEL_NONE) {
+        mbar_wait_sleep(&mbar[MB_RS], parb);
+        SRLX_FSTAMP(ct == 0, 2);
+        // -------------------------------------------------------------- owner: sum the C partials, dueling combine
+        for (int w = lane; w < nIt * rpi; w += 32) {
+          const int ii = w / rpi, j = w - ii * rpi;
+          const int set = j == 0 ? 0 : (j <= M ? 1 : 2);
+          if (set == 1 && !need_online_next) continue;
+          float4 v = ld4(weff + set * WS + nCh * 36);  // effective output bias of this forward call
+          for (int c = 0; c < C; ++c) {
+            const float4 o = ld4(rs + (((size_t)parb * C + c) * nOwn + w) * 4);
+            v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
+          }
+          // (fixed-bound unrolled loops keep raw/q in registers: A <= 4, nout <= 4)
+          const float raw[4] = {v.x, v.y, v.z, v.w};
+          float q[4] = {0.f, 0.f, 0.f, 0.f};
+          if (dueling == SRLX_DUEL_NONE) {
 #pragma unroll
-          for (int a = 0; a < 4; ++a) q[a] = raw[a];
-        } else {
-          float red = 0.f;
-          if (net.dueling == SRLX_DUEL_AVERAGE) {
+            for (int a = 0; a < 4; ++a) q[a] = raw[a];
+          } else {
+            float red = 0.f;
+            if (dueling == SRLX_DUEL_AVERAGE) {
+#pragma unroll
+              for (int a = 0; a < 3; ++a)
+                if (a < A) red += raw[1 + a];
+              red = red / (float)A;
+            } else if (dueling == SRLX_DUEL_MAX) {
+              red = raw[1];
+#pragma unroll
+              for (int a = 1; a < 3; ++a)
+                if (a < A) red = fmaxf(red, raw[1 + a]);
+            }
 #pragma unroll
             for (int a = 0; a < 3; ++a)
-              if (a < A) red += raw[1 + a];
-            red = red / (float)A;
-          } else if (net.dueling == SRLX_DUEL_MAX) {
-            red = raw[1];
-#pragma unroll
-            for (int a = 1; a < 3; ++a)
-              if (a < A) red = fmaxf(red, raw[1 + a]);
+              if (a < A) q[a] = raw[0] + raw[1 + a] - red;
           }
-#pragma unroll
-          for (int a = 0; a < 3; ++a)
-            if (a < A) q[a] = raw[0] + raw[1 + a] - red;
+          *reinterpret_cast<float4*>(qown + (size_t)w * 4) = make_float4(q[0], q[1], q[2], q[3]);
+          if (set == 0) *reinterpret_cast<float4*>(rawown + (size_t)ii * 4) = v;
         }
-        *reinterpret_cast<float4*>(qown + (size_t)w * 4) = make_float4(q[0], q[1], q[2], q[3]);
-        if (set == 0) *reinterpret_cast<float4*>(rawown + (size_t)ii * 4) = v;
-      }
-      __syncwarp();
-      SRLX_FSTAMP(ct == 0, 6);
-      mbar_wait_sleep(&mbar[MB_WT], parb);  // IS weights of this batch
-      SRLX_FSTAMP(ct == 0, 7);
-      if (ct == 0 && upd + 1 < n_updates) mbar_expect_tx(&mbar[MB_WT], (uint32_t)pl.B4 * 4);
-      // ---------------------------------------------------------------- owner: targets, Huber gradient (thread per item)
-      for (int ii = lane; ii < nIt; ii += 32) {
-        const int i = rank * ipc + ii;
-        const float* qs = qown + (size_t)(ii * rpi) * 4;
-        const float* qon = qs + 4;             // online(s')  [M][4]
-        const float* qtg = qs + 4 * (1 + M);   // target(s')  [M][4]
-        const float gamma = (float)eng.discount;
-        float target = 0.f, retrace = 1.f;
-        for (int k = 0; k < M; ++k) {
-          const float* qo = qon + k * 4;
-          const float* qt = qtg + k * 4;
-          const float* qsel = eng.enable_double_dqn ? qo : qt;
-          int am = 0;
-          float best = qsel[0];
-          for (int a = 1; a < A; ++a)
-            if (qsel[a] > best) { best = qsel[a]; am = a; }  // np.argmax: first max wins
-          // Retrace with the reference's index shift (rainbow.py:267): action taken at s_k vs greedy action at s_{k+1}
-          if (k >= 1) retrace = retrace * ((float)eng.retrace_h * ((w_act[i * M + k] == am) ? 1.f : 0.f));
-          float maxq = qt[am];
-          if (eng.enable_rescale) maxq = inverse_rescaling_f(maxq);
-          float gain = w_rew[i * M + k] + ((1.0f - w_term[i * M + k]) * gamma) * maxq;
-          if (eng.enable_rescale) gain = rescaling_f(gain);
-          float qk = 0.f;  // the first step is learnt by the trainer itself (rainbow.py:232-234)
-          if (k >= 1) qk = qon[(k - 1) * 4 + w_act[i * M + k]];
-          const float td = gain - qk;
-          target += (td * gpow[k]) * retrace;
-        }
-        const int a0 = w_act[i * M + 0];
-        const float q = qs[a0];
-        const float w = samp_w[parb * pl.B4 + i];
-        const float d = q * w - target * w;
-        const float ad = fabsf(d);
-        const float delta = (float)eng.huber_delta;
-        const float lterm = (ad <= delta) ? 0.5f * d * d : delta * (ad - 0.5f * delta);
-        const float dq = fminf(fmaxf(d, -delta), delta) * w / (float)B;
-        float dr[4] = {0.f, 0.f, 0.f, 0.f};
-        if (net.dueling == SRLX_DUEL_NONE) {
+        __syncwarp();
+        SRLX_FSTAMP(ct == 0, 6);
+        mbar_wait_sleep(&mbar[MB_WT], parb);  // IS weights of this batch
+        SRLX_FSTAMP(ct == 0, 7);
+        if (ct == 0 && upd + 1 < n_updates) mbar_expect_tx(&mbar[MB_WT], (uint32_t)B4 * 4);
+        // -------------------------------------------------------------- owner: targets, Huber gradient (lane per item)
+        for (int ii0 = 0; ii0 < nIt; ii0 += 32) {
+          const int ii = ii0 + lane;
+          float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
+          if (ii < nIt) {
+            const int i = rank * ipc + ii;
+            const float* qs = qown + (size_t)(ii * rpi) * 4;
+            const float* qon = qs + 4;             // online(s')  [M][4]
+            const float* qtg = qs + 4 * (1 + M);   // target(s')  [M][4]
+            const float gamma = (float)eng.discount;
+            float target = 0.f, retrace = 1.f;
+            for (int k = 0; k < M; ++k) {
+              const float* qo = qon + k * 4;
+              const float* qt = qtg + k * 4;
+              const float* qsel = eng.enable_double_dqn ? qo : qt;
+              int am = 0;
+              float best = qsel[0];
+              for (int a = 1; a < A; ++a)
+                if (qsel[a] > best) { best = qsel[a]; am = a; }  // np.argmax: first max wins
+              // Retrace with the reference's index shift (rainbow.py:267): action taken at s_k vs greedy action at s_{k+1}
+              if (k >= 1) retrace = retrace * ((float)eng.retrace_h * ((w_act[i * M + k] == am) ? 1.f : 0.f));
+              float maxq = qt[am];
+              if (eng.enable_rescale) maxq = inverse_rescaling_f(maxq);
+              float gain = w_rew[i * M + k] + ((1.0f - w_term[i * M + k]) * gamma) * maxq;
+              if (eng.enable_rescale) gain = rescaling_f(gain);
+              float qk = 0.f;  // the first step is learnt by the trainer itself (rainbow.py:232-234)
+              if (k >= 1) qk = qon[(k - 1) * 4 + w_act[i * M + k]];
+              const float td = gain - qk;
+              target += (td * gpow[k]) * retrace;
+            }
+            const int a0 = w_act[i * M + 0];
+            const float q = qs[a0];
+            const float w = samp_w[parb * B4 + i];
+            const float d = q * w - target * w;
+            const float ad = fabsf(d);
+            const float delta = (float)eng.huber_delta;
+            const float lterm = (ad <= delta) ? 0.5f * d * d : delta * (ad - 0.5f * delta);
+            const float dq = fminf(fmaxf(d, -delta), delta) * w / (float)B;
+            float dr[4] = {0.f, 0.f, 0.f, 0.f};
+            if (dueling == SRLX_DUEL_NONE) {
 #pragma unroll
-          for (int a = 0; a < 4; ++a) dr[a] = (a == a0) ? dq : 0.f;
-        } else {  // dueling combine backward (dueling_network.py:51-58)
-          int amax = 0;
-          if (net.dueling == SRLX_DUEL_MAX) {
-            const float* rw = rawown + ii * 4;
-            float bestr = rw[1];
-            for (int a = 1; a < A; ++a)
-              if (rw[1 + a] > bestr) { bestr = rw[1 + a]; amax = a; }
+              for (int a = 0; a < 4; ++a) dr[a] = (a == a0) ? dq : 0.f;
+            } else {  // dueling combine backward (dueling_network.py:51-58)
+              int amax = 0;
+              if (dueling == SRLX_DUEL_MAX) {
+                const float* rw = rawown + ii * 4;
+                float bestr = rw[1];
+                for (int a = 1; a < A; ++a)
+                  if (rw[1 + a] > bestr) { bestr = rw[1 + a]; amax = a; }
+              }
+#pragma unroll
+              for (int a = 0; a < 3; ++a) {
+                if (a < A) {
+                  float dd = (a == a0) ? dq : 0.f;
+                  if (dueling == SRLX_DUEL_AVERAGE) dd -= dq / (float)A;
+                  else if (dueling == SRLX_DUEL_MAX && a == amax) dd -= dq;
+                  dr[1 + a] = dd;
+                }
+              }
+              dr[0] = dq;
+            }
+            v0 = make_float4(dr[0], dr[1], dr[2], dr[3]);
+            v1 = make_float4(target, q, lterm, 0.f);
           }
-#pragma unroll
-          for (int a = 0; a < 3; ++a) {
-            if (a < A) {
-              float dd = (a == a0) ? dq : 0.f;
-              if (net.dueling == SRLX_DUEL_AVERAGE) dd -= dq / (float)A;
-              else if (net.dueling == SRLX_DUEL_MAX && a == amax) dd -= dq;
-              dr[1 + a] = dd;
+          // all-gather: lane l sends the result of item (l % n) to CTAs l / n, l / n + 32 / n, ... (n items this pass)
+          const int n = min(32, nIt - ii0);
+          if (n > 0) {
+            const int src = lane % n;
+            float4 s0, s1;
+            s0.x = __shfl_sync(FULL, v0.x, src); s0.y = __shfl_sync(FULL, v0.y, src); s0.z = __shfl_sync(FULL, v0.z, src);
+            s0.w = __shfl_sync(FULL, v0.w, src); s1.x = __shfl_sync(FULL, v1.x, src); s1.y = __shfl_sync(FULL, v1.y, src);
+            s1.z = __shfl_sync(FULL, v1.z, src); s1.w = __shfl_sync(FULL, v1.w, src);
+            const int i = rank * ipc + ii0 + src;
+            const uint32_t dst = smem_u32(ag + ((size_t)parb * B + i) * 8);
+            const int cstep = 32 / n;  // n <= 32
+            if (lane < n * cstep) {
+              for (int c = lane / n; c < C; c += cstep) {
+                const uint32_t rb = mapa_u32(mb_ag, (uint32_t)c);
+                st_async_f4(mapa_u32(dst, (uint32_t)c), s0, rb);
+                st_async_f4(mapa_u32(dst + 16, (uint32_t)c), s1, rb);
+              }
             }
           }
-          dr[0] = dq;
         }
-        const float4 v0 = make_float4(dr[0], dr[1], dr[2], dr[3]), v1 = make_float4(target, q, lterm, 0.f);
-        const uint32_t dst = smem_u32(ag + ((size_t)parb * B + i) * 8);
-        for (int c = 0; c < C; ++c) {
-          const uint32_t rb = mapa_u32(mb_ag, (uint32_t)c);
-          st_async_f4(mapa_u32(dst, (uint32_t)c), v0, rb);
-          st_async_f4(mapa_u32(dst + 16, (uint32_t)c), v1, rb);
-        }
-      }
-      SRLX_FSTAMP(ct == 0, 8);
-      mbar_wait_sleep(&mbar[MB_AG], parb);
+        SRLX_FSTAMP(ct == 0, 8);
+        mbar_wait_sleep(&mbar[MB_AG], parb);
       }
       named_bar_sync(FBAR_CMP, FNC);
       SRLX_FSTAMP(ct == 0, 3);
@@ -631,7 +663,7 @@ learner_fast_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_up
       {
         const float* agb = ag + (size_t)parb * B * 8;
         const float* wS = weff;  // online(s)
-        for (int it = ct; it < Us * pl.nRG; it += FNC) {
+        for (int it = ct; it < Us * nRG; it += FNC) {
           const int rg = it / Us, u = it - rg * Us;
           const float* wo = wS + nCh * 20 + (u >> 2) * 16 + (u & 3);
           const float wo0 = wo[0], wo1 = wo[4], wo2 = wo[8], wo3 = wo[12];
@@ -639,7 +671,7 @@ learner_fast_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_up
           const float* wi = wS + (u >> 2) * 16 + (u & 3);
           const float wi0 = wi[0], wi1 = wi[4], wi2 = wi[8], wi3 = wi[12], bi = wS[nCh * 16 + u];
           float gW0 = 0.f, gW1 = 0.f, gW2 = 0.f, gW3 = 0.f, gb = 0.f, gO0 = 0.f, gO1 = 0.f, gO2 = 0.f, gO3 = 0.f;
-          const int r0 = rg * pl.rpg, r1 = min(B, r0 + pl.rpg);
+          const int r0 = rg * rpg, r1 = min(B, r0 + rpg);
           for (int r = r0; r < r1; ++r) {
             const float4 dr = ld4(agb + (size_t)r * 8);
             const float4 x = ld4(x_cur + (size_t)r * 4);
@@ -655,7 +687,9 @@ learner_fast_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_up
           }
           float* g = part + (size_t)rg * Pl;
           const float gW[4] = {gW0, gW1, gW2, gW3}, gO[4] = {gO0, gO1, gO2, gO3};
-          for (int k = 0; k < K; ++k) g[u * K + k] = gW[k];
+          if (K == 4) *reinterpret_cast<float4*>(g + u * 4) = make_float4(gW0, gW1, gW2, gW3);
+          else
+            for (int k = 0; k < K; ++k) g[u * K + k] = gW[k];
           g[Us * K + u] = gb;
           for (int s = 2; s < n_seg; ++s) {
             const FSeg& sg = segs[s];
@@ -663,7 +697,7 @@ learner_fast_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_up
           }
         }
         // output bias (replicated parameter, identical on every CTA): row group 0 holds the sum, the others zero
-        if (ct < nout * pl.nRG) {
+        if (ct < nout * nRG) {
           const int rg = ct / nout, o = ct - rg * nout;
           float a = 0.f;
           if (rg == 0)
@@ -683,393 +717,456 @@ learner_fast_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_up
     }
   } else {
     // ================================================= MEMORY WARPS =================================================
+    // warp 0 of every CTA: gather of x(t) as soon as the slots arrive, TMA prefetch of the noise ring.
+    // CTA 0, all four warps: the replay memory -- IS weights, the SumTree update of batch t, the PER sample of batch t+1.
     const int mt = tid - FNC, mw = warp - kFCmpWarps;
-    const int64_t cap1 = cap - 1;
-    const unsigned FULL = 0xffffffffu;
-
-    // ---- sample of update `tc` (CTA 0): slots, then IS weights, into buffer `pb` of every CTA ---------------------------
-    auto sample_and_send = [&](uint64_t tc, int pb, uint32_t upd) {
-#define SRLX_SSTAMP(slot)                                                                                  \
-  do {                                                                                                     \
-    if (eng.dbg_clock && mt == 0 && upd + 1 == n_updates) eng.dbg_clock[slot] = clock64();                 \
-  } while (0)
-      double total = 0.0, beta = 1.0;
-      auto draw = [&](int i, int k) -> double {
+    if (rank != 0 && mw != 0) goto done_roles;  // nothing to do for memory warps 1..3 outside CTA 0
+    {
+      const uint32_t glR = (uint32_t)((vec_steps - 1) % (uint64_t)R);  // ring row of the last vector step
+      const int dmax = 31 - __clz(n_nodes);                            // depth of the deepest leaf
+      // ---- sampler state (CTA 0): lane g < 8 of warp mw owns sample mw*8+g ------------------------------------------
+      const int own_i = mw * 8 + lane;
+      const bool own = lane < 8 && own_i < B;
+      double u_next = 0.0;  // pre-drawn uniform of the owner's next sample
+      auto draw = [&](uint64_t tc, int i, int k) -> double {
         const uint4 w = philox(eng.seed, STREAM_SAMPLE, (uint32_t)i | ((uint32_t)k << 16), (uint32_t)tc, (uint32_t)(tc >> 32));
         return u01_f64(w.x, w.y);
       };
-      if (per) {
-        total = cache[0];
-        // PriorityReplayBuffer.step is the train_count of the PREVIOUS update() call (priority_replay_buffer.py:232,250)
-        const double stepd = (tc > 0) ? (double)(tc - 1) : 0.0;
-        beta = eng.per_beta_initial + (1.0 - eng.per_beta_initial) * stepd / eng.per_beta_steps;
-        beta = beta > 1.0 ? 1.0 : beta;
-        // lane g < 8 of memory warp mw owns sample mw*8+g
-        const int i = mw * 8 + lane;
-        const bool own = lane < 8 && i < B;
-        int idx = 0;
-        double val = 0.0, pcur = 0.0;
-        if (own) {  // (a) the cached top levels, out of shared memory
-          val = draw(i, 0) * total;
-          while (2 * idx + 1 < pl.n_cache) {
-            const double tl = cache[2 * idx + 1];
-            if (val <= tl) idx = 2 * idx + 1;
-            else { val -= tl; idx = 2 * idx + 2; }
-          }
-          pcur = cache[idx];
-        }
-        SRLX_SSTAMP(22);
-        bool done = !own || (2 * (int64_t)idx + 1 >= n_nodes);
-        // (b) the remaining levels, five per L2 round trip: 31 lanes fetch both children of every node of the 5-level
-        //     subtree below each of the warp's 8 samples, the owner lanes replay the "val <= tree[left]" walk out of smem
-        double* wsub = sub + (size_t)mw * 8 * kFSubLd;
-        const int k_l = 32 - __clz(lane + 1);         // level (1..5) whose nodes this lane fetches; lane 31 idles
-        const int q_l = lane + 1 - (1 << (k_l - 1));  // parent position inside level k_l - 1
-        const int pos_l = (1 << k_l) - 2 + 2 * q_l;
-        int rnd = 0;
-        while (__any_sync(FULL, !done)) {
-          double v0[8], v1[8];
-          // unconditional loads from clamped addresses (a predicated load + select makes ptxas wait for every load in
-          // turn): nodes past the end of the tree or below finished samples are fetched but never looked at
+      // ---- update plan of the current batch (per warp: its tree levels mw, mw+4, ...), filled before the targets arrive
+      int s_item = 0, s_li = 0x7fffffff;  // sorted lane r: item, its tree index (sorted by root-to-leaf path)
+      bool s_valid = false;
+      int p_node[8], p_end[8];
+      double p_old[8];
 #pragma unroll
-          for (int g = 0; g < 8; ++g) {
-            const int ig = __shfl_sync(FULL, idx, g);
-            int64_t node = (((int64_t)ig + 1) << k_l) - 1 + 2 * q_l;
-            node = node < n_nodes - 1 ? node : (n_nodes > 1 ? n_nodes - 2 : 0);
-            v0[g] = __ldcg(eng.tree + node);
-            v1[g] = __ldcg(eng.tree + (n_nodes > 1 ? node + 1 : 0));
+      for (int q = 0; q < 8; ++q) { p_node[q] = -1; p_end[q] = 0; p_old[q] = 0.0; }
+
+      // PER sample of update `tc` (CTA 0, all memory threads): tree walk -> s_idx / s_pri -> slots to every CTA
+      auto sample_slots = [&](uint64_t tc, int pb, bool stamp) {
+#define SRLX_SSTAMP(slot)                                                                                  \
+  do {                                                                                                     \
+    if (eng.dbg_clock && mt == 0 && stamp) eng.dbg_clock[slot] = clock64();                                \
+  } while (0)
+        if (per) {
+          const double total = cache[0];
+          int idx = 0;
+          double val = 0.0, pcur = 0.0;
+          if (own) {  // (a) the cached top levels, out of shared memory
+            val = u_next * total;
+            while (2 * idx + 1 < n_cache) {
+              const double tl = cache[2 * idx + 1];
+              if (val <= tl) idx = 2 * idx + 1;
+              else { val -= tl; idx = 2 * idx + 2; }
+            }
+            pcur = cache[idx];
           }
-          if (rnd < 3) SRLX_SSTAMP(32 + rnd * 4);
-          if (lane < 31) {
+          SRLX_SSTAMP(22);
+          bool done = !own || (2 * idx + 1 >= n_nodes);
+          // (b) the remaining levels, five per L2 round trip: 31 lanes fetch both children of every node of the 5-level
+          //     subtree below each of the warp's 8 samples, the owner lanes replay the "val <= tree[left]" walk out of smem
+          double* wsub = sub + (size_t)mw * 8 * kFSubLd;
+          const int k_l = 32 - __clz(lane + 1);         // level (1..5) whose nodes this lane fetches; lane 31 idles
+          const int q_l = lane + 1 - (1 << (k_l - 1));  // parent position inside level k_l - 1
+          const int pos_l = (1 << k_l) - 2 + 2 * q_l;
+          const unsigned c_l = (1u << k_l) - 1u + 2u * (unsigned)q_l;
+          const unsigned last_pair = n_nodes > 1 ? (unsigned)n_nodes - 2u : 0u;
+          while (__any_sync(FULL, !done)) {
+            double v0[8], v1[8];
+            // unconditional loads from clamped addresses (a predicated load + select makes ptxas wait for every load in
+            // turn): nodes past the end of the tree or below finished samples are fetched but never looked at
 #pragma unroll
-            for (int g = 0; g < 8; ++g) *reinterpret_cast<double2*>(wsub + g * kFSubLd + pos_l) = make_double2(v0[g], v1[g]);
+            for (int g = 0; g < 8; ++g) {
+              const unsigned ig = (unsigned)__shfl_sync(FULL, idx, g);
+              unsigned node = (ig << k_l) + c_l;  // < 2^32: fast_shape_ok bounds the tree at 2^27 nodes
+              node = node < last_pair ? node : last_pair;
+              const double* src = eng.tree + node;
+              v0[g] = __ldcg(src);
+              v1[g] = __ldcg(src + (n_nodes > 1 ? 1 : 0));
+            }
+            if (lane < 31) {
+#pragma unroll
+              for (int g = 0; g < 8; ++g) *reinterpret_cast<double2*>(wsub + g * kFSubLd + pos_l) = make_double2(v0[g], v1[g]);
+            }
+            __syncwarp();
+            if (!done) {
+              const double* ms = wsub + lane * kFSubLd;
+              int rel = 0;
+#pragma unroll
+              for (int k = 1; k <= 5; ++k) {
+                const int left = 2 * idx + 1;
+                if (left < n_nodes) {
+                  const int base = (1 << k) - 2 + 2 * rel;
+                  const double2 ch = *reinterpret_cast<const double2*>(ms + base);
+                  if (val <= ch.x) { idx = left; rel = 2 * rel; pcur = ch.x; }
+                  else { val -= ch.x; pcur = ch.y; idx = left + 1; rel = 2 * rel + 1; }
+                }
+              }
+              done = 2 * idx + 1 >= n_nodes;
+            }
+            __syncwarp();
           }
-          __syncwarp();
-          if (rnd < 3) SRLX_SSTAMP(33 + rnd * 4);
-          if (!done) {
-            const double* ms = wsub + lane * kFSubLd;
-            int rel = 0;
-#pragma unroll
-            for (int k = 1; k <= 5; ++k) {
-              const int64_t left = 2 * (int64_t)idx + 1;
-              if (left < n_nodes) {
-                const int base = (1 << k) - 2 + 2 * rel;
-                const double tl = ms[base];
-                if (val <= tl) { idx = (int)left; rel = 2 * rel; pcur = tl; }
-                else { val -= tl; pcur = ms[base + 1]; idx = (int)left + 1; rel = 2 * rel + 1; }
+          SRLX_SSTAMP(23);
+          if (own) {  // a zero-priority leaf is re-drawn (proportional_memory.py:150-152), sequentially
+            int li = idx;
+            double p = pcur;
+            int k = 0;
+            while (p == 0.0 && k + 1 < 9999) {
+              ++k;
+              li = (int)tree_retrieve_seq(eng.tree, n_nodes, draw(tc, own_i, k) * total);
+              p = __ldcg(eng.tree + li);
+            }
+            s_idx[own_i] = li;
+            s_pri[own_i] = p;
+            s_att[own_i] = k;
+            if (k) atomicAdd(&sc->retries, (unsigned long long)k);
+          }
+          named_bar_sync(FBAR_MEM, FNM);
+          if (!eng.has_duplicate) {
+            if (mt == 0) {
+              for (int i2 = 1; i2 < B; ++i2) {
+                int k = s_att[i2];
+                while (k < 9999) {
+                  bool dup = false;
+                  for (int j = 0; j < i2; ++j) dup |= (s_idx[j] == s_idx[i2]);
+                  if (!dup && s_pri[i2] != 0.0) break;
+                  ++k;
+                  sc->retries += 1;
+                  if (k >= 9999) break;
+                  s_idx[i2] = (int)tree_retrieve_seq(eng.tree, n_nodes, draw(tc, i2, k) * total);
+                  s_pri[i2] = __ldcg(eng.tree + s_idx[i2]);
+                }
               }
             }
-            done = 2 * (int64_t)idx + 1 >= n_nodes;
+            named_bar_sync(FBAR_MEM, FNM);
           }
-          __syncwarp();
-          if (rnd < 3) SRLX_SSTAMP(34 + rnd * 4);
-          ++rnd;
-        }
-        SRLX_SSTAMP(23);
-        if (own) {  // a zero-priority leaf is re-drawn (proportional_memory.py:150-152), sequentially
-          int64_t li = idx;
-          double p = pcur;
-          int k = 0;
-          while (p == 0.0 && k + 1 < 9999) {
-            ++k;
-            li = tree_retrieve_seq(eng.tree, n_nodes, draw(i, k) * total);
-            p = __ldcg(eng.tree + li);
-          }
-          s_idx[i] = li;
-          s_pri[i] = p;
-          s_tmp[i] = (double)k;
-          if (k) atomicAdd(&sc->retries, (unsigned long long)k);
-        }
-        named_bar_sync(FBAR_MEM, FNM);
-        if (!eng.has_duplicate) {
+        } else {
+          // uniform replay: B distinct items (replay_buffer.py:34-36), sequential rejection
           if (mt == 0) {
-            for (int i2 = 1; i2 < B; ++i2) {
-              int k = (int)s_tmp[i2];
-              while (k < 9999) {
+            const uint64_t g_next = vec_steps;
+            const uint64_t g_lo = g_next > (uint64_t)R ? g_next - R : 0;
+            const uint64_t n_g = g_next - (uint64_t)(M - 1) - g_lo;
+            const uint32_t n_valid = (uint32_t)(n_g * E);
+            for (int i = 0; i < B; ++i) {
+              uint32_t pick = 0;
+              for (int k = 0; k < 65536; ++k) {
+                const uint4 w = philox(eng.seed, STREAM_UNIFORM_SAMPLE, (uint32_t)i | ((uint32_t)k << 16), (uint32_t)tc, (uint32_t)(tc >> 32));
+                pick = u_below(w.x, n_valid);
                 bool dup = false;
-                for (int j = 0; j < i2; ++j) dup |= (s_idx[j] == s_idx[i2]);
-                if (!dup && s_pri[i2] != 0.0) break;
-                ++k;
-                sc->retries += 1;
-                if (k >= 9999) break;
-                s_idx[i2] = tree_retrieve_seq(eng.tree, n_nodes, draw(i2, k) * total);
-                s_pri[i2] = __ldcg(eng.tree + s_idx[i2]);
+                for (int j = 0; j < i; ++j) dup |= (s_idx[j] == (int)pick);
+                if (!dup) break;
               }
+              s_idx[i] = (int)pick;
+            }
+            for (int i = 0; i < B; ++i) {
+              const uint64_t pick = (uint64_t)s_idx[i];
+              const uint64_t g = g_lo + pick / E;
+              s_idx[i] = (int)((g % R) * E + pick % E) + cap1;  // stored as if it were a tree index
             }
           }
           named_bar_sync(FBAR_MEM, FNM);
         }
-      } else {
-        // uniform replay: B distinct items (replay_buffer.py:34-36), sequential rejection
-        if (mt == 0) {
-          const uint64_t g_next = vec_steps;
-          const uint64_t g_lo = g_next > (uint64_t)R ? g_next - R : 0;
-          const uint64_t n_g = g_next - (uint64_t)(M - 1) - g_lo;
-          const uint32_t n_valid = (uint32_t)(n_g * E);
-          for (int i = 0; i < B; ++i) {
-            uint32_t pick = 0;
-            for (int k = 0; k < 65536; ++k) {
-              const uint4 w = philox(eng.seed, STREAM_UNIFORM_SAMPLE, (uint32_t)i | ((uint32_t)k << 16), (uint32_t)tc, (uint32_t)(tc >> 32));
-              pick = u_below(w.x, n_valid);
-              bool dup = false;
-              for (int j = 0; j < i; ++j) dup |= (s_idx[j] == (int64_t)pick);
-              if (!dup) break;
-            }
-            s_idx[i] = pick;
-          }
-          for (int i = 0; i < B; ++i) {
-            const uint64_t pick = (uint64_t)s_idx[i];
-            const uint64_t g = g_lo + pick / E;
-            s_idx[i] = (int64_t)((g % R) * E + pick % E) + cap1;  // stored as if it were a tree index
-          }
-        }
-        named_bar_sync(FBAR_MEM, FNM);
-      }
-      SRLX_SSTAMP(24);
-      // slots to every CTA (4 per store)
-      {
-        const int nq = pl.B4 / 4;
-        const uint32_t dst = smem_u32(samp_slot + pb * pl.B4);
-        for (int w = mt; w < nq * C; w += FNM) {
-          const int c = w / nq, q = w - c * nq;
-          int v[4];
+        SRLX_SSTAMP(24);
+        // slots to every CTA (4 per store)
+        {
+          const int nq = B4 / 4;
+          const uint32_t dst = smem_u32(samp_slot + pb * B4);
+          for (int w = mt; w < nq * C; w += FNM) {
+            const int c = w / nq, q = w - c * nq;
+            int v[4];
 #pragma unroll
-          for (int e = 0; e < 4; ++e) v[e] = (4 * q + e < B) ? (int)(s_idx[4 * q + e] - cap1) : 0;
-          st_async_i4(mapa_u32(dst + 16 * q, (uint32_t)c), make_int4(v[0], v[1], v[2], v[3]), mapa_u32(mb_s, (uint32_t)c));
+            for (int e = 0; e < 4; ++e) v[e] = (4 * q + e < B) ? (s_idx[4 * q + e] - cap1) : 0;
+            st_async_i4(mapa_u32(dst + 16 * q, (uint32_t)c), make_int4(v[0], v[1], v[2], v[3]), mapa_u32(mb_s, (uint32_t)c));
+          }
         }
-      }
-      SRLX_SSTAMP(25);
-      // IS weights (proportional_memory.py:159-167): only the Huber step needs them, so they follow the slots
-      if (per) {
-        if (mt < B) s_tmp[mt] = pow((double)mem_size * (s_pri[mt] / total), -beta);
-        named_bar_sync(FBAR_MEM, FNM);
-        SRLX_SSTAMP(26);
-        if (mw == 0) {
-          double mx = 0.0;
-          for (int i = lane; i < B; i += 32) mx = fmax(mx, s_tmp[i]);
+        SRLX_SSTAMP(25);
+        if (eng.dbg_sample_idx)
+          for (int i = mt; i < B; i += FNM) eng.dbg_sample_idx[i] = per ? (int64_t)s_idx[i] : (int64_t)(s_idx[i] - cap1);
+      };
+
+      // IS weights of the batch sampled for update `tc` (proportional_memory.py:159-167), one warp; only the Huber step
+      // needs them, so they are computed after the slots have gone out
+      auto send_weights = [&](uint64_t tc, int pb) {
+        double wv = 1.0;
+        if (per) {
+          const double total = cache[0];  // the tree has not changed since the sample
+          // PriorityReplayBuffer.step is the train_count of the PREVIOUS update() call (priority_replay_buffer.py:232,250)
+          const double stepd = (tc > 0) ? (double)(tc - 1) : 0.0;
+          double beta = eng.per_beta_initial + (1.0 - eng.per_beta_initial) * stepd / eng.per_beta_steps;
+          beta = beta > 1.0 ? 1.0 : beta;
+          const double w = lane < B ? pow((double)mem_size * (s_pri[lane] / total), -beta) : 0.0;
+          double mx = w;
           for (int s = 16; s > 0; s >>= 1) mx = fmax(mx, __shfl_xor_sync(FULL, mx, s));
-          for (int i = lane; i < B; i += 32) s_val[i] = s_tmp[i] / mx;
+          wv = w / mx;
         }
-      } else {
-        if (mt < B) s_val[mt] = 1.0;
-      }
-      named_bar_sync(FBAR_MEM, FNM);
-      {
-        const int nq = pl.B4 / 4;
-        const uint32_t dst = smem_u32(samp_w + pb * pl.B4);
-        for (int w = mt; w < nq * C; w += FNM) {
+        if (lane < B) s_tmp[lane] = wv;
+        __syncwarp();
+        const int nq = B4 / 4;
+        const uint32_t dst = smem_u32(samp_w + pb * B4);
+        for (int w = lane; w < nq * C; w += 32) {
           const int c = w / nq, q = w - c * nq;
           float v[4];
 #pragma unroll
-          for (int e = 0; e < 4; ++e) v[e] = (4 * q + e < B) ? (float)s_val[4 * q + e] : 0.f;
+          for (int e = 0; e < 4; ++e) v[e] = (4 * q + e < B) ? (float)s_tmp[4 * q + e] : 0.f;
           st_async_f4(mapa_u32(dst + 16 * q, (uint32_t)c), make_float4(v[0], v[1], v[2], v[3]), mapa_u32(mb_wt, (uint32_t)c));
-        }
-      }
-    };
-
-    if (rank == 0) sample_and_send(tc0, 0, 0);
-
-    for (uint32_t upd = 0; upd < n_updates; ++upd) {
-      const uint64_t tc = tc0 + upd;
-      const int parb = upd & 1;
-      float* x_cur = xin + (size_t)parb * pl.NX * 4;
-      int* w_act = reinterpret_cast<int*>(meta + (size_t)parb * 3 * BM);
-      float* w_rew = meta + (size_t)parb * 3 * BM + BM;
-      float* w_term = w_rew + BM;
-      const int* slot = samp_slot + parb * pl.B4;
-      if (mw == 0) mbar_wait_sleep(&mbar[MB_S], parb);  // slots of update t have arrived from CTA 0
-      named_bar_sync(FBAR_MEM, FNM);
-      SRLX_FSTAMP(mt == 0, 16);
-      // ---------------------------------------------------------------- gather the windows (one memory round trip)
-      for (int w = mt; w < BM + B; w += FNM) {
-        if (w < BM) {
-          const int i = w / M, k = w - i * M;
-          const int s0 = slot[i];
-          const int rho = s0 / E, e = s0 - rho * E;
-          const int sk = ((rho + k) % R) * E + e;
-          // every load of this thread is issued before the first dependent store
-          const int a = __ldcg(eng.ring_action + sk);
-          const float rw = __ldcg(eng.ring_reward + sk);
-          const unsigned char tm = __ldcg(eng.ring_term + sk), dn = __ldcg(eng.ring_done + sk);
-          float4 xv = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (D == 4) {
-            xv = __ldcg(reinterpret_cast<const float4*>(eng.ring_next_obs + (size_t)sk * 4));
-          } else {
-            const float* src = eng.ring_next_obs + (size_t)sk * D;
-            xv.x = __ldcg(src);
-            if (D > 1) xv.y = __ldcg(src + 1);
-            if (D > 2) xv.z = __ldcg(src + 2);
-          }
-          g_act[w] = a;
-          g_rew[w] = rw;
-          g_term[w] = (float)tm;
-          g_done[w] = (int)dn;
-          *reinterpret_cast<float4*>(x_cur + (size_t)(B + w) * 4) = xv;
-        } else {
-          const int i = w - BM;
-          float4 xv = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (D == 4) {
-            xv = __ldcg(reinterpret_cast<const float4*>(eng.ring_obs + (size_t)slot[i] * 4));
-          } else {
-            const float* src = eng.ring_obs + (size_t)slot[i] * D;
-            xv.x = __ldcg(src);
-            if (D > 1) xv.y = __ldcg(src + 1);
-            if (D > 2) xv.z = __ldcg(src + 2);
-          }
-          *reinterpret_cast<float4*>(x_cur + (size_t)i * 4) = xv;
-        }
-      }
-      named_bar_sync(FBAR_MEM, FNM);
-      for (int i = mt; i < B; i += FNM) {
-        const int s0 = slot[i];
-        const int rho = s0 / E, e = s0 - rho * E;
-        const uint64_t g_last = vec_steps - 1;
-        const uint64_t g_item = g_last - ((g_last + (uint64_t)R - (uint64_t)rho) % (uint64_t)R);
-        bool ended = false;
-        int last_k = 0;
-        for (int k = 0; k < M; ++k) {
-          const int w = i * M + k;
-          if (!ended) {
-            w_act[w] = g_act[w];
-            w_rew[w] = g_rew[w];
-            w_term[w] = g_term[w];
-            last_k = k;
-            if (g_done[w]) ended = true;
-          } else {
-            // padded tail record: random action, reward 0, terminated 1, state = last next_state (rainbow.py:358-371)
-            const uint64_t gp = g_item + (uint64_t)k;
-            const uint4 pw = philox(eng.seed, STREAM_PAD_ACTION, (uint32_t)e, (uint32_t)gp, (uint32_t)(gp >> 32));
-            w_act[w] = (int)u_below(pw.x, (uint32_t)A);
-            w_rew[w] = 0.f;
-            w_term[w] = 1.f;
-            *reinterpret_cast<float4*>(x_cur + (size_t)(B + w) * 4) = ld4(x_cur + (size_t)(B + i * M + last_k) * 4);
-          }
-        }
-      }
-      named_bar_sync(FBAR_MEM, FNM);
-      if (mt == 0) {
-        mbar_arrive_local(&mbar[MB_XR]);  // x(t) ready for the compute warps
-        if (upd + 1 < n_updates) mbar_expect_tx(&mbar[MB_S], (uint32_t)pl.B4 * 4);
-      }
-      SRLX_FSTAMP(mt == 0, 17);
-
-      if (mw == 0) mbar_wait_sleep(&mbar[MB_AG], parb);  // update t's targets are known everywhere: forward(t) is over in every CTA
-      named_bar_sync(FBAR_MEM, FNM);
-      SRLX_FSTAMP(mt == 0, 18);
-      if (mt == 0 && noisy && upd + 2 < n_updates) {  // ring slot (t+2)%3 was last read by Adam(t-1)
-        uint64_t* nb = &mbar[MB_NZ0 + (upd + 2) % 3];
-        mbar_expect_tx(nb, (uint32_t)nz_bytes);
-        bulk_g2s(nzr + (size_t)((upd + 2) % 3) * 3 * Pl, nz_src(upd + 2), (uint32_t)nz_bytes, nb);
-      }
-      if (rank == 0) {
-        const float* agb = ag + (size_t)parb * B * 8;
-        if (eng.dbg_sample_idx)  // before the sampler reuses s_idx for update t+1
-          for (int i = mt; i < B; i += FNM) eng.dbg_sample_idx[i] = per ? s_idx[i] : (s_idx[i] - cap1);
-        if (per) {
-          // ProportionalMemory.update (proportional_memory.py:171-177), bit-identical to the sequential loop:
-          // per-item change in item order for duplicate leaves ...
-          if (mw == 0) {
-            const bool v = lane < B;
-            const int li = v ? (int)s_idx[lane] : -1 - lane;
-            double pnew = 0.0;
-            if (v) pnew = pow(fabs((double)fabsf(agb[lane * 8 + 4] - agb[lane * 8 + 5])) + eng.per_epsilon, eng.per_alpha);
-            const unsigned mask = __match_any_sync(FULL, li);
-            const unsigned lower = mask & ((1u << lane) - 1u);
-            const int j = lower ? 31 - __clz(lower) : -1;
-            const double prevnew = __shfl_sync(FULL, pnew, j < 0 ? 0 : j);
-            if (v) {
-              const double prev = j >= 0 ? prevnew : s_pri[lane];
-              s_new[lane] = pnew;
-              s_chg[lane] = pnew - prev;
-              if (((mask >> lane) >> 1) == 0) {  // the last item touching a leaf wins
-                __stcg(eng.tree + li, pnew);
-                if (li < pl.n_cache) cache[li] = pnew;
-              }
-            }
-            double mx = pnew;
-            for (int s = 16; s > 0; s >>= 1) mx = fmax(mx, __shfl_xor_sync(FULL, mx, s));
-            if (lane == 0 && mx > sc->max_priority) sc->max_priority = mx;
-          }
-          named_bar_sync(FBAR_MEM, FNM);
-          SRLX_FSTAMP(mt == 0, 19);
-          // ... and every ancestor receives the changes of the items below it in item order: warp per tree level,
-          // lane per item, the first lane of each group of equal nodes applies the whole group.  All loads first.
-          {
-            const int dmax = 63 - __clzll((long long)n_nodes);  // depth of the deepest leaf
-            const bool valid = lane < B;
-            const long long ip1 = valid ? (long long)s_idx[lane] + 1 : 1;
-            const int d = 63 - __clzll(ip1);
-            double v[8];
-            unsigned msk[8];
-            long long nd[8];
+          if (c == 0 && eng.dbg_weights) {
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
-              const int a = mw + kFMemWarps * q;
-              nd[q] = -1;
-              msk[q] = 0;
-              v[q] = 0.0;
-              if (a < dmax) {
-                const bool has = valid && d > a;
-                const long long node = has ? (ip1 >> (d - a)) - 1 : -1 - (long long)lane;
-                const unsigned mask = __match_any_sync(FULL, node);
-                if (has && lane == __ffs(mask) - 1) {
-                  nd[q] = node;
-                  msk[q] = mask;
-                }
-              }
-              // unconditional load (node 0 for non-leaders): the global tree is write-through, so it is current
-              v[q] = __ldcg(eng.tree + (nd[q] >= 0 ? nd[q] : 0));
-            }
+            for (int e = 0; e < 4; ++e)
+              if (4 * q + e < B) eng.dbg_weights[4 * q + e] = v[e];
+          }
+        }
+        __syncwarp();
+      };
+
+      // Plan of the SumTree update of the current batch (every warp for its own levels): items sorted by root-to-leaf
+      // path, so the items below any node are consecutive lanes; per level the first lane of a run ("leader") knows the
+      // node, the last lane of its run, and has the node's old value in a register before the new priorities exist.
+      auto plan_update = [&]() {
+        const bool v = lane < B;
+        const int li = v ? s_idx[lane] : 0x7ffffffe;
+        const unsigned ip1 = (unsigned)li + 1u;
+        const int d = 31 - __clz(ip1);
+        const unsigned key = v ? (ip1 << (31 - d)) : 0xffffffffu;
+        int rank_l = 0;
+#pragma unroll 8
+        for (int j = 0; j < 32; ++j) {
+          const unsigned kj = __shfl_sync(FULL, key, j);
+          rank_l += (kj < key || (kj == key && j < lane)) ? 1 : 0;
+        }
+        int* pw = sperm + mw * 32;
+        pw[rank_l] = lane;
+        __syncwarp();
+        s_item = pw[lane];
+        __syncwarp();
+        s_valid = s_item < B;
+        s_li = s_valid ? s_idx[s_item] : 0x7ffffffe;
+        const unsigned sip1 = (unsigned)s_li + 1u;
+        const int sd = 31 - __clz(sip1);
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
-              if (nd[q] >= 0) {
-                unsigned m = msk[q];
-                double a = v[q];
-                while (m) {
-                  const int j = __ffs(m) - 1;
-                  m &= m - 1;
-                  a += s_chg[j];
-                }
-                __stcg(eng.tree + nd[q], a);
-                if (nd[q] < (long long)pl.n_cache) cache[nd[q]] = a;
-              }
+        for (int q = 0; q < 8; ++q) {
+          const int a = mw + kFMemWarps * q;
+          p_node[q] = -1;
+          p_end[q] = lane;
+          if (a < dmax) {
+            const bool has = s_valid && sd > a;
+            const int node = has ? (int)(sip1 >> (sd - a)) - 1 : -1;
+            const int prevn = __shfl_up_sync(FULL, node, 1), nextn = __shfl_down_sync(FULL, node, 1);
+            const bool lead = has && (lane == 0 || prevn != node);
+            const bool last = has && (lane == 31 || nextn != node);
+            const unsigned bl = __ballot_sync(FULL, last);
+            p_end[q] = lane + __ffs(bl >> lane) - 1;  // first "last" flag at or after this lane (leaders always find one)
+            p_node[q] = lead ? node : -1;
+          }
+          p_old[q] = __ldcg(eng.tree + (p_node[q] >= 0 ? p_node[q] : 0));  // unconditional: all levels in flight at once
+        }
+      };
+
+      // ProportionalMemory.update of the current batch (proportional_memory.py:171-177).  The new priorities, their
+      // changes and the running sum are computed by every warp (no cross-warp hand-off); each warp then writes the nodes
+      // of its levels: new = old + (sum of the changes of the items below the node).  The reference adds the changes one
+      // item at a time in batch order; here a node's changes are summed in path order as a difference of running sums
+      // (exact for the common single-item run) -- a different association of the same fp64 terms, see DESIGN.md.
+      auto apply_update = [&](const float* agb) {
+        double pnew = 0.0;
+        if (s_valid) pnew = pow(fabs((double)fabsf(agb[s_item * 8 + 4] - agb[s_item * 8 + 5])) + eng.per_epsilon, eng.per_alpha);
+        const int prevli = __shfl_up_sync(FULL, s_li, 1), nextli = __shfl_down_sync(FULL, s_li, 1);
+        const double prevp = __shfl_up_sync(FULL, pnew, 1);
+        const bool dupprev = lane > 0 && prevli == s_li;  // duplicates of a leaf are consecutive, in batch order
+        const double chg = s_valid ? pnew - (dupprev ? prevp : s_pri[s_item]) : 0.0;
+        if (mw == 0) {
+          if (s_valid && (lane == 31 || nextli != s_li)) {  // the last item touching a leaf wins
+            __stcg(eng.tree + s_li, pnew);
+            if (s_li < n_cache) cache[s_li] = pnew;
+          }
+          double mx = pnew;
+          for (int s = 16; s > 0; s >>= 1) mx = fmax(mx, __shfl_xor_sync(FULL, mx, s));
+          if (lane == 0 && mx > sc->max_priority) sc->max_priority = mx;
+        }
+        double P = chg;  // inclusive running sum over the sorted lanes
+#pragma unroll
+        for (int s = 1; s < 32; s <<= 1) {
+          const double t = __shfl_up_sync(FULL, P, s);
+          if (lane >= s) P += t;
+        }
+        double Pex = __shfl_up_sync(FULL, P, 1);
+        if (lane == 0) Pex = 0.0;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const int a = mw + kFMemWarps * q;
+          if (a < dmax) {
+            const double Pe = __shfl_sync(FULL, P, p_end[q]);
+            if (p_node[q] >= 0) {
+              const double sum = (p_end[q] == lane) ? chg : (Pe - Pex);
+              const double nv = p_old[q] + sum;
+              __stcg(eng.tree + p_node[q], nv);
+              if (p_node[q] < n_cache) cache[p_node[q]] = nv;
             }
           }
-          named_bar_sync(FBAR_MEM, FNM);
         }
-        SRLX_FSTAMP(mt == 0, 20);
-        if (upd + 1 < n_updates) sample_and_send(tc + 1, parb ^ 1, upd + 1);
-        SRLX_FSTAMP(mt == 0, 21);
-        // loss, counters, debug taps (off the critical path)
-        if (mt == 0) {
+      };
+
+      // loss / counters / debug taps of update `u` (off the critical path)
+      auto bookkeeping = [&](uint32_t u) {
+        const float* agb = ag + (size_t)(u & 1) * B * 8;
+        if (lane == 0) {
           float l = 0.f;
           for (int i = 0; i < B; ++i) l += agb[i * 8 + 6];
           const double ld = (double)l / (double)B;
           sc->last_loss = ld;
           sc->loss_sum += ld;
-          if ((tc % (uint64_t)eng.target_update_interval) == 0) sc->sync_count += 1;
+          if (((tc0 + u) % (uint64_t)eng.target_update_interval) == 0) sc->sync_count += 1;
         }
         if (eng.dbg_target_q)
-          for (int i = mt; i < B; i += FNM) eng.dbg_target_q[i] = agb[i * 8 + 4];
+          for (int i = lane; i < B; i += 32) eng.dbg_target_q[i] = agb[i * 8 + 4];
         if (eng.dbg_q_sa)
-          for (int i = mt; i < B; i += FNM) eng.dbg_q_sa[i] = agb[i * 8 + 5];
-        if (eng.dbg_weights)
-          for (int i = mt; i < B; i += FNM) eng.dbg_weights[i] = samp_w[parb * pl.B4 + i];
-        if (eng.dbg_windows) {
-          float* dw = eng.dbg_windows;
-          const int n_states = B * (M + 1) * D;
-          for (int w = mt; w < n_states; w += FNM) {
-            const int i = w / ((M + 1) * D), rem = w - i * (M + 1) * D, k = rem / D, d = rem - k * D;
-            dw[w] = (k == 0) ? x_cur[(size_t)i * 4 + d] : x_cur[(size_t)(B + i * M + k - 1) * 4 + d];
+          for (int i = lane; i < B; i += 32) eng.dbg_q_sa[i] = agb[i * 8 + 5];
+      };
+
+      if (rank == 0) {
+        if (own && per) u_next = draw(tc0, own_i, 0);
+        sample_slots(tc0, 0, false);
+      }
+
+      for (uint32_t upd = 0; upd < n_updates; ++upd) {
+        const uint64_t tc = tc0 + upd;
+        const int parb = upd & 1;
+        float* x_cur = xin + (size_t)parb * NX * 4;
+        int* w_act = reinterpret_cast<int*>(meta + (size_t)parb * 3 * BM);
+        float* w_rew = meta + (size_t)parb * 3 * BM + BM;
+        float* w_term = w_rew + BM;
+        const int* slot = samp_slot + parb * B4;
+        if (mw == 0) {
+          mbar_wait_sleep(&mbar[MB_S], parb);  // slots of update t have arrived from CTA 0
+          SRLX_FSTAMP(mt == 0, 16);
+          // -------------------------------------------------------------- gather the windows: lane = batch item, every load
+          // of the window in flight at once (one memory round trip), the padding rule applied in registers
+          const bool v = lane < B;
+          const int s0 = v ? slot[lane] : 0;
+          const int rho = s0 / E, e = s0 - rho * E;
+          const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          auto ldx = [&](const float* base, int sk) -> float4 {
+            if (D == 4) return __ldcg(reinterpret_cast<const float4*>(base + (size_t)sk * 4));
+            float4 xv = z4;
+            const float* src = base + (size_t)sk * D;
+            xv.x = __ldcg(src);
+            if (D > 1) xv.y = __ldcg(src + 1);
+            if (D > 2) xv.z = __ldcg(src + 2);
+            return xv;
+          };
+          const float4 x0 = ldx(eng.ring_obs, s0);
+          // g_item: the vector step that wrote ring row rho (the ring holds the last R steps)
+          const uint32_t back = glR >= (uint32_t)rho ? glR - (uint32_t)rho : glR + (uint32_t)R - (uint32_t)rho;
+          const uint64_t g_item = (vec_steps - 1) - (uint64_t)back;
+          if (FLAG) {
+            int a[3]; float rw[3]; unsigned char tm[3], dn[3]; float4 xv[3];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+              int rk = rho + k; rk = rk >= R ? rk - R : rk;
+              const int sk = rk * E + e;
+              a[k] = __ldcg(eng.ring_action + sk); rw[k] = __ldcg(eng.ring_reward + sk);
+              tm[k] = __ldcg(eng.ring_term + sk); dn[k] = __ldcg(eng.ring_done + sk);
+              xv[k] = ldx(eng.ring_next_obs, sk);
+            }
+            bool ended = false;
+            int last_k = 0;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+              if (ended) {  // padded tail record: random action, reward 0, terminated 1, state = last next_state (rainbow.py:358-371)
+                const uint64_t gp = g_item + (uint64_t)k;
+                const uint4 pw = philox(eng.seed, STREAM_PAD_ACTION, (uint32_t)e, (uint32_t)gp, (uint32_t)(gp >> 32));
+                a[k] = (int)u_below(pw.x, (uint32_t)A); rw[k] = 0.f; tm[k] = 1;
+                xv[k] = last_k == 0 ? xv[0] : xv[1];
+              } else {
+                last_k = k;
+                if (dn[k]) ended = true;
+              }
+            }
+            if (v) {
+              *reinterpret_cast<float4*>(x_cur + (size_t)lane * 4) = x0;
+#pragma unroll
+              for (int k = 0; k < 3; ++k) {
+                const int w = lane * 3 + k;
+                w_act[w] = a[k]; w_rew[w] = rw[k]; w_term[w] = (float)tm[k];
+                *reinterpret_cast<float4*>(x_cur + (size_t)(B + w) * 4) = xv[k];
+              }
+            }
+          } else {
+            if (v) *reinterpret_cast<float4*>(x_cur + (size_t)lane * 4) = x0;
+            bool ended = false;
+            float4 xlast = z4;
+            for (int k = 0; k < M; ++k) {
+              const int w = lane * M + k;
+              int a; float rw, tm; float4 xv;
+              if (!ended) {
+                const int sk = ((rho + k) % R) * E + e;
+                a = __ldcg(eng.ring_action + sk); rw = __ldcg(eng.ring_reward + sk);
+                tm = (float)__ldcg(eng.ring_term + sk);
+                const int dn = (int)__ldcg(eng.ring_done + sk);
+                xv = ldx(eng.ring_next_obs, sk);
+                xlast = xv;
+                if (dn) ended = true;
+              } else {
+                const uint64_t gp = g_item + (uint64_t)k;
+                const uint4 pw = philox(eng.seed, STREAM_PAD_ACTION, (uint32_t)e, (uint32_t)gp, (uint32_t)(gp >> 32));
+                a = (int)u_below(pw.x, (uint32_t)A); rw = 0.f; tm = 1.f; xv = xlast;
+              }
+              if (v) {
+                w_act[w] = a; w_rew[w] = rw; w_term[w] = tm;
+                *reinterpret_cast<float4*>(x_cur + (size_t)(B + w) * 4) = xv;
+              }
+            }
           }
-          for (int w = mt; w < BM; w += FNM) {
-            dw[n_states + w] = (float)w_act[w];
-            dw[n_states + BM + w] = w_rew[w];
-            dw[n_states + 2 * BM + w] = w_term[w];
+          __syncwarp();
+          if (lane == 0) {
+            mbar_arrive_local(&mbar[MB_XR]);  // x(t) ready for the compute warps
+            if (upd + 1 < n_updates) mbar_expect_tx(&mbar[MB_S], (uint32_t)B4 * 4);
+          }
+          SRLX_FSTAMP(mt == 0, 17);
+          if (rank == 0 && eng.dbg_windows) {
+            float* dw = eng.dbg_windows;
+            const int n_states = B * (M + 1) * D;
+            for (int w = lane; w < n_states; w += 32) {
+              const int i = w / ((M + 1) * D), rem = w - i * (M + 1) * D, k = rem / D, d = rem - k * D;
+              dw[w] = (k == 0) ? x_cur[(size_t)i * 4 + d] : x_cur[(size_t)(B + i * M + k - 1) * 4 + d];
+            }
+            for (int w = lane; w < BM; w += 32) {
+              dw[n_states + w] = (float)w_act[w];
+              dw[n_states + BM + w] = w_rew[w];
+              dw[n_states + 2 * BM + w] = w_term[w];
+            }
           }
         }
+        if (rank == 0) {
+          // ---- off the critical path, while the compute warps run forward(t) -------------------------------------------
+          if (mw == 1) send_weights(tc, parb);
+          if (mw == 2 && upd > 0) bookkeeping(upd - 1);
+          if (per) {
+            plan_update();
+            if (own && upd + 1 < n_updates) u_next = draw(tc + 1, own_i, 0);
+          }
+          SRLX_FSTAMP(mt == 0, 26);
+        }
+        if (mw == 0) {
+          mbar_wait_sleep(&mbar[MB_AG], parb);  // update t's targets are known everywhere: forward(t) is over in every CTA
+          if (lane == 0 && noisy && upd + 2 < n_updates) {  // ring slot (t+2)%3 was last read by Adam(t-1)
+            uint64_t* nb = &mbar[MB_NZ0 + (upd + 2) % 3];
+            mbar_expect_tx(nb, (uint32_t)nz_bytes);
+            bulk_g2s(nzr + (size_t)((upd + 2) % 3) * 3 * Pl, nz_src(upd + 2), (uint32_t)nz_bytes, nb);
+          }
+        }
+        if (rank == 0) {
+          named_bar_sync(FBAR_MEM, FNM);
+          SRLX_FSTAMP(mt == 0, 18);
+          if (per) {
+            apply_update(ag + (size_t)parb * B * 8);
+            named_bar_sync(FBAR_MEM, FNM);
+          }
+          SRLX_FSTAMP(mt == 0, 20);
+          if (upd + 1 < n_updates) sample_slots(tc + 1, parb ^ 1, upd + 2 == n_updates);
+          SRLX_FSTAMP(mt == 0, 21);
+        }
       }
+      if (rank == 0 && mw == 2) bookkeeping(n_updates - 1);
     }
+  done_roles:;
   }
 
   // ---- write back: parameters, Adam moments, target copy, counters ----------------------------------------------------
@@ -1108,8 +1205,12 @@ static int learn_fast(const srlx_engine* eng, uint32_t n_updates, uintptr_t cuda
   const long long n_nodes = 2ll * eng->ring_rows * eng->n_envs - 1;
   const FPlan pl = make_fplan(*eng, C, n_nodes);
   (void)max_smem;
-  SRLX_CHECK_CUDA(cudaFuncSetAttribute(learner_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.total));
-  if (C > 8) SRLX_CHECK_CUDA(cudaFuncSetAttribute(learner_fast_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+  // the reference's Rainbow default shape gets the instantiation with compile-time loop bounds
+  const bool flag = eng->batch_size == 32 && eng->multisteps == 3 && eng->n_actions == 2 && eng->obs_dim == 4 &&
+                    eng->net.out_dim[1] == 3 && eng->net.dueling == SRLX_DUEL_AVERAGE && eng->net.out_dim[0] == 1024 && C == 8;
+  auto kern = flag ? learner_fast_kernel<true> : learner_fast_kernel<false>;
+  SRLX_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.total));
+  if (C > 8) SRLX_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
   const size_t per_update = (size_t)C * 3 * pl.Pl * 4;
   uint32_t chunk = kFMaxChunk;
   if (eng->net.noisy) {
@@ -1140,7 +1241,7 @@ static int learn_fast(const srlx_engine* eng, uint32_t n_updates, uintptr_t cuda
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    SRLX_CHECK_CUDA(cudaLaunchKernelEx(&cfg, learner_fast_kernel, *eng, n, (const float*)eng->noise_scratch));
+    SRLX_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, *eng, n, (const float*)eng->noise_scratch));
     count_launch();
     SRLX_CHECK_CUDA(cudaGetLastError());
     done += n;
