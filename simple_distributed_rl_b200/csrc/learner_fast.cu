@@ -48,7 +48,7 @@ struct FSeg {
 struct FPlan {
   int C, B, M, A, D, K, nout, Uh, Us, nCh, BM, NX, NRq, ipc, rpi, nOwn, Pl, WS, nRG, rpg, B4, n_cache;
   size_t off_mbar, off_seg, off_scal, off_adam, off_gpow, off_gidx, off_slot, off_par, off_nz, off_weff, off_xin, off_meta,
-      off_part, off_rs, off_ag, off_qown, off_rawown, off_samp_slot, off_samp_w, off_sdbl, off_sub, off_cache, total;
+      off_part, off_rs, off_ag, off_qown, off_rawown, off_samp_slot, off_samp_w, off_sdbl, off_plan, off_sub, off_cache, total;
 };
 
 __host__ __device__ inline int fast_pick_cluster(const srlx_net& net, int want) {
@@ -139,6 +139,7 @@ __host__ __device__ inline FPlan make_fplan(const srlx_engine& eng, int C, long 
   p.off_samp_slot = take((size_t)2 * p.B4 * 4);
   p.off_samp_w = take((size_t)2 * p.B4 * 4);
   p.off_sdbl = take(2048);  // s_idx, s_att, sperm[4][32] (int), then s_pri, s_tmp (double)
+  p.off_plan = take(eng.mem_kind == SRLX_MEM_PROPORTIONAL ? (size_t)5 * FNM * 8 : 0);
   p.n_cache = 0;
   if (eng.mem_kind == SRLX_MEM_PROPORTIONAL) {
     p.off_sub = take((size_t)kFMemWarps * 8 * kFSubLd * 8);
@@ -233,14 +234,15 @@ __global__ void __launch_bounds__(128) noise_precompute_kernel(const __grid_cons
 }
 
 // =====================================================================================================================
-// FLAG = true: the reference's Rainbow default shape (batch 32, 3-step, 2 actions, 4 observation floats, dueling-average
-// head of 2 x 512 units over 8 CTAs) with every loop bound a compile-time constant; FLAG = false: same code, run-time bounds.
-template <bool FLAG>
+// TC = 8 / 16: the reference's Rainbow default shape (batch 32, 3-step, 2 actions, 4 observation floats, dueling-average
+// head of 2 x 512 units) on a cluster of TC CTAs, every loop bound a compile-time constant; TC = 0: same code, run-time bounds.
+template <int TC>
 __global__ void __launch_bounds__(FNT, 1)
 learner_fast_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_updates, const float* __restrict__ noise) {
   extern __shared__ __align__(16) unsigned char smem[];
   cg::cluster_group cluster = cg::this_cluster();
-  const int C = FLAG ? 8 : (int)cluster.num_blocks();
+  constexpr bool FLAG = TC > 0;
+  const int C = FLAG ? TC : (int)cluster.num_blocks();
   const int rank = (int)cluster.block_rank();
   const srlx_net& net = eng.net;
   const int cap = eng.ring_rows * eng.n_envs, n_nodes = 2 * cap - 1, cap1 = cap - 1;
@@ -257,7 +259,7 @@ learner_fast_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_up
   int* gidx = reinterpret_cast<int*>(smem + pl.off_gidx);
   int* slot_t = reinterpret_cast<int*>(smem + pl.off_slot);
   float* par = reinterpret_cast<float*>(smem + pl.off_par);
-  const int Pl = FLAG ? 1028 : pl.Pl;
+  const int Pl = FLAG ? (8 * (1024 / (FLAG ? TC : 1)) + 4) : pl.Pl;
   float *p_mu = par, *p_sg = par + Pl, *p_m1 = par + 2 * Pl, *p_v1 = par + 3 * Pl, *p_m2 = par + 4 * Pl,
         *p_v2 = par + 5 * Pl, *p_tmu = par + 6 * Pl, *p_tsg = par + 7 * Pl;
   float* nzr = reinterpret_cast<float*>(smem + pl.off_nz);      // [3 ring][3 set][Pl]
@@ -277,13 +279,15 @@ learner_fast_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_up
   double* s_pri = reinterpret_cast<double*>(smem + pl.off_sdbl + 1024);
   double* s_tmp = s_pri + 32;
   double* sub = reinterpret_cast<double*>(smem + pl.off_sub);
+  double* plan_old = reinterpret_cast<double*>(smem + pl.off_plan);
   double* cache = reinterpret_cast<double*>(smem + pl.off_cache);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int B = FLAG ? 32 : pl.B, M = FLAG ? 3 : pl.M, A = FLAG ? 2 : pl.A, D = FLAG ? 4 : pl.D, K = D;
   const int E = eng.n_envs, R = eng.ring_rows, BM = B * M, NRq = B + 2 * BM, NX = B + BM, B4 = FLAG ? 32 : pl.B4;
-  const int Us = FLAG ? 128 : pl.Us, nout = FLAG ? 3 : pl.nout, nCh = Us / 4, WS = nCh * 36 + 4, rpi = 1 + 2 * M;
-  const int ipc = FLAG ? 4 : pl.ipc, nOwn = ipc * rpi, nRG = FLAG ? 4 : pl.nRG, rpg = FLAG ? 8 : pl.rpg;
+  const int Us = FLAG ? 1024 / (FLAG ? TC : 1) : pl.Us, nout = FLAG ? 3 : pl.nout, nCh = Us / 4, WS = nCh * 36 + 4, rpi = 1 + 2 * M;
+  const int ipc = FLAG ? 32 / (FLAG ? TC : 1) : pl.ipc, nOwn = ipc * rpi, nRG = FLAG ? (TC == 8 ? 4 : 8) : pl.nRG,
+            rpg = FLAG ? (TC == 8 ? 8 : 4) : pl.rpg;
   const int dueling = FLAG ? (int)SRLX_DUEL_AVERAGE : net.dueling;
   const int n_cache = pl.n_cache;
   const int u0 = rank * Us;
@@ -457,6 +461,52 @@ learner_fast_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_up
       SRLX_FSTAMP(ct == 0, 0);
 
       // ---------------------------------------------------------------- forward: warp = 4-unit chunk(s), lane = row
+      if (FLAG) {
+        // compile-time shape: 1 tile of s rows + 3 tiles of s' rows for each of the two s' forwards; the warp's chunk(s)
+        // accumulate into registers (no read-modify-write of the partial buffer), tiles are independent FMA chains.
+        // A chunk lies entirely in the value half (output 0 only) or in the advantage half (outputs 1, 2) of the head.
+        constexpr int NCHW = TC == 8 ? 2 : 1;
+        float4 acc[7];
+#pragma unroll
+        for (int t = 0; t < 7; ++t) acc[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int cp = 0; cp < NCHW; ++cp) {
+          const int ch = cw + kFCmpWarps * cp;
+          const bool vhalf = (u0 + ch * 4) < 512;
+#pragma unroll
+          for (int set = 0; set < 3; ++set) {
+            const float* ws = weff + set * WS;
+            const float4 W0 = ld4(ws + ch * 16), W1 = ld4(ws + ch * 16 + 4), W2 = ld4(ws + ch * 16 + 8), W3 = ld4(ws + ch * 16 + 12);
+            const float4 Bv = ld4(ws + nCh * 16 + ch * 4);
+            const float* wo = ws + nCh * 20 + ch * 16;
+            const float4 Oa = ld4(wo + (vhalf ? 0 : 4)), Ob = ld4(wo + 8);  // value row, or the two advantage rows
+#pragma unroll
+            for (int tl = 0; tl < (set == 0 ? 1 : 3); ++tl) {
+              const int t = set == 0 ? 0 : (set == 1 ? 1 + tl : 4 + tl);
+              const float4 x = ld4(x_cur + (size_t)((set == 0 ? 0 : 32) + tl * 32 + lane) * 4);
+              float2 a01 = f2(Bv.x, Bv.y), a23 = f2(Bv.z, Bv.w);
+              a01 = __ffma2_rn(f2(W0.x, W0.y), f2(x.x, x.x), a01); a23 = __ffma2_rn(f2(W0.z, W0.w), f2(x.x, x.x), a23);
+              a01 = __ffma2_rn(f2(W1.x, W1.y), f2(x.y, x.y), a01); a23 = __ffma2_rn(f2(W1.z, W1.w), f2(x.y, x.y), a23);
+              a01 = __ffma2_rn(f2(W2.x, W2.y), f2(x.z, x.z), a01); a23 = __ffma2_rn(f2(W2.z, W2.w), f2(x.z, x.z), a23);
+              a01 = __ffma2_rn(f2(W3.x, W3.y), f2(x.w, x.w), a01); a23 = __ffma2_rn(f2(W3.z, W3.w), f2(x.w, x.w), a23);
+              const float2 h01 = f2(fmaxf(a01.x, 0.f), fmaxf(a01.y, 0.f)), h23 = f2(fmaxf(a23.x, 0.f), fmaxf(a23.y, 0.f));
+              float2 ta = __ffma2_rn(h01, f2(Oa.x, Oa.y), f2(0.f, 0.f));
+              ta = __ffma2_rn(h23, f2(Oa.z, Oa.w), ta);
+              if (vhalf) {
+                acc[t].x += ta.x + ta.y;
+              } else {
+                float2 tb = __ffma2_rn(h01, f2(Ob.x, Ob.y), f2(0.f, 0.f));
+                tb = __ffma2_rn(h23, f2(Ob.z, Ob.w), tb);
+                acc[t].y += ta.x + ta.y;
+                acc[t].z += tb.x + tb.y;
+              }
+            }
+          }
+        }
+        float* mypart = part + (size_t)cw * NRq * 4;
+#pragma unroll
+        for (int t = 0; t < 7; ++t) *reinterpret_cast<float4*>(mypart + (size_t)(t * 32 + lane) * 4) = acc[t];
+      } else
       for (int ch = cw; ch < nCh; ch += kFCmpWarps) {
         const bool first = ch < kFCmpWarps;
         float* mypart = part + (size_t)cw * NRq * 4;
@@ -686,14 +736,15 @@ learner_fast_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_up
             gW0 = fmaf(dh, x.x, gW0); gW1 = fmaf(dh, x.y, gW1); gW2 = fmaf(dh, x.z, gW2); gW3 = fmaf(dh, x.w, gW3);
           }
           float* g = part + (size_t)rg * Pl;
-          const float gW[4] = {gW0, gW1, gW2, gW3}, gO[4] = {gO0, gO1, gO2, gO3};
+          const float gW[4] = {gW0, gW1, gW2, gW3};
           if (K == 4) *reinterpret_cast<float4*>(g + u * 4) = make_float4(gW0, gW1, gW2, gW3);
           else
             for (int k = 0; k < K; ++k) g[u * K + k] = gW[k];
           g[Us * K + u] = gb;
           for (int s = 2; s < n_seg; ++s) {
             const FSeg& sg = segs[s];
-            if (sg.kind == FSEG_O && u >= sg.ulo && u < sg.ulo + sg.n) g[sg.l0 + (u - sg.ulo)] = gO[sg.o];
+            if (sg.kind == FSEG_O && u >= sg.ulo && u < sg.ulo + sg.n)
+              g[sg.l0 + (u - sg.ulo)] = sg.o == 0 ? gO0 : (sg.o == 1 ? gO1 : (sg.o == 2 ? gO2 : gO3));
           }
         }
         // output bias (replicated parameter, identical on every CTA): row group 0 holds the sum, the others zero
@@ -735,17 +786,24 @@ learner_fast_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_up
       // ---- update plan of the current batch (per warp: its tree levels mw, mw+4, ...), filled before the targets arrive
       int s_item = 0, s_li = 0x7fffffff;  // sorted lane r: item, its tree index (sorted by root-to-leaf path)
       bool s_valid = false;
-      int p_node[8], p_end[8];
-      double p_old[8];
+      // levels are dealt to memory warps 1..3 (warp 0 keeps the gather / IS weights / polling): slot q < kLc is level
+      // (mw-1) + 3q of the shared-memory-cached top of the tree, slot kLc + q is level clev + (mw-1) + 3q below it
+      constexpr int kLc = 4, kLu = 5, kLv = kLc + kLu;  // 12 cached levels / 3 warps; up to 15 deeper levels / 3 warps
+      const int clev = 31 - __clz(n_cache + 1);         // number of cached levels
+      int p_node[kLv];
+      unsigned long long p_ends = 0;  // 5 bits per slot: last lane of the leader's run
+      double* p_old = plan_old + mt;  // [kLu][FNM]: old values of the uncached nodes, fetched while the forward pass runs
 #pragma unroll
-      for (int q = 0; q < 8; ++q) { p_node[q] = -1; p_end[q] = 0; p_old[q] = 0.0; }
+      for (int q = 0; q < kLv; ++q) p_node[q] = -1;
+      auto level_of = [&](int q) -> int { return q < kLc ? (mw - 1) + 3 * q : clev + (mw - 1) + 3 * (q - kLc); };
+      auto level_ok = [&](int q, int a) -> bool { return q < kLc ? (a < clev && a < dmax) : (a < dmax); };
 
       // PER sample of update `tc` (CTA 0, all memory threads): tree walk -> s_idx / s_pri -> slots to every CTA
-      auto sample_slots = [&](uint64_t tc, int pb, bool stamp) {
 #define SRLX_SSTAMP(slot)                                                                                  \
   do {                                                                                                     \
-    if (eng.dbg_clock && mt == 0 && stamp) eng.dbg_clock[slot] = clock64();                                \
+    if (eng.dbg_clock && mt == ((slot) >= 40 ? 32 : 0) && stamp) eng.dbg_clock[slot] = clock64();           \
   } while (0)
+      auto sample_slots = [&](uint64_t tc, int pb, bool stamp) {
         if (per) {
           const double total = cache[0];
           int idx = 0;
@@ -769,6 +827,7 @@ learner_fast_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_up
           const int pos_l = (1 << k_l) - 2 + 2 * q_l;
           const unsigned c_l = (1u << k_l) - 1u + 2u * (unsigned)q_l;
           const unsigned last_pair = n_nodes > 1 ? (unsigned)n_nodes - 2u : 0u;
+          int rnd = 0;
           while (__any_sync(FULL, !done)) {
             double v0[8], v1[8];
             // unconditional loads from clamped addresses (a predicated load + select makes ptxas wait for every load in
@@ -782,11 +841,13 @@ learner_fast_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_up
               v0[g] = __ldcg(src);
               v1[g] = __ldcg(src + (n_nodes > 1 ? 1 : 0));
             }
+            if (rnd < 3) SRLX_SSTAMP(32 + rnd * 3);
             if (lane < 31) {
 #pragma unroll
               for (int g = 0; g < 8; ++g) *reinterpret_cast<double2*>(wsub + g * kFSubLd + pos_l) = make_double2(v0[g], v1[g]);
             }
             __syncwarp();
+            if (rnd < 3) SRLX_SSTAMP(33 + rnd * 3);
             if (!done) {
               const double* ms = wsub + lane * kFSubLd;
               int rel = 0;
@@ -803,6 +864,8 @@ learner_fast_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_up
               done = 2 * idx + 1 >= n_nodes;
             }
             __syncwarp();
+            if (rnd < 3) SRLX_SSTAMP(34 + rnd * 3);
+            ++rnd;
           }
           SRLX_SSTAMP(23);
           if (own) {  // a zero-priority leaf is re-drawn (proportional_memory.py:150-152), sequentially
@@ -940,23 +1003,29 @@ learner_fast_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_up
         s_li = s_valid ? s_idx[s_item] : 0x7ffffffe;
         const unsigned sip1 = (unsigned)s_li + 1u;
         const int sd = 31 - __clz(sip1);
+        p_ends = 0;
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const int a = mw + kFMemWarps * q;
+        for (int q = 0; q < kLv; ++q) {
+          const int a = level_of(q);
           p_node[q] = -1;
-          p_end[q] = lane;
-          if (a < dmax) {
+          if (level_ok(q, a)) {
             const bool has = s_valid && sd > a;
             const int node = has ? (int)(sip1 >> (sd - a)) - 1 : -1;
             const int prevn = __shfl_up_sync(FULL, node, 1), nextn = __shfl_down_sync(FULL, node, 1);
             const bool lead = has && (lane == 0 || prevn != node);
             const bool last = has && (lane == 31 || nextn != node);
             const unsigned bl = __ballot_sync(FULL, last);
-            p_end[q] = lane + __ffs(bl >> lane) - 1;  // first "last" flag at or after this lane (leaders always find one)
+            const int e = (lane + __ffs(bl >> lane) - 1) & 31;  // first "last" flag at or after this lane (leaders find one)
+            p_ends |= (unsigned long long)e << (5 * q);
             p_node[q] = lead ? node : -1;
           }
-          p_old[q] = __ldcg(eng.tree + (p_node[q] >= 0 ? p_node[q] : 0));  // unconditional: all levels in flight at once
         }
+        // uncached levels: unconditional loads (node 0 for non-leaders), all in flight at once, then parked in shared memory
+        double ov[kLu];
+#pragma unroll
+        for (int q = 0; q < kLu; ++q) ov[q] = __ldcg(eng.tree + (p_node[kLc + q] >= 0 ? p_node[kLc + q] : 0));
+#pragma unroll
+        for (int q = 0; q < kLu; ++q) p_old[q * FNM] = ov[q];
       };
 
       // ProportionalMemory.update of the current batch (proportional_memory.py:171-177).  The new priorities, their
@@ -964,14 +1033,15 @@ learner_fast_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_up
       // of its levels: new = old + (sum of the changes of the items below the node).  The reference adds the changes one
       // item at a time in batch order; here a node's changes are summed in path order as a difference of running sums
       // (exact for the common single-item run) -- a different association of the same fp64 terms, see DESIGN.md.
-      auto apply_update = [&](const float* agb) {
+      auto apply_update = [&](const float* agb, bool stamp) {
         double pnew = 0.0;
         if (s_valid) pnew = pow(fabs((double)fabsf(agb[s_item * 8 + 4] - agb[s_item * 8 + 5])) + eng.per_epsilon, eng.per_alpha);
+        SRLX_SSTAMP(40);
         const int prevli = __shfl_up_sync(FULL, s_li, 1), nextli = __shfl_down_sync(FULL, s_li, 1);
         const double prevp = __shfl_up_sync(FULL, pnew, 1);
         const bool dupprev = lane > 0 && prevli == s_li;  // duplicates of a leaf are consecutive, in batch order
         const double chg = s_valid ? pnew - (dupprev ? prevp : s_pri[s_item]) : 0.0;
-        if (mw == 0) {
+        if (mw == 1) {
           if (s_valid && (lane == 31 || nextli != s_li)) {  // the last item touching a leaf wins
             __stcg(eng.tree + s_li, pnew);
             if (s_li < n_cache) cache[s_li] = pnew;
@@ -980,6 +1050,7 @@ learner_fast_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_up
           for (int s = 16; s > 0; s >>= 1) mx = fmax(mx, __shfl_xor_sync(FULL, mx, s));
           if (lane == 0 && mx > sc->max_priority) sc->max_priority = mx;
         }
+        SRLX_SSTAMP(41);
         double P = chg;  // inclusive running sum over the sorted lanes
 #pragma unroll
         for (int s = 1; s < 32; s <<= 1) {
@@ -988,19 +1059,23 @@ learner_fast_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_up
         }
         double Pex = __shfl_up_sync(FULL, P, 1);
         if (lane == 0) Pex = 0.0;
+        SRLX_SSTAMP(42);
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const int a = mw + kFMemWarps * q;
-          if (a < dmax) {
-            const double Pe = __shfl_sync(FULL, P, p_end[q]);
+        for (int q = 0; q < kLv; ++q) {
+          const int a = level_of(q);
+          if (level_ok(q, a)) {
+            const int e = (int)((p_ends >> (5 * q)) & 31ull);
+            const double Pe = __shfl_sync(FULL, P, e);
             if (p_node[q] >= 0) {
-              const double sum = (p_end[q] == lane) ? chg : (Pe - Pex);
-              const double nv = p_old[q] + sum;
+              const double sum = (e == lane) ? chg : (Pe - Pex);
+              const double old = q < kLc ? cache[p_node[q]] : p_old[(q < kLc ? 0 : q - kLc) * FNM];
+              const double nv = old + sum;
               __stcg(eng.tree + p_node[q], nv);
-              if (p_node[q] < n_cache) cache[p_node[q]] = nv;
+              if (q < kLc) cache[p_node[q]] = nv;
             }
           }
         }
+        SRLX_SSTAMP(43);
       };
 
       // loss / counters / debug taps of update `u` (off the critical path)
@@ -1136,13 +1211,15 @@ learner_fast_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_up
         }
         if (rank == 0) {
           // ---- off the critical path, while the compute warps run forward(t) -------------------------------------------
-          if (mw == 1) send_weights(tc, parb);
-          if (mw == 2 && upd > 0) bookkeeping(upd - 1);
-          if (per) {
+          if (mw == 0) {
+            send_weights(tc, parb);
+            if (upd > 0) bookkeeping(upd - 1);
+          } else if (per) {
             plan_update();
-            if (own && upd + 1 < n_updates) u_next = draw(tc + 1, own_i, 0);
           }
+          if (per && own && upd + 1 < n_updates) u_next = draw(tc + 1, own_i, 0);
           SRLX_FSTAMP(mt == 0, 26);
+          SRLX_FSTAMP(mt == 32, 27);
         }
         if (mw == 0) {
           mbar_wait_sleep(&mbar[MB_AG], parb);  // update t's targets are known everywhere: forward(t) is over in every CTA
@@ -1156,7 +1233,7 @@ learner_fast_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_up
           named_bar_sync(FBAR_MEM, FNM);
           SRLX_FSTAMP(mt == 0, 18);
           if (per) {
-            apply_update(ag + (size_t)parb * B * 8);
+            if (mw != 0) apply_update(ag + (size_t)parb * B * 8, upd + 2 == n_updates);
             named_bar_sync(FBAR_MEM, FNM);
           }
           SRLX_FSTAMP(mt == 0, 20);
@@ -1164,7 +1241,7 @@ learner_fast_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_up
           SRLX_FSTAMP(mt == 0, 21);
         }
       }
-      if (rank == 0 && mw == 2) bookkeeping(n_updates - 1);
+      if (rank == 0 && mw == 0) bookkeeping(n_updates - 1);
     }
   done_roles:;
   }
@@ -1205,10 +1282,10 @@ static int learn_fast(const srlx_engine* eng, uint32_t n_updates, uintptr_t cuda
   const long long n_nodes = 2ll * eng->ring_rows * eng->n_envs - 1;
   const FPlan pl = make_fplan(*eng, C, n_nodes);
   (void)max_smem;
-  // the reference's Rainbow default shape gets the instantiation with compile-time loop bounds
+  // the reference's Rainbow default shape gets the instantiations with compile-time loop bounds
   const bool flag = eng->batch_size == 32 && eng->multisteps == 3 && eng->n_actions == 2 && eng->obs_dim == 4 &&
-                    eng->net.out_dim[1] == 3 && eng->net.dueling == SRLX_DUEL_AVERAGE && eng->net.out_dim[0] == 1024 && C == 8;
-  auto kern = flag ? learner_fast_kernel<true> : learner_fast_kernel<false>;
+                    eng->net.out_dim[1] == 3 && eng->net.dueling == SRLX_DUEL_AVERAGE && eng->net.out_dim[0] == 1024;
+  auto kern = (flag && C == 8) ? learner_fast_kernel<8> : (flag && C == 16) ? learner_fast_kernel<16> : learner_fast_kernel<0>;
   SRLX_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.total));
   if (C > 8) SRLX_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
   const size_t per_update = (size_t)C * 3 * pl.Pl * 4;
@@ -1222,6 +1299,34 @@ static int learn_fast(const srlx_engine* eng, uint32_t n_updates, uintptr_t cuda
     if (v >= 1 && (uint32_t)v < chunk) chunk = (uint32_t)v;
   }
   cudaStream_t stream = (cudaStream_t)cuda_stream;
+  // L2 set-aside for the tree (device-wide limit, set once per device; SRLX_L2_PERSIST=0 disables)
+  size_t l2_window_bytes = 0;
+  {
+    const char* e = getenv("SRLX_L2_PERSIST");
+    if (eng->mem_kind == SRLX_MEM_PROPORTIONAL && !(e && e[0] == '0')) {
+      static int persist_dev[64] = {};  // 0 = unknown, 1 = configured, -1 = unavailable
+      static size_t persist_max_window[64] = {};
+      int dev = 0;
+      SRLX_CHECK_CUDA(cudaGetDevice(&dev));
+      const size_t tree_bytes = (size_t)(2ll * eng->ring_rows * eng->n_envs - 1) * 8;
+      if (dev >= 0 && dev < 64) {
+        if (persist_dev[dev] == 0) {
+          int max_persist = 0, max_window = 0;
+          cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev);
+          cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, dev);
+          size_t want = tree_bytes < (size_t)max_persist ? tree_bytes : (size_t)max_persist;
+          if (want > 0 && max_window > 0 && cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess) {
+            persist_dev[dev] = 1;
+            persist_max_window[dev] = (size_t)max_window;
+          } else {
+            persist_dev[dev] = -1;
+            cudaGetLastError();
+          }
+        }
+        if (persist_dev[dev] == 1) l2_window_bytes = tree_bytes < persist_max_window[dev] ? tree_bytes : persist_max_window[dev];
+      }
+    }
+  }
   for (uint32_t done = 0; done < n_updates;) {
     const uint32_t n = (n_updates - done) < chunk ? (n_updates - done) : chunk;
     if (eng->net.noisy) {
@@ -1234,13 +1339,22 @@ static int learn_fast(const srlx_engine* eng, uint32_t n_updates, uintptr_t cuda
     cfg.blockDim = dim3(FNT, 1, 1);
     cfg.dynamicSmemBytes = pl.total;
     cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = (unsigned)C;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
+    if (l2_window_bytes > 0) {  // keep the SumTree resident in L2: its deep levels are re-read at random every update
+      attr[1].id = cudaLaunchAttributeAccessPolicyWindow;
+      attr[1].val.accessPolicyWindow.base_ptr = (void*)eng->tree;
+      attr[1].val.accessPolicyWindow.num_bytes = l2_window_bytes;
+      attr[1].val.accessPolicyWindow.hitRatio = 1.0f;
+      attr[1].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+      attr[1].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+      cfg.numAttrs = 2;
+    }
     SRLX_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, *eng, n, (const float*)eng->noise_scratch));
     count_launch();
     SRLX_CHECK_CUDA(cudaGetLastError());
