@@ -3,7 +3,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsrlx.so")
+LIB_PATH = os.environ.get("SRLX_LIB") or os.path.join(_HERE, "libsrlx.so")  # SRLX_LIB: diagnostic builds (phase clocks)
 
 SRLX_MAX_LAYERS = 6
 ENV_GRID, ENV_CARTPOLE = 0, 1

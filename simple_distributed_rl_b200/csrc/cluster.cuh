@@ -45,6 +45,10 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 }
 // try_wait with a suspend-time hint: the warp sleeps in hardware until the phase completes (or the hint expires) instead
 // of re-issuing the poll every few dozen cycles -- pollers share the MIO queue with the warps doing the actual work.
+#ifndef SRLX_MBAR_HINT
+#define SRLX_MBAR_HINT 20000u
+#endif
+constexpr uint32_t kMbarSuspendHint = SRLX_MBAR_HINT;
 __device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity) {
   uint32_t ok = 0;
   const uint32_t addr = smem_u32(bar);
@@ -56,7 +60,7 @@ __device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity) 
         "  selp.u32 %0, 1, 0, p;\n"
         "}\n"
         : "=r"(ok)
-        : "r"(addr), "r"(parity), "r"(20000u)
+        : "r"(addr), "r"(parity), "r"(kMbarSuspendHint)
         : "memory");
   } while (!ok);
 }

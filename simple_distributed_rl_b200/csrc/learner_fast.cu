@@ -32,7 +32,7 @@ int learn_generic(const srlx_engine* eng, uint32_t n_updates, uintptr_t cuda_str
 
 constexpr int kFCmpWarps = 16, kFMemWarps = 4;
 constexpr int FNC = kFCmpWarps * 32, FNM = kFMemWarps * 32, FNT = FNC + FNM;
-constexpr int kFMaxC = 16, kFMaxSeg = 8, kFCacheLevels = 12, kFMaxChunk = 512, kFSubLd = 66;
+constexpr int kFMaxC = 16, kFMaxSeg = 8, kFCacheLevels = 12, kFMaxChunk = 256, kFSubLd = 66;
 enum { FBAR_CMP = 1, FBAR_MEM = 2 };
 enum { FSEG_W = 0, FSEG_B = 1, FSEG_O = 2, FSEG_OB = 3 };
 enum { MB_RS = 0, MB_AG, MB_S, MB_WT, MB_XR, MB_NZ0, MB_NZ1, MB_NZ2, MB_COUNT };
@@ -53,7 +53,7 @@ struct FPlan {
 
 __host__ __device__ inline int fast_pick_cluster(const srlx_net& net, int want) {
   const int Uh = net.out_dim[0];
-  int c = want > 0 ? want : 8;
+  int c = want > 0 ? want : 16;
   if (c > kFMaxC) c = kFMaxC;
   while (c > 1 && (Uh % c != 0 || (Uh / c) % 4 != 0)) c >>= 1;
   if (Uh % c != 0 || (Uh / c) % 4 != 0) return 0;
@@ -89,7 +89,7 @@ __host__ __device__ inline bool fast_shape_ok(const srlx_engine& eng) {
          eng.multisteps <= SRLX_MAX_MULTISTEPS && (2ll * eng.ring_rows * eng.n_envs) < (1ll << 27);
 }
 
-__host__ __device__ inline FPlan make_fplan(const srlx_engine& eng, int C, long long n_tree_nodes) {
+__host__ __device__ inline FPlan make_fplan(const srlx_engine& eng, int C, long long n_tree_nodes, int max_cache_levels) {
   FPlan p;
   const srlx_net& net = eng.net;
   p.C = C;
@@ -139,12 +139,12 @@ __host__ __device__ inline FPlan make_fplan(const srlx_engine& eng, int C, long 
   p.off_samp_slot = take((size_t)2 * p.B4 * 4);
   p.off_samp_w = take((size_t)2 * p.B4 * 4);
   p.off_sdbl = take(2048);  // s_idx, s_att, sperm[4][32] (int), then s_pri, s_tmp (double)
-  p.off_plan = take(eng.mem_kind == SRLX_MEM_PROPORTIONAL ? (size_t)5 * FNM * 8 : 0);
+  p.off_plan = take(eng.mem_kind == SRLX_MEM_PROPORTIONAL ? (size_t)FNM * (5 * 8 + 2 * 9 * 4) : 0);  // old[5], node[9], end[9]
   p.n_cache = 0;
   if (eng.mem_kind == SRLX_MEM_PROPORTIONAL) {
     p.off_sub = take((size_t)kFMemWarps * 8 * kFSubLd * 8);
     int lev = 0;
-    while (lev < kFCacheLevels && ((1ll << (lev + 1)) - 1) <= n_tree_nodes) ++lev;
+    while (lev < max_cache_levels && lev < kFCacheLevels && ((1ll << (lev + 1)) - 1) <= n_tree_nodes) ++lev;
     p.n_cache = (int)((1ll << lev) - 1);
   } else {
     p.off_sub = take(0);
@@ -185,16 +185,31 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
 __device__ __forceinline__ float2 f2(float a, float b) { return make_float2(a, b); }
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 
+// x^a for the priority (|td| + eps)^alpha: exp(a log x) is ~2x shorter than pow() on the dependent chain td -> SumTree
+// update -> next sample (456 vs 821 cycles, tools/ubench) and differs from it by a few ulp of fp64
+// Out of line on purpose: the per-update code of a CTA has to fit the SM's instruction cache (every first-touched
+// 128-byte line of straight-line code costs a fetch from L2 on the serial chain), so the big scalar
+// routines exist once per kernel.
+__device__ __noinline__ double pow_chain(double x, double a) { return x > 0.0 ? exp(a * log(x)) : pow(x, a); }
+__device__ __noinline__ uint4 philox_ni(uint64_t seed, uint32_t stream, uint32_t a, uint32_t b, uint32_t c) {
+  return philox(seed, stream, a, b, c);
+}
+
 struct FScal {
   double max_priority, loss_sum, last_loss;
   unsigned long long retries;
   unsigned int sync_count;
 };
 
+// phase clocks (tools/phase_clocks.py): compiled in only with -DSRLX_STAMPS (libsrlx_stamps.so), they cost code space
+#ifdef SRLX_STAMPS
 #define SRLX_FSTAMP(cond, slot)                                                                                    \
   do {                                                                                                             \
     if (eng.dbg_clock && rank == 0 && (cond) && upd + 2 == n_updates) eng.dbg_clock[slot] = clock64();             \
   } while (0)
+#else
+#define SRLX_FSTAMP(cond, slot) do { } while (0)
+#endif
 
 // =====================================================================================================================
 // N(0,1) tensors of `n_updates` consecutive updates, CTA-local order: out[((u * C + rank) * 3 + set) * Pl + i].
@@ -238,7 +253,8 @@ __global__ void __launch_bounds__(128) noise_precompute_kernel(const __grid_cons
 // head of 2 x 512 units) on a cluster of TC CTAs, every loop bound a compile-time constant; TC = 0: same code, run-time bounds.
 template <int TC>
 __global__ void __launch_bounds__(FNT, 1)
-learner_fast_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_updates, const float* __restrict__ noise) {
+learner_fast_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_updates, const float* __restrict__ noise,
+                    const int max_cache_levels) {
   extern __shared__ __align__(16) unsigned char smem[];
   cg::cluster_group cluster = cg::this_cluster();
   constexpr bool FLAG = TC > 0;
@@ -246,7 +262,7 @@ learner_fast_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_up
   const int rank = (int)cluster.block_rank();
   const srlx_net& net = eng.net;
   const int cap = eng.ring_rows * eng.n_envs, n_nodes = 2 * cap - 1, cap1 = cap - 1;
-  const FPlan pl = make_fplan(eng, C, n_nodes);
+  const FPlan pl = make_fplan(eng, C, n_nodes, max_cache_levels);
 
   uint64_t* mbar = reinterpret_cast<uint64_t*>(smem + pl.off_mbar);
   FSeg* segs = reinterpret_cast<FSeg*>(smem + pl.off_seg);
@@ -280,6 +296,8 @@ learner_fast_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_up
   double* s_tmp = s_pri + 32;
   double* sub = reinterpret_cast<double*>(smem + pl.off_sub);
   double* plan_old = reinterpret_cast<double*>(smem + pl.off_plan);
+  int* plan_node = reinterpret_cast<int*>(smem + pl.off_plan + (size_t)FNM * 5 * 8);
+  int* plan_end = plan_node + 9 * FNM;
   double* cache = reinterpret_cast<double*>(smem + pl.off_cache);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -389,6 +407,8 @@ learner_fast_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_up
     // ================================================ COMPUTE WARPS ================================================
     const int ct = tid, cw = warp;
     const float b1 = (float)eng.adam_beta1, b2 = (float)eng.adam_beta2, aeps = (float)eng.adam_eps;
+    const float gamma = (float)eng.discount, rh = (float)eng.retrace_h, delta = (float)eng.huber_delta;
+    const bool ddqn = eng.enable_double_dqn != 0, rescale = eng.enable_rescale != 0;
 
     // Adam (update `upd`, if do_adam) + target sync + effective weights of the next update: one pass over the CTA's parameters
     auto finish = [&](bool do_adam, uint32_t upd, bool build_next) {
@@ -564,6 +584,7 @@ learner_fast_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_up
           const int w = row - B; item = w / M; j = 1 + (w - item * M);
         } else { const int w = row - B - BM; item = w / M; j = 1 + M + (w - item * M); }
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
         for (int w = half; w < nActive; w += 2) {
           const float4 o = ld4(part + ((size_t)w * NRq + row) * 4);
           v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
@@ -585,6 +606,7 @@ learner_fast_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_up
           const int set = j == 0 ? 0 : (j <= M ? 1 : 2);
           if (set == 1 && !need_online_next) continue;
           float4 v = ld4(weff + set * WS + nCh * 36);  // effective output bias of this forward call
+#pragma unroll 4
           for (int c = 0; c < C; ++c) {
             const float4 o = ld4(rs + (((size_t)parb * C + c) * nOwn + w) * 4);
             v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
@@ -629,22 +651,22 @@ learner_fast_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_up
             const float* qs = qown + (size_t)(ii * rpi) * 4;
             const float* qon = qs + 4;             // online(s')  [M][4]
             const float* qtg = qs + 4 * (1 + M);   // target(s')  [M][4]
-            const float gamma = (float)eng.discount;
             float target = 0.f, retrace = 1.f;
+#pragma unroll 1
             for (int k = 0; k < M; ++k) {
               const float* qo = qon + k * 4;
               const float* qt = qtg + k * 4;
-              const float* qsel = eng.enable_double_dqn ? qo : qt;
+              const float* qsel = ddqn ? qo : qt;
               int am = 0;
               float best = qsel[0];
               for (int a = 1; a < A; ++a)
                 if (qsel[a] > best) { best = qsel[a]; am = a; }  // np.argmax: first max wins
               // Retrace with the reference's index shift (rainbow.py:267): action taken at s_k vs greedy action at s_{k+1}
-              if (k >= 1) retrace = retrace * ((float)eng.retrace_h * ((w_act[i * M + k] == am) ? 1.f : 0.f));
+              if (k >= 1) retrace = retrace * (rh * ((w_act[i * M + k] == am) ? 1.f : 0.f));
               float maxq = qt[am];
-              if (eng.enable_rescale) maxq = inverse_rescaling_f(maxq);
+              if (rescale) maxq = inverse_rescaling_f(maxq);
               float gain = w_rew[i * M + k] + ((1.0f - w_term[i * M + k]) * gamma) * maxq;
-              if (eng.enable_rescale) gain = rescaling_f(gain);
+              if (rescale) gain = rescaling_f(gain);
               float qk = 0.f;  // the first step is learnt by the trainer itself (rainbow.py:232-234)
               if (k >= 1) qk = qon[(k - 1) * 4 + w_act[i * M + k]];
               const float td = gain - qk;
@@ -655,7 +677,6 @@ learner_fast_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_up
             const float w = samp_w[parb * B4 + i];
             const float d = q * w - target * w;
             const float ad = fabsf(d);
-            const float delta = (float)eng.huber_delta;
             const float lterm = (ad <= delta) ? 0.5f * d * d : delta * (ad - 0.5f * delta);
             const float dq = fminf(fmaxf(d, -delta), delta) * w / (float)B;
             float dr[4] = {0.f, 0.f, 0.f, 0.f};
@@ -722,6 +743,7 @@ learner_fast_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_up
           const float wi0 = wi[0], wi1 = wi[4], wi2 = wi[8], wi3 = wi[12], bi = wS[nCh * 16 + u];
           float gW0 = 0.f, gW1 = 0.f, gW2 = 0.f, gW3 = 0.f, gb = 0.f, gO0 = 0.f, gO1 = 0.f, gO2 = 0.f, gO3 = 0.f;
           const int r0 = rg * rpg, r1 = min(B, r0 + rpg);
+#pragma unroll 2
           for (int r = r0; r < r1; ++r) {
             const float4 dr = ld4(agb + (size_t)r * 8);
             const float4 x = ld4(x_cur + (size_t)r * 4);
@@ -780,7 +802,7 @@ learner_fast_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_up
       const bool own = lane < 8 && own_i < B;
       double u_next = 0.0;  // pre-drawn uniform of the owner's next sample
       auto draw = [&](uint64_t tc, int i, int k) -> double {
-        const uint4 w = philox(eng.seed, STREAM_SAMPLE, (uint32_t)i | ((uint32_t)k << 16), (uint32_t)tc, (uint32_t)(tc >> 32));
+        const uint4 w = philox_ni(eng.seed, STREAM_SAMPLE, (uint32_t)i | ((uint32_t)k << 16), (uint32_t)tc, (uint32_t)(tc >> 32));
         return u01_f64(w.x, w.y);
       };
       // ---- update plan of the current batch (per warp: its tree levels mw, mw+4, ...), filled before the targets arrive
@@ -790,30 +812,38 @@ learner_fast_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_up
       // (mw-1) + 3q of the shared-memory-cached top of the tree, slot kLc + q is level clev + (mw-1) + 3q below it
       constexpr int kLc = 4, kLu = 5, kLv = kLc + kLu;  // 12 cached levels / 3 warps; up to 15 deeper levels / 3 warps
       const int clev = 31 - __clz(n_cache + 1);         // number of cached levels
-      int p_node[kLv];
-      unsigned long long p_ends = 0;  // 5 bits per slot: last lane of the leader's run
-      double* p_old = plan_old + mt;  // [kLu][FNM]: old values of the uncached nodes, fetched while the forward pass runs
-#pragma unroll
-      for (int q = 0; q < kLv; ++q) p_node[q] = -1;
+      // per-thread plan, parked in shared memory ([slot][thread], conflict-free) so the level loops stay rolled:
+      int* p_node = plan_node + mt;   // [kLv][FNM] node a leader lane writes at slot q, -1 otherwise
+      int* p_end = plan_end + mt;     // [kLv][FNM] last lane of the leader's run
+      double* p_old = plan_old + mt;  // [kLu][FNM] old values of the uncached nodes, fetched while the forward pass runs
       auto level_of = [&](int q) -> int { return q < kLc ? (mw - 1) + 3 * q : clev + (mw - 1) + 3 * (q - kLc); };
       auto level_ok = [&](int q, int a) -> bool { return q < kLc ? (a < clev && a < dmax) : (a < dmax); };
 
       // PER sample of update `tc` (CTA 0, all memory threads): tree walk -> s_idx / s_pri -> slots to every CTA
+#ifdef SRLX_STAMPS
 #define SRLX_SSTAMP(slot)                                                                                  \
   do {                                                                                                     \
     if (eng.dbg_clock && mt == ((slot) >= 40 ? 32 : 0) && stamp) eng.dbg_clock[slot] = clock64();           \
   } while (0)
+#else
+#define SRLX_SSTAMP(slot) do { (void)stamp; } while (0)
+#endif
       auto sample_slots = [&](uint64_t tc, int pb, bool stamp) {
         if (per) {
-          const double total = cache[0];
+          const double total = *reinterpret_cast<volatile double*>(cache);
+          SRLX_SSTAMP(28);
           int idx = 0;
           double val = 0.0, pcur = 0.0;
           if (own) {  // (a) the cached top levels, out of shared memory
             val = u_next * total;
-            while (2 * idx + 1 < n_cache) {
+            // branch-free: the cached top is a complete binary tree, every lane walks clev - 1 levels
+#pragma unroll 1
+            for (int l = 1; l < clev; ++l) {
               const double tl = cache[2 * idx + 1];
-              if (val <= tl) idx = 2 * idx + 1;
-              else { val -= tl; idx = 2 * idx + 2; }
+              const bool right = !(val <= tl);
+              const double vr = val - tl;
+              val = right ? vr : val;
+              idx = 2 * idx + 1 + (right ? 1 : 0);
             }
             pcur = cache[idx];
           }
@@ -841,30 +871,33 @@ learner_fast_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_up
               v0[g] = __ldcg(src);
               v1[g] = __ldcg(src + (n_nodes > 1 ? 1 : 0));
             }
-            if (rnd < 3) SRLX_SSTAMP(32 + rnd * 3);
+            SRLX_SSTAMP(32 + rnd * 3);
             if (lane < 31) {
 #pragma unroll
               for (int g = 0; g < 8; ++g) *reinterpret_cast<double2*>(wsub + g * kFSubLd + pos_l) = make_double2(v0[g], v1[g]);
             }
             __syncwarp();
-            if (rnd < 3) SRLX_SSTAMP(33 + rnd * 3);
+            SRLX_SSTAMP(33 + rnd * 3);
             if (!done) {
               const double* ms = wsub + lane * kFSubLd;
               int rel = 0;
-#pragma unroll
-              for (int k = 1; k <= 5; ++k) {
+#pragma unroll 1
+              for (int k = 1; k <= 5; ++k) {  // branch-free; a lane that reached its leaf keeps its state
                 const int left = 2 * idx + 1;
-                if (left < n_nodes) {
-                  const int base = (1 << k) - 2 + 2 * rel;
-                  const double2 ch = *reinterpret_cast<const double2*>(ms + base);
-                  if (val <= ch.x) { idx = left; rel = 2 * rel; pcur = ch.x; }
-                  else { val -= ch.x; pcur = ch.y; idx = left + 1; rel = 2 * rel + 1; }
-                }
+                const bool act = left < n_nodes;
+                const int base = (1 << k) - 2 + 2 * rel;
+                const double2 ch = *reinterpret_cast<const double2*>(ms + base);
+                const bool right = !(val <= ch.x);
+                const double vr = val - ch.x;
+                val = (act && right) ? vr : val;
+                pcur = act ? (right ? ch.y : ch.x) : pcur;
+                idx = act ? left + (right ? 1 : 0) : idx;
+                rel = act ? 2 * rel + (right ? 1 : 0) : 0;
               }
               done = 2 * idx + 1 >= n_nodes;
             }
             __syncwarp();
-            if (rnd < 3) SRLX_SSTAMP(34 + rnd * 3);
+            SRLX_SSTAMP(34 + rnd * 3);
             ++rnd;
           }
           SRLX_SSTAMP(23);
@@ -911,7 +944,7 @@ learner_fast_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_up
             for (int i = 0; i < B; ++i) {
               uint32_t pick = 0;
               for (int k = 0; k < 65536; ++k) {
-                const uint4 w = philox(eng.seed, STREAM_UNIFORM_SAMPLE, (uint32_t)i | ((uint32_t)k << 16), (uint32_t)tc, (uint32_t)(tc >> 32));
+                const uint4 w = philox_ni(eng.seed, STREAM_UNIFORM_SAMPLE, (uint32_t)i | ((uint32_t)k << 16), (uint32_t)tc, (uint32_t)(tc >> 32));
                 pick = u_below(w.x, n_valid);
                 bool dup = false;
                 for (int j = 0; j < i; ++j) dup |= (s_idx[j] == (int)pick);
@@ -955,7 +988,7 @@ learner_fast_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_up
           const double stepd = (tc > 0) ? (double)(tc - 1) : 0.0;
           double beta = eng.per_beta_initial + (1.0 - eng.per_beta_initial) * stepd / eng.per_beta_steps;
           beta = beta > 1.0 ? 1.0 : beta;
-          const double w = lane < B ? pow((double)mem_size * (s_pri[lane] / total), -beta) : 0.0;
+          const double w = lane < B ? pow_chain((double)mem_size * (s_pri[lane] / total), -beta) : 0.0;
           double mx = w;
           for (int s = 16; s > 0; s >>= 1) mx = fmax(mx, __shfl_xor_sync(FULL, mx, s));
           wv = w / mx;
@@ -989,7 +1022,7 @@ learner_fast_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_up
         const int d = 31 - __clz(ip1);
         const unsigned key = v ? (ip1 << (31 - d)) : 0xffffffffu;
         int rank_l = 0;
-#pragma unroll 8
+#pragma unroll 4
         for (int j = 0; j < 32; ++j) {
           const unsigned kj = __shfl_sync(FULL, key, j);
           rank_l += (kj < key || (kj == key && j < lane)) ? 1 : 0;
@@ -1003,11 +1036,10 @@ learner_fast_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_up
         s_li = s_valid ? s_idx[s_item] : 0x7ffffffe;
         const unsigned sip1 = (unsigned)s_li + 1u;
         const int sd = 31 - __clz(sip1);
-        p_ends = 0;
-#pragma unroll
+#pragma unroll 1
         for (int q = 0; q < kLv; ++q) {
           const int a = level_of(q);
-          p_node[q] = -1;
+          int pn = -1, pe = lane;
           if (level_ok(q, a)) {
             const bool has = s_valid && sd > a;
             const int node = has ? (int)(sip1 >> (sd - a)) - 1 : -1;
@@ -1015,15 +1047,19 @@ learner_fast_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_up
             const bool lead = has && (lane == 0 || prevn != node);
             const bool last = has && (lane == 31 || nextn != node);
             const unsigned bl = __ballot_sync(FULL, last);
-            const int e = (lane + __ffs(bl >> lane) - 1) & 31;  // first "last" flag at or after this lane (leaders find one)
-            p_ends |= (unsigned long long)e << (5 * q);
-            p_node[q] = lead ? node : -1;
+            pe = (lane + __ffs(bl >> lane) - 1) & 31;  // first "last" flag at or after this lane (leaders find one)
+            pn = lead ? node : -1;
           }
+          p_node[q * FNM] = pn;
+          p_end[q * FNM] = pe;
         }
         // uncached levels: unconditional loads (node 0 for non-leaders), all in flight at once, then parked in shared memory
         double ov[kLu];
 #pragma unroll
-        for (int q = 0; q < kLu; ++q) ov[q] = __ldcg(eng.tree + (p_node[kLc + q] >= 0 ? p_node[kLc + q] : 0));
+        for (int q = 0; q < kLu; ++q) {
+          const int pn = p_node[(kLc + q) * FNM];
+          ov[q] = __ldcg(eng.tree + (pn >= 0 ? pn : 0));
+        }
 #pragma unroll
         for (int q = 0; q < kLu; ++q) p_old[q * FNM] = ov[q];
       };
@@ -1035,7 +1071,7 @@ learner_fast_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_up
       // (exact for the common single-item run) -- a different association of the same fp64 terms, see DESIGN.md.
       auto apply_update = [&](const float* agb, bool stamp) {
         double pnew = 0.0;
-        if (s_valid) pnew = pow(fabs((double)fabsf(agb[s_item * 8 + 4] - agb[s_item * 8 + 5])) + eng.per_epsilon, eng.per_alpha);
+        if (s_valid) pnew = pow_chain(fabs((double)fabsf(agb[s_item * 8 + 4] - agb[s_item * 8 + 5])) + eng.per_epsilon, eng.per_alpha);
         SRLX_SSTAMP(40);
         const int prevli = __shfl_up_sync(FULL, s_li, 1), nextli = __shfl_down_sync(FULL, s_li, 1);
         const double prevp = __shfl_up_sync(FULL, pnew, 1);
@@ -1046,9 +1082,6 @@ learner_fast_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_up
             __stcg(eng.tree + s_li, pnew);
             if (s_li < n_cache) cache[s_li] = pnew;
           }
-          double mx = pnew;
-          for (int s = 16; s > 0; s >>= 1) mx = fmax(mx, __shfl_xor_sync(FULL, mx, s));
-          if (lane == 0 && mx > sc->max_priority) sc->max_priority = mx;
         }
         SRLX_SSTAMP(41);
         double P = chg;  // inclusive running sum over the sorted lanes
@@ -1060,19 +1093,16 @@ learner_fast_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_up
         double Pex = __shfl_up_sync(FULL, P, 1);
         if (lane == 0) Pex = 0.0;
         SRLX_SSTAMP(42);
-#pragma unroll
+#pragma unroll 3
         for (int q = 0; q < kLv; ++q) {
-          const int a = level_of(q);
-          if (level_ok(q, a)) {
-            const int e = (int)((p_ends >> (5 * q)) & 31ull);
-            const double Pe = __shfl_sync(FULL, P, e);
-            if (p_node[q] >= 0) {
-              const double sum = (e == lane) ? chg : (Pe - Pex);
-              const double old = q < kLc ? cache[p_node[q]] : p_old[(q < kLc ? 0 : q - kLc) * FNM];
-              const double nv = old + sum;
-              __stcg(eng.tree + p_node[q], nv);
-              if (q < kLc) cache[p_node[q]] = nv;
-            }
+          const int pn = p_node[q * FNM], e = p_end[q * FNM];
+          const double Pe = __shfl_sync(FULL, P, e);
+          if (pn >= 0) {
+            const double sum = (e == lane) ? chg : (Pe - Pex);
+            const double old = q < kLc ? cache[pn] : p_old[(q < kLc ? 0 : q - kLc) * FNM];
+            const double nv = old + sum;
+            __stcg(eng.tree + pn, nv);
+            if (q < kLc) cache[pn] = nv;
           }
         }
         SRLX_SSTAMP(43);
@@ -1146,7 +1176,7 @@ learner_fast_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_up
             for (int k = 0; k < 3; ++k) {
               if (ended) {  // padded tail record: random action, reward 0, terminated 1, state = last next_state (rainbow.py:358-371)
                 const uint64_t gp = g_item + (uint64_t)k;
-                const uint4 pw = philox(eng.seed, STREAM_PAD_ACTION, (uint32_t)e, (uint32_t)gp, (uint32_t)(gp >> 32));
+                const uint4 pw = philox_ni(eng.seed, STREAM_PAD_ACTION, (uint32_t)e, (uint32_t)gp, (uint32_t)(gp >> 32));
                 a[k] = (int)u_below(pw.x, (uint32_t)A); rw[k] = 0.f; tm[k] = 1;
                 xv[k] = last_k == 0 ? xv[0] : xv[1];
               } else {
@@ -1180,7 +1210,7 @@ learner_fast_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_up
                 if (dn) ended = true;
               } else {
                 const uint64_t gp = g_item + (uint64_t)k;
-                const uint4 pw = philox(eng.seed, STREAM_PAD_ACTION, (uint32_t)e, (uint32_t)gp, (uint32_t)(gp >> 32));
+                const uint4 pw = philox_ni(eng.seed, STREAM_PAD_ACTION, (uint32_t)e, (uint32_t)gp, (uint32_t)(gp >> 32));
                 a = (int)u_below(pw.x, (uint32_t)A); rw = 0.f; tm = 1.f; xv = xlast;
               }
               if (v) {
@@ -1233,7 +1263,18 @@ learner_fast_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_up
           named_bar_sync(FBAR_MEM, FNM);
           SRLX_FSTAMP(mt == 0, 18);
           if (per) {
-            if (mw != 0) apply_update(ag + (size_t)parb * B * 8, upd + 2 == n_updates);
+            if (mw != 0) {
+              apply_update(ag + (size_t)parb * B * 8, upd + 2 == n_updates);
+            } else {
+              // max_priority (proportional_memory.py:176): the priority is monotone in |td|, so one evaluation at max |td|
+              const float* agb = ag + (size_t)parb * B * 8;
+              float m = lane < B ? fabsf(agb[lane * 8 + 4] - agb[lane * 8 + 5]) : 0.f;
+              for (int s = 16; s > 0; s >>= 1) m = fmaxf(m, __shfl_xor_sync(FULL, m, s));
+              if (lane == 0) {
+                const double pm = pow_chain(fabs((double)m) + eng.per_epsilon, eng.per_alpha);
+                if (pm > sc->max_priority) sc->max_priority = pm;
+              }
+            }
             named_bar_sync(FBAR_MEM, FNM);
           }
           SRLX_FSTAMP(mt == 0, 20);
@@ -1278,10 +1319,9 @@ learner_fast_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_up
 }
 
 // ---- host side ---------------------------------------------------------------------------------------------------
-static int learn_fast(const srlx_engine* eng, uint32_t n_updates, uintptr_t cuda_stream, int C, int max_smem) {
+static int learn_fast(const srlx_engine* eng, uint32_t n_updates, uintptr_t cuda_stream, int C, int cache_levels) {
   const long long n_nodes = 2ll * eng->ring_rows * eng->n_envs - 1;
-  const FPlan pl = make_fplan(*eng, C, n_nodes);
-  (void)max_smem;
+  const FPlan pl = make_fplan(*eng, C, n_nodes, cache_levels);
   // the reference's Rainbow default shape gets the instantiations with compile-time loop bounds
   const bool flag = eng->batch_size == 32 && eng->multisteps == 3 && eng->n_actions == 2 && eng->obs_dim == 4 &&
                     eng->net.out_dim[1] == 3 && eng->net.dueling == SRLX_DUEL_AVERAGE && eng->net.out_dim[0] == 1024;
@@ -1355,7 +1395,7 @@ static int learn_fast(const srlx_engine* eng, uint32_t n_updates, uintptr_t cuda
       attr[1].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
       cfg.numAttrs = 2;
     }
-    SRLX_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, *eng, n, (const float*)eng->noise_scratch));
+    SRLX_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, *eng, n, (const float*)eng->noise_scratch, cache_levels));
     count_launch();
     SRLX_CHECK_CUDA(cudaGetLastError());
     done += n;
@@ -1365,29 +1405,50 @@ static int learn_fast(const srlx_engine* eng, uint32_t n_updates, uintptr_t cuda
 
 }  // namespace srlx
 
+// Pick the cluster size and the number of SumTree levels cached in shared memory: the widest cluster (16, then 8, ...)
+// whose plan fits the per-CTA shared memory with at least 8 cached levels.  Returns 1 if the fast kernel applies.
+static int fast_choose(const srlx_engine* eng, int* C_out, int* lev_out, size_t* smem_out) {
+  using namespace srlx;
+  const char* force = getenv("SRLX_LEARNER");
+  if ((force && force[0] == 'g') || !fast_shape_ok(*eng)) return 0;
+  int want = 0;
+  if (const char* e = getenv("SRLX_CLUSTER")) want = atoi(e);
+  int dev = 0, max_smem = 0;
+  SRLX_CHECK_CUDA(cudaGetDevice(&dev));
+  SRLX_CHECK_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+  const long long n_nodes = 2ll * eng->ring_rows * eng->n_envs - 1;
+  for (int c0 = want > 0 ? want : kFMaxC; c0 >= 1; c0 >>= 1) {
+    const int C = fast_pick_cluster(eng->net, c0);
+    if (C < 1) return 0;
+    for (int lev = kFCacheLevels; lev >= 8; --lev) {
+      const FPlan pl = make_fplan(*eng, C, n_nodes, lev);
+      const bool noise_ok = !eng->net.noisy || (eng->noise_scratch && eng->noise_scratch_bytes >= (uint64_t)C * 3 * pl.Pl * 4);
+      if (!noise_ok) return 0;
+      if ((long long)pl.total + 1024 <= max_smem) {
+        *C_out = C;
+        *lev_out = lev;
+        *smem_out = pl.total;
+        return 1;
+      }
+      if (eng->mem_kind != SRLX_MEM_PROPORTIONAL) break;  // no cache to shrink
+    }
+    if (C == 1) break;
+    c0 = C;  // next: half of the cluster just tried
+  }
+  return 0;
+}
+
 // Which kernel srlx_learn will run for this engine: 1 = learner_fast_kernel (single hidden layer, <= 4 observation floats,
 // <= 4 outputs, batch <= 32), 0 = the generic learner_kernel; negative = error.
 extern "C" int srlx_learner_info(const srlx_engine* eng, int* cluster_size, size_t* smem_bytes) {
   using namespace srlx;
   SRLX_REQUIRE(eng != nullptr, "srlx_learner_info: eng is NULL");
-  if (cluster_size) *cluster_size = 0;
-  if (smem_bytes) *smem_bytes = 0;
-  const char* force = getenv("SRLX_LEARNER");
-  const bool want_generic = force && force[0] == 'g';
-  if (want_generic || !fast_shape_ok(*eng)) return 0;
-  int want = 0;
-  if (const char* e = getenv("SRLX_CLUSTER")) want = atoi(e);
-  const int C = fast_pick_cluster(eng->net, want);
-  if (C < 1) return 0;
-  int dev = 0, max_smem = 0;
-  SRLX_CHECK_CUDA(cudaGetDevice(&dev));
-  SRLX_CHECK_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-  const FPlan pl = make_fplan(*eng, C, 2ll * eng->ring_rows * eng->n_envs - 1);
-  const bool noise_ok = !eng->net.noisy || (eng->noise_scratch && eng->noise_scratch_bytes >= (uint64_t)C * 3 * pl.Pl * 4);
-  if ((long long)pl.total + 1024 > max_smem || !noise_ok) return 0;
-  if (cluster_size) *cluster_size = C;
-  if (smem_bytes) *smem_bytes = pl.total;
-  return 1;
+  int C = 0, lev = 0;
+  size_t sm = 0;
+  const int rc = fast_choose(eng, &C, &lev, &sm);
+  if (cluster_size) *cluster_size = rc == 1 ? C : 0;
+  if (smem_bytes) *smem_bytes = rc == 1 ? sm : 0;
+  return rc;
 }
 
 extern "C" int srlx_learn(const srlx_engine* eng, uint32_t n_updates, uintptr_t cuda_stream) {
@@ -1404,8 +1465,10 @@ extern "C" int srlx_learn(const srlx_engine* eng, uint32_t n_updates, uintptr_t 
   SRLX_REQUIRE(eng->ring_obs && eng->ring_next_obs && eng->ring_action && eng->ring_reward && eng->ring_term && eng->ring_done,
                "srlx_learn: ring buffer pointer is NULL");
   if (n_updates == 0) return 0;
-  int C = 0;
+  int C = 0, lev = 0;
   size_t smem_bytes = 0;
-  if (srlx_learner_info(eng, &C, &smem_bytes) == 1) return learn_fast(eng, n_updates, cuda_stream, C, 0);
+  const int rc = fast_choose(eng, &C, &lev, &smem_bytes);
+  if (rc < 0) return rc;
+  if (rc == 1) return learn_fast(eng, n_updates, cuda_stream, C, lev);
   return learn_generic(eng, n_updates, cuda_stream);
 }

@@ -17,6 +17,8 @@ def main():
     kw = dict(env="CartPole-v1", algo="rainbow", hidden=(512,), dueling="average", noisy=True, mem_kind=1, multisteps=3,
               n_envs=E, ring_rows=R, batch_size=32, warmup_size=1000, seed=1)
     d = DeviceEngine(EngineConfig(**kw), debug=True)
+    for f in ("dbg_q", "dbg_action", "dbg_sample_idx", "dbg_weights", "dbg_target_q", "dbg_q_sa", "dbg_grads", "dbg_windows"):
+        setattr(d.c, f, None)  # only the clock tap stays on: the other taps cost time inside the learner
     d.run(R, 0)
     d.learn(64)
     torch.cuda.synchronize()
@@ -27,7 +29,8 @@ def main():
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
     c = d.t["dbg_clock"].cpu().numpy().astype("int64")
-    base = min(int(x) for x in c if x > 0)
+    nz = [int(x) for x in c if x > 0]
+    base = min(nz) if nz else 0  # no stamps: not the -DSRLX_STAMPS build (SRLX_LIB=.../libsrlx_stamps.so)
     rel = {i: int(c[i] - base) for i in range(64) if c[i] > 0}
     out = {"us_per_update": 1e3 * ms / 1024, "learner": d.learner_info(), "stamps_cycles_rel": rel}
     print(json.dumps(out))
