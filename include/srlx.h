@@ -186,6 +186,9 @@ uint64_t srlx_launch_count(void);
 /* out[i*4..i*4+3] = philox4x32-10(ctr = (a0+i, b, c, stream), key = seed) for i < n. */
 int srlx_philox_words(uint64_t seed, uint32_t stream, uint32_t a0, uint32_t b, uint32_t c, uint32_t* out_dev,
                       size_t n, uintptr_t cuda_stream);
+/* out[i] = x[i]^a as the fused learner evaluates the priority (|td| + eps)^alpha and the IS weights (a short fp64
+ * log/exp, csrc/learner_fast.cu::pow_chain): test tap for its parity with libm pow (max rel. difference 4e-15). */
+int srlx_dbg_pow(const double* x_dev, double a, double* out_dev, size_t n, uintptr_t cuda_stream);
 /* The N(0,1) noise tensor a NoisyLinear forward call `call_id` of kind `kind` uses (flat param layout). */
 int srlx_noise_fill(uint64_t seed, uint32_t kind, uint64_t call_id, float* out_dev, size_t n_params,
                     uintptr_t cuda_stream);

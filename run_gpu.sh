@@ -1,6 +1,5 @@
 set -x
 mkdir -p gpurun_out
 timeout 600 python -m pytest tests -m gpu -x -q --timeout 60 2>&1 | tail -6
-SRLX_LIB=$PWD/simple_distributed_rl_b200/libsrlx_stamps.so SRLX_CLUSTER=8 timeout 300 python tools/phase_clocks.py 2>&1 | tail -1
+SRLX_LIB=$PWD/simple_distributed_rl_b200/libsrlx_stamps.so timeout 300 python tools/phase_clocks.py 2>&1 | tail -1
 timeout 300 python tools/phase_clocks.py 2>&1 | tail -1
-timeout 600 python bench.py --steps 10 --warmup 3 2>&1 | tail -1 | tee gpurun_out/bench_r1_c.json

@@ -99,6 +99,7 @@ SYMBOLS = [
     ("srlx_launch_count", _u64, []),
     ("srlx_philox_words", C.c_int, [_u64, _u32, _u32, _u32, _u32, _P, _sz, _uptr]),
     ("srlx_noise_fill", C.c_int, [_u64, _u32, _u64, _P, _sz, _uptr]),
+    ("srlx_dbg_pow", C.c_int, [_P, _dbl, _P, _sz, _uptr]),
     ("srlx_tree_clear", C.c_int, [_P, _u64, _P, _uptr]),
     ("srlx_tree_add", C.c_int, [_P, _u64, _P, _P, _u64, _dbl, _dbl, _i32, _uptr]),
     ("srlx_tree_sample", C.c_int, [_P, _u64, _P, _u32, _u64, _dbl, _dbl, _i32, _u64, _P, _u32, _P, _P, _P, _uptr]),

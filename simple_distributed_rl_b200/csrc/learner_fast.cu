@@ -33,7 +33,7 @@ int learn_generic(const srlx_engine* eng, uint32_t n_updates, uintptr_t cuda_str
 constexpr int kFCmpWarps = 16, kFMemWarps = 4;
 constexpr int FNC = kFCmpWarps * 32, FNM = kFMemWarps * 32, FNT = FNC + FNM;
 constexpr int kFMaxC = 16, kFMaxSeg = 8, kFCacheLevels = 12, kFMaxChunk = 256, kFSubLd = 66;
-enum { FBAR_CMP = 1, FBAR_MEM = 2 };
+enum { FBAR_CMP = 1, FBAR_MEM = 2, FBAR_MA = 3, FBAR_MB = 4, FBAR_FW = 5, FBAR_UP = 6 };
 enum { FSEG_W = 0, FSEG_B = 1, FSEG_O = 2, FSEG_OB = 3 };
 enum { MB_RS = 0, MB_AG, MB_S, MB_WT, MB_XR, MB_NZ0, MB_NZ1, MB_NZ2, MB_COUNT };
 
@@ -185,12 +185,45 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
 __device__ __forceinline__ float2 f2(float a, float b) { return make_float2(a, b); }
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 
-// x^a for the priority (|td| + eps)^alpha: exp(a log x) is ~2x shorter than pow() on the dependent chain td -> SumTree
-// update -> next sample (456 vs 821 cycles, tools/ubench) and differs from it by a few ulp of fp64
-// Out of line on purpose: the per-update code of a CTA has to fit the SM's instruction cache (every first-touched
-// 128-byte line of straight-line code costs a fetch from L2 on the serial chain), so the big scalar
-// routines exist once per kernel.
-__device__ __noinline__ double pow_chain(double x, double a) { return x > 0.0 ? exp(a * log(x)) : pow(x, a); }
+// x^a on the dependent chain td -> priority -> SumTree update -> next sample, in ~70 fp64 instructions instead of the
+// ~300 of exp(a*log(x)) / pow(): what the chain pays for is instruction count (tools/ubench: a cold instruction stream
+// runs at ~7 cycles/instruction), not flops.  ln x = e ln2 + 2 atanh((m-1)/(m+1)) with m in [sqrt(1/2), sqrt(2))
+// (odd series to s^23), a*ln x carried as hi + lo, exp by Cody-Waite reduction + degree-13 Taylor.  Max relative
+// difference to libm pow over x in [1e-14, 1e5], a in [-1, 1]: 3.6e-15 (tests/test_oracle_golden.py restates the check).
+// Out of line on purpose: the per-update code of a CTA should stay inside the SM's instruction cache.
+__constant__ double kPowAtanh[11] = {1.0 / 23.0, 1.0 / 21.0, 1.0 / 19.0, 1.0 / 17.0, 1.0 / 15.0, 1.0 / 13.0,
+                                     1.0 / 11.0, 1.0 / 9.0,  1.0 / 7.0,  1.0 / 5.0,  1.0 / 3.0};
+__constant__ double kPowExp[14] = {1.0 / 6227020800.0, 1.0 / 479001600.0, 1.0 / 39916800.0, 1.0 / 3628800.0, 1.0 / 362880.0,
+                                   1.0 / 40320.0,      1.0 / 5040.0,      1.0 / 720.0,      1.0 / 120.0,     1.0 / 24.0,
+                                   1.0 / 6.0,          0.5,               1.0,              1.0};
+__device__ __noinline__ double pow_chain(double x, double a) {
+  bool ok = (x >= 1e-290 && x <= 1e290) && (fabs(a) <= 8.0);
+  double res = 0.0;
+  if (ok) {
+    const long long bits = __double_as_longlong(x);
+    int e = (int)((bits >> 52) & 0x7ff) - 1023;
+    double m = __longlong_as_double((bits & 0x000fffffffffffffll) | 0x3ff0000000000000ll);
+    if (m > 1.4142135623730951) { m *= 0.5; e += 1; }
+    const double s = (m - 1.0) / (m + 1.0), s2 = s * s;
+    double p = kPowAtanh[0];
+#pragma unroll
+    for (int i = 1; i < 11; ++i) p = fma(p, s2, kPowAtanh[i]);
+    const double lnm = 2.0 * fma(p * s2, s, s);
+    const double LN2_HI = 6.93147180369123816490e-01, LN2_LO = 1.90821492927058770002e-10;
+    const double lx_hi = fma((double)e, LN2_HI, lnm), lx_lo = (double)e * LN2_LO;
+    const double y = a * lx_hi, y_lo = fma(a, lx_hi, -y) + a * lx_lo;
+    ok = fabs(y) <= 690.0;
+    const double k = rint(y * 1.44269504088896338700e+00);
+    double r = fma(-k, LN2_HI, y);
+    r = fma(-k, LN2_LO, r) + y_lo;
+    double q = kPowExp[0];
+#pragma unroll
+    for (int i = 1; i < 14; ++i) q = fma(q, r, kPowExp[i]);
+    res = __longlong_as_double(__double_as_longlong(q) + ((long long)k << 52));
+  }
+  if (!ok) res = pow(x, a);  // zeros, denormals, huge exponents: the library routine
+  return res;
+}
 __device__ __noinline__ uint4 philox_ni(uint64_t seed, uint32_t stream, uint32_t a, uint32_t b, uint32_t c) {
   return philox(seed, stream, a, b, c);
 }
@@ -254,7 +287,7 @@ __global__ void __launch_bounds__(128) noise_precompute_kernel(const __grid_cons
 template <int TC>
 __global__ void __launch_bounds__(FNT, 1)
 learner_fast_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_updates, const float* __restrict__ noise,
-                    const int max_cache_levels) {
+                    const int max_cache_levels, const int sched) {
   extern __shared__ __align__(16) unsigned char smem[];
   cg::cluster_group cluster = cg::this_cluster();
   constexpr bool FLAG = TC > 0;
@@ -294,6 +327,8 @@ learner_fast_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_up
   int* sperm = s_idx + 64;                                  // [4 warps][32]
   double* s_pri = reinterpret_cast<double*>(smem + pl.off_sdbl + 1024);
   double* s_tmp = s_pri + 32;
+  double* s_wval = s_tmp + 32;                              // hand-over of the top-level walk: remaining value,
+  int* s_widx = reinterpret_cast<int*>(s_wval + 32);        // node reached
   double* sub = reinterpret_cast<double*>(smem + pl.off_sub);
   double* plan_old = reinterpret_cast<double*>(smem + pl.off_plan);
   int* plan_node = reinterpret_cast<int*>(smem + pl.off_plan + (size_t)FNM * 5 * 8);
@@ -569,6 +604,9 @@ learner_fast_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_up
           }
         }
       }
+      // CTA 0 time-slices its SM: the replay warps' bookkeeping (update plan, IS weights) runs in the window where the
+      // compute warps idle (reduce-scatter / targets / all-gather), not against the forward pass
+      if (rank == 0 && (sched & 1)) named_bar_arrive(FBAR_FW, FNT);
       named_bar_sync(FBAR_CMP, FNC);
       SRLX_FSTAMP(ct == 0, 1);
       // ---------------------------------------------------------------- reduce over warps, scatter to the owning CTA
@@ -729,6 +767,9 @@ learner_fast_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_up
         mbar_wait_sleep(&mbar[MB_AG], parb);
       }
       named_bar_sync(FBAR_CMP, FNC);
+      // ... and backward + Adam of CTA 0 wait for the SumTree update (the head of the chain to the next sample); they then
+      // overlap the sampler's memory round trips.  The other CTAs start backward at once.
+      if (rank == 0 && per && (sched & 2)) named_bar_sync(FBAR_UP, FNC + 96);
       SRLX_FSTAMP(ct == 0, 3);
       // ---------------------------------------------------------------- backward of this CTA's slice: thread = (unit, row group)
       {
@@ -800,7 +841,7 @@ learner_fast_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_up
       // ---- sampler state (CTA 0): lane g < 8 of warp mw owns sample mw*8+g ------------------------------------------
       const int own_i = mw * 8 + lane;
       const bool own = lane < 8 && own_i < B;
-      double u_next = 0.0;  // pre-drawn uniform of the owner's next sample
+      double u_next = 0.0;  // warp 0, lane = sample: pre-drawn uniform of the next batch
       auto draw = [&](uint64_t tc, int i, int k) -> double {
         const uint4 w = philox_ni(eng.seed, STREAM_SAMPLE, (uint32_t)i | ((uint32_t)k << 16), (uint32_t)tc, (uint32_t)(tc >> 32));
         return u01_f64(w.x, w.y);
@@ -828,27 +869,33 @@ learner_fast_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_up
 #else
 #define SRLX_SSTAMP(slot) do { (void)stamp; } while (0)
 #endif
+      // Walk of the shared-memory-cached top levels for ALL samples of update `tc` (warp 0, lane = sample; branch-free,
+      // the cached top is a complete binary tree): leaves (node, remaining value) in s_widx / s_wval.
+      auto walk_top = [&](double u) {
+        const double total = cache[0];
+        int idx = 0;
+        double val = u * total;
+#pragma unroll 1
+        for (int l = 1; l < clev; ++l) {
+          const double tl = cache[2 * idx + 1];
+          const bool right = !(val <= tl);
+          const double vr = val - tl;
+          val = right ? vr : val;
+          idx = 2 * idx + 1 + (right ? 1 : 0);
+        }
+        if (lane < B) { s_widx[lane] = idx; s_wval[lane] = val; }
+      };
       auto sample_slots = [&](uint64_t tc, int pb, bool stamp) {
         if (per) {
-          const double total = *reinterpret_cast<volatile double*>(cache);
-          SRLX_SSTAMP(28);
+          const double total = cache[0];
+          // (a) the cached top levels were walked by warp 0 for all B samples (walk_top) while warps 1..3 finished the
+          //     deep levels of the update; each owner lane picks its sample's state up from shared memory
           int idx = 0;
           double val = 0.0, pcur = 0.0;
-          if (own) {  // (a) the cached top levels, out of shared memory
-            val = u_next * total;
-            // branch-free: the cached top is a complete binary tree, every lane walks clev - 1 levels
-#pragma unroll 1
-            for (int l = 1; l < clev; ++l) {
-              const double tl = cache[2 * idx + 1];
-              const bool right = !(val <= tl);
-              const double vr = val - tl;
-              val = right ? vr : val;
-              idx = 2 * idx + 1 + (right ? 1 : 0);
-            }
-            pcur = cache[idx];
-          }
+          if (own) { idx = s_widx[own_i]; val = s_wval[own_i]; pcur = cache[idx]; }
           SRLX_SSTAMP(22);
           bool done = !own || (2 * idx + 1 >= n_nodes);
+          bool pc_ok = true;
           // (b) the remaining levels, five per L2 round trip: 31 lanes fetch both children of every node of the 5-level
           //     subtree below each of the warp's 8 samples, the owner lanes replay the "val <= tree[left]" walk out of smem
           double* wsub = sub + (size_t)mw * 8 * kFSubLd;
@@ -861,15 +908,21 @@ learner_fast_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_up
           while (__any_sync(FULL, !done)) {
             double v0[8], v1[8];
             // unconditional loads from clamped addresses (a predicated load + select makes ptxas wait for every load in
-            // turn): nodes past the end of the tree or below finished samples are fetched but never looked at
+            // turn): nodes past the end of the tree or below finished samples are fetched but never looked at.  Left
+            // children drive the walk; a right child's value is only ever needed as the priority of the leaf the walk
+            // ends on, so only the lanes of the deepest fetched level load it (fewer L1 wavefronts on the critical chain).
+            unsigned nodes[8];
 #pragma unroll
             for (int g = 0; g < 8; ++g) {
               const unsigned ig = (unsigned)__shfl_sync(FULL, idx, g);
               unsigned node = (ig << k_l) + c_l;  // < 2^32: fast_shape_ok bounds the tree at 2^27 nodes
-              node = node < last_pair ? node : last_pair;
-              const double* src = eng.tree + node;
-              v0[g] = __ldcg(src);
-              v1[g] = __ldcg(src + (n_nodes > 1 ? 1 : 0));
+              nodes[g] = node < last_pair ? node : last_pair;
+              v0[g] = __ldcg(eng.tree + nodes[g]);
+              v1[g] = 0.0;
+            }
+            if (k_l == 5) {
+#pragma unroll
+              for (int g = 0; g < 8; ++g) v1[g] = __ldcg(eng.tree + nodes[g] + (n_nodes > 1 ? 1 : 0));
             }
             SRLX_SSTAMP(32 + rnd * 3);
             if (lane < 31) {
@@ -891,6 +944,7 @@ learner_fast_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_up
                 const double vr = val - ch.x;
                 val = (act && right) ? vr : val;
                 pcur = act ? (right ? ch.y : ch.x) : pcur;
+                pc_ok = act ? (!right || k == 5) : pc_ok;
                 idx = act ? left + (right ? 1 : 0) : idx;
                 rel = act ? 2 * rel + (right ? 1 : 0) : 0;
               }
@@ -901,8 +955,10 @@ learner_fast_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_up
             ++rnd;
           }
           SRLX_SSTAMP(23);
+          int s_li_final = cap1;
           if (own) {  // a zero-priority leaf is re-drawn (proportional_memory.py:150-152), sequentially
             int li = idx;
+            if (!pc_ok) pcur = __ldcg(eng.tree + idx);  // ragged tree: the walk ended on a right child above the fetched bottom
             double p = pcur;
             int k = 0;
             while (p == 0.0 && k + 1 < 9999) {
@@ -913,7 +969,28 @@ learner_fast_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_up
             s_idx[own_i] = li;
             s_pri[own_i] = p;
             s_att[own_i] = k;
+            s_li_final = li;
             if (k) atomicAdd(&sc->retries, (unsigned long long)k);
+          }
+          {
+            // The ring rows of the sampled windows are read by every CTA ~1000 cycles from now: start their DRAM fetch
+            // (L2 prefetch).  Lane = (sample lane & 7, part lane >> 3): part 0 the observation, parts 1.. one window step
+            // each (next observation, action, reward, flags) -- the idle lanes share the address arithmetic.
+            const int g = lane & 7, part_j = lane >> 3;
+            const int lg = __shfl_sync(FULL, s_li_final, g);
+            if (mw * 8 + g < B && part_j <= M) {
+              const int s0 = lg - cap1, rho = s0 / E, e = s0 - rho * E;
+              if (part_j == 0) {
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(eng.ring_obs + (size_t)s0 * D));
+              } else {
+                const int sk = ((rho + part_j - 1) % R) * E + e;
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(eng.ring_next_obs + (size_t)sk * D));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(eng.ring_action + sk));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(eng.ring_reward + sk));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(eng.ring_term + sk));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(eng.ring_done + sk));
+              }
+            }
           }
           named_bar_sync(FBAR_MEM, FNM);
           if (!eng.has_duplicate) {
@@ -1015,7 +1092,8 @@ learner_fast_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_up
       // Plan of the SumTree update of the current batch (every warp for its own levels): items sorted by root-to-leaf
       // path, so the items below any node are consecutive lanes; per level the first lane of a run ("leader") knows the
       // node, the last lane of its run, and has the node's old value in a register before the new priorities exist.
-      auto plan_update = [&]() {
+      auto plan_update = [&](bool stamp) {
+        SRLX_SSTAMP(46);
         const bool v = lane < B;
         const int li = v ? s_idx[lane] : 0x7ffffffe;
         const unsigned ip1 = (unsigned)li + 1u;
@@ -1025,8 +1103,9 @@ learner_fast_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_up
 #pragma unroll 4
         for (int j = 0; j < 32; ++j) {
           const unsigned kj = __shfl_sync(FULL, key, j);
-          rank_l += (kj < key || (kj == key && j < lane)) ? 1 : 0;
+          rank_l += (int)(kj < key) + ((int)(kj == key) & (int)(j < lane));  // bitwise: no divergent short-circuit branches
         }
+        SRLX_SSTAMP(47);
         int* pw = sperm + mw * 32;
         pw[rank_l] = lane;
         __syncwarp();
@@ -1041,11 +1120,11 @@ learner_fast_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_up
           const int a = level_of(q);
           int pn = -1, pe = lane;
           if (level_ok(q, a)) {
-            const bool has = s_valid && sd > a;
+            const bool has = (int)s_valid & (int)(sd > a);
             const int node = has ? (int)(sip1 >> (sd - a)) - 1 : -1;
             const int prevn = __shfl_up_sync(FULL, node, 1), nextn = __shfl_down_sync(FULL, node, 1);
-            const bool lead = has && (lane == 0 || prevn != node);
-            const bool last = has && (lane == 31 || nextn != node);
+            const bool lead = (int)has & ((int)(lane == 0) | (int)(prevn != node));
+            const bool last = (int)has & ((int)(lane == 31) | (int)(nextn != node));
             const unsigned bl = __ballot_sync(FULL, last);
             pe = (lane + __ffs(bl >> lane) - 1) & 31;  // first "last" flag at or after this lane (leaders find one)
             pn = lead ? node : -1;
@@ -1053,6 +1132,7 @@ learner_fast_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_up
           p_node[q * FNM] = pn;
           p_end[q * FNM] = pe;
         }
+        SRLX_SSTAMP(48);
         // uncached levels: unconditional loads (node 0 for non-leaders), all in flight at once, then parked in shared memory
         double ov[kLu];
 #pragma unroll
@@ -1062,6 +1142,7 @@ learner_fast_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_up
         }
 #pragma unroll
         for (int q = 0; q < kLu; ++q) p_old[q * FNM] = ov[q];
+        SRLX_SSTAMP(49);
       };
 
       // ProportionalMemory.update of the current batch (proportional_memory.py:171-177).  The new priorities, their
@@ -1093,8 +1174,8 @@ learner_fast_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_up
         double Pex = __shfl_up_sync(FULL, P, 1);
         if (lane == 0) Pex = 0.0;
         SRLX_SSTAMP(42);
-#pragma unroll 3
-        for (int q = 0; q < kLv; ++q) {
+        // cached levels first: the sampler's top-level walk (warp 0) needs only these
+        auto level_slot = [&](int q) {
           const int pn = p_node[q * FNM], e = p_end[q * FNM];
           const double Pe = __shfl_sync(FULL, P, e);
           if (pn >= 0) {
@@ -1104,7 +1185,12 @@ learner_fast_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_up
             __stcg(eng.tree + pn, nv);
             if (q < kLc) cache[pn] = nv;
           }
-        }
+        };
+#pragma unroll 2
+        for (int q = 0; q < kLc; ++q) level_slot(q);
+        named_bar_arrive(FBAR_MB, FNM);  // the cached top is final: warp 0 starts the next batch's top-level walk
+#pragma unroll 1
+        for (int q = kLc; q < kLv; ++q) level_slot(q);
         SRLX_SSTAMP(43);
       };
 
@@ -1126,7 +1212,10 @@ learner_fast_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_up
       };
 
       if (rank == 0) {
-        if (own && per) u_next = draw(tc0, own_i, 0);
+        if (per) {
+          if (mw == 0) walk_top(lane < B ? draw(tc0, lane, 0) : 0.0);
+          named_bar_sync(FBAR_MEM, FNM);
+        }
         sample_slots(tc0, 0, false);
       }
 
@@ -1240,19 +1329,21 @@ learner_fast_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_up
           }
         }
         if (rank == 0) {
-          // ---- off the critical path, while the compute warps run forward(t) -------------------------------------------
+          // ---- off the critical path: after the compute warps have issued forward(t), while they wait for the targets --
+          if (sched & 1) named_bar_sync(FBAR_FW, FNT);
           if (mw == 0) {
             send_weights(tc, parb);
             if (upd > 0) bookkeeping(upd - 1);
           } else if (per) {
-            plan_update();
+            plan_update(upd + 2 == n_updates);
           }
-          if (per && own && upd + 1 < n_updates) u_next = draw(tc + 1, own_i, 0);
+          if (per && mw == 0 && lane < B && upd + 1 < n_updates) u_next = draw(tc + 1, lane, 0);
           SRLX_FSTAMP(mt == 0, 26);
           SRLX_FSTAMP(mt == 32, 27);
         }
         if (mw == 0) {
           mbar_wait_sleep(&mbar[MB_AG], parb);  // update t's targets are known everywhere: forward(t) is over in every CTA
+          if (rank == 0 && per) named_bar_arrive(FBAR_MA, FNM);  // release the update warps first
           if (lane == 0 && noisy && upd + 2 < n_updates) {  // ring slot (t+2)%3 was last read by Adam(t-1)
             uint64_t* nb = &mbar[MB_NZ0 + (upd + 2) % 3];
             mbar_expect_tx(nb, (uint32_t)nz_bytes);
@@ -1260,11 +1351,12 @@ learner_fast_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_up
           }
         }
         if (rank == 0) {
-          named_bar_sync(FBAR_MEM, FNM);
           SRLX_FSTAMP(mt == 0, 18);
           if (per) {
             if (mw != 0) {
+              named_bar_sync(FBAR_MA, FNM);  // targets of update t have arrived (warp 0 saw the AG barrier complete)
               apply_update(ag + (size_t)parb * B * 8, upd + 2 == n_updates);
+              if (sched & 2) named_bar_arrive(FBAR_UP, FNC + 96);  // CTA 0's compute warps may start backward
             } else {
               // max_priority (proportional_memory.py:176): the priority is monotone in |td|, so one evaluation at max |td|
               const float* agb = ag + (size_t)parb * B * 8;
@@ -1274,7 +1366,12 @@ learner_fast_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_up
                 const double pm = pow_chain(fabs((double)m) + eng.per_epsilon, eng.per_alpha);
                 if (pm > sc->max_priority) sc->max_priority = pm;
               }
+              named_bar_sync(FBAR_MB, FNM);  // cached levels of the tree are updated
+              SRLX_FSTAMP(mt == 0, 28);
+              if (upd + 1 < n_updates) walk_top(u_next);
             }
+            named_bar_sync(FBAR_MEM, FNM);  // deep levels written + top-level walk handed over
+          } else {
             named_bar_sync(FBAR_MEM, FNM);
           }
           SRLX_FSTAMP(mt == 0, 20);
@@ -1338,6 +1435,8 @@ static int learn_fast(const srlx_engine* eng, uint32_t n_updates, uintptr_t cuda
     const int v = atoi(e);
     if (v >= 1 && (uint32_t)v < chunk) chunk = (uint32_t)v;
   }
+  int sched = 0;  // (experiment knobs, default off) bit 0: CTA 0's replay bookkeeping waits for the forward pass; bit 1: its backward waits for the tree update
+  if (const char* e = getenv("SRLX_SCHED")) sched = atoi(e);
   cudaStream_t stream = (cudaStream_t)cuda_stream;
   // L2 set-aside for the tree (device-wide limit, set once per device; SRLX_L2_PERSIST=0 disables)
   size_t l2_window_bytes = 0;
@@ -1395,7 +1494,7 @@ static int learn_fast(const srlx_engine* eng, uint32_t n_updates, uintptr_t cuda
       attr[1].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
       cfg.numAttrs = 2;
     }
-    SRLX_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, *eng, n, (const float*)eng->noise_scratch, cache_levels));
+    SRLX_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, *eng, n, (const float*)eng->noise_scratch, cache_levels, sched));
     count_launch();
     SRLX_CHECK_CUDA(cudaGetLastError());
     done += n;
@@ -1403,7 +1502,23 @@ static int learn_fast(const srlx_engine* eng, uint32_t n_updates, uintptr_t cuda
   return 0;
 }
 
+__global__ void pow_chain_kernel(const double* __restrict__ x, double a, double* __restrict__ out, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = pow_chain(x[i], a);
+}
+
 }  // namespace srlx
+
+// out[i] = the learner's priority power x[i]^a (test tap: parity of pow_chain with libm pow)
+extern "C" int srlx_dbg_pow(const double* x_dev, double a, double* out_dev, size_t n, uintptr_t cuda_stream) {
+  using namespace srlx;
+  SRLX_REQUIRE(x_dev && out_dev, "srlx_dbg_pow: NULL buffer");
+  if (n == 0) return 0;
+  pow_chain_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)cuda_stream>>>(x_dev, a, out_dev, n);
+  count_launch();
+  SRLX_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
 
 // Pick the cluster size and the number of SumTree levels cached in shared memory: the widest cluster (16, then 8, ...)
 // whose plan fits the per-CTA shared memory with at least 8 cached levels.  Returns 1 if the fast kernel applies.

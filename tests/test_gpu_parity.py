@@ -64,6 +64,21 @@ def test_noise_matches_box_muller_and_is_normal(lib):
 
 
 # ------------------------------------------------------------------------------------------------------------------
+def test_priority_pow_matches_libm(lib):
+    """pow_chain (the short fp64 x^a on the learner's td -> priority -> SumTree chain) vs numpy's pow."""
+    rng = np.random.default_rng(0)
+    x = np.concatenate([10.0 ** rng.uniform(-14, 5, size=200_000), rng.uniform(1e-4, 3.0, size=200_000).astype(np.float32).astype(np.float64),
+                        np.array([1e-4, 1.0, 0.0, 1e-310, 1e300, 2.0 ** -1022])])
+    xd = torch.as_tensor(x, device=_dev())
+    out = torch.empty_like(xd)
+    for a in (0.6, 0.0, 1.0, -0.4, -1.0, 0.37):
+        assert lib.srlx_dbg_pow(xd.data_ptr(), a, out.data_ptr(), x.size, _stream()) == 0
+        torch.cuda.synchronize()
+        with np.errstate(divide="ignore"):
+            want = np.power(x, a)
+        np.testing.assert_allclose(out.cpu().numpy(), want, rtol=1e-14)
+
+
 def _upload_tree(arr):
     return torch.as_tensor(np.asarray(arr, dtype=np.float64)).to(_dev())
 
