@@ -293,15 +293,28 @@ def own_arm(args):
         pass
     peak_gbs, peak_src = (float(peaks["hbm_gbs"]), "measured") if "hbm_gbs" in peaks else (6650.0, "fallback")
     bytes_per_update = algorithmic_bytes_per_update(P_total)
-    learn_ms_per_launch = t_learn / K
-    achieved = bytes_per_update * U / (learn_ms_per_launch * 1e-3) / 1e9
-    roofline = {"kernel": "learner_kernel", "bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
-                "frac": achieved / peak_gbs, "traffic": None, "peak_source": peak_src,
-                "algorithmic_bytes_per_update": bytes_per_update, "updates_per_launch": U,
-                "launch_ms": learn_ms_per_launch, "share_of_step": t_learn / t_dev,
-                "us_per_update": 1e3 * learn_ms_per_launch / U,
-                "note": "consecutive updates are data-dependent (weights_t -> weights_t+1): the limiter is dependent-step "
-                        "latency, not HBM; see DESIGN.md"}
+    kname, cluster, smem = eng.learner_info()
+    chunk = 256 if kname == "learner_fast_kernel" else U  # srlx_learn issues the fast kernel in launches of <= 256 updates
+    n_launch = (U + chunk - 1) // chunk
+    learn_ms_per_launch = t_learn / (K * n_launch)
+    achieved = bytes_per_update * min(U, chunk) / (learn_ms_per_launch * 1e-3) / 1e9
+    traffic, traffic_src = None, None
+    try:  # dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the committed ncu --set full capture
+        for k in json.load(open(os.path.join(ROOT, "profiles", "r1_d_learner_ncu_summary.json"))):
+            if kname in k["kernel"] and int(k.get("cluster", 0)) == cluster:
+                traffic, traffic_src = k["dram_bytes"], "profiles/r1_d_learner_ncu_summary.json (256 updates per launch)"
+    except Exception:
+        pass
+    roofline = {"kernel": kname, "cluster_ctas": cluster, "smem_bytes_per_cta": smem, "bound": "hbm", "achieved": achieved,
+                "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs, "traffic": traffic, "traffic_source": traffic_src,
+                "peak_source": peak_src, "algorithmic_bytes_per_update": bytes_per_update, "updates_per_launch": min(U, chunk),
+                "launches_per_step": n_launch, "launch_ms": learn_ms_per_launch, "share_of_step": t_learn / t_dev,
+                "us_per_update": 1e3 * t_learn / (K * U),
+                "note": "consecutive updates are data-dependent (weights_t -> weights_t+1, priorities_t -> sample_t+1): the "
+                        "limiter is the dependent-step latency of one 16-SM cluster, not HBM; the kernel keeps weights, Adam "
+                        "state and the top of the SumTree in shared memory, so its DRAM traffic is below the algorithmic "
+                        "figure (which counts 5 weight passes + Adam per update); launch_ms includes the ~1% noise_precompute "
+                        "launches; see DESIGN.md"}
     rollout_bytes = 76 * E
     roll_ms = t_roll / K
     roofline_rollout = {"kernel": "rollout_kernel+post_step_kernel", "bound": "hbm", "achieved": rollout_bytes / (roll_ms * 1e-3) / 1e9,

@@ -105,9 +105,9 @@ class DeviceEngine:
         if noisy:
             self.t["params_sigma"] = z(P, torch.float32)
             self.t["target_sigma"] = z(P, torch.float32)
-            # NoisyNet draws of a chunk of trainer updates (csrc/learner_fast.cu): 3 forward calls x P values per update,
-            # sized for 256 updates at a time (L2-resident at the default network)
-            self.t["noise_scratch"] = torch.empty(max(1 << 20, 256 * 3 * (P + 64 * 16)), dtype=torch.float32, device=dev)
+            # NoisyNet draws of a chunk of 256 trainer updates (csrc/learner_fast.cu): 3 forward calls x the parameters in
+            # CTA-local order (a few replicated / padding floats per CTA on top of P) per update; ~40 MB at the default net
+            self.t["noise_scratch"] = torch.empty(256 * 3 * (2 * P + 4096), dtype=torch.float32, device=dev)
         if debug:
             B, M, D, A = self.B, self.M, self.D, self.A
             self.t.update(
