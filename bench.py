@@ -6,8 +6,9 @@ Workload (configs[2], the configuration the metric is quoted on; fits one GPU):
   srl/algorithms/rainbow/rainbow.py:57-108) on CartPole-v1, 8192 vectorised envs per GPU, SumTree replay of 2M
   transitions per GPU (ring 256 rows x 8192 envs), batch 32, lr 1e-3, target sync every 1000 updates.
 One bench "step" = ONE vector step of all E envs (E env steps: policy forward, env.step, ring write, replay add)
-followed by E/train_interval trainer updates (RunContext.train_interval, srl/base/context.py:60; default here 8, i.e.
-one Trainer.train() per 8 env steps) -- all enqueued on one CUDA stream with no host round trip in between.
+followed by E/train_interval trainer updates (RunContext.train_interval, srl/base/context.py:60; default here 10, i.e.
+one Trainer.train() per 10 env steps -- the ratio the two north-star targets, >= 1M env-steps/s and >= 100k updates/s,
+imply; the reference's own default of 1 makes env-steps/s == updates/s) -- all enqueued on one CUDA stream with no host round trip in between.
 
   python bench.py [--gpus N] [--steps K] [--warmup W]            own arm (CUDA, libsrlx.so)
   python bench.py --impl reference [...]                          the CPU path (oracle port of the reference loop)
@@ -349,7 +350,9 @@ def main():
     ap.add_argument("--impl", default="own", choices=["own", "reference"])
     ap.add_argument("--envs", type=int, default=8192)
     ap.add_argument("--ring-rows", type=int, default=256)
-    ap.add_argument("--train-interval", type=int, default=8)
+    ap.add_argument("--train-interval", type=int, default=10,
+                    help="env steps per trainer update (RunContext.train_interval); 10 = the ratio of the two north-star targets "
+                         "(>= 1M env-steps/s with >= 100k updates/s)")
     ap.add_argument("--cpu-envs", type=int, default=64, help="env copies in the bounded CPU sample")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
