@@ -35,7 +35,7 @@ constexpr int FNC = kFCmpWarps * 32, FNM = kFMemWarps * 32, FNT = FNC + FNM;
 constexpr int kFMaxC = 16, kFMaxSeg = 8, kFCacheLevels = 12, kFMaxChunk = 256, kFSubLd = 66;
 enum { FBAR_CMP = 1, FBAR_MEM = 2, FBAR_MA = 3, FBAR_MB = 4, FBAR_FW = 5, FBAR_UP = 6 };
 enum { FSEG_W = 0, FSEG_B = 1, FSEG_O = 2, FSEG_OB = 3 };
-enum { MB_RS = 0, MB_AG, MB_S, MB_WT, MB_XR, MB_NZ0, MB_NZ1, MB_NZ2, MB_COUNT };
+enum { MB_RS = 0, MB_AG, MB_S, MB_WT, MB_XR, MB_NZ0, MB_NZ1, MB_NZ2, MB_TQ, MB_COUNT };
 
 // A contiguous run of the flat (global) parameter vector held by one CTA.
 struct FSeg {
@@ -48,7 +48,7 @@ struct FSeg {
 struct FPlan {
   int C, B, M, A, D, K, nout, Uh, Us, nCh, BM, NX, NRq, ipc, rpi, nOwn, Pl, WS, nRG, rpg, B4, n_cache;
   size_t off_mbar, off_seg, off_scal, off_adam, off_gpow, off_gidx, off_slot, off_par, off_nz, off_weff, off_xin, off_meta,
-      off_part, off_rs, off_ag, off_qown, off_rawown, off_samp_slot, off_samp_w, off_sdbl, off_plan, off_sub, off_cache, total;
+      off_part, off_rs, off_ag, off_tq, off_qown, off_rawown, off_samp_slot, off_samp_w, off_sdbl, off_plan, off_sub, off_cache, total;
 };
 
 __host__ __device__ inline int fast_pick_cluster(const srlx_net& net, int want) {
@@ -134,6 +134,7 @@ __host__ __device__ inline FPlan make_fplan(const srlx_engine& eng, int C, long 
   }
   p.off_rs = take((size_t)2 * C * p.nOwn * 16);
   p.off_ag = take((size_t)2 * p.B * 32);
+  p.off_tq = take((size_t)2 * p.B * 8);  // CTA 0: (target, q) of every item, sent ahead of the all-gather
   p.off_qown = take((size_t)p.nOwn * 16);
   p.off_rawown = take((size_t)p.ipc * 16);
   p.off_samp_slot = take((size_t)2 * p.B4 * 4);
@@ -163,6 +164,11 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t saddr, uint32_t rank) {
 __device__ __forceinline__ void st_async_f4(uint32_t raddr, float4 v, uint32_t rmbar) {
   asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.f32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(raddr),
                "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "r"(rmbar)
+               : "memory");
+}
+__device__ __forceinline__ void st_async_f2(uint32_t raddr, float a, float b, uint32_t rmbar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.f32 [%0], {%1, %2}, [%3];" ::"r"(raddr), "f"(a),
+               "f"(b), "r"(rmbar)
                : "memory");
 }
 __device__ __forceinline__ void st_async_i4(uint32_t raddr, int4 v, uint32_t rmbar) {
@@ -318,6 +324,7 @@ learner_fast_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_up
   float* part = reinterpret_cast<float*>(smem + pl.off_part);   // [16][NRq][4]  (forward)  /  [nRG][Pl] (backward)
   float* rs = reinterpret_cast<float*>(smem + pl.off_rs);       // [2][C][nOwn][4]
   float* ag = reinterpret_cast<float*>(smem + pl.off_ag);       // [2][B][8]: d(raw)[4], target, q, loss term, -
+  float* tqb = reinterpret_cast<float*>(smem + pl.off_tq);      // [2][B][2]
   float* qown = reinterpret_cast<float*>(smem + pl.off_qown);   // [nOwn][4]
   float* rawown = reinterpret_cast<float*>(smem + pl.off_rawown);
   int* samp_slot = reinterpret_cast<int*>(smem + pl.off_samp_slot);
@@ -368,9 +375,11 @@ learner_fast_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_up
     mbar_init(&mbar[MB_NZ0], 1);
     mbar_init(&mbar[MB_NZ1], 1);
     mbar_init(&mbar[MB_NZ2], 1);
+    mbar_init(&mbar[MB_TQ], 1);
     fence_mbar_init();
     mbar_expect_tx(&mbar[MB_S], (uint32_t)B4 * 4);
     mbar_expect_tx(&mbar[MB_WT], (uint32_t)B4 * 4);
+    if (rank == 0) mbar_expect_tx(&mbar[MB_TQ], (uint32_t)B * 8);
     if (noisy) {
       mbar_expect_tx(&mbar[MB_NZ0], (uint32_t)nz_bytes);
       bulk_g2s(nzr, nz_src(0), (uint32_t)nz_bytes, &mbar[MB_NZ0]);
@@ -677,10 +686,8 @@ learner_fast_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_up
         }
         __syncwarp();
         SRLX_FSTAMP(ct == 0, 6);
-        mbar_wait_sleep(&mbar[MB_WT], parb);  // IS weights of this batch
-        SRLX_FSTAMP(ct == 0, 7);
-        if (ct == 0 && upd + 1 < n_updates) mbar_expect_tx(&mbar[MB_WT], (uint32_t)B4 * 4);
         // -------------------------------------------------------------- owner: targets, Huber gradient (lane per item)
+        bool wt_seen = false;
         for (int ii0 = 0; ii0 < nIt; ii0 += 32) {
           const int ii = ii0 + lane;
           float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
@@ -712,6 +719,13 @@ learner_fast_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_up
             }
             const int a0 = w_act[i * M + 0];
             const float q = qs[a0];
+            // the SumTree chain (priority -> update -> next sample) needs only |target - q|: CTA 0 gets it ahead of the
+            // all-gather, before the Huber gradient is even computed
+            st_async_f2(mapa_u32(smem_u32(tqb + ((size_t)parb * B + i) * 2), 0u), target, q, mapa_u32(smem_u32(&mbar[MB_TQ]), 0u));
+            if (!wt_seen) {
+              mbar_wait_sleep(&mbar[MB_WT], parb);  // IS weights of this batch (sent after the slots)
+              wt_seen = true;
+            }
             const float w = samp_w[parb * B4 + i];
             const float d = q * w - target * w;
             const float ad = fabsf(d);
@@ -764,6 +778,8 @@ learner_fast_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_up
           }
         }
         SRLX_FSTAMP(ct == 0, 8);
+        mbar_wait_sleep(&mbar[MB_WT], parb);  // (a CTA without items still consumes the phase)
+        if (ct == 0 && upd + 1 < n_updates) mbar_expect_tx(&mbar[MB_WT], (uint32_t)B4 * 4);
         mbar_wait_sleep(&mbar[MB_AG], parb);
       }
       named_bar_sync(FBAR_CMP, FNC);
@@ -1150,9 +1166,9 @@ learner_fast_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_up
       // of its levels: new = old + (sum of the changes of the items below the node).  The reference adds the changes one
       // item at a time in batch order; here a node's changes are summed in path order as a difference of running sums
       // (exact for the common single-item run) -- a different association of the same fp64 terms, see DESIGN.md.
-      auto apply_update = [&](const float* agb, bool stamp) {
+      auto apply_update = [&](const float* tq, bool stamp) {
         double pnew = 0.0;
-        if (s_valid) pnew = pow_chain(fabs((double)fabsf(agb[s_item * 8 + 4] - agb[s_item * 8 + 5])) + eng.per_epsilon, eng.per_alpha);
+        if (s_valid) pnew = pow_chain(fabs((double)fabsf(tq[s_item * 2] - tq[s_item * 2 + 1])) + eng.per_epsilon, eng.per_alpha);
         SRLX_SSTAMP(40);
         const int prevli = __shfl_up_sync(FULL, s_li, 1), nextli = __shfl_down_sync(FULL, s_li, 1);
         const double prevp = __shfl_up_sync(FULL, pnew, 1);
@@ -1342,8 +1358,12 @@ learner_fast_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_up
           SRLX_FSTAMP(mt == 32, 27);
         }
         if (mw == 0) {
+          if (rank == 0) {
+            mbar_wait_sleep(&mbar[MB_TQ], parb);  // (target, q) of every item, ahead of the all-gather
+            if (per) named_bar_arrive(FBAR_MA, FNM);  // release the update warps first
+            if (lane == 0 && upd + 1 < n_updates) mbar_expect_tx(&mbar[MB_TQ], (uint32_t)B * 8);
+          }
           mbar_wait_sleep(&mbar[MB_AG], parb);  // update t's targets are known everywhere: forward(t) is over in every CTA
-          if (rank == 0 && per) named_bar_arrive(FBAR_MA, FNM);  // release the update warps first
           if (lane == 0 && noisy && upd + 2 < n_updates) {  // ring slot (t+2)%3 was last read by Adam(t-1)
             uint64_t* nb = &mbar[MB_NZ0 + (upd + 2) % 3];
             mbar_expect_tx(nb, (uint32_t)nz_bytes);
@@ -1355,12 +1375,12 @@ learner_fast_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_up
           if (per) {
             if (mw != 0) {
               named_bar_sync(FBAR_MA, FNM);  // targets of update t have arrived (warp 0 saw the AG barrier complete)
-              apply_update(ag + (size_t)parb * B * 8, upd + 2 == n_updates);
+              apply_update(tqb + (size_t)parb * B * 2, upd + 2 == n_updates);
               if (sched & 2) named_bar_arrive(FBAR_UP, FNC + 96);  // CTA 0's compute warps may start backward
             } else {
               // max_priority (proportional_memory.py:176): the priority is monotone in |td|, so one evaluation at max |td|
-              const float* agb = ag + (size_t)parb * B * 8;
-              float m = lane < B ? fabsf(agb[lane * 8 + 4] - agb[lane * 8 + 5]) : 0.f;
+              const float* tq = tqb + (size_t)parb * B * 2;
+              float m = lane < B ? fabsf(tq[lane * 2] - tq[lane * 2 + 1]) : 0.f;
               for (int s = 16; s > 0; s >>= 1) m = fmaxf(m, __shfl_xor_sync(FULL, m, s));
               if (lane == 0) {
                 const double pm = pow_chain(fabs((double)m) + eng.per_epsilon, eng.per_alpha);
