@@ -1,4 +1,1 @@
-set -x
-mkdir -p gpurun_out
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 5 --warmup 3 2>&1 | tail -2 | tee gpurun_out/bench_r1_e_2gpu.json
-timeout 600 python bench.py --steps 10 --warmup 3 2>&1 | tail -1 | tee gpurun_out/bench_r1_e.json
+timeout 900 python -m pytest tests -m gpu -x -q --timeout 120 -k "learning" 2>&1 | tail -8
