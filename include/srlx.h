@@ -171,6 +171,11 @@ typedef struct srlx_engine {
   float* noise_scratch;     /* NoisyNet draws of a chunk of updates, precomputed by all SMs and streamed by the learner
                                (learner_fast.cu); NULL -> the generic learner draws in-kernel */
   uint64_t noise_scratch_bytes;
+  double* tree_blk;         /* optional: blocked copy of the SumTree levels below the shared-memory-cached top (each 5-level
+                               subtree = 62 contiguous doubles in a 512-byte block), rebuilt by srlx_learn at every call and
+                               kept in step by the learner, so the sampler fetches a subtree with one coalesced load per
+                               lane; srlx_tree_blk_bytes(capacity) bytes; NULL -> the sampler reads the flat tree */
+  uint64_t tree_blk_bytes;
 } srlx_engine;
 
 /* ---- library ------------------------------------------------------------------------------------------ */
@@ -226,6 +231,8 @@ int srlx_engine_run(const srlx_engine* eng, uint32_t n_steps, uint32_t updates_p
 /* Which kernel srlx_learn runs for this engine: 1 = the short-critical-path kernel for single-hidden-layer networks
  * (csrc/learner_fast.cu; *cluster_size CTAs, *smem_bytes of shared memory each), 0 = the generic kernel (csrc/learner.cu). */
 int srlx_learner_info(const srlx_engine* eng, int* cluster_size, size_t* smem_bytes);
+/* Bytes the optional srlx_engine.tree_blk buffer needs for a SumTree of `capacity` leaves. */
+size_t srlx_tree_blk_bytes(uint64_t capacity);
 /* The two halves separately (parity tests drive them one at a time). */
 int srlx_vec_step(const srlx_engine* eng, int training, uintptr_t cuda_stream);
 int srlx_learn(const srlx_engine* eng, uint32_t n_updates, uintptr_t cuda_stream);

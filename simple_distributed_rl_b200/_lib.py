@@ -81,6 +81,7 @@ class SrlxEngine(C.Structure):
         ("dbg_q", _P), ("dbg_action", _P), ("dbg_sample_idx", _P), ("dbg_weights", _P), ("dbg_target_q", _P),
         ("dbg_q_sa", _P), ("dbg_grads", _P), ("dbg_windows", _P), ("dbg_clock", _P),
         ("noise_scratch", _P), ("noise_scratch_bytes", C.c_uint64),
+        ("tree_blk", _P), ("tree_blk_bytes", C.c_uint64),
     ]
 
 
@@ -110,6 +111,7 @@ SYMBOLS = [
     ("srlx_vec_step", C.c_int, [C.POINTER(SrlxEngine), _i32, _uptr]),
     ("srlx_learn", C.c_int, [C.POINTER(SrlxEngine), _u32, _uptr]),
     ("srlx_learner_info", C.c_int, [C.POINTER(SrlxEngine), C.POINTER(C.c_int), C.POINTER(C.c_size_t)]),
+    ("srlx_tree_blk_bytes", _sz, [_u64]),
     ("srlx_qnet_forward", C.c_int, [C.POINTER(SrlxEngine), _i32, _P, _u32, _u64, _P, _uptr]),
 ]
 

@@ -140,7 +140,7 @@ __host__ __device__ inline FPlan make_fplan(const srlx_engine& eng, int C, long 
   p.off_samp_slot = take((size_t)2 * p.B4 * 4);
   p.off_samp_w = take((size_t)2 * p.B4 * 4);
   p.off_sdbl = take(2048);  // s_idx, s_att, sperm[4][32] (int), then s_pri, s_tmp (double)
-  p.off_plan = take(eng.mem_kind == SRLX_MEM_PROPORTIONAL ? (size_t)FNM * (5 * 8 + 2 * 9 * 4) : 0);  // old[5], node[9], end[9]
+  p.off_plan = take(eng.mem_kind == SRLX_MEM_PROPORTIONAL ? (size_t)FNM * (5 * 8 + 2 * 9 * 4 + 5 * 4) : 0);  // old[5], node[9], end[9], blocked address[5]
   p.n_cache = 0;
   if (eng.mem_kind == SRLX_MEM_PROPORTIONAL) {
     p.off_sub = take((size_t)kFMemWarps * 8 * kFSubLd * 8);
@@ -153,6 +153,62 @@ __host__ __device__ inline FPlan make_fplan(const srlx_engine& eng, int C, long 
   p.off_cache = take((size_t)p.n_cache * 8);
   p.total = o;
   return p;
+}
+
+// ---- blocked copy of the deep SumTree levels ---------------------------------------------------------------------------
+// Below the `clev` levels cached in shared memory the sampler descends five levels per memory round trip.  In the flat
+// (BFS) layout the 62 nodes of a 5-level subtree sit in five separate runs (6-8 cache lines, two loads per lane); the
+// blocked copy stores every such subtree contiguously -- block = [level 1: 2][level 2: 4]...[level 5: 32] doubles, 512-byte
+// stride -- so lane l's 16-byte load at offset 16*l fetches both children of the subtree's l-th node: one coalesced load
+// per lane, 4 lines per subtree.  Tier r holds the subtrees rooted at level (clev-1) + 5r.
+struct BlkPlan {
+  int n_tiers, total;   // total blocks
+  int first[4], off[4]; // first node index of the tier's root level, block offset of the tier
+};
+__host__ __device__ inline BlkPlan make_blk_plan(long long n_nodes, int clev) {
+  BlkPlan p;
+  p.n_tiers = 0;
+  p.total = 0;
+  for (int r = 0; r < 4; ++r) { p.first[r] = 0; p.off[r] = 0; }
+  if (clev < 1) return p;
+  for (int r = 0; r < 4; ++r) {
+    const int L = clev - 1 + 5 * r;
+    if (L > 28) break;
+    const long long first = (1ll << L) - 1;
+    if (first >= n_nodes || 2 * first + 1 >= n_nodes) break;
+    const long long nb = (1ll << L) < (n_nodes - first) ? (1ll << L) : (n_nodes - first);
+    p.first[r] = (int)first;
+    p.off[r] = p.total;
+    p.total += (int)nb;
+    p.n_tiers = r + 1;
+  }
+  return p;
+}
+// element index (in doubles) of tree node `node` (level >= clev) inside the blocked copy
+__device__ __forceinline__ int blk_addr(const BlkPlan& bp, int clev, int node) {
+  const int a = 31 - __clz(node + 1);  // level of the node
+  const int r = (a - clev) / 5, k = (a - clev) - 5 * r + 1;
+  const int root = ((node + 1) >> k) - 1, j = (node + 1) - ((root + 1) << k);
+  const int first = r == 0 ? bp.first[0] : (r == 1 ? bp.first[1] : (r == 2 ? bp.first[2] : bp.first[3]));
+  const int off = r == 0 ? bp.off[0] : (r == 1 ? bp.off[1] : (r == 2 ? bp.off[2] : bp.off[3]));
+  return (off + root - first) * 64 + (1 << k) - 2 + j;
+}
+__global__ void __launch_bounds__(256) tree_blk_build_kernel(const double* __restrict__ tree, const int n_nodes, const int clev,
+                                                             double* __restrict__ blk) {
+  const BlkPlan bp = make_blk_plan(n_nodes, clev);
+  const int b = blockIdx.x * 4 + (threadIdx.x >> 6), e = threadIdx.x & 63;
+  if (b >= bp.total) return;
+  int r = 0;
+  for (int t = 1; t < bp.n_tiers; ++t)
+    if (b >= bp.off[t]) r = t;
+  const int root = bp.first[r] + (b - bp.off[r]);
+  double v = 0.0;
+  if (e < 62) {
+    const int k = 31 - __clz(e + 2), j = e + 2 - (1 << k);
+    const long long node = (((long long)root + 1) << k) - 1 + j;
+    if (node < n_nodes) v = __ldcg(tree + node);
+  }
+  blk[(size_t)b * 64 + e] = v;
 }
 
 // ---- PTX helpers: DSMEM stores that complete a transaction count on the destination CTA's mbarrier, TMA bulk copy ------
@@ -340,6 +396,7 @@ learner_fast_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_up
   double* plan_old = reinterpret_cast<double*>(smem + pl.off_plan);
   int* plan_node = reinterpret_cast<int*>(smem + pl.off_plan + (size_t)FNM * 5 * 8);
   int* plan_end = plan_node + 9 * FNM;
+  int* plan_baddr = plan_end + 9 * FNM;
   double* cache = reinterpret_cast<double*>(smem + pl.off_cache);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -869,9 +926,13 @@ learner_fast_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_up
       // (mw-1) + 3q of the shared-memory-cached top of the tree, slot kLc + q is level clev + (mw-1) + 3q below it
       constexpr int kLc = 4, kLu = 5, kLv = kLc + kLu;  // 12 cached levels / 3 warps; up to 15 deeper levels / 3 warps
       const int clev = 31 - __clz(n_cache + 1);         // number of cached levels
+      const BlkPlan bp = make_blk_plan(n_nodes, clev);
+      const bool use_blk = per && eng.tree_blk != nullptr && bp.n_tiers > 0 && eng.tree_blk_bytes >= (uint64_t)bp.total * 512;
+      int s_leaf_b = -1;  // sorted lane: element of the item's leaf inside the blocked copy (-1: none)
       // per-thread plan, parked in shared memory ([slot][thread], conflict-free) so the level loops stay rolled:
       int* p_node = plan_node + mt;   // [kLv][FNM] node a leader lane writes at slot q, -1 otherwise
       int* p_end = plan_end + mt;     // [kLv][FNM] last lane of the leader's run
+      int* p_baddr = plan_baddr + mt; // [kLu][FNM] where the uncached node lives in the blocked copy
       double* p_old = plan_old + mt;  // [kLu][FNM] old values of the uncached nodes, fetched while the forward pass runs
       auto level_of = [&](int q) -> int { return q < kLc ? (mw - 1) + 3 * q : clev + (mw - 1) + 3 * (q - kLc); };
       auto level_ok = [&](int q, int a) -> bool { return q < kLc ? (a < clev && a < dmax) : (a < dmax); };
@@ -923,6 +984,22 @@ learner_fast_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_up
           int rnd = 0;
           while (__any_sync(FULL, !done)) {
             double v0[8], v1[8];
+            if (use_blk) {
+              // blocked copy: the 5-level subtree below each sample's node is one 512-byte block; lane l < 31 fetches
+              // both children of the subtree's l-th node with one 16-byte load (finished samples read block 0, unused)
+              const int tfirst = rnd == 0 ? bp.first[0] : (rnd == 1 ? bp.first[1] : (rnd == 2 ? bp.first[2] : bp.first[3]));
+              const int toff = rnd == 0 ? bp.off[0] : (rnd == 1 ? bp.off[1] : (rnd == 2 ? bp.off[2] : bp.off[3]));
+              const double2* bbase = reinterpret_cast<const double2*>(eng.tree_blk) + (lane < 31 ? lane : 0);
+#pragma unroll
+              for (int g = 0; g < 8; ++g) {
+                const int ig = __shfl_sync(FULL, idx, g);
+                const int dg = __shfl_sync(FULL, (int)done, g);
+                const int b = dg ? 0 : toff + (ig - tfirst);
+                const double2 c2 = __ldcg(bbase + (size_t)b * 32);
+                v0[g] = c2.x;
+                v1[g] = c2.y;
+              }
+            } else {
             // unconditional loads from clamped addresses (a predicated load + select makes ptxas wait for every load in
             // turn): nodes past the end of the tree or below finished samples are fetched but never looked at.  Left
             // children drive the walk; a right child's value is only ever needed as the priority of the leaf the walk
@@ -939,6 +1016,7 @@ learner_fast_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_up
             if (k_l == 5) {
 #pragma unroll
               for (int g = 0; g < 8; ++g) v1[g] = __ldcg(eng.tree + nodes[g] + (n_nodes > 1 ? 1 : 0));
+            }
             }
             SRLX_SSTAMP(32 + rnd * 3);
             if (lane < 31) {
@@ -960,7 +1038,7 @@ learner_fast_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_up
                 const double vr = val - ch.x;
                 val = (act && right) ? vr : val;
                 pcur = act ? (right ? ch.y : ch.x) : pcur;
-                pc_ok = act ? (!right || k == 5) : pc_ok;
+                pc_ok = act ? (!right || k == 5 || use_blk) : pc_ok;
                 idx = act ? left + (right ? 1 : 0) : idx;
                 rel = act ? 2 * rel + (right ? 1 : 0) : 0;
               }
@@ -1156,6 +1234,14 @@ learner_fast_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_up
           const int pn = p_node[(kLc + q) * FNM];
           ov[q] = __ldcg(eng.tree + (pn >= 0 ? pn : 0));
         }
+        if (use_blk) {
+#pragma unroll 1
+          for (int q = 0; q < kLu; ++q) {
+            const int pn = p_node[(kLc + q) * FNM];
+            p_baddr[q * FNM] = pn >= 0 ? blk_addr(bp, clev, pn) : -1;
+          }
+          s_leaf_b = (s_valid && sd >= clev) ? blk_addr(bp, clev, s_li) : -1;
+        }
 #pragma unroll
         for (int q = 0; q < kLu; ++q) p_old[q * FNM] = ov[q];
         SRLX_SSTAMP(49);
@@ -1178,6 +1264,7 @@ learner_fast_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_up
           if (s_valid && (lane == 31 || nextli != s_li)) {  // the last item touching a leaf wins
             __stcg(eng.tree + s_li, pnew);
             if (s_li < n_cache) cache[s_li] = pnew;
+            if (use_blk && s_leaf_b >= 0) __stcg(eng.tree_blk + s_leaf_b, pnew);
           }
         }
         SRLX_SSTAMP(41);
@@ -1200,6 +1287,7 @@ learner_fast_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_up
             const double nv = old + sum;
             __stcg(eng.tree + pn, nv);
             if (q < kLc) cache[pn] = nv;
+            else if (use_blk) __stcg(eng.tree_blk + p_baddr[(q - kLc) * FNM], nv);
           }
         };
 #pragma unroll 2
@@ -1486,6 +1574,17 @@ static int learn_fast(const srlx_engine* eng, uint32_t n_updates, uintptr_t cuda
       }
     }
   }
+  // blocked copy of the deep tree levels: the rollout writes only the flat tree, so rebuild once per call
+  if (eng->mem_kind == SRLX_MEM_PROPORTIONAL && eng->tree_blk) {
+    int clev = 0;
+    while (clev < cache_levels && clev < kFCacheLevels && ((1ll << (clev + 1)) - 1) <= n_nodes) ++clev;
+    const BlkPlan bp = make_blk_plan(n_nodes, clev);
+    if (bp.n_tiers > 0 && eng->tree_blk_bytes >= (uint64_t)bp.total * 512) {
+      tree_blk_build_kernel<<<(unsigned)((bp.total + 3) / 4), 256, 0, stream>>>(eng->tree, (int)n_nodes, clev, eng->tree_blk);
+      count_launch();
+      SRLX_CHECK_CUDA(cudaGetLastError());
+    }
+  }
   for (uint32_t done = 0; done < n_updates;) {
     const uint32_t n = (n_updates - done) < chunk ? (n_updates - done) : chunk;
     if (eng->net.noisy) {
@@ -1528,6 +1627,19 @@ __global__ void pow_chain_kernel(const double* __restrict__ x, double a, double*
 }
 
 }  // namespace srlx
+
+// bytes of the blocked deep-tree copy for `capacity` leaves: the largest layout over the cache depths srlx_learn may pick
+extern "C" size_t srlx_tree_blk_bytes(uint64_t capacity) {
+  using namespace srlx;
+  const long long n_nodes = 2ll * (long long)capacity - 1;
+  size_t best = 0;
+  for (int clev = 1; clev <= kFCacheLevels; ++clev) {
+    if (((1ll << clev) - 1) > n_nodes) break;
+    const BlkPlan bp = make_blk_plan(n_nodes, clev);
+    if ((size_t)bp.total * 512 > best) best = (size_t)bp.total * 512;
+  }
+  return best;
+}
 
 // out[i] = the learner's priority power x[i]^a (test tap: parity of pow_chain with libm pow)
 extern "C" int srlx_dbg_pow(const double* x_dev, double a, double* out_dev, size_t n, uintptr_t cuda_stream) {

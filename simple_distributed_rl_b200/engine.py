@@ -99,6 +99,8 @@ class DeviceEngine:
         if self.per:
             self.t["tree"] = z(2 * self.cap - 1, torch.float64)
             self.t["tree_scratch"] = z(2 * (self.E + 2), torch.float64)
+            # blocked copy of the deep SumTree levels for the learner's sampler (csrc/learner_fast.cu), rebuilt per learn call
+            self.t["tree_blk"] = z(max(64, self.lib.srlx_tree_blk_bytes(self.cap) // 8), torch.float64)
         if track_episodes:
             self.t["env_first_ep_reward"] = z(self.E, torch.float64)
             self.t["env_last_ep_len"] = z(self.E, torch.int32)
@@ -140,6 +142,8 @@ class DeviceEngine:
         c.net = self.spec.to_c()
         if "noise_scratch" in self.t:
             c.noise_scratch_bytes = self.t["noise_scratch"].numel() * 4
+        if "tree_blk" in self.t:
+            c.tree_blk_bytes = self.t["tree_blk"].numel() * 8
         for name, _ in _lib.SrlxEngine._fields_:
             if name in self.t:
                 setattr(c, name, self.t[name].data_ptr())
