@@ -1,1 +1,2 @@
-timeout 900 python -m pytest tests -m gpu -x -q --timeout 120 -k "learning" 2>&1 | tail -8
+SRLX_SCHED=0 timeout 300 python tools/phase_clocks.py 2>&1 | tail -1 | cut -c1-50
+SRLX_SCHED=4 timeout 300 python tools/phase_clocks.py 2>&1 | tail -1 | cut -c1-50

@@ -33,7 +33,7 @@ int learn_generic(const srlx_engine* eng, uint32_t n_updates, uintptr_t cuda_str
 constexpr int kFCmpWarps = 16, kFMemWarps = 4;
 constexpr int FNC = kFCmpWarps * 32, FNM = kFMemWarps * 32, FNT = FNC + FNM;
 constexpr int kFMaxC = 16, kFMaxSeg = 8, kFCacheLevels = 12, kFMaxChunk = 256, kFSubLd = 66;
-enum { FBAR_CMP = 1, FBAR_MEM = 2, FBAR_MA = 3, FBAR_MB = 4, FBAR_FW = 5, FBAR_UP = 6 };
+enum { FBAR_CMP = 1, FBAR_MEM = 2, FBAR_MA = 3, FBAR_MB = 4 };
 enum { FSEG_W = 0, FSEG_B = 1, FSEG_O = 2, FSEG_OB = 3 };
 enum { MB_RS = 0, MB_AG, MB_S, MB_WT, MB_XR, MB_NZ0, MB_NZ1, MB_NZ2, MB_TQ, MB_COUNT };
 
@@ -349,7 +349,7 @@ __global__ void __launch_bounds__(128) noise_precompute_kernel(const __grid_cons
 template <int TC>
 __global__ void __launch_bounds__(FNT, 1)
 learner_fast_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_updates, const float* __restrict__ noise,
-                    const int max_cache_levels, const int sched) {
+                    const int max_cache_levels) {
   extern __shared__ __align__(16) unsigned char smem[];
   cg::cluster_group cluster = cg::this_cluster();
   constexpr bool FLAG = TC > 0;
@@ -670,9 +670,6 @@ learner_fast_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_up
           }
         }
       }
-      // CTA 0 time-slices its SM: the replay warps' bookkeeping (update plan, IS weights) runs in the window where the
-      // compute warps idle (reduce-scatter / targets / all-gather), not against the forward pass
-      if (rank == 0 && (sched & 1)) named_bar_arrive(FBAR_FW, FNT);
       named_bar_sync(FBAR_CMP, FNC);
       SRLX_FSTAMP(ct == 0, 1);
       // ---------------------------------------------------------------- reduce over warps, scatter to the owning CTA
@@ -840,9 +837,6 @@ learner_fast_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_up
         mbar_wait_sleep(&mbar[MB_AG], parb);
       }
       named_bar_sync(FBAR_CMP, FNC);
-      // ... and backward + Adam of CTA 0 wait for the SumTree update (the head of the chain to the next sample); they then
-      // overlap the sampler's memory round trips.  The other CTAs start backward at once.
-      if (rank == 0 && per && (sched & 2)) named_bar_sync(FBAR_UP, FNC + 96);
       SRLX_FSTAMP(ct == 0, 3);
       // ---------------------------------------------------------------- backward of this CTA's slice: thread = (unit, row group)
       {
@@ -1434,7 +1428,6 @@ learner_fast_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_up
         }
         if (rank == 0) {
           // ---- off the critical path: after the compute warps have issued forward(t), while they wait for the targets --
-          if (sched & 1) named_bar_sync(FBAR_FW, FNT);
           if (mw == 0) {
             send_weights(tc, parb);
             if (upd > 0) bookkeeping(upd - 1);
@@ -1464,7 +1457,6 @@ learner_fast_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_up
             if (mw != 0) {
               named_bar_sync(FBAR_MA, FNM);  // targets of update t have arrived (warp 0 saw the AG barrier complete)
               apply_update(tqb + (size_t)parb * B * 2, upd + 2 == n_updates);
-              if (sched & 2) named_bar_arrive(FBAR_UP, FNC + 96);  // CTA 0's compute warps may start backward
             } else {
               // max_priority (proportional_memory.py:176): the priority is monotone in |td|, so one evaluation at max |td|
               const float* tq = tqb + (size_t)parb * B * 2;
@@ -1543,8 +1535,6 @@ static int learn_fast(const srlx_engine* eng, uint32_t n_updates, uintptr_t cuda
     const int v = atoi(e);
     if (v >= 1 && (uint32_t)v < chunk) chunk = (uint32_t)v;
   }
-  int sched = 0;  // (experiment knobs, default off) bit 0: CTA 0's replay bookkeeping waits for the forward pass; bit 1: its backward waits for the tree update
-  if (const char* e = getenv("SRLX_SCHED")) sched = atoi(e);
   cudaStream_t stream = (cudaStream_t)cuda_stream;
   // L2 set-aside for the tree (device-wide limit, set once per device; SRLX_L2_PERSIST=0 disables)
   size_t l2_window_bytes = 0;
@@ -1613,7 +1603,7 @@ static int learn_fast(const srlx_engine* eng, uint32_t n_updates, uintptr_t cuda
       attr[1].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
       cfg.numAttrs = 2;
     }
-    SRLX_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, *eng, n, (const float*)eng->noise_scratch, cache_levels, sched));
+    SRLX_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, *eng, n, (const float*)eng->noise_scratch, cache_levels));
     count_launch();
     SRLX_CHECK_CUDA(cudaGetLastError());
     done += n;

@@ -1,0 +1,25 @@
+#!/usr/bin/env python
+"""Small learner workload for compute-sanitizer (memcheck / racecheck / synccheck): a few vector steps and updates of the
+Rainbow default shape (learner_fast_kernel<16>) and of a generic-kernel shape."""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from simple_distributed_rl_b200.engine import DeviceEngine, EngineConfig  # noqa: E402
+
+kw = dict(env="CartPole-v1", algo="rainbow", hidden=(512,), dueling="average", noisy=True, mem_kind=1, multisteps=3,
+          n_envs=64, ring_rows=16, batch_size=32, warmup_size=64, seed=1)
+d = DeviceEngine(EngineConfig(**kw))
+d.run(20, 0)
+d.learn(int(os.environ.get("SAN_UPDATES", "6")))
+torch.cuda.synchronize()
+print("fast:", d.learner_info(), d.read_state().train_count)
+kw2 = dict(env="CartPole-v1", algo="dqn", hidden=(64, 64), mem_kind=1, multisteps=1, n_envs=64, ring_rows=8, batch_size=32,
+           warmup_size=64, epsilon=0.2)
+g = DeviceEngine(EngineConfig(**kw2))
+g.run(10, 0)
+g.learn(3)
+torch.cuda.synchronize()
+print("generic:", g.learner_info(), g.read_state().train_count)
