@@ -1536,35 +1536,9 @@ static int learn_fast(const srlx_engine* eng, uint32_t n_updates, uintptr_t cuda
     if (v >= 1 && (uint32_t)v < chunk) chunk = (uint32_t)v;
   }
   cudaStream_t stream = (cudaStream_t)cuda_stream;
-  // L2 set-aside for the tree (device-wide limit, set once per device; SRLX_L2_PERSIST=0 disables)
-  size_t l2_window_bytes = 0;
-  {
-    const char* e = getenv("SRLX_L2_PERSIST");
-    if (eng->mem_kind == SRLX_MEM_PROPORTIONAL && !(e && e[0] == '0')) {
-      static int persist_dev[64] = {};  // 0 = unknown, 1 = configured, -1 = unavailable
-      static size_t persist_max_window[64] = {};
-      int dev = 0;
-      SRLX_CHECK_CUDA(cudaGetDevice(&dev));
-      const size_t tree_bytes = (size_t)(2ll * eng->ring_rows * eng->n_envs - 1) * 8;
-      if (dev >= 0 && dev < 64) {
-        if (persist_dev[dev] == 0) {
-          int max_persist = 0, max_window = 0;
-          cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev);
-          cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, dev);
-          size_t want = tree_bytes < (size_t)max_persist ? tree_bytes : (size_t)max_persist;
-          if (want > 0 && max_window > 0 && cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess) {
-            persist_dev[dev] = 1;
-            persist_max_window[dev] = (size_t)max_window;
-          } else {
-            persist_dev[dev] = -1;
-            cudaGetLastError();
-          }
-        }
-        if (persist_dev[dev] == 1) l2_window_bytes = tree_bytes < persist_max_window[dev] ? tree_bytes : persist_max_window[dev];
-      }
-    }
-  }
   // blocked copy of the deep tree levels: the rollout writes only the flat tree, so rebuild once per call
+  const void* l2_base = eng->tree;
+  size_t l2_want = eng->mem_kind == SRLX_MEM_PROPORTIONAL ? (size_t)n_nodes * 8 : 0;
   if (eng->mem_kind == SRLX_MEM_PROPORTIONAL && eng->tree_blk) {
     int clev = 0;
     while (clev < cache_levels && clev < kFCacheLevels && ((1ll << (clev + 1)) - 1) <= n_nodes) ++clev;
@@ -1573,6 +1547,40 @@ static int learn_fast(const srlx_engine* eng, uint32_t n_updates, uintptr_t cuda
       tree_blk_build_kernel<<<(unsigned)((bp.total + 3) / 4), 256, 0, stream>>>(eng->tree, (int)n_nodes, clev, eng->tree_blk);
       count_launch();
       SRLX_CHECK_CUDA(cudaGetLastError());
+      l2_base = eng->tree_blk;  // what the sampler re-reads at random every update
+      l2_want = (size_t)bp.total * 512;
+    }
+  }
+  // L2 set-aside (persisting access-policy window, a launch attribute of the learner) for the structure the sampler reads:
+  // its deep levels are touched once per ~4000 updates each and would otherwise be evicted by the ring / noise traffic.
+  // The device-wide set-aside size only ever grows; SRLX_L2_PERSIST=0 disables.
+  size_t l2_window_bytes = 0;
+  {
+    const char* e = getenv("SRLX_L2_PERSIST");
+    if (l2_want > 0 && !(e && e[0] == '0')) {
+      static size_t persist_limit[64] = {};  // current cudaLimitPersistingL2CacheSize we set, per device
+      static int persist_state[64] = {};     // 0 = unknown, 1 = available, -1 = unavailable
+      static size_t persist_max[64] = {}, window_max[64] = {};
+      int dev = 0;
+      SRLX_CHECK_CUDA(cudaGetDevice(&dev));
+      if (dev >= 0 && dev < 64) {
+        if (persist_state[dev] == 0) {
+          int max_persist = 0, max_window = 0;
+          cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev);
+          cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, dev);
+          persist_max[dev] = (size_t)(max_persist > 0 ? max_persist : 0);
+          window_max[dev] = (size_t)(max_window > 0 ? max_window : 0);
+          persist_state[dev] = (max_persist > 0 && max_window > 0) ? 1 : -1;
+        }
+        if (persist_state[dev] == 1) {
+          const size_t want = l2_want < persist_max[dev] ? l2_want : persist_max[dev];
+          if (want > persist_limit[dev]) {
+            if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess) persist_limit[dev] = want;
+            else cudaGetLastError();
+          }
+          if (persist_limit[dev] > 0) l2_window_bytes = l2_want < window_max[dev] ? l2_want : window_max[dev];
+        }
+      }
     }
   }
   for (uint32_t done = 0; done < n_updates;) {
@@ -1596,7 +1604,7 @@ static int learn_fast(const srlx_engine* eng, uint32_t n_updates, uintptr_t cuda
     cfg.numAttrs = 1;
     if (l2_window_bytes > 0) {  // keep the SumTree resident in L2: its deep levels are re-read at random every update
       attr[1].id = cudaLaunchAttributeAccessPolicyWindow;
-      attr[1].val.accessPolicyWindow.base_ptr = (void*)eng->tree;
+      attr[1].val.accessPolicyWindow.base_ptr = const_cast<void*>(l2_base);
       attr[1].val.accessPolicyWindow.num_bytes = l2_window_bytes;
       attr[1].val.accessPolicyWindow.hitRatio = 1.0f;
       attr[1].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
