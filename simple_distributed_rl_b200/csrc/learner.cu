@@ -637,7 +637,8 @@ learner_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_updates
           fence_cluster();
           mbar_arrive_remote(&mbar[1], lane);
         }
-        mbar_wait(&mbar[1], upd & 1);
+        if (cw == 0) mbar_wait_sleep(&mbar[1], upd & 1);  // one polling warp; the others block on the named barrier
+        named_bar_sync(BAR_CMP, NCP);
         // dA_lw[r][k] (in place in the stored activations), ReLU-masked, summed over the CTAs in rank order
         for (int w = ct; w < n_vals; w += NCP) {
           const int r = w / Kw, k = w - r * Kw;
@@ -748,10 +749,13 @@ learner_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_updates
           bool any = true;
           while (any) {
             double v[kSampleGroup];
+            // unconditional loads from clamped addresses (a predicated load + select makes every load wait for the previous
+            // one); values of nodes past the end of the tree are never looked at
 #pragma unroll
             for (int g = 0; g < kSampleGroup; ++g) {
-              const int64_t node = ((idx[g] + 1) << k_l) - 1 + 2 * q_l;
-              v[g] = (lane < 31 && node < n_nodes) ? __ldcg(eng.tree + node) : 0.0;
+              int64_t node = ((idx[g] + 1) << k_l) - 1 + 2 * q_l;
+              node = node < n_nodes ? node : n_nodes - 1;
+              v[g] = __ldcg(eng.tree + node);
             }
             any = false;
 #pragma unroll
@@ -866,7 +870,8 @@ learner_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_updates
       float* x_cur = xin + (size_t)parb * pl.NX * pl.ldx0;
       const int* slot = samp_slot + parb * B;
       const float* s_w = samp_w + parb * B;
-      mbar_wait(&mbar[2], upd & 1);  // sample(t) has arrived from CTA 0
+      if (aw == 0) mbar_wait_sleep(&mbar[2], upd & 1);  // sample(t) has arrived from CTA 0 (one polling warp)
+      named_bar_sync(BAR_AUX, NA);
       SRLX_STAMP(at == 0, 16);
       // ---------------------------------------------------------------- gather the windows (one L2 round trip)
       for (int w = at; w < BM; w += NA) {
@@ -874,12 +879,21 @@ learner_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_updates
         const int s0 = slot[i];
         const int rho = s0 / E, e = s0 - rho * E;
         const int sk = ((rho + k) % R) * E + e;
-        g_act[w] = __ldcg(eng.ring_action + sk);
-        g_rew[w] = __ldcg(eng.ring_reward + sk);
-        g_term[w] = (float)__ldcg(eng.ring_term + sk);
-        g_done[w] = (int)__ldcg(eng.ring_done + sk);
+        // all loads of this record are issued before the first dependent store
+        const int a = __ldcg(eng.ring_action + sk);
+        const float rw = __ldcg(eng.ring_reward + sk);
+        const unsigned char tm = __ldcg(eng.ring_term + sk), dn = __ldcg(eng.ring_done + sk);
+        float xv[SRLX_MAX_OBS];
+#pragma unroll
+        for (int d = 0; d < SRLX_MAX_OBS; ++d) xv[d] = d < D ? __ldcg(eng.ring_next_obs + (size_t)sk * D + d) : 0.f;
+        g_act[w] = a;
+        g_rew[w] = rw;
+        g_term[w] = (float)tm;
+        g_done[w] = (int)dn;
         float* xr = x_cur + (size_t)(B + w) * pl.ldx0;
-        for (int d = 0; d < D; ++d) xr[d] = __ldcg(eng.ring_next_obs + (size_t)sk * D + d);
+#pragma unroll
+        for (int d = 0; d < SRLX_MAX_OBS; ++d)
+          if (d < D) xr[d] = xv[d];
       }
       for (int w = at; w < B * D; w += NA) {
         const int i = w / D, d = w - i * D;
@@ -919,7 +933,8 @@ learner_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_updates
       SRLX_STAMP(at == 0, 17);
 
       // ---------------------------------------------------------------- reduce the partial sums, dueling combine
-      mbar_wait(&mbar[0], upd & 1);
+      if (aw == 0) mbar_wait_sleep(&mbar[0], upd & 1);
+      named_bar_sync(BAR_AUX, NA);
       SRLX_STAMP(at == 0, 18);
       {
         const int n_vals = pl.NRq * nout;
@@ -1086,7 +1101,7 @@ learner_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_updates
               const long long node = has ? (ip1 >> (d - a)) - 1 : -1 - (long long)lane;
               const unsigned mask = __match_any_sync(0xffffffffu, node);
               if (has && lane == __ffs(mask) - 1) {
-                double v = (node < (long long)pl.n_cache) ? cache[node] : __ldcg(eng.tree + node);
+                double v = __ldcg(eng.tree + node);  // write-through keeps the global tree current
                 unsigned m = mask;
                 while (m) {
                   const int j = __ffs(m) - 1;
