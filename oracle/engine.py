@@ -145,10 +145,13 @@ class OracleEngine:
         b = a + len(values) - 1
         change = np.asarray(values, dtype=np.float64) - tree[a : b + 1]
         tree[a : b + 1] = values
-        while a > 0:
-            pa, pb = (a - 1) // 2, (b - 1) // 2
+        # a row of a non-power-of-two tree can straddle the two leaf depths, so [a, b] may span two levels: climb until
+        # the whole range has collapsed into the root (b == 0); the root has no parent
+        while b > 0:
+            lo = max(a, 1)
+            pa, pb = (lo - 1) // 2, (b - 1) // 2
             pc = np.zeros(pb - pa + 1, dtype=np.float64)
-            for i in range(a, b + 1):
+            for i in range(lo, b + 1):
                 pc[(i - 1) // 2 - pa] += change[i - a]
             tree[pa : pb + 1] += pc
             a, b, change = pa, pb, pc

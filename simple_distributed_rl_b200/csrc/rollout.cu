@@ -157,15 +157,18 @@ __device__ inline void tree_set_row(double* __restrict__ tree, int64_t cap, int6
     __stcg(tree + a + i, value);
   }
   __syncthreads();
-  while (a > 0) {
-    const int64_t pa = (a - 1) / 2, pb = (b - 1) / 2;
+  // A row of a non-power-of-two tree can straddle the two leaf depths, so [a, b] may span two levels: keep climbing until
+  // the whole range has collapsed into the root (b == 0), not just its left end; the root itself has no parent.
+  while (b > 0) {
+    const int64_t lo = a > 0 ? a : 1;
+    const int64_t pa = (lo - 1) / 2, pb = (b - 1) / 2;
     const int np = (int)(pb - pa + 1);
     for (int i = tid; i < np; i += nt) {
       const int64_t p = pa + i;
       const int64_t l = 2 * p + 1, r = 2 * p + 2;
       double c = 0.0;
-      if (l >= a && l <= b) c += __ldcg(cur + (l - a));
-      if (r >= a && r <= b) c += __ldcg(cur + (r - a));
+      if (l >= lo && l <= b) c += __ldcg(cur + (l - a));
+      if (r >= lo && r <= b) c += __ldcg(cur + (r - a));
       __stcg(nxt + i, c);
       __stcg(tree + p, __ldcg(tree + p) + c);
     }

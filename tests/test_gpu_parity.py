@@ -529,6 +529,53 @@ def test_full_size_properties():
     assert np.abs(obs[:, 0]).max() <= 2.4 + 1e-6 and np.abs(obs[:, 2]).max() <= 0.2095 + 1e-6
 
 
+def _blocked_copy_from_flat(tree, n_nodes, clev):
+    """numpy restatement of csrc/learner_fast.cu::make_blk_plan / tree_blk_build_kernel."""
+    blocks = []
+    for r in range(4):
+        L = clev - 1 + 5 * r
+        first = (1 << L) - 1
+        if first >= n_nodes or 2 * first + 1 >= n_nodes:
+            break
+        nb = min(1 << L, n_nodes - first)
+        blk = np.zeros((nb, 64))
+        for k in range(1, 6):
+            j = np.arange(1 << k)
+            node = ((first + np.arange(nb)[:, None] + 1) << k) - 1 + j[None, :]
+            ok = node < n_nodes
+            vals = np.where(ok, tree[np.minimum(node, n_nodes - 1)], 0.0)
+            blk[:, (1 << k) - 2:(1 << k) - 2 + (1 << k)] = vals
+        blocks.append(blk)
+    return np.concatenate(blocks).reshape(-1) if blocks else np.zeros(0)
+
+
+@pytest.mark.parametrize("n_envs,ring_rows", [(8192, 32), (1000, 37)])
+def test_blocked_tree_copy_stays_in_step_with_the_flat_tree(n_envs, ring_rows):
+    """The sampler reads a blocked copy of the deep SumTree levels that the learner writes through: after many updates
+    inside one launch it must still be exactly the flat (reference-layout) tree re-blocked, and the flat tree must
+    still be a sum tree (power-of-two and ragged capacity)."""
+    from simple_distributed_rl_b200.engine import DeviceEngine, EngineConfig
+
+    cfg = EngineConfig(env="CartPole-v1", algo="rainbow", hidden=(512,), dueling="average", noisy=True, mem_kind=1, multisteps=3,
+                       n_envs=n_envs, ring_rows=ring_rows, batch_size=32, warmup_size=1000)
+    dev = DeviceEngine(cfg)
+    dev.run(ring_rows + 3, 0)
+    dev.learn(700)  # 512 + 188: two launches, the second one continues on the copy the first one maintained
+    assert dev.read_state().train_count == 700
+    tree = dev.t["tree"].cpu().numpy()
+    n_nodes = 2 * dev.cap - 1
+    clev = 12
+    while (1 << clev) - 1 > n_nodes:
+        clev -= 1
+    want = _blocked_copy_from_flat(tree, n_nodes, clev)
+    got = dev.t["tree_blk"].cpu().numpy()[: want.size]
+    np.testing.assert_array_equal(got, want)
+    cap = dev.cap
+    child_sum = tree[1::2][: cap - 1] + tree[2::2][: cap - 1]
+    np.testing.assert_allclose(tree[: cap - 1], child_sum, rtol=1e-9, atol=1e-9)
+    assert np.isfinite(dev.get_params()[0]).all()
+
+
 # ------------------------------------------------------------------------------------------------------------------
 # Learning-quality gates: the reference's real acceptance tests are reward thresholds after training
 # (tests/algorithms_/base_dqn.py:8-36, base_rainbow.py:8-38: Grid mean reward >= its baseline 0.65 over 100 episodes,

@@ -185,3 +185,31 @@ def test_trainer_update_matches_reference(path):
             tsig = st.sigma.detach().numpy().copy() if noisy else None
         np.testing.assert_allclose(tmu, g["tmu_after"][u], rtol=1e-5, atol=1e-7)
     assert list(g["update_steps"]) == list(range(len(g["losses"])))
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# The vectorised engine adds a whole row of E leaves to the SumTree at once (oracle/engine.py::_tree_set_range, device twin
+# csrc/rollout.cu::tree_set_row).  Its result has to equal the reference's one-leaf-at-a-time update
+# (proportional_memory.py:85-90, restated and golden-pinned in oracle/sumtree.py) up to fp64 association -- including rows
+# that straddle the two leaf depths of a non-power-of-two tree, where the index range spans two levels.
+@pytest.mark.parametrize("E,R", [(3, 11), (5, 7), (48, 12), (33, 5), (40, 6), (1000, 37), (7, 1), (64, 4)])
+def test_bulk_row_set_equals_sequential_reference_updates(E, R):
+    from types import SimpleNamespace
+
+    from oracle import engine as oeng
+    from oracle import sumtree
+
+    cap = E * R
+    bulk = SimpleNamespace(cap=cap, per=SimpleNamespace(tree=sumtree.SumTree(cap)))
+    seq = sumtree.SumTree(cap)
+    rng = np.random.default_rng(E * 1000 + R)
+    for step in range(2 * R + 3):  # wraps the ring twice: rows are overwritten
+        row = step % R
+        vals = rng.uniform(0.0, 2.0, size=E) if step % 3 else np.zeros(E)
+        oeng.OracleEngine._tree_set_range(bulk, row * E, vals)
+        for j in range(E):
+            seq.update(row * E + j + cap - 1, float(vals[j]))
+        np.testing.assert_allclose(bulk.per.tree.tree, seq.tree, rtol=1e-12, atol=1e-9)  # sums of up to E x 2.0
+    tree = bulk.per.tree.tree
+    if cap > 1:
+        np.testing.assert_allclose(tree[: cap - 1], tree[1::2][: cap - 1] + tree[2::2][: cap - 1], rtol=1e-12, atol=1e-9)
