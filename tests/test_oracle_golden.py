@@ -270,4 +270,25 @@ def test_dqn_record_equals_reference_worker_batches(golden_dir):
     np.testing.assert_array_equal(d["dqn_b_a"], d["dqn_a"][:n])
     np.testing.assert_array_equal(d["dqn_b_r"], d["dqn_r"][:n])
     np.testing.assert_array_equal(d["dqn_b_undone"], 1 - d["dqn_term"][:n])  # == 1 - ring_term, what the learner multiplies gamma with
-    assert (d["dqn_done"][:n] > d["dqn_term"][:n]).any() or True  # truncated-but-not-terminated steps keep undone = 1
+
+
+def test_grid_truncation_step_matches_reference_envrun(golden_dir):
+    """EnvRun truncates when step_num > max_episode_steps (env_run.py:361): on Grid (max 50) every truncated episode of the
+    reference log is 51 steps long and no episode is longer -- the engine's trunc_limit (oracle/envs.py, envspec.py)."""
+    from oracle import envs as oenvs
+
+    d = np.load(os.path.join(golden_dir, "worker_records.npz"))
+    limit = oenvs.make_spec("Grid").trunc_limit
+    seen_truncated = False
+    for name in ("rainbow_m3", "rainbow_m2_clip", "dqn"):
+        done, term = d[f"{name}_done"], d[f"{name}_term"]
+        cur = 0
+        for i in range(len(done)):
+            cur += 1
+            assert cur <= limit
+            if done[i]:
+                if not term[i]:
+                    assert cur == limit
+                    seen_truncated = True
+                cur = 0
+    assert seen_truncated
