@@ -44,7 +44,7 @@ extern "C" {
 #define SRLX_MAX_BATCH 256
 
 /* ---- environments (closed-form, stepped on device) ------------------------------------------------------ */
-enum { SRLX_ENV_GRID = 0, SRLX_ENV_CARTPOLE = 1 };
+enum { SRLX_ENV_GRID = 0, SRLX_ENV_CARTPOLE = 1, SRLX_ENV_PENDULUM = 2 };
 
 /* dueling combine: srl/rl/torch_/blocks/dueling_network.py:51-58 */
 enum { SRLX_DUEL_NONE = 0, SRLX_DUEL_AVERAGE = 1, SRLX_DUEL_MAX = 2, SRLX_DUEL_NAIVE = 3 };
@@ -131,6 +131,9 @@ typedef struct srlx_engine {
   double grid_slip_cdf[16];    /* [chosen action][4] normalised cdf in the order np.random.choice sees (UP,DOWN,RIGHT,LEFT) */
   int32_t grid_slip_action[4]; /* executed action for each cdf slot: {3,1,2,0} */
   double grid_move_reward, grid_goal_reward, grid_hole_reward;
+  /* ---- discretised continuous action (Pendulum): value of action index a, the reference's BoxSpace division table
+   *      (srl/base/spaces/box.py:317-366, RLConfig.action_division_num srl/base/rl/config.py:55), float32 values ---- */
+  double act_tbl[16];
   /* ---- network ---- */
   srlx_net net;
   /* ---- device buffers (caller-owned) ---- */

@@ -218,9 +218,87 @@ class CartPoleSpec:
         return np.array([x, x_dot, theta, theta_dot], dtype=np.float64), 1.0, terminated
 
 
+# --------------------------------------------------------------------------------------------------------
+# Pendulum-v1 (gymnasium 1.2.0 restatement; parity vs gymnasium unpinned) with the reference's discretised actions
+# --------------------------------------------------------------------------------------------------------
+_PSIN_C = [-1.0 / 25852016738884976640000.0, 1.0 / 51090942171709440000.0, -1.0 / 121645100408832000.0,
+           1.0 / 355687428096000.0, -1.0 / 1307674368000.0, 1.0 / 6227020800.0, -1.0 / 39916800.0, 1.0 / 362880.0,
+           -1.0 / 5040.0, 1.0 / 120.0, -1.0 / 6.0, 1.0]
+_PCOS_C = [-1.0 / 1124000727777607680000.0, 1.0 / 2432902008176640000.0, -1.0 / 6402373705728000.0,
+           1.0 / 20922789888000.0, -1.0 / 87178291200.0, 1.0 / 479001600.0, -1.0 / 3628800.0, 1.0 / 40320.0,
+           -1.0 / 720.0, 1.0 / 24.0, -1.0 / 2.0, 1.0]
+_PI, _TWO_PI, _INV_TWO_PI, _HALF_PI = np.float64(3.141592653589793), np.float64(6.283185307179586), np.float64(0.15915494309189535), np.float64(1.5707963267948966)
+
+
+def pend_angle_normalize(x):
+    """((x + pi) mod 2 pi) - pi as y - floor(y / 2pi) * 2pi - pi (device twin: csrc/envs.cuh::pend_angle_normalize)."""
+    y = np.float64(x) + _PI
+    k = np.floor(y * _INV_TWO_PI)
+    return (y - k * _TWO_PI) - _PI
+
+
+def pend_sincos(an):
+    an = np.float64(an)
+    r, csign = an, np.float64(1.0)
+    if an > _HALF_PI:
+        r, csign = _PI - an, np.float64(-1.0)
+    elif an < -_HALF_PI:
+        r, csign = -_PI - an, np.float64(-1.0)
+    z = r * r
+    ps = np.float64(_PSIN_C[0])
+    for c in _PSIN_C[1:]:
+        ps = ps * z + np.float64(c)
+    pc = np.float64(_PCOS_C[0])
+    for c in _PCOS_C[1:]:
+        pc = pc * z + np.float64(c)
+    return ps * r, csign * pc
+
+
+def division_table(low, high, n):
+    """BoxSpace.create_division_tbl, 1-D float32 Box (srl/base/spaces/box.py:340-365)."""
+    lo, hi = np.float32(low), np.float32(high)
+    diff = (hi - lo) / (n - 1)
+    return np.array([np.float32(lo + diff * j) for j in range(n)], dtype=np.float32)
+
+
+class PendulumSpec:
+    env_id = 2
+    obs_dim = 3
+    trunc_limit = 200  # gymnasium TimeLimit(max_episode_steps=200)
+    trunc_overrides_term = 1
+    max_speed, max_torque, dt = 8.0, 2.0, 0.05
+
+    def __init__(self, action_division_num=10):
+        self.n_actions = int(action_division_num)
+        self.action_table = division_table(-self.max_torque, self.max_torque, self.n_actions).astype(np.float64)
+
+    def reset(self, seed, e, episode):
+        w = philox.words(seed, philox.STREAM_ENV_RESET, e, episode, 0)
+        th = -_PI + _TWO_PI * np.float64(philox.u01_f64(w[0], w[1]))
+        thdot = np.float64(-1.0) + np.float64(2.0) * np.float64(philox.u01_f64(w[2], w[3]))
+        return np.array([th, thdot, 0.0, 0.0], dtype=np.float64)
+
+    def obs(self, st):
+        sn, cs = pend_sincos(pend_angle_normalize(st[0]))
+        return np.array([cs, sn, st[1]], dtype=np.float64).astype(np.float32)
+
+    def step(self, st, action, seed=None, e=None, g=None):
+        th, thdot = np.float64(st[0]), np.float64(st[1])
+        u = np.float64(self.action_table[action])
+        an = pend_angle_normalize(th)
+        sn, _ = pend_sincos(an)
+        costs = (an * an + np.float64(0.1) * (thdot * thdot)) + np.float64(0.001) * (u * u)
+        newthdot = thdot + (np.float64(15.0) * sn + np.float64(3.0) * u) * np.float64(self.dt)
+        newthdot = np.float64(min(max(newthdot, -self.max_speed), self.max_speed))
+        newth = th + newthdot * np.float64(self.dt)
+        return np.array([newth, newthdot, 0.0, 0.0], dtype=np.float64), float(-costs), False
+
+
 def make_spec(env_id, **kw):
     if env_id in (0, "Grid", "grid"):
         return GridSpec(**kw)
     if env_id in (1, "CartPole-v1", "cartpole"):
         return CartPoleSpec()
+    if env_id in (2, "Pendulum-v1", "pendulum"):
+        return PendulumSpec(**kw)
     raise ValueError(env_id)

@@ -6,7 +6,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("SRLX_LIB") or os.path.join(_HERE, "libsrlx.so")  # SRLX_LIB: diagnostic builds (phase clocks)
 
 SRLX_MAX_LAYERS = 6
-ENV_GRID, ENV_CARTPOLE = 0, 1
+ENV_GRID, ENV_CARTPOLE, ENV_PENDULUM = 0, 1, 2
 DUEL_NONE, DUEL_AVERAGE, DUEL_MAX, DUEL_NAIVE = 0, 1, 2, 3
 MEM_UNIFORM, MEM_PROPORTIONAL = 0, 1
 NOISE_KIND_ROLLOUT, NOISE_KIND_TRAIN, NOISE_KIND_PRED = 0, 1, 3
@@ -71,6 +71,7 @@ class SrlxEngine(C.Structure):
         ("grid_slip_cdf", C.c_double * 16),
         ("grid_slip_action", C.c_int32 * 4),
         ("grid_move_reward", C.c_double), ("grid_goal_reward", C.c_double), ("grid_hole_reward", C.c_double),
+        ("act_tbl", C.c_double * 16),
         ("net", SrlxNet),
         ("state", _P), ("env_state", _P), ("env_step_num", _P), ("env_episode", _P), ("env_ep_reward", _P),
         ("env_needs_reset", _P), ("env_first_ep_reward", _P), ("env_last_ep_len", _P),

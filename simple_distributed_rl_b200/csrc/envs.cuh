@@ -1,6 +1,8 @@
 // envs.cuh -- closed-form environments stepped on device.  CPU twin: oracle/envs.py (bit-exact, see its header).
 //   Grid      srl/envs/grid.py:88-208,340-378 (+ EnvRun truncation srl/base/env/env_run.py:360-362)
 //   CartPole  gymnasium==1.2.0 classic_control/cartpole.py restated (third-party; parity vs gymnasium unpinned)
+//   Pendulum  gymnasium==1.2.0 classic_control/pendulum.py restated (third-party; parity vs gymnasium unpinned), driven by
+//             the reference's discretised action table (BoxSpace.create_division_tbl, srl/base/spaces/box.py:317-366)
 #pragma once
 #include "philox.cuh"
 
@@ -116,17 +118,95 @@ __device__ inline double cartpole_step(int action, double* st, bool& terminated)
   return 1.0;
 }
 
+// ---- Pendulum-v1 -------------------------------------------------------------------------------------------------
+// state (theta, theta_dot) in fp64, theta unwrapped as in gymnasium; every operation an explicitly rounded IEEE double op
+// in the order of oracle/envs.py::PendulumSpec.  angle_normalize(x) = ((x + pi) mod 2 pi) - pi is evaluated as
+// y - floor(y / 2pi) * 2pi - pi with y = x + pi; sin / cos of the normalised angle fold to [-pi/2, pi/2] and use Taylor
+// polynomials to x^23 / x^22 (error < 1e-17 there).
+__device__ inline double pend_angle_normalize(double x) {
+  const double pi = 3.141592653589793, two_pi = 6.283185307179586, inv_two_pi = 0.15915494309189535;
+  const double y = da(x, pi);
+  const double k = floor(dm(y, inv_two_pi));
+  return ds(ds(y, dm(k, two_pi)), pi);
+}
+__device__ inline void pend_sincos(double an, double& s_out, double& c_out) {  // an in [-pi, pi]
+  const double pi = 3.141592653589793, half_pi = 1.5707963267948966;
+  double r = an, csign = 1.0;
+  if (an > half_pi) { r = ds(pi, an); csign = -1.0; }
+  else if (an < -half_pi) { r = ds(-pi, an); csign = -1.0; }
+  const double z = dm(r, r);
+  double ps = -1.0 / 25852016738884976640000.0;  // -1/23!
+  ps = da(dm(ps, z), 1.0 / 51090942171709440000.0);   // 1/21!
+  ps = da(dm(ps, z), -1.0 / 121645100408832000.0);    // -1/19!
+  ps = da(dm(ps, z), 1.0 / 355687428096000.0);
+  ps = da(dm(ps, z), -1.0 / 1307674368000.0);
+  ps = da(dm(ps, z), 1.0 / 6227020800.0);
+  ps = da(dm(ps, z), -1.0 / 39916800.0);
+  ps = da(dm(ps, z), 1.0 / 362880.0);
+  ps = da(dm(ps, z), -1.0 / 5040.0);
+  ps = da(dm(ps, z), 1.0 / 120.0);
+  ps = da(dm(ps, z), -1.0 / 6.0);
+  ps = da(dm(ps, z), 1.0);
+  s_out = dm(ps, r);
+  double pc = -1.0 / 1124000727777607680000.0;        // -1/22!
+  pc = da(dm(pc, z), 1.0 / 2432902008176640000.0);     // 1/20!
+  pc = da(dm(pc, z), -1.0 / 6402373705728000.0);       // -1/18!
+  pc = da(dm(pc, z), 1.0 / 20922789888000.0);
+  pc = da(dm(pc, z), -1.0 / 87178291200.0);
+  pc = da(dm(pc, z), 1.0 / 479001600.0);
+  pc = da(dm(pc, z), -1.0 / 3628800.0);
+  pc = da(dm(pc, z), 1.0 / 40320.0);
+  pc = da(dm(pc, z), -1.0 / 720.0);
+  pc = da(dm(pc, z), 1.0 / 24.0);
+  pc = da(dm(pc, z), -1.0 / 2.0);
+  pc = da(dm(pc, z), 1.0);
+  c_out = dm(csign, pc);
+}
+__device__ inline void pendulum_reset(const srlx_engine& eng, uint32_t e, uint32_t episode, double* st) {
+  uint4 w = philox(eng.seed, STREAM_ENV_RESET, e, episode, 0);
+  // np_random.uniform(low=[-pi, -1], high=[pi, 1]): low + (high - low) * u
+  st[0] = da(-3.141592653589793, dm(6.283185307179586, u01_f64(w.x, w.y)));
+  st[1] = da(-1.0, dm(2.0, u01_f64(w.z, w.w)));
+  st[2] = 0.0;
+  st[3] = 0.0;
+}
+__device__ inline double pendulum_step(const srlx_engine& eng, int action, double* st, bool& terminated) {
+  const double dt = 0.05, max_speed = 8.0;
+  const double th = st[0], thdot = st[1];
+  const double u = eng.act_tbl[action];  // already inside [-max_torque, max_torque]
+  const double an = pend_angle_normalize(th);
+  double sn, cs;
+  pend_sincos(an, sn, cs);
+  const double costs = da(da(dm(an, an), dm(0.1, dm(thdot, thdot))), dm(0.001, dm(u, u)));
+  double newthdot = da(thdot, dm(da(dm(15.0, sn), dm(3.0, u)), dt));  // 3g/(2l) = 15, 3/(m l^2) = 3
+  newthdot = newthdot < -max_speed ? -max_speed : (newthdot > max_speed ? max_speed : newthdot);
+  st[0] = da(th, dm(newthdot, dt));
+  st[1] = newthdot;
+  terminated = false;  // Pendulum only ever ends by the 200-step TimeLimit
+  return -costs;
+}
+
 // ---- dispatch ---------------------------------------------------------------------------------------------------
 __device__ inline void env_reset(const srlx_engine& eng, uint32_t e, uint32_t episode, double* st) {
   if (eng.env_id == SRLX_ENV_GRID) grid_reset(eng, e, episode, st);
+  else if (eng.env_id == SRLX_ENV_PENDULUM) pendulum_reset(eng, e, episode, st);
   else cartpole_reset(eng, e, episode, st);
 }
 __device__ inline double env_step(const srlx_engine& eng, uint32_t e, uint64_t g, int action, double* st, bool& terminated) {
   if (eng.env_id == SRLX_ENV_GRID) return grid_step(eng, e, g, action, st, terminated);
+  if (eng.env_id == SRLX_ENV_PENDULUM) return pendulum_step(eng, action, st, terminated);
   return cartpole_step(action, st, terminated);
 }
 // observation as the RL side sees it: float32 cast (BoxSpace encode srl/base/spaces/box.py:585-598)
 __device__ inline void env_obs(const srlx_engine& eng, const double* st, float* obs) {
+  if (eng.env_id == SRLX_ENV_PENDULUM) {  // [cos(theta), sin(theta), theta_dot]
+    double sn, cs;
+    pend_sincos(pend_angle_normalize(st[0]), sn, cs);
+    obs[0] = (float)cs;
+    obs[1] = (float)sn;
+    obs[2] = (float)st[1];
+    return;
+  }
   for (int d = 0; d < eng.obs_dim; ++d) obs[d] = (float)st[d];
 }
 

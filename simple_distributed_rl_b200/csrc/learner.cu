@@ -1188,6 +1188,11 @@ int srlx::learn_generic(const srlx_engine* eng, uint32_t n_updates, uintptr_t cu
   const long long n_nodes = 2ll * eng->ring_rows * eng->n_envs - 1;
   int C = pick_cluster(eng->net, want);
   LPlan pl = make_lplan(*eng, C, max_smem, n_nodes);
+  // the exchange buffers grow with the cluster size: fall back to a narrower cluster when the widest does not fit
+  while ((long long)pl.total + 1024 > max_smem && C > 1) {
+    C = pick_cluster(eng->net, C / 2);
+    pl = make_lplan(*eng, C, max_smem, n_nodes);
+  }
   SRLX_REQUIRE((long long)pl.total + 1024 <= max_smem,
                "network / batch too large for the fused learner: needs %zu bytes of shared memory per CTA, device allows %d",
                pl.total + 1024, max_smem);

@@ -252,7 +252,8 @@ static int check_engine(const srlx_engine* eng) {
   SRLX_REQUIRE(eng->net.n_layers >= 1 && eng->net.n_layers <= SRLX_MAX_LAYERS, "n_layers %d out of range", eng->net.n_layers);
   SRLX_REQUIRE(eng->net.in_dim == eng->obs_dim, "net.in_dim != obs_dim");
   SRLX_REQUIRE(eng->ring_rows >= eng->multisteps, "ring_rows (%d) must be >= multisteps (%d)", eng->ring_rows, eng->multisteps);
-  SRLX_REQUIRE(eng->env_id == SRLX_ENV_GRID || eng->env_id == SRLX_ENV_CARTPOLE, "unknown env_id %d", eng->env_id);
+  SRLX_REQUIRE(eng->env_id == SRLX_ENV_GRID || eng->env_id == SRLX_ENV_CARTPOLE || eng->env_id == SRLX_ENV_PENDULUM,
+               "unknown env_id %d", eng->env_id);
   SRLX_REQUIRE(eng->state && eng->env_state && eng->env_step_num && eng->env_episode && eng->env_ep_reward &&
                    eng->env_needs_reset && eng->params,
                "engine buffer pointer is NULL");

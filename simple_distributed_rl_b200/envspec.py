@@ -3,6 +3,9 @@
 Grid      srl/envs/grid.py:21-30 (registration kwargs), :88-161 (field, slip table, max_episode_steps=50)
 CartPole  gymnasium==1.2.0 CartPole-v1 restated (obs Box(4,) float32, Discrete(2), TimeLimit 500);
           srl/base/env/gymnasium_wrapper.py:290-374 is the reference-side wrapper.
+Pendulum  gymnasium==1.2.0 Pendulum-v1 restated (obs Box(3,) float32, action Box(1,) in [-2, 2], TimeLimit 200); value-based
+          algorithms see the reference's discretisation of the action Box: RLConfig.action_division_num (default 10,
+          srl/base/rl/config.py:55) evenly spaced float32 values, BoxSpace.create_division_tbl (srl/base/spaces/box.py:317-366).
 """
 from dataclasses import dataclass, field
 from typing import List
@@ -39,10 +42,13 @@ class EnvSpec:
     hole_reward: float = -1.0
     obs_low: tuple = ()
     obs_high: tuple = ()
+    action_table: tuple = ()  # continuous value of each discrete action index (Pendulum)
 
     def fill(self, eng: "_lib.SrlxEngine"):
         eng.env_id, eng.obs_dim, eng.n_actions = self.env_id, self.obs_dim, self.n_actions
         eng.trunc_limit, eng.trunc_overrides_term = self.trunc_limit, self.trunc_overrides_term
+        for i, v in enumerate(self.action_table):
+            eng.act_tbl[i] = float(v)
         if self.env_id == _lib.ENV_GRID:
             f = np.array(self.field, dtype=np.int8)
             h, w = f.shape
@@ -82,4 +88,17 @@ def make_env_spec(name: str, **kw) -> EnvSpec:
     if name == "CartPole-v1":
         return EnvSpec(name, _lib.ENV_CARTPOLE, 4, 2, 500, 1, 500, reward_baseline={"episode": 10, "baseline": 0},
                        obs_low=(-4.8, -np.inf, -0.41887903, -np.inf), obs_high=(4.8, np.inf, 0.41887903, np.inf))
-    raise ValueError(f"environment {name!r} is not available on device (supported: Grid, EasyGrid, CartPole-v1)")
+    if name == "Pendulum-v1":
+        n = int(kw.get("action_division_num", 10))
+        if not 2 <= n <= 16:
+            raise ValueError("Pendulum-v1: action_division_num must be in [2, 16]")
+        return EnvSpec(name, _lib.ENV_PENDULUM, 3, n, 200, 1, 200, reward_baseline={"episode": 10, "baseline": -500},
+                       obs_low=(-1.0, -1.0, -8.0), obs_high=(1.0, 1.0, 8.0), action_table=tuple(division_table(-2.0, 2.0, n)))
+    raise ValueError(f"environment {name!r} is not available on device (supported: Grid, EasyGrid, CartPole-v1, Pendulum-v1)")
+
+
+def division_table(low: float, high: float, n: int):
+    """BoxSpace.create_division_tbl for a 1-D float32 Box (srl/base/spaces/box.py:340-365): low + diff * j in float32."""
+    lo, hi = np.float32(low), np.float32(high)
+    diff = (hi - lo) / (n - 1)
+    return [np.float32(lo + diff * j) for j in range(n)]

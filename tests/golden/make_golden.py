@@ -410,8 +410,26 @@ def gen_worker_records():
     print("worker_records:", {k: v.shape for k, v in out.items() if k.endswith("_b_a") or k.endswith("_a")})
 
 
+def gen_spaces():
+    """BoxSpace.create_division_tbl (srl/base/spaces/box.py:317-366): the discrete action set value-based algorithms see on a
+    continuous-action env (Pendulum-v1: Box(1,) in [-2, 2], RLConfig.action_division_num = 10 by default)."""
+    from srl.base.rl.config import RLConfig
+    from srl.base.spaces.box import BoxSpace
+
+    out = {}
+    for n in (2, 3, 5, 10, 16):
+        sp = BoxSpace((1,), -2.0, 2.0, np.float32)
+        sp.create_division_tbl(n)
+        out[f"pendulum_div{n}"] = np.asarray(sp.division_tbl, dtype=np.float32).reshape(-1)
+    out["default_action_division_num"] = np.array([RLConfig.__dataclass_fields__["action_division_num"].default])
+    np.savez_compressed(os.path.join(HERE, "spaces.npz"), **out)
+    print("spaces:", {k: v.tolist() for k, v in out.items() if k.endswith("10") or k.startswith("default")})
+
+
 if __name__ == "__main__":
     only = set(sys.argv[1:])  # e.g. `make_golden.py worker` regenerates only worker_records.npz
+    if not only or "spaces" in only:
+        gen_spaces()
     if not only or "worker" in only:
         gen_worker_records()
     if not only or "base" in only:

@@ -270,6 +270,12 @@ ENGINE_CASES = {
     "cartpole_rainbow_noisy_plain_m2_b24": dict(env="CartPole-v1", algo="rainbow", hidden=(96,), dueling=None, noisy=True, mem_kind=1,
                                                 multisteps=2, n_envs=36, ring_rows=9, batch_size=24, warmup_size=72,
                                                 enable_double_dqn=False),
+    # Pendulum-v1 with the reference's discretised torques: 10 actions on the generic kernel; 3 actions, D = 3 < 4 on the fast one
+    "pendulum_dqn_per_a10": dict(env="Pendulum-v1", algo="dqn", hidden=(64, 64), mem_kind=1, multisteps=1, n_envs=24, ring_rows=10,
+                                 batch_size=16, warmup_size=48, epsilon=0.3, enable_double_dqn=False),
+    "pendulum_rainbow_a3_fast": dict(env="Pendulum-v1", algo="rainbow", hidden=(64,), dueling="average", noisy=False, mem_kind=1,
+                                     multisteps=3, n_envs=32, ring_rows=8, batch_size=32, warmup_size=64, epsilon=0.2,
+                                     env_kwargs=dict(action_division_num=3)),
     "cartpole_rainbow_naive_m4": dict(env="CartPole-v1", algo="rainbow", hidden=(40,), dueling="", noisy=True, mem_kind=1,
                                       multisteps=4, n_envs=20, ring_rows=10, batch_size=12, warmup_size=40),
 }
@@ -376,7 +382,7 @@ def test_engine_lockstep(name):
             if cfg.noisy:
                 orc.tgt_sigma = tsg.copy()
     assert n_upd_total > 0
-    assert orc.episode_count > 0 or cfg.env == "CartPole-v1"
+    assert orc.episode_count > 0 or cfg.env in ("CartPole-v1", "Pendulum-v1")
 
 
 def test_engine_run_equals_stepwise():
@@ -609,3 +615,12 @@ def test_learning_cartpole_rainbow_default_config():
     kw = dict(env="CartPole-v1", algo="rainbow", hidden=(512,), dueling="average", noisy=True, mem_kind=1, multisteps=3, n_envs=1024,
               ring_rows=256, batch_size=32, warmup_size=1000, lr=1e-3, target_update_interval=1000, seed=1)
     assert _train_and_evaluate(kw, 400, 4) >= 150.0
+
+
+def test_learning_pendulum_dqn_reaches_reference_baseline():
+    """The reference's own DQN acceptance run (tests/algorithms_/base_dqn.py:38-43: Pendulum-v1, MLP (64, 64), no double DQN,
+    20 000 steps, mean evaluation reward over 10 episodes >= the env baseline -500, gymnasium_wrapper.py:327-329) on the
+    device path: 64 env copies x 320 vector steps, 10 discretised torques (RLConfig.action_division_num)."""
+    kw = dict(env="Pendulum-v1", algo="dqn", hidden=(64, 64), mem_kind=0, multisteps=1, n_envs=64, ring_rows=512, batch_size=32,
+              warmup_size=1000, epsilon=0.1, lr=1e-3, target_update_interval=1000, enable_double_dqn=False, seed=1)
+    assert _train_and_evaluate(kw, 320, 1, episodes=10) >= -500.0

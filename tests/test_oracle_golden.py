@@ -292,3 +292,43 @@ def test_grid_truncation_step_matches_reference_envrun(golden_dir):
                     seen_truncated = True
                 cur = 0
     assert seen_truncated
+
+
+def test_action_division_table_matches_reference_boxspace(golden_dir):
+    """Pendulum-v1 on the value-based path: the discrete action set is the reference's BoxSpace division table
+    (srl/base/spaces/box.py:317-366), float32 arithmetic included -- both the oracle's and the host spec's restatement."""
+    from oracle import envs as oenvs
+    from simple_distributed_rl_b200 import envspec
+
+    d = np.load(os.path.join(golden_dir, "spaces.npz"))
+    assert int(d["default_action_division_num"][0]) == 10
+    for n in (2, 3, 5, 10, 16):
+        want = d[f"pendulum_div{n}"]
+        np.testing.assert_array_equal(oenvs.division_table(-2.0, 2.0, n), want)
+        np.testing.assert_array_equal(np.array(envspec.division_table(-2.0, 2.0, n), dtype=np.float32), want)
+    assert oenvs.make_spec("Pendulum-v1").n_actions == 10
+
+
+def test_pendulum_restatement_properties():
+    """gymnasium Pendulum-v1 restated (parity vs gymnasium unpinned): observation = (cos, sin, thdot) of the state within
+    1e-6 of libm, speed clipped to 8, reward = -(angle_normalize(th)^2 + .1 thdot^2 + .001 u^2) in [-16.2736, 0]."""
+    import math
+
+    from oracle import envs as oenvs
+
+    sp = oenvs.make_spec("Pendulum-v1")
+    st = sp.reset(7, 3, 0)
+    assert -math.pi <= st[0] < math.pi and -1.0 <= st[1] < 1.0
+    for t in range(400):
+        a = (t * 7) % 10
+        th, thdot = st[0], st[1]
+        st2, r, term = sp.step(st, a)
+        u = float(sp.action_table[a])
+        an = ((th + math.pi) % (2 * math.pi)) - math.pi
+        want_r = -(an * an + 0.1 * thdot * thdot + 0.001 * u * u)
+        assert abs(r - want_r) < 1e-9 and -16.2736044 <= r <= 0.0 and term is False
+        want_thdot = min(max(thdot + (15.0 * math.sin(th) + 3.0 * u) * 0.05, -8.0), 8.0)
+        assert abs(st2[1] - want_thdot) < 1e-9 and abs(st2[0] - (th + want_thdot * 0.05)) < 1e-9
+        o = sp.obs(st2)
+        assert abs(o[0] - math.cos(st2[0])) < 1e-6 and abs(o[1] - math.sin(st2[0])) < 1e-6 and o[2] == np.float32(st2[1])
+        st = st2
