@@ -50,6 +50,8 @@ def engine_config_from_srl(env: Any, rl_config: Any, num_envs: int, seed: int = 
     env_name = env if isinstance(env, str) else _get(env, "name", _get(env, "id", None))
     env_kwargs = {} if isinstance(env, str) else dict(_get(env, "kwargs", {}) or {})
     algo = _algo_of(rl_config)
+    if env_name == "Pendulum-v1":  # continuous action Box: the value-based worker sees RLConfig.action_division_num torques
+        env_kwargs.setdefault("action_division_num", int(_get(rl_config, "action_division_num", 10)))
     # ---- things the device path does not implement: refuse loudly
     if _get(rl_config, "window_length", 1) not in (0, 1):
         raise NotImplementedError("window_length > 1 is not supported on the device path")

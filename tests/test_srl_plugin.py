@@ -68,3 +68,18 @@ def test_register_memory_uses_reference_custom_seam(srl_mod):
     register_memory(cfg)
     assert cfg.memory.name == "custom" and cfg.memory.kwargs["entry_point"] == MEMORY_ENTRY_POINT
     assert cfg.memory.kwargs["kwargs"]["alpha"] == 0.5
+
+
+def test_pendulum_takes_the_reference_action_division(srl_mod):
+    from simple_distributed_rl_b200.envspec import make_env_spec
+    from simple_distributed_rl_b200.srl_plugin import engine_config_from_srl
+
+    dqn, _ = srl_mod
+    cfg = dqn.Config(enable_double_dqn=False)
+    cfg.hidden_block.set((64, 64))
+    e = engine_config_from_srl("Pendulum-v1", cfg, num_envs=64)  # tests/algorithms_/base_dqn.py:30-43
+    assert e.env == "Pendulum-v1" and e.env_kwargs["action_division_num"] == cfg.action_division_num == 10
+    spec = make_env_spec(e.env, **e.env_kwargs)
+    assert (spec.obs_dim, spec.n_actions, spec.trunc_limit) == (3, 10, 200) and spec.reward_baseline["baseline"] == -500
+    cfg.action_division_num = 5
+    assert engine_config_from_srl("Pendulum-v1", cfg, num_envs=64).env_kwargs["action_division_num"] == 5
