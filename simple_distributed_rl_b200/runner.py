@@ -192,6 +192,21 @@ class VecRunner:
         self.state.episode_rewards_list = [[float(r)] for r in first]
         return [float(r) for r in first]
 
+    def evaluate_compare_to_baseline_single_player(self, episode: int = -1, baseline: Optional[float] = None,
+                                                   eval_kwargs: Optional[dict] = None, enable_backup_restore: bool = True) -> bool:
+        """Runner.evaluate_compare_to_baseline_single_player (runner.py:1357-1392), the reference's acceptance gate: mean
+        reward of `episode` greedy episodes >= the env's reward_baseline (Grid 0.65 over 100, Pendulum-v1 -500 over 10)."""
+        rb = self.engine.env.reward_baseline or {}
+        if episode <= 0:
+            episode = int(rb.get("episode", 0)) or 100
+        if baseline is None:
+            baseline = rb.get("baseline", None)
+        assert baseline is not None, "Please specify a 'baseline'."
+        if enable_backup_restore:  # the reference round-trips the parameters through backup()/restore() first
+            self.engine.load_state_dict(self.engine.state_dict())
+        rewards = self.evaluate(max_episodes=episode, **(eval_kwargs or {}))
+        return bool(float(np.mean(rewards)) >= float(baseline))
+
     # ---- parameters (RLParameter.call_backup / call_restore) ----------------------------------------------
     def state_dict(self):
         return self.engine.state_dict()

