@@ -596,7 +596,6 @@ def _train_and_evaluate(kw, vec_steps, train_interval, episodes=100):
     assert st.total_step >= kw["n_envs"] * vec_steps and st.train_count > 0
     mean = float(np.mean(r.evaluate(max_episodes=episodes, test_epsilon=0.0)))
     if kw["env"] in ("Grid", "Pendulum-v1"):  # envs with a reference reward_baseline: the Runner-shaped gate must agree
-        assert r.evaluate_compare_to_baseline_single_player() == (mean >= r.engine.env.reward_baseline["baseline"]) or True
         assert r.evaluate_compare_to_baseline_single_player()
     return mean
 
