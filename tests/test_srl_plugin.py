@@ -83,3 +83,26 @@ def test_pendulum_takes_the_reference_action_division(srl_mod):
     assert (spec.obs_dim, spec.n_actions, spec.trunc_limit) == (3, 10, 200) and spec.reward_baseline["baseline"] == -500
     cfg.action_division_num = 5
     assert engine_config_from_srl("Pendulum-v1", cfg, num_envs=64).env_kwargs["action_division_num"] == 5
+
+
+def test_reference_runner_runs_on_the_restated_envs(srl_mod):
+    """oracle/ref_envs.py: the reference's own loop (core_play.play) steps the CPU restatements of CartPole-v1 / Pendulum-v1
+    registered under the gymnasium ids (baseline tooling: BASELINE.md section 2b)."""
+    sys.path.insert(0, REF)
+    try:
+        import srl
+        from oracle.ref_envs import register_restated_envs
+
+        dqn, _ = srl_mod
+        register_restated_envs()
+        for env_id, n_act in (("CartPole-v1", 2), ("Pendulum-v1", 10)):
+            cfg = dqn.Config()
+            cfg.hidden_block.set((16,))
+            cfg.memory.warmup_size = 50
+            runner = srl.Runner(env_id, cfg)
+            runner.set_device("CPU")
+            st = runner.train(max_steps=150, enable_progress=False)
+            assert st.total_step == 150 and st.train_count > 0
+            assert runner.rl_config.action_space.n == n_act  # Pendulum: the reference's own 10-way division of the torque Box
+    finally:
+        sys.path.remove(REF)
