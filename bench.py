@@ -38,10 +38,23 @@ def rainbow_kwargs(n_envs, ring_rows, warmup_size, seed):
                 enable_double_dqn=True, target_update_interval=1000, lr=1e-3, discount=0.99)
 
 
+def dqn_kwargs(n_envs, ring_rows, warmup_size, seed):
+    """BASELINE configs[1]: DQN (double, no dueling / noisy / n-step), MLP[64,64], uniform replay."""
+    return dict(env="CartPole-v1", algo="dqn", hidden=(64, 64), dueling=None, noisy=False, mem_kind=0, multisteps=1,
+                n_envs=n_envs, ring_rows=ring_rows, batch_size=32, warmup_size=warmup_size, seed=seed, epsilon=0.1,
+                enable_double_dqn=True, target_update_interval=1000, lr=1e-3, discount=0.99)
+
+
+def workload_kwargs(args, **kw):
+    return (dqn_kwargs if args.workload == "dqn" else rainbow_kwargs)(**kw)
+
+
 def workload_config(args, world):
-    return {"workload": "Rainbow(double+dueling512+noisy+3step-retrace+PER) CartPole-v1 (BASELINE configs[2])",
+    name = ("DQN(double) MLP[64,64] uniform replay CartPole-v1 (BASELINE configs[1]; not the headline config)" if args.workload == "dqn"
+            else "Rainbow(double+dueling512+noisy+3step-retrace+PER) CartPole-v1 (BASELINE configs[2])")
+    return {"workload": name,
             "n_envs_per_gpu": args.envs, "replay_capacity_per_gpu": args.envs * args.ring_rows, "batch_size": 32,
-            "multisteps": 3, "train_interval": args.train_interval,
+            "multisteps": 1 if args.workload == "dqn" else 3, "train_interval": args.train_interval,
             "updates_per_step_per_gpu": args.envs // args.train_interval,
             "env_steps_per_step": args.envs * world,
             "parallelism": (f"shard{world}: env/replay/SumTree shards + learner replica per GPU, parameters averaged by one "
@@ -50,7 +63,8 @@ def workload_config(args, world):
 
 
 def algorithmic_bytes_per_update(n_params_total, batch=32, multisteps=3, depth=21):
-    """gather + weights fwd/bwd (5 passes) + Adam (7 x 4 B per parameter) + SumTree sample/update."""
+    """gather + weights fwd/bwd (5 passes) + Adam (7 x 4 B per parameter) + SumTree sample/update
+    (depth 0 = uniform replay: no tree)."""
     gather = batch * multisteps * 44
     weights = 5 * 4 * n_params_total
     adam = 7 * 4 * n_params_total
@@ -113,7 +127,7 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------------------------------------
 # CPU path (oracle port of the reference loop) -- used by cpu_baseline and by --impl reference
 # ---------------------------------------------------------------------------------------------------------------------
-def cpu_port_run(n_envs, train_interval, steps, warmup, budget_s, threads):
+def cpu_port_run(n_envs, train_interval, steps, warmup, budget_s, threads, workload="rainbow"):
     """Times `steps` steps of the sequential CPU port (oracle/engine.py) on a bounded sample of the workload:
     n_envs env copies instead of 8192, same network / algorithm / train_interval."""
     import torch
@@ -123,8 +137,8 @@ def cpu_port_run(n_envs, train_interval, steps, warmup, budget_s, threads):
 
     torch.set_num_threads(max(1, threads))
     U = max(1, n_envs // train_interval)
-    kw = rainbow_kwargs(n_envs, ring_rows=64, warmup_size=n_envs, seed=1)
-    spec = NetSpec(4, (512,), 2, "average", True, "rainbow")
+    kw = (dqn_kwargs if workload == "dqn" else rainbow_kwargs)(n_envs, ring_rows=64, warmup_size=n_envs, seed=1)
+    spec = NetSpec(4, kw["hidden"], 2, kw["dueling"], kw["noisy"], kw["algo"])
     mu, sigma = spec.init_params(0)
     orc = oeng.OracleEngine(oeng.EngineConfig(**kw), mu, sigma)
     for _ in range(3):  # prefill so the first update has M-step windows to sample
@@ -160,7 +174,7 @@ def reference_arm(args):
     import multiprocessing as mp
 
     cores = min(os.cpu_count() or 1, 64)
-    a = (args.cpu_envs, args.train_interval, args.steps, min(args.warmup, 1), 150.0, 1)
+    a = (args.cpu_envs, args.train_interval, args.steps, min(args.warmup, 1), 150.0, 1, args.workload)
     with mp.get_context("spawn").Pool(cores) as pool:
         rs = pool.map(_cpu_worker, [a] * cores)
     r = dict(env_steps_per_s=sum(x["env_steps_per_s"] for x in rs), updates_per_s=sum(x["updates_per_s"] for x in rs),
@@ -201,11 +215,11 @@ def own_arm(args):
 
     E, R, TI = args.envs, args.ring_rows, args.train_interval
     U = E // TI
-    kw = rainbow_kwargs(E, R, warmup_size=1000, seed=1 + rank)
+    kw = workload_kwargs(args, n_envs=E, ring_rows=R, warmup_size=1000, seed=1 + rank)
     runner = VecRunner(EngineConfig(**kw), device=dev)
     eng = runner.engine
     lib = eng.lib
-    P_total = eng.spec.n_params * 2  # mu + sigma
+    P_total = eng.spec.n_params * (2 if kw["noisy"] else 1)  # mu (+ sigma)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
     sync_tensors = [eng.t["params"]] + ([eng.t["params_sigma"]] if "params_sigma" in eng.t else [])
@@ -293,7 +307,8 @@ def own_arm(args):
     except Exception:
         pass
     peak_gbs, peak_src = (float(peaks["hbm_gbs"]), "measured") if "hbm_gbs" in peaks else (6650.0, "fallback")
-    bytes_per_update = algorithmic_bytes_per_update(P_total)
+    bytes_per_update = algorithmic_bytes_per_update(P_total, multisteps=kw["multisteps"],
+                                                    depth=(E * R - 1).bit_length() if kw["mem_kind"] else 0)
     kname, cluster, smem = eng.learner_info()
     chunk = 256 if kname == "learner_fast_kernel" else U  # srlx_learn issues the fast kernel in launches of <= 256 updates
     n_launch = (U + chunk - 1) // chunk
@@ -325,7 +340,7 @@ def own_arm(args):
     # ---- CPU baseline (bounded sample, rank 0, N=1 only) ---------------------------------------------------------
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        r = cpu_port_run(args.cpu_envs, TI, steps=10_000, warmup=1, budget_s=args.cpu_seconds, threads=1)
+        r = cpu_port_run(args.cpu_envs, TI, steps=10_000, warmup=1, budget_s=args.cpu_seconds, threads=1, workload=args.workload)
         cpu = {"value": r["env_steps_per_s"], "unit": UNIT, "cores": 1, "kind": "port", "sample": r["sample"],
                "trainer_updates_per_sec": r["updates_per_s"]}
 
@@ -348,6 +363,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="own", choices=["own", "reference"])
+    ap.add_argument("--workload", default="rainbow", choices=["rainbow", "dqn"],
+                    help="rainbow = BASELINE configs[2] (the headline, default); dqn = configs[1] (use --envs 4096), a side measurement")
     ap.add_argument("--envs", type=int, default=8192)
     ap.add_argument("--ring-rows", type=int, default=256)
     ap.add_argument("--train-interval", type=int, default=10,

@@ -179,6 +179,11 @@ typedef struct srlx_engine {
                                kept in step by the learner, so the sampler fetches a subtree with one coalesced load per
                                lane; srlx_tree_blk_bytes(capacity) bytes; NULL -> the sampler reads the flat tree */
   uint64_t tree_blk_bytes;
+  /* ---- linear epsilon schedule (srl/rl/schedulers/schedulers/linear.py:16-21, read per step at dqn.py:196 / rainbow.py:312 with
+   *      the worker's step_in_training, here the vector step count g): eps_phase_steps == 0 -> constant `epsilon`;
+   *      else training rollouts use g >= phase ? eps_end : epsilon - ((epsilon - eps_end) / phase) * g ---- */
+  double eps_end;
+  uint64_t eps_phase_steps;
 } srlx_engine;
 
 /* ---- library ------------------------------------------------------------------------------------------ */

@@ -46,6 +46,8 @@ class EngineConfig:
     seed: int = 0
     warmup_size: int = 16
     epsilon: float = 0.1
+    eps_end: float = 0.1  # linear schedule epsilon -> eps_end over eps_phase_steps steps (0 = constant epsilon)
+    eps_phase_steps: int = 0
     discount: float = 0.99
     lr: float = 1e-3
     adam_beta1: float = 0.9
@@ -157,6 +159,16 @@ class OracleEngine:
             a, b, change = pa, pb, pc
 
     # ---- one vector step ---------------------------------------------------------------------------------
+    def epsilon_at(self, step):
+        """Linear.update(step).to_float() (srl/rl/schedulers/schedulers/linear.py:11-21); phase 0 = Constant (constant.py)."""
+        cfg = self.cfg
+        if not cfg.eps_phase_steps:
+            return cfg.epsilon
+        if step >= cfg.eps_phase_steps:
+            return cfg.eps_end
+        step_rate = (cfg.epsilon - cfg.eps_end) / cfg.eps_phase_steps
+        return cfg.epsilon - step_rate * step
+
     def vec_step(self, training=True, q_override=None):
         cfg, env, E = self.cfg, self.env, self.E
         g = self.vec_steps
@@ -176,10 +188,11 @@ class OracleEngine:
         if q_override is not None:  # drive the policy with the device's Q so the action indices are comparable bit for bit
             q = np.asarray(q_override, dtype=np.float32)
         actions = np.zeros(E, dtype=np.int32)
+        eps = np.float32(self.epsilon_at(g) if training else cfg.epsilon)
         for e in range(E):
             w = philox.words(cfg.seed, philox.STREAM_POLICY, e, g & 0xFFFFFFFF, g >> 32)
             u = philox.u01_f32(w[0])
-            if (not cfg.noisy) and (u < np.float32(cfg.epsilon)):
+            if (not cfg.noisy) and (u < eps):
                 a = (int(w[1]) * self.A) >> 32
             else:
                 a = int(np.argmax(q[e]))

@@ -83,6 +83,7 @@ class SrlxEngine(C.Structure):
         ("dbg_q_sa", _P), ("dbg_grads", _P), ("dbg_windows", _P), ("dbg_clock", _P),
         ("noise_scratch", _P), ("noise_scratch_bytes", C.c_uint64),
         ("tree_blk", _P), ("tree_blk_bytes", C.c_uint64),
+        ("eps_end", C.c_double), ("eps_phase_steps", C.c_uint64),
     ]
 
 

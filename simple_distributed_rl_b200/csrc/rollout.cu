@@ -45,6 +45,11 @@ rollout_kernel(const __grid_constant__ srlx_engine eng, const int envs_per_cta, 
   const uint64_t g = eng.state->vec_steps;
   const int row = (int)(g % (uint64_t)R);
   const bool noisy = net.noisy != 0;
+  // Linear.update(step_in_training).to_float() (schedulers/linear.py:16-21); evaluation passes test_epsilon in eng.epsilon
+  double eps_d = eng.epsilon;
+  if (training && eng.eps_phase_steps)
+    eps_d = g >= eng.eps_phase_steps ? eng.eps_end : eng.epsilon - ((eng.epsilon - eng.eps_end) / (double)eng.eps_phase_steps) * (double)g;
+  const float eps = (float)eps_d;
 
   if (tid == 0) { s_episodes = 0; s_eplen = 0; s_epreward = 0.0; }
   zero_floats(weff, pl.weff_floats);
@@ -80,7 +85,7 @@ rollout_kernel(const __grid_constant__ srlx_engine eng, const int envs_per_cta, 
       const float* qe = q + tid * A;
       const uint4 w = philox(eng.seed, STREAM_POLICY, (uint32_t)e, (uint32_t)g, (uint32_t)(g >> 32));
       int action;
-      if (!noisy && u01_f32(w.x) < (float)eng.epsilon) {
+      if (!noisy && u01_f32(w.x) < eps) {
         action = (int)u_below(w.y, (uint32_t)A);  // random.choice over the valid actions (dqn.py:200-202)
       } else {
         action = 0;

@@ -42,6 +42,8 @@ class EngineConfig:
     seed: int = 0
     warmup_size: int = 1000
     epsilon: float = 0.1
+    eps_end: float = 0.1  # linear schedule epsilon -> eps_end over eps_phase_steps vector steps (0 = constant epsilon)
+    eps_phase_steps: int = 0
     discount: float = 0.99
     lr: float = 1e-3
     adam_beta1: float = 0.9
@@ -139,6 +141,7 @@ class DeviceEngine:
         for k in ("epsilon", "discount", "lr", "adam_beta1", "adam_beta2", "adam_eps", "retrace_h", "per_alpha", "per_beta_initial",
                   "per_beta_steps", "per_epsilon", "reward_shift", "reward_scale", "huber_delta"):
             setattr(c, k, float(getattr(cfg, k)))
+        c.eps_end, c.eps_phase_steps = float(cfg.eps_end), int(cfg.eps_phase_steps)
         c.net = self.spec.to_c()
         if "noise_scratch" in self.t:
             c.noise_scratch_bytes = self.t["noise_scratch"].numel() * 4

@@ -57,10 +57,9 @@ def engine_config_from_srl(env: Any, rl_config: Any, num_envs: int, seed: int = 
         raise NotImplementedError("window_length > 1 is not supported on the device path")
     if _get(rl_config, "frameskip", 0) not in (0, None):
         raise NotImplementedError("frameskip is not supported on the device path")
-    for sched in ("epsilon_scheduler", "lr_scheduler"):
-        s = _get(rl_config, sched)
-        if s is not None and (getattr(s, "schedulers", None) or getattr(s, "schedule_type", "") not in ("", None)):
-            raise NotImplementedError(f"{sched} with phases is not supported on the device path (constant rates only)")
+    eps_sched = _schedule_of(rl_config, "epsilon_scheduler", float(_get(rl_config, "epsilon", 0.1)), allow_linear=True)
+    if getattr(_get(rl_config, "lr_scheduler"), "schedule_type", "") not in ("", None):  # LRSchedulerConfig (rl/schedulers/lr_scheduler.py)
+        raise NotImplementedError("lr_scheduler: only the constant learning rate is supported on the device path")
     mem = rl_config.memory
     if _get(mem, "enable_demo_memory", False):
         raise NotImplementedError("demo memory is not supported on the device path")
@@ -99,10 +98,29 @@ def engine_config_from_srl(env: Any, rl_config: Any, num_envs: int, seed: int = 
         mem_kind=mem_kind, algo=algo, enable_double_dqn=bool(rl_config.enable_double_dqn),
         enable_rescale=bool(rl_config.enable_rescale), enable_reward_clip=bool(rl_config.enable_reward_clip),
         target_update_interval=int(rl_config.target_model_update_interval), seed=int(seed),
-        warmup_size=int(mem.warmup_size), epsilon=float(rl_config.epsilon), discount=float(rl_config.discount),
+        warmup_size=int(mem.warmup_size), epsilon=eps_sched[0], eps_end=eps_sched[1], eps_phase_steps=eps_sched[2], discount=float(rl_config.discount),
         lr=float(rl_config.lr), retrace_h=float(_get(rl_config, "retrace_h", 1.0)),
         reward_shift=float(_get(rl_config, "reward_shift", 0.0) or 0.0), reward_scale=float(_get(rl_config, "reward_scale", 1.0) or 1.0),
         hidden=hidden, dueling=dueling, noisy=noisy, env_kwargs=env_kwargs, **per)
+
+
+def _schedule_of(rl_config: Any, field: str, val: float, allow_linear: bool = True):
+    """SchedulerConfig.create(val) (srl/rl/schedulers/scheduler.py:232-246) for what the device implements: no phases or a
+    default scheduler -> Constant(val); one constant phase -> its rate; one linear phase -> (start, end, phase_steps)."""
+    s = _get(rl_config, field)
+    phases = list(getattr(s, "schedulers", None) or []) if s is not None else []
+    if not phases or getattr(s, "default_scheduler", False):
+        return (val, val, 0)
+    if len(phases) == 1 and phases[0].get("name") == "constant":
+        r = float(phases[0]["rate"])
+        return (r, r, 0)
+    if allow_linear and len(phases) == 1 and phases[0].get("name") == "linear":
+        ph = phases[0]
+        if int(ph["phase_steps"]) <= 0:
+            raise ValueError(f"{field}: linear phase_steps must be > 0")
+        return (float(ph["start_rate"]), float(ph["end_rate"]), int(ph["phase_steps"]))
+    raise NotImplementedError(f"{field}: only a constant rate" + (" or one linear phase" if allow_linear else "")
+                              + " is supported on the device path")
 
 
 class DeviceRunner(VecRunner):

@@ -276,6 +276,9 @@ ENGINE_CASES = {
     "pendulum_rainbow_a3_fast": dict(env="Pendulum-v1", algo="rainbow", hidden=(64,), dueling="average", noisy=False, mem_kind=1,
                                      multisteps=3, n_envs=32, ring_rows=8, batch_size=32, warmup_size=64, epsilon=0.2,
                                      env_kwargs=dict(action_division_num=3)),
+    # linear epsilon schedule (DQN/Rainbow .setup_from_atari style: 1.0 -> 0.1), phase ends inside the run
+    "cartpole_dqn_linear_epsilon": dict(env="CartPole-v1", algo="dqn", hidden=(32,), mem_kind=0, multisteps=1, n_envs=48, ring_rows=8,
+                                        batch_size=16, warmup_size=48, epsilon=1.0, eps_end=0.1, eps_phase_steps=12),
     "cartpole_rainbow_naive_m4": dict(env="CartPole-v1", algo="rainbow", hidden=(40,), dueling="", noisy=True, mem_kind=1,
                                       multisteps=4, n_envs=20, ring_rows=10, batch_size=12, warmup_size=40),
 }

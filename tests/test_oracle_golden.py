@@ -332,3 +332,27 @@ def test_pendulum_restatement_properties():
         o = sp.obs(st2)
         assert abs(o[0] - math.cos(st2[0])) < 1e-6 and abs(o[1] - math.sin(st2[0])) < 1e-6 and o[2] == np.float32(st2[1])
         st = st2
+
+
+def test_epsilon_schedule_is_the_reference_linear_phase():
+    """oracle.engine.epsilon_at restates Linear.update(step).to_float() (srl/rl/schedulers/schedulers/linear.py:11-21):
+    start - ((start - end) / phase) * step below the phase, end_rate from `phase` on, and it only applies to training steps.
+    (tests/test_srl_plugin.py compares it with the imported reference class value for value where the reference is present.)"""
+    from oracle import engine as oeng
+    from oracle import nets as onets
+
+    cfg = oeng.EngineConfig(env="Grid", algo="dqn", hidden=(8,), mem_kind=0, multisteps=1, n_envs=64, ring_rows=4, batch_size=4,
+                            warmup_size=8, epsilon=1.0, eps_end=0.0, eps_phase_steps=4)
+    spec = onets.NetSpec(2, (8,), 4, None, False)
+    rng = np.random.default_rng(0)
+    mu = rng.normal(size=spec.n_params).astype(np.float32)
+    orc = oeng.OracleEngine(cfg, mu, None)
+    assert [orc.epsilon_at(s) for s in (0, 1, 2, 3, 4, 9)] == [1.0, 0.75, 0.5, 0.25, 0.0, 0.0]
+    greedy = []
+    for s in range(6):
+        res = orc.vec_step()
+        greedy.append(float(np.mean(res["actions"] == np.argmax(res["q"], axis=1))))
+    assert greedy[4] == 1.0 and greedy[5] == 1.0  # epsilon 0 from step `phase` on: every action is the argmax
+    assert greedy[0] < 0.6  # epsilon 1 at step 0: uniformly random over 4 actions (argmax hit ~ 1/4)
+    c2 = oeng.EngineConfig(**{**cfg.__dict__, "eps_phase_steps": 0, "epsilon": 0.3})
+    assert oeng.OracleEngine(c2, mu, None).epsilon_at(123) == 0.3

@@ -54,9 +54,42 @@ def test_dqn_config_maps_and_unsupported_raises(srl_mod):
     with pytest.raises(NotImplementedError):
         engine_config_from_srl("Grid", cfg, num_envs=64)
     cfg2 = rainbow.Config()
-    cfg2.epsilon_scheduler.set_linear(1.0, 0.1, 1000)
+    cfg2.epsilon_scheduler.add_linear(1.0, 0.1, 1000).add_linear(0.1, 0.01, 1000)  # ListScheduler: not on the device
     with pytest.raises(NotImplementedError):
         engine_config_from_srl("Grid", cfg2, num_envs=64)
+    cfg3 = dqn.Config()
+    cfg3.lr_scheduler.set_step(1000, 0.5)
+    with pytest.raises(NotImplementedError):
+        engine_config_from_srl("Grid", cfg3, num_envs=64)
+
+
+def test_epsilon_scheduler_maps_and_oracle_follows_reference_linear(srl_mod):
+    """SchedulerConfig.create(config.epsilon) (scheduler.py:232-246): no phases -> Constant(epsilon); one constant -> its rate;
+    one linear phase -> Linear (schedulers/linear.py), which the oracle's epsilon_at restates value for value."""
+    from oracle import engine as oeng
+    from simple_distributed_rl_b200.srl_plugin import engine_config_from_srl
+
+    dqn, rainbow = srl_mod
+    cfg = dqn.Config(epsilon=0.07)
+    e = engine_config_from_srl("Grid", cfg, num_envs=8)
+    assert (e.epsilon, e.eps_end, e.eps_phase_steps) == (0.07, 0.07, 0)
+    cfg.epsilon_scheduler.set(0.3)
+    e = engine_config_from_srl("Grid", cfg, num_envs=8)
+    assert (e.epsilon, e.eps_phase_steps) == (0.3, 0)
+    for c in (dqn.Config(), rainbow.Config()):
+        c.epsilon_scheduler.set_linear(0.9, 0.05, 37)
+        e = engine_config_from_srl("Grid", c, num_envs=8)
+        assert (e.epsilon, e.eps_end, e.eps_phase_steps) == (0.9, 0.05, 37)
+        sch = c.epsilon_scheduler.create(c.epsilon)
+        o = oeng.OracleEngine.__new__(oeng.OracleEngine)
+        o.cfg = oeng.EngineConfig(env="Grid", epsilon=e.epsilon, eps_end=e.eps_end, eps_phase_steps=e.eps_phase_steps)
+        for step in list(range(0, 45)) + [1000]:
+            assert o.epsilon_at(step) == sch.update(step).to_float()
+    at = dqn.Config()
+    at.set_atari_config()  # dqn.py:89-102 (the image input block is ignored: the env here is a vector env)
+    e = engine_config_from_srl("Grid", at, num_envs=8)
+    assert (e.epsilon, e.eps_end, e.eps_phase_steps) == (1.0, 0.1, 1_000_000)
+    assert (e.hidden, e.enable_reward_clip, e.enable_double_dqn, e.target_update_interval) == ((512,), True, False, 10000)
 
 
 def test_register_memory_uses_reference_custom_seam(srl_mod):
