@@ -41,8 +41,9 @@ __global__ void noise_fill_kernel(uint64_t seed, uint32_t kind, uint64_t call_id
 }
 
 // ---- standalone tree kernels (one thread block each; batch <= 1024) ------------------------------------------------
-constexpr int kTreeThreads = 512;
+constexpr int kTreeThreads = 1024;  // sampler: one warp walks one sample, 32 samples in flight
 constexpr int kTreeMaxBatch = 1024;
+constexpr int kTreeAddChunk = 64;   // items per exact-order pass of a bulk add (the leader search is quadratic in the pass size)
 
 __global__ void tree_clear_kernel(double* tree, uint64_t n_nodes, srlx_state* meta) {
   const size_t i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
@@ -57,13 +58,14 @@ __global__ void tree_clear_kernel(double* tree, uint64_t n_nodes, srlx_state* me
 __global__ void __launch_bounds__(kTreeThreads)
 tree_add_kernel(double* tree, uint64_t capacity, srlx_state* meta, const double* priorities, uint64_t n, double alpha,
                 double epsilon, int restore_skip) {
-  __shared__ int64_t s_idx[kTreeMaxBatch];
-  __shared__ double s_pri[kTreeMaxBatch];
-  __shared__ double s_chg[kTreeMaxBatch];
+  __shared__ int64_t s_idx[kTreeAddChunk];
+  __shared__ double s_pri[kTreeAddChunk];
+  __shared__ double s_chg[kTreeAddChunk];
+  __shared__ int s_dep[kTreeAddChunk + 1];
   const uint64_t write = meta->vec_steps;
   const double maxp = meta->max_priority;
-  for (uint64_t base = 0; base < n; base += kTreeMaxBatch) {
-    const int m = (int)((n - base < (uint64_t)kTreeMaxBatch) ? (n - base) : kTreeMaxBatch);
+  for (uint64_t base = 0; base < n; base += kTreeAddChunk) {
+    const int m = (int)((n - base < (uint64_t)kTreeAddChunk) ? (n - base) : kTreeAddChunk);
     for (int i = threadIdx.x; i < m; i += blockDim.x) {
       s_idx[i] = (int64_t)((write + base + i) % capacity) + (int64_t)capacity - 1;
       double p = maxp;
@@ -74,7 +76,7 @@ tree_add_kernel(double* tree, uint64_t capacity, srlx_state* meta, const double*
       s_pri[i] = p;
     }
     __syncthreads();
-    tree_update_batch(tree, s_idx, s_pri, s_chg, m);
+    tree_update_batch(tree, s_idx, s_pri, s_chg, s_dep, m);
   }
   if (threadIdx.x == 0) {
     meta->vec_steps = (write + n) % capacity;
@@ -114,12 +116,13 @@ tree_update_kernel(double* tree, srlx_state* meta, const int64_t* idx, const flo
   __shared__ int64_t s_idx[kTreeMaxBatch];
   __shared__ double s_pri[kTreeMaxBatch];
   __shared__ double s_chg[kTreeMaxBatch];
+  __shared__ int s_dep[kTreeMaxBatch + 1];
   for (int i = threadIdx.x; i < (int)n; i += blockDim.x) {
     s_idx[i] = idx[i];
     s_pri[i] = pow(fabs((double)priorities[i]) + epsilon, alpha);
   }
   __syncthreads();
-  tree_update_batch(tree, s_idx, s_pri, s_chg, (int)n);
+  tree_update_batch(tree, s_idx, s_pri, s_chg, s_dep, (int)n);
   if (threadIdx.x == 0) {
     double mp = meta->max_priority;
     for (int i = 0; i < (int)n; ++i) mp = (mp < s_pri[i]) ? s_pri[i] : mp;

@@ -1683,16 +1683,33 @@ static int fast_choose(const srlx_engine* eng, int* C_out, int* lev_out, size_t*
   return 0;
 }
 
+namespace srlx {
+int small_choose(const srlx_engine* eng, size_t* smem_out);                             // learner_small.cu
+int learn_small(const srlx_engine* eng, uint32_t n_updates, uintptr_t cuda_stream);
+}  // namespace srlx
+
+// 2 when the single-block kernel (learner_small.cu: uniform replay, no NoisyNet, everything in one SM) is the one to run
+static int small_pick(const srlx_engine* eng, size_t* smem_out) {
+  const char* force = getenv("SRLX_LEARNER");
+  if (force && force[0] == 'g') return 0;
+  return srlx::small_choose(eng, smem_out) == 1 ? 2 : 0;
+}
+
 // Which kernel srlx_learn will run for this engine: 1 = learner_fast_kernel (single hidden layer, <= 4 observation floats,
-// <= 4 outputs, batch <= 32), 0 = the generic learner_kernel; negative = error.
+// <= 4 outputs, batch <= 32), 2 = learner_small_kernel (uniform replay, plain weights, one thread block), 0 = the generic
+// learner_kernel; negative = error.
 extern "C" int srlx_learner_info(const srlx_engine* eng, int* cluster_size, size_t* smem_bytes) {
   using namespace srlx;
   SRLX_REQUIRE(eng != nullptr, "srlx_learner_info: eng is NULL");
   int C = 0, lev = 0;
   size_t sm = 0;
-  const int rc = fast_choose(eng, &C, &lev, &sm);
-  if (cluster_size) *cluster_size = rc == 1 ? C : 0;
-  if (smem_bytes) *smem_bytes = rc == 1 ? sm : 0;
+  int rc = fast_choose(eng, &C, &lev, &sm);
+  if (rc == 0) {
+    rc = small_pick(eng, &sm);
+    C = rc == 2 ? 1 : 0;
+  }
+  if (cluster_size) *cluster_size = rc >= 1 ? C : 0;
+  if (smem_bytes) *smem_bytes = rc >= 1 ? sm : 0;
   return rc;
 }
 
@@ -1715,5 +1732,6 @@ extern "C" int srlx_learn(const srlx_engine* eng, uint32_t n_updates, uintptr_t 
   const int rc = fast_choose(eng, &C, &lev, &smem_bytes);
   if (rc < 0) return rc;
   if (rc == 1) return learn_fast(eng, n_updates, cuda_stream, C, lev);
+  if (small_pick(eng, &smem_bytes) == 2) return learn_small(eng, n_updates, cuda_stream);
   return learn_generic(eng, n_updates, cuda_stream);
 }

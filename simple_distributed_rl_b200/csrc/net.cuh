@@ -96,51 +96,59 @@ __device__ inline void zero_floats(float* p, int n) {
 
 // Hidden layer: Y[r][u] = relu(sum_k X[r][k] W[u][k] + b[u]), r < R (<= kRowTile), u < U.
 // Warp tile = 4 rows x 64 units (lane -> units lane, lane+32); X rows are warp-broadcast float4 loads, W rows are
-// conflict-free float4 loads (padded_ld) -> 32 FMA per 6 shared loads.
+// conflict-free float4 loads (padded_ld) -> 32 FMA per 6 shared loads.  dense_relu_task is one such warp tile
+// (row tile rt, unit tile ut); dense_relu_fwd spreads the tiles of one layer over the warps of the block.
+__device__ __forceinline__ void dense_relu_task(const float* __restrict__ X, int ldx, int R, int K, const float* __restrict__ W,
+                                                int ldw, const float* __restrict__ b, int U, float* __restrict__ Y, int ldy,
+                                                int rt, int ut) {
+  const int lane = threadIdx.x & 31;
+  const int K4 = round_up(K, 4);
+  const int r0 = rt * 4;
+  const int u0 = ut * 64 + lane, u1 = u0 + 32;
+  const bool v0 = u0 < U, v1 = u1 < U;
+  const float* w0p = W + (v0 ? u0 : 0) * ldw;
+  const float* w1p = W + (v1 ? u1 : 0) * ldw;
+  const float b0 = v0 ? b[u0] : 0.f, b1 = v1 ? b[u1] : 0.f;
+  float acc0[4], acc1[4];
+  const float* xr[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    acc0[i] = b0;
+    acc1[i] = b1;
+    xr[i] = X + min(r0 + i, R - 1) * ldx;
+  }
+  for (int k = 0; k < K4; k += 4) {
+    const float4 wa = *reinterpret_cast<const float4*>(w0p + k);
+    const float4 wb = *reinterpret_cast<const float4*>(w1p + k);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float4 x = *reinterpret_cast<const float4*>(xr[i] + k);
+      acc0[i] = fmaf(x.x, wa.x, acc0[i]);
+      acc0[i] = fmaf(x.y, wa.y, acc0[i]);
+      acc0[i] = fmaf(x.z, wa.z, acc0[i]);
+      acc0[i] = fmaf(x.w, wa.w, acc0[i]);
+      acc1[i] = fmaf(x.x, wb.x, acc1[i]);
+      acc1[i] = fmaf(x.y, wb.y, acc1[i]);
+      acc1[i] = fmaf(x.z, wb.z, acc1[i]);
+      acc1[i] = fmaf(x.w, wb.w, acc1[i]);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    if (r0 + i < R) {
+      if (v0) Y[(r0 + i) * ldy + u0] = fmaxf(acc0[i], 0.f);
+      if (v1) Y[(r0 + i) * ldy + u1] = fmaxf(acc1[i], 0.f);
+    }
+  }
+}
+
 __device__ inline void dense_relu_fwd(const float* __restrict__ X, int ldx, int R, int K, const float* __restrict__ W,
                                       int ldw, const float* __restrict__ b, int U, float* __restrict__ Y, int ldy) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  const int warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   const int n_ut = (U + 63) >> 6, n_rt = (R + 3) >> 2;
-  const int K4 = round_up(K, 4);
   for (int t = warp; t < n_ut * n_rt; t += nwarps) {
     const int rt = t / n_ut, ut = t - rt * n_ut;
-    const int r0 = rt * 4;
-    const int u0 = ut * 64 + lane, u1 = u0 + 32;
-    const bool v0 = u0 < U, v1 = u1 < U;
-    const float* w0p = W + (v0 ? u0 : 0) * ldw;
-    const float* w1p = W + (v1 ? u1 : 0) * ldw;
-    const float b0 = v0 ? b[u0] : 0.f, b1 = v1 ? b[u1] : 0.f;
-    float acc0[4], acc1[4];
-    const float* xr[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      acc0[i] = b0;
-      acc1[i] = b1;
-      xr[i] = X + min(r0 + i, R - 1) * ldx;
-    }
-    for (int k = 0; k < K4; k += 4) {
-      const float4 wa = *reinterpret_cast<const float4*>(w0p + k);
-      const float4 wb = *reinterpret_cast<const float4*>(w1p + k);
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float4 x = *reinterpret_cast<const float4*>(xr[i] + k);
-        acc0[i] = fmaf(x.x, wa.x, acc0[i]);
-        acc0[i] = fmaf(x.y, wa.y, acc0[i]);
-        acc0[i] = fmaf(x.z, wa.z, acc0[i]);
-        acc0[i] = fmaf(x.w, wa.w, acc0[i]);
-        acc1[i] = fmaf(x.x, wb.x, acc1[i]);
-        acc1[i] = fmaf(x.y, wb.y, acc1[i]);
-        acc1[i] = fmaf(x.z, wb.z, acc1[i]);
-        acc1[i] = fmaf(x.w, wb.w, acc1[i]);
-      }
-    }
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      if (r0 + i < R) {
-        if (v0) Y[(r0 + i) * ldy + u0] = fmaxf(acc0[i], 0.f);
-        if (v1) Y[(r0 + i) * ldy + u1] = fmaxf(acc1[i], 0.f);
-      }
-    }
+    dense_relu_task(X, ldx, R, K, W, ldw, b, U, Y, ldy, rt, ut);
   }
 }
 

@@ -74,10 +74,13 @@ __device__ inline bool tree_is_ancestor(int64_t node, int64_t x) {
 //   idx[i]   tree index of item i (leaf + capacity - 1)
 //   pri[i]   final priority (already (|td|+eps)^alpha)
 //   change[] scratch (n doubles, shared memory)
+//   dep[]    scratch (n ints, shared memory): depth of idx[i]; dep[n] receives the deepest one
 // Requires blockDim-wide participation; ends with __syncthreads().
 __device__ inline void tree_update_batch(double* __restrict__ tree, const int64_t* idx, const double* pri, double* change,
-                                         int n) {
+                                         int* dep, int n) {
   const int tid = threadIdx.x, nt = blockDim.x;
+  if (tid == 0) dep[n] = 0;
+  __syncthreads();
   // 1) per-item change, in item order for duplicate leaves
   for (int i = tid; i < n; i += nt) {
     const int64_t li = idx[i];
@@ -87,6 +90,9 @@ __device__ inline void tree_update_batch(double* __restrict__ tree, const int64_
       if (idx[j] == li) { prev = pri[j]; found = true; break; }
     if (!found) prev = __ldcg(tree + li);
     change[i] = pri[i] - prev;
+    const int d = 63 - __clzll((long long)(li + 1));
+    dep[i] = d;
+    atomicMax(&dep[n], d);
   }
   __syncthreads();
   // 2) leaves: the last item touching a leaf wins
@@ -97,22 +103,27 @@ __device__ inline void tree_update_batch(double* __restrict__ tree, const int64_
       if (idx[j] == li) { last = false; break; }
     if (last) __stcg(tree + li, pri[i]);
   }
-  // 3) ancestors: work item = (item i, level l); leader applies all changes to that node in item order.
-  //    (leaves of a non-power-of-two tree sit at two depths, so "same node" is tested by ancestry, not by level.)
-  const int max_levels = 48;
-  for (int w = tid; w < n * max_levels; w += nt) {
-    const int i = w / max_levels, l = w % max_levels + 1;
-    const int64_t ip1 = idx[i] + 1;
-    if ((ip1 >> l) == 0) continue;  // above the root
-    const int64_t node = (ip1 >> l) - 1;
+  // 3) ancestors: work item = (level l above the leaf, item i), consecutive threads on the same level; the leader applies
+  //    all changes to its node in item order.  Leaves of a non-power-of-two tree sit at two depths, so "same node" is
+  //    tested through the depths: x lies below `node` (depth dn) iff (x+1) >> (depth(x) - dn) == node + 1.
+  const int levels = dep[n];
+  for (int w = tid; w < n * levels; w += nt) {
+    const int l = w / n + 1, i = w - (l - 1) * n;
+    const int dn = dep[i] - l;
+    if (dn < 0) continue;  // above the root
+    const int64_t node1 = (idx[i] + 1) >> l;
     bool leader = true;
-    for (int j = 0; j < i; ++j)
-      if (tree_is_ancestor(node, idx[j])) { leader = false; break; }
+    for (int j = 0; j < i; ++j) {
+      const int lj = dep[j] - dn;
+      if (lj >= 1 && ((idx[j] + 1) >> lj) == node1) { leader = false; break; }
+    }
     if (!leader) continue;
-    double v = __ldcg(tree + node);
-    for (int j = i; j < n; ++j)
-      if (tree_is_ancestor(node, idx[j])) v += change[j];
-    __stcg(tree + node, v);
+    double v = __ldcg(tree + node1 - 1) + change[i];
+    for (int j = i + 1; j < n; ++j) {
+      const int lj = dep[j] - dn;
+      if (lj >= 1 && ((idx[j] + 1) >> lj) == node1) v += change[j];
+    }
+    __stcg(tree + node1 - 1, v);
   }
   __syncthreads();
 }

@@ -179,7 +179,7 @@ class DeviceEngine:
             rc = self.lib.srlx_learner_info(C.byref(self.c), C.byref(cs), C.byref(sm))
         if rc < 0:
             _lib.check(rc)
-        return ("learner_fast_kernel" if rc == 1 else "learner_kernel", cs.value, sm.value)
+        return ({1: "learner_fast_kernel", 2: "learner_small_kernel"}.get(rc, "learner_kernel"), cs.value, sm.value)
 
     def run(self, n_steps, updates_per_step, training=True):
         """n_steps x (one vector step of all E envs + updates_per_step trainer updates), no host sync in between."""
@@ -234,6 +234,46 @@ class DeviceEngine:
     def load_state_dict(self, sd, also_target=True):
         mu, sigma = self.spec.from_state_dict(sd)
         self.set_params(mu, sigma, also_target=also_target)
+
+    # ---- replay memory <-> reference backup format (checkpoint.py) ----------------------------------------
+    def ring_view(self):
+        """Host copy of the ring (+ SumTree leaves) as a checkpoint.RingView."""
+        from . import checkpoint
+
+        st = self.read_state()
+        v = checkpoint.RingView(self.E, self.R, self.M, self.A, self.D, vec_steps=int(st.vec_steps))
+        v.obs[:] = self.t["ring_obs"].cpu().numpy().reshape(-1, self.D)
+        v.next_obs[:] = self.t["ring_next_obs"].cpu().numpy().reshape(-1, self.D)
+        v.action[:] = self.t["ring_action"].cpu().numpy().reshape(-1)
+        v.reward[:] = self.t["ring_reward"].cpu().numpy().reshape(-1)
+        v.term[:] = self.t["ring_term"].cpu().numpy().reshape(-1)
+        v.done[:] = self.t["ring_done"].cpu().numpy().reshape(-1)
+        if self.per:
+            cap = self.E * self.R
+            v.leaf_priority = self.t["tree"][cap - 1:].cpu().numpy().astype(np.float64)
+            v.max_priority = float(st.max_priority)
+        return v
+
+    def load_ring(self, v):
+        """Replace the replay contents with a checkpoint.RingView (same E, R, M); counters follow the reference's
+        restore: memory length = the restored items, the vector step counter moves to the restored row count."""
+        from . import checkpoint
+
+        if (v.E, v.R, v.M, v.D) != (self.E, self.R, self.M, self.D):
+            raise ValueError("load_ring: ring geometry differs from the engine's")
+        for name, arr in (("ring_obs", v.obs), ("ring_next_obs", v.next_obs), ("ring_action", v.action), ("ring_reward", v.reward),
+                          ("ring_term", v.term), ("ring_done", v.done)):
+            t = self.t[name]
+            t.copy_(torch.as_tensor(np.ascontiguousarray(arr)).reshape(t.shape).to(t.dtype))
+        st = self.read_state()
+        g_lo, n_g = v.valid_rows()
+        st.vec_steps, st.total_step, st.mem_size = v.vec_steps, v.vec_steps * self.E, n_g * self.E
+        if self.per:
+            leaves = v.leaf_priority if v.leaf_priority is not None else np.zeros(self.E * self.R)
+            self.t["tree"].copy_(torch.as_tensor(checkpoint.build_sum_tree(leaves, self.E * self.R)))
+            st.max_priority = float(v.max_priority)
+        self.write_state(st)
+        self.t["env_needs_reset"].fill_(1)  # the env copies start fresh episodes after a restore
 
     def hbm_bytes(self):
         return sum(t.numel() * t.element_size() for t in self.t.values())

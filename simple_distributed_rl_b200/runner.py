@@ -213,3 +213,42 @@ class VecRunner:
 
     def load_state_dict(self, sd):
         self.engine.load_state_dict(sd)
+
+    # ---- files the reference reads and writes (RunnerBase.save_parameter / load_parameter / save_memory / load_memory,
+    #      srl/runner/runner_base.py:141-165; formats in checkpoint.py) ------------------------------------------
+    def save_parameter(self, path: str, compress: bool = True) -> None:
+        from . import checkpoint
+
+        mu, sigma = self.engine.get_params()
+        checkpoint.save_file(path, checkpoint.parameter_backup(self.engine.spec, mu, sigma), compress)
+
+    def load_parameter(self, path: str) -> None:
+        from . import checkpoint
+
+        mu, sigma = checkpoint.parameter_restore(self.engine.spec, checkpoint.load_file(path))
+        self.engine.set_params(mu, sigma, also_target=True)  # call_restore loads q_online and q_target (model_torch.py:47-49)
+
+    def memory_backup(self, item_compress: bool = False) -> list:
+        from . import checkpoint
+
+        eng = self.engine
+        seed, A = int(eng.cfg.seed) & 0xFFFFFFFFFFFFFFFF, eng.A
+        return checkpoint.memory_backup(eng.ring_view(), bool(eng.per), compress=item_compress,
+                                        pad_action=lambda e, g: checkpoint.philox_pad_action(seed, e, g, A))
+
+    def memory_restore(self, data: list) -> None:
+        from . import checkpoint
+
+        eng = self.engine
+        eng.load_ring(checkpoint.memory_restore(data, eng.E, eng.R, eng.M, eng.A, eng.D, bool(eng.per)))
+
+    def save_memory(self, path: str, compress: bool = True, item_compress: bool = False) -> None:
+        """item_compress = the reference's memory.compress (items stored as zlib(pickle(item)), default True there)."""
+        from . import checkpoint
+
+        checkpoint.save_file(path, self.memory_backup(item_compress), compress)
+
+    def load_memory(self, path: str) -> None:
+        from . import checkpoint
+
+        self.memory_restore(checkpoint.load_file(path))

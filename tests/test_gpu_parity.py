@@ -279,6 +279,14 @@ ENGINE_CASES = {
     # linear epsilon schedule (DQN/Rainbow .setup_from_atari style: 1.0 -> 0.1), phase ends inside the run
     "cartpole_dqn_linear_epsilon": dict(env="CartPole-v1", algo="dqn", hidden=(32,), mem_kind=0, multisteps=1, n_envs=48, ring_rows=8,
                                         batch_size=16, warmup_size=48, epsilon=1.0, eps_end=0.1, eps_phase_steps=12),
+    # uniform replay + plain weights + more than one hidden layer: learner_small_kernel (one thread block, learner_small.cu)
+    "cartpole_dqn_uniform_64x64": dict(env="CartPole-v1", algo="dqn", hidden=(64, 64), mem_kind=0, multisteps=1, n_envs=64,
+                                       ring_rows=8, batch_size=32, warmup_size=64, epsilon=0.2),  # BASELINE configs[1] shape
+    "grid_rainbow_duel_m3_uniform_2layer": dict(env="Grid", algo="rainbow", hidden=(32, 16), dueling="average", noisy=False,
+                                                mem_kind=0, multisteps=3, n_envs=24, ring_rows=9, batch_size=16, warmup_size=48,
+                                                epsilon=0.3, enable_double_dqn=False, enable_rescale=True, retrace_h=0.9),
+    "pendulum_dqn_uniform_a10_b48": dict(env="Pendulum-v1", algo="dqn", hidden=(48, 24, 16), mem_kind=0, multisteps=1, n_envs=32,
+                                         ring_rows=6, batch_size=48, warmup_size=64, epsilon=0.3, enable_double_dqn=False),
     "cartpole_rainbow_naive_m4": dict(env="CartPole-v1", algo="rainbow", hidden=(40,), dueling="", noisy=True, mem_kind=1,
                                       multisteps=4, n_envs=20, ring_rows=10, batch_size=12, warmup_size=40),
 }
@@ -407,7 +415,8 @@ def test_engine_run_equals_stepwise():
 
 @pytest.mark.parametrize("name", ["cartpole_rainbow_default", "grid_dqn_per_nodouble_rescale", "cartpole_rainbow_naive_m4",
                                   "cartpole_dqn_per", "grid_rainbow_max_m2_uniform_clip", "cartpole_dqn_uniform_h64",
-                                  "cartpole_rainbow_noisy_plain_m2_b24"])
+                                  "cartpole_rainbow_noisy_plain_m2_b24", "cartpole_dqn_uniform_64x64",
+                                  "grid_rainbow_duel_m3_uniform_2layer"])
 def test_learn_many_updates_per_launch_equals_one_by_one(name):
     """One launch of n dependent updates (sample/gather of t+1 overlapped with backward/Adam of t, noise ring, parity
     toggles) == n launches of one update: the in-kernel pipelining must not change a single bit."""
@@ -452,6 +461,9 @@ def test_learner_info_reports_fast_kernel_for_the_default_shape():
     assert name == "learner_fast_kernel" and cluster == 16 and 0 < smem <= 227 * 1024
     dev2 = DeviceEngine(EngineConfig(**ENGINE_CASES["cartpole_dqn_per"]))  # two hidden layers: generic kernel
     assert dev2.learner_info()[0] == "learner_kernel"
+    dev3 = DeviceEngine(EngineConfig(**ENGINE_CASES["cartpole_dqn_uniform_64x64"]))  # uniform replay, plain MLP: one block
+    name3, cluster3, smem3 = dev3.learner_info()
+    assert name3 == "learner_small_kernel" and cluster3 == 1 and 0 < smem3 <= 227 * 1024
 
 
 def test_fast_learner_agrees_with_generic_learner(monkeypatch):
@@ -630,3 +642,60 @@ def test_learning_pendulum_dqn_reaches_reference_baseline():
     kw = dict(env="Pendulum-v1", algo="dqn", hidden=(64, 64), mem_kind=0, multisteps=1, n_envs=64, ring_rows=512, batch_size=32,
               warmup_size=1000, epsilon=0.1, lr=1e-3, target_update_interval=1000, enable_double_dqn=False, seed=1)
     assert _train_and_evaluate(kw, 320, 1, episodes=10) >= -500.0
+
+
+# ---- checkpoint / wire compatibility on the device (formats pinned on CPU in tests/test_checkpoint.py) -----
+@pytest.mark.parametrize("kw", [
+    dict(env="Grid", algo="rainbow", hidden=(32,), dueling="average", noisy=True, mem_kind=1, multisteps=3, n_envs=16, ring_rows=12,
+         batch_size=8, warmup_size=32),
+    dict(env="CartPole-v1", algo="dqn", hidden=(32, 16), mem_kind=0, multisteps=1, n_envs=24, ring_rows=6, batch_size=8,
+         warmup_size=24, epsilon=0.3),
+], ids=["grid_rainbow_per_m3", "cartpole_dqn_uniform"])
+def test_memory_and_parameter_files_round_trip_through_the_device(kw, tmp_path):
+    """VecRunner.save_memory / load_memory / save_parameter / load_parameter (RunnerBase, runner_base.py:141-165): a second
+    engine loaded from the files holds the same sampleable windows and leaf priorities, a consistent SumTree, the same network,
+    and keeps training."""
+    from simple_distributed_rl_b200 import checkpoint as ck
+    from simple_distributed_rl_b200.engine import EngineConfig
+    from simple_distributed_rl_b200.runner import VecRunner
+
+    a = VecRunner(EngineConfig(**kw, seed=5))
+    a.train(max_steps=kw["n_envs"] * (kw["ring_rows"] + 7), train_interval=1)  # the ring has wrapped
+    mem_path, par_path = str(tmp_path / "memory.dat"), str(tmp_path / "parameter.dat")
+    a.save_memory(mem_path, item_compress=True)
+    a.save_parameter(par_path)
+    b = VecRunner(EngineConfig(**kw, seed=99))
+    b.load_memory(mem_path)
+    b.load_parameter(par_path)
+    va, vb = a.engine.ring_view(), b.engine.ring_view()
+    ia, pa = ck.export_items(va)
+    ib, pb = ck.export_items(vb)
+    n_g = va.valid_rows()[1]
+    assert len(ia) == len(ib) == n_g * kw["n_envs"] and n_g == kw["ring_rows"] - kw["multisteps"] + 1
+    import pickle
+
+    assert pickle.dumps(ia) == pickle.dumps(ib)
+    st = b.engine.read_state()
+    assert st.mem_size == n_g * kw["n_envs"] and st.vec_steps == n_g + kw["multisteps"] - 1
+    if kw["mem_kind"]:
+        np.testing.assert_array_equal(pa, pb)
+        assert np.all(pa > 0) and st.max_priority == a.engine.read_state().max_priority
+        tree = b.engine.t["tree"].cpu().numpy()
+        cap = kw["n_envs"] * kw["ring_rows"]
+        np.testing.assert_array_equal(tree[: cap - 1], tree[1: 2 * cap - 2: 2] + tree[2: 2 * cap - 1: 2])
+        np.testing.assert_allclose(tree[0], pa.sum(), rtol=1e-12)
+    for x, y in zip(a.engine.get_params(), b.engine.get_params()):
+        if x is not None:
+            np.testing.assert_array_equal(x, y)
+    for x, y in zip(b.engine.get_params(), b.engine.get_target()):  # call_restore loads online and target
+        if x is not None:
+            np.testing.assert_array_equal(x, y)
+    tc = st.train_count
+    b.engine.learn(5)
+    b.engine.vec_step()
+    b.engine.learn(5)
+    st2 = b.engine.read_state()
+    assert st2.train_count == tc + 10 and np.isfinite(st2.last_loss)
+    if kw["mem_kind"]:
+        tree = b.engine.t["tree"].cpu().numpy()
+        np.testing.assert_allclose(tree[0], tree[cap - 1:].sum(), rtol=1e-9)

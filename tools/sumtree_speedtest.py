@@ -60,7 +60,21 @@ def arm_python():
         return "reference ProportionalMemory (python)", ProportionalMemory(CAPACITY, ALPHA, BETA0, BETA_STEPS, has_duplicate=True)
     from oracle.sumtree import ProportionalMemory
 
-    return "oracle restatement (python)", ProportionalMemory(CAPACITY, ALPHA, BETA0, BETA_STEPS, has_duplicate=True)
+    class Port:  # the port has no payload list and takes its uniforms from a callback: adapt it to the protocol's calls
+        def __init__(self):
+            self.m = ProportionalMemory(CAPACITY, ALPHA, BETA0, BETA_STEPS, has_duplicate=True)
+
+        def add(self, batch, priority=None):
+            self.m.add(priority)
+
+        def sample(self, batch_size, step):
+            idx, w, _, _ = self.m.sample(batch_size, step, lambda i, k: random.random())
+            return idx, w, idx
+
+        def update(self, indices, priorities):
+            self.m.update(indices, priorities)
+
+    return "oracle restatement (python, oracle/sumtree.py)", Port()
 
 
 def arm_cpp():
