@@ -11,7 +11,7 @@
 //   2. gather      the (M+1)-state windows from the ring, padded tails rebuilt (rainbow.py:358-371)
 //   3. forward     online(s), online(s'), target(s'): all row tiles of a layer run concurrently (net.cuh warp tiles)
 //   4. targets     double-DQN / n-step Retrace target, Huber gradient (thread per sample; same code as learner.cu)
-//   5. backward    net_backward_tile on the s rows
+//   5. backward    on the s rows: net.cuh's backward with register-tiled dW / dX loops (small_backward_tile)
 //   6. Adam        torch _single_tensor_adam arithmetic (adam_apply), hard target sync when train_count % interval == 0
 //
 // Reference path: srl/algorithms/dqn/model_torch.py:90-132, rainbow/model_torch.py:85-122, rainbow/rainbow.py:185-287.
@@ -22,6 +22,12 @@
 namespace srlx {
 
 constexpr int kSmThreads = 512;
+
+// clock64() of thread 0 at the phase boundaries of the second-to-last update of a launch (tools/phase_clocks.py)
+#define SRLX_SMSTAMP(slot)                                                                          \
+  do {                                                                                              \
+    if (eng.dbg_clock && tid == 0 && upd + 2 == n_updates) eng.dbg_clock[slot] = clock64();         \
+  } while (0)
 
 struct SPlan {
   NetPlan np;
@@ -87,11 +93,231 @@ __device__ __forceinline__ void adam_apply(float& pp, float& mm, float& vv, floa
   pp = pp - step_size * (mm / denom);
 }
 
+
+// ---- register-tiled pieces of the backward pass (same per-output summation order as net.cuh::net_backward_tile: rows /
+//      units ascending, one fmaf per term -> bit-identical gradients, ~6x fewer shared-memory loads per FMA) -------------
+// dW[u][k] += sum_r dY[r][u] * X[r][k],  db[u] += sum_r dY[r][u]        thread tile 4 units x 4 inputs
+__device__ __forceinline__ void small_dw(const float* __restrict__ dY, int ldy, const float* __restrict__ X, int ldx, int R, int U,
+                                         int K, float* __restrict__ Gw, float* __restrict__ Gb) {
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const int n_kt = (K + 3) >> 2, n_ut = (U + 3) >> 2;
+  for (int item = tid; item < n_ut * n_kt; item += nt) {
+    const int ut = item / n_kt, kt = item - ut * n_kt;
+    const int u0 = ut * 4, k0 = kt * 4;
+    float acc[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
+#pragma unroll 4
+    for (int r = 0; r < R; ++r) {
+      const float4 dy = *reinterpret_cast<const float4*>(dY + r * ldy + u0);
+      const float4 x = *reinterpret_cast<const float4*>(X + r * ldx + k0);
+      const float dv[4] = {dy.x, dy.y, dy.z, dy.w}, xv[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) acc[a][b] = fmaf(dv[a], xv[b], acc[a][b]);
+    }
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b)
+        if (u0 + a < U && k0 + b < K) Gw[(u0 + a) * K + k0 + b] += acc[a][b];
+  }
+  for (int u = tid; u < U; u += nt) {
+    float acc = 0.f;
+    for (int r = 0; r < R; ++r) acc += dY[r * ldy + u];
+    Gb[u] += acc;
+  }
+}
+
+// X[r][k] <- (X[r][k] > 0) ? sum_u dY[r][u] * W[u][k] : 0                thread tile 2 rows x 4 inputs, 4 units per step
+__device__ __forceinline__ void small_dx(const float* __restrict__ dY, int ldy, const float* __restrict__ W, int ldw,
+                                         float* __restrict__ X, int ldx, int R, int U, int K) {
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const int n_kt = (K + 3) >> 2, n_rt = (R + 1) >> 1;
+  const int U4 = U & ~3;
+  for (int item = tid; item < n_rt * n_kt; item += nt) {
+    const int rt = item / n_kt, kt = item - rt * n_kt;
+    const int r0 = rt * 2, r1 = min(r0 + 1, R - 1), k0 = kt * 4;
+    float acc[2][4];
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
+    const float* dy0 = dY + r0 * ldy;
+    const float* dy1 = dY + r1 * ldy;
+    for (int u = 0; u < U4; u += 4) {
+      const float4 d0 = *reinterpret_cast<const float4*>(dy0 + u);
+      const float4 d1 = *reinterpret_cast<const float4*>(dy1 + u);
+      const float d0v[4] = {d0.x, d0.y, d0.z, d0.w}, d1v[4] = {d1.x, d1.y, d1.z, d1.w};
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const float4 w = *reinterpret_cast<const float4*>(W + (u + c) * ldw + k0);
+        const float wv[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+          acc[0][b] = fmaf(d0v[c], wv[b], acc[0][b]);
+          acc[1][b] = fmaf(d1v[c], wv[b], acc[1][b]);
+        }
+      }
+    }
+    for (int u = U4; u < U; ++u) {
+      const float4 w = *reinterpret_cast<const float4*>(W + u * ldw + k0);
+      const float wv[4] = {w.x, w.y, w.z, w.w};
+      const float a0 = dy0[u], a1 = dy1[u];
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        acc[0][b] = fmaf(a0, wv[b], acc[0][b]);
+        acc[1][b] = fmaf(a1, wv[b], acc[1][b]);
+      }
+    }
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      if (k0 + b < K) {
+        float* x0 = X + r0 * ldx + k0 + b;
+        *x0 = (*x0 > 0.f) ? acc[0][b] : 0.f;
+        if (r0 + 1 < R) {
+          float* x1 = X + (r0 + 1) * ldx + k0 + b;
+          *x1 = (*x1 > 0.f) ? acc[1][b] : 0.f;
+        }
+      }
+    }
+  }
+}
+
+// net.cuh::net_backward_tile with the two hidden-layer loops above; the output layer / dueling head (<= 17 rows) is unchanged
+__device__ inline void small_backward_tile(const srlx_net& net, const NetPlan& pl, const float* weff, float* acts, int R,
+                                           const float* dQ, int lddq, float* G) {
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const int L = net.n_layers, A = net.n_actions;
+  const int nout = net.out_dim[L - 1], Ko = net.k_dim[L - 1];
+  float* raw = acts + pl.x_s[L];
+  const int ldr = pl.ldx[L];
+  for (int r = tid; r < R; r += nt) {  // dueling combine backward (dueling_network.py:51-58) -> d raw
+    if (net.dueling == SRLX_DUEL_NONE) {
+      for (int a = 0; a < A; ++a) raw[r * ldr + a] = dQ[r * lddq + a];
+    } else {
+      float sum = 0.f;
+      for (int a = 0; a < A; ++a) sum += dQ[r * lddq + a];
+      int amax = 0;
+      if (net.dueling == SRLX_DUEL_MAX) {
+        float best = raw[r * ldr + 1];
+        for (int a = 1; a < A; ++a)
+          if (raw[r * ldr + 1 + a] > best) { best = raw[r * ldr + 1 + a]; amax = a; }
+      }
+      for (int a = 0; a < A; ++a) {
+        float d = dQ[r * lddq + a];
+        if (net.dueling == SRLX_DUEL_AVERAGE) d -= sum / (float)A;
+        else if (net.dueling == SRLX_DUEL_MAX && a == amax) d -= sum;
+        raw[r * ldr + 1 + a] = d;
+      }
+      raw[r * ldr + 0] = sum;
+    }
+  }
+  __syncthreads();
+  {  // output layer: dW, db
+    const float* X = acts + pl.x_s[L - 1];
+    const int ldx = pl.ldx[L - 1];
+    for (int w = tid; w < nout * Ko; w += nt) {
+      const int o = w / Ko, k = w - o * Ko;
+      const int koff = (net.dueling != SRLX_DUEL_NONE && o > 0) ? Ko : 0;
+      float acc = 0.f;
+      for (int r = 0; r < R; ++r) acc = fmaf(raw[r * ldr + o], X[r * ldx + koff + k], acc);
+      G[net.w_off[L - 1] + w] += acc;
+    }
+    for (int o = tid; o < nout; o += nt) {
+      float acc = 0.f;
+      for (int r = 0; r < R; ++r) acc += raw[r * ldr + o];
+      G[net.b_off[L - 1] + o] += acc;
+    }
+  }
+  __syncthreads();
+  if (L > 1) {  // d hidden (input of the output layer), ReLU-masked, in place
+    float* X = acts + pl.x_s[L - 1];
+    const int ldx = pl.ldx[L - 1], width = pl.xw[L - 1];
+    const float* W = weff + pl.w_s[L - 1];
+    const int ldw = pl.ldw[L - 1];
+    for (int w = tid; w < R * width; w += nt) {
+      const int r = w / width, kk = w - r * width;
+      float d = 0.f;
+      if (net.dueling == SRLX_DUEL_NONE) {
+        for (int o = 0; o < nout; ++o) d = fmaf(raw[r * ldr + o], W[o * ldw + kk], d);
+      } else if (kk < Ko) {
+        d = raw[r * ldr + 0] * W[kk];
+      } else {
+        for (int o = 1; o < nout; ++o) d = fmaf(raw[r * ldr + o], W[o * ldw + (kk - Ko)], d);
+      }
+      X[r * ldx + kk] = (X[r * ldx + kk] > 0.f) ? d : 0.f;
+    }
+  }
+  __syncthreads();
+  for (int l = L - 2; l >= 0; --l) {  // hidden layers, top down
+    const float* dY = acts + pl.x_s[l + 1];
+    float* X = acts + pl.x_s[l];
+    small_dw(dY, pl.ldx[l + 1], X, pl.ldx[l], R, net.out_dim[l], net.k_dim[l], G + net.w_off[l], G + net.b_off[l]);
+    __syncthreads();
+    if (l > 0) {
+      small_dx(dY, pl.ldx[l + 1], weff + pl.w_s[l], pl.ldw[l], X, pl.ldx[l], R, net.out_dim[l], net.k_dim[l]);
+      __syncthreads();
+    }
+  }
+}
+
+// Output layer of a row tile, thread per (row, output): float4 dot products instead of a warp per row
+__device__ inline void small_out_layer(const srlx_net& net, const float* __restrict__ X, int ldx, int R, const float* __restrict__ W,
+                                       int ldw, const float* __restrict__ b, float* __restrict__ raw, int ldr) {
+  const int L = net.n_layers, nout = net.out_dim[L - 1], K = net.k_dim[L - 1];
+  const int K4 = round_up(K, 4);
+  for (int w = threadIdx.x; w < R * nout; w += blockDim.x) {
+    const int o = w / R, r = w - o * R;  // rows fastest: a warp reads one weight row (broadcast) and 32 activation rows
+    const int koff = (net.dueling != SRLX_DUEL_NONE && o > 0) ? K : 0;
+    const float* x = X + r * ldx + koff;
+    const float* wr = W + o * ldw;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    for (int k = 0; k < K4; k += 4) {
+      const float4 xv = *reinterpret_cast<const float4*>(x + k);
+      const float4 wv = *reinterpret_cast<const float4*>(wr + k);
+      a0 = fmaf(xv.x, wv.x, a0);
+      a1 = fmaf(xv.y, wv.y, a1);
+      a2 = fmaf(xv.z, wv.z, a2);
+      a3 = fmaf(xv.w, wv.w, a3);
+    }
+    raw[r * ldr + o] = ((a0 + a1) + (a2 + a3)) + b[o];
+  }
+}
+
+// raw -> Q (plain | V + A - mean(A) | V + A - max(A) | V + A), thread per row
+__device__ inline void small_dueling(const srlx_net& net, const float* __restrict__ raw, int ldr, int R, float* __restrict__ Q, int ldq) {
+  const int A = net.n_actions;
+  for (int r = threadIdx.x; r < R; r += blockDim.x) {
+    const float* rr = raw + r * ldr;
+    if (net.dueling == SRLX_DUEL_NONE) {
+      for (int a = 0; a < A; ++a) Q[r * ldq + a] = rr[a];
+    } else {
+      const float v = rr[0];
+      float red = 0.f;
+      if (net.dueling == SRLX_DUEL_AVERAGE) {
+        for (int a = 0; a < A; ++a) red += rr[1 + a];
+        red = red / (float)A;
+      } else if (net.dueling == SRLX_DUEL_MAX) {
+        red = rr[1];
+        for (int a = 1; a < A; ++a) red = fmaxf(red, rr[1 + a]);
+      }
+      for (int a = 0; a < A; ++a) Q[r * ldq + a] = v + rr[1 + a] - red;
+    }
+  }
+}
+
 __global__ void __launch_bounds__(kSmThreads, 1)
 learner_small_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_updates) {
   extern __shared__ __align__(16) unsigned char smem[];
   const srlx_net& net = eng.net;
-  const SPlan pl = make_splan(eng);
+  __shared__ SPlan s_plan;  // the plan lives in shared memory: its per-layer tables are indexed at run time
+  if (threadIdx.x == 0) s_plan = make_splan(eng);
+  __syncthreads();
+  const SPlan& pl = s_plan;
   const NetPlan& np = pl.np;
   float* weff = reinterpret_cast<float*>(smem + pl.off_weff);
   float* wefft = reinterpret_cast<float*>(smem + pl.off_wefft);
@@ -145,39 +371,53 @@ learner_small_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_u
   const uint64_t g_lo = g_next > (uint64_t)R ? g_next - R : 0;
   const uint32_t n_valid = (uint32_t)((g_next - (uint64_t)(M - 1) - g_lo) * E);
   const float b1 = (float)eng.adam_beta1, b2 = (float)eng.adam_beta2, aeps = (float)eng.adam_eps;
+  float* disc_pow = red + 32;  // multi_discounts (rainbow.py:175): float32 of discount ** k
+  if (tid < M) disc_pow[tid] = (float)pow(eng.discount, (double)tid);
+  __syncthreads();
 
   for (uint32_t upd = 0; upd < n_updates; ++upd) {
     const uint64_t tc = tc0 + upd;
     // ---------------------------------------------------------------- 1. sample
+    SRLX_SMSTAMP(0);
     if (warp == 0) {
-      for (int i0 = 0; i0 < B; i0 += 32) {
-        const int i = i0 + lane;
-        if (i < B) {
-          const uint4 w = philox(eng.seed, STREAM_UNIFORM_SAMPLE, (uint32_t)i, (uint32_t)tc, (uint32_t)(tc >> 32));
-          pick[i] = (int)u_below(w.x, n_valid);
-        }
+      for (int i = lane; i < B; i += 32) {
+        const uint4 w = philox(eng.seed, STREAM_UNIFORM_SAMPLE, (uint32_t)i, (uint32_t)tc, (uint32_t)(tc >> 32));
+        pick[i] = (int)u_below(w.x, n_valid);
       }
       __syncwarp();
-      if (lane == 0) {
-        for (int i = 1; i < B; ++i) {  // a pick that repeats an earlier one is redrawn (attempt k = 1, 2, ...), in order
-          int k = 0;
-          while (true) {
-            bool dup = false;
-            for (int j = 0; j < i; ++j) dup |= (pick[j] == pick[i]);
-            if (!dup || ++k >= 65536) break;
-            const uint4 w = philox(eng.seed, STREAM_UNIFORM_SAMPLE, (uint32_t)i | ((uint32_t)k << 16), (uint32_t)tc, (uint32_t)(tc >> 32));
-            pick[i] = (int)u_below(w.x, n_valid);
+      bool dup = false;  // does any pick repeat an earlier one?  (rare: B^2 / (2 n_valid))
+      for (int i = lane; i < B; i += 32) {
+        const int pi = pick[i];
+        for (int j = 0; j < i; ++j) dup |= (pick[j] == pi);
+      }
+      if (__any_sync(0xffffffffu, dup)) {
+        if (lane == 0) {
+          for (int i = 1; i < B; ++i) {  // a repeated pick is redrawn (attempt k = 1, 2, ...), in sample order
+            int k = 0;
+            while (true) {
+              bool d2 = false;
+              for (int j = 0; j < i; ++j) d2 |= (pick[j] == pick[i]);
+              if (!d2 || ++k >= 65536) break;
+              const uint4 w = philox(eng.seed, STREAM_UNIFORM_SAMPLE, (uint32_t)i | ((uint32_t)k << 16), (uint32_t)tc, (uint32_t)(tc >> 32));
+              pick[i] = (int)u_below(w.x, n_valid);
+            }
           }
         }
+        __syncwarp();
       }
-      __syncwarp();
       for (int i = lane; i < B; i += 32) {
         const uint64_t pk = (uint64_t)pick[i];
         const uint64_t g = g_lo + pk / E;
         slot[i] = (int)((g % R) * E + pk % E);
       }
+    } else if (tid == 32) {
+      // Adam bias corrections of this update (torch/optim/adam.py: 1 - beta ** step), off the critical path
+      const double t = (double)(adam0 + upd + 1);
+      sc->step_size = (float)(eng.lr / (1.0 - pow(eng.adam_beta1, t)));
+      sc->bc2_sqrt = (float)sqrt(1.0 - pow(eng.adam_beta2, t));
     }
     __syncthreads();
+    SRLX_SMSTAMP(1);
     // ---------------------------------------------------------------- 2. gather (all loads of a record before its stores)
     for (int w = tid; w < BM; w += kSmThreads) {
       const int i = w / M, k = w - i * M;
@@ -204,6 +444,7 @@ learner_small_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_u
       x_row(0, i)[d] = __ldcg(eng.ring_obs + (size_t)slot[i] * D + d);
     }
     __syncthreads();
+    SRLX_SMSTAMP(2);
     // padded tails (rainbow.py:358-371), then the online copy of the next states
     for (int i = tid; i < B; i += kSmThreads) {
       const int s0 = slot[i];
@@ -253,6 +494,7 @@ learner_small_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_u
       }
     }
     __syncthreads();
+    SRLX_SMSTAMP(3);
     // ---------------------------------------------------------------- 3. forward, every tile of a layer concurrently
     auto tile_rows = [&](int t) -> int {
       const int rows = t < pl.n_on_tiles ? pl.n_on_rows - t * kRowTile : BM - (t - pl.n_on_tiles) * kRowTile;
@@ -272,15 +514,22 @@ learner_small_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_u
       }
       __syncthreads();
     }
+    SRLX_SMSTAMP(4);
     for (int tile = 0; tile < pl.n_tiles; ++tile) {
       const float* wset = tile < pl.n_on_tiles ? weff : wefft;
       float* a = acts + (size_t)tile * np.act_floats;
-      // Q rows: online set first ([0, n_on_rows)), target rows at B + BM
-      float* q = tile < pl.n_on_tiles ? Q + (size_t)tile * kRowTile * A : Q + (size_t)(B + BM + (tile - pl.n_on_tiles) * kRowTile) * A;
-      out_layer_fwd(net, a + np.x_s[L - 1], np.ldx[L - 1], tile_rows(tile), wset + np.w_s[L - 1], np.ldw[L - 1], wset + np.b_s[L - 1],
-                    a + np.x_s[L], np.ldx[L], q, A);
+      small_out_layer(net, a + np.x_s[L - 1], np.ldx[L - 1], tile_rows(tile), wset + np.w_s[L - 1], np.ldw[L - 1], wset + np.b_s[L - 1],
+                      a + np.x_s[L], np.ldx[L]);
     }
     __syncthreads();
+    for (int tile = 0; tile < pl.n_tiles; ++tile) {
+      float* a = acts + (size_t)tile * np.act_floats;
+      // Q rows: online set first ([0, n_on_rows)), target rows at B + BM
+      float* q = tile < pl.n_on_tiles ? Q + (size_t)tile * kRowTile * A : Q + (size_t)(B + BM + (tile - pl.n_on_tiles) * kRowTile) * A;
+      small_dueling(net, a + np.x_s[L], np.ldx[L], tile_rows(tile), q, A);
+    }
+    __syncthreads();
+    SRLX_SMSTAMP(5);
     // ---------------------------------------------------------------- 4. targets, Huber gradient (thread per sample)
     {
       const float* qon = Q + (size_t)B * A;         // online(s')  [BM][A]
@@ -306,7 +555,7 @@ learner_small_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_u
           float qk = 0.f;  // the first step is learnt by the trainer itself (rainbow.py:232-234)
           if (k >= 1) qk = qon[(size_t)(i * M + k - 1) * A + w_act[i * M + k]];
           const float td = gain - qk;
-          target += (td * (float)pow(eng.discount, (double)k)) * retrace;
+          target += (td * disc_pow[k]) * retrace;
         }
         tq[i] = target;
         const int a0 = w_act[i * M + 0];
@@ -329,21 +578,20 @@ learner_small_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_u
       l /= (double)B;
       sc->last_loss = l;
       sc->loss_sum += l;
-      const double t = (double)(adam0 + upd + 1);
-      sc->step_size = (float)(eng.lr / (1.0 - pow(eng.adam_beta1, t)));
-      sc->bc2_sqrt = (float)sqrt(1.0 - pow(eng.adam_beta2, t));
       if ((tc % (uint64_t)eng.target_update_interval) == 0) sc->sync_count += 1;
     }
     if (eng.dbg_target_q)
       for (int i = tid; i < B; i += kSmThreads) eng.dbg_target_q[i] = tq[i];
     if (eng.dbg_q_sa)
       for (int i = tid; i < B; i += kSmThreads) eng.dbg_q_sa[i] = qsa[i];
+    SRLX_SMSTAMP(6);
     // ---------------------------------------------------------------- 5. backward on the s rows (G was zeroed by Adam)
     for (int tile = 0; tile < pl.n_s_tiles; ++tile) {
       const int Rt = min(kRowTile, B - tile * kRowTile);
-      net_backward_tile(net, np, weff, acts + (size_t)tile * np.act_floats, Rt, dQ + (size_t)tile * kRowTile * A, A, G);
+      small_backward_tile(net, np, weff, acts + (size_t)tile * np.act_floats, Rt, dQ + (size_t)tile * kRowTile * A, A, G);
     }
     __syncthreads();
+    SRLX_SMSTAMP(7);
     // ---------------------------------------------------------------- 6. Adam, target sync
     {
       const float step_size = sc->step_size, bc2_sqrt = sc->bc2_sqrt;
@@ -362,6 +610,7 @@ learner_small_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_u
       }
     }
     __syncthreads();
+    SRLX_SMSTAMP(8);
   }
 
   // ---- write the state back ----------------------------------------------------------------------------------------

@@ -103,12 +103,13 @@ __device__ inline void tree_update_batch(double* __restrict__ tree, const int64_
       if (idx[j] == li) { last = false; break; }
     if (last) __stcg(tree + li, pri[i]);
   }
-  // 3) ancestors: work item = (level l above the leaf, item i), consecutive threads on the same level; the leader applies
-  //    all changes to its node in item order.  Leaves of a non-power-of-two tree sit at two depths, so "same node" is
-  //    tested through the depths: x lies below `node` (depth dn) iff (x+1) >> (depth(x) - dn) == node + 1.
+  // 3) ancestors: work item = (item i, level l above its leaf); the lanes of a warp share the item (same loop bounds, same
+  //    shared-memory words -> no divergence, broadcast reads) and differ in the level; the leader applies all changes to
+  //    its node in item order.  Leaves of a non-power-of-two tree sit at two depths, so "same node" is tested through
+  //    the depths: x lies below `node` (depth dn) iff (x+1) >> (depth(x) - dn) == node + 1.
   const int levels = dep[n];
   for (int w = tid; w < n * levels; w += nt) {
-    const int l = w / n + 1, i = w - (l - 1) * n;
+    const int i = w / levels, l = w - i * levels + 1;
     const int dn = dep[i] - l;
     if (dn < 0) continue;  // above the root
     const int64_t node1 = (idx[i] + 1) >> l;
