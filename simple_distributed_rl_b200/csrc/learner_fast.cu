@@ -1684,15 +1684,15 @@ static int fast_choose(const srlx_engine* eng, int* C_out, int* lev_out, size_t*
 }
 
 namespace srlx {
-int small_choose(const srlx_engine* eng, size_t* smem_out);                             // learner_small.cu
+int small_choose(const srlx_engine* eng, size_t* smem_out, int* C_out);                 // learner_small.cu
 int learn_small(const srlx_engine* eng, uint32_t n_updates, uintptr_t cuda_stream);
 }  // namespace srlx
 
-// 2 when the single-block kernel (learner_small.cu: uniform replay, no NoisyNet, everything in one SM) is the one to run
-static int small_pick(const srlx_engine* eng, size_t* smem_out) {
+// 2 when the row-split kernel (learner_small.cu: uniform replay, no NoisyNet, batch rows over a small cluster) is the one to run
+static int small_pick(const srlx_engine* eng, size_t* smem_out, int* C_out) {
   const char* force = getenv("SRLX_LEARNER");
   if (force && force[0] == 'g') return 0;
-  return srlx::small_choose(eng, smem_out) == 1 ? 2 : 0;
+  return srlx::small_choose(eng, smem_out, C_out) == 1 ? 2 : 0;
 }
 
 // Which kernel srlx_learn will run for this engine: 1 = learner_fast_kernel (single hidden layer, <= 4 observation floats,
@@ -1705,8 +1705,8 @@ extern "C" int srlx_learner_info(const srlx_engine* eng, int* cluster_size, size
   size_t sm = 0;
   int rc = fast_choose(eng, &C, &lev, &sm);
   if (rc == 0) {
-    rc = small_pick(eng, &sm);
-    C = rc == 2 ? 1 : 0;
+    rc = small_pick(eng, &sm, &C);
+    if (rc != 2) C = 0;
   }
   if (cluster_size) *cluster_size = rc >= 1 ? C : 0;
   if (smem_bytes) *smem_bytes = rc >= 1 ? sm : 0;
@@ -1732,6 +1732,6 @@ extern "C" int srlx_learn(const srlx_engine* eng, uint32_t n_updates, uintptr_t 
   const int rc = fast_choose(eng, &C, &lev, &smem_bytes);
   if (rc < 0) return rc;
   if (rc == 1) return learn_fast(eng, n_updates, cuda_stream, C, lev);
-  if (small_pick(eng, &smem_bytes) == 2) return learn_small(eng, n_updates, cuda_stream);
+  if (small_pick(eng, &smem_bytes, &C) == 2) return learn_small(eng, n_updates, cuda_stream);
   return learn_generic(eng, n_updates, cuda_stream);
 }

@@ -1,40 +1,46 @@
-// learner_small.cu -- Trainer.train() for small plain MLPs on uniform replay, ONE thread block, everything in shared memory.
+// learner_small.cu -- Trainer.train() for small plain MLPs on uniform replay: the batch rows are split over a small
+// thread-block cluster, every CTA holds the whole network in shared memory.
 //
-// BASELINE configs[1] (DQN, MLP[64,64], uniform replay 1M) has ~4.6k parameters: the cluster kernels (learner.cu,
-// learner_fast.cu) shard a wide layer over 8..16 SMs and pay a DSMEM exchange per layer boundary, which for a net this
-// small is all latency and no work (37 us per update on the generic kernel).  Here the online weights, the target
-// weights, both Adam moments and the activations of every row tile stay in the shared memory of one SM for the whole
-// launch; an update is a short chain of block-wide phases:
+// BASELINE configs[1] (DQN, MLP[64,64], uniform replay 1M) has ~4.6k parameters.  The unit-sharded cluster kernels
+// (learner.cu, learner_fast.cu) pay a DSMEM exchange per layer boundary, which for a net this small is all latency and no
+// work (37 us per update on the generic kernel); one SM alone is bound by its shared-memory bandwidth (25 us).  Here the
+// cluster is data parallel over the BATCH: CTA c owns B/C of the sampled items end to end -- gather, the three forwards,
+// targets, backward -- with a full copy of the online and target weights in its shared memory, and owns 1/C of the
+// parameters for the optimiser step.  An update is
 //
-//   1. sample      B distinct uniform picks (replay_buffer.py:34-36): attempt 0 of all B draws in parallel, duplicates
-//                  resolved in sample order (the result equals the sequential rejection loop of oracle/sumtree.py)
-//   2. gather      the (M+1)-state windows from the ring, padded tails rebuilt (rainbow.py:358-371)
-//   3. forward     online(s), online(s'), target(s'): all row tiles of a layer run concurrently (net.cuh warp tiles)
-//   4. targets     double-DQN / n-step Retrace target, Huber gradient (thread per sample; same code as learner.cu)
-//   5. backward    on the s rows: net.cuh's backward with register-tiled dW / dX loops (small_backward_tile)
-//   6. Adam        torch _single_tensor_adam arithmetic (adam_apply), hard target sync when train_count % interval == 0
+//   1. sample      B distinct uniform picks (replay_buffer.py:34-36), every CTA redundantly: attempt 0 of all draws in
+//                  parallel, duplicates resolved in sample order (== the sequential rejection loop of oracle/sumtree.py)
+//   2. gather      the (M+1)-state windows of the CTA's items from the ring, padded tails rebuilt (rainbow.py:358-371)
+//   3. forward     online(s), online(s'), target(s') on the CTA's rows (register-tiled warp tasks, weights in smem)
+//   4. targets     double-DQN / n-step Retrace target, Huber gradient (thread per item; same code as learner.cu)
+//   5. backward    on the CTA's rows -> a partial gradient of every parameter
+//   6. REDUCE-SCATTER the partial gradients to the CTA that owns the parameter slice (st.async + mbarrier tx, DSMEM),
+//      summed there in CTA order; Adam on the slice (torch _single_tensor_adam arithmetic)
+//   7. ALL-GATHER the updated slice into every CTA's weight copy; hard target sync when train_count % interval == 0
 //
-// Reference path: srl/algorithms/dqn/model_torch.py:90-132, rainbow/model_torch.py:85-122, rainbow/rainbow.py:185-287.
-// CPU twin: oracle/engine.py::learn.  Applies to: uniform replay, no NoisyNet, any depth / dueling head that fits.
+// two DSMEM hops per update instead of two per layer.  Reference path: srl/algorithms/dqn/model_torch.py:90-132,
+// rainbow/model_torch.py:85-122, rainbow/rainbow.py:185-287.  CPU twin: oracle/engine.py::learn.
+// Applies to: uniform replay, no NoisyNet, any depth / dueling head whose plan fits the shared memory of an SM.
 #include "cluster.cuh"
 #include "net.cuh"
 
 namespace srlx {
 
 constexpr int kSmThreads = 512;
+constexpr int kSmMaxCluster = 8;
 
-// clock64() of thread 0 at the phase boundaries of the second-to-last update of a launch (tools/phase_clocks.py)
-#define SRLX_SMSTAMP(slot)                                                                          \
-  do {                                                                                              \
-    if (eng.dbg_clock && tid == 0 && upd + 2 == n_updates) eng.dbg_clock[slot] = clock64();         \
+// clock64() of thread 0 of CTA 0 at the phase boundaries of the second-to-last update of a launch (tools/phase_clocks.py)
+#define SRLX_SMSTAMP(slot)                                                                                     \
+  do {                                                                                                         \
+    if (eng.dbg_clock && rank == 0 && tid == 0 && upd + 2 == n_updates) eng.dbg_clock[slot] = clock64();       \
   } while (0)
 
 struct SPlan {
   NetPlan np;
-  int B, M, A, D, BM, P, P4;
+  int C, B, Bc, M, A, D, BcM, P, S;  // Bc = items per CTA, S = floats per parameter slice (multiple of 4), C * S >= P
   int n_on_rows, n_on_tiles, n_tg_tiles, n_tiles, n_s_tiles;
-  size_t off_weff, off_wefft, off_m, off_v, off_g, off_slot, off_acts, off_q, off_dq, off_pick, off_win, off_tq, off_red,
-      off_scal, total;
+  size_t off_mbar, off_weff, off_wefft, off_m, off_v, off_g, off_recv, off_wflat, off_wnew, off_slot, off_acts, off_q, off_dq, off_pick,
+      off_win, off_tq, off_red, off_loss, off_scal, total;
 };
 
 struct SScal {
@@ -43,45 +49,114 @@ struct SScal {
   unsigned int sync_count;
 };
 
-__host__ __device__ inline SPlan make_splan(const srlx_engine& eng) {
+__host__ __device__ inline SPlan make_splan(const srlx_engine& eng, int C) {
   SPlan p;
   p.np = make_plan(eng.net);
+  p.C = C;
   p.B = eng.batch_size;
+  p.Bc = (p.B + C - 1) / C;
   p.M = eng.multisteps;
   p.A = eng.n_actions;
   p.D = eng.obs_dim;
-  p.BM = p.B * p.M;
+  p.BcM = p.Bc * p.M;
   p.P = eng.net.n_params;
-  p.P4 = round_up(p.P, 4);
+  p.S = round_up((p.P + C - 1) / C, 4);
   const bool need_online_next = eng.enable_double_dqn || p.M > 1;
-  p.n_on_rows = p.B + (need_online_next ? p.BM : 0);  // online rows: [0,B) = s, [B,B+BM) = s'_k
+  p.n_on_rows = p.Bc + (need_online_next ? p.BcM : 0);  // online rows of a CTA: [0,Bc) = s, [Bc,Bc+BcM) = s'_k
   p.n_on_tiles = (p.n_on_rows + kRowTile - 1) / kRowTile;
-  p.n_tg_tiles = (p.BM + kRowTile - 1) / kRowTile;   // target rows: s'_k
+  p.n_tg_tiles = (p.BcM + kRowTile - 1) / kRowTile;     // target rows: s'_k
   p.n_tiles = p.n_on_tiles + p.n_tg_tiles;
-  p.n_s_tiles = (p.B + kRowTile - 1) / kRowTile;
+  p.n_s_tiles = (p.Bc + kRowTile - 1) / kRowTile;
   size_t o = 0;
   auto take = [&](size_t bytes) { size_t r = o; o += (bytes + 15) / 16 * 16; return r; };
+  p.off_mbar = take(64);
   p.off_weff = take((size_t)p.np.weff_floats * 4);
   p.off_wefft = take((size_t)p.np.weff_floats * 4);
-  p.off_m = take((size_t)p.P4 * 4);
-  p.off_v = take((size_t)p.P4 * 4);
-  p.off_g = take((size_t)p.P4 * 4);
-  p.off_slot = take((size_t)p.P4 * 2);
+  p.off_m = take((size_t)p.S * 4);
+  p.off_v = take((size_t)p.S * 4);
+  p.off_g = take((size_t)C * p.S * 4);       // this CTA's partial gradient, flat parameter order (padded to C * S)
+  p.off_recv = take((size_t)C * p.S * 4);    // partial gradients of the own slice, one row per source CTA
+  p.off_wflat = take((size_t)C * p.S * 4);   // all-gathered new parameters, flat order
+  p.off_wnew = take((size_t)p.S * 4);        // the own slice after Adam (source of the all-gather copies)
+  p.off_slot = take((size_t)C * p.S * 2);
   p.off_acts = take((size_t)p.n_tiles * p.np.act_floats * 4);
-  p.off_q = take((size_t)(p.B + 2 * p.BM) * p.A * 4);  // Q(s) [B][A], online Q(s') [BM][A], target Q(s') [BM][A]
-  p.off_dq = take((size_t)p.B * p.A * 4);
-  p.off_pick = take((size_t)p.B * 4 * 2);              // picks, slots
-  p.off_win = take((size_t)p.BM * 4 * 4);              // action, reward, term, done of every window step
-  p.off_tq = take((size_t)p.B * 4 * 2);                // target, q(s,a)
+  p.off_q = take((size_t)(p.Bc + 2 * p.BcM) * p.A * 4);  // Q(s) [Bc][A], online Q(s') [BcM][A], target Q(s') [BcM][A]
+  p.off_dq = take((size_t)p.Bc * p.A * 4);
+  p.off_pick = take((size_t)p.B * 4 * 3);                // picks, slots of update t and t+1 (all B items, every CTA)
+  p.off_win = take((size_t)p.BcM * 4 * 4);               // action, reward, term, done of every local window step
+  p.off_tq = take((size_t)p.Bc * 4 * 2);                 // target, q(s,a)
   p.off_red = take(64 * 4);
+  p.off_loss = take((size_t)kSmMaxCluster * 8);
   p.off_scal = take(64);
   p.total = o;
   return p;
 }
 
 __host__ inline bool small_shape_ok(const srlx_engine& eng) {
-  return eng.mem_kind == SRLX_MEM_UNIFORM && !eng.net.noisy && eng.net.n_layers >= 2 && eng.net.n_params < 65536 &&
+  return eng.mem_kind == SRLX_MEM_UNIFORM && !eng.net.noisy && eng.net.n_layers >= 2 && eng.net.n_params < 60000 &&
          eng.obs_dim <= SRLX_MAX_OBS;
+}
+
+// ---- PTX: DSMEM stores that complete a transaction count on the destination CTA's mbarrier -----------------------------
+__device__ __forceinline__ uint32_t sm_mapa(uint32_t saddr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void sm_st_async_f4(uint32_t raddr, float4 v, uint32_t rmbar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.f32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(raddr),
+               "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "r"(rmbar)
+               : "memory");
+}
+__device__ __forceinline__ void sm_st_async_f2(uint32_t raddr, float a, float b, uint32_t rmbar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.f32 [%0], {%1, %2}, [%3];" ::"r"(raddr), "f"(a),
+               "f"(b), "r"(rmbar)
+               : "memory");
+}
+// one bulk copy of `bytes` (multiple of 16) from this CTA's shared memory into a peer's, completing on the peer's mbarrier
+__device__ __forceinline__ void sm_bulk_s2c(uint32_t dst_cluster_addr, const void* src_smem, uint32_t bytes, uint32_t rmbar) {
+  asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_cluster_addr),
+               "r"(smem_u32(src_smem)), "r"(bytes), "r"(rmbar)
+               : "memory");
+}
+__device__ __forceinline__ void sm_fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void sm_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.release.cta.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+
+// one warp tile of a hidden layer with ONE unit per lane (4 rows x 32 units): half the dependent chain of net.cuh's
+// 64-unit tile, for the few rows a CTA owns
+__device__ __forceinline__ void dense_relu_task32(const float* __restrict__ X, int ldx, int R, int K, const float* __restrict__ W,
+                                                  int ldw, const float* __restrict__ b, int U, float* __restrict__ Y, int ldy,
+                                                  int rt, int ut) {
+  const int lane = threadIdx.x & 31;
+  const int K4 = round_up(K, 4);
+  const int r0 = rt * 4;
+  const int u0 = ut * 32 + lane;
+  const bool v0 = u0 < U;
+  const float* w0p = W + (v0 ? u0 : 0) * ldw;
+  const float b0 = v0 ? b[u0] : 0.f;
+  float acc[4];
+  const float* xr[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    acc[i] = b0;
+    xr[i] = X + min(r0 + i, R - 1) * ldx;
+  }
+  for (int k = 0; k < K4; k += 4) {
+    const float4 wa = *reinterpret_cast<const float4*>(w0p + k);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float4 x = *reinterpret_cast<const float4*>(xr[i] + k);
+      acc[i] = fmaf(x.x, wa.x, acc[i]);
+      acc[i] = fmaf(x.y, wa.y, acc[i]);
+      acc[i] = fmaf(x.z, wa.z, acc[i]);
+      acc[i] = fmaf(x.w, wa.w, acc[i]);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    if (r0 + i < R && v0) Y[(r0 + i) * ldy + u0] = fmaxf(acc[i], 0.f);
 }
 
 __device__ __forceinline__ void adam_apply(float& pp, float& mm, float& vv, float g, float b1, float b2, float eps,
@@ -109,7 +184,7 @@ __device__ __forceinline__ void small_dw(const float* __restrict__ dY, int ldy, 
     for (int a = 0; a < 4; ++a)
 #pragma unroll
       for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
-#pragma unroll 4
+#pragma unroll 1
     for (int r = 0; r < R; ++r) {
       const float4 dy = *reinterpret_cast<const float4*>(dY + r * ldy + u0);
       const float4 x = *reinterpret_cast<const float4*>(X + r * ldx + k0);
@@ -310,20 +385,70 @@ __device__ inline void small_dueling(const srlx_net& net, const float* __restric
   }
 }
 
+// B distinct uniform picks of update `tc` -> ring slots (one warp).  Attempt 0 of every draw in parallel; a pick that repeats
+// an earlier one is redrawn (attempt k = 1, 2, ...) in sample order, which is what the sequential rejection loop produces.
+__device__ __noinline__ void small_sample(const srlx_engine& eng, uint64_t tc, int B, uint32_t n_valid, uint32_t g_lo_mod, int* pick,
+                                          int* slot) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t E = (uint32_t)eng.n_envs, R = (uint32_t)eng.ring_rows;
+  for (int i = lane; i < B; i += 32) {
+    const uint4 w = philox(eng.seed, STREAM_UNIFORM_SAMPLE, (uint32_t)i, (uint32_t)tc, (uint32_t)(tc >> 32));
+    pick[i] = (int)u_below(w.x, n_valid);
+  }
+  __syncwarp();
+  bool dup = false;  // does any pick repeat an earlier one?  (rare: B^2 / (2 n_valid))
+  for (int i = lane; i < B; i += 32) {
+    const int pi = pick[i];
+    for (int j = 0; j < i; ++j) dup |= (pick[j] == pi);
+  }
+  if (__any_sync(0xffffffffu, dup)) {
+    if (lane == 0) {
+      for (int i = 1; i < B; ++i) {
+        int k = 0;
+        while (true) {
+          bool d2 = false;
+          for (int j = 0; j < i; ++j) d2 |= (pick[j] == pick[i]);
+          if (!d2 || ++k >= 65536) break;
+          const uint4 w = philox(eng.seed, STREAM_UNIFORM_SAMPLE, (uint32_t)i | ((uint32_t)k << 16), (uint32_t)tc, (uint32_t)(tc >> 32));
+          pick[i] = (int)u_below(w.x, n_valid);
+        }
+      }
+    }
+    __syncwarp();
+  }
+  for (int i = lane; i < B; i += 32) {
+    const uint32_t pk = (uint32_t)pick[i];
+    const uint32_t q = pk / E;                       // row offset inside the valid range (g = g_lo + q)
+    slot[i] = (int)(((g_lo_mod + q) % R) * E + (pk - q * E));
+  }
+}
+
+// Adam bias corrections of optimiser step t (torch/optim/adam.py: 1 - beta ** step)
+__device__ __noinline__ void small_adam_scalars(const srlx_engine& eng, double t, SScal* sc) {
+  sc->step_size = (float)(eng.lr / (1.0 - pow(eng.adam_beta1, t)));
+  sc->bc2_sqrt = (float)sqrt(1.0 - pow(eng.adam_beta2, t));
+}
+
 __global__ void __launch_bounds__(kSmThreads, 1)
 learner_small_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_updates) {
   extern __shared__ __align__(16) unsigned char smem[];
+  cg::cluster_group cluster = cg::this_cluster();
+  const int C = (int)cluster.num_blocks();
+  const int rank = (int)cluster.block_rank();
   const srlx_net& net = eng.net;
   __shared__ SPlan s_plan;  // the plan lives in shared memory: its per-layer tables are indexed at run time
-  if (threadIdx.x == 0) s_plan = make_splan(eng);
+  if (threadIdx.x == 0) s_plan = make_splan(eng, C);
   __syncthreads();
   const SPlan& pl = s_plan;
   const NetPlan& np = pl.np;
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(smem + pl.off_mbar);  // [0] reduce-scatter, [1] all-gather
   float* weff = reinterpret_cast<float*>(smem + pl.off_weff);
   float* wefft = reinterpret_cast<float*>(smem + pl.off_wefft);
   float* am = reinterpret_cast<float*>(smem + pl.off_m);
   float* av = reinterpret_cast<float*>(smem + pl.off_v);
   float* G = reinterpret_cast<float*>(smem + pl.off_g);
+  float* recv = reinterpret_cast<float*>(smem + pl.off_recv);
+  float* wflat = reinterpret_cast<float*>(smem + pl.off_wflat);
   unsigned short* pslot = reinterpret_cast<unsigned short*>(smem + pl.off_slot);
   float* acts = reinterpret_cast<float*>(smem + pl.off_acts);
   float* Q = reinterpret_cast<float*>(smem + pl.off_q);
@@ -331,190 +456,197 @@ learner_small_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_u
   int* pick = reinterpret_cast<int*>(smem + pl.off_pick);
   int* slot = pick + pl.B;
   int* w_act = reinterpret_cast<int*>(smem + pl.off_win);
-  float* w_rew = reinterpret_cast<float*>(smem + pl.off_win) + pl.BM;
-  float* w_term = w_rew + pl.BM;
-  int* w_done = reinterpret_cast<int*>(w_term + pl.BM);
+  float* w_rew = reinterpret_cast<float*>(smem + pl.off_win) + pl.BcM;
+  float* w_term = w_rew + pl.BcM;
+  int* w_done = reinterpret_cast<int*>(w_term + pl.BcM);
   float* tq = reinterpret_cast<float*>(smem + pl.off_tq);
-  float* qsa = tq + pl.B;
+  float* qsa = tq + pl.Bc;
   float* red = reinterpret_cast<float*>(smem + pl.off_red);
+  float* lossbuf = reinterpret_cast<float*>(smem + pl.off_loss);  // [C][2] partial Huber sums (CTA 0)
   SScal* sc = reinterpret_cast<SScal*>(smem + pl.off_scal);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = kSmThreads >> 5;
-  const int B = pl.B, M = pl.M, A = pl.A, D = pl.D, BM = pl.BM, E = eng.n_envs, R = eng.ring_rows, P = pl.P;
+  const int B = pl.B, Bc = pl.Bc, M = pl.M, A = pl.A, D = pl.D, BcM = pl.BcM, E = eng.n_envs, R = eng.ring_rows, P = pl.P, S = pl.S;
   const int L = net.n_layers;
+  const int i0 = rank * Bc;                           // first batch item of this CTA
+  const int nb = max(0, min(Bc, B - i0));             // its item count
+  const int p0 = rank * S;                            // first parameter of its slice
   const bool need_online_next = eng.enable_double_dqn || M > 1;
   srlx_state* st = eng.state;
   const uint64_t tc0 = st->train_count, mem_size = st->mem_size, vec_steps = st->vec_steps, adam0 = st->adam_step;
-  if (!(mem_size >= eng.warmup_size && mem_size >= (uint64_t)B)) return;  // warming up: train() returns, no count
+  if (!(mem_size >= eng.warmup_size && mem_size >= (uint64_t)B)) return;  // warming up (uniform across the cluster)
 
-  // ---- one-time setup: parameters, moments and target into shared memory --------------------------------------------
+  // ---- one-time setup: the whole network into every CTA, the moments of the own slice ------------------------------------
   for (int i = tid; i < np.weff_floats; i += kSmThreads) { weff[i] = 0.f; wefft[i] = 0.f; }
   for (int i = tid; i < pl.n_tiles * np.act_floats; i += kSmThreads) acts[i] = 0.f;
-  for (int i = tid; i < pl.P4; i += kSmThreads) G[i] = 0.f;
-  if (tid == 0) { sc->loss_sum = 0.0; sc->last_loss = 0.0; sc->sync_count = 0; }
+  for (int i = tid; i < C * S; i += kSmThreads) { G[i] = 0.f; wflat[i] = 0.f; pslot[i] = 0; }
+  for (int i = tid; i < Bc * A; i += kSmThreads) dQ[i] = 0.f;
+  for (int i = tid; i < S; i += kSmThreads) { am[i] = 0.f; av[i] = 0.f; }
+  if (tid == 0) {
+    sc->loss_sum = 0.0; sc->last_loss = 0.0; sc->sync_count = 0;
+    mbar_init(&mbar[0], 1);
+    mbar_init(&mbar[1], 1);
+    fence_mbar_init();
+    sm_expect_tx(&mbar[0], (uint32_t)(C * S * 4 + (rank == 0 ? C * 8 : 0)));
+    sm_expect_tx(&mbar[1], (uint32_t)(C * S * 4));
+  }
   __syncthreads();
   for (int p = tid; p < P; p += kSmThreads) {
     const int s = weff_slot(net, np, p, layer_of_param(net, p));
     pslot[p] = (unsigned short)s;
     weff[s] = __ldcg(eng.params + p);
     wefft[s] = __ldcg(eng.target + p);
-    am[p] = __ldcg(eng.adam_m + p);
-    av[p] = __ldcg(eng.adam_v + p);
+    if (p >= p0 && p < p0 + S) {
+      am[p - p0] = __ldcg(eng.adam_m + p);
+      av[p - p0] = __ldcg(eng.adam_v + p);
+    }
   }
-  __syncthreads();
+  cluster.sync();  // mbarriers initialised and every CTA's shared memory ready before any remote store
 
-  // row r of the online set / target set -> its place in the tile activation areas
+  // local row r of the online set / target set -> its place in the tile activation areas
   auto x_row = [&](int set_tile0, int r) -> float* {
     return acts + (size_t)(set_tile0 + r / kRowTile) * np.act_floats + np.x_s[0] + (r % kRowTile) * np.ldx[0];
   };
   const uint64_t g_next = vec_steps;
   const uint64_t g_lo = g_next > (uint64_t)R ? g_next - R : 0;
   const uint32_t n_valid = (uint32_t)((g_next - (uint64_t)(M - 1) - g_lo) * E);
+  const uint32_t g_lo_mod = (uint32_t)(g_lo % (uint64_t)R), g_last_mod = (uint32_t)((vec_steps - 1) % (uint64_t)R);
   const float b1 = (float)eng.adam_beta1, b2 = (float)eng.adam_beta2, aeps = (float)eng.adam_eps;
   float* disc_pow = red + 32;  // multi_discounts (rainbow.py:175): float32 of discount ** k
   if (tid < M) disc_pow[tid] = (float)pow(eng.discount, (double)tid);
+  if (warp == 1) small_sample(eng, tc0, B, n_valid, g_lo_mod, pick, slot);  // slots of the first update
   __syncthreads();
+  const uint32_t mb_rs = smem_u32(&mbar[0]), mb_ag = smem_u32(&mbar[1]);
+  const int nbM = nb * M;
+  const bool one_warp = nbM <= 32;  // the CTA's window steps fit one warp: gather / padding / copy need no block barrier
+  float* wnew = reinterpret_cast<float*>(smem + pl.off_wnew);
 
   for (uint32_t upd = 0; upd < n_updates; ++upd) {
     const uint64_t tc = tc0 + upd;
-    // ---------------------------------------------------------------- 1. sample
+    const uint32_t par = upd & 1;
+    const int* slot_t = slot + par * B;  // sampled during the previous update's target phase
     SRLX_SMSTAMP(0);
-    if (warp == 0) {
-      for (int i = lane; i < B; i += 32) {
-        const uint4 w = philox(eng.seed, STREAM_UNIFORM_SAMPLE, (uint32_t)i, (uint32_t)tc, (uint32_t)(tc >> 32));
-        pick[i] = (int)u_below(w.x, n_valid);
-      }
-      __syncwarp();
-      bool dup = false;  // does any pick repeat an earlier one?  (rare: B^2 / (2 n_valid))
-      for (int i = lane; i < B; i += 32) {
-        const int pi = pick[i];
-        for (int j = 0; j < i; ++j) dup |= (pick[j] == pi);
-      }
-      if (__any_sync(0xffffffffu, dup)) {
-        if (lane == 0) {
-          for (int i = 1; i < B; ++i) {  // a repeated pick is redrawn (attempt k = 1, 2, ...), in sample order
-            int k = 0;
-            while (true) {
-              bool d2 = false;
-              for (int j = 0; j < i; ++j) d2 |= (pick[j] == pick[i]);
-              if (!d2 || ++k >= 65536) break;
-              const uint4 w = philox(eng.seed, STREAM_UNIFORM_SAMPLE, (uint32_t)i | ((uint32_t)k << 16), (uint32_t)tc, (uint32_t)(tc >> 32));
-              pick[i] = (int)u_below(w.x, n_valid);
+    // ---------------------------------------------------------------- 2. gather the CTA's items (loads before stores)
+    if (!one_warp || warp == 0) {
+      for (int w = tid; w < nbM; w += kSmThreads) {
+        const int il = w / M, k = w - il * M;
+        const int s0 = slot_t[i0 + il];
+        const int rho = s0 / E, e = s0 - rho * E;
+        const int sk = ((rho + k) % R) * E + e;
+        const int a = __ldcg(eng.ring_action + sk);
+        const float rw = __ldcg(eng.ring_reward + sk);
+        const unsigned char tm = __ldcg(eng.ring_term + sk), dn = __ldcg(eng.ring_done + sk);
+        float* xt = x_row(pl.n_on_tiles, w);
+        float* xs = x_row(0, il);
+        if (D <= 4) {
+          float xv[4], sv[4];
+#pragma unroll
+          for (int d = 0; d < 4; ++d) {
+            xv[d] = d < D ? __ldcg(eng.ring_next_obs + (size_t)sk * D + d) : 0.f;
+            sv[d] = (d < D && k == 0) ? __ldcg(eng.ring_obs + (size_t)s0 * D + d) : 0.f;
+          }
+#pragma unroll
+          for (int d = 0; d < 4; ++d)
+            if (d < D) {
+              xt[d] = xv[d];
+              if (k == 0) xs[d] = sv[d];
             }
+        } else {
+#pragma unroll 1
+          for (int d = 0; d < D; ++d) {
+            xt[d] = __ldcg(eng.ring_next_obs + (size_t)sk * D + d);
+            if (k == 0) xs[d] = __ldcg(eng.ring_obs + (size_t)s0 * D + d);
           }
         }
-        __syncwarp();
+        w_act[w] = a;
+        w_rew[w] = rw;
+        w_term[w] = (float)tm;
+        w_done[w] = (int)dn;
       }
-      for (int i = lane; i < B; i += 32) {
-        const uint64_t pk = (uint64_t)pick[i];
-        const uint64_t g = g_lo + pk / E;
-        slot[i] = (int)((g % R) * E + pk % E);
-      }
-    } else if (tid == 32) {
-      // Adam bias corrections of this update (torch/optim/adam.py: 1 - beta ** step), off the critical path
-      const double t = (double)(adam0 + upd + 1);
-      sc->step_size = (float)(eng.lr / (1.0 - pow(eng.adam_beta1, t)));
-      sc->bc2_sqrt = (float)sqrt(1.0 - pow(eng.adam_beta2, t));
     }
-    __syncthreads();
-    SRLX_SMSTAMP(1);
-    // ---------------------------------------------------------------- 2. gather (all loads of a record before its stores)
-    for (int w = tid; w < BM; w += kSmThreads) {
-      const int i = w / M, k = w - i * M;
-      const int s0 = slot[i];
-      const int rho = s0 / E, e = s0 - rho * E;
-      const int sk = ((rho + k) % R) * E + e;
-      const int a = __ldcg(eng.ring_action + sk);
-      const float rw = __ldcg(eng.ring_reward + sk);
-      const unsigned char tm = __ldcg(eng.ring_term + sk), dn = __ldcg(eng.ring_done + sk);
-      float xv[SRLX_MAX_OBS];
-#pragma unroll
-      for (int d = 0; d < SRLX_MAX_OBS; ++d) xv[d] = d < D ? __ldcg(eng.ring_next_obs + (size_t)sk * D + d) : 0.f;
-      w_act[w] = a;
-      w_rew[w] = rw;
-      w_term[w] = (float)tm;
-      w_done[w] = (int)dn;
-      float* xt = x_row(pl.n_on_tiles, w);
-#pragma unroll
-      for (int d = 0; d < SRLX_MAX_OBS; ++d)
-        if (d < D) xt[d] = xv[d];
-    }
-    for (int w = tid; w < B * D; w += kSmThreads) {
-      const int i = w / D, d = w - i * D;
-      x_row(0, i)[d] = __ldcg(eng.ring_obs + (size_t)slot[i] * D + d);
-    }
-    __syncthreads();
-    SRLX_SMSTAMP(2);
-    // padded tails (rainbow.py:358-371), then the online copy of the next states
-    for (int i = tid; i < B; i += kSmThreads) {
-      const int s0 = slot[i];
-      const int rho = s0 / E, e = s0 - rho * E;
-      const uint64_t g_last = vec_steps - 1;
-      const uint64_t g_item = g_last - ((g_last + (uint64_t)R - (uint64_t)rho) % (uint64_t)R);
-      bool ended = false;
-      int last_k = 0;
-      for (int k = 0; k < M; ++k) {
-        const int w = i * M + k;
-        if (!ended) {
-          last_k = k;
-          if (w_done[w]) ended = true;
-        } else {
-          const uint64_t gp = g_item + (uint64_t)k;
-          const uint4 pw = philox(eng.seed, STREAM_PAD_ACTION, (uint32_t)e, (uint32_t)gp, (uint32_t)(gp >> 32));
-          w_act[w] = (int)u_below(pw.x, (uint32_t)A);
-          w_rew[w] = 0.f;
-          w_term[w] = 1.f;
-          const float* src = x_row(pl.n_on_tiles, i * M + last_k);
-          float* dst = x_row(pl.n_on_tiles, w);
-          for (int d = 0; d < D; ++d) dst[d] = src[d];
+    if (one_warp) __syncwarp(); else __syncthreads();
+    // padded tails (rainbow.py:358-371)
+    if (M > 1 && (!one_warp || warp == 0)) {
+      for (int il = tid; il < nb; il += kSmThreads) {
+        const int s0 = slot_t[i0 + il];
+        const int rho = s0 / E, e = s0 - rho * E;
+        const uint64_t g_item = (vec_steps - 1) - (uint64_t)((g_last_mod + (uint32_t)R - (uint32_t)rho) % (uint32_t)R);
+        bool ended = false;
+        int last_k = 0;
+#pragma unroll 1
+        for (int k = 0; k < M; ++k) {
+          const int w = il * M + k;
+          if (!ended) {
+            last_k = k;
+            if (w_done[w]) ended = true;
+          } else {
+            const uint64_t gp = g_item + (uint64_t)k;
+            const uint4 pw = philox(eng.seed, STREAM_PAD_ACTION, (uint32_t)e, (uint32_t)gp, (uint32_t)(gp >> 32));
+            w_act[w] = (int)u_below(pw.x, (uint32_t)A);
+            w_rew[w] = 0.f;
+            w_term[w] = 1.f;
+            const float* src = x_row(pl.n_on_tiles, il * M + last_k);
+            float* dst = x_row(pl.n_on_tiles, w);
+            for (int d = 0; d < D; ++d) dst[d] = src[d];
+          }
         }
       }
+      if (one_warp) __syncwarp(); else __syncthreads();
     }
-    __syncthreads();
-    if (need_online_next)
-      for (int w = tid; w < BM * D; w += kSmThreads) {
+    if (need_online_next && (!one_warp || warp == 0))
+      for (int w = tid; w < nbM * D; w += (one_warp ? 32 : kSmThreads)) {
         const int r = w / D, d = w - r * D;
-        x_row(0, B + r)[d] = x_row(pl.n_on_tiles, r)[d];
+        x_row(0, Bc + r)[d] = x_row(pl.n_on_tiles, r)[d];
       }
-    if (eng.dbg_sample_idx)
-      for (int i = tid; i < B; i += kSmThreads) eng.dbg_sample_idx[i] = (int64_t)slot[i];
-    if (eng.dbg_weights)
-      for (int i = tid; i < B; i += kSmThreads) eng.dbg_weights[i] = 1.0f;
-    if (eng.dbg_windows) {
+    __syncthreads();
+    if (eng.dbg_windows) {  // debug taps (tests): sampled slots, weights, rebuilt windows
       float* dw = eng.dbg_windows;
-      const int n_states = B * (M + 1) * D;
-      for (int w = tid; w < n_states; w += kSmThreads) {
-        const int i = w / ((M + 1) * D), rem = w - i * (M + 1) * D, k = rem / D, d = rem - k * D;
-        dw[w] = (k == 0) ? x_row(0, i)[d] : x_row(pl.n_on_tiles, i * M + k - 1)[d];
+      const int n_states = B * (M + 1) * D, BM = B * M;
+      for (int w = tid; w < nb * (M + 1) * D; w += kSmThreads) {
+        const int il = w / ((M + 1) * D), rem = w - il * (M + 1) * D, k = rem / D, d = rem - k * D;
+        dw[(size_t)i0 * (M + 1) * D + w] = (k == 0) ? x_row(0, il)[d] : x_row(pl.n_on_tiles, il * M + k - 1)[d];
       }
-      for (int w = tid; w < BM; w += kSmThreads) {
-        dw[n_states + w] = (float)w_act[w];
-        dw[n_states + BM + w] = w_rew[w];
-        dw[n_states + 2 * BM + w] = w_term[w];
+      for (int w = tid; w < nbM; w += kSmThreads) {
+        dw[n_states + i0 * M + w] = (float)w_act[w];
+        dw[n_states + BM + i0 * M + w] = w_rew[w];
+        dw[n_states + 2 * BM + i0 * M + w] = w_term[w];
+      }
+      for (int il = tid; il < nb; il += kSmThreads) {
+        if (eng.dbg_sample_idx) eng.dbg_sample_idx[i0 + il] = (int64_t)slot_t[i0 + il];
+        if (eng.dbg_weights) eng.dbg_weights[i0 + il] = 1.0f;
       }
     }
-    __syncthreads();
     SRLX_SMSTAMP(3);
-    // ---------------------------------------------------------------- 3. forward, every tile of a layer concurrently
+    // ---------------------------------------------------------------- 3. forward: the row tiles of a layer spread over the warps
     auto tile_rows = [&](int t) -> int {
-      const int rows = t < pl.n_on_tiles ? pl.n_on_rows - t * kRowTile : BM - (t - pl.n_on_tiles) * kRowTile;
+      const int rows = t < pl.n_on_tiles ? pl.n_on_rows - t * kRowTile : BcM - (t - pl.n_on_tiles) * kRowTile;
       return rows < kRowTile ? rows : kRowTile;
     };
+#pragma unroll 1
     for (int l = 0; l < L - 1; ++l) {
       const int U = net.out_dim[l], K = net.k_dim[l];
-      const int n_ut = (U + 63) >> 6, n_rt = kRowTile / 4;
-      for (int t = warp; t < pl.n_tiles * n_rt * n_ut; t += nwarps) {
-        const int tile = t / (n_rt * n_ut), rem = t - tile * n_rt * n_ut, rt = rem / n_ut, ut = rem - rt * n_ut;
+      const int n_ut = (U + 31) >> 5;
+      int base = 0;  // tasks (tile, 4-row group, 32-unit group) are dealt round-robin across the tiles
+#pragma unroll 1
+      for (int tile = 0; tile < pl.n_tiles; ++tile) {
         const int Rt = tile_rows(tile);
-        if (rt * 4 >= Rt) continue;
+        const int n_task = ((Rt + 3) >> 2) * n_ut;
         const float* wset = tile < pl.n_on_tiles ? weff : wefft;
         float* a = acts + (size_t)tile * np.act_floats;
-        dense_relu_task(a + np.x_s[l], np.ldx[l], Rt, K, wset + np.w_s[l], np.ldw[l], wset + np.b_s[l], U, a + np.x_s[l + 1],
-                        np.ldx[l + 1], rt, ut);
+        int t = warp - (base & (nwarps - 1));
+        if (t < 0) t += nwarps;
+#pragma unroll 1
+        for (; t < n_task; t += nwarps) {
+          const int rt = t / n_ut, ut = t - rt * n_ut;
+          dense_relu_task32(a + np.x_s[l], np.ldx[l], Rt, K, wset + np.w_s[l], np.ldw[l], wset + np.b_s[l], U, a + np.x_s[l + 1],
+                            np.ldx[l + 1], rt, ut);
+        }
+        base += n_task;
       }
       __syncthreads();
     }
     SRLX_SMSTAMP(4);
+#pragma unroll 1
     for (int tile = 0; tile < pl.n_tiles; ++tile) {
       const float* wset = tile < pl.n_on_tiles ? weff : wefft;
       float* a = acts + (size_t)tile * np.act_floats;
@@ -522,130 +654,194 @@ learner_small_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_u
                       a + np.x_s[L], np.ldx[L]);
     }
     __syncthreads();
+#pragma unroll 1
     for (int tile = 0; tile < pl.n_tiles; ++tile) {
       float* a = acts + (size_t)tile * np.act_floats;
-      // Q rows: online set first ([0, n_on_rows)), target rows at B + BM
-      float* q = tile < pl.n_on_tiles ? Q + (size_t)tile * kRowTile * A : Q + (size_t)(B + BM + (tile - pl.n_on_tiles) * kRowTile) * A;
+      // Q rows: online set first ([0, n_on_rows)), target rows at Bc + BcM
+      float* q = tile < pl.n_on_tiles ? Q + (size_t)tile * kRowTile * A : Q + (size_t)(Bc + BcM + (tile - pl.n_on_tiles) * kRowTile) * A;
       small_dueling(net, a + np.x_s[L], np.ldx[L], tile_rows(tile), q, A);
     }
     __syncthreads();
     SRLX_SMSTAMP(5);
-    // ---------------------------------------------------------------- 4. targets, Huber gradient (thread per sample)
-    {
-      const float* qon = Q + (size_t)B * A;         // online(s')  [BM][A]
-      const float* qtg = Q + (size_t)(B + BM) * A;  // target(s')  [BM][A]
+    // ---------------------------------------------------------------- 4. targets, Huber gradient (thread per local item) | next sample
+    if (warp == 0) {
+      const float* qon = Q + (size_t)Bc * A;          // online(s')  [BcM][A]
+      const float* qtg = Q + (size_t)(Bc + BcM) * A;  // target(s')  [BcM][A]
       float lsum = 0.f;
-      for (int i = tid; i < B; i += kSmThreads) {
+      for (int il = lane; il < nb; il += 32) {
         const float gamma = (float)eng.discount;
         float target = 0.f, retrace = 1.f;
+#pragma unroll 1
         for (int k = 0; k < M; ++k) {
-          const float* qo = qon + (size_t)(i * M + k) * A;
-          const float* qt = qtg + (size_t)(i * M + k) * A;
+          const float* qo = qon + (size_t)(il * M + k) * A;
+          const float* qt = qtg + (size_t)(il * M + k) * A;
           const float* qsel = eng.enable_double_dqn ? qo : qt;
           int amx = 0;
           float best = qsel[0];
           for (int a = 1; a < A; ++a)
             if (qsel[a] > best) { best = qsel[a]; amx = a; }  // np.argmax: first max wins
           // Retrace with the reference's index shift (rainbow.py:267): action taken at s_k vs greedy action at s_{k+1}
-          if (k >= 1) retrace = retrace * ((float)eng.retrace_h * ((w_act[i * M + k] == amx) ? 1.f : 0.f));
+          if (k >= 1) retrace = retrace * ((float)eng.retrace_h * ((w_act[il * M + k] == amx) ? 1.f : 0.f));
           float maxq = qt[amx];
           if (eng.enable_rescale) maxq = inverse_rescaling_f(maxq);
-          float gain = w_rew[i * M + k] + ((1.0f - w_term[i * M + k]) * gamma) * maxq;
+          float gain = w_rew[il * M + k] + ((1.0f - w_term[il * M + k]) * gamma) * maxq;
           if (eng.enable_rescale) gain = rescaling_f(gain);
           float qk = 0.f;  // the first step is learnt by the trainer itself (rainbow.py:232-234)
-          if (k >= 1) qk = qon[(size_t)(i * M + k - 1) * A + w_act[i * M + k]];
+          if (k >= 1) qk = qon[(size_t)(il * M + k - 1) * A + w_act[il * M + k]];
           const float td = gain - qk;
           target += (td * disc_pow[k]) * retrace;
         }
-        tq[i] = target;
-        const int a0 = w_act[i * M + 0];
-        const float q = Q[i * A + a0];
-        qsa[i] = q;
+        tq[il] = target;
+        const int a0 = w_act[il * M + 0];
+        const float q = Q[il * A + a0];
+        qsa[il] = q;
         const float d = q - target;  // IS weight 1 on uniform replay (replay_buffer.py:37)
         const float ad = fabsf(d);
         const float delta = (float)eng.huber_delta;
         lsum += (ad <= delta) ? 0.5f * d * d : delta * (ad - 0.5f * delta);
         const float dq = fminf(fmaxf(d, -delta), delta) / (float)B;
-        for (int a = 0; a < A; ++a) dQ[i * A + a] = (a == a0) ? dq : 0.f;
+        for (int a = 0; a < A; ++a) dQ[il * A + a] = (a == a0) ? dq : 0.f;
+        if (eng.dbg_target_q) eng.dbg_target_q[i0 + il] = target;
+        if (eng.dbg_q_sa) eng.dbg_q_sa[i0 + il] = q;
       }
       for (int s = 16; s > 0; s >>= 1) lsum += __shfl_xor_sync(0xffffffffu, lsum, s);
-      if (lane == 0) red[warp] = lsum;
+      // the CTA's partial Huber sum -> CTA 0 (rides on the reduce-scatter barrier)
+      if (lane == 0) sm_st_async_f2(sm_mapa(smem_u32(lossbuf + 2 * rank), 0u), lsum, 0.f, sm_mapa(mb_rs, 0u));
+    } else if (warp == 1) {
+      if (upd + 1 < n_updates) small_sample(eng, tc + 1, B, n_valid, g_lo_mod, pick, slot + (par ^ 1) * B);
+    } else if (tid == 64) {
+      small_adam_scalars(eng, (double)(adam0 + upd + 1), sc);
     }
     __syncthreads();
-    if (tid == 0) {
-      double l = 0.0;
-      for (int w = 0; w < nwarps; ++w) l += (double)red[w];
-      l /= (double)B;
-      sc->last_loss = l;
-      sc->loss_sum += l;
-      if ((tc % (uint64_t)eng.target_update_interval) == 0) sc->sync_count += 1;
-    }
-    if (eng.dbg_target_q)
-      for (int i = tid; i < B; i += kSmThreads) eng.dbg_target_q[i] = tq[i];
-    if (eng.dbg_q_sa)
-      for (int i = tid; i < B; i += kSmThreads) eng.dbg_q_sa[i] = qsa[i];
     SRLX_SMSTAMP(6);
-    // ---------------------------------------------------------------- 5. backward on the s rows (G was zeroed by Adam)
+    // ---------------------------------------------------------------- 5. backward on the CTA's s rows (G zero since the last scatter)
+#pragma unroll 1
     for (int tile = 0; tile < pl.n_s_tiles; ++tile) {
-      const int Rt = min(kRowTile, B - tile * kRowTile);
+      const int Rt = min(kRowTile, Bc - tile * kRowTile);
       small_backward_tile(net, np, weff, acts + (size_t)tile * np.act_floats, Rt, dQ + (size_t)tile * kRowTile * A, A, G);
     }
+    sm_fence_proxy_async();  // this thread's gradient stores -> visible to the bulk-copy (async) proxy
     __syncthreads();
     SRLX_SMSTAMP(7);
-    // ---------------------------------------------------------------- 6. Adam, target sync
+    // ---------------------------------------------------------------- 6. reduce-scatter the partial gradients, Adam on the slice
     {
+      if (tid == 0) {  // one bulk DSMEM copy per owner: slice c of the local gradient -> row `rank` of the owner's receive buffer
+        for (int c = 0; c < C; ++c)
+          sm_bulk_s2c(sm_mapa(smem_u32(recv + (size_t)rank * S), (uint32_t)c), G + (size_t)c * S, (uint32_t)S * 4, sm_mapa(mb_rs, (uint32_t)c));
+      }
+      if (warp == 0) mbar_wait_sleep(&mbar[0], par);
+      __syncthreads();
+      if (tid == 0) {
+        if (rank == 0) {  // the partial losses are read BEFORE this CTA's all-gather copies leave: no peer can be a phase ahead
+          double l = 0.0;
+          for (int c = 0; c < C; ++c) l += (double)lossbuf[2 * c];
+          l /= (double)B;
+          sc->last_loss = l;
+          sc->loss_sum += l;
+          if ((tc % (uint64_t)eng.target_update_interval) == 0) sc->sync_count += 1;
+        }
+        sm_expect_tx(&mbar[0], (uint32_t)(C * S * 4 + (rank == 0 ? C * 8 : 0)));  // arm the next phase
+      }
       const float step_size = sc->step_size, bc2_sqrt = sc->bc2_sqrt;
+      for (int j = tid; j < S; j += kSmThreads) {
+        float g = 0.f;
+        for (int c = 0; c < C; ++c) g += recv[(size_t)c * S + j];  // CTA order: deterministic
+        const int p = p0 + j;
+        float w = p < P ? weff[pslot[p]] : 0.f, m = am[j], v = av[j];
+        adam_apply(w, m, v, g, b1, b2, aeps, step_size, bc2_sqrt);
+        am[j] = m;
+        av[j] = v;
+        wnew[j] = w;
+        if (eng.dbg_grads && p < P) eng.dbg_grads[p] = g;
+      }
+      sm_fence_proxy_async();
+      __syncthreads();
+      if (tid == 0) {  // all-gather: the updated slice into every CTA's flat parameter copy
+        for (int c = 0; c < C; ++c)
+          sm_bulk_s2c(sm_mapa(smem_u32(wflat + (size_t)p0), (uint32_t)c), wnew, (uint32_t)S * 4, sm_mapa(mb_ag, (uint32_t)c));
+      }
+    }
+    SRLX_SMSTAMP(8);
+    // ---------------------------------------------------------------- 7. new parameters into the weight copies, target sync
+    {
+      if (warp == 0) mbar_wait_sleep(&mbar[1], par);
+      __syncthreads();
+      if (tid == 0) sm_expect_tx(&mbar[1], (uint32_t)(C * S * 4));
       const bool do_sync = (tc % (uint64_t)eng.target_update_interval) == 0;
       for (int p = tid; p < P; p += kSmThreads) {
         const int s = pslot[p];
-        const float g = G[p];
-        if (eng.dbg_grads) eng.dbg_grads[p] = g;
-        float mu = weff[s], m = am[p], v = av[p];
-        adam_apply(mu, m, v, g, b1, b2, aeps, step_size, bc2_sqrt);
-        weff[s] = mu;
-        am[p] = m;
-        av[p] = v;
-        G[p] = 0.f;
-        if (do_sync) wefft[s] = mu;  // hard sync after the step, before train_count += 1 (model_torch.py:126-132)
+        const float w = wflat[p];
+        weff[s] = w;
+        if (do_sync) wefft[s] = w;  // hard sync after the step, before train_count += 1 (model_torch.py:126-132)
       }
+      // every peer has finished its Adam (its all-gather copy arrived), so it has consumed this CTA's gradient slices
+      for (int i = tid; i < (C * S) >> 2; i += kSmThreads) reinterpret_cast<float4*>(G)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
     __syncthreads();
-    SRLX_SMSTAMP(8);
+    SRLX_SMSTAMP(9);
   }
 
-  // ---- write the state back ----------------------------------------------------------------------------------------
-  for (int p = tid; p < P; p += kSmThreads) {
-    const int s = pslot[p];
-    __stcg(eng.params + p, weff[s]);
-    __stcg(eng.target + p, wefft[s]);
-    __stcg(eng.adam_m + p, am[p]);
-    __stcg(eng.adam_v + p, av[p]);
+  // ---- write the state back: every CTA its slice -----------------------------------------------------------------------
+  for (int j = tid; j < S; j += kSmThreads) {
+    const int p = p0 + j;
+    if (p < P) {
+      const int s = pslot[p];
+      __stcg(eng.params + p, weff[s]);
+      __stcg(eng.target + p, wefft[s]);
+      __stcg(eng.adam_m + p, am[j]);
+      __stcg(eng.adam_v + p, av[j]);
+    }
   }
-  if (tid == 0) {
+  if (rank == 0 && tid == 0) {
     st->train_count = tc0 + n_updates;
     st->adam_step = adam0 + n_updates;
     st->last_loss = sc->last_loss;
     st->loss_sum += sc->loss_sum;
     st->sync_count += sc->sync_count;
   }
+  cluster.sync();  // no CTA may exit while a peer can still address its shared memory
 }
 
-// 1 when the single-block kernel applies to this engine and fits the shared memory of one SM
-int small_choose(const srlx_engine* eng, size_t* smem_out) {
+// Cluster size for the row-split kernel: SRLX_SMALL_CLUSTER or 4, halved until the batch gives every CTA an item and the
+// plan fits one SM's shared memory.  Returns 0 when the kernel does not apply.
+int small_choose(const srlx_engine* eng, size_t* smem_out, int* C_out) {
   if (!small_shape_ok(*eng)) return 0;
   int dev = 0, max_smem = 0;
   SRLX_CHECK_CUDA(cudaGetDevice(&dev));
   SRLX_CHECK_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-  const SPlan pl = make_splan(*eng);
-  if ((long long)pl.total + 1024 > max_smem) return 0;
-  if (smem_out) *smem_out = pl.total;
-  return 1;
+  int want = 4;
+  if (const char* e = getenv("SRLX_SMALL_CLUSTER")) want = atoi(e);
+  if (want < 1) want = 1;
+  if (want > kSmMaxCluster) want = kSmMaxCluster;
+  for (int C = want; C >= 1; --C) {
+    if ((C & (C - 1)) != 0 || C > eng->batch_size) continue;
+    const SPlan pl = make_splan(*eng, C);
+    if ((long long)pl.total + 1024 > max_smem || pl.np.weff_floats > 65535) continue;
+    if (smem_out) *smem_out = pl.total;
+    if (C_out) *C_out = C;
+    return 1;
+  }
+  return 0;
 }
 
 int learn_small(const srlx_engine* eng, uint32_t n_updates, uintptr_t cuda_stream) {
-  const SPlan pl = make_splan(*eng);
-  SRLX_CHECK_CUDA(cudaFuncSetAttribute(learner_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.total));
-  learner_small_kernel<<<1, kSmThreads, pl.total, (cudaStream_t)cuda_stream>>>(*eng, n_updates);
+  size_t total = 0;
+  int C = 0;
+  SRLX_REQUIRE(small_choose(eng, &total, &C) == 1, "learn_small: the row-split learner does not apply to this engine");
+  SRLX_CHECK_CUDA(cudaFuncSetAttribute(learner_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)total));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)C, 1, 1);
+  cfg.blockDim = dim3(kSmThreads, 1, 1);
+  cfg.dynamicSmemBytes = total;
+  cfg.stream = (cudaStream_t)cuda_stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)C;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  SRLX_CHECK_CUDA(cudaLaunchKernelEx(&cfg, learner_small_kernel, *eng, n_updates));
   count_launch();
   SRLX_CHECK_CUDA(cudaGetLastError());
   return 0;

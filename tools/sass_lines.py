@@ -20,7 +20,7 @@ for ln in dis.splitlines():
         continue
     if re.match(r"\s*/\*[0-9a-f]{4,}\*/", ln) and cur:
         files[cur[0]] += 1
-        if cur[0].startswith("learner_fast"):
+        if cur[0].startswith("learner_fast") or cur[0].startswith("learner_small"):
             cnt[cur[1] // bucket * bucket] += 1
         else:
             cnt[cur[0]] += 1
