@@ -39,7 +39,7 @@ struct SPlan {
   NetPlan np;
   int C, B, Bc, M, A, D, BcM, P, S;  // Bc = items per CTA, S = floats per parameter slice (multiple of 4), C * S >= P
   int n_on_rows, n_on_tiles, n_tg_tiles, n_tiles, n_s_tiles;
-  size_t off_mbar, off_weff, off_wefft, off_m, off_v, off_g, off_recv, off_wflat, off_wnew, off_slot, off_acts, off_q, off_dq, off_pick,
+  size_t off_mbar, off_weff, off_wefft, off_m, off_v, off_g, off_recv, off_wflat, off_wnew, off_slot, off_acts, off_dacts, off_q, off_dq, off_pick,
       off_win, off_tq, off_red, off_loss, off_scal, total;
 };
 
@@ -80,6 +80,7 @@ __host__ __device__ inline SPlan make_splan(const srlx_engine& eng, int C) {
   p.off_wnew = take((size_t)p.S * 4);        // the own slice after Adam (source of the all-gather copies)
   p.off_slot = take((size_t)C * p.S * 2);
   p.off_acts = take((size_t)p.n_tiles * p.np.act_floats * 4);
+  p.off_dacts = take((size_t)p.n_s_tiles * p.np.act_floats * 4);  // d loss / d activation of the s rows (same layout as acts)
   p.off_q = take((size_t)(p.Bc + 2 * p.BcM) * p.A * 4);  // Q(s) [Bc][A], online Q(s') [BcM][A], target Q(s') [BcM][A]
   p.off_dq = take((size_t)p.Bc * p.A * 4);
   p.off_pick = take((size_t)p.B * 4 * 3);                // picks, slots of update t and t+1 (all B items, every CTA)
@@ -207,9 +208,9 @@ __device__ __forceinline__ void small_dw(const float* __restrict__ dY, int ldy, 
   }
 }
 
-// X[r][k] <- (X[r][k] > 0) ? sum_u dY[r][u] * W[u][k] : 0                thread tile 2 rows x 4 inputs, 4 units per step
+// dX[r][k] = (X[r][k] > 0) ? sum_u dY[r][u] * W[u][k] : 0                thread tile 2 rows x 4 inputs, 4 units per step
 __device__ __forceinline__ void small_dx(const float* __restrict__ dY, int ldy, const float* __restrict__ W, int ldw,
-                                         float* __restrict__ X, int ldx, int R, int U, int K) {
+                                         const float* __restrict__ X, float* __restrict__ dX, int ldx, int R, int U, int K) {
   const int tid = threadIdx.x, nt = blockDim.x;
   const int n_kt = (K + 3) >> 2, n_rt = (R + 1) >> 1;
   const int U4 = U & ~3;
@@ -251,48 +252,66 @@ __device__ __forceinline__ void small_dx(const float* __restrict__ dY, int ldy, 
 #pragma unroll
     for (int b = 0; b < 4; ++b) {
       if (k0 + b < K) {
-        float* x0 = X + r0 * ldx + k0 + b;
-        *x0 = (*x0 > 0.f) ? acc[0][b] : 0.f;
+        const int o0 = r0 * ldx + k0 + b;
+        dX[o0] = (X[o0] > 0.f) ? acc[0][b] : 0.f;
         if (r0 + 1 < R) {
-          float* x1 = X + (r0 + 1) * ldx + k0 + b;
-          *x1 = (*x1 > 0.f) ? acc[1][b] : 0.f;
+          const int o1 = (r0 + 1) * ldx + k0 + b;
+          dX[o1] = (X[o1] > 0.f) ? acc[1][b] : 0.f;
         }
       }
     }
   }
 }
 
-// net.cuh::net_backward_tile with the two hidden-layer loops above; the output layer / dueling head (<= 17 rows) is unchanged
-__device__ inline void small_backward_tile(const srlx_net& net, const NetPlan& pl, const float* weff, float* acts, int R,
-                                           const float* dQ, int lddq, float* G) {
+// Backward of a row tile in two stages (same arithmetic as net.cuh::net_backward_tile, fewer block barriers):
+//   small_delta_chain: d loss / d (pre-activation) of every hidden layer, top down, into `dacts` (layout of `acts`); the
+//                      output layer's d raw was written there by the target step
+//   small_all_dw:      every layer's dW / db from (dacts, acts) in one barrier-free sweep
+__device__ inline void small_delta_chain(const srlx_net& net, const NetPlan& pl, const float* weff, const float* acts, float* dacts, int R,
+                                         long long* clk) {
   const int tid = threadIdx.x, nt = blockDim.x;
-  const int L = net.n_layers, A = net.n_actions;
+  const int L = net.n_layers;
   const int nout = net.out_dim[L - 1], Ko = net.k_dim[L - 1];
-  float* raw = acts + pl.x_s[L];
+  const float* raw = dacts + pl.x_s[L];
   const int ldr = pl.ldx[L];
-  for (int r = tid; r < R; r += nt) {  // dueling combine backward (dueling_network.py:51-58) -> d raw
-    if (net.dueling == SRLX_DUEL_NONE) {
-      for (int a = 0; a < A; ++a) raw[r * ldr + a] = dQ[r * lddq + a];
-    } else {
-      float sum = 0.f;
-      for (int a = 0; a < A; ++a) sum += dQ[r * lddq + a];
-      int amax = 0;
-      if (net.dueling == SRLX_DUEL_MAX) {
-        float best = raw[r * ldr + 1];
-        for (int a = 1; a < A; ++a)
-          if (raw[r * ldr + 1 + a] > best) { best = raw[r * ldr + 1 + a]; amax = a; }
+  {  // d hidden (input of the output layer), ReLU-masked
+    const float* X = acts + pl.x_s[L - 1];
+    float* dX = dacts + pl.x_s[L - 1];
+    const int ldx = pl.ldx[L - 1], width = pl.xw[L - 1];
+    const float* W = weff + pl.w_s[L - 1];
+    const int ldw = pl.ldw[L - 1];
+    for (int w = tid; w < R * width; w += nt) {
+      const int r = w / width, kk = w - r * width;
+      float d = 0.f;
+      if (net.dueling == SRLX_DUEL_NONE) {
+        for (int o = 0; o < nout; ++o) d = fmaf(raw[r * ldr + o], W[o * ldw + kk], d);
+      } else if (kk < Ko) {
+        d = raw[r * ldr + 0] * W[kk];
+      } else {
+        for (int o = 1; o < nout; ++o) d = fmaf(raw[r * ldr + o], W[o * ldw + (kk - Ko)], d);
       }
-      for (int a = 0; a < A; ++a) {
-        float d = dQ[r * lddq + a];
-        if (net.dueling == SRLX_DUEL_AVERAGE) d -= sum / (float)A;
-        else if (net.dueling == SRLX_DUEL_MAX && a == amax) d -= sum;
-        raw[r * ldr + 1 + a] = d;
-      }
-      raw[r * ldr + 0] = sum;
+      dX[r * ldx + kk] = (X[r * ldx + kk] > 0.f) ? d : 0.f;
     }
   }
   __syncthreads();
-  {  // output layer: dW, db
+  if (clk) clk[10] = clock64();
+#pragma unroll 1
+  for (int l = L - 2; l >= 1; --l) {  // delta of layer l-1's output from delta of layer l's output
+    small_dx(dacts + pl.x_s[l + 1], pl.ldx[l + 1], weff + pl.w_s[l], pl.ldw[l], acts + pl.x_s[l], dacts + pl.x_s[l], pl.ldx[l], R,
+             net.out_dim[l], net.k_dim[l]);
+    __syncthreads();
+  }
+  if (clk) clk[11] = clock64();
+}
+
+__device__ inline void small_all_dw(const srlx_net& net, const NetPlan& pl, const float* acts, const float* dacts, int R, float* G,
+                                    long long* clk) {
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const int L = net.n_layers;
+  const int nout = net.out_dim[L - 1], Ko = net.k_dim[L - 1];
+  const float* raw = dacts + pl.x_s[L];
+  const int ldr = pl.ldx[L];
+  {  // output layer
     const float* X = acts + pl.x_s[L - 1];
     const int ldx = pl.ldx[L - 1];
     for (int w = tid; w < nout * Ko; w += nt) {
@@ -308,36 +327,11 @@ __device__ inline void small_backward_tile(const srlx_net& net, const NetPlan& p
       G[net.b_off[L - 1] + o] += acc;
     }
   }
-  __syncthreads();
-  if (L > 1) {  // d hidden (input of the output layer), ReLU-masked, in place
-    float* X = acts + pl.x_s[L - 1];
-    const int ldx = pl.ldx[L - 1], width = pl.xw[L - 1];
-    const float* W = weff + pl.w_s[L - 1];
-    const int ldw = pl.ldw[L - 1];
-    for (int w = tid; w < R * width; w += nt) {
-      const int r = w / width, kk = w - r * width;
-      float d = 0.f;
-      if (net.dueling == SRLX_DUEL_NONE) {
-        for (int o = 0; o < nout; ++o) d = fmaf(raw[r * ldr + o], W[o * ldw + kk], d);
-      } else if (kk < Ko) {
-        d = raw[r * ldr + 0] * W[kk];
-      } else {
-        for (int o = 1; o < nout; ++o) d = fmaf(raw[r * ldr + o], W[o * ldw + (kk - Ko)], d);
-      }
-      X[r * ldx + kk] = (X[r * ldx + kk] > 0.f) ? d : 0.f;
-    }
-  }
-  __syncthreads();
-  for (int l = L - 2; l >= 0; --l) {  // hidden layers, top down
-    const float* dY = acts + pl.x_s[l + 1];
-    float* X = acts + pl.x_s[l];
-    small_dw(dY, pl.ldx[l + 1], X, pl.ldx[l], R, net.out_dim[l], net.k_dim[l], G + net.w_off[l], G + net.b_off[l]);
-    __syncthreads();
-    if (l > 0) {
-      small_dx(dY, pl.ldx[l + 1], weff + pl.w_s[l], pl.ldw[l], X, pl.ldx[l], R, net.out_dim[l], net.k_dim[l]);
-      __syncthreads();
-    }
-  }
+  if (clk) clk[12] = clock64();
+#pragma unroll 1
+  for (int l = L - 2; l >= 0; --l)
+    small_dw(dacts + pl.x_s[l + 1], pl.ldx[l + 1], acts + pl.x_s[l], pl.ldx[l], R, net.out_dim[l], net.k_dim[l], G + net.w_off[l],
+             G + net.b_off[l]);
 }
 
 // Output layer of a row tile, thread per (row, output): float4 dot products instead of a warp per row
@@ -360,6 +354,44 @@ __device__ inline void small_out_layer(const srlx_net& net, const float* __restr
       a3 = fmaf(xv.w, wv.w, a3);
     }
     raw[r * ldr + o] = ((a0 + a1) + (a2 + a3)) + b[o];
+  }
+}
+
+// Narrow heads (nout * K <= 512, e.g. DQN's 64 -> 2): one thread per row computes all raw outputs and the row's Q values,
+// saving the barrier between small_out_layer and small_dueling
+__device__ inline void small_out_q_row(const srlx_net& net, const float* __restrict__ xrow, const float* __restrict__ W, int ldw,
+                                       const float* __restrict__ b, float* __restrict__ rr, float* __restrict__ q) {
+  const int L = net.n_layers, nout = net.out_dim[L - 1], K = net.k_dim[L - 1], A = net.n_actions;
+  const int K4 = round_up(K, 4);
+#pragma unroll 1
+  for (int o = 0; o < nout; ++o) {
+    const int koff = (net.dueling != SRLX_DUEL_NONE && o > 0) ? K : 0;
+    const float* x = xrow + koff;
+    const float* wr = W + o * ldw;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    for (int k = 0; k < K4; k += 4) {
+      const float4 xv = *reinterpret_cast<const float4*>(x + k);
+      const float4 wv = *reinterpret_cast<const float4*>(wr + k);
+      a0 = fmaf(xv.x, wv.x, a0);
+      a1 = fmaf(xv.y, wv.y, a1);
+      a2 = fmaf(xv.z, wv.z, a2);
+      a3 = fmaf(xv.w, wv.w, a3);
+    }
+    rr[o] = ((a0 + a1) + (a2 + a3)) + b[o];
+  }
+  if (net.dueling == SRLX_DUEL_NONE) {
+    for (int a = 0; a < A; ++a) q[a] = rr[a];
+  } else {
+    const float v = rr[0];
+    float red = 0.f;
+    if (net.dueling == SRLX_DUEL_AVERAGE) {
+      for (int a = 0; a < A; ++a) red += rr[1 + a];
+      red = red / (float)A;
+    } else if (net.dueling == SRLX_DUEL_MAX) {
+      red = rr[1];
+      for (int a = 1; a < A; ++a) red = fmaxf(red, rr[1 + a]);
+    }
+    for (int a = 0; a < A; ++a) q[a] = v + rr[1 + a] - red;
   }
 }
 
@@ -451,6 +483,7 @@ learner_small_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_u
   float* wflat = reinterpret_cast<float*>(smem + pl.off_wflat);
   unsigned short* pslot = reinterpret_cast<unsigned short*>(smem + pl.off_slot);
   float* acts = reinterpret_cast<float*>(smem + pl.off_acts);
+  float* dacts = reinterpret_cast<float*>(smem + pl.off_dacts);
   float* Q = reinterpret_cast<float*>(smem + pl.off_q);
   float* dQ = reinterpret_cast<float*>(smem + pl.off_dq);
   int* pick = reinterpret_cast<int*>(smem + pl.off_pick);
@@ -481,6 +514,7 @@ learner_small_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_u
   for (int i = tid; i < pl.n_tiles * np.act_floats; i += kSmThreads) acts[i] = 0.f;
   for (int i = tid; i < C * S; i += kSmThreads) { G[i] = 0.f; wflat[i] = 0.f; pslot[i] = 0; }
   for (int i = tid; i < Bc * A; i += kSmThreads) dQ[i] = 0.f;
+  for (int i = tid; i < pl.n_s_tiles * np.act_floats; i += kSmThreads) dacts[i] = 0.f;
   for (int i = tid; i < S; i += kSmThreads) { am[i] = 0.f; av[i] = 0.f; }
   if (tid == 0) {
     sc->loss_sum = 0.0; sc->last_loss = 0.0; sc->sync_count = 0;
@@ -646,22 +680,36 @@ learner_small_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_u
       __syncthreads();
     }
     SRLX_SMSTAMP(4);
+    if (net.out_dim[L - 1] * net.k_dim[L - 1] <= 512) {
+      // all tiles' rows in one sweep: thread = (tile, row)
+      for (int w = tid; w < pl.n_tiles * kRowTile; w += kSmThreads) {
+        const int tile = w / kRowTile, r = w - tile * kRowTile;
+        if (r >= tile_rows(tile)) continue;
+        const float* wset = tile < pl.n_on_tiles ? weff : wefft;
+        float* a = acts + (size_t)tile * np.act_floats;
+        float* q = tile < pl.n_on_tiles ? Q + (size_t)tile * kRowTile * A : Q + (size_t)(Bc + BcM + (tile - pl.n_on_tiles) * kRowTile) * A;
+        small_out_q_row(net, a + np.x_s[L - 1] + r * np.ldx[L - 1], wset + np.w_s[L - 1], np.ldw[L - 1], wset + np.b_s[L - 1],
+                        a + np.x_s[L] + r * np.ldx[L], q + r * A);
+      }
+      __syncthreads();
+    } else {
 #pragma unroll 1
-    for (int tile = 0; tile < pl.n_tiles; ++tile) {
-      const float* wset = tile < pl.n_on_tiles ? weff : wefft;
-      float* a = acts + (size_t)tile * np.act_floats;
-      small_out_layer(net, a + np.x_s[L - 1], np.ldx[L - 1], tile_rows(tile), wset + np.w_s[L - 1], np.ldw[L - 1], wset + np.b_s[L - 1],
-                      a + np.x_s[L], np.ldx[L]);
-    }
-    __syncthreads();
+      for (int tile = 0; tile < pl.n_tiles; ++tile) {
+        const float* wset = tile < pl.n_on_tiles ? weff : wefft;
+        float* a = acts + (size_t)tile * np.act_floats;
+        small_out_layer(net, a + np.x_s[L - 1], np.ldx[L - 1], tile_rows(tile), wset + np.w_s[L - 1], np.ldw[L - 1], wset + np.b_s[L - 1],
+                        a + np.x_s[L], np.ldx[L]);
+      }
+      __syncthreads();
 #pragma unroll 1
-    for (int tile = 0; tile < pl.n_tiles; ++tile) {
-      float* a = acts + (size_t)tile * np.act_floats;
-      // Q rows: online set first ([0, n_on_rows)), target rows at Bc + BcM
-      float* q = tile < pl.n_on_tiles ? Q + (size_t)tile * kRowTile * A : Q + (size_t)(Bc + BcM + (tile - pl.n_on_tiles) * kRowTile) * A;
-      small_dueling(net, a + np.x_s[L], np.ldx[L], tile_rows(tile), q, A);
+      for (int tile = 0; tile < pl.n_tiles; ++tile) {
+        float* a = acts + (size_t)tile * np.act_floats;
+        // Q rows: online set first ([0, n_on_rows)), target rows at Bc + BcM
+        float* q = tile < pl.n_on_tiles ? Q + (size_t)tile * kRowTile * A : Q + (size_t)(Bc + BcM + (tile - pl.n_on_tiles) * kRowTile) * A;
+        small_dueling(net, a + np.x_s[L], np.ldx[L], tile_rows(tile), q, A);
+      }
+      __syncthreads();
     }
-    __syncthreads();
     SRLX_SMSTAMP(5);
     // ---------------------------------------------------------------- 4. targets, Huber gradient (thread per local item) | next sample
     if (warp == 0) {
@@ -700,7 +748,28 @@ learner_small_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_u
         const float delta = (float)eng.huber_delta;
         lsum += (ad <= delta) ? 0.5f * d * d : delta * (ad - 0.5f * delta);
         const float dq = fminf(fmaxf(d, -delta), delta) / (float)B;
-        for (int a = 0; a < A; ++a) dQ[il * A + a] = (a == a0) ? dq : 0.f;
+        {  // dueling combine backward (dueling_network.py:51-58) -> d raw of the s row, where the backward pass picks it up
+          const size_t trow = (size_t)(il / kRowTile) * np.act_floats + np.x_s[L] + (il % kRowTile) * np.ldx[L];
+          float* dr = dacts + trow;
+          if (net.dueling == SRLX_DUEL_NONE) {
+            for (int a = 0; a < A; ++a) dr[a] = (a == a0) ? dq : 0.f;
+          } else {
+            const float* fr = acts + trow;  // forward raw outputs of the row
+            int amax = 0;
+            if (net.dueling == SRLX_DUEL_MAX) {
+              float bestr = fr[1];
+              for (int a = 1; a < A; ++a)
+                if (fr[1 + a] > bestr) { bestr = fr[1 + a]; amax = a; }
+            }
+            for (int a = 0; a < A; ++a) {
+              float dd = (a == a0) ? dq : 0.f;
+              if (net.dueling == SRLX_DUEL_AVERAGE) dd -= dq / (float)A;
+              else if (net.dueling == SRLX_DUEL_MAX && a == amax) dd -= dq;
+              dr[1 + a] = dd;
+            }
+            dr[0] = dq;
+          }
+        }
         if (eng.dbg_target_q) eng.dbg_target_q[i0 + il] = target;
         if (eng.dbg_q_sa) eng.dbg_q_sa[i0 + il] = q;
       }
@@ -718,7 +787,10 @@ learner_small_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_u
 #pragma unroll 1
     for (int tile = 0; tile < pl.n_s_tiles; ++tile) {
       const int Rt = min(kRowTile, Bc - tile * kRowTile);
-      small_backward_tile(net, np, weff, acts + (size_t)tile * np.act_floats, Rt, dQ + (size_t)tile * kRowTile * A, A, G);
+      long long* clk = (eng.dbg_clock && rank == 0 && tid == 0 && upd + 2 == n_updates) ? eng.dbg_clock : nullptr;
+      small_delta_chain(net, np, weff, acts + (size_t)tile * np.act_floats, dacts + (size_t)tile * np.act_floats, Rt, clk);
+      small_all_dw(net, np, acts + (size_t)tile * np.act_floats, dacts + (size_t)tile * np.act_floats, Rt, G, clk);
+      if (clk) clk[13] = clock64();
     }
     sm_fence_proxy_async();  // this thread's gradient stores -> visible to the bulk-copy (async) proxy
     __syncthreads();
@@ -802,14 +874,14 @@ learner_small_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_u
   cluster.sync();  // no CTA may exit while a peer can still address its shared memory
 }
 
-// Cluster size for the row-split kernel: SRLX_SMALL_CLUSTER or 4, halved until the batch gives every CTA an item and the
+// Cluster size for the row-split kernel: SRLX_SMALL_CLUSTER or 8, halved until the batch gives every CTA an item and the
 // plan fits one SM's shared memory.  Returns 0 when the kernel does not apply.
 int small_choose(const srlx_engine* eng, size_t* smem_out, int* C_out) {
   if (!small_shape_ok(*eng)) return 0;
   int dev = 0, max_smem = 0;
   SRLX_CHECK_CUDA(cudaGetDevice(&dev));
   SRLX_CHECK_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-  int want = 4;
+  int want = 8;
   if (const char* e = getenv("SRLX_SMALL_CLUSTER")) want = atoi(e);
   if (want < 1) want = 1;
   if (want > kSmMaxCluster) want = kSmMaxCluster;

@@ -23,3 +23,15 @@ g.run(10, 0)
 g.learn(3)
 torch.cuda.synchronize()
 print("generic:", g.learner_info(), g.read_state().train_count)
+if os.environ.get("SAN_SMALL", "1") == "1":  # learner_small_kernel: uniform replay, plain weights, rows over an 8-CTA cluster
+    for kw3 in (dict(env="CartPole-v1", algo="dqn", hidden=(64, 64), mem_kind=0, multisteps=1, n_envs=64, ring_rows=8, batch_size=32,
+                     warmup_size=64, epsilon=0.2),
+                dict(env="Grid", algo="rainbow", hidden=(32, 16), dueling="average", noisy=False, mem_kind=0, multisteps=3, n_envs=24,
+                     ring_rows=9, batch_size=16, warmup_size=48, epsilon=0.3, enable_double_dqn=False)):
+        s = DeviceEngine(EngineConfig(**kw3))
+        s.run(12, 0)
+        s.learn(4)
+        s.vec_step()
+        s.learn(2)
+        torch.cuda.synchronize()
+        print("small:", s.learner_info(), s.read_state().train_count)
