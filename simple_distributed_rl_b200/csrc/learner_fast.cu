@@ -1100,27 +1100,47 @@ learner_fast_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_up
             named_bar_sync(FBAR_MEM, FNM);
           }
         } else {
-          // uniform replay: B distinct items (replay_buffer.py:34-36), sequential rejection
-          if (mt == 0) {
+          // uniform replay: B distinct items (replay_buffer.py:34-36).  Attempt 0 of every draw in parallel (B <= 32: one lane
+          // each); a pick that repeats an earlier one is redrawn (attempt k = 1, 2, ...) in sample order, which is exactly what
+          // the sequential rejection loop (oracle/sumtree.py::uniform_sample_distinct) produces
+          if (mt < 32) {
             const uint64_t g_next = vec_steps;
             const uint64_t g_lo = g_next > (uint64_t)R ? g_next - R : 0;
-            const uint64_t n_g = g_next - (uint64_t)(M - 1) - g_lo;
-            const uint32_t n_valid = (uint32_t)(n_g * E);
-            for (int i = 0; i < B; ++i) {
-              uint32_t pick = 0;
-              for (int k = 0; k < 65536; ++k) {
-                const uint4 w = philox_ni(eng.seed, STREAM_UNIFORM_SAMPLE, (uint32_t)i | ((uint32_t)k << 16), (uint32_t)tc, (uint32_t)(tc >> 32));
-                pick = u_below(w.x, n_valid);
-                bool dup = false;
-                for (int j = 0; j < i; ++j) dup |= (s_idx[j] == (int)pick);
-                if (!dup) break;
-              }
-              s_idx[i] = (int)pick;
+            const uint32_t n_g = (uint32_t)(g_next - (uint64_t)(M - 1) - g_lo);
+            const uint32_t n_valid = n_g * (uint32_t)E;
+            const uint32_t g_lo_mod = (uint32_t)(g_lo % (uint64_t)R);
+            int pick = -1 - mt;  // idle lanes hold distinct negative values
+            if (mt < B) {
+              const uint4 w = philox_ni(eng.seed, STREAM_UNIFORM_SAMPLE, (uint32_t)mt, (uint32_t)tc, (uint32_t)(tc >> 32));
+              pick = (int)u_below(w.x, n_valid);
             }
-            for (int i = 0; i < B; ++i) {
-              const uint64_t pick = (uint64_t)s_idx[i];
-              const uint64_t g = g_lo + pick / E;
-              s_idx[i] = (int)((g % R) * E + pick % E) + cap1;  // stored as if it were a tree index
+            bool dup = false;
+#pragma unroll 1
+            for (int j = 0; j < B; ++j) {
+              const int pj = __shfl_sync(FULL, pick, j);
+              dup |= (j < mt) & (pj == pick);
+            }
+            if (__any_sync(FULL, dup)) {  // rare (B^2 / (2 n_valid)): resolve in sample order on one lane
+              if (mt < B) s_idx[mt] = pick;
+              __syncwarp();
+              if (mt == 0) {
+                for (int i = 1; i < B; ++i) {
+                  int k = 0;
+                  while (true) {
+                    bool d2 = false;
+                    for (int j = 0; j < i; ++j) d2 |= (s_idx[j] == s_idx[i]);
+                    if (!d2 || ++k >= 65536) break;
+                    const uint4 w = philox_ni(eng.seed, STREAM_UNIFORM_SAMPLE, (uint32_t)i | ((uint32_t)k << 16), (uint32_t)tc, (uint32_t)(tc >> 32));
+                    s_idx[i] = (int)u_below(w.x, n_valid);
+                  }
+                }
+              }
+              __syncwarp();
+              if (mt < B) pick = s_idx[mt];
+            }
+            if (mt < B) {
+              const uint32_t pk = (uint32_t)pick, q = pk / (uint32_t)E;
+              s_idx[mt] = (int)(((g_lo_mod + q) % (uint32_t)R) * (uint32_t)E + (pk - q * (uint32_t)E)) + cap1;  // stored as if it were a tree index
             }
           }
           named_bar_sync(FBAR_MEM, FNM);

@@ -521,8 +521,8 @@ learner_small_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_u
     mbar_init(&mbar[0], 1);
     mbar_init(&mbar[1], 1);
     fence_mbar_init();
-    sm_expect_tx(&mbar[0], (uint32_t)(C * S * 4 + (rank == 0 ? C * 8 : 0)));
-    sm_expect_tx(&mbar[1], (uint32_t)(C * S * 4));
+    sm_expect_tx(&mbar[0], (uint32_t)((C - 1) * S * 4 + (rank == 0 ? C * 8 : 0)));
+    sm_expect_tx(&mbar[1], (uint32_t)((C - 1) * S * 4));
   }
   __syncthreads();
   for (int p = tid; p < P; p += kSmThreads) {
@@ -797,9 +797,14 @@ learner_small_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_u
     SRLX_SMSTAMP(7);
     // ---------------------------------------------------------------- 6. reduce-scatter the partial gradients, Adam on the slice
     {
-      if (tid == 0) {  // one bulk DSMEM copy per owner: slice c of the local gradient -> row `rank` of the owner's receive buffer
+      // slice c of the local gradient -> row `rank` of owner c's receive buffer: one bulk DSMEM copy per peer, plain stores
+      // for the own slice
+      for (int q = tid; q < (S >> 2); q += kSmThreads)
+        reinterpret_cast<float4*>(recv + (size_t)rank * S)[q] = reinterpret_cast<const float4*>(G + (size_t)rank * S)[q];
+      if (tid == 0) {
         for (int c = 0; c < C; ++c)
-          sm_bulk_s2c(sm_mapa(smem_u32(recv + (size_t)rank * S), (uint32_t)c), G + (size_t)c * S, (uint32_t)S * 4, sm_mapa(mb_rs, (uint32_t)c));
+          if (c != rank)
+            sm_bulk_s2c(sm_mapa(smem_u32(recv + (size_t)rank * S), (uint32_t)c), G + (size_t)c * S, (uint32_t)S * 4, sm_mapa(mb_rs, (uint32_t)c));
       }
       if (warp == 0) mbar_wait_sleep(&mbar[0], par);
       __syncthreads();
@@ -812,7 +817,7 @@ learner_small_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_u
           sc->loss_sum += l;
           if ((tc % (uint64_t)eng.target_update_interval) == 0) sc->sync_count += 1;
         }
-        sm_expect_tx(&mbar[0], (uint32_t)(C * S * 4 + (rank == 0 ? C * 8 : 0)));  // arm the next phase
+        sm_expect_tx(&mbar[0], (uint32_t)((C - 1) * S * 4 + (rank == 0 ? C * 8 : 0)));  // arm the next phase
       }
       const float step_size = sc->step_size, bc2_sqrt = sc->bc2_sqrt;
       for (int j = tid; j < S; j += kSmThreads) {
@@ -824,13 +829,14 @@ learner_small_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_u
         am[j] = m;
         av[j] = v;
         wnew[j] = w;
+        wflat[p0 + j] = w;  // the own slice of the flat copy; peers get it by bulk copy below
         if (eng.dbg_grads && p < P) eng.dbg_grads[p] = g;
       }
       sm_fence_proxy_async();
       __syncthreads();
-      if (tid == 0) {  // all-gather: the updated slice into every CTA's flat parameter copy
+      if (tid == 0) {  // all-gather: the updated slice into every peer's flat parameter copy
         for (int c = 0; c < C; ++c)
-          sm_bulk_s2c(sm_mapa(smem_u32(wflat + (size_t)p0), (uint32_t)c), wnew, (uint32_t)S * 4, sm_mapa(mb_ag, (uint32_t)c));
+          if (c != rank) sm_bulk_s2c(sm_mapa(smem_u32(wflat + (size_t)p0), (uint32_t)c), wnew, (uint32_t)S * 4, sm_mapa(mb_ag, (uint32_t)c));
       }
     }
     SRLX_SMSTAMP(8);
@@ -838,7 +844,7 @@ learner_small_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_u
     {
       if (warp == 0) mbar_wait_sleep(&mbar[1], par);
       __syncthreads();
-      if (tid == 0) sm_expect_tx(&mbar[1], (uint32_t)(C * S * 4));
+      if (tid == 0) sm_expect_tx(&mbar[1], (uint32_t)((C - 1) * S * 4));
       const bool do_sync = (tc % (uint64_t)eng.target_update_interval) == 0;
       for (int p = tid; p < P; p += kSmThreads) {
         const int s = pslot[p];
