@@ -229,6 +229,20 @@ int srlx_tree_update(double* tree, uint64_t capacity, srlx_state* meta, const in
 int srlx_tree_retrieve(const double* tree, uint64_t capacity, const double* vals_dev, uint32_t n,
                        int64_t* out_tree_idx, uintptr_t cuda_stream);
 
+/* ---- PPO worker-side returns (R15, the worker half) ------------------------------------------------------ */
+#define SRLX_RETURNS_GAE 0
+#define SRLX_RETURNS_MC 1
+/* ppo.Worker.on_step at episode end (srl/algorithms/ppo/ppo.py:357-406) over a time-major rollout buffer [n_steps][n_envs]:
+ * method GAE: out = delta + discount*gae_discount*out_next with delta = r - v at the last step of an episode, else
+ * r + discount*next_v - v (float32, the reference's rounding order); method MC: out = r + discount*out_next in float64
+ * (reward_f64_dev if given, else reward_dev), stored as float32.  done[t][e] != 0 ends an episode; steps after a column's
+ * last episode end are not emitted by the reference yet: out = 0, valid = 0 (valid_dev may be NULL) unless
+ * tail_is_episode_end.  clip_enable: reward clip to [clip_lo, clip_hi] first (ppo.py:362-367). */
+int srlx_returns_scan(const float* reward_dev, const double* reward_f64_dev, const float* value_dev, const float* next_value_dev,
+                      const unsigned char* done_dev, float* out_dev, unsigned char* valid_dev, uint32_t n_steps, uint32_t n_envs,
+                      double discount, double gae_discount, int method, int tail_is_episode_end, int clip_enable, double clip_lo,
+                      double clip_hi, uintptr_t cuda_stream);
+
 /* ---- engine (R1-R6, R8-R12) ------------------------------------------------------------------------------ */
 /* Zero the counters, mark every env for reset, clear ring flags and the tree. */
 int srlx_engine_reset(const srlx_engine* eng, uintptr_t cuda_stream);

@@ -7,6 +7,7 @@ LIB_PATH = os.environ.get("SRLX_LIB") or os.path.join(_HERE, "libsrlx.so")  # SR
 
 SRLX_MAX_LAYERS = 6
 ENV_GRID, ENV_CARTPOLE, ENV_PENDULUM = 0, 1, 2
+RETURNS_GAE, RETURNS_MC = 0, 1  # srlx_returns_scan methods
 DUEL_NONE, DUEL_AVERAGE, DUEL_MAX, DUEL_NAIVE = 0, 1, 2, 3
 MEM_UNIFORM, MEM_PROPORTIONAL = 0, 1
 NOISE_KIND_ROLLOUT, NOISE_KIND_TRAIN, NOISE_KIND_PRED = 0, 1, 3
@@ -115,6 +116,7 @@ SYMBOLS = [
     ("srlx_learner_info", C.c_int, [C.POINTER(SrlxEngine), C.POINTER(C.c_int), C.POINTER(C.c_size_t)]),
     ("srlx_tree_blk_bytes", _sz, [_u64]),
     ("srlx_qnet_forward", C.c_int, [C.POINTER(SrlxEngine), _i32, _P, _u32, _u64, _P, _uptr]),
+    ("srlx_returns_scan", C.c_int, [_P, _P, _P, _P, _P, _P, _P, _u32, _u32, _dbl, _dbl, _i32, _i32, _i32, _dbl, _dbl, _uptr]),
 ]
 
 _lib = None

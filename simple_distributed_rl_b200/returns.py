@@ -1,0 +1,58 @@
+"""Worker-side returns of the reference's PPO on a device rollout buffer (the worker half).
+
+`ppo.Worker.on_step` (srl/algorithms/ppo/ppo.py:357-406) turns a finished episode into per-step "discounted_reward" values --
+GAE advantages (`experience_collection_method="GAE"`, the default; `discount`, `gae_discount` of ppo/config.py:67-70) or
+Monte-Carlo returns ("MC") -- after clipping the reward (`reward_clip`).  A vectorised on-policy rollout holds the same
+quantities time-major, [T, E] with E env copies: `returns_scan` runs the accumulation for every column in one launch of
+csrc/returns.cu (srlx_returns_scan) and returns what the worker would have handed to `memory.add()`, in place.
+
+The PPO trainer (clipped surrogate, `ppo.py:103-291`) is not built yet; this is the piece of the path that is a pure function of
+the rollout buffer.  There is no CPU fallback."""
+import ctypes as C
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+
+METHODS = {"GAE": _lib.RETURNS_GAE, "MC": _lib.RETURNS_MC}
+
+
+def returns_scan(reward: torch.Tensor, done: torch.Tensor, value: Optional[torch.Tensor] = None, next_value: Optional[torch.Tensor] = None,
+                 discount: float = 0.9, gae_discount: float = 0.9, method: str = "GAE", reward_clip: Optional[Tuple[float, float]] = None,
+                 tail_is_episode_end: bool = False, with_valid: bool = True):
+    """reward [T, E] float32 (float64 allowed for MC: the reference accumulates python floats), done [T, E] uint8 / bool,
+    value / next_value [T, E] float32 (GAE) -> (returns float32 [T, E], valid uint8 [T, E] or None).  valid = 0 marks the
+    steps of episodes that have not ended inside the buffer (the reference emits an episode only when it is done)."""
+    if method not in METHODS:
+        raise ValueError(f"experience_collection_method {method!r} (GAE or MC)")
+    if not reward.is_cuda:
+        raise _lib.SrlxError("returns_scan needs CUDA tensors (no CPU fallback)")
+    lib = _lib.load()
+    T, E = reward.shape
+    dev = reward.device
+    done8 = done.to(torch.uint8).contiguous()
+    r32 = r64 = None
+    if reward.dtype == torch.float64:
+        if method != "MC":
+            raise ValueError("float64 rewards are only meaningful for MC (GAE is float32 arithmetic in the reference)")
+        r64 = reward.contiguous()
+    else:
+        r32 = reward.to(torch.float32).contiguous()
+    if method == "GAE":
+        if value is None or next_value is None:
+            raise ValueError("GAE needs value and next_value")
+        value, next_value = value.to(torch.float32).contiguous(), next_value.to(torch.float32).contiguous()
+        if value.shape != reward.shape or next_value.shape != reward.shape:
+            raise ValueError("value / next_value must have the shape of reward")
+    if done8.shape != reward.shape:
+        raise ValueError("done must have the shape of reward")
+    out = torch.empty((T, E), dtype=torch.float32, device=dev)
+    valid = torch.empty((T, E), dtype=torch.uint8, device=dev) if with_valid else None
+    ptr = lambda t: None if t is None else t.data_ptr()  # noqa: E731
+    lo, hi = (reward_clip if reward_clip is not None else (0.0, 0.0))
+    with torch.cuda.device(dev):
+        _lib.check(lib.srlx_returns_scan(ptr(r32), ptr(r64), ptr(value), ptr(next_value), ptr(done8), ptr(out), ptr(valid), int(T), int(E),
+                                         float(discount), float(gae_discount), METHODS[method], int(tail_is_episode_end),
+                                         int(reward_clip is not None), float(lo), float(hi), torch.cuda.current_stream(dev).cuda_stream))
+    return out, valid

@@ -426,10 +426,108 @@ def gen_spaces():
     print("spaces:", {k: v.tolist() for k, v in out.items() if k.endswith("10") or k.startswith("default")})
 
 
+def gen_ppo_returns():
+    """ppo.Worker.on_step (srl/algorithms/ppo/ppo.py:357-406): the GAE / Monte-Carlo return accumulation at episode end, executed
+    from the reference's own source.  The module imports TensorFlow (absent here) only for the network classes, so it is imported
+    over permissive stub modules; on_step itself is python + numpy.  The value network is replaced by a stub that returns the
+    prepared V(s) / V(s') arrays (what `self.parameter.model(...)` would give), so the golden pins the ARITHMETIC of the
+    accumulation (order of operations, float32 vs python-float rounding, the last-step rule delta = r - v), which is what the
+    device scan (srlx_returns_scan) restates."""
+    import types
+
+    class _Any(type):
+        def __getattr__(cls, k):
+            return _Stub
+
+    class _Stub(metaclass=_Any):
+        def __init__(self, *a, **k):
+            pass
+
+        def __call__(self, *a, **k):
+            return _Stub()
+
+        def __getattr__(self, k):
+            return _Stub()
+
+    def fake(name):
+        m = types.ModuleType(name)
+        m.__getattr__ = lambda k: _Stub
+        m.__path__ = []
+        return m
+
+    for n in ["tensorflow", "tensorflow.keras", "tensorflow.keras.layers", "tensorflow_probability"]:
+        sys.modules.setdefault(n, fake(n))
+    sys.modules["tensorflow"].keras = sys.modules["tensorflow.keras"]
+    from srl.algorithms.ppo import ppo
+
+    class _Val:
+        def __init__(self, a):
+            self.a = a
+
+        def numpy(self):
+            return self.a
+
+    rng = np.random.default_rng(11)
+    out = {"numpy_version": np.array(np.__version__)}
+    for method, discount, lam, clip in (("GAE", 0.9, 0.9, None), ("GAE", 0.99, 0.95, (-1.0, 1.5)), ("MC", 0.9, 0.9, None),
+                                        ("MC", 0.997, 0.9, (-2.0, 0.25))):
+        name = f"{method.lower()}_g{discount}_l{lam}_{'clip' if clip else 'noclip'}"
+        lens = [1, 2, 7, 33, 200, 5]
+        T = sum(lens)
+        reward = rng.normal(size=T) * 2.0                       # python floats reach the worker (worker.reward)
+        v = rng.normal(size=T).astype(np.float32)               # V(s_t)
+        nv = rng.normal(size=T).astype(np.float32)              # V(s_{t+1})
+        done = np.zeros(T, dtype=np.uint8)
+        added = []
+        w = object.__new__(ppo.Worker)
+        ctx = types.SimpleNamespace(training=True, distributed=False, rl_render_mode="")
+        w._RLWorkerGeneric__worker_run = types.SimpleNamespace(_context=ctx)
+        w.config = types.SimpleNamespace(reward_clip=clip, experience_collection_method=method, state_clip=None, discount=discount,
+                                         gae_discount=lam)
+        w.memory = types.SimpleNamespace(add=lambda b: added.append(float(b["discounted_reward"])) or
+                                         added_dtype.append(b["discounted_reward"].dtype))
+        added_dtype = []
+        t = 0
+        for n in lens:
+            w.on_reset(None)
+            ep0 = t
+            calls = []
+
+            def model(x, _ep0=ep0, _calls=calls):
+                # first call: V of the recent states, second call: V of the recent next states (ppo.py:386-387)
+                _calls.append(len(x))
+                src = v if len(_calls) == 1 else nv
+                return _Val(src[_ep0:_ep0 + len(x)].reshape(-1, 1)), None
+
+            w.parameter = types.SimpleNamespace(model=model)
+            for i in range(n):
+                w.recent_batch.append({"state": np.zeros(3, np.float32)})   # what policy() appends (ppo.py:325-345)
+                last = i == n - 1
+                wk = types.SimpleNamespace(reward=float(reward[t]), next_state=np.zeros(3, np.float32), done=last)
+                w.on_step(wk)
+                done[t] = last
+                t += 1
+        # the reference emits an episode's items LAST step first (reversed loop): put them back in time order
+        ret = np.zeros(T, dtype=np.float32)
+        pos, k = 0, 0
+        for n in lens:
+            for i in reversed(range(n)):
+                ret[pos + i] = np.float32(added[k])
+                k += 1
+            pos += n
+        assert k == T and all(d == np.float32 for d in added_dtype)
+        out[f"{name}_reward"], out[f"{name}_v"], out[f"{name}_nv"], out[f"{name}_done"], out[f"{name}_ret"] = reward, v, nv, done, ret
+        out[f"{name}_params"] = np.array([discount, lam, clip[0] if clip else np.nan, clip[1] if clip else np.nan])
+    np.savez_compressed(os.path.join(HERE, "ppo_returns.npz"), **out)
+    print("ppo_returns:", [k for k in out if k.endswith("_ret")], "numpy", np.__version__)
+
+
 if __name__ == "__main__":
     only = set(sys.argv[1:])  # e.g. `make_golden.py worker` regenerates only worker_records.npz
     if not only or "spaces" in only:
         gen_spaces()
+    if not only or "ppo" in only:
+        gen_ppo_returns()
     if not only or "worker" in only:
         gen_worker_records()
     if not only or "base" in only:

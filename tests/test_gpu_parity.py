@@ -708,3 +708,83 @@ def test_memory_and_parameter_files_round_trip_through_the_device(kw, tmp_path):
     if kw["mem_kind"]:
         tree = b.engine.t["tree"].cpu().numpy()
         np.testing.assert_allclose(tree[0], tree[cap - 1:].sum(), rtol=1e-9)
+
+
+# ---- PPO worker-side returns (worker half): csrc/returns.cu vs oracle/gae.py and the reference golden ------------
+@pytest.mark.parametrize("name", ["gae_g0.9_l0.9_noclip", "gae_g0.99_l0.95_clip", "mc_g0.9_l0.9_noclip", "mc_g0.997_l0.9_clip"])
+def test_returns_scan_equals_reference_worker_golden(name, golden_dir):
+    """The device scan reproduces, bit for bit, the values the reference's ppo.Worker.on_step handed to memory.add()."""
+    from simple_distributed_rl_b200.returns import returns_scan
+
+    d = np.load(os.path.join(golden_dir, "ppo_returns.npz"))
+    discount, lam, lo, hi = [float(x) for x in d[f"{name}_params"]]
+    clip = None if np.isnan(lo) else (lo, hi)
+    method = "GAE" if name.startswith("gae") else "MC"
+    T = len(d[f"{name}_ret"])
+    dev = "cuda:0"
+    col = lambda a, dt: torch.as_tensor(np.ascontiguousarray(a).reshape(T, 1)).to(dt).to(dev)  # noqa: E731
+    reward = col(d[f"{name}_reward"], torch.float64 if method == "MC" else torch.float32)
+    out, valid = returns_scan(reward, col(d[f"{name}_done"], torch.uint8), col(d[f"{name}_v"], torch.float32), col(d[f"{name}_nv"], torch.float32),
+                              discount=discount, gae_discount=lam, method=method, reward_clip=clip)
+    assert bool(valid.all())
+    np.testing.assert_array_equal(out.cpu().numpy()[:, 0], d[f"{name}_ret"])
+
+
+@pytest.mark.parametrize("T,E,method,tail", [(7, 5, "GAE", False), (300, 33, "GAE", True), (513, 70, "MC", False), (129, 64, "MC", True),
+                                            (1, 1, "GAE", True), (200, 96, "GAE", False)])
+def test_returns_scan_equals_oracle_on_ragged_buffers(T, E, method, tail):
+    """Random episode ends (columns with none, with one at the very end, with many), E not a multiple of 32, T longer than a
+    staged chunk: exact equality with oracle/gae.py including the valid mask of unfinished tails."""
+    from oracle import gae as ogae
+    from simple_distributed_rl_b200.returns import returns_scan
+
+    rng = np.random.default_rng(T * 1000 + E)
+    reward = rng.normal(size=(T, E)) * 3
+    v = rng.normal(size=(T, E)).astype(np.float32)
+    nv = rng.normal(size=(T, E)).astype(np.float32)
+    done = (rng.random((T, E)) < 0.03).astype(np.uint8)
+    done[:, 0] = 0
+    if E > 1:
+        done[:, 1] = 0
+        done[T - 1, 1] = 1
+    clip = (-2.5, 4.0) if T % 2 else None
+    r_in = reward if method == "MC" else reward.astype(np.float32)
+    want, want_valid = ogae.returns_scan(ogae.clip_reward(r_in, clip), v, nv, done, 0.97, 0.9,
+                                         ogae.METHOD_GAE if method == "GAE" else ogae.METHOD_MC, tail_is_episode_end=tail)
+    dev = "cuda:0"
+    out, valid = returns_scan(torch.as_tensor(r_in).to(dev), torch.as_tensor(done).to(dev), torch.as_tensor(v).to(dev),
+                              torch.as_tensor(nv).to(dev), discount=0.97, gae_discount=0.9, method=method, reward_clip=clip,
+                              tail_is_episode_end=tail)
+    np.testing.assert_array_equal(valid.cpu().numpy(), want_valid)
+    np.testing.assert_array_equal(out.cpu().numpy(), want)
+
+
+def test_returns_scan_full_size_properties():
+    """BASELINE configs[4] shape (16384 env copies x 200-step Pendulum episodes): every column is one finished episode.  Size-
+    independent checks: identical columns give identical outputs, the scan of an all-zero buffer is zero, a sample of columns
+    equals the oracle, and shifting every reward by a constant shifts MC returns by the geometric series."""
+    from oracle import gae as ogae
+    from simple_distributed_rl_b200.returns import returns_scan
+
+    T, E = 200, 16384
+    g = torch.Generator(device="cuda:0").manual_seed(3)
+    reward = torch.randn((T, E), device="cuda:0", generator=g)
+    v = torch.randn((T, E), device="cuda:0", generator=g)
+    nv = torch.randn((T, E), device="cuda:0", generator=g)
+    done = torch.zeros((T, E), dtype=torch.uint8, device="cuda:0")
+    done[T - 1] = 1
+    reward[:, 1::2] = reward[:, 0::2]
+    v[:, 1::2] = v[:, 0::2]
+    nv[:, 1::2] = nv[:, 0::2]
+    out, valid = returns_scan(reward, done, v, nv, discount=0.9, gae_discount=0.95)
+    assert bool(valid.all()) and torch.equal(out[:, 1::2], out[:, 0::2])
+    cols = [0, 31, 32, 4097, E - 1]
+    want, _ = ogae.returns_scan(reward[:, cols].cpu().numpy(), v[:, cols].cpu().numpy(), nv[:, cols].cpu().numpy(),
+                                done[:, cols].cpu().numpy(), 0.9, 0.95, ogae.METHOD_GAE)
+    np.testing.assert_array_equal(out[:, cols].cpu().numpy(), want)
+    z, _ = returns_scan(torch.zeros_like(reward), done, torch.zeros_like(v), torch.zeros_like(v), discount=0.9, gae_discount=0.95)
+    assert not bool(z.any())
+    mc0, _ = returns_scan(reward.double(), done, method="MC", discount=0.9)
+    mc1, _ = returns_scan(reward.double() + 1.0, done, method="MC", discount=0.9)
+    series = torch.tensor([(1 - 0.9 ** (T - t)) / (1 - 0.9) for t in range(T)], dtype=torch.float64, device="cuda:0")
+    torch.testing.assert_close((mc1 - mc0).double(), series[:, None].expand(T, E), rtol=1e-5, atol=1e-5)

@@ -356,3 +356,22 @@ def test_epsilon_schedule_is_the_reference_linear_phase():
     assert greedy[0] < 0.6  # epsilon 1 at step 0: uniformly random over 4 actions (argmax hit ~ 1/4)
     c2 = oeng.EngineConfig(**{**cfg.__dict__, "eps_phase_steps": 0, "epsilon": 0.3})
     assert oeng.OracleEngine(c2, mu, None).epsilon_at(123) == 0.3
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# PPO worker-side returns (the worker half): tests/golden/ppo_returns.npz = the "discounted_reward" values the
+# reference's ppo.Worker.on_step handed to memory.add() over six episodes (lengths 1..200), GAE and MC, with and without clip.
+@pytest.mark.parametrize("name", ["gae_g0.9_l0.9_noclip", "gae_g0.99_l0.95_clip", "mc_g0.9_l0.9_noclip", "mc_g0.997_l0.9_clip"])
+def test_ppo_returns_equal_reference_worker(name, golden_dir):
+    from oracle import gae as ogae
+
+    d = np.load(os.path.join(golden_dir, "ppo_returns.npz"))
+    discount, lam, lo, hi = d[f"{name}_params"]
+    clip = None if np.isnan(lo) else (lo, hi)
+    method = ogae.METHOD_GAE if name.startswith("gae") else ogae.METHOD_MC
+    reward = ogae.clip_reward(d[f"{name}_reward"], clip)
+    T = len(reward)
+    out, valid = ogae.returns_scan(reward.reshape(T, 1), d[f"{name}_v"].reshape(T, 1), d[f"{name}_nv"].reshape(T, 1),
+                                   d[f"{name}_done"].reshape(T, 1), float(discount), float(lam), method)
+    assert valid.all() and d[f"{name}_done"][-1] == 1
+    np.testing.assert_array_equal(out[:, 0], d[f"{name}_ret"])  # float32 bit for bit
