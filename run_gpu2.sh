@@ -1,11 +1,8 @@
 mkdir -p gpurun_out
-timeout 300 python -m pytest tests/test_gpu_parity.py -m gpu -x -q --timeout 120 -k returns 2>&1 | tail -3
-timeout 300 python tools/returns_bench.py --out gpurun_out/returns_bench.json 2>&1 | tail -1 | cut -c1-400
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:'returns_scan_kernel' -s 8 -c 1 -o gpurun_out/r1_j_returns -f python tools/returns_bench.py > gpurun_out/ncu_returns.log 2>&1
-python tools/ncu_summary.py gpurun_out/r1_j_returns.ncu-rep > gpurun_out/r1_j_returns_ncu_summary.json; cat gpurun_out/r1_j_returns_ncu_summary.json
-ncu -i gpurun_out/r1_j_returns.ncu-rep --page details --csv 2>/dev/null | python -c "
-import csv,sys
-rows=list(csv.reader(sys.stdin)); h=rows[0]; mi=h.index('Metric Name'); vi=h.index('Metric Value'); ui=h.index('Metric Unit')
-for r in rows[1:]:
-    if r[mi] in ('Duration','DRAM Throughput','Memory Throughput','L2 Cache Throughput','Achieved Occupancy','Theoretical Occupancy','Issue Slots Busy','Max Bandwidth','Mem Busy','L1/TEX Hit Rate','L2 Hit Rate','Registers Per Thread','Block Limit Registers','Block Limit Shared Mem'): print(r[mi], r[vi], r[ui])
-"
+python -c "import __graft_entry__ as g; g.build(); g.smoke(); print('smoke ok')" 2>&1 | tail -3
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --impl reference --gpus 2 --steps 3 --warmup 1 2>&1 | tail -1 | cut -c1-300
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 2 --steps 20 --warmup 3 > gpurun_out/bench_j_2gpu.json 2> gpurun_out/bench_j_2gpu.err; tail -c 300 gpurun_out/bench_j_2gpu.err
+python - <<PY
+import json
+d=json.loads(open('gpurun_out/bench_j_2gpu.json').read().strip().splitlines()[-1]); print(d['n_gpus'], d['value'], d['trainer_updates_per_sec'], d['ms_per_step'], d['e2e']['value'], d['roofline']['traffic_source'])
+PY
