@@ -287,6 +287,11 @@ ENGINE_CASES = {
                                                 epsilon=0.3, enable_double_dqn=False, enable_rescale=True, retrace_h=0.9),
     "pendulum_dqn_uniform_a10_b48": dict(env="Pendulum-v1", algo="dqn", hidden=(48, 24, 16), mem_kind=0, multisteps=1, n_envs=32,
                                          ring_rows=6, batch_size=48, warmup_size=64, epsilon=0.3, enable_double_dqn=False),
+    # large batch on the row-split kernel: 32 items and 64 window steps per CTA (more than one warp's worth: block barriers in
+    # the gather), three online row tiles per CTA
+    "cartpole_rainbow_plain_uniform_b256_m2": dict(env="CartPole-v1", algo="rainbow", hidden=(32, 32), dueling=None, noisy=False,
+                                                   mem_kind=0, multisteps=2, n_envs=64, ring_rows=10, batch_size=256, warmup_size=320,
+                                                   epsilon=0.3),
     "cartpole_rainbow_naive_m4": dict(env="CartPole-v1", algo="rainbow", hidden=(40,), dueling="", noisy=True, mem_kind=1,
                                       multisteps=4, n_envs=20, ring_rows=10, batch_size=12, warmup_size=40),
 }
@@ -416,7 +421,7 @@ def test_engine_run_equals_stepwise():
 @pytest.mark.parametrize("name", ["cartpole_rainbow_default", "grid_dqn_per_nodouble_rescale", "cartpole_rainbow_naive_m4",
                                   "cartpole_dqn_per", "grid_rainbow_max_m2_uniform_clip", "cartpole_dqn_uniform_h64",
                                   "cartpole_rainbow_noisy_plain_m2_b24", "cartpole_dqn_uniform_64x64",
-                                  "grid_rainbow_duel_m3_uniform_2layer"])
+                                  "grid_rainbow_duel_m3_uniform_2layer", "cartpole_rainbow_plain_uniform_b256_m2"])
 def test_learn_many_updates_per_launch_equals_one_by_one(name):
     """One launch of n dependent updates (sample/gather of t+1 overlapped with backward/Adam of t, noise ring, parity
     toggles) == n launches of one update: the in-kernel pipelining must not change a single bit."""
@@ -788,3 +793,26 @@ def test_returns_scan_full_size_properties():
     mc1, _ = returns_scan(reward.double() + 1.0, done, method="MC", discount=0.9)
     series = torch.tensor([(1 - 0.9 ** (T - t)) / (1 - 0.9) for t in range(T)], dtype=torch.float64, device="cuda:0")
     torch.testing.assert_close((mc1 - mc0).double(), series[:, None].expand(T, E), rtol=1e-5, atol=1e-5)
+
+
+def test_row_split_learner_long_run_stays_finite():
+    """20 000 dependent updates of learner_small_kernel in launches of 500 (target syncs, Adam bias corrections far from step 1,
+    mbarrier parity over many phases): counters exact, parameters and losses finite and bounded."""
+    from simple_distributed_rl_b200.engine import DeviceEngine, EngineConfig
+
+    kw = dict(env="CartPole-v1", algo="dqn", hidden=(64, 64), mem_kind=0, multisteps=1, n_envs=256, ring_rows=64, batch_size=32,
+              warmup_size=1000, epsilon=0.1, target_update_interval=1000, seed=2)
+    d = DeviceEngine(EngineConfig(**kw))
+    assert d.learner_info()[0] == "learner_small_kernel"
+    d.run(64, 0)
+    losses = []
+    for _ in range(40):
+        d.vec_step()
+        d.learn(500)
+        st = d.read_state()
+        losses.append(st.last_loss)
+    assert st.train_count == 20000 and st.adam_step == 20000 and st.sync_count == 20
+    mu, _ = d.get_params()
+    tm, _ = d.get_target()
+    assert np.isfinite(mu).all() and np.isfinite(tm).all() and np.isfinite(losses).all()
+    assert max(losses) < 50.0 and np.abs(mu).max() < 1e3  # Huber loss of CartPole returns (<= ~100 discounted) stays small
