@@ -1,8 +1,14 @@
 mkdir -p gpurun_out
-python -c "import __graft_entry__ as g; g.build(); g.smoke(); print('smoke ok')" 2>&1 | tail -3
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --impl reference --gpus 2 --steps 3 --warmup 1 2>&1 | tail -1 | cut -c1-300
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 2 --steps 20 --warmup 3 > gpurun_out/bench_j_2gpu.json 2> gpurun_out/bench_j_2gpu.err; tail -c 300 gpurun_out/bench_j_2gpu.err
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 540 -c 60 --csv --log-file gpurun_out/r1_j_launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_launches.log 2>&1
 python - <<PY
-import json
-d=json.loads(open('gpurun_out/bench_j_2gpu.json').read().strip().splitlines()[-1]); print(d['n_gpus'], d['value'], d['trainer_updates_per_sec'], d['ms_per_step'], d['e2e']['value'], d['roofline']['traffic_source'])
+import csv, collections
+rows=list(csv.reader(open('gpurun_out/r1_j_launches.csv')))
+hdr=[i for i,r in enumerate(rows) if r and r[0]=='ID'][0]
+h=rows[hdr]; k=h.index('Kernel Name'); v=h.index('Metric Value')
+agg=collections.defaultdict(lambda:[0,0.0])
+for r in rows[hdr+1:]:
+    if len(r)>v:
+        n=r[k].split('(')[0]; agg[n][0]+=1; agg[n][1]+=float(r[v].replace(',',''))
+tot=sum(x[1] for x in agg.values())
+for n,(c,t) in sorted(agg.items(), key=lambda x:-x[1][1])[:10]: print(f"{n[:60]:60s} launches {c:4d} total {t/1e3:10.1f} us share {t/tot:.3f}")
 PY
