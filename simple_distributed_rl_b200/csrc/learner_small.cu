@@ -9,13 +9,15 @@
 // parameters for the optimiser step.  An update is
 //
 //   1. sample      B distinct uniform picks (replay_buffer.py:34-36), every CTA redundantly: attempt 0 of all draws in
-//                  parallel, duplicates resolved in sample order (== the sequential rejection loop of oracle/sumtree.py)
+//                  parallel, duplicates resolved in sample order (== the sequential rejection loop of oracle/sumtree.py);
+//                  done one update ahead by an idle warp while warp 0 evaluates the targets
 //   2. gather      the (M+1)-state windows of the CTA's items from the ring, padded tails rebuilt (rainbow.py:358-371)
 //   3. forward     online(s), online(s'), target(s') on the CTA's rows (register-tiled warp tasks, weights in smem)
 //   4. targets     double-DQN / n-step Retrace target, Huber gradient (thread per item; same code as learner.cu)
-//   5. backward    on the CTA's rows -> a partial gradient of every parameter
-//   6. REDUCE-SCATTER the partial gradients to the CTA that owns the parameter slice (st.async + mbarrier tx, DSMEM),
-//      summed there in CTA order; Adam on the slice (torch _single_tensor_adam arithmetic)
+//   5. backward    on the CTA's rows: a delta chain (one barrier per layer), then every layer's dW / db in one sweep
+//                  -> a partial gradient of every parameter
+//   6. REDUCE-SCATTER the partial gradients to the CTA that owns the parameter slice (one bulk DSMEM copy per peer, mbarrier
+//      transaction count), summed there in CTA order; Adam on the slice (torch _single_tensor_adam arithmetic)
 //   7. ALL-GATHER the updated slice into every CTA's weight copy; hard target sync when train_count % interval == 0
 //
 // two DSMEM hops per update instead of two per layer.  Reference path: srl/algorithms/dqn/model_torch.py:90-132,
@@ -39,7 +41,7 @@ struct SPlan {
   NetPlan np;
   int C, B, Bc, M, A, D, BcM, P, S;  // Bc = items per CTA, S = floats per parameter slice (multiple of 4), C * S >= P
   int n_on_rows, n_on_tiles, n_tg_tiles, n_tiles, n_s_tiles;
-  size_t off_mbar, off_weff, off_wefft, off_m, off_v, off_g, off_recv, off_wflat, off_wnew, off_slot, off_acts, off_dacts, off_q, off_dq, off_pick,
+  size_t off_mbar, off_weff, off_wefft, off_m, off_v, off_g, off_recv, off_wflat, off_wnew, off_slot, off_acts, off_dacts, off_q, off_pick,
       off_win, off_tq, off_red, off_loss, off_scal, total;
 };
 
@@ -82,7 +84,6 @@ __host__ __device__ inline SPlan make_splan(const srlx_engine& eng, int C) {
   p.off_acts = take((size_t)p.n_tiles * p.np.act_floats * 4);
   p.off_dacts = take((size_t)p.n_s_tiles * p.np.act_floats * 4);  // d loss / d activation of the s rows (same layout as acts)
   p.off_q = take((size_t)(p.Bc + 2 * p.BcM) * p.A * 4);  // Q(s) [Bc][A], online Q(s') [BcM][A], target Q(s') [BcM][A]
-  p.off_dq = take((size_t)p.Bc * p.A * 4);
   p.off_pick = take((size_t)p.B * 4 * 3);                // picks, slots of update t and t+1 (all B items, every CTA)
   p.off_win = take((size_t)p.BcM * 4 * 4);               // action, reward, term, done of every local window step
   p.off_tq = take((size_t)p.Bc * 4 * 2);                 // target, q(s,a)
@@ -485,7 +486,6 @@ learner_small_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_u
   float* acts = reinterpret_cast<float*>(smem + pl.off_acts);
   float* dacts = reinterpret_cast<float*>(smem + pl.off_dacts);
   float* Q = reinterpret_cast<float*>(smem + pl.off_q);
-  float* dQ = reinterpret_cast<float*>(smem + pl.off_dq);
   int* pick = reinterpret_cast<int*>(smem + pl.off_pick);
   int* slot = pick + pl.B;
   int* w_act = reinterpret_cast<int*>(smem + pl.off_win);
@@ -513,7 +513,6 @@ learner_small_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_u
   for (int i = tid; i < np.weff_floats; i += kSmThreads) { weff[i] = 0.f; wefft[i] = 0.f; }
   for (int i = tid; i < pl.n_tiles * np.act_floats; i += kSmThreads) acts[i] = 0.f;
   for (int i = tid; i < C * S; i += kSmThreads) { G[i] = 0.f; wflat[i] = 0.f; pslot[i] = 0; }
-  for (int i = tid; i < Bc * A; i += kSmThreads) dQ[i] = 0.f;
   for (int i = tid; i < pl.n_s_tiles * np.act_floats; i += kSmThreads) dacts[i] = 0.f;
   for (int i = tid; i < S; i += kSmThreads) { am[i] = 0.f; av[i] = 0.f; }
   if (tid == 0) {
