@@ -43,7 +43,7 @@ __global__ void noise_fill_kernel(uint64_t seed, uint32_t kind, uint64_t call_id
 // ---- standalone tree kernels (one thread block each; batch <= 1024) ------------------------------------------------
 constexpr int kTreeThreads = 1024;  // sampler: one warp walks one sample, 32 samples in flight
 constexpr int kTreeMaxBatch = 1024;
-constexpr int kTreeAddChunk = 64;   // items per exact-order pass of a bulk add (the leader search is quadratic in the pass size)
+constexpr int kTreeAddChunk = 1024;  // items staged per pass of a bulk add
 
 __global__ void tree_clear_kernel(double* tree, uint64_t n_nodes, srlx_state* meta) {
   const size_t i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
@@ -58,10 +58,10 @@ __global__ void tree_clear_kernel(double* tree, uint64_t n_nodes, srlx_state* me
 __global__ void __launch_bounds__(kTreeThreads)
 tree_add_kernel(double* tree, uint64_t capacity, srlx_state* meta, const double* priorities, uint64_t n, double alpha,
                 double epsilon, int restore_skip) {
+  extern __shared__ __align__(16) unsigned char tree_smem[];
+  TreeHashScratch* hs = reinterpret_cast<TreeHashScratch*>(tree_smem);
   __shared__ int64_t s_idx[kTreeAddChunk];
   __shared__ double s_pri[kTreeAddChunk];
-  __shared__ double s_chg[kTreeAddChunk];
-  __shared__ int s_dep[kTreeAddChunk + 1];
   const uint64_t write = meta->vec_steps;
   const double maxp = meta->max_priority;
   for (uint64_t base = 0; base < n; base += kTreeAddChunk) {
@@ -76,7 +76,7 @@ tree_add_kernel(double* tree, uint64_t capacity, srlx_state* meta, const double*
       s_pri[i] = p;
     }
     __syncthreads();
-    tree_update_batch(tree, s_idx, s_pri, s_chg, s_dep, m);
+    tree_update_batch(tree, s_idx, s_pri, m, hs);
   }
   if (threadIdx.x == 0) {
     meta->vec_steps = (write + n) % capacity;
@@ -113,16 +113,16 @@ tree_sample_kernel(const double* tree, uint64_t capacity, srlx_state* meta, uint
 __global__ void __launch_bounds__(kTreeThreads)
 tree_update_kernel(double* tree, srlx_state* meta, const int64_t* idx, const float* priorities, uint32_t n, double alpha,
                    double epsilon) {
+  extern __shared__ __align__(16) unsigned char tree_smem[];
+  TreeHashScratch* hs = reinterpret_cast<TreeHashScratch*>(tree_smem);
   __shared__ int64_t s_idx[kTreeMaxBatch];
   __shared__ double s_pri[kTreeMaxBatch];
-  __shared__ double s_chg[kTreeMaxBatch];
-  __shared__ int s_dep[kTreeMaxBatch + 1];
   for (int i = threadIdx.x; i < (int)n; i += blockDim.x) {
     s_idx[i] = idx[i];
     s_pri[i] = pow(fabs((double)priorities[i]) + epsilon, alpha);
   }
   __syncthreads();
-  tree_update_batch(tree, s_idx, s_pri, s_chg, s_dep, (int)n);
+  tree_update_batch(tree, s_idx, s_pri, (int)n, hs);
   if (threadIdx.x == 0) {
     double mp = meta->max_priority;
     for (int i = 0; i < (int)n; ++i) mp = (mp < s_pri[i]) ? s_pri[i] : mp;
@@ -226,7 +226,10 @@ extern "C" int srlx_tree_add(double* tree, uint64_t capacity, srlx_state* meta, 
   SRLX_REQUIRE(tree && meta && capacity >= 1, "srlx_tree_add: bad arguments");
   SRLX_REQUIRE(n <= capacity, "srlx_tree_add: n (%llu) > capacity (%llu)", (unsigned long long)n, (unsigned long long)capacity);
   if (n == 0) return 0;
-  tree_add_kernel<<<1, kTreeThreads, 0, (cudaStream_t)cuda_stream>>>(tree, capacity, meta, priorities_dev, n, alpha, epsilon, restore_skip);
+  SRLX_REQUIRE(capacity < (1ull << 30), "srlx_tree_add: capacity %llu too large (node ids are 32-bit)", (unsigned long long)capacity);
+  SRLX_CHECK_CUDA(cudaFuncSetAttribute(tree_add_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TreeHashScratch)));
+  tree_add_kernel<<<1, kTreeThreads, sizeof(TreeHashScratch), (cudaStream_t)cuda_stream>>>(tree, capacity, meta, priorities_dev, n, alpha,
+                                                                                          epsilon, restore_skip);
   count_launch();
   SRLX_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -251,9 +254,11 @@ extern "C" int srlx_tree_update(double* tree, uint64_t capacity, srlx_state* met
                                 const float* priorities_dev, uint32_t n, double alpha, double epsilon, uintptr_t cuda_stream) {
   SRLX_REQUIRE(tree && meta && tree_idx_dev && priorities_dev, "srlx_tree_update: bad arguments");
   SRLX_REQUIRE(n <= (uint32_t)kTreeMaxBatch, "srlx_tree_update: n %u > %d", n, kTreeMaxBatch);
-  (void)capacity;
+  SRLX_REQUIRE(capacity < (1ull << 30), "srlx_tree_update: capacity %llu too large (node ids are 32-bit)", (unsigned long long)capacity);
   if (n == 0) return 0;
-  tree_update_kernel<<<1, kTreeThreads, 0, (cudaStream_t)cuda_stream>>>(tree, meta, tree_idx_dev, priorities_dev, n, alpha, epsilon);
+  SRLX_CHECK_CUDA(cudaFuncSetAttribute(tree_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TreeHashScratch)));
+  tree_update_kernel<<<1, kTreeThreads, sizeof(TreeHashScratch), (cudaStream_t)cuda_stream>>>(tree, meta, tree_idx_dev, priorities_dev, n,
+                                                                                             alpha, epsilon);
   count_launch();
   SRLX_CHECK_CUDA(cudaGetLastError());
   return 0;

@@ -59,74 +59,78 @@ __device__ inline int64_t tree_retrieve_seq(const double* __restrict__ tree, int
   }
 }
 
-// true iff `node` is a proper ancestor of tree index x (heap numbering: parent(i) = (i-1)/2)
-__device__ inline bool tree_is_ancestor(int64_t node, int64_t x) {
-  const int dn = 63 - __clzll((long long)(node + 1));
-  const int dx = 63 - __clzll((long long)(x + 1));
-  const int l = dx - dn;
-  return l >= 1 && ((x + 1) >> l) == node + 1;
-}
-
 // ProportionalMemory.update for a batch (proportional_memory.py:171-177), executed by one thread block.
-// The reference applies the items one after the other: leaf <- p_i, every ancestor += (p_i - old leaf).  To stay
-// bit-identical in fp64 each node's additions are applied in item order by ONE thread (the "leader": the first item
-// that touches the node), while all nodes proceed in parallel -> one memory round trip instead of n*depth.
-//   idx[i]   tree index of item i (leaf + capacity - 1)
-//   pri[i]   final priority (already (|td|+eps)^alpha)
-//   change[] scratch (n doubles, shared memory)
-//   dep[]    scratch (n ints, shared memory): depth of idx[i]; dep[n] receives the deepest one
-// Requires blockDim-wide participation; ends with __syncthreads().
-__device__ inline void tree_update_batch(double* __restrict__ tree, const int64_t* idx, const double* pri, double* change,
-                                         int* dep, int n) {
-  const int tid = threadIdx.x, nt = blockDim.x;
-  if (tid == 0) dep[n] = 0;
-  __syncthreads();
-  // 1) per-item change, in item order for duplicate leaves
-  for (int i = tid; i < n; i += nt) {
-    const int64_t li = idx[i];
-    double prev = 0.0;
-    bool found = false;
-    for (int j = i - 1; j >= 0; --j)
-      if (idx[j] == li) { prev = pri[j]; found = true; break; }
-    if (!found) prev = __ldcg(tree + li);
-    change[i] = pri[i] - prev;
-    const int d = 63 - __clzll((long long)(li + 1));
-    dep[i] = d;
-    atomicMax(&dep[n], d);
-  }
-  __syncthreads();
-  // 2) leaves: the last item touching a leaf wins
-  for (int i = tid; i < n; i += nt) {
-    const int64_t li = idx[i];
-    bool last = true;
-    for (int j = i + 1; j < n; ++j)
-      if (idx[j] == li) { last = false; break; }
-    if (last) __stcg(tree + li, pri[i]);
-  }
-  // 3) ancestors: work item = (item i, level l above its leaf); the lanes of a warp share the item (same loop bounds, same
-  //    shared-memory words -> no divergence, broadcast reads) and differ in the level; the leader applies all changes to
-  //    its node in item order.  Leaves of a non-power-of-two tree sit at two depths, so "same node" is tested through
-  //    the depths: x lies below `node` (depth dn) iff (x+1) >> (depth(x) - dn) == node + 1.
-  const int levels = dep[n];
-  for (int w = tid; w < n * levels; w += nt) {
-    const int i = w / levels, l = w - i * levels + 1;
-    const int dn = dep[i] - l;
-    if (dn < 0) continue;  // above the root
-    const int64_t node1 = (idx[i] + 1) >> l;
-    bool leader = true;
-    for (int j = 0; j < i; ++j) {
-      const int lj = dep[j] - dn;
-      if (lj >= 1 && ((idx[j] + 1) >> lj) == node1) { leader = false; break; }
+// The reference applies the items one after the other: change = p_i - tree[leaf_i]; tree[leaf_i] = p_i; every ancestor +=
+// change.  fp64 addition is not associative, so a node's value depends on the ORDER of its additions; to stay bit-identical
+// the items are applied in item order -- but out of shared memory, where one item costs a few dozen cycles instead of
+// depth x an L2 round trip:
+//   1. every (item, level) pair hashes its node id into a shared-memory table (atomicCAS, linear probing): all pairs that
+//      name the same node get the same slot; the pair that claims a slot loads the node's current value (one round trip,
+//      all nodes in parallel)
+//   2. ONE warp walks the items in order, lane = level above the leaf: lane 0 forms the change and overwrites the leaf,
+//      the other lanes add the change to their ancestor -- the levels of one item are distinct nodes, so the lanes never
+//      collide, and consecutive items see each other's results as the sequential loop does (duplicate leaves included)
+//   3. every claimed slot is written back.
+// Batches are cut into passes of kTreeHashChunk items (table load factor <= 1/2 for trees of up to 2^31 nodes).
+//   idx[i]   tree index of item i (leaf + capacity - 1), pri[i] its final priority (already (|td|+eps)^alpha)
+// Requires blockDim-wide participation (blockDim >= 64); ends with __syncthreads().
+constexpr int kTreeHashSlots = 4096;
+constexpr int kTreeHashChunk = 64;
+constexpr uint32_t kTreeHashEmpty = 0xFFFFFFFFu;
+struct TreeHashScratch {
+  double vals[kTreeHashSlots];
+  uint32_t keys[kTreeHashSlots];
+  unsigned short slot[kTreeHashChunk * 32];  // [item][level] -> table slot, 0xFFFF above the root
+};
+
+__device__ inline void tree_update_batch(double* __restrict__ tree, const int64_t* idx, const double* pri, int n, TreeHashScratch* hs) {
+  const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31;
+  for (int base = 0; base < n; base += kTreeHashChunk) {
+    const int m = min(kTreeHashChunk, n - base);
+    for (int h = tid; h < kTreeHashSlots; h += nt) hs->keys[h] = kTreeHashEmpty;
+    __syncthreads();
+    // 1) claim a slot per distinct node; the claimer fetches the node
+    for (int w = tid; w < m * 32; w += nt) {
+      const int i = w >> 5, l = w & 31;
+      const uint64_t ip1 = (uint64_t)idx[base + i] + 1;
+      unsigned short s = 0xFFFF;
+      if ((ip1 >> l) != 0) {
+        const uint32_t node = (uint32_t)((ip1 >> l) - 1);
+        uint32_t h = (node * 2654435761u) >> 20;  // Fibonacci hash -> 12 bits
+        while (true) {
+          const uint32_t old = atomicCAS(&hs->keys[h], kTreeHashEmpty, node);
+          if (old == kTreeHashEmpty) { hs->vals[h] = __ldcg(tree + node); break; }
+          if (old == node) break;
+          h = (h + 1) & (kTreeHashSlots - 1);
+        }
+        s = (unsigned short)h;
+      }
+      hs->slot[w] = s;
     }
-    if (!leader) continue;
-    double v = __ldcg(tree + node1 - 1) + change[i];
-    for (int j = i + 1; j < n; ++j) {
-      const int lj = dep[j] - dn;
-      if (lj >= 1 && ((idx[j] + 1) >> lj) == node1) v += change[j];
+    __syncthreads();
+    // 2) the items in order, one warp, lane = level
+    if (tid < 32) {
+      for (int i = 0; i < m; ++i) {
+        const unsigned short s = hs->slot[i * 32 + lane];
+        double c = 0.0;
+        if (lane == 0) {
+          const double p = pri[base + i];
+          c = p - hs->vals[s];
+          hs->vals[s] = p;
+        }
+        c = __shfl_sync(0xffffffffu, c, 0);
+        if (lane > 0 && s != 0xFFFF) hs->vals[s] += c;
+        __syncwarp();
+      }
     }
-    __stcg(tree + node1 - 1, v);
+    __syncthreads();
+    // 3) write back
+    for (int h = tid; h < kTreeHashSlots; h += nt) {
+      const uint32_t node = hs->keys[h];
+      if (node != kTreeHashEmpty) __stcg(tree + node, hs->vals[h]);
+    }
+    __syncthreads();
   }
-  __syncthreads();
 }
 
 // ProportionalMemory.sample draw for a whole batch (proportional_memory.py:142-157), executed by one thread block.
