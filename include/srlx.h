@@ -243,6 +243,18 @@ int srlx_returns_scan(const float* reward_dev, const double* reward_f64_dev, con
                       double discount, double gae_discount, int method, int tail_is_episode_end, int clip_enable, double clip_lo,
                       double clip_hi, uintptr_t cuda_stream);
 
+/* ---- R2D2 trainer, per-sequence targets (R14, the target / Retrace / priority half) ----------------------------- */
+/* r2d2.Trainer._train_on_batches, the loop between the network forwards and the loss (srl/algorithms/r2d2/r2d2.py:150-203),
+ * for n_seq stored sequences of seq_len (<= 128) steps: q_online / q_target [n_seq][seq_len+1][n_actions] float32 (the online
+ * and target Q of every step after burn-in), actions int32 / mu (behaviour probability) / rewards float64 / dones uint8
+ * [n_seq][seq_len] -> target_out float64 [n_seq][seq_len] (the regression target of Q_online(s_t)[a_t]), td_mean_out [n_seq]
+ * (mean TD error of the sequence: the priority input, :204) and td_kind_out (0: the reference holds it as float32, 1: float64).
+ * Bit-exact with the reference's numpy/python arithmetic (tests/golden/r2d2_targets.npz). */
+int srlx_sequence_targets(const float* q_online_dev, const float* q_target_dev, const int32_t* actions_dev, const double* mu_dev,
+                          const double* rewards_dev, const unsigned char* dones_dev, double* target_out_dev, double* td_mean_out_dev,
+                          unsigned char* td_kind_out_dev, uint32_t n_seq, uint32_t seq_len, uint32_t n_actions, double discount,
+                          double retrace_h, int enable_double_dqn, int enable_rescale, int enable_retrace, uintptr_t cuda_stream);
+
 /* ---- engine (R1-R6, R8-R12) ------------------------------------------------------------------------------ */
 /* Zero the counters, mark every env for reset, clear ring flags and the tree. */
 int srlx_engine_reset(const srlx_engine* eng, uintptr_t cuda_stream);

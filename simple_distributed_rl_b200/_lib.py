@@ -116,6 +116,7 @@ SYMBOLS = [
     ("srlx_learner_info", C.c_int, [C.POINTER(SrlxEngine), C.POINTER(C.c_int), C.POINTER(C.c_size_t)]),
     ("srlx_tree_blk_bytes", _sz, [_u64]),
     ("srlx_qnet_forward", C.c_int, [C.POINTER(SrlxEngine), _i32, _P, _u32, _u64, _P, _uptr]),
+    ("srlx_sequence_targets", C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _u32, _u32, _u32, _dbl, _dbl, _i32, _i32, _i32, _uptr]),
     ("srlx_returns_scan", C.c_int, [_P, _P, _P, _P, _P, _P, _P, _u32, _u32, _dbl, _dbl, _i32, _i32, _i32, _dbl, _dbl, _uptr]),
 ]
 

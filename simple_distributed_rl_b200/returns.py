@@ -56,3 +56,35 @@ def returns_scan(reward: torch.Tensor, done: torch.Tensor, value: Optional[torch
                                          float(discount), float(gae_discount), METHODS[method], int(tail_is_episode_end),
                                          int(reward_clip is not None), float(lo), float(hi), torch.cuda.current_stream(dev).cuda_stream))
     return out, valid
+
+
+def sequence_targets(q_online: torch.Tensor, q_target: torch.Tensor, actions: torch.Tensor, mu: torch.Tensor, rewards: torch.Tensor,
+                     dones: torch.Tensor, discount: float = 0.997, retrace_h: float = 1.0, enable_double_dqn: bool = True,
+                     enable_rescale: bool = False, enable_retrace: bool = True):
+    """The per-sequence target loop of the reference's R2D2 trainer (srl/algorithms/r2d2/r2d2.py:150-203; SURVEY.md 8a R14, the
+    target / Retrace / priority half) on the device: q_online / q_target [B, T+1, A] float32, actions [B, T], mu (stored behaviour
+    probabilities) / rewards [B, T] (float64: the reference keeps them as python floats), dones [B, T] ->
+    (target float64 [B, T], td_mean float64 [B], td_is_float64 bool [B]).  `td_mean` is the sequence's priority input (:204);
+    where the reference holds it as float32 its value here is that float32 widened.  The LSTM Q-network, burn-in and the sequence
+    replay around this loop are not built.  There is no CPU fallback."""
+    if not q_online.is_cuda:
+        raise _lib.SrlxError("sequence_targets needs CUDA tensors (no CPU fallback)")
+    lib = _lib.load()
+    B, T1, A = q_online.shape
+    T = T1 - 1
+    dev = q_online.device
+    qo, qt = q_online.to(torch.float32).contiguous(), q_target.to(torch.float32).contiguous()
+    if qt.shape != qo.shape or tuple(actions.shape) != (B, T):
+        raise ValueError("q_target must have the shape of q_online [B, T+1, A] and actions the shape [B, T]")
+    act = actions.to(torch.int32).contiguous()
+    mu64, r64 = mu.to(torch.float64).contiguous(), rewards.to(torch.float64).contiguous()
+    dn = dones.to(torch.uint8).contiguous()
+    target = torch.empty((B, T), dtype=torch.float64, device=dev)
+    td_mean = torch.empty(B, dtype=torch.float64, device=dev)
+    td_kind = torch.empty(B, dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.srlx_sequence_targets(qo.data_ptr(), qt.data_ptr(), act.data_ptr(), mu64.data_ptr(), r64.data_ptr(), dn.data_ptr(),
+                                             target.data_ptr(), td_mean.data_ptr(), td_kind.data_ptr(), int(B), int(T), int(A),
+                                             float(discount), float(retrace_h), int(enable_double_dqn), int(enable_rescale),
+                                             int(enable_retrace), torch.cuda.current_stream(dev).cuda_stream))
+    return target, td_mean, td_kind.bool()

@@ -522,12 +522,146 @@ def gen_ppo_returns():
     print("ppo_returns:", [k for k in out if k.endswith("_ret")], "numpy", np.__version__)
 
 
+def gen_r2d2_targets():
+    """r2d2.Trainer._train_on_batches (srl/algorithms/r2d2/r2d2.py:109-215): the per-sequence target / TD-error / Retrace loop
+    (:150-203), executed from the reference's own source.  TensorFlow (absent here) is replaced by numpy-backed stubs and the
+    two LSTM Q-networks by stubs that return prepared Q arrays, so the golden pins the ARITHMETIC of the loop -- double-DQN
+    index from the online Q, value from the target Q, optional rescaling, `target_t = gain_t + retrace * td_{t+1}`,
+    `retrace *= discount * retrace_h * min(1, pi/mu)`, the mixed float32 / python-float rounding, the mean TD error per
+    sequence -- which is what srlx_sequence_targets restates on the device."""
+    import types
+
+    captured = {}
+
+    class _Loss:
+        def __init__(self, v=0.0):
+            self.v = v
+
+        def __add__(self, o):
+            return _Loss(self.v)
+
+        __iadd__ = __add__
+
+        def numpy(self):
+            return self.v
+
+    class _Frozen:
+        def __init__(self, a):
+            self.a = a
+
+        def numpy(self):
+            return self.a
+
+    class _Tape:
+        def __enter__(self):
+            return self
+
+        def __exit__(self, *a):
+            return False
+
+        def gradient(self, loss, variables):
+            return []
+
+    tf = types.ModuleType("tensorflow")
+    tf.__path__ = []
+    tf.__version__ = "2.16.1"
+    tf.function = lambda *a, **k: (lambda f: f)
+    tf.__getattr__ = lambda k: _Stub
+    tf.one_hot = lambda idx, n, axis=2: np.eye(n, dtype=np.float32)[np.asarray(idx)]
+    tf.stack = lambda xs: np.stack(xs)
+    tf.GradientTape = _Tape
+    tf.stop_gradient = lambda x: _Frozen(np.asarray(x))
+    tf.reduce_sum = lambda x, axis=None: np.sum(x, axis=axis) if axis is not None else float(np.sum(x))
+
+    class _Any(type):
+        def __getattr__(cls, k):
+            return _Stub
+
+    class _Stub(metaclass=_Any):
+        def __init__(self, *a, **k):
+            pass
+
+        def __call__(self, *a, **k):
+            return _Stub()
+
+        def __getattr__(self, k):
+            return _Stub()
+
+    keras = types.ModuleType("tensorflow.keras")
+    keras.__getattr__ = lambda k: _Stub
+    keras.__path__ = []
+    tf.keras = keras
+    saved = {n: sys.modules.get(n) for n in ("tensorflow", "tensorflow.keras")}
+    sys.modules["tensorflow"], sys.modules["tensorflow.keras"] = tf, keras
+    for n in [m for m in sys.modules if m.startswith("srl.algorithms.r2d2") or m.startswith("srl.rl.tf")]:
+        del sys.modules[n]
+    lay = types.ModuleType("tensorflow.keras.layers")
+    lay.__getattr__ = lambda k: _Stub
+    sys.modules["tensorflow.keras.layers"] = lay
+    from srl.algorithms.r2d2 import r2d2
+
+    rng = np.random.default_rng(5)
+    out = {"numpy_version": np.array(np.__version__)}
+    B, T, A = 6, 80, 4
+    for name, double, rescale, retrace, h, disc in (("double_retrace", True, False, True, 0.95, 0.997),
+                                                   ("plain", False, False, False, 1.0, 0.99),
+                                                   ("double_rescale_retrace", True, True, True, 0.9, 0.997),
+                                                   ("target_rescale", False, True, False, 1.0, 0.9)):
+        q_on = rng.normal(size=(B, T + 1, A)).astype(np.float32) * 2
+        q_tg = rng.normal(size=(B, T + 1, A)).astype(np.float32) * 2
+        q_on[0, 3, :] = q_on[0, 3, 0]          # ties: argmax takes the first, pi = 1 / (number of maxima)
+        q_on[1, 10, 2] = q_on[1, 10, 1] = q_on[1, 10].max() + 1
+        actions = rng.integers(A, size=(B, T))
+        greedy = np.argmax(q_on[:, :T], axis=2)
+        take = rng.random((B, T)) < 0.7         # mostly greedy behaviour so Retrace coefficients are not all zero
+        actions = np.where(take, greedy, actions)
+        mu = rng.uniform(0.05, 1.0, size=(B, T))
+        rewards = rng.normal(size=(B, T))
+        dones = (rng.random((B, T)) < 0.05)
+        dones[2, T - 1] = True
+        batches = []
+        for b in range(B):
+            batches.append({"states": [np.zeros(3, np.float32)] * (T + 1), "actions": [int(a) for a in actions[b]],
+                            "probs": [float(x) for x in mu[b]], "rewards": [float(x) for x in rewards[b]],
+                            "dones": [bool(x) for x in dones[b]], "invalid_actions": [[] for _ in range(T + 1)],
+                            "hidden_states": [np.zeros(2, np.float32), np.zeros(2, np.float32)]})
+        tr = object.__new__(r2d2.Trainer)
+        tr.config = types.SimpleNamespace(burnin=0, sequence_length=T, action_space=types.SimpleNamespace(n=A), enable_double_dqn=double,
+                                          enable_rescale=rescale, discount=disc, enable_retrace=retrace, retrace_h=h)
+        online = types.SimpleNamespace(losses=[], trainable_variables=[])
+        tr.parameter = types.SimpleNamespace(
+            q_online=type("Q", (), {"__call__": lambda self, x, hs, training=False: (q_on, hs), "losses": [], "trainable_variables": []})(),
+            q_target=type("Q", (), {"__call__": lambda self, x, hs, training=False: (_Frozen(q_tg), hs)})())
+        tr.loss = lambda target, q: captured.update(target=np.asarray(target), q=np.asarray(q)) or _Loss()
+        tr.optimizer = types.SimpleNamespace(apply_gradients=lambda pairs: None)
+        td_means, _ = tr._train_on_batches(batches, np.ones((B, 1)))
+        tgt = captured["target"]
+        assert tgt.shape == (B, T)
+        out[f"{name}_q_on"], out[f"{name}_q_tg"] = q_on, q_tg
+        out[f"{name}_actions"], out[f"{name}_mu"], out[f"{name}_rewards"], out[f"{name}_dones"] = actions, mu, rewards, dones
+        out[f"{name}_target"] = tgt
+        out[f"{name}_target_dtype"] = np.array(str(tgt.dtype))
+        out[f"{name}_td_mean"] = np.asarray(td_means)
+        out[f"{name}_td_mean_dtype"] = np.array(str(np.asarray(td_means).dtype))
+        out[f"{name}_q_sa"] = captured["q"]
+        out[f"{name}_params"] = np.array([float(double), float(rescale), float(retrace), h, disc])
+    for n, m in saved.items():
+        if m is None:
+            sys.modules.pop(n, None)
+        else:
+            sys.modules[n] = m
+    np.savez_compressed(os.path.join(HERE, "r2d2_targets.npz"), **out)
+    print("r2d2_targets:", [(k, str(out[k])) for k in out if k.endswith("dtype")])
+
+
 if __name__ == "__main__":
     only = set(sys.argv[1:])  # e.g. `make_golden.py worker` regenerates only worker_records.npz
     if not only or "spaces" in only:
         gen_spaces()
     if not only or "ppo" in only:
         gen_ppo_returns()
+    if not only or "r2d2" in only:
+        gen_r2d2_targets()
     if not only or "worker" in only:
         gen_worker_records()
     if not only or "base" in only:

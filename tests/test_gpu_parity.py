@@ -816,3 +816,57 @@ def test_row_split_learner_long_run_stays_finite():
     tm, _ = d.get_target()
     assert np.isfinite(mu).all() and np.isfinite(tm).all() and np.isfinite(losses).all()
     assert max(losses) < 50.0 and np.abs(mu).max() < 1e3  # Huber loss of CartPole returns (<= ~100 discounted) stays small
+
+
+# ---- R2D2 trainer, per-sequence targets (target / Retrace / priority half): csrc/sequence_targets.cu -----------
+@pytest.mark.parametrize("name", ["double_retrace", "plain", "double_rescale_retrace", "target_rescale"])
+def test_sequence_targets_equal_reference_trainer_golden(name, golden_dir):
+    """Bit for bit what r2d2.Trainer._train_on_batches computed (float64 targets, the mean TD error in the reference's dtype)."""
+    from simple_distributed_rl_b200.returns import sequence_targets
+
+    d = np.load(os.path.join(golden_dir, "r2d2_targets.npz"))
+    double, rescale, retrace, h, disc = [float(x) for x in d[f"{name}_params"]]
+    dev = "cuda:0"
+    t = lambda k: torch.as_tensor(d[f"{name}_{k}"]).to(dev)  # noqa: E731
+    target, td_mean, is64 = sequence_targets(t("q_on"), t("q_tg"), t("actions"), t("mu"), t("rewards"), t("dones"), discount=disc,
+                                             retrace_h=h, enable_double_dqn=bool(double), enable_rescale=bool(rescale),
+                                             enable_retrace=bool(retrace))
+    np.testing.assert_array_equal(target.cpu().numpy(), d[f"{name}_target"])
+    want = d[f"{name}_td_mean"]
+    assert bool(is64.all()) == (str(d[f"{name}_td_mean_dtype"]) == "float64") or want.dtype == np.float64
+    np.testing.assert_array_equal(td_mean.cpu().numpy().astype(want.dtype), want)
+
+
+@pytest.mark.parametrize("B,T,A,double,rescale,retrace", [(1, 1, 2, True, False, True), (70, 128, 3, False, True, True),
+                                                          (33, 7, 16, True, True, False), (256, 80, 4, True, False, True)])
+def test_sequence_targets_equal_oracle(B, T, A, double, rescale, retrace):
+    from oracle import r2d2_targets as o
+    from simple_distributed_rl_b200.returns import sequence_targets
+
+    rng = np.random.default_rng(B * 7 + T)
+    q_on = (rng.normal(size=(B, T + 1, A)) * 3).astype(np.float32)
+    q_tg = (rng.normal(size=(B, T + 1, A)) * 3).astype(np.float32)
+    q_on[0, 0, :] = 1.5  # a full tie
+    greedy = np.argmax(q_on[:, :T], axis=2)
+    actions = np.where(rng.random((B, T)) < 0.6, greedy, rng.integers(A, size=(B, T)))
+    mu = rng.uniform(0.01, 1.0, size=(B, T))
+    rewards = rng.normal(size=(B, T)) * 2
+    dones = rng.random((B, T)) < 0.08
+    want_t, want_m = o.batch_targets(q_on, q_tg, actions, mu.tolist(), rewards.tolist(), dones, 0.997, 0.9, double, rescale, retrace)
+    dev = "cuda:0"
+    target, td_mean, is64 = sequence_targets(*(torch.as_tensor(x).to(dev) for x in (q_on, q_tg, actions, mu, rewards, dones)),
+                                             discount=0.997, retrace_h=0.9, enable_double_dqn=double, enable_rescale=rescale,
+                                             enable_retrace=retrace)
+    got_m, got64 = td_mean.cpu().numpy(), is64.cpu().numpy()
+    if rescale:
+        # inverse_rescaling squares with `n ** 2` on a numpy float32 scalar, which goes through libm powf -- not correctly rounded
+        # (about 1 value in 2000 is off by one float32 ulp from the exact product the device forms); everything downstream of
+        # such a value moves with it, so the bar here is a few float32 ulps instead of bit equality
+        np.testing.assert_allclose(target.cpu().numpy(), want_t, rtol=5e-7, atol=5e-7)
+        np.testing.assert_allclose(got_m, np.asarray([float(x) for x in want_m]), rtol=5e-6, atol=1e-6)
+    else:
+        np.testing.assert_array_equal(target.cpu().numpy(), want_t)
+    for b in range(B):
+        assert got64[b] == (np.asarray(want_m[b]).dtype == np.float64)
+        if not rescale:
+            assert got_m[b] == float(want_m[b]), (b, got_m[b], want_m[b])

@@ -375,3 +375,26 @@ def test_ppo_returns_equal_reference_worker(name, golden_dir):
                                    d[f"{name}_done"].reshape(T, 1), float(discount), float(lam), method)
     assert valid.all() and d[f"{name}_done"][-1] == 1
     np.testing.assert_array_equal(out[:, 0], d[f"{name}_ret"])  # float32 bit for bit
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# R2D2 trainer, per-sequence target loop (the target / Retrace / priority half): tests/golden/r2d2_targets.npz =
+# what r2d2.Trainer._train_on_batches computed for six 80-step sequences (reference source executed over TensorFlow stubs).
+R2D2_CASES = ["double_retrace", "plain", "double_rescale_retrace", "target_rescale"]
+
+
+@pytest.mark.parametrize("name", R2D2_CASES)
+def test_r2d2_sequence_targets_equal_reference_trainer(name, golden_dir):
+    from oracle import r2d2_targets as o
+
+    d = np.load(os.path.join(golden_dir, "r2d2_targets.npz"))
+    double, rescale, retrace, h, disc = [float(x) for x in d[f"{name}_params"]]
+    tgt, td_mean = o.batch_targets(d[f"{name}_q_on"], d[f"{name}_q_tg"], d[f"{name}_actions"], d[f"{name}_mu"].tolist(),
+                                   d[f"{name}_rewards"].tolist(), d[f"{name}_dones"], disc, h, bool(double), bool(rescale), bool(retrace))
+    np.testing.assert_array_equal(tgt, d[f"{name}_target"])  # float64, bit for bit
+    want = d[f"{name}_td_mean"]
+    assert str(np.asarray(td_mean).dtype) == str(d[f"{name}_td_mean_dtype"])
+    np.testing.assert_array_equal(np.asarray(td_mean), want)
+    # np.mean of the TD errors is numpy's pairwise sum / n: the restated summation order reproduces it exactly
+    tds32 = np.random.default_rng(0).normal(size=80).astype(np.float32)
+    assert o.np_pairwise_sum(tds32) == np.add.reduce(tds32) and o.np_pairwise_sum(tds32.astype(np.float64)) == np.add.reduce(tds32.astype(np.float64))
