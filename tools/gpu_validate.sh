@@ -1,3 +1,4 @@
+# Full validation on a GPU box: gpurun --timeout 2700 -- "bash tools/gpu_validate.sh" (tests, both bench workloads, SumTree speedtest, ncu capture of learner_small)
 set -x
 mkdir -p gpurun_out
 timeout 1100 python -m pytest tests -m gpu -x -q --timeout 120 2>&1 | tail -6
