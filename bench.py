@@ -45,16 +45,27 @@ def dqn_kwargs(n_envs, ring_rows, warmup_size, seed):
                 enable_double_dqn=True, target_update_interval=1000, lr=1e-3, discount=0.99)
 
 
+def dqn_default_kwargs(n_envs, ring_rows, warmup_size, seed):
+    """The reference's default DQN: one hidden layer of 512 (MLPBlockConfig default), double DQN, uniform ReplayBuffer."""
+    kw = dqn_kwargs(n_envs, ring_rows, warmup_size, seed)
+    kw["hidden"] = (512,)
+    return kw
+
+
+WORKLOADS = {"rainbow": rainbow_kwargs, "dqn": dqn_kwargs, "dqn_default": dqn_default_kwargs}
+
+
 def workload_kwargs(args, **kw):
-    return (dqn_kwargs if args.workload == "dqn" else rainbow_kwargs)(**kw)
+    return WORKLOADS[args.workload](**kw)
 
 
 def workload_config(args, world):
-    name = ("DQN(double) MLP[64,64] uniform replay CartPole-v1 (BASELINE configs[1]; not the headline config)" if args.workload == "dqn"
-            else "Rainbow(double+dueling512+noisy+3step-retrace+PER) CartPole-v1 (BASELINE configs[2])")
+    name = {"dqn": "DQN(double) MLP[64,64] uniform replay CartPole-v1 (BASELINE configs[1]; not the headline config)",
+            "dqn_default": "DQN(double) MLP[512] uniform replay CartPole-v1 (the reference's default DQN config; not the headline config)",
+            "rainbow": "Rainbow(double+dueling512+noisy+3step-retrace+PER) CartPole-v1 (BASELINE configs[2])"}[args.workload]
     return {"workload": name,
             "n_envs_per_gpu": args.envs, "replay_capacity_per_gpu": args.envs * args.ring_rows, "batch_size": 32,
-            "multisteps": 1 if args.workload == "dqn" else 3, "train_interval": args.train_interval,
+            "multisteps": 3 if args.workload == "rainbow" else 1, "train_interval": args.train_interval,
             "updates_per_step_per_gpu": args.envs // args.train_interval,
             "env_steps_per_step": args.envs * world,
             "parallelism": (f"shard{world}: env/replay/SumTree shards + learner replica per GPU, parameters averaged by one "
@@ -137,7 +148,7 @@ def cpu_port_run(n_envs, train_interval, steps, warmup, budget_s, threads, workl
 
     torch.set_num_threads(max(1, threads))
     U = max(1, n_envs // train_interval)
-    kw = (dqn_kwargs if workload == "dqn" else rainbow_kwargs)(n_envs, ring_rows=64, warmup_size=n_envs, seed=1)
+    kw = WORKLOADS[workload](n_envs, ring_rows=64, warmup_size=n_envs, seed=1)
     spec = NetSpec(4, kw["hidden"], 2, kw["dueling"], kw["noisy"], kw["algo"])
     mu, sigma = spec.init_params(0)
     orc = oeng.OracleEngine(oeng.EngineConfig(**kw), mu, sigma)
@@ -364,8 +375,9 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="own", choices=["own", "reference"])
-    ap.add_argument("--workload", default="rainbow", choices=["rainbow", "dqn"],
-                    help="rainbow = BASELINE configs[2] (the headline, default); dqn = configs[1] (use --envs 4096), a side measurement")
+    ap.add_argument("--workload", default="rainbow", choices=sorted(WORKLOADS),
+                    help="rainbow = BASELINE configs[2] (the headline, default); dqn = configs[1] (use --envs 4096) and dqn_default = "
+                         "the reference's default DQN config: side measurements")
     ap.add_argument("--envs", type=int, default=8192)
     ap.add_argument("--ring-rows", type=int, default=256)
     ap.add_argument("--train-interval", type=int, default=10,
