@@ -175,7 +175,7 @@ __device__ __forceinline__ void adam_apply(float& pp, float& mm, float& vv, floa
 //      units ascending, one fmaf per term -> bit-identical gradients, ~6x fewer shared-memory loads per FMA) -------------
 // dW[u][k] += sum_r dY[r][u] * X[r][k],  db[u] += sum_r dY[r][u]        thread tile 4 units x 4 inputs
 __device__ __forceinline__ void small_dw(const float* __restrict__ dY, int ldy, const float* __restrict__ X, int ldx, int R, int U,
-                                         int K, float* __restrict__ Gw, float* __restrict__ Gb) {
+                                         int K, float* __restrict__ Gw, float* __restrict__ Gb, bool accum) {
   const int tid = threadIdx.x, nt = blockDim.x;
   const int n_kt = (K + 3) >> 2, n_ut = (U + 3) >> 2;
   for (int item = tid; item < n_ut * n_kt; item += nt) {
@@ -200,12 +200,15 @@ __device__ __forceinline__ void small_dw(const float* __restrict__ dY, int ldy, 
     for (int a = 0; a < 4; ++a)
 #pragma unroll
       for (int b = 0; b < 4; ++b)
-        if (u0 + a < U && k0 + b < K) Gw[(u0 + a) * K + k0 + b] += acc[a][b];
+        if (u0 + a < U && k0 + b < K) {
+          float* gp = Gw + (u0 + a) * K + k0 + b;
+          *gp = accum ? *gp + acc[a][b] : acc[a][b];  // first row tile of an update: plain store (no zeroing pass needed)
+        }
   }
   for (int u = tid; u < U; u += nt) {
     float acc = 0.f;
     for (int r = 0; r < R; ++r) acc += dY[r * ldy + u];
-    Gb[u] += acc;
+    Gb[u] = accum ? Gb[u] + acc : acc;
   }
 }
 
@@ -306,7 +309,7 @@ __device__ inline void small_delta_chain(const srlx_net& net, const NetPlan& pl,
 }
 
 __device__ inline void small_all_dw(const srlx_net& net, const NetPlan& pl, const float* acts, const float* dacts, int R, float* G,
-                                    long long* clk) {
+                                    bool accum, long long* clk) {
   const int tid = threadIdx.x, nt = blockDim.x;
   const int L = net.n_layers;
   const int nout = net.out_dim[L - 1], Ko = net.k_dim[L - 1];
@@ -320,19 +323,21 @@ __device__ inline void small_all_dw(const srlx_net& net, const NetPlan& pl, cons
       const int koff = (net.dueling != SRLX_DUEL_NONE && o > 0) ? Ko : 0;
       float acc = 0.f;
       for (int r = 0; r < R; ++r) acc = fmaf(raw[r * ldr + o], X[r * ldx + koff + k], acc);
-      G[net.w_off[L - 1] + w] += acc;
+      float* gp = G + net.w_off[L - 1] + w;
+      *gp = accum ? *gp + acc : acc;
     }
     for (int o = tid; o < nout; o += nt) {
       float acc = 0.f;
       for (int r = 0; r < R; ++r) acc += raw[r * ldr + o];
-      G[net.b_off[L - 1] + o] += acc;
+      float* gp = G + net.b_off[L - 1] + o;
+      *gp = accum ? *gp + acc : acc;
     }
   }
   if (clk) clk[12] = clock64();
 #pragma unroll 1
   for (int l = L - 2; l >= 0; --l)
     small_dw(dacts + pl.x_s[l + 1], pl.ldx[l + 1], acts + pl.x_s[l], pl.ldx[l], R, net.out_dim[l], net.k_dim[l], G + net.w_off[l],
-             G + net.b_off[l]);
+             G + net.b_off[l], accum);
 }
 
 // Output layer of a row tile, thread per (row, output): float4 dot products instead of a warp per row
@@ -782,13 +787,13 @@ learner_small_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_u
     }
     __syncthreads();
     SRLX_SMSTAMP(6);
-    // ---------------------------------------------------------------- 5. backward on the CTA's s rows (G zero since the last scatter)
+    // ---------------------------------------------------------------- 5. backward on the CTA's s rows -> G (stored, not accumulated)
 #pragma unroll 1
     for (int tile = 0; tile < pl.n_s_tiles; ++tile) {
       const int Rt = min(kRowTile, Bc - tile * kRowTile);
       long long* clk = (eng.dbg_clock && rank == 0 && tid == 0 && upd + 2 == n_updates) ? eng.dbg_clock : nullptr;
       small_delta_chain(net, np, weff, acts + (size_t)tile * np.act_floats, dacts + (size_t)tile * np.act_floats, Rt, clk);
-      small_all_dw(net, np, acts + (size_t)tile * np.act_floats, dacts + (size_t)tile * np.act_floats, Rt, G, clk);
+      small_all_dw(net, np, acts + (size_t)tile * np.act_floats, dacts + (size_t)tile * np.act_floats, Rt, G, tile > 0, clk);
       if (clk) clk[13] = clock64();
     }
     sm_fence_proxy_async();  // this thread's gradient stores -> visible to the bulk-copy (async) proxy
@@ -851,8 +856,8 @@ learner_small_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_u
         weff[s] = w;
         if (do_sync) wefft[s] = w;  // hard sync after the step, before train_count += 1 (model_torch.py:126-132)
       }
-      // every peer has finished its Adam (its all-gather copy arrived), so it has consumed this CTA's gradient slices
-      for (int i = tid; i < (C * S) >> 2; i += kSmThreads) reinterpret_cast<float4*>(G)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      // (every peer has finished its Adam -- its all-gather copy arrived -- so it has consumed this CTA's gradient slices: the
+      // next backward may overwrite G; its first row tile stores, later tiles accumulate, the padding past P stays zero)
     }
     __syncthreads();
     SRLX_SMSTAMP(9);
