@@ -12,7 +12,8 @@
 // (delta and the episode-end flag are formed on the fly, thread per element) while one warp runs the 32 column recurrences of
 // the current chunk in place; then all warps store the finished rows.  Several CTAs per SM keep the memory system busy
 // (algorithmic bytes: 13 B read + 5 B written per env step for GAE).  Measured on B200 at 16384 x 200 (profiles/r1_j_*):
-// 13.4 us = 4.4 TB/s, 67 % of the measured copy peak, with 16-byte accesses (a thread owns 4 adjacent columns); the scalar
+// 13.4 us = 4.4 TB/s, 67 % of the measured copy peak (5.1 TB/s = 78 % at 65536 x 200 or 16384 x 1000: the 59 MB job is
+// short enough for launch ramp and tail to show), with 16-byte accesses (a thread owns 4 adjacent columns); the scalar
 // path, used when n_envs % 4 != 0 or a buffer is not 16-byte aligned, reaches 3.2 TB/s -- it is issue-bound (107 instructions
 // per warp row), which the ncu capture showed before the vector path existed.  A cp.async (LDGSTS.32) three-stage variant was
 // slower (26.6 us) and is not kept; 2-D TMA tiles over 256-byte column groups are the next step.  CPU twin: oracle/gae.py, pinned by tests/golden/ppo_returns.npz.
@@ -50,13 +51,14 @@ returns_scan_kernel(const float* __restrict__ reward, const double* __restrict__
     const int lo = t_lo(k), n_t = t_hi(k) - lo;
     acc_t* sv = s_val + (size_t)b * kChunk * kRetCols;
     unsigned char* sf = s_flag + (size_t)b * kChunk * kRetCols;
-    if constexpr (VEC && !MC) {
+    if constexpr (VEC) {
       // 16-byte path (n_envs % 4 == 0, 16-byte aligned buffers): a thread owns 4 adjacent columns of a row, a warp covers 4
       // rows per instruction; kV quads per thread are in flight before the first delta is formed
       constexpr int kV = 2;
       const int n_q = n_t * (kRetCols / 4);
       for (int i0 = (wrp - w0) * 32 + lane; i0 < n_q; i0 += nw * 32 * kV) {
         float4 r4[kV], v4[kV], n4[kV];
+        double2 ra[kV], rb[kV];
         uchar4 d4[kV];
 #pragma unroll
         for (int u = 0; u < kV; ++u) {
@@ -64,10 +66,19 @@ returns_scan_kernel(const float* __restrict__ reward, const double* __restrict__
           const int tt = i >> 3, q = i & 7;
           const bool ok = i < n_q && col0 + 4 * q < E;
           const size_t o = ok ? (size_t)(lo + tt) * E + col0 + 4 * q : 0;
-          r4[u] = __ldcs(reinterpret_cast<const float4*>(reward + o));
-          v4[u] = __ldcs(reinterpret_cast<const float4*>(value + o));
-          n4[u] = __ldcs(reinterpret_cast<const float4*>(next_value + o));
           d4[u] = __ldcs(reinterpret_cast<const uchar4*>(done + o));
+          if (MC) {
+            if (reward64) {
+              ra[u] = __ldcs(reinterpret_cast<const double2*>(reward64 + o));
+              rb[u] = __ldcs(reinterpret_cast<const double2*>(reward64 + o + 2));
+            } else {
+              r4[u] = __ldcs(reinterpret_cast<const float4*>(reward + o));
+            }
+          } else {
+            r4[u] = __ldcs(reinterpret_cast<const float4*>(reward + o));
+            v4[u] = __ldcs(reinterpret_cast<const float4*>(value + o));
+            n4[u] = __ldcs(reinterpret_cast<const float4*>(next_value + o));
+          }
         }
 #pragma unroll
         for (int u = 0; u < kV; ++u) {
@@ -75,18 +86,29 @@ returns_scan_kernel(const float* __restrict__ reward, const double* __restrict__
           if (i >= n_q) continue;
           const int tt = i >> 3, q = i & 7;
           const bool last = tail_is_end && lo + tt == T - 1;
-          float rr[4] = {r4[u].x, r4[u].y, r4[u].z, r4[u].w};
-          const float vv4[4] = {v4[u].x, v4[u].y, v4[u].z, v4[u].w}, nn4[4] = {n4[u].x, n4[u].y, n4[u].z, n4[u].w};
           const unsigned char dd[4] = {d4[u].x, d4[u].y, d4[u].z, d4[u].w};
-          float dl[4];
           unsigned char en[4];
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            if (clip_enable) rr[e] = rr[e] < (float)clip_lo ? (float)clip_lo : (rr[e] > (float)clip_hi ? (float)clip_hi : rr[e]);
-            en[e] = (dd[e] != 0 || last) ? 1 : 0;
-            dl[e] = en[e] ? __fsub_rn(rr[e], vv4[e]) : __fsub_rn(__fadd_rn(rr[e], __fmul_rn(g, nn4[e])), vv4[e]);
+          for (int e = 0; e < 4; ++e) en[e] = (dd[e] != 0 || last) ? 1 : 0;
+          acc_t* dst = sv + tt * kRetCols + 4 * q;
+          if (MC) {
+            double rr[4];
+            if (reward64) { rr[0] = ra[u].x; rr[1] = ra[u].y; rr[2] = rb[u].x; rr[3] = rb[u].y; }
+            else { rr[0] = r4[u].x; rr[1] = r4[u].y; rr[2] = r4[u].z; rr[3] = r4[u].w; }
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              if (clip_enable) rr[e] = rr[e] < clip_lo ? clip_lo : (rr[e] > clip_hi ? clip_hi : rr[e]);
+              dst[e] = (acc_t)rr[e];
+            }
+          } else {
+            float rr[4] = {r4[u].x, r4[u].y, r4[u].z, r4[u].w};
+            const float vv4[4] = {v4[u].x, v4[u].y, v4[u].z, v4[u].w}, nn4[4] = {n4[u].x, n4[u].y, n4[u].z, n4[u].w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              if (clip_enable) rr[e] = rr[e] < (float)clip_lo ? (float)clip_lo : (rr[e] > (float)clip_hi ? (float)clip_hi : rr[e]);
+              dst[e] = (acc_t)(en[e] ? __fsub_rn(rr[e], vv4[e]) : __fsub_rn(__fadd_rn(rr[e], __fmul_rn(g, nn4[e])), vv4[e]));
+            }
           }
-          *reinterpret_cast<float4*>(reinterpret_cast<float*>(sv) + tt * kRetCols + 4 * q) = make_float4(dl[0], dl[1], dl[2], dl[3]);
           *reinterpret_cast<uchar4*>(sf + tt * kRetCols + 4 * q) = make_uchar4(en[0], en[1], en[2], en[3]);
         }
       }
@@ -191,12 +213,13 @@ returns_scan_kernel(const float* __restrict__ reward, const double* __restrict__
     }
     __syncthreads();
     // results of chunk k -> global, coalesced rows, all warps
-    if constexpr (VEC && !MC) {
+    if constexpr (VEC) {
       for (int i = tid; i < n_t * (kRetCols / 4); i += kRetThreads) {
         const int tt = i >> 3, q = i & 7;
         if (col0 + 4 * q < E) {
           const size_t o = (size_t)(lo + tt) * E + col0 + 4 * q;
-          __stcs(reinterpret_cast<float4*>(out + o), *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(sv) + tt * kRetCols + 4 * q));
+          const acc_t* src = sv + tt * kRetCols + 4 * q;
+          __stcs(reinterpret_cast<float4*>(out + o), make_float4((float)src[0], (float)src[1], (float)src[2], (float)src[3]));
           if (valid) *reinterpret_cast<uchar4*>(valid + o) = *reinterpret_cast<const uchar4*>(sf + tt * kRetCols + 4 * q);
         }
       }
@@ -228,9 +251,18 @@ extern "C" int srlx_returns_scan(const float* reward_dev, const double* reward_f
   cudaStream_t st = (cudaStream_t)cuda_stream;
   if (method == SRLX_RETURNS_MC) {
     const size_t sm = (size_t)2 * kChunk * kRetCols * (sizeof(double) + 1);
-    returns_scan_kernel<true, false><<<grid, kRetThreads, sm, st>>>(reward_dev, reward_f64_dev, value_dev, next_value_dev, done_dev, out_dev,
-                                                             valid_dev, (int)n_steps, (int)n_envs, discount, gae_discount,
-                                                             tail_is_episode_end, clip_enable, clip_lo, clip_hi);
+    auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+    const bool vec = n_envs % 4 == 0 && al16(reward_f64_dev ? (const void*)reward_f64_dev : (const void*)reward_dev) && al16(out_dev) &&
+                     (reinterpret_cast<uintptr_t>(done_dev) & 3) == 0 && (!valid_dev || (reinterpret_cast<uintptr_t>(valid_dev) & 3) == 0) &&
+                     !getenv("SRLX_RETURNS_SCALAR");
+    if (vec)
+      returns_scan_kernel<true, true><<<grid, kRetThreads, sm, st>>>(reward_dev, reward_f64_dev, value_dev, next_value_dev, done_dev, out_dev,
+                                                                     valid_dev, (int)n_steps, (int)n_envs, discount, gae_discount,
+                                                                     tail_is_episode_end, clip_enable, clip_lo, clip_hi);
+    else
+      returns_scan_kernel<true, false><<<grid, kRetThreads, sm, st>>>(reward_dev, reward_f64_dev, value_dev, next_value_dev, done_dev, out_dev,
+                                                                      valid_dev, (int)n_steps, (int)n_envs, discount, gae_discount,
+                                                                      tail_is_episode_end, clip_enable, clip_lo, clip_hi);
   } else {
     const size_t sm = (size_t)2 * kChunk * kRetCols * (sizeof(float) + 1);
     // 16-byte accesses when every row of every buffer starts on a 16-byte boundary
