@@ -870,3 +870,71 @@ def test_sequence_targets_equal_oracle(B, T, A, double, rescale, retrace):
         assert got64[b] == (np.asarray(want_m[b]).dtype == np.float64)
         if not rescale:
             assert got_m[b] == float(want_m[b]), (b, got_m[b], want_m[b])
+
+
+# ---- run-loop contract (SURVEY 8b "Run-loop seam", 8f rank 2): the reference's own runner / callback tests, for E env copies ----
+def test_vec_runner_stop_conditions_counters_and_callbacks():
+    """tests/quick/runner/test_runner_play.py:12-58 (train with max_episodes / timeout / max_steps / max_train_count, rollout with
+    max_memory, train_only) and tests/quick/base/run/test_callback.py:42-93 (hook counts, stop from on_step_end), at the batch
+    granularity VecRunner documents: one host iteration = one vector step of E env steps."""
+    import time
+
+    from simple_distributed_rl_b200.engine import EngineConfig
+    from simple_distributed_rl_b200.runner import VecRunner
+
+    E = 32
+    kw = dict(env="Grid", algo="dqn", hidden=(16,), mem_kind=1, multisteps=1, n_envs=E, ring_rows=64, batch_size=8, warmup_size=64,
+              epsilon=0.3, seed=4)
+    r = VecRunner(EngineConfig(**kw))
+    st = r.train(max_steps=10 * E)
+    assert st.total_step == 10 * E and st.end_reason == "max_steps over."           # never overshoots: whole vector steps
+    st = r.train(max_train_count=37)
+    assert st.train_count == 37 and st.end_reason == "max_train_count over."          # exact, as the reference's
+    st = r.train(max_episodes=5)
+    assert st.episode_count >= 5 and st.end_reason == "episode_count over." and len(st.last_episode_rewards) == 1
+    t0 = time.time()
+    st = r.train(timeout=0.3)
+    assert time.time() - t0 >= 0.29 and st.end_reason == "timeout." and st.total_step > 0 and st.train_count > 0
+    with pytest.raises(AssertionError):
+        r.train()                                                                      # the reference asserts on no stop condition too
+
+    r2 = VecRunner(EngineConfig(**kw))
+    st = r2.rollout(max_memory=1000)                                                   # fills the memory, trains nothing
+    assert st.memory_size >= 1000 and st.train_count == 0 and r2.engine.read_state().train_count == 0
+    st = r2.train_only(max_train_count=500)
+    assert st.train_count == 500 and st.total_step == 0
+    r3 = VecRunner(EngineConfig(**kw))
+    st = r3.train_only(max_train_count=10)                                             # empty memory: train() keeps returning early
+    assert st.train_count == 0 and "warmup" in st.end_reason
+
+    class Hooks:
+        def __init__(self, stop_after=0):
+            self.calls, self.stop_after = [], stop_after
+
+        def on_start(self, context, state):
+            self.calls.append("start")
+
+        def on_episodes_begin(self, context, state):
+            self.calls.append("episodes_begin")
+
+        def on_step_end(self, context, state):
+            self.calls.append("step_end")
+            return self.stop_after and self.calls.count("step_end") >= self.stop_after
+
+        def on_episode_end(self, context, state):
+            self.calls.append("episode_end")
+            assert state.last_episode_step > 0
+
+        def on_episodes_end(self, context, state):
+            self.calls.append("episodes_end")
+
+        def on_end(self, context, state):
+            self.calls.append("end")
+
+    h = Hooks()
+    st = r.train(max_steps=20 * E, callbacks=[h])
+    assert h.calls[:2] == ["start", "episodes_begin"] and h.calls[-2:] == ["episodes_end", "end"]
+    assert h.calls.count("step_end") == 20 and 1 <= h.calls.count("episode_end") <= 20  # one per host iteration with finished episodes
+    h2 = Hooks(stop_after=3)
+    st = r.train(max_steps=1000 * E, callbacks=[h2])                                   # a True from on_step_end stops the run
+    assert h2.calls.count("step_end") == 3 and st.total_step == 3 * E and st.end_reason == "callback.on_step_end"
