@@ -25,6 +25,7 @@
 // Applies to: uniform replay, no NoisyNet, any depth / dueling head whose plan fits the shared memory of an SM.
 #include "cluster.cuh"
 #include "net.cuh"
+#include "tree.cuh"
 
 namespace srlx {
 
@@ -42,7 +43,7 @@ struct SPlan {
   int C, B, Bc, M, A, D, BcM, P, S;  // Bc = items per CTA, S = floats per parameter slice (multiple of 4), C * S >= P
   int n_on_rows, n_on_tiles, n_tg_tiles, n_tiles, n_s_tiles;
   size_t off_mbar, off_weff, off_wefft, off_m, off_v, off_g, off_recv, off_wflat, off_wnew, off_slot, off_acts, off_dacts, off_q, off_pick,
-      off_win, off_tq, off_red, off_loss, off_scal, total;
+      off_win, off_tq, off_red, off_loss, off_scal, off_per, off_mem, total;
 };
 
 struct SScal {
@@ -90,13 +91,19 @@ __host__ __device__ inline SPlan make_splan(const srlx_engine& eng, int C) {
   p.off_red = take(64 * 4);
   p.off_loss = take((size_t)kSmMaxCluster * 8);
   p.off_scal = take(64);
+  p.off_per = take((size_t)2 * p.B * 8);  // proportional replay: (slot, IS weight) of every item, two updates deep
   p.total = o;
+  // the replay CTA (proportional replay only) overlays its own layout on the same allocation: hash scratch, batch arrays, TDs
+  p.off_mem = 128;
+  const size_t mem_total = p.off_mem + sizeof(TreeHashScratch) + (size_t)p.B * (8 + 8 + 8 + 4 + 8) + 64;
+  if (eng.mem_kind == SRLX_MEM_PROPORTIONAL && mem_total > p.total) p.total = mem_total;
   return p;
 }
 
 __host__ inline bool small_shape_ok(const srlx_engine& eng) {
-  return eng.mem_kind == SRLX_MEM_UNIFORM && !eng.net.noisy && eng.net.n_layers >= 2 && eng.net.n_params < 60000 &&
-         eng.obs_dim <= SRLX_MAX_OBS;
+  const bool per_ok = eng.mem_kind == SRLX_MEM_UNIFORM ||
+                      (eng.tree != nullptr && (long long)eng.ring_rows * eng.n_envs < (1ll << 30) && eng.batch_size <= 1024);
+  return per_ok && !eng.net.noisy && eng.net.n_layers >= 2 && eng.net.n_params < 60000 && eng.obs_dim <= SRLX_MAX_OBS;
 }
 
 // ---- PTX: DSMEM stores that complete a transaction count on the destination CTA's mbarrier -----------------------------
@@ -471,8 +478,11 @@ __global__ void __launch_bounds__(kSmThreads, 1)
 learner_small_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_updates) {
   extern __shared__ __align__(16) unsigned char smem[];
   cg::cluster_group cluster = cg::this_cluster();
-  const int C = (int)cluster.num_blocks();
+  const bool per = eng.mem_kind == SRLX_MEM_PROPORTIONAL;
+  // proportional replay: the last CTA of the cluster is the replay CTA (SumTree update + next sample), the others compute
+  const int C = (int)cluster.num_blocks() - (per ? 1 : 0);
   const int rank = (int)cluster.block_rank();
+  const bool is_replay = per && rank == C;
   const srlx_net& net = eng.net;
   __shared__ SPlan s_plan;  // the plan lives in shared memory: its per-layer tables are indexed at run time
   if (threadIdx.x == 0) s_plan = make_splan(eng, C);
@@ -524,9 +534,16 @@ learner_small_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_u
     sc->loss_sum = 0.0; sc->last_loss = 0.0; sc->sync_count = 0;
     mbar_init(&mbar[0], 1);
     mbar_init(&mbar[1], 1);
+    mbar_init(&mbar[2], 1);  // compute CTAs: (slot, IS weight) of the next batch from the replay CTA
+    mbar_init(&mbar[3], 1);  // replay CTA: |TD| of the current batch from the compute CTAs
     fence_mbar_init();
-    sm_expect_tx(&mbar[0], (uint32_t)((C - 1) * S * 4 + (rank == 0 ? C * 8 : 0)));
-    sm_expect_tx(&mbar[1], (uint32_t)((C - 1) * S * 4));
+    if (!is_replay) {
+      sm_expect_tx(&mbar[0], (uint32_t)((C - 1) * S * 4 + (rank == 0 ? C * 8 : 0)));
+      sm_expect_tx(&mbar[1], (uint32_t)((C - 1) * S * 4));
+      if (per) sm_expect_tx(&mbar[2], (uint32_t)B * 8);
+    } else {
+      sm_expect_tx(&mbar[3], (uint32_t)B * 8);
+    }
   }
   __syncthreads();
   for (int p = tid; p < P; p += kSmThreads) {
@@ -540,6 +557,69 @@ learner_small_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_u
     }
   }
   cluster.sync();  // mbarriers initialised and every CTA's shared memory ready before any remote store
+  float* perbuf = reinterpret_cast<float*>(smem + pl.off_per);  // [2][B][2]: (slot as int bits, IS weight) of update t, t+1
+
+  if (is_replay) {
+    // ============================ REPLAY CTA (proportional replay): SumTree update(t), then sample(t+1) ============================
+    // ProportionalMemory.update / .sample (proportional_memory.py:131-177) with the block-wide routines of tree.cuh: the update
+    // applies the items in the reference's order (bit-identical node sums), the sampler makes the reference's decisions on the
+    // same node values.  Both run while the compute CTAs are in backward / exchange / Adam of update t.
+    unsigned char* mb = smem + pl.off_mem;
+    TreeHashScratch* hs = reinterpret_cast<TreeHashScratch*>(mb);
+    int64_t* s_idx = reinterpret_cast<int64_t*>(mb + sizeof(TreeHashScratch));
+    double* s_pri = reinterpret_cast<double*>(s_idx + B);
+    double* s_tmp = s_pri + B;
+    float* tdbuf = reinterpret_cast<float*>(s_tmp + B);   // [B][2] |td| of the current batch (from the compute CTAs)
+    float* s_w = tdbuf + 2 * B;
+    __shared__ unsigned long long s_retries;
+    __shared__ double s_maxp;
+    const int64_t cap = (int64_t)R * E, n_nodes = 2 * cap - 1;
+    if (tid == 0) { s_retries = 0; s_maxp = st->max_priority; }
+    __syncthreads();
+    auto sample_and_send = [&](uint64_t tc, uint32_t parb) {
+      const double total = __ldcg(eng.tree);
+      // PriorityReplayBuffer.step is the train_count of the PREVIOUS update() call (priority_replay_buffer.py:232,250)
+      const double stepd = (tc > 0) ? (double)(tc - 1) : 0.0;
+      double beta = eng.per_beta_initial + (1.0 - eng.per_beta_initial) * stepd / eng.per_beta_steps;
+      beta = beta > 1.0 ? 1.0 : beta;
+      per_sample_block(eng.tree, n_nodes, total, B, eng.seed, tc, nullptr, 9999, eng.has_duplicate, s_idx, s_pri, s_tmp, &s_retries);
+      per_weights_block(total, (double)mem_size, beta, B, s_pri, s_tmp, s_w);
+      for (int w = tid; w < C * B; w += kSmThreads) {
+        const int c = w / B, i = w - c * B;
+        const int slot_i = (int)(s_idx[i] - (cap - 1));
+        sm_st_async_f2(sm_mapa(smem_u32(perbuf + ((size_t)parb * B + i) * 2), (uint32_t)c), __int_as_float(slot_i), s_w[i],
+                       sm_mapa(smem_u32(&mbar[2]), (uint32_t)c));
+      }
+      for (int i = tid; i < B; i += kSmThreads) {
+        if (eng.dbg_sample_idx) eng.dbg_sample_idx[i] = s_idx[i];
+        if (eng.dbg_weights) eng.dbg_weights[i] = s_w[i];
+      }
+      __syncthreads();
+    };
+    sample_and_send(tc0, 0);
+    for (uint32_t upd = 0; upd < n_updates; ++upd) {
+      const uint32_t par = upd & 1;
+      if (warp == 0) mbar_wait_sleep(&mbar[3], par);  // all |td| of update `upd` have arrived
+      __syncthreads();
+      if (tid == 0) sm_expect_tx(&mbar[3], (uint32_t)B * 8);
+      for (int i = tid; i < B; i += kSmThreads) s_pri[i] = pow(fabs((double)tdbuf[2 * i]) + eng.per_epsilon, eng.per_alpha);
+      __syncthreads();
+      tree_update_batch(eng.tree, s_idx, s_pri, B, hs);
+      if (tid == 0) {
+        double mp = s_maxp;
+        for (int i = 0; i < B; ++i) mp = (mp < s_pri[i]) ? s_pri[i] : mp;
+        s_maxp = mp;
+      }
+      __syncthreads();
+      if (upd + 1 < n_updates) sample_and_send(tc0 + upd + 1, par ^ 1);
+    }
+    if (tid == 0) {
+      st->max_priority = s_maxp;
+      st->sample_retries += s_retries;
+    }
+    cluster.sync();
+    return;
+  }
 
   // local row r of the online set / target set -> its place in the tile activation areas
   auto x_row = [&](int set_tile0, int r) -> float* {
@@ -552,9 +632,11 @@ learner_small_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_u
   const float b1 = (float)eng.adam_beta1, b2 = (float)eng.adam_beta2, aeps = (float)eng.adam_eps;
   float* disc_pow = red + 32;  // multi_discounts (rainbow.py:175): float32 of discount ** k
   if (tid < M) disc_pow[tid] = (float)pow(eng.discount, (double)tid);
-  if (warp == 1) small_sample(eng, tc0, B, n_valid, g_lo_mod, pick, slot);  // slots of the first update
+  if (warp == 1 && !per) small_sample(eng, tc0, B, n_valid, g_lo_mod, pick, slot);  // slots of the first update
   __syncthreads();
   const uint32_t mb_rs = smem_u32(&mbar[0]), mb_ag = smem_u32(&mbar[1]);
+  // where the replay CTA keeps the |td| of the batch (its own layout, see above), as an address in this CTA's window for mapa
+  float* tdbuf_remote = reinterpret_cast<float*>(smem + pl.off_mem + sizeof(TreeHashScratch) + (size_t)B * 24);
   const int nbM = nb * M;
   const bool one_warp = nbM <= 32;  // the CTA's window steps fit one warp: gather / padding / copy need no block barrier
   float* wnew = reinterpret_cast<float*>(smem + pl.off_wnew);
@@ -563,6 +645,13 @@ learner_small_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_u
     const uint64_t tc = tc0 + upd;
     const uint32_t par = upd & 1;
     const int* slot_t = slot + par * B;  // sampled during the previous update's target phase
+    if (per) {  // proportional replay: (slot, IS weight) of this batch come from the replay CTA
+      if (warp == 0) mbar_wait_sleep(&mbar[2], par);
+      __syncthreads();
+      if (tid == 0) sm_expect_tx(&mbar[2], (uint32_t)B * 8);
+      for (int i = tid; i < B; i += kSmThreads) slot[par * B + i] = __float_as_int(perbuf[((size_t)par * B + i) * 2]);
+      __syncthreads();
+    }
     SRLX_SMSTAMP(0);
     // ---------------------------------------------------------------- 2. gather the CTA's items (loads before stores)
     if (!one_warp || warp == 0) {
@@ -649,10 +738,11 @@ learner_small_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_u
         dw[n_states + BM + i0 * M + w] = w_rew[w];
         dw[n_states + 2 * BM + i0 * M + w] = w_term[w];
       }
-      for (int il = tid; il < nb; il += kSmThreads) {
-        if (eng.dbg_sample_idx) eng.dbg_sample_idx[i0 + il] = (int64_t)slot_t[i0 + il];
-        if (eng.dbg_weights) eng.dbg_weights[i0 + il] = 1.0f;
-      }
+      if (!per)  // (proportional replay: the replay CTA reports the tree indices and IS weights)
+        for (int il = tid; il < nb; il += kSmThreads) {
+          if (eng.dbg_sample_idx) eng.dbg_sample_idx[i0 + il] = (int64_t)slot_t[i0 + il];
+          if (eng.dbg_weights) eng.dbg_weights[i0 + il] = 1.0f;
+        }
     }
     SRLX_SMSTAMP(3);
     // ---------------------------------------------------------------- 3. forward: the row tiles of a layer spread over the warps
@@ -747,11 +837,16 @@ learner_small_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_u
         const int a0 = w_act[il * M + 0];
         const float q = Q[il * A + a0];
         qsa[il] = q;
-        const float d = q - target;  // IS weight 1 on uniform replay (replay_buffer.py:37)
+        // Huber(target * w, q * w): the IS weight sits inside the loss argument (model_torch.py:115); 1 on uniform replay
+        const float wgt = per ? perbuf[((size_t)par * B + i0 + il) * 2 + 1] : 1.f;
+        const float d = q * wgt - target * wgt;
         const float ad = fabsf(d);
         const float delta = (float)eng.huber_delta;
         lsum += (ad <= delta) ? 0.5f * d * d : delta * (ad - 0.5f * delta);
-        const float dq = fminf(fmaxf(d, -delta), delta) / (float)B;
+        const float dq = fminf(fmaxf(d, -delta), delta) * wgt / (float)B;
+        if (per)  // priorities = abs(target - q), unweighted (model_torch.py:123) -> the replay CTA
+          sm_st_async_f2(sm_mapa(smem_u32(tdbuf_remote + 2 * (i0 + il)), (uint32_t)C), fabsf(target - q), 0.f,
+                         sm_mapa(smem_u32(&mbar[3]), (uint32_t)C));
         {  // dueling combine backward (dueling_network.py:51-58) -> d raw of the s row, where the backward pass picks it up
           const size_t trow = (size_t)(il / kRowTile) * np.act_floats + np.x_s[L] + (il % kRowTile) * np.ldx[L];
           float* dr = dacts + trow;
@@ -781,7 +876,7 @@ learner_small_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_u
       // the CTA's partial Huber sum -> CTA 0 (rides on the reduce-scatter barrier)
       if (lane == 0) sm_st_async_f2(sm_mapa(smem_u32(lossbuf + 2 * rank), 0u), lsum, 0.f, sm_mapa(mb_rs, 0u));
     } else if (warp == 1) {
-      if (upd + 1 < n_updates) small_sample(eng, tc + 1, B, n_valid, g_lo_mod, pick, slot + (par ^ 1) * B);
+      if (upd + 1 < n_updates && !per) small_sample(eng, tc + 1, B, n_valid, g_lo_mod, pick, slot + (par ^ 1) * B);
     } else if (tid == 64) {
       small_adam_scalars(eng, (double)(adam0 + upd + 1), sc);
     }
@@ -912,13 +1007,15 @@ int learn_small(const srlx_engine* eng, uint32_t n_updates, uintptr_t cuda_strea
   SRLX_REQUIRE(small_choose(eng, &total, &C) == 1, "learn_small: the row-split learner does not apply to this engine");
   SRLX_CHECK_CUDA(cudaFuncSetAttribute(learner_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)total));
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((unsigned)C, 1, 1);
+  const unsigned n_cta = (unsigned)C + (eng->mem_kind == SRLX_MEM_PROPORTIONAL ? 1u : 0u);  // + the replay CTA
+  if (n_cta > 8) SRLX_CHECK_CUDA(cudaFuncSetAttribute(learner_small_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+  cfg.gridDim = dim3(n_cta, 1, 1);
   cfg.blockDim = dim3(kSmThreads, 1, 1);
   cfg.dynamicSmemBytes = total;
   cfg.stream = (cudaStream_t)cuda_stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = (unsigned)C;
+  attr[0].val.clusterDim.x = n_cta;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
