@@ -22,7 +22,10 @@
 //
 // two DSMEM hops per update instead of two per layer.  Reference path: srl/algorithms/dqn/model_torch.py:90-132,
 // rainbow/model_torch.py:85-122, rainbow/rainbow.py:185-287.  CPU twin: oracle/engine.py::learn.
-// Applies to: uniform replay, no NoisyNet, any depth / dueling head whose plan fits the shared memory of an SM.
+// Proportional replay adds a REPLAY CTA to the cluster: it receives the |TD| of the batch from the compute CTAs, applies
+// ProportionalMemory.update in the reference's order, samples the next batch and sends (slot, IS weight) back, all in the shadow
+// of the compute CTAs' backward / exchanges.
+// Applies to: no NoisyNet, any depth / dueling head whose plan fits the shared memory of an SM.
 #include "cluster.cuh"
 #include "net.cuh"
 #include "tree.cuh"
