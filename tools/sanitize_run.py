@@ -22,7 +22,14 @@ g = DeviceEngine(EngineConfig(**kw2))
 g.run(10, 0)
 g.learn(3)
 torch.cuda.synchronize()
-print("generic:", g.learner_info(), g.read_state().train_count)
+print("dqn 64x64 PER (row-split + replay CTA):", g.learner_info(), g.read_state().train_count)
+kw2b = dict(env="Grid", algo="rainbow", hidden=(32, 16), dueling=None, noisy=True, mem_kind=1, multisteps=1, n_envs=24, ring_rows=4,
+            batch_size=8, warmup_size=24)
+gg = DeviceEngine(EngineConfig(**kw2b))
+gg.run(6, 0)
+gg.learn(3)
+torch.cuda.synchronize()
+print("generic:", gg.learner_info(), gg.read_state().train_count)
 if os.environ.get("SAN_SMALL", "1") == "1":  # learner_small_kernel: uniform replay, plain weights, rows over an 8-CTA cluster
     for kw3 in (dict(env="CartPole-v1", algo="dqn", hidden=(64, 64), mem_kind=0, multisteps=1, n_envs=64, ring_rows=8, batch_size=32,
                      warmup_size=64, epsilon=0.2),
