@@ -34,6 +34,7 @@ namespace srlx {
 
 constexpr int kSmThreads = 512;
 constexpr int kSmMaxCluster = 8;
+constexpr int kSmTreeCache = 4095;  // replay CTA: the top 12 levels of the SumTree in shared memory
 
 // clock64() of thread 0 of CTA 0 at the phase boundaries of the second-to-last update of a launch (tools/phase_clocks.py)
 #define SRLX_SMSTAMP(slot)                                                                                     \
@@ -98,7 +99,7 @@ __host__ __device__ inline SPlan make_splan(const srlx_engine& eng, int C) {
   p.total = o;
   // the replay CTA (proportional replay only) overlays its own layout on the same allocation: hash scratch, batch arrays, TDs
   p.off_mem = 128;
-  const size_t mem_total = p.off_mem + sizeof(TreeHashScratch) + (size_t)p.B * (8 + 8 + 8 + 4 + 8) + 64;
+  const size_t mem_total = p.off_mem + sizeof(TreeHashScratch) + (size_t)p.B * (8 + 8 + 8 + 4 + 8) + 64 + (size_t)kSmTreeCache * 8;
   if (eng.mem_kind == SRLX_MEM_PROPORTIONAL && mem_total > p.total) p.total = mem_total;
   return p;
 }
@@ -119,6 +120,9 @@ __device__ __forceinline__ void sm_st_async_f4(uint32_t raddr, float4 v, uint32_
   asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.f32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(raddr),
                "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "r"(rmbar)
                : "memory");
+}
+__device__ __forceinline__ void sm_st_async_b32(uint32_t raddr, uint32_t v, uint32_t rmbar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(raddr), "r"(v), "r"(rmbar) : "memory");
 }
 __device__ __forceinline__ void sm_st_async_f2(uint32_t raddr, float a, float b, uint32_t rmbar) {
   asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.f32 [%0], {%1, %2}, [%3];" ::"r"(raddr), "f"(a),
@@ -539,11 +543,15 @@ learner_small_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_u
     mbar_init(&mbar[1], 1);
     mbar_init(&mbar[2], 1);  // compute CTAs: (slot, IS weight) of the next batch from the replay CTA
     mbar_init(&mbar[3], 1);  // replay CTA: |TD| of the current batch from the compute CTAs
+    mbar_init(&mbar[4], 1);  // compute CTAs: IS weights of the next batch (sent after the slots: only the target step needs them)
     fence_mbar_init();
     if (!is_replay) {
       sm_expect_tx(&mbar[0], (uint32_t)((C - 1) * S * 4 + (rank == 0 ? C * 8 : 0)));
       sm_expect_tx(&mbar[1], (uint32_t)((C - 1) * S * 4));
-      if (per) sm_expect_tx(&mbar[2], (uint32_t)B * 8);
+      if (per) {
+        sm_expect_tx(&mbar[2], (uint32_t)B * 4);
+        sm_expect_tx(&mbar[4], (uint32_t)B * 4);
+      }
     } else {
       sm_expect_tx(&mbar[3], (uint32_t)B * 8);
     }
@@ -560,7 +568,8 @@ learner_small_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_u
     }
   }
   cluster.sync();  // mbarriers initialised and every CTA's shared memory ready before any remote store
-  float* perbuf = reinterpret_cast<float*>(smem + pl.off_per);  // [2][B][2]: (slot as int bits, IS weight) of update t, t+1
+  int* per_slot = reinterpret_cast<int*>(smem + pl.off_per);          // [2][B] ring slots of the batches of update t, t+1
+  float* per_w = reinterpret_cast<float*>(smem + pl.off_per) + 2 * B;  // [2][B] their IS weights
 
   if (is_replay) {
     // ============================ REPLAY CTA (proportional replay): SumTree update(t), then sample(t+1) ============================
@@ -574,24 +583,37 @@ learner_small_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_u
     double* s_tmp = s_pri + B;
     float* tdbuf = reinterpret_cast<float*>(s_tmp + B);   // [B][2] |td| of the current batch (from the compute CTAs)
     float* s_w = tdbuf + 2 * B;
+    double* cache = reinterpret_cast<double*>(mb + sizeof(TreeHashScratch) + (((size_t)B * 36 + 15) / 16) * 16);
     __shared__ unsigned long long s_retries;
     __shared__ double s_maxp;
     const int64_t cap = (int64_t)R * E, n_nodes = 2 * cap - 1;
+    // whole top levels that fit the cache and the tree's inner nodes
+    int n_cache = 1;
+    while (2 * n_cache + 1 <= kSmTreeCache && 2 * n_cache + 1 <= (int)min((int64_t)kSmTreeCache, cap - 1)) n_cache = 2 * n_cache + 1;
+    for (int i = tid; i < n_cache; i += kSmThreads) cache[i] = __ldcg(eng.tree + i);
     if (tid == 0) { s_retries = 0; s_maxp = st->max_priority; }
     __syncthreads();
     auto sample_and_send = [&](uint64_t tc, uint32_t parb) {
-      const double total = __ldcg(eng.tree);
+      const double total = cache[0];
       // PriorityReplayBuffer.step is the train_count of the PREVIOUS update() call (priority_replay_buffer.py:232,250)
       const double stepd = (tc > 0) ? (double)(tc - 1) : 0.0;
       double beta = eng.per_beta_initial + (1.0 - eng.per_beta_initial) * stepd / eng.per_beta_steps;
       beta = beta > 1.0 ? 1.0 : beta;
-      per_sample_block(eng.tree, n_nodes, total, B, eng.seed, tc, nullptr, 9999, eng.has_duplicate, s_idx, s_pri, s_tmp, &s_retries);
-      per_weights_block(total, (double)mem_size, beta, B, s_pri, s_tmp, s_w);
+      per_sample_block(eng.tree, n_nodes, total, B, eng.seed, tc, nullptr, 9999, eng.has_duplicate, s_idx, s_pri, s_tmp, &s_retries, cache,
+                       n_cache);
+      if (eng.dbg_clock && tid == 0 && tc + 2 == tc0 + n_updates) eng.dbg_clock[23] = clock64();
+      // the slots go out first: the compute CTAs start their gather and forwards while the IS weights are formed
       for (int w = tid; w < C * B; w += kSmThreads) {
         const int c = w / B, i = w - c * B;
-        const int slot_i = (int)(s_idx[i] - (cap - 1));
-        sm_st_async_f2(sm_mapa(smem_u32(perbuf + ((size_t)parb * B + i) * 2), (uint32_t)c), __int_as_float(slot_i), s_w[i],
-                       sm_mapa(smem_u32(&mbar[2]), (uint32_t)c));
+        sm_st_async_b32(sm_mapa(smem_u32(per_slot + (size_t)parb * B + i), (uint32_t)c), (uint32_t)(int)(s_idx[i] - (cap - 1)),
+                        sm_mapa(smem_u32(&mbar[2]), (uint32_t)c));
+      }
+      per_weights_block(total, (double)mem_size, beta, B, s_pri, s_tmp, s_w);
+      if (eng.dbg_clock && tid == 0 && tc + 2 == tc0 + n_updates) eng.dbg_clock[24] = clock64();
+      for (int w = tid; w < C * B; w += kSmThreads) {
+        const int c = w / B, i = w - c * B;
+        sm_st_async_b32(sm_mapa(smem_u32(per_w + (size_t)parb * B + i), (uint32_t)c), __float_as_uint(s_w[i]),
+                        sm_mapa(smem_u32(&mbar[4]), (uint32_t)c));
       }
       for (int i = tid; i < B; i += kSmThreads) {
         if (eng.dbg_sample_idx) eng.dbg_sample_idx[i] = s_idx[i];
@@ -604,10 +626,13 @@ learner_small_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_u
       const uint32_t par = upd & 1;
       if (warp == 0) mbar_wait_sleep(&mbar[3], par);  // all |td| of update `upd` have arrived
       __syncthreads();
+      if (eng.dbg_clock && tid == 0 && upd + 3 == n_updates) eng.dbg_clock[20] = clock64();
       if (tid == 0) sm_expect_tx(&mbar[3], (uint32_t)B * 8);
       for (int i = tid; i < B; i += kSmThreads) s_pri[i] = pow(fabs((double)tdbuf[2 * i]) + eng.per_epsilon, eng.per_alpha);
       __syncthreads();
-      tree_update_batch(eng.tree, s_idx, s_pri, B, hs);
+      if (eng.dbg_clock && tid == 0 && upd + 3 == n_updates) eng.dbg_clock[21] = clock64();
+      tree_update_batch(eng.tree, s_idx, s_pri, B, hs, cache, n_cache);
+      if (eng.dbg_clock && tid == 0 && upd + 3 == n_updates) eng.dbg_clock[22] = clock64();
       if (tid == 0) {
         double mp = s_maxp;
         for (int i = 0; i < B; ++i) mp = (mp < s_pri[i]) ? s_pri[i] : mp;
@@ -651,8 +676,8 @@ learner_small_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_u
     if (per) {  // proportional replay: (slot, IS weight) of this batch come from the replay CTA
       if (warp == 0) mbar_wait_sleep(&mbar[2], par);
       __syncthreads();
-      if (tid == 0) sm_expect_tx(&mbar[2], (uint32_t)B * 8);
-      for (int i = tid; i < B; i += kSmThreads) slot[par * B + i] = __float_as_int(perbuf[((size_t)par * B + i) * 2]);
+      if (tid == 0) sm_expect_tx(&mbar[2], (uint32_t)B * 4);
+      for (int i = tid; i < B; i += kSmThreads) slot[par * B + i] = per_slot[(size_t)par * B + i];
       __syncthreads();
     }
     SRLX_SMSTAMP(0);
@@ -810,6 +835,11 @@ learner_small_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_u
     SRLX_SMSTAMP(5);
     // ---------------------------------------------------------------- 4. targets, Huber gradient (thread per local item) | next sample
     if (warp == 0) {
+      if (per) {  // the IS weights of this batch (the replay CTA sent them after the slots)
+        mbar_wait_sleep(&mbar[4], par);
+        if (lane == 0) sm_expect_tx(&mbar[4], (uint32_t)B * 4);
+        __syncwarp();
+      }
       const float* qon = Q + (size_t)Bc * A;          // online(s')  [BcM][A]
       const float* qtg = Q + (size_t)(Bc + BcM) * A;  // target(s')  [BcM][A]
       float lsum = 0.f;
@@ -841,7 +871,7 @@ learner_small_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_u
         const float q = Q[il * A + a0];
         qsa[il] = q;
         // Huber(target * w, q * w): the IS weight sits inside the loss argument (model_torch.py:115); 1 on uniform replay
-        const float wgt = per ? perbuf[((size_t)par * B + i0 + il) * 2 + 1] : 1.f;
+        const float wgt = per ? per_w[(size_t)par * B + i0 + il] : 1.f;
         const float d = q * wgt - target * wgt;
         const float ad = fabsf(d);
         const float delta = (float)eng.huber_delta;

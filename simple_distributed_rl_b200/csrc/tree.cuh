@@ -11,9 +11,12 @@ namespace srlx {
 // contiguous runs of the BFS array (2,4,8,16,32 doubles), the warp fetches them with independent coalesced loads and
 // then replays the five "val <= tree[left]" decisions out of registers with shuffles -- same comparisons on the same
 // stored values as the sequential walk, but ~4 dependent L2 latencies for a 2M-leaf tree instead of 21.
-__device__ inline int64_t tree_retrieve_warp(const double* __restrict__ tree, int64_t n_nodes, double val) {
-  const int lane = threadIdx.x & 31;
-  int64_t idx = 0;
+__device__ inline int64_t tree_retrieve_warp(const double* __restrict__ tree, int64_t n_nodes, double val, int64_t idx = 0,
+                                             double* node_val = nullptr) {
+  const int lane = threadIdx.x & 31;  // (idx, val): where an earlier part of the same walk -- a cached top of the tree -- arrived
+  // node_val (optional): receives tree[returned index] as fetched during the walk (the chosen child is always among the values
+  // of the last round), which saves the caller a dependent load of the leaf priority; NaN if the walk took no step
+  double chosen = __longlong_as_double(0x7ff8000000000000ll);
   while (true) {
     // level k (1..5) of the subtree rooted at idx occupies [(idx+1)*2^k - 1, (idx+1)*2^k - 1 + 2^k)
     // lane l loads: k=1: l<2, k=2: l<4, k=3: l<8, k=4: l<16, k=5: all 32
@@ -33,17 +36,22 @@ __device__ inline int64_t tree_retrieve_warp(const double* __restrict__ tree, in
       if (left >= n_nodes) { leaf = true; break; }
       const double vk = (k == 1) ? v1 : (k == 2) ? v2 : (k == 3) ? v3 : (k == 4) ? v4 : v5;
       const double tl = __shfl_sync(0xffffffffu, vk, 2 * rel);
+      const double tr = __shfl_sync(0xffffffffu, vk, 2 * rel + 1);
       if (val <= tl) {
         idx = left;
         rel = 2 * rel;
+        chosen = tl;
       } else {
         idx = left + 1;
         val -= tl;
         rel = 2 * rel + 1;
+        chosen = tr;
       }
     }
-    if (leaf) return idx;
-    if (2 * idx + 1 >= n_nodes) return idx;
+    if (leaf || 2 * idx + 1 >= n_nodes) {
+      if (node_val) *node_val = chosen;
+      return idx;
+    }
   }
 }
 
@@ -83,7 +91,8 @@ struct TreeHashScratch {
   unsigned short slot[kTreeHashChunk * 32];  // [item][level] -> table slot, 0xFFFF above the root
 };
 
-__device__ inline void tree_update_batch(double* __restrict__ tree, const int64_t* idx, const double* pri, int n, TreeHashScratch* hs) {
+__device__ inline void tree_update_batch(double* __restrict__ tree, const int64_t* idx, const double* pri, int n, TreeHashScratch* hs,
+                                         double* cache = nullptr, int n_cache = 0) {
   const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31;
   for (int base = 0; base < n; base += kTreeHashChunk) {
     const int m = min(kTreeHashChunk, n - base);
@@ -127,7 +136,10 @@ __device__ inline void tree_update_batch(double* __restrict__ tree, const int64_
     // 3) write back
     for (int h = tid; h < kTreeHashSlots; h += nt) {
       const uint32_t node = hs->keys[h];
-      if (node != kTreeHashEmpty) __stcg(tree + node, hs->vals[h]);
+      if (node != kTreeHashEmpty) {
+        __stcg(tree + node, hs->vals[h]);
+        if (node < (uint32_t)n_cache) cache[node] = hs->vals[h];  // the caller's shared-memory copy of the top levels
+      }
     }
     __syncthreads();
   }
@@ -142,7 +154,9 @@ __device__ inline void tree_update_batch(double* __restrict__ tree, const int64_
 __device__ inline void per_sample_block(const double* __restrict__ tree, int64_t n_nodes, double total, int B,
                                         uint64_t seed, uint64_t rng_step, const double* __restrict__ u01, int max_tries,
                                         int has_duplicate, int64_t* s_idx, double* s_pri, double* s_att,
-                                        unsigned long long* retries) {
+                                        unsigned long long* retries, const double* cache = nullptr, int n_cache = 0) {
+  // cache: optional copy of tree[0 .. n_cache) (n_cache = 2^k - 1 whole top levels) in shared memory, kept equal to the tree by
+  // the caller; the walk takes its first k-1 decisions out of it (same values, same comparisons) and continues in the tree
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nwarps = blockDim.x >> 5;
   auto draw = [&](int i, int k) -> double {
     if (u01) return u01[(size_t)i * max_tries + k];
@@ -154,9 +168,15 @@ __device__ inline void per_sample_block(const double* __restrict__ tree, int64_t
     double p = 0.0;
     int k = 0;
     for (; k < max_tries; ++k) {
-      const double r = draw(i, k) * total;
-      idx = tree_retrieve_warp(tree, n_nodes, r);
-      p = __ldcg(tree + idx);
+      double r = draw(i, k) * total;
+      int64_t top = 0;
+      while (2 * top + 1 < (int64_t)n_cache) {  // warp-uniform
+        const double tl = cache[2 * top + 1];
+        if (r <= tl) top = 2 * top + 1;
+        else { r -= tl; top = 2 * top + 2; }
+      }
+      idx = tree_retrieve_warp(tree, n_nodes, r, top, &p);  // p = tree[idx] as read by the walk's last round
+      if (p != p) p = __ldcg(tree + idx);                   // (no step taken: a one-leaf tree)
       if (p != 0.0) break;
     }
     if (lane == 0) {
