@@ -620,6 +620,9 @@ learner_small_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_u
         if (eng.dbg_weights) eng.dbg_weights[i] = s_w[i];
       }
       __syncthreads();
+      // the first half of this batch's priority update needs only its tree indices: claim the hash slots and fetch the nodes
+      // now, while the compute CTAs gather / forward / form the targets (nothing else writes the tree meanwhile)
+      if (B <= kTreeHashChunk) tree_update_prepare(eng.tree, s_idx, B, hs);
     };
     sample_and_send(tc0, 0);
     for (uint32_t upd = 0; upd < n_updates; ++upd) {
@@ -631,7 +634,8 @@ learner_small_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_u
       for (int i = tid; i < B; i += kSmThreads) s_pri[i] = pow(fabs((double)tdbuf[2 * i]) + eng.per_epsilon, eng.per_alpha);
       __syncthreads();
       if (eng.dbg_clock && tid == 0 && upd + 3 == n_updates) eng.dbg_clock[21] = clock64();
-      tree_update_batch(eng.tree, s_idx, s_pri, B, hs, cache, n_cache);
+      if (B <= kTreeHashChunk) tree_update_apply(eng.tree, s_pri, B, hs, cache, n_cache);
+      else tree_update_batch(eng.tree, s_idx, s_pri, B, hs, cache, n_cache);
       if (eng.dbg_clock && tid == 0 && upd + 3 == n_updates) eng.dbg_clock[22] = clock64();
       if (tid == 0) {
         double mp = s_maxp;

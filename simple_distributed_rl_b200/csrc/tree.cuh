@@ -91,57 +91,68 @@ struct TreeHashScratch {
   unsigned short slot[kTreeHashChunk * 32];  // [item][level] -> table slot, 0xFFFF above the root
 };
 
+// The three steps for one pass of m <= kTreeHashChunk items.  `prepare` needs only the tree indices, so a caller that knows them
+// early (the replay CTA of learner_small.cu: the batch was sampled an update ago) runs it before the priorities exist.
+__device__ inline void tree_update_prepare(const double* __restrict__ tree, const int64_t* idx, int m, TreeHashScratch* hs) {
+  const int tid = threadIdx.x, nt = blockDim.x;
+  for (int h = tid; h < kTreeHashSlots; h += nt) hs->keys[h] = kTreeHashEmpty;
+  __syncthreads();
+  // claim a slot per distinct node; the claimer fetches the node
+  for (int w = tid; w < m * 32; w += nt) {
+    const int i = w >> 5, l = w & 31;
+    const uint64_t ip1 = (uint64_t)idx[i] + 1;
+    unsigned short s = 0xFFFF;
+    if ((ip1 >> l) != 0) {
+      const uint32_t node = (uint32_t)((ip1 >> l) - 1);
+      uint32_t h = (node * 2654435761u) >> 20;  // Fibonacci hash -> 12 bits
+      while (true) {
+        const uint32_t old = atomicCAS(&hs->keys[h], kTreeHashEmpty, node);
+        if (old == kTreeHashEmpty) { hs->vals[h] = __ldcg(tree + node); break; }
+        if (old == node) break;
+        h = (h + 1) & (kTreeHashSlots - 1);
+      }
+      s = (unsigned short)h;
+    }
+    hs->slot[w] = s;
+  }
+  __syncthreads();
+}
+
+__device__ inline void tree_update_apply(double* __restrict__ tree, const double* pri, int m, TreeHashScratch* hs, double* cache, int n_cache) {
+  const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31;
+  // the items in order, one warp, lane = level
+  if (tid < 32) {
+    for (int i = 0; i < m; ++i) {
+      const unsigned short s = hs->slot[i * 32 + lane];
+      double c = 0.0;
+      if (lane == 0) {
+        const double p = pri[i];
+        c = p - hs->vals[s];
+        hs->vals[s] = p;
+      }
+      c = __shfl_sync(0xffffffffu, c, 0);
+      if (lane > 0 && s != 0xFFFF) hs->vals[s] += c;
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+  // write back
+  for (int h = tid; h < kTreeHashSlots; h += nt) {
+    const uint32_t node = hs->keys[h];
+    if (node != kTreeHashEmpty) {
+      __stcg(tree + node, hs->vals[h]);
+      if (node < (uint32_t)n_cache) cache[node] = hs->vals[h];  // the caller's shared-memory copy of the top levels
+    }
+  }
+  __syncthreads();
+}
+
 __device__ inline void tree_update_batch(double* __restrict__ tree, const int64_t* idx, const double* pri, int n, TreeHashScratch* hs,
                                          double* cache = nullptr, int n_cache = 0) {
-  const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31;
   for (int base = 0; base < n; base += kTreeHashChunk) {
     const int m = min(kTreeHashChunk, n - base);
-    for (int h = tid; h < kTreeHashSlots; h += nt) hs->keys[h] = kTreeHashEmpty;
-    __syncthreads();
-    // 1) claim a slot per distinct node; the claimer fetches the node
-    for (int w = tid; w < m * 32; w += nt) {
-      const int i = w >> 5, l = w & 31;
-      const uint64_t ip1 = (uint64_t)idx[base + i] + 1;
-      unsigned short s = 0xFFFF;
-      if ((ip1 >> l) != 0) {
-        const uint32_t node = (uint32_t)((ip1 >> l) - 1);
-        uint32_t h = (node * 2654435761u) >> 20;  // Fibonacci hash -> 12 bits
-        while (true) {
-          const uint32_t old = atomicCAS(&hs->keys[h], kTreeHashEmpty, node);
-          if (old == kTreeHashEmpty) { hs->vals[h] = __ldcg(tree + node); break; }
-          if (old == node) break;
-          h = (h + 1) & (kTreeHashSlots - 1);
-        }
-        s = (unsigned short)h;
-      }
-      hs->slot[w] = s;
-    }
-    __syncthreads();
-    // 2) the items in order, one warp, lane = level
-    if (tid < 32) {
-      for (int i = 0; i < m; ++i) {
-        const unsigned short s = hs->slot[i * 32 + lane];
-        double c = 0.0;
-        if (lane == 0) {
-          const double p = pri[base + i];
-          c = p - hs->vals[s];
-          hs->vals[s] = p;
-        }
-        c = __shfl_sync(0xffffffffu, c, 0);
-        if (lane > 0 && s != 0xFFFF) hs->vals[s] += c;
-        __syncwarp();
-      }
-    }
-    __syncthreads();
-    // 3) write back
-    for (int h = tid; h < kTreeHashSlots; h += nt) {
-      const uint32_t node = hs->keys[h];
-      if (node != kTreeHashEmpty) {
-        __stcg(tree + node, hs->vals[h]);
-        if (node < (uint32_t)n_cache) cache[node] = hs->vals[h];  // the caller's shared-memory copy of the top levels
-      }
-    }
-    __syncthreads();
+    tree_update_prepare(tree, idx + base, m, hs);
+    tree_update_apply(tree, pri + base, m, hs, cache, n_cache);
   }
 }
 
