@@ -671,6 +671,9 @@ learner_small_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_u
   float* tdbuf_remote = reinterpret_cast<float*>(smem + pl.off_mem + sizeof(TreeHashScratch) + (size_t)B * 24);
   const int nbM = nb * M;
   const bool one_warp = nbM <= 32;  // the CTA's window steps fit one warp: gather / padding / copy need no block barrier
+  // uniform replay samples update t+1 during the target step of update t: warp 2 then issues that batch's ring loads before the
+  // backward pass and parks them in registers until the pass no longer needs the current rows
+  const bool can_prefetch = !per && one_warp && D <= 4;
   float* wnew = reinterpret_cast<float*>(smem + pl.off_wnew);
 
   for (uint32_t upd = 0; upd < n_updates; ++upd) {
@@ -686,7 +689,9 @@ learner_small_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_u
     }
     SRLX_SMSTAMP(0);
     // ---------------------------------------------------------------- 2. gather the CTA's items (loads before stores)
-    if (!one_warp || warp == 0) {
+    // (uniform replay knows its next batch an update ahead: from the second update on the rows were fetched across the
+    // previous update's backward pass, see "prefetch" below)
+    if ((!one_warp || warp == 0) && !(can_prefetch && upd > 0)) {
       for (int w = tid; w < nbM; w += kSmThreads) {
         const int il = w / M, k = w - il * M;
         const int s0 = slot_t[i0 + il];
@@ -919,6 +924,27 @@ learner_small_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_u
     }
     __syncthreads();
     SRLX_SMSTAMP(6);
+    // ---------------------------------------------------------------- prefetch: the next batch's ring rows -> registers (warp 2)
+    int pf_a = 0;
+    float pf_rw = 0.f, pf_xv[4] = {0.f, 0.f, 0.f, 0.f}, pf_sv[4] = {0.f, 0.f, 0.f, 0.f};
+    int pf_tm = 0, pf_dn = 0;
+    const bool do_prefetch = can_prefetch && upd + 1 < n_updates && warp == 2 && lane < nbM;
+    if (do_prefetch) {
+      const int* slot_n = slot + (par ^ 1) * B;
+      const int il = lane / M, k = lane - il * M;
+      const int s0 = slot_n[i0 + il];
+      const int rho = s0 / E, e = s0 - rho * E;
+      const int sk = ((rho + k) % R) * E + e;
+      pf_a = __ldcg(eng.ring_action + sk);
+      pf_rw = __ldcg(eng.ring_reward + sk);
+      pf_tm = (int)__ldcg(eng.ring_term + sk);
+      pf_dn = (int)__ldcg(eng.ring_done + sk);
+#pragma unroll
+      for (int d = 0; d < 4; ++d) {
+        pf_xv[d] = d < D ? __ldcg(eng.ring_next_obs + (size_t)sk * D + d) : 0.f;
+        pf_sv[d] = (d < D && k == 0) ? __ldcg(eng.ring_obs + (size_t)s0 * D + d) : 0.f;
+      }
+    }
     // ---------------------------------------------------------------- 5. backward on the CTA's s rows -> G (stored, not accumulated)
 #pragma unroll 1
     for (int tile = 0; tile < pl.n_s_tiles; ++tile) {
@@ -930,6 +956,25 @@ learner_small_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_u
     }
     sm_fence_proxy_async();  // this thread's gradient stores -> visible to the bulk-copy (async) proxy
     __syncthreads();
+    if (do_prefetch) {  // the backward pass is done with the current rows: the next batch's rows take their place
+      // (first use of the prefetched registers: the empty asm keeps the compiler from converting / consuming them any earlier,
+      // which would make warp 2 wait for the loads at the start of the backward pass instead of here)
+      asm volatile("" : "+r"(pf_a), "+r"(pf_tm), "+r"(pf_dn), "+f"(pf_rw), "+f"(pf_xv[0]), "+f"(pf_xv[1]), "+f"(pf_xv[2]), "+f"(pf_xv[3]),
+                        "+f"(pf_sv[0]), "+f"(pf_sv[1]), "+f"(pf_sv[2]), "+f"(pf_sv[3]));
+      const int il = lane / M, k = lane - il * M;
+      float* xt = x_row(pl.n_on_tiles, lane);
+      float* xs = x_row(0, il);
+#pragma unroll
+      for (int d = 0; d < 4; ++d)
+        if (d < D) {
+          xt[d] = pf_xv[d];
+          if (k == 0) xs[d] = pf_sv[d];
+        }
+      w_act[lane] = pf_a;
+      w_rew[lane] = pf_rw;
+      w_term[lane] = (float)pf_tm;
+      w_done[lane] = (int)pf_dn;
+    }
     SRLX_SMSTAMP(7);
     // ---------------------------------------------------------------- 6. reduce-scatter the partial gradients, Adam on the slice
     {
