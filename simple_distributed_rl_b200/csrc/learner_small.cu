@@ -671,7 +671,7 @@ learner_small_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_u
   float* tdbuf_remote = reinterpret_cast<float*>(smem + pl.off_mem + sizeof(TreeHashScratch) + (size_t)B * 24);
   const int nbM = nb * M;
   const bool one_warp = nbM <= 32;  // the CTA's window steps fit one warp: gather / padding / copy need no block barrier
-  // uniform replay samples update t+1 during the target step of update t: warp 2 then issues that batch's ring loads before the
+  // uniform replay samples update t+1 during the target step of update t: the last warp then issues that batch's ring loads before the
   // backward pass and parks them in registers until the pass no longer needs the current rows
   const bool can_prefetch = !per && one_warp && D <= 4;
   float* wnew = reinterpret_cast<float*>(smem + pl.off_wnew);
@@ -924,11 +924,11 @@ learner_small_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_u
     }
     __syncthreads();
     SRLX_SMSTAMP(6);
-    // ---------------------------------------------------------------- prefetch: the next batch's ring rows -> registers (warp 2)
+    // ---------------------------------------------------------------- prefetch: the next batch's ring rows -> registers (last warp)
     int pf_a = 0;
     float pf_rw = 0.f, pf_xv[4] = {0.f, 0.f, 0.f, 0.f}, pf_sv[4] = {0.f, 0.f, 0.f, 0.f};
     int pf_tm = 0, pf_dn = 0;
-    const bool do_prefetch = can_prefetch && upd + 1 < n_updates && warp == 2 && lane < nbM;
+    const bool do_prefetch = can_prefetch && upd + 1 < n_updates && warp == nwarps - 1 && lane < nbM;  // the last warp: least work in the backward stages
     if (do_prefetch) {
       const int* slot_n = slot + (par ^ 1) * B;
       const int il = lane / M, k = lane - il * M;
