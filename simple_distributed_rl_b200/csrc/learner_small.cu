@@ -189,8 +189,10 @@ __device__ __forceinline__ void adam_apply(float& pp, float& mm, float& vv, floa
 //      units ascending, one fmaf per term -> bit-identical gradients, ~6x fewer shared-memory loads per FMA) -------------
 // dW[u][k] += sum_r dY[r][u] * X[r][k],  db[u] += sum_r dY[r][u]        thread tile 4 units x 4 inputs
 __device__ __forceinline__ void small_dw(const float* __restrict__ dY, int ldy, const float* __restrict__ X, int ldx, int R, int U,
-                                         int K, float* __restrict__ Gw, float* __restrict__ Gb, bool accum) {
-  const int tid = threadIdx.x, nt = blockDim.x;
+                                         int K, float* __restrict__ Gw, float* __restrict__ Gb, bool accum, int rot) {
+  // rot: the thread that takes item 0 -- the sweeps of different layers start on different warps, so they run side by side
+  const int nt = blockDim.x;
+  const int tid = ((int)threadIdx.x - rot + nt) % nt;
   const int n_kt = (K + 3) >> 2, n_ut = (U + 3) >> 2;
   for (int item = tid; item < n_ut * n_kt; item += nt) {
     const int ut = item / n_kt, kt = item - ut * n_kt;
@@ -351,7 +353,7 @@ __device__ inline void small_all_dw(const srlx_net& net, const NetPlan& pl, cons
 #pragma unroll 1
   for (int l = L - 2; l >= 0; --l)
     small_dw(dacts + pl.x_s[l + 1], pl.ldx[l + 1], acts + pl.x_s[l], pl.ldx[l], R, net.out_dim[l], net.k_dim[l], G + net.w_off[l],
-             G + net.b_off[l], accum);
+             G + net.b_off[l], accum, ((nt >> 1) + (L - 2 - l) * 96) % nt);
 }
 
 // Output layer of a row tile, thread per (row, output): float4 dot products instead of a warp per row
