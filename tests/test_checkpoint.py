@@ -294,3 +294,43 @@ def test_reference_memory_imports_and_reexports_unchanged(srl_mod, algo, M, mem,
         assert trainer.train_count == before + 1
     finally:
         sys.path.remove(REF)
+
+
+def test_restore_edge_cases():
+    """Fewer items than env columns -> an empty ring (nothing sampleable, counters at zero); a ReplayBuffer backup that has wrapped
+    (idx in the middle of the list) is read oldest first; more items than the ring holds -> the newest survive."""
+    E, R, M = 4, 5, 1
+
+    def item(v):
+        return [np.full(2, v, np.float32), np.full(2, v + 0.5, np.float32), [0, 1, 0], float(v), 1, []]
+
+    few = ck.memory_restore([[[item(1), item(2)], 2], None], E, R, M, 3, 2, False)
+    assert few.vec_steps == 0 and few.valid_rows() == (0, 0)
+    # a wrapped ReplayBuffer of capacity 8: memory[idx:] are the oldest
+    mem = [item(v) for v in (8, 9, 2, 3, 4, 5, 6, 7)]
+    ring = ck.memory_restore([[mem, 2], None], E, R, M, 3, 2, False)
+    n_g = ring.valid_rows()[1]
+    assert n_g == 2 and ring.vec_steps == 2
+    got = sorted(float(ring.reward[s]) for s in range(n_g * E))
+    assert got == [2.0, 3.0, 4.0, 5.0, 6.0, 7.0, 8.0, 9.0]
+    # column c holds the c-th contiguous chunk of the oldest-first stream 2..9: (2,3), (4,5), (6,7), (8,9)
+    assert [float(ring.reward[0 * E + c]) for c in range(E)] == [2.0, 4.0, 6.0, 8.0]
+    assert [float(ring.reward[1 * E + c]) for c in range(E)] == [3.0, 5.0, 7.0, 9.0]
+    # 30 items into a ring of 4 x 5: the newest 20 survive
+    big = ck.memory_restore([[[item(v) for v in range(30)], 30], None], E, R, M, 3, 2, False)
+    assert big.valid_rows()[1] == R and sorted(float(big.reward[s]) for s in range(R * E)) == [float(v) for v in range(10, 30)]
+
+
+def test_proportional_backup_of_other_capacity_restores_by_item():
+    """ProportionalMemory.backup() written with another capacity (proportional_memory.py:196-205 re-adds item by item): the
+    items and their leaf priorities land in the ring, the tree is rebuilt over them."""
+    E, R, M = 2, 6, 1
+    cap_src, n = 7, 6
+    leaves = np.array([0.5, 1.5, 0.25, 2.0, 1.0, 0.75, 0.0])
+    tree = ck.build_sum_tree(leaves, cap_src)
+    data = [[np.full(2, i, np.float32), np.full(2, i + 1, np.float32), [1, 0], float(i), 1, []] for i in range(n)] + [None]
+    ring = ck.memory_restore([[cap_src, 2.0, n, n % cap_src, tree.tolist(), data], None], E, R, M, 2, 2, True)
+    assert ring.valid_rows() == (0, 3) and ring.max_priority == 2.0
+    items, pri = ck.export_items(ring)
+    assert [it[3] for it in items] == [0.0, 1.0, 2.0, 3.0, 4.0, 5.0]
+    np.testing.assert_array_equal(pri, leaves[:n])
