@@ -327,7 +327,7 @@ def own_arm(args):
     achieved = bytes_per_update * min(U, chunk) / (learn_ms_per_launch * 1e-3) / 1e9
     traffic, traffic_src = None, None
     try:  # dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the committed ncu --set full captures
-        for fn, note in (("r1_j_learner_ncu_summary.json", "256 updates per launch"), ("r1_i_learner_small_ncu_summary.json", "409 updates per launch")):
+        for fn, note in (("r1_j_learner_ncu_summary.json", "256 updates per launch"), ("r1_o_learner_small_ncu_summary.json", "1024 updates per launch")):
             for k in json.load(open(os.path.join(ROOT, "profiles", fn))):
                 if kname in k["kernel"] and int(k.get("cluster", 0)) == cluster:
                     traffic, traffic_src = k["dram_bytes"], f"profiles/{fn} ({note})"
