@@ -5,13 +5,15 @@ Workload (configs[2], the configuration the metric is quoted on; fits one GPU):
   Rainbow as the reference implements it (DoubleDQN + dueling(512,) + NoisyNet + 3-step Retrace + proportional PER;
   srl/algorithms/rainbow/rainbow.py:57-108) on CartPole-v1, 8192 vectorised envs per GPU, SumTree replay of 2M
   transitions per GPU (ring 256 rows x 8192 envs), batch 32, lr 1e-3, target sync every 1000 updates.
-One bench "step" = ONE vector step of all E envs (E env steps: policy forward, env.step, ring write, replay add)
-followed by E/train_interval trainer updates (RunContext.train_interval, srl/base/context.py:60; default here 10, i.e.
+One bench "step" = S = --vec-steps-per-step (default 16) consecutive passes of the hot path, each pass ONE vector step of all
+E envs (E env steps: policy forward, env.step, ring write, replay add) followed by E/train_interval trainer updates (RunContext.train_interval, srl/base/context.py:60; default here 10, i.e.
 one Trainer.train() per 10 env steps -- the ratio the two north-star targets, >= 1M env-steps/s and >= 100k updates/s,
 imply; the reference's own default of 1 makes env-steps/s == updates/s) -- all enqueued on one CUDA stream with no host round trip in between.
 
   python bench.py [--gpus N] [--steps K] [--warmup W]            own arm (CUDA, libsrlx.so)
-  python bench.py --impl reference [...]                          the CPU path (oracle port of the reference loop)
+  python bench.py --impl reference [...]                          the CPU path: the UNMODIFIED reference (srl.Runner.train from
+                                                                  baseline/_ref, one process per host core) when that install is
+                                                                  present, else the oracle port of the loop (oracle/engine.py)
 N > 1: launched under torchrun, one rank per GPU; each rank owns its env shard + replay shard (weak scaling);
 see DESIGN.md "Multi-GPU" for what is exchanged.
 """
@@ -66,11 +68,12 @@ def workload_config(args, world):
     return {"workload": name,
             "n_envs_per_gpu": args.envs, "replay_capacity_per_gpu": args.envs * args.ring_rows, "batch_size": 32,
             "multisteps": 3 if args.workload == "rainbow" else 1, "train_interval": args.train_interval,
-            "updates_per_step_per_gpu": args.envs // args.train_interval,
-            "env_steps_per_step": args.envs * world,
+            "vec_steps_per_step": args.vec_steps_per_step,
+            "updates_per_step_per_gpu": (args.envs // args.train_interval) * args.vec_steps_per_step,
+            "env_steps_per_step": args.envs * world * args.vec_steps_per_step,
             "parallelism": (f"shard{world}: env/replay/SumTree shards + learner replica per GPU, parameters averaged by one "
                             f"NCCL all-reduce per step") if world > 1 else "single",
-            "l2": "flushed between timed steps (256 MiB write)"}
+            "l2": "flushed between timed steps (256 MiB write), device-timed and e2e alike"}
 
 
 def algorithmic_bytes_per_update(n_params_total, batch=32, multisteps=3, depth=21):
@@ -136,8 +139,63 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------------------------------------
-# CPU path (oracle port of the reference loop) -- used by cpu_baseline and by --impl reference
+# CPU path -- used by cpu_baseline and by --impl reference
+#   kind "reference": the UNMODIFIED reference, srl.Runner(...).train() = core_play.play (srl/base/run/core_play.py:115-214), from
+#                     the offline install under baseline/_ref (python -m pip install --no-index --no-deps --target baseline/_ref
+#                     <copy of /root/reference>; __graft_entry__.build() makes it when /root/reference is present), on the CPU
+#                     restatement of CartPole-v1 registered with the reference's env registry (oracle/ref_envs.py; gymnasium is absent)
+#   kind "port":      the oracle's sequential port of the vectorised loop (oracle/engine.py) when that install is missing
 # ---------------------------------------------------------------------------------------------------------------------
+REF_DIR = os.path.join(ROOT, "baseline", "_ref")
+
+
+def reference_available():
+    return os.path.isfile(os.path.join(REF_DIR, "srl", "__init__.py"))
+
+
+def cpu_reference_run(train_interval, env_steps, warmup_env_steps, threads, workload="rainbow", capacity=2_000_000):
+    """One process of the unmodified reference: srl.Runner("CartPole-v1", <workload config>).train(max_steps=env_steps,
+    train_interval=train_interval) on one env (the reference's loop is one env per process), memory.capacity as the workload
+    says, after a warm-up train() that fills the memory past warmup_size.  Rates as print_progress.py:224-237 defines them."""
+    import torch
+
+    torch.set_num_threads(max(1, threads))
+    if REF_DIR not in sys.path:
+        sys.path.insert(0, REF_DIR)
+    import srl
+    from srl.algorithms import dqn, rainbow
+
+    from oracle.ref_envs import register_restated_envs
+
+    try:
+        register_restated_envs()
+    except AssertionError:
+        pass  # already registered in this process
+    if workload == "rainbow":
+        c = rainbow.Config(multisteps=3, enable_noisy_dense=True, enable_double_dqn=True, batch_size=32, lr=1e-3, discount=0.99,
+                           target_model_update_interval=1000)  # hidden block default: dueling (512,)
+        c.memory.set_proportional()
+    else:
+        c = dqn.Config(batch_size=32, lr=1e-3, discount=0.99, target_model_update_interval=1000, enable_double_dqn=True, epsilon=0.1)
+        c.hidden_block.set((64, 64) if workload == "dqn" else (512,))
+        c.memory.set_replay_buffer()
+    c.framework = "torch"
+    c.memory.capacity = int(capacity)
+    c.memory.warmup_size = 1000
+    c.memory.compress = False
+    runner = srl.Runner("CartPole-v1", c)
+    runner.set_device("CPU")
+    runner.set_seed(1 + os.getpid() % 1000)
+    runner.train(max_steps=max(1200, warmup_env_steps), train_interval=train_interval, enable_progress=False)
+    t0 = time.perf_counter()
+    st = runner.train(max_steps=env_steps, train_interval=train_interval, enable_progress=False)
+    dt = time.perf_counter() - t0
+    return dict(env_steps_per_s=st.total_step / dt, updates_per_s=st.train_count / dt, env_steps=int(st.total_step), seconds=dt,
+                sample=f"srl.Runner('CartPole-v1', {workload} config).train(max_steps={env_steps}, train_interval={train_interval}): "
+                       f"1 env per process (the reference's loop), memory.capacity {capacity}, batch 32, device CPU, torch threads="
+                       f"{threads}, CartPole-v1 = CPU restatement registered with the reference (gymnasium absent)")
+
+
 def cpu_port_run(n_envs, train_interval, steps, warmup, budget_s, threads, workload="rainbow"):
     """Times `steps` steps of the sequential CPU port (oracle/engine.py) on a bounded sample of the workload:
     n_envs env copies instead of 8192, same network / algorithm / train_interval."""
@@ -166,38 +224,52 @@ def cpu_port_run(n_envs, train_interval, steps, warmup, budget_s, threads, workl
         if budget_s and time.perf_counter() - t0 > budget_s:
             break
     dt = time.perf_counter() - t0
-    return dict(env_steps_per_s=done * n_envs / dt, updates_per_s=(orc.train_count - tc0) / dt, steps=done, seconds=dt,
-                sample=f"{done} steps x ({n_envs} env copies + {U} updates), same net/algorithm/train_interval, "
-                       f"sequential CPU port (oracle/engine.py), torch threads={threads}")
+    return dict(env_steps_per_s=done * n_envs / dt, updates_per_s=(orc.train_count - tc0) / dt, env_steps=done * n_envs, seconds=dt,
+                sample=f"{done} passes x ({n_envs} env copies + {U} updates), replay capacity {64 * n_envs}, same net/algorithm/"
+                       f"train_interval, sequential CPU port (oracle/engine.py), torch threads={threads}")
 
 
 def _cpu_worker(a):
-    return cpu_port_run(*a)
+    kind, a = a[0], a[1:]
+    return cpu_reference_run(*a) if kind == "reference" else cpu_port_run(*a)
 
 
 def reference_arm(args):
-    """All host cores: one sequential replica of the loop per core, each on its own shard of env copies (the same
-    sharding the GPU arm uses across ranks; the reference's own multi-core mode, train_mp, likewise runs one
-    sequential actor loop per process, srl/base/run/play_mp.py:539-552)."""
+    """All host cores: one sequential replica of the loop per core (the same sharding the GPU arm uses across ranks; the
+    reference's own multi-core mode, train_mp, likewise runs one sequential actor loop per process,
+    srl/base/run/play_mp.py:539-552).  One bench step = --ref-env-steps-per-step env steps in every process."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     import multiprocessing as mp
 
     cores = min(os.cpu_count() or 1, 64)
-    a = (args.cpu_envs, args.train_interval, args.steps, min(args.warmup, 1), 150.0, 1, args.workload)
+    K = max(1, args.steps)
+    if reference_available() and not args.force_port:
+        kind = "reference"
+        a = (kind, args.train_interval, K * args.ref_env_steps_per_step, max(1, args.warmup) * args.ref_env_steps_per_step, 1,
+             args.workload, args.envs * args.ring_rows)
+    else:
+        kind = "port"
+        a = (kind, args.cpu_envs, args.train_interval, K * max(1, args.ref_env_steps_per_step // args.cpu_envs), 1, 150.0, 1, args.workload)
     with mp.get_context("spawn").Pool(cores) as pool:
         rs = pool.map(_cpu_worker, [a] * cores)
-    r = dict(env_steps_per_s=sum(x["env_steps_per_s"] for x in rs), updates_per_s=sum(x["updates_per_s"] for x in rs),
-             steps=min(x["steps"] for x in rs), seconds=max(x["seconds"] for x in rs),
-             sample=f"{cores} processes x [" + rs[0]["sample"] + "]")
-    line = {"impl": "reference", "metric": METRIC, "value": r["env_steps_per_s"], "unit": UNIT, "n_gpus": args.gpus,
-            "steps": r["steps"], "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * r["seconds"] / max(1, r["steps"]),
+    secs = max(x["seconds"] for x in rs)
+    env_steps = sum(x["env_steps"] for x in rs)
+    value = env_steps / secs
+    upd = sum(x["updates_per_s"] * x["seconds"] for x in rs) / secs
+    sample = f"{cores} processes x [" + rs[0]["sample"] + "]"
+    cfg = workload_config(args, 1)
+    # the workload keys are the own arm's; "cpu_arm" says what the CPU processes actually ran (a bounded sample of that workload)
+    cfg["cpu_arm"] = {"kind": kind, "processes": cores, "n_envs_per_process": 1 if kind == "reference" else args.cpu_envs,
+                      "replay_capacity_per_process": args.envs * args.ring_rows if kind == "reference" else 64 * args.cpu_envs,
+                      "env_steps_per_step_all_processes": env_steps // K, "sample": sample}
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": K, "warmup": max(1, args.warmup), "ms_per_step": 1e3 * secs / K,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "trainer_updates_per_sec": r["updates_per_s"],
-            "config": workload_config(args, 1),
-            "cpu_baseline": {"value": r["env_steps_per_s"], "unit": UNIT, "cores": cores, "kind": "port", "sample": r["sample"]},
-            "e2e": {"value": r["env_steps_per_s"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "trainer_updates_per_sec": upd, "config": cfg,
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
 
@@ -224,7 +296,7 @@ def own_arm(args):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
 
-    E, R, TI = args.envs, args.ring_rows, args.train_interval
+    E, R, TI, S = args.envs, args.ring_rows, args.train_interval, args.vec_steps_per_step
     U = E // TI
     kw = workload_kwargs(args, n_envs=E, ring_rows=R, warmup_size=1000, seed=1 + rank)
     runner = VecRunner(EngineConfig(**kw), device=dev)
@@ -240,18 +312,32 @@ def own_arm(args):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    def one_step(events=None):
+        """S passes of (vector step + U updates); the replicas' online parameters are averaged once per step (N > 1)."""
+        t_roll = []
+        for _ in range(S):
+            if events is not None:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+            eng.vec_step()
+            if events is not None:
+                e1.record()
+                t_roll.append((e0, e1))
+            eng.learn(U)
+        if world > 1:  # replicas' online parameters averaged over NVLink once per step (parallel.py)
+            parallel.average_parameters(sync_tensors)
+        return t_roll
+
     # fill the whole ring so sampling spans the full 2M-slot replay (steady state), then warm up
     eng.run(R, 0)
     for _ in range(max(3, args.warmup)):
-        eng.vec_step()
-        eng.learn(U)
-        if world > 1:
-            parallel.average_parameters(sync_tensors)
+        one_step()
     barrier()
 
-    # ---- timed region: K steps, device-timed per phase, L2 flushed between steps ------------------------------
+    # ---- timed region: K steps, device-timed, L2 flushed between steps ----------------------------------------------
     K = args.steps
-    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(K)]
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(K)]
+    rolls = []
     st0 = eng.read_state()
     launches0 = lib.srlx_launch_count()
     clocks = ClockSampler("GPU-" + str(torch.cuda.get_device_properties(dev).uuid).replace("GPU-", ""))
@@ -262,20 +348,16 @@ def own_arm(args):
     for k in range(K):
         flush.zero_()
         ev[k][0].record()
-        eng.vec_step()
+        rolls.extend(one_step(events=True))
         ev[k][1].record()
-        eng.learn(U)
-        if world > 1:  # replicas' online parameters averaged over NVLink once per step (parallel.py)
-            parallel.average_parameters(sync_tensors)
-        ev[k][2].record()
     barrier()
     t_wall = time.perf_counter() - t_wall0
     clk = clocks.stop() if rank == 0 else None
     launches = lib.srlx_launch_count() - launches0
     st1 = eng.read_state()
-    t_roll = sum(ev[k][0].elapsed_time(ev[k][1]) for k in range(K))  # ms
-    t_learn = sum(ev[k][1].elapsed_time(ev[k][2]) for k in range(K))
-    t_dev = t_roll + t_learn
+    t_dev = sum(ev[k][0].elapsed_time(ev[k][1]) for k in range(K))  # ms
+    t_roll = sum(a.elapsed_time(b) for a, b in rolls)
+    t_learn = t_dev - t_roll  # learner launches (+ the once-per-step parameter average when N > 1)
     tt = torch.tensor([t_dev, t_roll, t_learn], dtype=torch.float64, device=dev)
     cnt = torch.tensor([st1.total_step - st0.total_step, st1.train_count - st0.train_count], dtype=torch.float64, device=dev)
     if world > 1:
@@ -286,10 +368,20 @@ def own_arm(args):
     value = env_steps / (t_dev * 1e-3)
     upd_rate = updates / (t_dev * 1e-3)
 
-    # ---- e2e: the same K steps through the public API (VecRunner.train), host in the loop ----------------------
+    # ---- e2e: the same K steps through the public API (VecRunner.train), host in the loop, L2 flushed once per bench step -----
+    class _Flush:
+        def __init__(self):
+            self.n = 0
+
+        def on_step_end(self, context, state):
+            self.n += 1
+            if self.n % S == 0:
+                flush.zero_()
+            return False
+
     barrier()
     t0 = time.perf_counter()
-    rs = runner.train(max_steps=K * E, train_interval=TI)
+    rs = runner.train(max_steps=K * S * E, train_interval=TI, callbacks=[_Flush()])
     barrier()
     t_e2e = time.perf_counter() - t0
     e2e_t = torch.tensor([t_e2e], dtype=torch.float64, device=dev)
@@ -298,20 +390,24 @@ def own_arm(args):
         dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
         dist.all_reduce(e2e_n, op=dist.ReduceOp.SUM)
     e2e_value = float(e2e_n.item()) / float(e2e_t.item())
-    n_launch_per_step = 3
+    kname, cluster, smem = eng.learner_info()
+    chunk = 256 if kname == "learner_fast_kernel" else U  # srlx_learn issues the fast kernel in launches of <= 256 updates
+    upl = [min(chunk, U - i) for i in range(0, U, chunk)]  # updates per learner launch within one pass
+    n_launch_per_pass = 2 + len(upl) * (2 if kw["noisy"] and kname == "learner_fast_kernel" else 1)
     e2e = {"value": e2e_value, "unit": UNIT,
-           "h2d_bytes_per_step": n_launch_per_step * C.sizeof(_lib.SrlxEngine),  # the engine block rides in as kernel parameters
-           "d2h_bytes_per_step": C.sizeof(_lib.SrlxState),
+           "h2d_bytes_per_step": S * n_launch_per_pass * C.sizeof(_lib.SrlxEngine),  # the engine block rides in as kernel parameters
+           "d2h_bytes_per_step": S * C.sizeof(_lib.SrlxState),
            "trainer_updates_per_sec": float(rs.train_count) * world / float(e2e_t.item()),
-           "note": "VecRunner.train(max_steps=K*E): per step 3 launches + one pinned 128 B counter read + host stop checks; "
-                   "envs are generated on device by design, so there is no bulk host input on this path"}
+           "note": f"VecRunner.train(max_steps=K*S*E): per pass {n_launch_per_pass} launches + one pinned 128 B counter read + host stop "
+                   "checks and callbacks; L2 flushed once per bench step; envs are generated on device by design, so there is no "
+                   "bulk host input on this path"}
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
-    # ---- roofline of the dominant kernel (learner_kernel: one launch = U dependent updates) ---------------------
+    # ---- roofline of the dominant kernel (learner: one launch = up to 256 dependent updates) ---------------------------
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -320,31 +416,37 @@ def own_arm(args):
     peak_gbs, peak_src = (float(peaks["hbm_gbs"]), "measured") if "hbm_gbs" in peaks else (6650.0, "fallback")
     bytes_per_update = algorithmic_bytes_per_update(P_total, multisteps=kw["multisteps"],
                                                     depth=(E * R - 1).bit_length() if kw["mem_kind"] else 0)
-    kname, cluster, smem = eng.learner_info()
-    chunk = 256 if kname == "learner_fast_kernel" else U  # srlx_learn issues the fast kernel in launches of <= 256 updates
-    n_launch = (U + chunk - 1) // chunk
-    learn_ms_per_launch = t_learn / (K * n_launch)
-    achieved = bytes_per_update * min(U, chunk) / (learn_ms_per_launch * 1e-3) / 1e9
+    n_launch = len(upl) * S * K                      # learner launches in the timed region
+    upd_per_rank = updates / world                   # updates one rank's learner did in the timed region
+    learn_ms_per_launch = t_learn / n_launch         # average launch duration (CUDA events on the launching stream)
+    # algorithmic bytes per (average) launch / average launch duration == bytes_per_update * updates / learner time
+    achieved = bytes_per_update * (upd_per_rank / n_launch) / (learn_ms_per_launch * 1e-3) / 1e9
     traffic, traffic_src = None, None
     try:  # dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the committed ncu --set full captures
-        for fn, note in (("r1_j_learner_ncu_summary.json", "256 updates per launch"), ("r1_o_learner_small_ncu_summary.json", "1024 updates per launch")):
-            for k in json.load(open(os.path.join(ROOT, "profiles", fn))):
+        for fn, note in (("r1_j_learner_ncu_summary.json", "256 updates per launch"), ("r1_o_learner_small_ncu_summary.json", "1024 updates per launch"),
+                         ("r2_learner_ncu_summary.json", "256 updates per launch"), ("r2_learner_small_ncu_summary.json", "per launch")):
+            fp = os.path.join(ROOT, "profiles", fn)
+            if not os.path.exists(fp):
+                continue
+            for k in json.load(open(fp)):
                 if kname in k["kernel"] and int(k.get("cluster", 0)) == cluster:
                     traffic, traffic_src = k["dram_bytes"], f"profiles/{fn} ({note})"
     except Exception:
         pass
     roofline = {"kernel": kname, "cluster_ctas": cluster, "smem_bytes_per_cta": smem, "bound": "hbm", "achieved": achieved,
                 "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs, "traffic": traffic, "traffic_source": traffic_src,
-                "peak_source": peak_src, "algorithmic_bytes_per_update": bytes_per_update, "updates_per_launch": min(U, chunk),
-                "launches_per_step": n_launch, "launch_ms": learn_ms_per_launch, "share_of_step": t_learn / t_dev,
-                "us_per_update": 1e3 * t_learn / (K * U),
+                "peak_source": peak_src, "algorithmic_bytes_per_update": bytes_per_update,
+                "updates_per_launch": upl, "updates_per_launch_mean": upd_per_rank / n_launch, "launches_per_step": len(upl) * S,
+                "launch_ms": learn_ms_per_launch, "learner_ms_per_step": t_learn / K, "updates_per_step": upd_per_rank / K,
+                "share_of_step": t_learn / t_dev, "us_per_update": 1e3 * t_learn / upd_per_rank,
+                "formula": "achieved = algorithmic_bytes_per_update * updates_per_step / learner_ms_per_step",
                 "note": "consecutive updates are data-dependent (weights_t -> weights_t+1, priorities_t -> sample_t+1): the "
                         "limiter is the dependent-step latency of one 16-SM cluster, not HBM; the kernel keeps weights, Adam "
                         "state and the top of the SumTree in shared memory, so its DRAM traffic is below the algorithmic "
-                        "figure (which counts 5 weight passes + Adam per update); launch_ms includes the ~1% noise_precompute "
-                        "launches; see DESIGN.md"}
+                        "figure (which counts 5 weight passes + Adam per update); learner time = step time minus the rollout "
+                        "launches and includes the ~1% noise_precompute / tree_blk_build launches; see DESIGN.md"}
     rollout_bytes = 76 * E
-    roll_ms = t_roll / K
+    roll_ms = t_roll / (K * S)
     roofline_rollout = {"kernel": "rollout_kernel+post_step_kernel", "bound": "hbm", "achieved": rollout_bytes / (roll_ms * 1e-3) / 1e9,
                         "peak": peak_gbs, "unit": "GB/s", "frac": rollout_bytes / (roll_ms * 1e-3) / 1e9 / peak_gbs,
                         "algorithmic_bytes_per_env_step": 76, "launch_ms": roll_ms, "share_of_step": t_roll / t_dev}
@@ -352,9 +454,17 @@ def own_arm(args):
     # ---- CPU baseline (bounded sample, rank 0, N=1 only) ---------------------------------------------------------
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        r = cpu_port_run(args.cpu_envs, TI, steps=10_000, warmup=1, budget_s=args.cpu_seconds, threads=1, workload=args.workload)
-        cpu = {"value": r["env_steps_per_s"], "unit": UNIT, "cores": 1, "kind": "port", "sample": r["sample"],
-               "trainer_updates_per_sec": r["updates_per_s"]}
+        if reference_available() and not args.force_port:
+            n = max(2000, int(args.cpu_seconds * 1500))
+            r = cpu_reference_run(TI, n, 1200, 1, args.workload, E * R)
+            cpu = {"value": r["env_steps_per_s"], "unit": UNIT, "cores": 1, "kind": "reference", "sample": r["sample"],
+                   "trainer_updates_per_sec": r["updates_per_s"]}
+        else:
+            r = cpu_port_run(args.cpu_envs, TI, steps=10_000, warmup=1, budget_s=args.cpu_seconds, threads=1, workload=args.workload)
+            cpu = {"value": r["env_steps_per_s"], "unit": UNIT, "cores": 1, "kind": "port", "sample": r["sample"],
+                   "trainer_updates_per_sec": r["updates_per_s"],
+                   "note": "baseline/_ref (the reference install) is absent; BASELINE.md section 2b: the unmodified reference measured "
+                           "216 updates/s per core where this port measures 100"}
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": max(3, args.warmup),
             "ms_per_step": t_dev / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
@@ -383,9 +493,14 @@ def main():
     ap.add_argument("--train-interval", type=int, default=10,
                     help="env steps per trainer update (RunContext.train_interval); 10 = the ratio of the two north-star targets "
                          "(>= 1M env-steps/s with >= 100k updates/s)")
-    ap.add_argument("--cpu-envs", type=int, default=64, help="env copies in the bounded CPU sample")
+    ap.add_argument("--vec-steps-per-step", type=int, default=16,
+                    help="passes of the hot path (vector step + its updates) in one bench step: 16 makes 20 steps a ~2.4 s timed region")
+    ap.add_argument("--ref-env-steps-per-step", type=int, default=1000,
+                    help="--impl reference: env steps every CPU process does in one bench step (a bounded sample of the workload)")
+    ap.add_argument("--cpu-envs", type=int, default=64, help="env copies in the bounded sample of the oracle port (fallback CPU arm)")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--force-port", action="store_true", help="CPU arms: use the oracle port even when baseline/_ref is present")
     args = ap.parse_args()
     if args.impl == "reference":
         reference_arm(args)

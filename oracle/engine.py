@@ -139,6 +139,29 @@ class OracleEngine:
     def sigma(self):
         return None if self.adam.sigma is None else self.adam.sigma.detach().numpy()
 
+    # ---- replay contents from a ring view (tests: frozen memories, device state downloaded at full size) -----------
+    def load_ring(self, v, tree=None):
+        """Adopt the replay contents of a checkpoint.RingView-like object (obs, next_obs, action, reward, term, done, vec_steps,
+        leaf_priority, max_priority), as DeviceEngine.load_ring does; `tree` = the full node array if the caller has one."""
+        assert (v.E, v.R, v.M, v.D) == (self.E, self.R, self.M, self.D)
+        self.ring_obs[:], self.ring_next_obs[:] = v.obs, v.next_obs
+        self.ring_action[:], self.ring_reward[:], self.ring_term[:], self.ring_done[:] = v.action, v.reward, v.term, v.done
+        self.vec_steps = int(v.vec_steps)
+        self.total_step = self.vec_steps * self.E
+        self.mem_size = self._valid_range()[1] * self.E
+        self.per.size = self.mem_size
+        if self.cfg.mem_kind == MEM_PROPORTIONAL:
+            if tree is not None:
+                self.per.tree.tree[:] = tree
+            else:
+                t = self.per.tree.tree
+                t[:] = 0.0
+                t[self.cap - 1:] = v.leaf_priority
+                for i in range(self.cap - 2, -1, -1):
+                    t[i] = t[2 * i + 1] + t[2 * i + 2]
+            self.per.max_priority = float(v.max_priority)
+        self.needs_reset[:] = 1
+
     # ---- SumTree bulk row set (device: tree_set_row kernel) ------------------------------------------------
     def _tree_set_range(self, leaf_lo, values):
         """leaves [leaf_lo, leaf_lo+n) <- values; ancestors += pairwise-summed change (left child + right child)."""

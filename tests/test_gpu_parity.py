@@ -20,6 +20,8 @@ from oracle import nets as onets  # noqa: E402
 from oracle import philox as ophilox  # noqa: E402
 from oracle import sumtree as osumtree  # noqa: E402
 
+import learner_cases  # noqa: E402  (tests/learner_cases.py)
+
 
 @pytest.fixture(scope="module")
 def lib():
@@ -334,6 +336,60 @@ def _compare_env_and_ring(dev, orc):
         np.testing.assert_array_equal(t["tree"].cpu().numpy(), orc.per.tree.tree)  # bulk add: same pairwise order
 
 
+def _check_update_and_resync(dev, orc, o, check_tree=True):
+    """One trainer update, device vs oracle: leaf selection and windows exact, IS weights 1e-6, target / Q / loss / parameters
+    1e-4 (north_star), gradients 1e-3 ("tolerances"); then the oracle adopts the device's tree, parameters
+    and target so that the NEXT update is again compared from identical inputs."""
+    cfg = orc.cfg
+    st = dev.read_state()
+    B, M, D = cfg.batch_size, cfg.multisteps, orc.D
+    np.testing.assert_array_equal(dev.t["dbg_sample_idx"].cpu().numpy(), o["idx"])  # leaf selection: exact
+    np.testing.assert_allclose(dev.t["dbg_weights"].cpu().numpy(), o["weights"], rtol=1e-6)
+    win = dev.t["dbg_windows"].cpu().numpy()
+    ns = B * (M + 1) * D
+    np.testing.assert_array_equal(win[:ns].reshape(B, M + 1, D), o["states"])
+    np.testing.assert_array_equal(win[ns:ns + B * M].reshape(B, M).astype(np.int64), o["actions"])
+    np.testing.assert_array_equal(win[ns + B * M:ns + 2 * B * M].reshape(B, M), o["rewards"])
+    np.testing.assert_array_equal(win[ns + 2 * B * M:].reshape(B, M), o["terms"])
+    np.testing.assert_allclose(dev.t["dbg_target_q"].cpu().numpy(), o["target_q"], rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(dev.t["dbg_q_sa"].cpu().numpy(), o["q"], rtol=1e-4, atol=1e-5)
+    assert math.isclose(st.last_loss, o["loss"], rel_tol=1e-4, abs_tol=1e-6)
+    g = dev.t["dbg_grads"].cpu().numpy()
+    P = orc.spec.n_params
+    np.testing.assert_allclose(g[:P], o["grad_mu"], rtol=1e-3, atol=2e-6)
+    if cfg.noisy:
+        np.testing.assert_allclose(g[P:], o["grad_sigma"], rtol=1e-3, atol=2e-6)
+    mu_d, sg_d = dev.get_params()
+    np.testing.assert_allclose(mu_d, orc.mu, rtol=1e-4, atol=2e-5)
+    if cfg.noisy:
+        np.testing.assert_allclose(sg_d, orc.sigma, rtol=1e-4, atol=2e-5)
+    tm_d, _ = dev.get_target()
+    np.testing.assert_allclose(tm_d, orc.tgt_mu, rtol=1e-4, atol=2e-5)
+    assert st.sync_count == orc.sync_count and st.adam_step == orc.train_count
+    if dev.per:
+        # priorities are (|td| + 1e-4)^alpha of a DIFFERENCE of two Q values: an fp32 ulp of Q (1e-7 abs) moves a
+        # near-zero |td| by up to ~1e-3 relative, hence the absolute term
+        tree_d = dev.t["tree"].cpu().numpy()
+        if check_tree:
+            np.testing.assert_allclose(tree_d, orc.per.tree.tree, rtol=1e-3, atol=1e-5)
+        else:  # large trees: the touched leaves and the root
+            leaves = np.asarray(o["idx"])
+            np.testing.assert_allclose(tree_d[leaves], orc.per.tree.tree[leaves], rtol=1e-3, atol=1e-5)
+            np.testing.assert_allclose(tree_d[0], orc.per.tree.tree[0], rtol=1e-9)
+        assert math.isclose(st.max_priority, orc.per.max_priority, rel_tol=1e-3)
+        # keep the two trees bit-identical so the next leaf selection is comparable (fp32 |td| differs in ulps)
+        orc.per.tree.tree[:] = tree_d
+        orc.per.max_priority = st.max_priority
+    # re-synchronise the parameters: Adam amplifies ulp-level gradient differences (g/sqrt(v) at step 1)
+    orc.adam.mu.data.copy_(torch.as_tensor(mu_d))
+    if cfg.noisy:
+        orc.adam.sigma.data.copy_(torch.as_tensor(sg_d))
+    tmu, tsg = dev.get_target()
+    orc.tgt_mu = tmu.copy()
+    if cfg.noisy:
+        orc.tgt_sigma = tsg.copy()
+
+
 @pytest.mark.parametrize("name", list(ENGINE_CASES))
 def test_engine_lockstep(name):
     """vector steps + trainer updates, device vs oracle, compared buffer by buffer after every call."""
@@ -351,52 +407,11 @@ def test_engine_lockstep(name):
         for _ in range(2):
             dev.learn(1)
             out = orc.learn(1)
-            st = dev.read_state()
-            assert st.train_count == orc.train_count
+            assert dev.read_state().train_count == orc.train_count
             if not out:
                 continue
-            o = out[0]
             n_upd_total += 1
-            B, M, D = cfg.batch_size, cfg.multisteps, orc.D
-            np.testing.assert_array_equal(dev.t["dbg_sample_idx"].cpu().numpy(), o["idx"])  # leaf selection: exact
-            np.testing.assert_allclose(dev.t["dbg_weights"].cpu().numpy(), o["weights"], rtol=1e-6)
-            win = dev.t["dbg_windows"].cpu().numpy()
-            ns = B * (M + 1) * D
-            np.testing.assert_array_equal(win[:ns].reshape(B, M + 1, D), o["states"])
-            np.testing.assert_array_equal(win[ns:ns + B * M].reshape(B, M).astype(np.int64), o["actions"])
-            np.testing.assert_array_equal(win[ns + B * M:ns + 2 * B * M].reshape(B, M), o["rewards"])
-            np.testing.assert_array_equal(win[ns + 2 * B * M:].reshape(B, M), o["terms"])
-            np.testing.assert_allclose(dev.t["dbg_target_q"].cpu().numpy(), o["target_q"], rtol=1e-4, atol=1e-5)
-            np.testing.assert_allclose(dev.t["dbg_q_sa"].cpu().numpy(), o["q"], rtol=1e-4, atol=1e-5)
-            assert math.isclose(st.last_loss, o["loss"], rel_tol=1e-4, abs_tol=1e-6)
-            g = dev.t["dbg_grads"].cpu().numpy()
-            P = orc.spec.n_params
-            np.testing.assert_allclose(g[:P], o["grad_mu"], rtol=1e-3, atol=2e-6)
-            if cfg.noisy:
-                np.testing.assert_allclose(g[P:], o["grad_sigma"], rtol=1e-3, atol=2e-6)
-            mu_d, sg_d = dev.get_params()
-            np.testing.assert_allclose(mu_d, orc.mu, rtol=1e-4, atol=2e-5)
-            if cfg.noisy:
-                np.testing.assert_allclose(sg_d, orc.sigma, rtol=1e-4, atol=2e-5)
-            tm_d, _ = dev.get_target()
-            np.testing.assert_allclose(tm_d, orc.tgt_mu, rtol=1e-4, atol=2e-5)
-            assert st.sync_count == orc.sync_count and st.adam_step == orc.train_count
-            if dev.per:
-                # priorities are (|td| + 1e-4)^alpha of a DIFFERENCE of two Q values: an fp32 ulp of Q (1e-7 abs) moves a
-                # near-zero |td| by up to ~1e-3 relative, hence the absolute term
-                np.testing.assert_allclose(dev.t["tree"].cpu().numpy(), orc.per.tree.tree, rtol=1e-3, atol=1e-5)
-                assert math.isclose(st.max_priority, orc.per.max_priority, rel_tol=1e-3)
-                # keep the two trees bit-identical so the next leaf selection is comparable (fp32 |td| differs in ulps)
-                orc.per.tree.tree[:] = dev.t["tree"].cpu().numpy()
-                orc.per.max_priority = st.max_priority
-            # re-synchronise the parameters: Adam amplifies ulp-level gradient differences (g/sqrt(v) at step 1)
-            orc.adam.mu.data.copy_(torch.as_tensor(mu_d))
-            if cfg.noisy:
-                orc.adam.sigma.data.copy_(torch.as_tensor(sg_d))
-            tmu, tsg = dev.get_target()
-            orc.tgt_mu = tmu.copy()
-            if cfg.noisy:
-                orc.tgt_sigma = tsg.copy()
+            _check_update_and_resync(dev, orc, out[0])
     assert n_upd_total > 0
     assert orc.episode_count > 0 or cfg.env in ("CartPole-v1", "Pendulum-v1")
 
@@ -564,6 +579,187 @@ def test_full_size_properties():
     # ring rows written so far hold valid CartPole observations
     obs = dev.t["ring_obs"][: 40 * 8192].cpu().numpy()
     assert np.abs(obs[:, 0]).max() <= 2.4 + 1e-6 and np.abs(obs[:, 2]).max() <= 0.2095 + 1e-6
+
+
+def _oracle_from_device(dev, kw):
+    """An OracleEngine holding the device's replay contents, SumTree, parameters, target network and counters (train_count 0)."""
+    v = dev.ring_view()
+    mu, sigma = dev.get_params()
+    orc = oeng.OracleEngine(oeng.EngineConfig(**kw), mu, sigma, noise_fn=lambda kind, call_id: dev.noise(kind, call_id))
+    tm, ts = dev.get_target()
+    orc.tgt_mu, orc.tgt_sigma = tm.copy(), (None if ts is None else ts.copy())
+    orc.load_ring(v, tree=dev.t["tree"].cpu().numpy() if dev.per else None)
+    st = dev.read_state()
+    assert st.train_count == 0 and st.mem_size == orc.mem_size and st.vec_steps == orc.vec_steps
+    if dev.per:
+        orc.per.max_priority = float(st.max_priority)
+    return orc
+
+
+FULL_SIZE = {
+    # BASELINE configs[2], the benched configuration: 8192 envs x 256 rows = 2 097 152 leaves (21 levels: 12 cached in shared memory
+    # + two deep rounds through the blocked copy), learner_fast_kernel<16>
+    "rainbow_8192x256_per": dict(env="CartPole-v1", algo="rainbow", hidden=(512,), dueling="average", noisy=True, mem_kind=1, multisteps=3,
+                                 n_envs=8192, ring_rows=256, batch_size=32, warmup_size=1000, seed=1),
+    # BASELINE configs[1]: 4096 envs x 256 rows = 1 048 576 transitions, uniform replay, learner_small_kernel
+    "dqn_4096x256_uniform": dict(env="CartPole-v1", algo="dqn", hidden=(64, 64), dueling=None, noisy=False, mem_kind=0, multisteps=1,
+                                 n_envs=4096, ring_rows=256, batch_size=32, warmup_size=1000, epsilon=0.1, seed=1),
+    # configs[1] with proportional replay: the replay CTA of learner_small_kernel on a 1M-leaf tree (20 levels)
+    "dqn_4096x256_per": dict(env="CartPole-v1", algo="dqn", hidden=(64, 64), dueling=None, noisy=False, mem_kind=1, multisteps=1,
+                             n_envs=4096, ring_rows=256, batch_size=32, warmup_size=1000, epsilon=0.1, seed=1),
+    # ragged capacity (not a power of two: leaves on two depths), 3-step windows
+    "rainbow_3000x100_per": dict(env="CartPole-v1", algo="rainbow", hidden=(512,), dueling="average", noisy=True, mem_kind=1, multisteps=3,
+                                 n_envs=3000, ring_rows=100, batch_size=32, warmup_size=1000, seed=2),
+}
+
+
+@pytest.mark.parametrize("name", list(FULL_SIZE))
+def test_full_size_lockstep_against_oracle(name):
+    """The BENCHED sizes, update by update against the oracle (SumTree walk = proportional_memory.py:57-66,131-169; update =
+    :171-177; targets / loss / Adam = rainbow/model_torch.py:85-122): the ring is filled (and wrapped) by the device rollout, the
+    leaf priorities are made heterogeneous over the whole tree, then 50 separate updates are compared -- sampled leaf indices and
+    rebuilt windows exactly, IS weights 1e-6, target / Q / loss / parameters 1e-4 -- the oracle replaying the device's Philox
+    uniforms on the downloaded tree.  On the 2M-leaf tree every sample goes through the 12 cached levels and both deep rounds of
+    the blocked copy."""
+    from simple_distributed_rl_b200.engine import DeviceEngine, EngineConfig
+
+    kw = dict(FULL_SIZE[name])
+    dev = DeviceEngine(EngineConfig(**kw), debug=True)
+    R = kw["ring_rows"]
+    dev.run(R + 9, 0)  # the ring has wrapped: rows 0..8 were overwritten
+    if dev.per:
+        v = dev.ring_view()
+        rng = np.random.default_rng(5)
+        g_lo, n_g = v.valid_rows()
+        pri = np.zeros(dev.cap)
+        rows = (np.arange(g_lo, g_lo + n_g) % R)
+        for r in rows:
+            pri[r * dev.E:(r + 1) * dev.E] = rng.random(dev.E) ** 4 * 3.0 + 1e-3  # four decades of priorities
+        z = rng.random(dev.cap) < 0.01
+        pri[z] = 0.0  # zero-priority leaves inside the valid range: the reference re-draws (proportional_memory.py:150-152)
+        v.leaf_priority, v.max_priority = pri, 3.5
+        dev.load_ring(v)
+    orc = _oracle_from_device(dev, kw)
+    n_retries0 = orc.sample_retries
+    for u in range(50):
+        dev.learn(1)
+        out = orc.learn(1)
+        assert len(out) == 1 and dev.read_state().train_count == orc.train_count == u + 1
+        _check_update_and_resync(dev, orc, out[0], check_tree=False)
+    if dev.per:
+        assert orc.sample_retries > n_retries0  # 1 % zero leaves, 1600 draws: the re-draw path was exercised
+        tree = dev.t["tree"].cpu().numpy()
+        cap = dev.cap
+        np.testing.assert_allclose(tree[: cap - 1], tree[1::2][: cap - 1] + tree[2::2][: cap - 1], rtol=1e-9, atol=1e-9)
+
+
+def test_full_size_many_updates_in_one_launch_then_lockstep():
+    """At the benched size: 300 updates inside launches (blocked copy written through, update plans, noise ring), then the
+    oracle adopts the state and the next updates are compared one by one -- what the pipelined launches left behind is a
+    state from which the reference's step continues exactly."""
+    from simple_distributed_rl_b200.engine import DeviceEngine, EngineConfig
+
+    kw = dict(FULL_SIZE["rainbow_8192x256_per"])
+    dev = DeviceEngine(EngineConfig(**kw), debug=True)
+    dev.run(kw["ring_rows"] + 3, 0)
+    dev.learn(300)
+    st = dev.read_state()
+    assert st.train_count == 300
+    # oracle from the device state, including the optimiser moments and counters
+    v = dev.ring_view()
+    mu, sigma = dev.get_params()
+    orc = oeng.OracleEngine(oeng.EngineConfig(**kw), mu, sigma, noise_fn=lambda kind, call_id: dev.noise(kind, call_id))
+    tm, ts = dev.get_target()
+    orc.tgt_mu, orc.tgt_sigma = tm.copy(), ts.copy()
+    orc.load_ring(v, tree=dev.t["tree"].cpu().numpy())
+    orc.per.max_priority = float(st.max_priority)
+    orc.train_count, orc.sync_count = int(st.train_count), int(st.sync_count)
+    P = orc.spec.n_params
+    m, vv = dev.t["adam_m"].cpu(), dev.t["adam_v"].cpu()
+    for i, p in enumerate([orc.adam.mu, orc.adam.sigma]):
+        orc.adam.opt.state[p] = dict(step=torch.tensor(float(st.adam_step)), exp_avg=m[i * P:(i + 1) * P].clone(),
+                                     exp_avg_sq=vv[i * P:(i + 1) * P].clone())
+    for u in range(10):
+        dev.learn(1)
+        out = orc.learn(1)
+        assert len(out) == 1
+        _check_update_and_resync(dev, orc, out[0], check_tree=False)
+
+
+def test_unresynced_drift_over_20_updates():
+    """20 dependent updates with NO re-synchronisation: the device (one launch) against an independent oracle trajectory from
+    the same start.  fp32 rounding differences are amplified by Adam (g / sqrt(v) is +-1 at step 1 whatever the size of g)
+    and by the priority feedback, so this is a drift bound, not an equality: stated in DESIGN.md section 2."""
+    from simple_distributed_rl_b200.engine import DeviceEngine, EngineConfig
+
+    res = {}
+    for name in ("cartpole_rainbow_default", "cartpole_dqn_uniform_64x64", "cartpole_dqn_per"):
+        kw = dict(ENGINE_CASES[name], seed=3, target_update_interval=7)
+        dev = DeviceEngine(EngineConfig(**kw), debug=True)
+        dev.run(kw["ring_rows"] + 2, 0)
+        orc = _oracle_from_device(dev, kw)
+        mu0, _ = dev.get_params()
+        dev.learn(20)
+        outs = orc.learn(20)
+        assert len(outs) == 20 and dev.read_state().train_count == 20
+        mu_d, sg_d = dev.get_params()
+        moved = np.abs(mu_d - mu0)
+        diff = np.abs(mu_d - orc.mu)
+        x = np.random.default_rng(0).normal(size=(256, dev.D)).astype(np.float32) * 0.3
+        noise = dev.noise(3, 5) if kw.get("noisy") else None
+        q_dev = onets.np_forward(orc.spec, mu_d, sg_d, noise, x)
+        q_orc = onets.np_forward(orc.spec, orc.mu, orc.sigma, noise, x)
+        same_idx = bool(np.array_equal(dev.t["dbg_sample_idx"].cpu().numpy(), outs[-1]["idx"]))
+        res[name] = dict(max_param_diff=float(diff.max()), mean_param_diff=float(diff.mean()), mean_moved=float(moved.mean()),
+                         q_max_diff=float(np.abs(q_dev - q_orc).max()), q_scale=float(np.abs(q_orc).max()),
+                         loss_dev=float(dev.read_state().last_loss), loss_orc=float(outs[-1]["loss"]), last_idx_equal=same_idx)
+        print("DRIFT", name, res[name])
+        # bounds: the parameters have moved ~20 x lr; the two trajectories stay within a small fraction of that movement
+        assert diff.mean() <= 0.02 * moved.mean() + 1e-6, res[name]
+        assert np.abs(q_dev - q_orc).max() <= 2e-3 * max(1.0, np.abs(q_orc).max()), res[name]
+        assert math.isclose(res[name]["loss_dev"], res[name]["loss_orc"], rel_tol=5e-3, abs_tol=1e-4), res[name]
+
+
+@pytest.mark.parametrize("path", learner_cases.PATHS, ids=learner_cases.IDS)
+def test_device_learner_equals_reference_trainer_on_frozen_memory(path):
+    """The device learner against the REFERENCE ITSELF, no oracle in between: tests/golden/learner_*.npz hold what the reference's
+    ProportionalMemory.sample / ReplayBuffer + Trainer.train + memory.update did on a frozen replay memory, fed the device's Philox
+    uniforms and NoisyNet draws (tests/golden/make_learner_golden.py).  Same memory in the ring, same parameters: the device must
+    pick the same leaves, form the same IS weights, targets, loss, |td|, post-Adam parameters, target network and leaf priorities,
+    on each of the three learner kernels."""
+    from simple_distributed_rl_b200.engine import DeviceEngine, EngineConfig
+
+    kw, v, g = learner_cases.load_case(path)
+    noisy = kw["noisy"]
+    dev = DeviceEngine(EngineConfig(**kw), debug=True, params=(g["mu0"], g["sigma0"] if noisy else None))
+    dev.set_target(g["tmu0"], g["tsigma0"] if noisy else None)
+    dev.load_ring(v)
+    cap = dev.cap
+    for u in range(len(g["loss"])):
+        dev.learn(1)
+        st = dev.read_state()
+        assert st.train_count == u + 1
+        np.testing.assert_array_equal(dev.t["dbg_sample_idx"].cpu().numpy(), g["idx"][u])                 # leaf selection: exact
+        np.testing.assert_allclose(dev.t["dbg_weights"].cpu().numpy(), g["weights"][u], rtol=1e-6)
+        np.testing.assert_allclose(dev.t["dbg_target_q"].cpu().numpy(), g["target_q"][u], rtol=1e-4, atol=1e-5)
+        assert math.isclose(st.last_loss, g["loss"][u], rel_tol=1e-4, abs_tol=1e-6)
+        td_dev = np.abs(dev.t["dbg_target_q"].cpu().numpy() - dev.t["dbg_q_sa"].cpu().numpy())
+        np.testing.assert_allclose(td_dev, g["td"][u], rtol=1e-4, atol=2e-5)
+        mu_d, sg_d = dev.get_params()
+        tm_d, ts_d = dev.get_target()
+        np.testing.assert_allclose(mu_d, g["mu_after"][u], rtol=1e-4, atol=2e-5)
+        np.testing.assert_allclose(tm_d, g["tmu_after"][u], rtol=1e-4, atol=2e-5)
+        if noisy:
+            np.testing.assert_allclose(sg_d, g["sigma_after"][u], rtol=1e-4, atol=2e-5)
+            np.testing.assert_allclose(ts_d, g["tsigma_after"][u], rtol=1e-4, atol=2e-5)
+        if dev.per:
+            tree = dev.t["tree"].cpu().numpy()
+            np.testing.assert_allclose(tree[cap - 1:][g["touched"]], g["leaves_after"][u], rtol=1e-3, atol=1e-5)
+            np.testing.assert_allclose(tree[0], g["total_after"][u], rtol=1e-5)
+            assert math.isclose(st.max_priority, g["maxp_after"][u], rel_tol=1e-3)
+        # like the lockstep test: continue from the reference's own state so that the next update starts from identical inputs
+        dev.set_params(g["mu_after"][u], g["sigma_after"][u] if noisy else None)
+        dev.set_target(g["tmu_after"][u], g["tsigma_after"][u] if noisy else None)
 
 
 def _blocked_copy_from_flat(tree, n_nodes, clev):

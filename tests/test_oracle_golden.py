@@ -187,6 +187,44 @@ def test_trainer_update_matches_reference(path):
     assert list(g["update_steps"]) == list(range(len(g["losses"])))
 
 
+# ---- the whole learner step on a frozen memory: the reference's own sample / Trainer.train / update -------------------------
+import learner_cases  # noqa: E402
+
+
+@pytest.mark.parametrize("path", learner_cases.PATHS, ids=learner_cases.IDS)
+def test_oracle_learner_step_matches_reference_on_frozen_memory(path):
+    """oracle/engine.py::OracleEngine.learn (sampler + window rebuild + targets + loss + Adam + priority update) against the
+    reference's ProportionalMemory.sample / ReplayBuffer + Trainer.train + memory.update executed on the same memory
+    (tests/golden/make_learner_golden.py): leaf indices exact, everything else to float32 resolution."""
+    from oracle import engine as oeng
+
+    kw, v, g = learner_cases.load_case(path)
+    noisy = kw["noisy"]
+    orc = oeng.OracleEngine(oeng.EngineConfig(**kw), g["mu0"], g["sigma0"] if noisy else None)
+    orc.tgt_mu = g["tmu0"].copy()
+    orc.tgt_sigma = g["tsigma0"].copy() if noisy else None
+    orc.load_ring(v)
+    cap = orc.cap
+    for u in range(len(g["loss"])):
+        o = orc.learn(1)[0]
+        np.testing.assert_array_equal(o["idx"], g["idx"][u])
+        np.testing.assert_allclose(o["weights"], g["weights"][u], rtol=1e-6)
+        np.testing.assert_allclose(o["target_q"], g["target_q"][u], rtol=1e-5, atol=1e-6)
+        assert abs(o["loss"] - g["loss"][u]) <= 1e-5 * max(1, abs(g["loss"][u]))
+        np.testing.assert_allclose(o["priorities"], g["td"][u], rtol=1e-4, atol=1e-6)
+        np.testing.assert_allclose(orc.mu, g["mu_after"][u], rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose(orc.tgt_mu, g["tmu_after"][u], rtol=1e-5, atol=1e-6)
+        if noisy:
+            np.testing.assert_allclose(orc.sigma, g["sigma_after"][u], rtol=1e-5, atol=1e-6)
+            np.testing.assert_allclose(orc.tgt_sigma, g["tsigma_after"][u], rtol=1e-5, atol=1e-6)
+        if kw["mem_kind"]:
+            # the reference forms (|td| + eps) ** alpha on the float32 array the trainer hands over (proportional_memory.py:172)
+            np.testing.assert_allclose(orc.per.tree.tree[cap - 1:][g["touched"]], g["leaves_after"][u], rtol=1e-5, atol=1e-7)
+            assert abs(orc.per.max_priority - g["maxp_after"][u]) <= 1e-5 * g["maxp_after"][u]
+            np.testing.assert_allclose(orc.per.tree.total(), g["total_after"][u], rtol=1e-7)
+    assert list(g["update_step"]) == list(range(len(g["loss"])))
+
+
 # ------------------------------------------------------------------------------------------------------------------
 # The vectorised engine adds a whole row of E leaves to the SumTree at once (oracle/engine.py::_tree_set_range, device twin
 # csrc/rollout.cu::tree_set_row).  Its result has to equal the reference's one-leaf-at-a-time update
