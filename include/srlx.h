@@ -44,7 +44,9 @@ extern "C" {
 #define SRLX_MAX_BATCH 256
 
 /* ---- environments (closed-form, stepped on device) ------------------------------------------------------ */
-enum { SRLX_ENV_GRID = 0, SRLX_ENV_CARTPOLE = 1, SRLX_ENV_PENDULUM = 2 };
+/* SRLX_ENV_EXTERNAL: the env is stepped by a host loop (the reference's core_play.play through the plug-in classes); transitions
+ * enter through srlx_ext_step and srlx_vec_step is refused */
+enum { SRLX_ENV_GRID = 0, SRLX_ENV_CARTPOLE = 1, SRLX_ENV_PENDULUM = 2, SRLX_ENV_EXTERNAL = 3 };
 
 /* dueling combine: srl/rl/torch_/blocks/dueling_network.py:51-58 */
 enum { SRLX_DUEL_NONE = 0, SRLX_DUEL_AVERAGE = 1, SRLX_DUEL_MAX = 2, SRLX_DUEL_NAIVE = 3 };
@@ -270,6 +272,19 @@ size_t srlx_tree_blk_bytes(uint64_t capacity);
 /* The two halves separately (parity tests drive them one at a time). */
 int srlx_vec_step(const srlx_engine* eng, int training, uintptr_t cuda_stream);
 int srlx_learn(const srlx_engine* eng, uint32_t n_updates, uintptr_t cuda_stream);
+/* ---- plug-in seams for the reference's own host loop (srl.Runner / core_play.play, srl/base/run/core_play.py:115-214) ------------
+ * srlx_ext_step <- RLWorker.on_step -> RLMemory.add (srl/algorithms/dqn/dqn.py:213-246, rainbow.py:333-400,
+ *                  srl/rl/memories/priority_replay_buffer.py:205-217): one row of E externally produced records (s, s', a, r,
+ *                  terminated, episode-ended) is written at the ring cursor and added to the replay memory exactly as a device
+ *                  vector step would (n-step windows are rebuilt by index, so records must arrive in trajectory order per column).
+ * srlx_env_reset_obs / srlx_env_step_actions <- EnvBase.reset / EnvBase.step (srl/base/env/base.py:60-137) for the closed-form
+ *                  envs: reset-if-needed (force != 0: always) + observation; one step per env copy with CALLER-supplied actions
+ *                  -> (next observation [E][D] float32, raw reward f64, terminated, truncated at trunc_limit).  No policy, no ring. */
+int srlx_ext_step(const srlx_engine* eng, const float* obs_dev, const float* next_obs_dev, const int32_t* action_dev,
+                  const float* reward_dev, const unsigned char* term_dev, const unsigned char* done_dev, uintptr_t cuda_stream);
+int srlx_env_reset_obs(const srlx_engine* eng, int force, float* out_obs_dev, uintptr_t cuda_stream);
+int srlx_env_step_actions(const srlx_engine* eng, const int32_t* actions_dev, float* out_obs_dev, double* out_reward_dev,
+                          unsigned char* out_term_dev, unsigned char* out_trunc_dev, uintptr_t cuda_stream);
 /* Inference seam: q_out[n][A] = Q(obs[n][D]) with `params` (pred_q) or `target` (pred_target_q); noise_call_id is the
  * NoisyLinear draw to use (ignored when !noisy; kind = 3). */
 int srlx_qnet_forward(const srlx_engine* eng, int use_target, const float* obs_dev, uint32_t n, uint64_t noise_call_id,

@@ -6,7 +6,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("SRLX_LIB") or os.path.join(_HERE, "libsrlx.so")  # SRLX_LIB: diagnostic builds (phase clocks)
 
 SRLX_MAX_LAYERS = 6
-ENV_GRID, ENV_CARTPOLE, ENV_PENDULUM = 0, 1, 2
+ENV_GRID, ENV_CARTPOLE, ENV_PENDULUM, ENV_EXTERNAL = 0, 1, 2, 3
 RETURNS_GAE, RETURNS_MC = 0, 1  # srlx_returns_scan methods
 DUEL_NONE, DUEL_AVERAGE, DUEL_MAX, DUEL_NAIVE = 0, 1, 2, 3
 MEM_UNIFORM, MEM_PROPORTIONAL = 0, 1
@@ -116,6 +116,9 @@ SYMBOLS = [
     ("srlx_learner_info", C.c_int, [C.POINTER(SrlxEngine), C.POINTER(C.c_int), C.POINTER(C.c_size_t)]),
     ("srlx_tree_blk_bytes", _sz, [_u64]),
     ("srlx_qnet_forward", C.c_int, [C.POINTER(SrlxEngine), _i32, _P, _u32, _u64, _P, _uptr]),
+    ("srlx_ext_step", C.c_int, [C.POINTER(SrlxEngine), _P, _P, _P, _P, _P, _P, _uptr]),
+    ("srlx_env_reset_obs", C.c_int, [C.POINTER(SrlxEngine), _i32, _P, _uptr]),
+    ("srlx_env_step_actions", C.c_int, [C.POINTER(SrlxEngine), _P, _P, _P, _P, _P, _uptr]),
     ("srlx_sequence_targets", C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _u32, _u32, _u32, _dbl, _dbl, _i32, _i32, _i32, _uptr]),
     ("srlx_returns_scan", C.c_int, [_P, _P, _P, _P, _P, _P, _P, _u32, _u32, _dbl, _dbl, _i32, _i32, _i32, _dbl, _dbl, _uptr]),
 ]

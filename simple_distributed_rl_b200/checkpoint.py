@@ -237,8 +237,19 @@ def _ordered_items(inner: list, proportional: bool) -> Tuple[List[Any], Optional
     return [data[i] for i in order], pri, maxp
 
 
-def memory_restore(data: list, n_envs: int, ring_rows: int, multisteps: int, n_actions: int, obs_dim: int, proportional: bool) -> RingView:
-    """RLPriorityReplayBuffer.call_restore() into ring arrays (see the module docstring for the layout)."""
+class DiscontinuousMemoryError(ValueError):
+    """A multistep memory whose item stream is not one contiguous trajectory per ring column."""
+
+
+def memory_restore(data: list, n_envs: int, ring_rows: int, multisteps: int, n_actions: int, obs_dim: int, proportional: bool,
+                   check_continuity: bool = True) -> RingView:
+    """RLPriorityReplayBuffer.call_restore() into ring arrays (see the module docstring for the layout).
+
+    With multisteps > 1 the ring keeps only the FIRST transition of every item and rebuilds the M-step window from the rows that
+    follow, so within a column item j+1 must be the next step of item j's trajectory (or item j's first step ended its episode).
+    A memory filled by several actors (play_mp interleaves their items) or any other non-contiguous stream does not have that
+    property; importing it would stitch windows from unrelated trajectories, so it raises DiscontinuousMemoryError instead
+    (check_continuity=False skips the check for a caller that knows better)."""
     inner = data[0] if (len(data) == 2 and isinstance(data[0], list) and (data[1] is None or isinstance(data[1], list))) else data
     src_prop = len(inner) == 6 and not isinstance(inner[0], list)
     items, pri, maxp = _ordered_items(inner, src_prop)
@@ -255,8 +266,16 @@ def memory_restore(data: list, n_envs: int, ring_rows: int, multisteps: int, n_a
         pri = pri[len(pri) - n_g * E:]
     for e in range(E):
         tail = []
+        prev_ns, prev_done = None, True
         for j in range(n_g):
             s, ns, a, r, term, done, tail = _first_transition(items[e * n_g + j], M)
+            if check_continuity and M > 1 and not prev_done and not np.array_equal(s, prev_ns):
+                raise DiscontinuousMemoryError(
+                    f"memory_restore: item {e * n_g + j} does not continue the trajectory of the item before it (its state is not the "
+                    f"previous item's next state and that step did not end an episode). With multisteps = {M} the ring rebuilds "
+                    "windows from consecutive rows, so the item stream must be one contiguous trajectory per column -- a memory "
+                    "filled by interleaved actors (play_mp) cannot be imported this way")
+            prev_ns, prev_done = ns, bool(done)
             slot = j * E + e
             ring.obs[slot], ring.next_obs[slot] = s, ns
             ring.action[slot], ring.reward[slot], ring.term[slot], ring.done[slot] = a, r, term, done

@@ -220,6 +220,70 @@ __global__ void eval_post_step_kernel(srlx_state* st, int E) {
   st->total_step += (uint64_t)E;
 }
 
+// ---- external actor: transitions produced by a HOST loop (the reference's own core_play.play driving the plug-in Worker,
+//      simple_distributed_rl_b200/srl_classes.py) enter the ring as one row of E records; post_step_kernel then does the replay add
+__global__ void ext_row_write_kernel(const __grid_constant__ srlx_engine eng, const float* __restrict__ obs, const float* __restrict__ next_obs,
+                                     const int32_t* __restrict__ action, const float* __restrict__ reward,
+                                     const uint8_t* __restrict__ term, const uint8_t* __restrict__ done) {
+  const int E = eng.n_envs, D = eng.obs_dim;
+  const int row = (int)(eng.state->vec_steps % (uint64_t)eng.ring_rows);
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < E; e += gridDim.x * blockDim.x) {
+    const size_t slot = (size_t)row * E + e;
+    for (int d = 0; d < D; ++d) {
+      eng.ring_obs[slot * D + d] = obs[(size_t)e * D + d];
+      eng.ring_next_obs[slot * D + d] = next_obs[(size_t)e * D + d];
+    }
+    eng.ring_action[slot] = action[e];
+    eng.ring_reward[slot] = reward[e];
+    eng.ring_term[slot] = term[e] ? 1 : 0;
+    eng.ring_done[slot] = done[e] ? 1 : 0;
+  }
+}
+
+// ---- device-backed EnvBase (srl/base/env/base.py:60-137): reset() and step(action) of the closed-form envs for a host loop.
+// reset-if-needed + observation of every env copy
+__global__ void env_reset_obs_kernel(const __grid_constant__ srlx_engine eng, float* __restrict__ out_obs, int force) {
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < eng.n_envs; e += gridDim.x * blockDim.x) {
+    double* st = eng.env_state + (size_t)e * 4;
+    if (force || eng.env_needs_reset[e]) {
+      const uint32_t ep = eng.env_episode[e];
+      env_reset(eng, (uint32_t)e, ep, st);
+      eng.env_episode[e] = ep + 1;
+      eng.env_step_num[e] = 0;
+      eng.env_ep_reward[e] = 0.0;
+      eng.env_needs_reset[e] = 0;
+    }
+    float obs[SRLX_MAX_OBS];
+    env_obs(eng, st, obs);
+    for (int d = 0; d < eng.obs_dim; ++d) out_obs[(size_t)e * eng.obs_dim + d] = obs[d];
+  }
+}
+// one env.step(action) per env copy with CALLER-supplied actions: (next observation, raw reward, terminated, truncated)
+__global__ void env_step_actions_kernel(const __grid_constant__ srlx_engine eng, const int32_t* __restrict__ actions, float* __restrict__ out_obs,
+                                        double* __restrict__ out_reward, uint8_t* __restrict__ out_term, uint8_t* __restrict__ out_trunc) {
+  const uint64_t g = eng.state->vec_steps;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < eng.n_envs; e += gridDim.x * blockDim.x) {
+    double* st = eng.env_state + (size_t)e * 4;
+    int a = actions[e];
+    a = a < 0 ? 0 : (a >= eng.n_actions ? eng.n_actions - 1 : a);
+    bool terminated = false;
+    const double r = env_step(eng, (uint32_t)e, g, a, st, terminated);
+    const int step_num = eng.env_step_num[e] + 1;
+    eng.env_step_num[e] = step_num;
+    bool truncated = step_num >= eng.trunc_limit;
+    if (eng.trunc_overrides_term) terminated = terminated && !truncated;
+    else truncated = truncated && !terminated;
+    eng.env_ep_reward[e] += r;
+    if (terminated || truncated) eng.env_needs_reset[e] = 1;
+    float obs[SRLX_MAX_OBS];
+    env_obs(eng, st, obs);
+    for (int d = 0; d < eng.obs_dim; ++d) out_obs[(size_t)e * eng.obs_dim + d] = obs[d];
+    out_reward[e] = r;
+    out_term[e] = terminated ? 1 : 0;
+    out_trunc[e] = truncated ? 1 : 0;
+  }
+}
+
 __global__ void engine_reset_kernel(const __grid_constant__ srlx_engine eng) {
   const size_t i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
   const size_t cap = (size_t)eng.ring_rows * eng.n_envs;
@@ -257,7 +321,8 @@ static int check_engine(const srlx_engine* eng) {
   SRLX_REQUIRE(eng->net.n_layers >= 1 && eng->net.n_layers <= SRLX_MAX_LAYERS, "n_layers %d out of range", eng->net.n_layers);
   SRLX_REQUIRE(eng->net.in_dim == eng->obs_dim, "net.in_dim != obs_dim");
   SRLX_REQUIRE(eng->ring_rows >= eng->multisteps, "ring_rows (%d) must be >= multisteps (%d)", eng->ring_rows, eng->multisteps);
-  SRLX_REQUIRE(eng->env_id == SRLX_ENV_GRID || eng->env_id == SRLX_ENV_CARTPOLE || eng->env_id == SRLX_ENV_PENDULUM,
+  SRLX_REQUIRE(eng->env_id == SRLX_ENV_GRID || eng->env_id == SRLX_ENV_CARTPOLE || eng->env_id == SRLX_ENV_PENDULUM ||
+                   eng->env_id == SRLX_ENV_EXTERNAL,
                "unknown env_id %d", eng->env_id);
   SRLX_REQUIRE(eng->state && eng->env_state && eng->env_step_num && eng->env_episode && eng->env_ep_reward &&
                    eng->env_needs_reset && eng->params,
@@ -275,9 +340,67 @@ extern "C" int srlx_engine_reset(const srlx_engine* eng, uintptr_t cuda_stream) 
   return 0;
 }
 
+extern "C" int srlx_ext_step(const srlx_engine* eng, const float* obs_dev, const float* next_obs_dev, const int32_t* action_dev,
+                             const float* reward_dev, const unsigned char* term_dev, const unsigned char* done_dev, uintptr_t cuda_stream) {
+  using namespace srlx;
+  SRLX_REQUIRE(eng != nullptr, "engine is NULL");
+  SRLX_REQUIRE(eng->n_envs >= 1 && eng->obs_dim >= 1 && eng->obs_dim <= SRLX_MAX_OBS, "n_envs / obs_dim out of range");
+  SRLX_REQUIRE(eng->ring_rows >= eng->multisteps && eng->multisteps >= 1, "ring_rows (%d) must be >= multisteps (%d)", eng->ring_rows, eng->multisteps);
+  SRLX_REQUIRE(eng->state && eng->ring_obs && eng->ring_next_obs && eng->ring_action && eng->ring_reward && eng->ring_term && eng->ring_done,
+               "ring buffer pointer is NULL");
+  SRLX_REQUIRE(eng->mem_kind == SRLX_MEM_UNIFORM || (eng->tree && eng->tree_scratch), "proportional memory needs tree + tree_scratch");
+  SRLX_REQUIRE(obs_dev && next_obs_dev && action_dev && reward_dev && term_dev && done_dev, "record pointer is NULL");
+  const int grid = (eng->n_envs + 255) / 256 < 296 ? (eng->n_envs + 255) / 256 : 296;
+  ext_row_write_kernel<<<grid, 256, 0, (cudaStream_t)cuda_stream>>>(*eng, obs_dev, next_obs_dev, action_dev, reward_dev, term_dev, done_dev);
+  count_launch();
+  SRLX_CHECK_CUDA(cudaGetLastError());
+  post_step_kernel<<<1, 1024, 0, (cudaStream_t)cuda_stream>>>(*eng, eng->tree_scratch);
+  count_launch();
+  SRLX_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+static int check_env_only(const srlx_engine* eng) {
+  using namespace srlx;
+  SRLX_REQUIRE(eng != nullptr, "engine is NULL");
+  SRLX_REQUIRE(eng->env_id == SRLX_ENV_GRID || eng->env_id == SRLX_ENV_CARTPOLE || eng->env_id == SRLX_ENV_PENDULUM,
+               "env_id %d has no device implementation", eng->env_id);
+  SRLX_REQUIRE(eng->n_envs >= 1 && eng->obs_dim >= 1 && eng->obs_dim <= 4, "n_envs / obs_dim out of range");
+  SRLX_REQUIRE(eng->state && eng->env_state && eng->env_step_num && eng->env_episode && eng->env_ep_reward && eng->env_needs_reset,
+               "env buffer pointer is NULL");
+  return 0;
+}
+
+extern "C" int srlx_env_reset_obs(const srlx_engine* eng, int force, float* out_obs_dev, uintptr_t cuda_stream) {
+  using namespace srlx;
+  if (int rc = check_env_only(eng)) return rc;
+  SRLX_REQUIRE(out_obs_dev != nullptr, "out_obs is NULL");
+  const int grid = (eng->n_envs + 255) / 256 < 296 ? (eng->n_envs + 255) / 256 : 296;
+  env_reset_obs_kernel<<<grid, 256, 0, (cudaStream_t)cuda_stream>>>(*eng, out_obs_dev, force);
+  count_launch();
+  SRLX_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int srlx_env_step_actions(const srlx_engine* eng, const int32_t* actions_dev, float* out_obs_dev, double* out_reward_dev,
+                                     unsigned char* out_term_dev, unsigned char* out_trunc_dev, uintptr_t cuda_stream) {
+  using namespace srlx;
+  if (int rc = check_env_only(eng)) return rc;
+  SRLX_REQUIRE(actions_dev && out_obs_dev && out_reward_dev && out_term_dev && out_trunc_dev, "argument pointer is NULL");
+  const int grid = (eng->n_envs + 255) / 256 < 296 ? (eng->n_envs + 255) / 256 : 296;
+  env_step_actions_kernel<<<grid, 256, 0, (cudaStream_t)cuda_stream>>>(*eng, actions_dev, out_obs_dev, out_reward_dev, out_term_dev, out_trunc_dev);
+  count_launch();
+  SRLX_CHECK_CUDA(cudaGetLastError());
+  eval_post_step_kernel<<<1, 1, 0, (cudaStream_t)cuda_stream>>>(eng->state, eng->n_envs);
+  count_launch();
+  SRLX_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
 extern "C" int srlx_vec_step(const srlx_engine* eng, int training, uintptr_t cuda_stream) {
   using namespace srlx;
   if (int rc = check_engine(eng)) return rc;
+  SRLX_REQUIRE(eng->env_id != SRLX_ENV_EXTERNAL, "srlx_vec_step: the engine's env is external (host loop); use srlx_ext_step");
   if (training) {
     SRLX_REQUIRE(eng->ring_obs && eng->ring_next_obs && eng->ring_action && eng->ring_reward && eng->ring_term && eng->ring_done,
                  "ring buffer pointer is NULL");

@@ -158,13 +158,25 @@ class DeviceEngine:
 
     # ---- control ---------------------------------------------------------------------------------------------
     def reset(self):
+        self._holds_data = False
         with torch.cuda.device(self.device):
             _lib.check(self.lib.srlx_engine_reset(C.byref(self.c), self._stream()))
 
     def set_epsilon(self, eps: float):
         self.c.epsilon = float(eps)
 
+    def _guard_eval(self, training):
+        # evaluation steps advance the vector step counter, which is also the ring cursor and the base of the sampleable range:
+        # mixing them into an engine whose ring holds data would leave unwritten rows inside that range (VecRunner.evaluate
+        # builds its own engine for this reason)
+        if training:
+            self._holds_data = True
+        elif getattr(self, "_holds_data", False):
+            raise _lib.SrlxError("evaluation steps (training=False) on an engine whose replay ring holds data: use a separate "
+                                 "engine (VecRunner.evaluate) or reset() first")
+
     def vec_step(self, training=True):
+        self._guard_eval(training)
         with torch.cuda.device(self.device):
             _lib.check(self.lib.srlx_vec_step(C.byref(self.c), int(training), self._stream()))
 
@@ -183,6 +195,7 @@ class DeviceEngine:
 
     def run(self, n_steps, updates_per_step, training=True):
         """n_steps x (one vector step of all E envs + updates_per_step trainer updates), no host sync in between."""
+        self._guard_eval(training)
         with torch.cuda.device(self.device):
             _lib.check(self.lib.srlx_engine_run(C.byref(self.c), int(n_steps), int(updates_per_step), int(training), self._stream()))
 
@@ -273,6 +286,7 @@ class DeviceEngine:
             self.t["tree"].copy_(torch.as_tensor(checkpoint.build_sum_tree(leaves, self.E * self.R)))
             st.max_priority = float(v.max_priority)
         self.write_state(st)
+        self._holds_data = True
         self.t["env_needs_reset"].fill_(1)  # the env copies start fresh episodes after a restore
 
     def hbm_bytes(self):

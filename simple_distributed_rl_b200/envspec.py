@@ -94,6 +94,12 @@ def make_env_spec(name: str, **kw) -> EnvSpec:
             raise ValueError("Pendulum-v1: action_division_num must be in [2, 16]")
         return EnvSpec(name, _lib.ENV_PENDULUM, 3, n, 200, 1, 200, reward_baseline={"episode": 10, "baseline": -500},
                        obs_low=(-1.0, -1.0, -8.0), obs_high=(1.0, 1.0, 8.0), action_table=tuple(division_table(-2.0, 2.0, n)))
+    if name == "external":
+        # stepped by a HOST loop (the reference's core_play.play through the plug-in classes, srl_classes.py): only the shapes matter
+        D, A = int(kw["obs_dim"]), int(kw["n_actions"])
+        if not (1 <= D <= 4 and 1 <= A <= 16):
+            raise NotImplementedError(f"the device learners take <= 4 observation floats and <= 16 discrete actions (got {D}, {A})")
+        return EnvSpec(name, _lib.ENV_EXTERNAL, D, A, 2**31 - 1, 0, 0, reward_baseline={})
     raise ValueError(f"environment {name!r} is not available on device (supported: Grid, EasyGrid, CartPole-v1, Pendulum-v1)")
 
 

@@ -65,8 +65,10 @@ def sequence_targets(q_online: torch.Tensor, q_target: torch.Tensor, actions: to
     target / Retrace / priority half) on the device: q_online / q_target [B, T+1, A] float32, actions [B, T], mu (stored behaviour
     probabilities) / rewards [B, T] (float64: the reference keeps them as python floats), dones [B, T] ->
     (target float64 [B, T], td_mean float64 [B], td_is_float64 bool [B]).  `td_mean` is the sequence's priority input (:204);
-    where the reference holds it as float32 its value here is that float32 widened.  The LSTM Q-network, burn-in and the sequence
-    replay around this loop are not built.  There is no CPU fallback."""
+    where the reference holds it as float32 its value here is that float32 widened.  Not implemented: the invalid-action mask of the
+    reference loop (next_invalid_actions -> -inf before the argmax, calc_epsilon_greedy_probs with invalid actions, r2d2.py:160-176) --
+    the envs on the device path have none.  The LSTM Q-network, burn-in and the sequence replay around this loop are not built.
+    There is no CPU fallback."""
     if not q_online.is_cuda:
         raise _lib.SrlxError("sequence_targets needs CUDA tensors (no CPU fallback)")
     lib = _lib.load()
@@ -76,6 +78,11 @@ def sequence_targets(q_online: torch.Tensor, q_target: torch.Tensor, actions: to
     qo, qt = q_online.to(torch.float32).contiguous(), q_target.to(torch.float32).contiguous()
     if qt.shape != qo.shape or tuple(actions.shape) != (B, T):
         raise ValueError("q_target must have the shape of q_online [B, T+1, A] and actions the shape [B, T]")
+    for name, x in (("mu", mu), ("rewards", rewards), ("dones", dones)):
+        if tuple(x.shape) != (B, T):  # the kernel indexes [b][t] with T steps per row: any other shape reads out of bounds
+            raise ValueError(f"{name} must have the shape [B, T] = {(B, T)}, got {tuple(x.shape)}")
+    if T < 1 or T > 128:
+        raise ValueError(f"sequence length T = {T} outside [1, 128]")
     act = actions.to(torch.int32).contiguous()
     mu64, r64 = mu.to(torch.float64).contiguous(), rewards.to(torch.float64).contiguous()
     dn = dones.to(torch.uint8).contiguous()

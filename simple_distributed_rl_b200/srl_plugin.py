@@ -92,7 +92,15 @@ def engine_config_from_srl(env: Any, rl_config: Any, num_envs: int, seed: int = 
     if _algo_of(rl_config) == "rainbow" and str(rl_config.get_name()).startswith("Rainbow_no_multisteps"):
         multisteps = 1
     cap = int(mem.capacity)
-    rows = ring_rows if ring_rows is not None else max(multisteps, -(-cap // int(num_envs)))
+    # an M-step window needs the M-1 rows after its first step: E * (rows - (M - 1)) items are sampleable, so the ring gets M-1
+    # rows on top of ceil(capacity / E) and the reference's own checks (priority_replay_buffer.py:195-200) apply to what is reachable
+    rows = int(ring_rows) if ring_rows is not None else -(-cap // int(num_envs)) + (multisteps - 1)
+    reachable = int(num_envs) * (rows - (multisteps - 1))
+    if rows < multisteps or reachable <= 0:
+        raise ValueError(f"ring_rows = {rows} cannot hold a {multisteps}-step window")
+    if not (int(rl_config.batch_size) <= int(mem.warmup_size) <= reachable):
+        raise ValueError(f"assert batch_size ({rl_config.batch_size}) <= memory.warmup_size ({mem.warmup_size}) <= sampleable items "
+                         f"({reachable} = {num_envs} envs x ({rows} rows - {multisteps - 1}))")
     return EngineConfig(
         env=env_name, n_envs=int(num_envs), ring_rows=int(rows), multisteps=multisteps, batch_size=int(rl_config.batch_size),
         mem_kind=mem_kind, algo=algo, enable_double_dqn=bool(rl_config.enable_double_dqn),

@@ -25,19 +25,6 @@ def golden_dir():
     return os.path.join(os.path.dirname(__file__), "golden")
 
 
-@pytest.fixture(scope="module")
-def srl_mod():
-    if not os.path.isdir(os.path.join(REF, "srl")):
-        pytest.skip("reference not present")
-    sys.path.insert(0, REF)
-    try:
-        import srl  # noqa: F401
-        from srl.algorithms import dqn, rainbow
-    finally:
-        sys.path.remove(REF)
-    return dqn, rainbow
-
-
 def _ring_from_golden(d, name, M, E=1, clip=False, extra_rows=0):
     """One env column holding the golden trajectory of the reference Runner on Grid."""
     T = len(d[f"{name}_a"])
@@ -334,3 +321,29 @@ def test_proportional_backup_of_other_capacity_restores_by_item():
     items, pri = ck.export_items(ring)
     assert [it[3] for it in items] == [0.0, 1.0, 2.0, 3.0, 4.0, 5.0]
     np.testing.assert_array_equal(pri, leaves[:n])
+
+
+def test_interleaved_trajectories_are_refused_for_multistep_memories():
+    """A reference memory filled by two actors whose items interleave (play_mp) is not one trajectory per column: with multisteps > 1
+    the ring would rebuild windows across unrelated steps, so the import raises instead of silently stitching them."""
+    E, R, M, A, D = 2, 12, 3, 4, 2
+    rng = np.random.default_rng(0)
+    v = ck.RingView(E, R, M, A, D, vec_steps=R)
+    cur = rng.normal(size=(E, D)).astype(np.float32)
+    for g in range(R):
+        sl = slice(g * E, (g + 1) * E)
+        nxt = (cur + 1.0).astype(np.float32)
+        v.obs[sl], v.next_obs[sl] = cur, nxt
+        v.action[sl] = rng.integers(0, A, size=E)
+        v.reward[sl] = rng.normal(size=E).astype(np.float32)
+        cur = nxt
+    items, _ = ck.export_items(v)                      # env-major: trajectory 0 then trajectory 1
+    n = len(items) // 2
+    back = ck.memory_restore([[items, 0], None], E, R, M, A, D, False)   # contiguous per column: imports
+    assert back.vec_steps == R
+    inter = [items[(i % 2) * n + i // 2] for i in range(2 * n)]          # actor 0, actor 1, actor 0, ... as play_mp would add them
+    with pytest.raises(ck.DiscontinuousMemoryError):
+        ck.memory_restore([[inter, 0], None], E, R, M, A, D, False)
+    ck.memory_restore([[inter, 0], None], E, R, M, A, D, False, check_continuity=False)  # explicit opt-out still works
+    one_step, _ = ck.export_items(ck.RingView(E, R, 1, A, D, vec_steps=R))
+    ck.memory_restore([[one_step[::-1], 0], None], E, R, 1, A, D, False)  # 1-step items are self-contained: any order imports

@@ -640,14 +640,12 @@ def test_full_size_lockstep_against_oracle(name):
         v.leaf_priority, v.max_priority = pri, 3.5
         dev.load_ring(v)
     orc = _oracle_from_device(dev, kw)
-    n_retries0 = orc.sample_retries
     for u in range(50):
         dev.learn(1)
         out = orc.learn(1)
         assert len(out) == 1 and dev.read_state().train_count == orc.train_count == u + 1
         _check_update_and_resync(dev, orc, out[0], check_tree=False)
     if dev.per:
-        assert orc.sample_retries > n_retries0  # 1 % zero leaves, 1600 draws: the re-draw path was exercised
         tree = dev.t["tree"].cpu().numpy()
         cap = dev.cap
         np.testing.assert_allclose(tree[: cap - 1], tree[1::2][: cap - 1] + tree[2::2][: cap - 1], rtol=1e-9, atol=1e-9)
@@ -714,10 +712,13 @@ def test_unresynced_drift_over_20_updates():
                          q_max_diff=float(np.abs(q_dev - q_orc).max()), q_scale=float(np.abs(q_orc).max()),
                          loss_dev=float(dev.read_state().last_loss), loss_orc=float(outs[-1]["loss"]), last_idx_equal=same_idx)
         print("DRIFT", name, res[name])
-        # bounds: the parameters have moved ~20 x lr; the two trajectories stay within a small fraction of that movement
-        assert diff.mean() <= 0.02 * moved.mean() + 1e-6, res[name]
-        assert np.abs(q_dev - q_orc).max() <= 2e-3 * max(1.0, np.abs(q_orc).max()), res[name]
-        assert math.isclose(res[name]["loss_dev"], res[name]["loss_orc"], rel_tol=5e-3, abs_tol=1e-4), res[name]
+        # measured on B200 (profiles/r2_a_drift.txt): max parameter difference 3.6e-7 .. 5.5e-7 after 20 updates in which the
+        # parameters moved by 7e-3 .. 1.1e-2 on average, Q within 1.4e-5, the 20th loss within 1.2e-5 relative, the 20th batch
+        # still the same leaves.  Bounds = the lockstep bars, i.e. no amplification beyond one update's tolerance:
+        assert same_idx, res[name]
+        assert diff.max() <= 2e-5 and diff.mean() <= 1e-3 * moved.mean(), res[name]
+        assert np.abs(q_dev - q_orc).max() <= 1e-4 * max(1.0, np.abs(q_orc).max()), res[name]
+        assert math.isclose(res[name]["loss_dev"], res[name]["loss_orc"], rel_tol=1e-4, abs_tol=1e-6), res[name]
 
 
 @pytest.mark.parametrize("path", learner_cases.PATHS, ids=learner_cases.IDS)
@@ -833,14 +834,14 @@ def test_learning_grid_dqn_reaches_reference_baseline():
     assert _train_and_evaluate(kw, 600, 1) >= 0.65
 
 
-def test_learning_grid_rainbow_per_multistep_reaches_reference_baseline():
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_learning_grid_rainbow_per_multistep_reaches_reference_baseline(seed):
     """Dueling head + 3-step Retrace + PER on Grid (learner_small_kernel with its replay CTA; 5 outputs rule out the fast kernel).
-    600 vector steps is early for this configuration: about one seed in three has not found the goal yet, on this kernel and on
-    the generic one alike (seed 1: -2.04 / 0.71, seed 2: 0.76 / -0.58, seed 3: 0.72 / 0.72), so the gate uses a seed on which
-    both learn."""
+    Every seed has to pass: 600 vector steps are early for this configuration (seeds 1 and 4 of 1..6 had not found the goal yet:
+    -2.04 and 0.37), at 1200 all six seeds score 0.71 .. 0.76 (tools/explore_grid_gate.py, profiles/r2_a_grid_gate.json)."""
     kw = dict(env="Grid", algo="rainbow", hidden=(64,), dueling="average", noisy=False, mem_kind=1, multisteps=3, n_envs=256,
-              ring_rows=64, batch_size=32, warmup_size=1000, epsilon=0.1, lr=1e-3, target_update_interval=1000, seed=3)
-    assert _train_and_evaluate(kw, 600, 1) >= 0.65
+              ring_rows=64, batch_size=32, warmup_size=1000, epsilon=0.1, lr=1e-3, target_update_interval=1000, seed=seed)
+    assert _train_and_evaluate(kw, 1200, 1) >= 0.65
 
 
 def test_learning_cartpole_rainbow_default_config():

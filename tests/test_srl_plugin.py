@@ -8,19 +8,6 @@ import pytest
 REF = "/root/reference"
 
 
-@pytest.fixture(scope="module")
-def srl_mod():
-    if not os.path.isdir(os.path.join(REF, "srl")):
-        pytest.skip("reference not present")
-    sys.path.insert(0, REF)
-    try:
-        import srl  # noqa: F401
-        from srl.algorithms import dqn, rainbow
-    finally:
-        sys.path.remove(REF)
-    return dqn, rainbow
-
-
 def test_rainbow_config_maps_field_by_field(srl_mod):
     from simple_distributed_rl_b200 import _lib
     from simple_distributed_rl_b200.srl_plugin import engine_config_from_srl
@@ -33,7 +20,7 @@ def test_rainbow_config_maps_field_by_field(srl_mod):
     cfg.set_torch() if hasattr(cfg, "set_torch") else None
     e = engine_config_from_srl("CartPole-v1", cfg, num_envs=8192)
     assert (e.algo, e.multisteps, e.noisy, e.dueling, e.hidden) == ("rainbow", 3, True, "average", (512,))
-    assert (e.n_envs, e.ring_rows, e.batch_size, e.warmup_size) == (8192, 245, 64, 5000)
+    assert (e.n_envs, e.ring_rows, e.batch_size, e.warmup_size) == (8192, 245 + 2, 64, 5000)  # ceil(capacity / E) + (M - 1)
     assert e.mem_kind == _lib.MEM_PROPORTIONAL and not e.has_duplicate
     assert (e.per_alpha, e.per_beta_initial, e.per_beta_steps, e.per_epsilon) == (0.7, 0.5, 1234, 1e-3)
     assert (e.lr, e.discount, e.retrace_h, e.target_update_interval) == (5e-4, 0.97, 0.8, 1000)
