@@ -152,6 +152,16 @@ class DeviceEngine:
                 setattr(c, name, self.t[name].data_ptr())
         return c
 
+    def adopt_tensors(self, tensors: dict):
+        """Bind caller-owned tensors (same shape and dtype) in place of the engine's own -- e.g. the parameter buffers of an
+        RLParameter object (srl_classes.DeviceParameter) -- and rebuild the C struct around them."""
+        for k, v in tensors.items():
+            old = self.t.get(k)
+            if old is None or old.shape != v.shape or old.dtype != v.dtype or v.device != old.device:
+                raise ValueError(f"adopt_tensors: {k!r} does not match the engine's buffer")
+            self.t[k] = v
+        self.c = self._build_struct()
+
     def _stream(self):
         s = self.stream if self.stream is not None else torch.cuda.current_stream(self.device)
         return s.cuda_stream

@@ -45,10 +45,12 @@ def _algo_of(rl_config) -> str:
     raise NotImplementedError(f"algorithm {name!r} is not on the device path (supported: DQN, Rainbow)")
 
 
-def engine_config_from_srl(env: Any, rl_config: Any, num_envs: int, seed: int = 0, ring_rows: Optional[int] = None) -> EngineConfig:
-    """Map (env id or EnvConfig, dqn/rainbow Config) -> EngineConfig.  Unsupported settings raise."""
+def engine_config_from_srl(env: Any, rl_config: Any, num_envs: int, seed: int = 0, ring_rows: Optional[int] = None,
+                           env_kwargs: Optional[dict] = None) -> EngineConfig:
+    """Map (env id or EnvConfig, dqn/rainbow Config) -> EngineConfig.  Unsupported settings raise.  env = "external" (with
+    env_kwargs = {obs_dim, n_actions}) describes an env stepped by a host loop (srl_classes.py)."""
     env_name = env if isinstance(env, str) else _get(env, "name", _get(env, "id", None))
-    env_kwargs = {} if isinstance(env, str) else dict(_get(env, "kwargs", {}) or {})
+    env_kwargs = dict(env_kwargs or {}) if isinstance(env, str) else {**dict(_get(env, "kwargs", {}) or {}), **dict(env_kwargs or {})}
     algo = _algo_of(rl_config)
     if env_name == "Pendulum-v1":  # continuous action Box: the value-based worker sees RLConfig.action_division_num torques
         env_kwargs.setdefault("action_division_num", int(_get(rl_config, "action_division_num", 10)))
