@@ -186,6 +186,17 @@ typedef struct srlx_engine {
    *      else training rollouts use g >= phase ? eps_end : epsilon - ((epsilon - eps_end) / phase) * g ---- */
   double eps_end;
   uint64_t eps_phase_steps;
+  /* ---- data-parallel single learner over the GPUs of one node (csrc/learner_fast.cu): every rank samples
+   *      batch_size items from its own replay shard, the gradients of the global batch (dp_world x batch_size items) are summed
+   *      over NVLink inside the learner kernel every update (peer stores into dp_peer[r] + flags), the IS weights use the global
+   *      N / total / max (srl/rl/memories/priority_memories/proportional_memory.py:138-167), and every rank applies the identical
+   *      Adam step -- the reference's ONE trainer (srl/base/run/play_mp.py:352-462) with its memory sharded over the GPUs ---- */
+  uint64_t learner_seed;  /* NoisyNet draws of the trainer (0 -> seed): the same on every rank, so every replica builds the same weights */
+  int32_t dp_world;       /* ranks exchanging gradients per update; 0 / 1 = off */
+  int32_t dp_rank;
+  void* dp_peer[8];       /* dp_peer[r]: the exchange buffer of rank r as addressable from this rank (own: srlx_dp_alloc or any
+                             zeroed device buffer of srlx_dp_bytes(); peers: srlx_dp_open of their IPC handle, or a peer-enabled pointer) */
+  uint64_t dp_bytes;      /* size of every exchange buffer */
 } srlx_engine;
 
 /* ---- library ------------------------------------------------------------------------------------------ */
@@ -285,6 +296,16 @@ int srlx_ext_step(const srlx_engine* eng, const float* obs_dev, const float* nex
 int srlx_env_reset_obs(const srlx_engine* eng, int force, float* out_obs_dev, uintptr_t cuda_stream);
 int srlx_env_step_actions(const srlx_engine* eng, const int32_t* actions_dev, float* out_obs_dev, double* out_reward_dev,
                           unsigned char* out_term_dev, unsigned char* out_trunc_dev, uintptr_t cuda_stream);
+/* ---- exchange buffers of the data-parallel learner (one per rank; peers write gradients and flags into them over NVLink) ------
+ * srlx_dp_bytes: bytes one buffer needs for this engine.  srlx_dp_alloc: cudaMalloc + zero + IPC handle (64 bytes) for the other
+ * processes of the node; srlx_dp_open / srlx_dp_close: map / unmap a peer's buffer from its handle; srlx_dp_free: release an own
+ * buffer; srlx_dp_enable_peer: cudaDeviceEnablePeerAccess both ways between two devices driven by ONE process. */
+size_t srlx_dp_bytes(const srlx_engine* eng);
+int srlx_dp_alloc(size_t bytes, void** ptr_out, unsigned char handle_out[64]);
+int srlx_dp_open(const unsigned char handle[64], void** ptr_out);
+int srlx_dp_close(void* ptr);
+int srlx_dp_free(void* ptr);
+int srlx_dp_enable_peer(int device_a, int device_b);
 /* Inference seam: q_out[n][A] = Q(obs[n][D]) with `params` (pred_q) or `target` (pred_target_q); noise_call_id is the
  * NoisyLinear draw to use (ignored when !noisy; kind = 3). */
 int srlx_qnet_forward(const srlx_engine* eng, int use_target, const float* obs_dev, uint32_t n, uint64_t noise_call_id,

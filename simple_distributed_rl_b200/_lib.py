@@ -85,6 +85,7 @@ class SrlxEngine(C.Structure):
         ("noise_scratch", _P), ("noise_scratch_bytes", C.c_uint64),
         ("tree_blk", _P), ("tree_blk_bytes", C.c_uint64),
         ("eps_end", C.c_double), ("eps_phase_steps", C.c_uint64),
+        ("learner_seed", C.c_uint64), ("dp_world", C.c_int32), ("dp_rank", C.c_int32), ("dp_peer", _P * 8), ("dp_bytes", C.c_uint64),
     ]
 
 
@@ -116,6 +117,12 @@ SYMBOLS = [
     ("srlx_learner_info", C.c_int, [C.POINTER(SrlxEngine), C.POINTER(C.c_int), C.POINTER(C.c_size_t)]),
     ("srlx_tree_blk_bytes", _sz, [_u64]),
     ("srlx_qnet_forward", C.c_int, [C.POINTER(SrlxEngine), _i32, _P, _u32, _u64, _P, _uptr]),
+    ("srlx_dp_bytes", _sz, [C.POINTER(SrlxEngine)]),
+    ("srlx_dp_alloc", C.c_int, [_sz, C.POINTER(C.c_void_p), C.c_char_p]),
+    ("srlx_dp_open", C.c_int, [C.c_char_p, C.POINTER(C.c_void_p)]),
+    ("srlx_dp_close", C.c_int, [_P]),
+    ("srlx_dp_free", C.c_int, [_P]),
+    ("srlx_dp_enable_peer", C.c_int, [_i32, _i32]),
     ("srlx_ext_step", C.c_int, [C.POINTER(SrlxEngine), _P, _P, _P, _P, _P, _P, _uptr]),
     ("srlx_env_reset_obs", C.c_int, [C.POINTER(SrlxEngine), _i32, _P, _uptr]),
     ("srlx_env_step_actions", C.c_int, [C.POINTER(SrlxEngine), _P, _P, _P, _P, _P, _uptr]),

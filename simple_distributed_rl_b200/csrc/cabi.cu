@@ -296,3 +296,54 @@ extern "C" int srlx_qnet_forward(const srlx_engine* eng, int use_target, const f
   SRLX_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
+
+// ---- exchange buffers of the data-parallel learner (learner_fast.cu): one per rank, written by the peers over NVLink ----------
+extern "C" int srlx_dp_alloc(size_t bytes, void** ptr_out, unsigned char handle_out[64]) {
+  SRLX_REQUIRE(ptr_out && handle_out && bytes > 0, "srlx_dp_alloc: bad arguments");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  void* p = nullptr;
+  SRLX_CHECK_CUDA(cudaMalloc(&p, bytes));
+  SRLX_CHECK_CUDA(cudaMemset(p, 0, bytes));
+  SRLX_CHECK_CUDA(cudaDeviceSynchronize());
+  cudaIpcMemHandle_t h;
+  SRLX_CHECK_CUDA(cudaIpcGetMemHandle(&h, p));
+  memcpy(handle_out, &h, 64);
+  *ptr_out = p;
+  return 0;
+}
+extern "C" int srlx_dp_open(const unsigned char handle[64], void** ptr_out) {
+  SRLX_REQUIRE(ptr_out && handle, "srlx_dp_open: bad arguments");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, 64);
+  void* p = nullptr;
+  SRLX_CHECK_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+  *ptr_out = p;
+  return 0;
+}
+extern "C" int srlx_dp_close(void* ptr) {
+  if (ptr) SRLX_CHECK_CUDA(cudaIpcCloseMemHandle(ptr));
+  return 0;
+}
+extern "C" int srlx_dp_free(void* ptr) {
+  if (ptr) SRLX_CHECK_CUDA(cudaFree(ptr));
+  return 0;
+}
+extern "C" int srlx_dp_enable_peer(int device_a, int device_b) {
+  if (device_a == device_b) return 0;
+  int cur = 0, ok = 0;
+  SRLX_CHECK_CUDA(cudaGetDevice(&cur));
+  for (int k = 0; k < 2; ++k) {
+    const int a = k == 0 ? device_a : device_b, b = k == 0 ? device_b : device_a;
+    SRLX_CHECK_CUDA(cudaDeviceCanAccessPeer(&ok, a, b));
+    SRLX_REQUIRE(ok, "device %d cannot access device %d (no P2P path)", a, b);
+    SRLX_CHECK_CUDA(cudaSetDevice(a));
+    cudaError_t e = cudaDeviceEnablePeerAccess(b, 0);
+    if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) {
+      cudaSetDevice(cur);
+      SRLX_CHECK_CUDA(e);
+    }
+    cudaGetLastError();
+  }
+  SRLX_CHECK_CUDA(cudaSetDevice(cur));
+  return 0;
+}

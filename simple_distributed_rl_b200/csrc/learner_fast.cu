@@ -244,6 +244,38 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
                "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
+// ---- data-parallel learner: exchange buffer of one rank (peers write into it over NVLink) -------------------------
+//   [0, 1024)      uint64 grad_flag[8 src ranks][16 CTAs]  = train_count + 1 of the update whose gradient slice has landed
+//   [1024, 1088)   uint64 w_flag[8 src ranks]              = train_count + 1 of the batch whose replay scalars have landed
+//   [1536, 2048)   double wsc[2 parities][8 src ranks][4]  = {shard total, shard size, min priority of the batch, max_priority}
+//   [2048, ...)    float grad[2 parities][8 src ranks][16 CTAs][PlPad]
+constexpr int kDpMaxWorld = 8, kDpHeader = 2048;
+__host__ __device__ inline size_t dp_bytes_for(int PlPad) { return (size_t)kDpHeader + (size_t)2 * kDpMaxWorld * kFMaxC * PlPad * 4; }
+__device__ __forceinline__ uint64_t* dp_grad_flag(void* base, int src, int cta) { return reinterpret_cast<uint64_t*>(base) + src * kFMaxC + cta; }
+__device__ __forceinline__ uint64_t* dp_w_flag(void* base, int src) { return reinterpret_cast<uint64_t*>(reinterpret_cast<char*>(base) + 1024) + src; }
+__device__ __forceinline__ double* dp_wsc(void* base, int par, int src) {
+  return reinterpret_cast<double*>(reinterpret_cast<char*>(base) + 1536) + (par * kDpMaxWorld + src) * 4;
+}
+__device__ __forceinline__ float* dp_grad(void* base, int par, int src, int cta, int PlPad) {
+  return reinterpret_cast<float*>(reinterpret_cast<char*>(base) + kDpHeader) + ((size_t)(par * kDpMaxWorld + src) * kFMaxC + cta) * PlPad;
+}
+__device__ __forceinline__ void st_release_sys_u64(uint64_t* p, uint64_t v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ uint64_t ld_acquire_sys_u64(const uint64_t* p) {
+  uint64_t v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+// wait until a peer's flag reaches `want`; gives up after ~1 s (a peer that died must not hang this GPU) and reports it
+__device__ __noinline__ bool dp_wait_flag(const uint64_t* flag, uint64_t want) {
+  const long long t0 = clock64();
+  while (ld_acquire_sys_u64(flag) < want) {
+    __nanosleep(40);
+    if (clock64() - t0 > 2000000000ll) return false;
+  }
+  return true;
+}
 __device__ __forceinline__ float2 f2(float a, float b) { return make_float2(a, b); }
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 
@@ -327,7 +359,7 @@ __global__ void __launch_bounds__(128) noise_precompute_kernel(const __grid_cons
       if (sg.noisy) {
 #pragma unroll
         for (int set = 0; set < 3; ++set) {
-          const float4 a = noise4(eng.seed, NOISE_KIND_TRAIN, tc * 3 + set, (uint32_t)blk);
+          const float4 a = noise4(eng.learner_seed ? eng.learner_seed : eng.seed, NOISE_KIND_TRAIN, tc * 3 + set, (uint32_t)blk);
           z[set][0] = a.x; z[set][1] = a.y; z[set][2] = a.z; z[set][3] = a.w;
         }
       }
@@ -346,7 +378,9 @@ __global__ void __launch_bounds__(128) noise_precompute_kernel(const __grid_cons
 // =====================================================================================================================
 // TC = 8 / 16: the reference's Rainbow default shape (batch 32, 3-step, 2 actions, 4 observation floats, dueling-average
 // head of 2 x 512 units) on a cluster of TC CTAs, every loop bound a compile-time constant; TC = 0: same code, run-time bounds.
-template <int TC>
+// DP: the data-parallel variant (gradient / replay-scalar exchange with the peer ranks); the single-GPU instantiations carry none of
+// its code (the per-update instruction stream is what bounds this kernel).
+template <int TC, bool DP>
 __global__ void __launch_bounds__(FNT, 1)
 learner_fast_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_updates, const float* __restrict__ noise,
                     const int max_cache_levels) {
@@ -364,6 +398,7 @@ learner_fast_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_up
   FScal* sc = reinterpret_cast<FScal*>(smem + pl.off_scal);
   int* n_seg_p = reinterpret_cast<int*>(smem + pl.off_scal + 128);
   int* n_used_p = n_seg_p + 1;
+  volatile int* dp_dead = n_seg_p + 2;  // a peer rank stopped answering: no further waits in this launch
   float* adam_ss = reinterpret_cast<float*>(smem + pl.off_adam);  // step_size per update of this launch
   float* adam_bc = adam_ss + kFMaxChunk;                          // sqrt(bias_correction2)
   float* gpow = reinterpret_cast<float*>(smem + pl.off_gpow);
@@ -411,6 +446,11 @@ learner_fast_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_up
   const bool per = eng.mem_kind == SRLX_MEM_PROPORTIONAL;
   const bool noisy = net.noisy != 0;
   const bool need_online_next = FLAG ? true : (eng.enable_double_dqn || M > 1);
+  // data-parallel learner (dp_world ranks, one engine each): gradients summed over the ranks every update
+  constexpr bool dp_on = DP;
+  const int G = DP ? eng.dp_world : 1, dp_rank = DP ? eng.dp_rank : 0;
+  const int PlPad = round_up(Pl, 4);
+  void* const dp_own = dp_on ? eng.dp_peer[dp_rank] : nullptr;
   const int rows_sent_per_item = 1 + M + (need_online_next ? M : 0);
   const int nIt = max(0, min(ipc, B - rank * ipc));  // batch items this CTA owns: [rank*ipc, rank*ipc + nIt)
   srlx_state* st = eng.state;
@@ -453,6 +493,7 @@ learner_fast_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_up
     sc->retries = 0;
     sc->sync_count = 0;
     sc->max_priority = st->max_priority;
+    *dp_dead = 0;
   }
   for (int i = tid; i < 3 * WS; i += FNT) weff[i] = 0.f;
   for (int i = tid; i < 2 * NX * 4; i += FNT) xin[i] = 0.f;
@@ -526,7 +567,14 @@ learner_fast_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_up
         float mu = p_mu[i], sgm = nz ? p_sg[i] : 0.f;
         if (do_adam) {
           float g = 0.f;
-          for (int rg = 0; rg < nRG; ++rg) g += part[(size_t)rg * Pl + i];
+          if (!dp_on) {
+            for (int rg = 0; rg < nRG; ++rg) g += part[(size_t)rg * Pl + i];
+          } else {
+            // mean over the global batch: the ranks' sums added in rank order (identical bits on every rank), own one from smem
+            const int tpar = (int)(tc_done & 1);
+            for (int r = 0; r < G; ++r) g += (r == dp_rank) ? part[i] : __ldcg(dp_grad(dp_own, tpar, r, rank, PlPad) + i);
+            g *= 1.0f / (float)G;
+          }
           float m = p_m1[i], v = p_v1[i];
           // torch/optim/adam.py _single_tensor_adam: lerp, mul_/addcmul_, sqrt/div/add_, addcdiv_
           m = m + (g - m) * (1.0f - b1);
@@ -890,6 +938,27 @@ learner_fast_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_up
       if (noisy && more && cw == 0) mbar_wait_sleep(&mbar[MB_NZ0 + (upd + 1) % 3], ((upd + 1) / 3) & 1);
       named_bar_sync(FBAR_CMP, FNC);
       SRLX_FSTAMP(ct == 0, 4);
+      if (dp_on) {
+        // ---------------------------------------------------------------- gradient all-reduce over the ranks (NVLink peer stores):
+        // this CTA's slice, summed over its row groups, goes into every peer's mailbox [parity][this rank][this CTA]; one
+        // release-store of the update number per peer publishes it; then wait for the peers' slices of the same update
+        const uint64_t seq = tc0 + upd + 1;
+        const int tpar = (int)((tc0 + upd) & 1);
+        for (int i = ct; i < n_used; i += FNC) {
+          float g = 0.f;
+          for (int rg = 0; rg < nRG; ++rg) g += part[(size_t)rg * Pl + i];
+          part[i] = g;  // row group 0's slot: only this thread touches index i
+          for (int r = 0; r < G; ++r)
+            if (r != dp_rank) dp_grad(eng.dp_peer[r], tpar, dp_rank, rank, PlPad)[i] = g;
+        }
+        __threadfence_system();
+        named_bar_sync(FBAR_CMP, FNC);
+        if (ct < G && ct != dp_rank) {
+          st_release_sys_u64(dp_grad_flag(eng.dp_peer[ct], dp_rank, rank), seq);
+          if (!*dp_dead && !dp_wait_flag(dp_grad_flag(dp_own, ct, rank), seq)) { *dp_dead = 1; st->reserved[0] = 1; }  // peer lost: results invalid
+        }
+        named_bar_sync(FBAR_CMP, FNC);
+      }
       // ---------------------------------------------------------------- Adam + target sync + next effective weights
       finish(true, upd, more);
       SRLX_FSTAMP(ct == 0, 5);
@@ -1173,10 +1242,41 @@ learner_fast_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_up
           const double stepd = (tc > 0) ? (double)(tc - 1) : 0.0;
           double beta = eng.per_beta_initial + (1.0 - eng.per_beta_initial) * stepd / eng.per_beta_steps;
           beta = beta > 1.0 ? 1.0 : beta;
-          const double w = lane < B ? pow_chain((double)mem_size * (s_pri[lane] / total), -beta) : 0.0;
-          double mx = w;
-          for (int s = 16; s > 0; s >>= 1) mx = fmax(mx, __shfl_xor_sync(FULL, mx, s));
-          wv = w / mx;
+          if (!dp_on) {
+            const double w = lane < B ? pow_chain((double)mem_size * (s_pri[lane] / total), -beta) : 0.0;
+            double mx = w;
+            for (int s = 16; s > 0; s >>= 1) mx = fmax(mx, __shfl_xor_sync(FULL, mx, s));
+            wv = w / mx;
+          } else {
+            // one memory sharded over the ranks: N, total and the weight maximum are those of ALL shards
+            // (proportional_memory.py:138-167).  w = (N p / total)^-beta falls with p, so the global maximum is the weight
+            // of the smallest priority any rank sampled: each rank publishes {total, size, min p of its batch, max_priority}
+            double pmin = lane < B ? s_pri[lane] : 1e300;
+            for (int s = 16; s > 0; s >>= 1) pmin = fmin(pmin, __shfl_xor_sync(FULL, pmin, s));
+            const uint64_t seq = tc + 1;
+            const int tpar = (int)(tc & 1);
+            double v_tot = total, v_n = (double)mem_size, v_pm = pmin, v_mx = sc->max_priority;
+            if (lane < G && lane != dp_rank) {
+              double* dst = dp_wsc(eng.dp_peer[lane], tpar, dp_rank);
+              dst[0] = v_tot; dst[1] = v_n; dst[2] = v_pm; dst[3] = v_mx;
+              __threadfence_system();
+              st_release_sys_u64(dp_w_flag(eng.dp_peer[lane], dp_rank), seq);
+              if (!*dp_dead && !dp_wait_flag(dp_w_flag(dp_own, lane), seq)) { *dp_dead = 1; st->reserved[0] = 1; }
+              const double* src = dp_wsc(dp_own, tpar, lane);
+              v_tot = __ldcg(src); v_n = __ldcg(src + 1); v_pm = __ldcg(src + 2); v_mx = __ldcg(src + 3);
+            }
+            double g_tot = 0.0, g_n = 0.0, g_pm = 1e300, g_mx = 0.0;
+            for (int r = 0; r < G; ++r) {  // rank order: the same sums on every rank
+              g_tot += __shfl_sync(FULL, v_tot, r);
+              g_n += __shfl_sync(FULL, v_n, r);
+              g_pm = fmin(g_pm, __shfl_sync(FULL, v_pm, r));
+              g_mx = fmax(g_mx, __shfl_sync(FULL, v_mx, r));
+            }
+            if (lane == 0 && g_mx > sc->max_priority) sc->max_priority = g_mx;  // one memory: one max_priority
+            const double w = lane < B ? pow_chain(g_n * (s_pri[lane] / g_tot), -beta) : 0.0;
+            const double mx = pow_chain(g_n * (g_pm / g_tot), -beta);
+            wv = w / mx;
+          }
         }
         if (lane < B) s_tmp[lane] = wv;
         __syncwarp();
@@ -1542,7 +1642,9 @@ static int learn_fast(const srlx_engine* eng, uint32_t n_updates, uintptr_t cuda
   // the reference's Rainbow default shape gets the instantiations with compile-time loop bounds
   const bool flag = eng->batch_size == 32 && eng->multisteps == 3 && eng->n_actions == 2 && eng->obs_dim == 4 &&
                     eng->net.out_dim[1] == 3 && eng->net.dueling == SRLX_DUEL_AVERAGE && eng->net.out_dim[0] == 1024;
-  auto kern = (flag && C == 8) ? learner_fast_kernel<8> : (flag && C == 16) ? learner_fast_kernel<16> : learner_fast_kernel<0>;
+  const bool dp = eng->dp_world > 1;
+  auto kern = dp ? ((flag && C == 16) ? learner_fast_kernel<16, true> : learner_fast_kernel<0, true>)
+                 : ((flag && C == 8) ? learner_fast_kernel<8, false> : (flag && C == 16) ? learner_fast_kernel<16, false> : learner_fast_kernel<0, false>);
   SRLX_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.total));
   if (C > 8) SRLX_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
   const size_t per_update = (size_t)C * 3 * pl.Pl * 4;
@@ -1554,6 +1656,13 @@ static int learn_fast(const srlx_engine* eng, uint32_t n_updates, uintptr_t cuda
   if (const char* e = getenv("SRLX_CHUNK")) {
     const int v = atoi(e);
     if (v >= 1 && (uint32_t)v < chunk) chunk = (uint32_t)v;
+  }
+  if (eng->dp_world > 1) {
+    SRLX_REQUIRE(eng->dp_world <= kDpMaxWorld && eng->dp_rank >= 0 && eng->dp_rank < eng->dp_world, "dp_rank %d / dp_world %d out of range",
+                 eng->dp_rank, eng->dp_world);
+    for (int r = 0; r < eng->dp_world; ++r) SRLX_REQUIRE(eng->dp_peer[r] != nullptr, "dp_peer[%d] is NULL", r);
+    SRLX_REQUIRE(eng->dp_bytes >= dp_bytes_for(round_up(pl.Pl, 4)), "dp exchange buffer too small: %llu < %zu bytes",
+                 (unsigned long long)eng->dp_bytes, dp_bytes_for(round_up(pl.Pl, 4)));
   }
   cudaStream_t stream = (cudaStream_t)cuda_stream;
   // blocked copy of the deep tree levels: the rollout writes only the flat tree, so rebuild once per call
@@ -1733,6 +1842,17 @@ extern "C" int srlx_learner_info(const srlx_engine* eng, int* cluster_size, size
   return rc;
 }
 
+// bytes of one rank's exchange buffer for the data-parallel learner (0: this engine does not take the cluster kernel)
+extern "C" size_t srlx_dp_bytes(const srlx_engine* eng) {
+  using namespace srlx;
+  if (eng == nullptr) return 0;
+  int C = 0, lev = 0;
+  size_t sm = 0;
+  if (fast_choose(eng, &C, &lev, &sm) != 1) return 0;
+  const FPlan pl = make_fplan(*eng, C, 2ll * eng->ring_rows * eng->n_envs - 1, lev);
+  return dp_bytes_for(round_up(pl.Pl, 4));
+}
+
 extern "C" int srlx_learn(const srlx_engine* eng, uint32_t n_updates, uintptr_t cuda_stream) {
   using namespace srlx;
   SRLX_REQUIRE(eng != nullptr, "srlx_learn: eng is NULL");
@@ -1752,6 +1872,7 @@ extern "C" int srlx_learn(const srlx_engine* eng, uint32_t n_updates, uintptr_t 
   const int rc = fast_choose(eng, &C, &lev, &smem_bytes);
   if (rc < 0) return rc;
   if (rc == 1) return learn_fast(eng, n_updates, cuda_stream, C, lev);
+  SRLX_REQUIRE(eng->dp_world <= 1, "the data-parallel learner (dp_world = %d) exists for the single-hidden-layer cluster kernel only", eng->dp_world);
   if (small_pick(eng, &smem_bytes, &C) == 2) return learn_small(eng, n_updates, cuda_stream);
   return learn_generic(eng, n_updates, cuda_stream);
 }

@@ -143,6 +143,11 @@ class DeviceEngine:
             setattr(c, k, float(getattr(cfg, k)))
         c.eps_end, c.eps_phase_steps = float(cfg.eps_end), int(cfg.eps_phase_steps)
         c.net = self.spec.to_c()
+        dp = getattr(self, "_dp", None)
+        if dp is not None:  # data-parallel learner (parallel.link_engines / link_engine_distributed)
+            c.learner_seed, c.dp_world, c.dp_rank, c.dp_bytes = dp["learner_seed"], dp["world"], dp["rank"], dp["nbytes"]
+            for r, ptr in enumerate(dp["peers"]):
+                c.dp_peer[r] = ptr
         if "noise_scratch" in self.t:
             c.noise_scratch_bytes = self.t["noise_scratch"].numel() * 4
         if "tree_blk" in self.t:
@@ -151,6 +156,27 @@ class DeviceEngine:
             if name in self.t:
                 setattr(c, name, self.t[name].data_ptr())
         return c
+
+    def set_data_parallel(self, world: int, rank: int, peer_ptrs, nbytes: int, learner_seed: int):
+        """Make this engine rank `rank` of a `world`-rank data-parallel learner: peer_ptrs[r] = the exchange buffer of rank r as
+        addressable from this device (include/srlx.h srlx_engine.dp_peer); world <= 1 turns it off."""
+        if world <= 1:
+            self._dp = None
+        else:
+            if not (0 <= rank < world <= 8) or len(peer_ptrs) != world:
+                raise ValueError("set_data_parallel: rank / world / peer_ptrs inconsistent (world <= 8)")
+            self._dp = dict(world=int(world), rank=int(rank), peers=[int(p) for p in peer_ptrs], nbytes=int(nbytes),
+                            learner_seed=int(learner_seed) & 0xFFFFFFFFFFFFFFFF)
+        self.c = self._build_struct()
+
+    def dp_bytes(self) -> int:
+        with torch.cuda.device(self.device):
+            return int(self.lib.srlx_dp_bytes(C.byref(self.c)))
+
+    def check_dp_alive(self):
+        """After a data-parallel launch: raises if a peer rank stopped answering inside the kernel (the wait gave up)."""
+        if getattr(self, "_dp", None) is not None and self.read_state().reserved[0] != 0:
+            raise _lib.SrlxError("data-parallel learner: a peer rank did not answer within the in-kernel timeout; results are invalid")
 
     def adopt_tensors(self, tensors: dict):
         """Bind caller-owned tensors (same shape and dtype) in place of the engine's own -- e.g. the parameter buffers of an

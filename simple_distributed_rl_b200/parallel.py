@@ -9,7 +9,15 @@ learner with a full weight replica -- experience never leaves the GPU that gener
     (srl/runner/callbacks/print_progress.py:224-237 defines the rates per process).
 Per-actor exploration follows the reference's Ape-X ladder (srl/rl/functions.py:145-154, hooked by
 rainbow.Config.setup_from_actor, srl/algorithms/rainbow/rainbow.py:109-114).
+
+Single-learner mode (`link_engines` / `link_engine_distributed`): the reference has ONE trainer
+(srl/base/run/play_mp.py:352-462) fed by all actors.  Here every rank keeps its replay shard and samples `batch_size` items from
+it; the gradients of the global batch are summed over NVLink INSIDE the learner kernel on every update (peer stores into the
+ranks' exchange buffers + release/acquire flags, csrc/learner_fast.cu), the IS weights use the global N / total / max
+(proportional_memory.py:138-167), and every rank applies the identical Adam step, so parameters, moments and the target network
+stay bit-identical on all ranks with no separate broadcast.  Replica mode (`average_parameters`) stays available.
 """
+import ctypes as C
 from dataclasses import replace
 from typing import List, Sequence
 
@@ -68,3 +76,84 @@ def reduce_counters(times_ms: Sequence[float], counts: Sequence[float], device="
         dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
         dist.all_reduce(c, op=dist.ReduceOp.SUM, group=group)
     return [float(x) for x in t.tolist()], [float(x) for x in c.tolist()]
+
+
+# ---- single-learner mode: exchange buffers of the in-kernel gradient all-reduce ------------------------------------------------
+_PARAM_TENSORS = ("params", "params_sigma", "target", "target_sigma", "adam_m", "adam_v")
+
+
+def link_engines(engines, learner_seed: int = 1) -> None:
+    """ONE process driving several engines, one per device: wire them into a data-parallel learner.  Rank r = engines[r].
+    Parameters, moments, target network and trainer counters are copied from engines[0]; the exchange buffers are plain zeroed
+    device tensors, addressable across devices after cudaDeviceEnablePeerAccess."""
+    from . import _lib
+
+    world = len(engines)
+    if world < 2:
+        return
+    lib = engines[0].lib
+    for a in engines:
+        for b in engines:
+            if a is not b and a.device != b.device:
+                _lib.check(lib.srlx_dp_enable_peer(a.device.index or 0, b.device.index or 0))
+    nbytes = engines[0].dp_bytes()
+    if nbytes == 0:
+        raise _lib.SrlxError("the data-parallel learner needs the single-hidden-layer cluster kernel (srlx_learner_info == 1)")
+    bufs = []
+    for e in engines:
+        if e.dp_bytes() != nbytes:
+            raise ValueError("link_engines: the engines' networks differ")
+        e.t["dp_xchg"] = torch.zeros(nbytes, dtype=torch.uint8, device=e.device)
+        bufs.append(e.t["dp_xchg"])
+    src = engines[0]
+    st0 = src.read_state()
+    for r, e in enumerate(engines):
+        if r > 0:
+            for k in _PARAM_TENSORS:
+                if k in e.t:
+                    e.t[k].copy_(src.t[k])
+            st = e.read_state()
+            st.train_count, st.adam_step, st.sync_count = st0.train_count, st0.adam_step, st0.sync_count
+            e.write_state(st)
+        e.set_data_parallel(world, r, [b.data_ptr() for b in bufs], nbytes, learner_seed)
+    for e in engines:
+        torch.cuda.synchronize(e.device)
+
+
+def link_engine_distributed(engine, learner_seed: int = 1, group=None) -> None:
+    """One process per GPU (torch.distributed initialised, all ranks on one node): allocate this rank's exchange buffer, swap CUDA
+    IPC handles with the peers, map theirs, broadcast rank 0's parameters / moments / target / trainer counters."""
+    from . import _lib
+
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    if world < 2:
+        return
+    lib = engine.lib
+    nbytes = engine.dp_bytes()
+    if nbytes == 0:
+        raise _lib.SrlxError("the data-parallel learner needs the single-hidden-layer cluster kernel (srlx_learner_info == 1)")
+    own, handle = C.c_void_p(0), C.create_string_buffer(64)
+    with torch.cuda.device(engine.device):
+        _lib.check(lib.srlx_dp_alloc(nbytes, C.byref(own), handle))
+    handles = [None] * world
+    dist.all_gather_object(handles, bytes(handle.raw), group=group)
+    peers = []
+    for r in range(world):
+        if r == rank:
+            peers.append(own.value)
+        else:
+            p = C.c_void_p(0)
+            with torch.cuda.device(engine.device):
+                _lib.check(lib.srlx_dp_open(handles[r], C.byref(p)))
+            peers.append(p.value)
+    engine._dp_own_ptr, engine._dp_peer_ptrs = own.value, peers
+    tensors = [engine.t[k] for k in _PARAM_TENSORS if k in engine.t]
+    broadcast_parameters(tensors, src=0, group=group)
+    st = engine.read_state()
+    cnt = torch.tensor([st.train_count, st.adam_step, st.sync_count], dtype=torch.int64, device=engine.device)
+    dist.broadcast(cnt, src=0, group=group)
+    st.train_count, st.adam_step, st.sync_count = [int(x) for x in cnt.tolist()]
+    engine.write_state(st)
+    engine.set_data_parallel(world, rank, peers, nbytes, learner_seed)
+    torch.cuda.synchronize(engine.device)
+    dist.barrier(group=group)

@@ -54,7 +54,7 @@ def test_reference_runner_trains_through_device_classes(plug, srl_mod, tmp_path)
     obs = eng.t["ring_obs"][:n].cpu().numpy()
     assert obs.min() >= 0 and obs[:, 0].max() <= 5 and obs[:, 1].max() <= 4
     assert set(np.unique(eng.t["ring_action"][:n].cpu().numpy())) <= {0, 1, 2, 3}
-    rewards = runner.evaluate(max_episodes=3, max_steps=30)
+    rewards = runner.evaluate(max_episodes=3)
     assert len(rewards) == 3
     # parameter / memory files in the reference's formats, through the reference's own Runner methods
     p, m = str(tmp_path / "p.dat"), str(tmp_path / "m.dat")

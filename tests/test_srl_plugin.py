@@ -126,3 +126,34 @@ def test_reference_runner_runs_on_the_restated_envs(srl_mod):
             assert runner.rl_config.action_space.n == n_act  # Pendulum: the reference's own 10-way division of the torque Box
     finally:
         sys.path.remove(REF)
+
+
+def test_plugin_classes_register_under_the_reference_keys_and_fail_loudly_without_cuda(srl_mod):
+    """srl_classes.register() takes over "DQN:torch" / "Rainbow:torch" / "Rainbow_no_multisteps:torch" in the reference's registry
+    (srl/base/rl/registration.py:228-251) and registers the device envs; unregister() restores the reference's classes; without a
+    CUDA device the classes refuse to construct (no CPU fallback) instead of silently training on the host."""
+    import torch
+
+    import srl
+    from srl.base.env import registration as env_reg
+    from srl.base.rl import registration as rl_reg
+
+    from simple_distributed_rl_b200 import _lib, srl_classes
+
+    dqn, rainbow = srl_mod
+    before = {k: list(v) for k, v in rl_reg._registry.items()}
+    srl_classes.register()
+    try:
+        for key in ("DQN:torch", "Rainbow:torch", "Rainbow_no_multisteps:torch"):
+            assert rl_reg._registry[key] == [f"simple_distributed_rl_b200.srl_classes:Device{n}" for n in ("Memory", "Parameter", "Trainer", "Worker")]
+        assert rl_reg._registry["DQN:tensorflow"] == before["DQN:tensorflow"]  # other frameworks untouched
+        for cls in (srl_classes.DeviceMemory, srl_classes.DeviceParameter, srl_classes.DeviceTrainer, srl_classes.DeviceWorker):
+            assert any(b.__module__.startswith("srl.base.rl") for b in cls.__mro__)  # the reference's own base classes
+        assert "Grid-b200" in env_reg._registry and "CartPole-v1" in env_reg._registry
+        if not torch.cuda.is_available():
+            runner = srl.Runner("Grid", dqn.Config())
+            with pytest.raises(_lib.SrlxError, match="no CPU fallback"):
+                runner.train(max_train_count=1)
+    finally:
+        srl_classes.unregister()
+    assert {k: rl_reg._registry[k] for k in before} == before
