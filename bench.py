@@ -72,7 +72,8 @@ def workload_config(args, world):
             "updates_per_step_per_gpu": (args.envs // args.train_interval) * args.vec_steps_per_step,
             "env_steps_per_step": args.envs * world * args.vec_steps_per_step,
             "parallelism": (f"shard{world}: env/replay/SumTree shards + learner replica per GPU, parameters averaged by one "
-                            f"NCCL all-reduce per step") if world > 1 else "single",
+                            f"NCCL all-reduce per step (the single-learner mode over the same shards is measured in the same run: key "
+                            f"single_learner)") if world > 1 else "single",
             "l2": "flushed between timed steps (256 MiB write), device-timed and e2e alike"}
 
 
@@ -402,6 +403,48 @@ def own_arm(args):
                    "checks and callbacks; L2 flushed once per bench step; envs are generated on device by design, so there is no "
                    "bulk host input on this path"}
 
+    # ---- N > 1: the SINGLE-LEARNER mode measured next to the replicas: every update is one Trainer.train() on the global
+    #      batch (world x 32 items), gradients summed over NVLink inside the learner kernel, identical Adam on every rank ----------
+    single = None
+    if world > 1:
+        parallel.link_engine_distributed(eng, learner_seed=12345)
+        for _ in range(2):
+            for _ in range(S):
+                eng.vec_step()
+                eng.learn(U)
+        barrier()
+        sl0 = eng.read_state()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        Ks = max(2, K // 2)
+        a.record()
+        for _ in range(Ks):
+            flush.zero_()
+            for _ in range(S):
+                eng.vec_step()
+                eng.learn(U)
+        b.record()
+        barrier()
+        eng.check_dp_alive()
+        sl1 = eng.read_state()
+        ms = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device=dev)
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        flat = torch.cat([eng.t[k].reshape(-1) for k in ("params", "target", "adam_m", "adam_v")])
+        ref = flat.clone()
+        dist.broadcast(ref, src=0)
+        same = torch.tensor([1.0 if torch.equal(ref, flat) else 0.0], device=dev)
+        dist.all_reduce(same, op=dist.ReduceOp.MIN)
+        n_upd = float(sl1.train_count - sl0.train_count)
+        sl_ms = float(ms.item())
+        single = {"env_steps_per_sec": world * Ks * S * E / (sl_ms * 1e-3), "trainer_updates_per_sec": n_upd / (sl_ms * 1e-3),
+                  "global_batch": 32 * world, "items_per_sec": 32 * world * n_upd / (sl_ms * 1e-3), "us_per_update": 1e3 * sl_ms / n_upd,
+                  "replica_us_per_update": 1e3 * t_learn / (updates / world),
+                  "exchange_us_per_update": 1e3 * sl_ms / n_upd - 1e3 * t_dev / (updates / world),
+                  "steps": Ks, "replicas_bit_identical": bool(same.item() == 1.0),
+                  "what": "one trainer over all shards: per-update gradient all-reduce + global PER scalars as NVLink peer stores "
+                          "inside learner_fast_kernel (words carry their own update tag), identical Adam on every rank; "
+                          "exchange_us_per_update = whole-pass time per update minus the replica mode's"}
+        eng.set_data_parallel(1, 0, [], 0, 0)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -471,7 +514,7 @@ def own_arm(args):
             "data": "synthetic", "config": workload_config(args, world),
             "trainer_updates_per_sec": upd_rate, "wall_ms_per_step": 1e3 * t_wall / K,
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clk, "roofline": roofline,
-            "roofline_rollout": roofline_rollout, "cpu_baseline": cpu,
+            "roofline_rollout": roofline_rollout, "cpu_baseline": cpu, "single_learner": single,
             "final_loss": float(st1.last_loss), "episodes": int(st1.episode_count),
             "mean_episode_len": float(st1.episode_len_sum) / max(1, st1.episode_count)}
     print(json.dumps(line), flush=True)

@@ -242,6 +242,22 @@ int srlx_tree_update(double* tree, uint64_t capacity, srlx_state* meta, const in
 int srlx_tree_retrieve(const double* tree, uint64_t capacity, const double* vals_dev, uint32_t n,
                        int64_t* out_tree_idx, uintptr_t cuda_stream);
 
+/* ---- rank-based prioritized replay (csrc/rankbased.cu) <- RankBasedMemory
+ *      srl/rl/memories/priority_memories/rankbased_memory.py:15-77 behind the IPriorityMemory seam (imemory.py:7-34) --------------
+ * priorities: float32 [capacity], item i's priority as the reference stores it (|td| as handed to update(); None -> NaN, sorted last).
+ * srlx_rank_sample = sample(batch_size, step) for the first n items: argsort(-priorities[:n]) (radix sort on device), rank
+ * probabilities (1/rank)^alpha, np.random.choice(..., replace=False) replayed on the uniform stream u01_dev (NULL: Philox(seed,
+ * draw_id)), IS weights (n * prob)^-beta / max as float64.  rebuild_cdf != 0 when n or alpha changed since the last call on this
+ * scratch.  out_idx: item indices (what the reference returns as `sampled_indices`); out_ranks (optional): their 0-based ranks;
+ * out_used (optional): uniforms consumed.  srlx_rank_update = update(indices, priorities): priorities[idx[i]] = values[i] in order. */
+size_t srlx_rank_scratch_bytes(uint64_t capacity);
+int srlx_rank_sample(const float* priorities_dev, uint64_t capacity, uint32_t n, double alpha, double beta, uint32_t batch,
+                     const double* u01_dev, uint32_t n_u, uint64_t seed, uint64_t draw_id, int rebuild_cdf, void* scratch_dev,
+                     int64_t* out_idx_dev, double* out_weights_dev, uint32_t* out_ranks_dev, uint32_t* out_used_dev, uintptr_t cuda_stream);
+int srlx_rank_update(float* priorities_dev, const int64_t* idx_dev, const float* values_dev, uint32_t n, uintptr_t cuda_stream);
+int srlx_rank_argsort(const float* priorities_dev, uint64_t capacity, uint32_t n, void* scratch_dev, uint32_t* out_sorted_idx_dev,
+                      uintptr_t cuda_stream);
+
 /* ---- PPO worker-side returns (R15, the worker half) ------------------------------------------------------ */
 #define SRLX_RETURNS_GAE 0
 #define SRLX_RETURNS_MC 1

@@ -117,6 +117,10 @@ SYMBOLS = [
     ("srlx_learner_info", C.c_int, [C.POINTER(SrlxEngine), C.POINTER(C.c_int), C.POINTER(C.c_size_t)]),
     ("srlx_tree_blk_bytes", _sz, [_u64]),
     ("srlx_qnet_forward", C.c_int, [C.POINTER(SrlxEngine), _i32, _P, _u32, _u64, _P, _uptr]),
+    ("srlx_rank_scratch_bytes", _sz, [_u64]),
+    ("srlx_rank_sample", C.c_int, [_P, _u64, _u32, _dbl, _dbl, _u32, _P, _u32, _u64, _u64, _i32, _P, _P, _P, _P, _P, _uptr]),
+    ("srlx_rank_update", C.c_int, [_P, _P, _P, _u32, _uptr]),
+    ("srlx_rank_argsort", C.c_int, [_P, _u64, _u32, _P, _P, _uptr]),
     ("srlx_dp_bytes", _sz, [C.POINTER(SrlxEngine)]),
     ("srlx_dp_alloc", C.c_int, [_sz, C.POINTER(C.c_void_p), C.c_char_p]),
     ("srlx_dp_open", C.c_int, [C.c_char_p, C.POINTER(C.c_void_p)]),

@@ -245,36 +245,36 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
                : "memory");
 }
 // ---- data-parallel learner: exchange buffer of one rank (peers write into it over NVLink) -------------------------
-//   [0, 1024)      uint64 grad_flag[8 src ranks][16 CTAs]  = train_count + 1 of the update whose gradient slice has landed
-//   [1024, 1088)   uint64 w_flag[8 src ranks]              = train_count + 1 of the batch whose replay scalars have landed
-//   [1536, 2048)   double wsc[2 parities][8 src ranks][4]  = {shard total, shard size, min priority of the batch, max_priority}
-//   [2048, ...)    float grad[2 parities][8 src ranks][16 CTAs][PlPad]
+// Every 64-bit word carries its own flag: {payload: 32 bits, update number (train_count + 1): 32 bits}.  A sender just stores
+// the words into the peer's buffer (no fence, no separate flag: an aligned 8-byte store lands whole); a receiver polls each word
+// until its tag is the update it waits for -- one NVLink store latency per exchange instead of store + fence + flag.  Two
+// parities, so a rank one update ahead never overwrites words its peer has not read yet.
+//   [0, 1024)   uint64 wsc[2 parities][8 src ranks][8]: the halves of {shard total, shard size, min priority of the batch, max_priority}
+//   [2048, ...) uint64 grad[2 parities][8 src ranks][16 CTAs][PlPad]: a CTA's gradient slice
 constexpr int kDpMaxWorld = 8, kDpHeader = 2048;
-__host__ __device__ inline size_t dp_bytes_for(int PlPad) { return (size_t)kDpHeader + (size_t)2 * kDpMaxWorld * kFMaxC * PlPad * 4; }
-__device__ __forceinline__ uint64_t* dp_grad_flag(void* base, int src, int cta) { return reinterpret_cast<uint64_t*>(base) + src * kFMaxC + cta; }
-__device__ __forceinline__ uint64_t* dp_w_flag(void* base, int src) { return reinterpret_cast<uint64_t*>(reinterpret_cast<char*>(base) + 1024) + src; }
-__device__ __forceinline__ double* dp_wsc(void* base, int par, int src) {
-  return reinterpret_cast<double*>(reinterpret_cast<char*>(base) + 1536) + (par * kDpMaxWorld + src) * 4;
+__host__ __device__ inline size_t dp_bytes_for(int PlPad) { return (size_t)kDpHeader + (size_t)2 * kDpMaxWorld * kFMaxC * PlPad * 8; }
+__device__ __forceinline__ unsigned long long* dp_wsc(void* base, int par, int src) {
+  return reinterpret_cast<unsigned long long*>(base) + (par * kDpMaxWorld + src) * 8;
 }
-__device__ __forceinline__ float* dp_grad(void* base, int par, int src, int cta, int PlPad) {
-  return reinterpret_cast<float*>(reinterpret_cast<char*>(base) + kDpHeader) + ((size_t)(par * kDpMaxWorld + src) * kFMaxC + cta) * PlPad;
+__device__ __forceinline__ unsigned long long* dp_grad(void* base, int par, int src, int cta, int PlPad) {
+  return reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(base) + kDpHeader) + ((size_t)(par * kDpMaxWorld + src) * kFMaxC + cta) * PlPad;
 }
-__device__ __forceinline__ void st_release_sys_u64(uint64_t* p, uint64_t v) {
-  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+__device__ __forceinline__ void dp_store(unsigned long long* p, uint32_t payload, uint32_t tag) {
+  const unsigned long long v = ((unsigned long long)tag << 32) | payload;
+  asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
-__device__ __forceinline__ uint64_t ld_acquire_sys_u64(const uint64_t* p) {
-  uint64_t v;
-  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-  return v;
-}
-// wait until a peer's flag reaches `want`; gives up after ~1 s (a peer that died must not hang this GPU) and reports it
-__device__ __noinline__ bool dp_wait_flag(const uint64_t* flag, uint64_t want) {
-  const long long t0 = clock64();
-  while (ld_acquire_sys_u64(flag) < want) {
-    __nanosleep(40);
-    if (clock64() - t0 > 2000000000ll) return false;
+// poll one word until it carries `tag`; gives up after ~1 s (a peer that died must not hang this GPU): *dead is then set
+__device__ __noinline__ uint32_t dp_load(const unsigned long long* p, uint32_t tag, volatile int* dead) {
+  unsigned long long v;
+  long long t0 = 0;
+  for (int it = 0;; ++it) {
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    if ((uint32_t)(v >> 32) == tag || *dead) break;
+    __nanosleep(100);  // thousands of threads poll at once: back off so the replay warps keep their L2 bandwidth
+    if (it == 256) t0 = clock64();
+    if (it > 256 && clock64() - t0 > 2000000000ll) { *dead = 1; break; }
   }
-  return true;
+  return (uint32_t)v;
 }
 __device__ __forceinline__ float2 f2(float a, float b) { return make_float2(a, b); }
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
@@ -570,9 +570,12 @@ learner_fast_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_up
           if (!dp_on) {
             for (int rg = 0; rg < nRG; ++rg) g += part[(size_t)rg * Pl + i];
           } else {
-            // mean over the global batch: the ranks' sums added in rank order (identical bits on every rank), own one from smem
+            // mean over the global batch: the ranks' sums added in rank order (identical bits on every rank), own one from smem,
+            // the peers' from this rank's mailboxes as they land
             const int tpar = (int)(tc_done & 1);
-            for (int r = 0; r < G; ++r) g += (r == dp_rank) ? part[i] : __ldcg(dp_grad(dp_own, tpar, r, rank, PlPad) + i);
+            const uint32_t tag = (uint32_t)(tc_done + 1);
+            for (int r = 0; r < G; ++r)
+              g += (r == dp_rank) ? part[i] : __uint_as_float(dp_load(dp_grad(dp_own, tpar, r, rank, PlPad) + i, tag, dp_dead));
             g *= 1.0f / (float)G;
           }
           float m = p_m1[i], v = p_v1[i];
@@ -940,24 +943,17 @@ learner_fast_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_up
       SRLX_FSTAMP(ct == 0, 4);
       if (dp_on) {
         // ---------------------------------------------------------------- gradient all-reduce over the ranks (NVLink peer stores):
-        // this CTA's slice, summed over its row groups, goes into every peer's mailbox [parity][this rank][this CTA]; one
-        // release-store of the update number per peer publishes it; then wait for the peers' slices of the same update
-        const uint64_t seq = tc0 + upd + 1;
+        // this CTA's slice, summed over its row groups, goes word by word (value + update tag) into every peer's mailbox
+        // [parity][this rank][this CTA]; the Adam pass below picks the peers' words up as they land
+        const uint32_t tag = (uint32_t)(tc0 + upd + 1);
         const int tpar = (int)((tc0 + upd) & 1);
         for (int i = ct; i < n_used; i += FNC) {
           float g = 0.f;
           for (int rg = 0; rg < nRG; ++rg) g += part[(size_t)rg * Pl + i];
-          part[i] = g;  // row group 0's slot: only this thread touches index i
+          part[i] = g;  // row group 0's slot: only this thread touches index i, here and in the Adam pass
           for (int r = 0; r < G; ++r)
-            if (r != dp_rank) dp_grad(eng.dp_peer[r], tpar, dp_rank, rank, PlPad)[i] = g;
+            if (r != dp_rank) dp_store(dp_grad(eng.dp_peer[r], tpar, dp_rank, rank, PlPad) + i, __float_as_uint(g), tag);
         }
-        __threadfence_system();
-        named_bar_sync(FBAR_CMP, FNC);
-        if (ct < G && ct != dp_rank) {
-          st_release_sys_u64(dp_grad_flag(eng.dp_peer[ct], dp_rank, rank), seq);
-          if (!*dp_dead && !dp_wait_flag(dp_grad_flag(dp_own, ct, rank), seq)) { *dp_dead = 1; st->reserved[0] = 1; }  // peer lost: results invalid
-        }
-        named_bar_sync(FBAR_CMP, FNC);
       }
       // ---------------------------------------------------------------- Adam + target sync + next effective weights
       finish(true, upd, more);
@@ -1228,6 +1224,22 @@ learner_fast_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_up
           }
         }
         SRLX_SSTAMP(25);
+        if (dp_on && per && mt < 32) {
+          // data-parallel learner: this shard's replay scalars of batch `tc` go to the peers NOW (the IS weights that need the
+          // peers' scalars are formed only after the gather, one NVLink latency from here)
+          double pmin = mt < B ? s_pri[mt] : 1e300;
+          for (int s = 16; s > 0; s >>= 1) pmin = fmin(pmin, __shfl_xor_sync(FULL, pmin, s));
+          if (mt < G && mt != dp_rank) {
+            const double v[4] = {cache[0], (double)mem_size, pmin, sc->max_priority};
+            unsigned long long* dst = dp_wsc(eng.dp_peer[mt], (int)(tc & 1), dp_rank);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const unsigned long long bits = (unsigned long long)__double_as_longlong(v[k]);
+              dp_store(dst + 2 * k, (uint32_t)bits, (uint32_t)(tc + 1));
+              dp_store(dst + 2 * k + 1, (uint32_t)(bits >> 32), (uint32_t)(tc + 1));
+            }
+          }
+        }
         if (eng.dbg_sample_idx)
           for (int i = mt; i < B; i += FNM) eng.dbg_sample_idx[i] = per ? (int64_t)s_idx[i] : (int64_t)(s_idx[i] - cap1);
       };
@@ -1253,18 +1265,27 @@ learner_fast_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_up
             // of the smallest priority any rank sampled: each rank publishes {total, size, min p of its batch, max_priority}
             double pmin = lane < B ? s_pri[lane] : 1e300;
             for (int s = 16; s > 0; s >>= 1) pmin = fmin(pmin, __shfl_xor_sync(FULL, pmin, s));
-            const uint64_t seq = tc + 1;
+            const uint32_t tag = (uint32_t)(tc + 1);
             const int tpar = (int)(tc & 1);
-            double v_tot = total, v_n = (double)mem_size, v_pm = pmin, v_mx = sc->max_priority;
+            double v[4] = {total, (double)mem_size, pmin, sc->max_priority};  // (what sample_slots sent to the peers)
             if (lane < G && lane != dp_rank) {
-              double* dst = dp_wsc(eng.dp_peer[lane], tpar, dp_rank);
-              dst[0] = v_tot; dst[1] = v_n; dst[2] = v_pm; dst[3] = v_mx;
-              __threadfence_system();
-              st_release_sys_u64(dp_w_flag(eng.dp_peer[lane], dp_rank), seq);
-              if (!*dp_dead && !dp_wait_flag(dp_w_flag(dp_own, lane), seq)) { *dp_dead = 1; st->reserved[0] = 1; }
-              const double* src = dp_wsc(dp_own, tpar, lane);
-              v_tot = __ldcg(src); v_n = __ldcg(src + 1); v_pm = __ldcg(src + 2); v_mx = __ldcg(src + 3);
+              const unsigned long long* src = dp_wsc(dp_own, tpar, lane);
+              unsigned long long w[8];
+              long long t0 = 0;
+              for (int it = 0;; ++it) {  // the eight words polled together: one L2 round trip per attempt
+                bool ok = true;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(w[k]) : "l"(src + k) : "memory");
+#pragma unroll
+                for (int k = 0; k < 8; ++k) ok = ok && ((uint32_t)(w[k] >> 32) == tag);
+                if (ok || *dp_dead) break;
+                if (it == 64) t0 = clock64();
+                if (it > 64 && clock64() - t0 > 2000000000ll) { *dp_dead = 1; break; }
+              }
+#pragma unroll
+              for (int k = 0; k < 4; ++k) v[k] = __longlong_as_double((long long)((w[2 * k + 1] << 32) | (w[2 * k] & 0xffffffffull)));
             }
+            const double v_tot = v[0], v_n = v[1], v_pm = v[2], v_mx = v[3];
             double g_tot = 0.0, g_n = 0.0, g_pm = 1e300, g_mx = 0.0;
             for (int r = 0; r < G; ++r) {  // rank order: the same sums on every rank
               g_tot += __shfl_sync(FULL, v_tot, r);
@@ -1623,6 +1644,7 @@ learner_fast_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_up
       }
     }
   }
+  if (DP && tid == 0 && *dp_dead) st->reserved[0] = 1;  // a peer rank stopped answering: the host raises (check_dp_alive)
   if (rank == 0 && tid == 0) {
     st->train_count = tc0 + n_updates;
     st->adam_step = adam0 + n_updates;

@@ -120,3 +120,100 @@ class DeviceProportionalMemory:
 
     def tree_array(self) -> np.ndarray:
         return self._tree.cpu().numpy()
+
+
+class DeviceRankBasedMemory:
+    """The reference's RankBasedMemory (srl/rl/memories/priority_memories/rankbased_memory.py:15-77) over device kernels
+    (csrc/rankbased.cu): same constructor arguments and IPriorityMemory methods (imemory.py:7-34), `sample` returns (batches,
+    float64 weights, numpy array of item indices) and the indices go back verbatim to `update`; `backup()` is the reference's
+    4-element list [capacity, buffer, priorities, pos].  Use through
+    `PriorityReplayBufferConfig.set_custom("simple_distributed_rl_b200.memory:DeviceRankBasedMemory", {...})`.
+
+    Where the reference runs np.argsort over all N priorities on the host at every sample, this sorts them with a radix sort on the
+    GPU, keeps the rank cdf (a function of N and alpha only) between calls, and replays numpy's choice(..., replace=False)
+    algorithm on a uniform stream -- Philox by default, or `uniforms=` to inject the stream a seeded np.random would produce
+    (parity tests).  Ties between equal priorities are ranked by ascending item index (numpy leaves their order unspecified).
+    Payloads stay in a host list, as in the reference."""
+
+    def __init__(self, capacity: int = 100_000, alpha: float = 0.6, beta_initial: float = 0.4, beta_steps: int = 1_000_000,
+                 device="cuda:0", seed: int = 0):
+        self.lib = _lib.load()
+        if not torch.cuda.is_available():
+            raise _lib.SrlxError("DeviceRankBasedMemory needs a CUDA device (no CPU fallback)")
+        self.capacity = int(capacity)
+        self.alpha, self.beta_initial, self.beta_steps = float(alpha), float(beta_initial), float(beta_steps)
+        self.device, self.seed = torch.device(device), int(seed)
+        nbytes = int(self.lib.srlx_rank_scratch_bytes(self.capacity))
+        if nbytes == 0:
+            raise ValueError("capacity outside [1, 2^27]")
+        self._scratch = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+        self._draws = 0
+        self.clear()
+
+    def _s(self):
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def clear(self) -> None:
+        self.buffer: List[Any] = []
+        self._pri = torch.zeros(self.capacity, dtype=torch.float32, device=self.device)
+        self.pos = 0
+        self._cdf_n = -1
+
+    def length(self) -> int:
+        return len(self.buffer)
+
+    def add(self, batch: Any, priority: Optional[float] = None) -> None:
+        if len(self.buffer) < self.capacity:
+            self.buffer.append(batch)
+        else:
+            self.buffer[self.pos] = batch
+        self._pri[self.pos] = float("nan") if priority is None else float(priority)  # numpy stores None as nan (:40)
+        self.pos = (self.pos + 1) % self.capacity
+
+    def sample(self, batch_size: int, step: int, uniforms: Optional[np.ndarray] = None):
+        beta = self.beta_initial + (1 - self.beta_initial) * step / self.beta_steps
+        beta = 1.0 if beta > 1 else float(beta)
+        n = len(self.buffer)
+        idx = torch.empty(batch_size, dtype=torch.int64, device=self.device)
+        w = torch.empty(batch_size, dtype=torch.float64, device=self.device)
+        u_ptr, n_u = None, 0
+        if uniforms is not None:
+            u = torch.as_tensor(np.ascontiguousarray(uniforms, dtype=np.float64)).to(self.device)
+            u_ptr, n_u = u.data_ptr(), int(u.numel())
+        self._draws += 1
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.srlx_rank_sample(self._pri.data_ptr(), self.capacity, n, self.alpha, beta, int(batch_size), u_ptr, n_u,
+                                                 self.seed & 0xFFFFFFFFFFFFFFFF, self._draws, int(self._cdf_n != n), self._scratch.data_ptr(),
+                                                 idx.data_ptr(), w.data_ptr(), None, None, self._s()))
+        self._cdf_n = n
+        sampled = idx.cpu().numpy()
+        return [self.buffer[i] for i in sampled], w.cpu().numpy(), sampled
+
+    def update(self, indices: List[Any], priorities: np.ndarray) -> None:
+        n = len(indices)
+        if n == 0:
+            return
+        idx = torch.as_tensor(np.asarray(indices, dtype=np.int64)).to(self.device)
+        val = torch.as_tensor(np.asarray(priorities, dtype=np.float32)).to(self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.srlx_rank_update(self._pri.data_ptr(), idx.data_ptr(), val.data_ptr(), n, self._s()))
+
+    def backup(self):
+        return [self.capacity, self.buffer[:], self._pri.cpu().numpy(), self.pos]
+
+    def restore(self, data) -> None:
+        self.buffer = list(data[1][:])
+        pri = np.zeros(self.capacity, dtype=np.float32)
+        src = np.asarray(data[2], dtype=np.float32)
+        pri[: min(len(src), self.capacity)] = src[: self.capacity]
+        self._pri.copy_(torch.as_tensor(pri))
+        self.pos = int(data[3])
+        self._cdf_n = -1
+
+    def argsort(self) -> np.ndarray:
+        """Item indices by descending priority (tests / tools)."""
+        n = len(self.buffer)
+        out = torch.empty(n, dtype=torch.int32, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.srlx_rank_argsort(self._pri.data_ptr(), self.capacity, n, self._scratch.data_ptr(), out.data_ptr(), self._s()))
+        return out.cpu().numpy().astype(np.int64)

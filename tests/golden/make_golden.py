@@ -410,6 +410,44 @@ def gen_worker_records():
     print("worker_records:", {k: v.shape for k, v in out.items() if k.endswith("_b_a") or k.endswith("_a")})
 
 
+def gen_rankbased():
+    """RankBasedMemory (srl/rl/memories/priority_memories/rankbased_memory.py) with np.random seeded: add / sample / update
+    sequences; the uniform stream np.random.choice consumes is RandomState(seed).random_sample, stored next to the outputs."""
+    from srl.rl.memories.priority_memories.rankbased_memory import RankBasedMemory
+
+    out = {}
+    cases = [(64, 0.6, 0.4, 100, 8), (1000, 1.0, 0.5, 50, 32), (300, 0.0, 0.4, 10, 16), (5000, 0.8, 0.4, 1000, 64)]
+    out["n_cases"] = len(cases)
+    for c, (cap, alpha, beta0, bsteps, B) in enumerate(cases):
+        rng = np.random.default_rng(100 + c)
+        m = RankBasedMemory(cap, alpha, beta0, bsteps)
+        n_add = cap if c != 2 else cap // 2 + 7  # one case samples from a partly filled memory
+        pri0 = (rng.random(n_add) ** 2 * 3).astype(np.float32)
+        for i in range(n_add):
+            m.add(("item", i), float(pri0[i]))
+        out[f"c{c}_cfg"] = np.array([cap, alpha, beta0, bsteps, B, n_add], dtype=np.float64)
+        out[f"c{c}_pri0"] = pri0
+        idxs, ws, us, upds, sorts = [], [], [], [], []
+        for step in range(6):
+            seed = 1000 * c + step
+            np.random.seed(seed)
+            us.append(np.random.RandomState(seed).random_sample(4 * B))
+            batches, w, idx = m.sample(B, step * 7)
+            assert [b[1] for b in batches] == list(idx)
+            sorts.append(np.argsort(-m.priorities[:n_add]))
+            idxs.append(np.asarray(idx, dtype=np.int64))
+            ws.append(np.asarray(w, dtype=np.float64))
+            td = np.abs(rng.normal(size=B)).astype(np.float32)
+            upds.append(td)
+            m.update(idx, td)
+        out[f"c{c}_idx"], out[f"c{c}_w"], out[f"c{c}_u"], out[f"c{c}_upd"] = np.array(idxs), np.array(ws), np.array(us), np.array(upds)
+        out[f"c{c}_pri_final"] = m.priorities.copy()
+        b = m.backup()
+        assert b[0] == cap and len(b) == 4 and b[3] == n_add % cap
+    np.savez_compressed(os.path.join(HERE, "rankbased.npz"), **out)
+    print("rankbased: ok")
+
+
 def gen_spaces():
     """BoxSpace.create_division_tbl (srl/base/spaces/box.py:317-366): the discrete action set value-based algorithms see on a
     continuous-action env (Pendulum-v1: Box(1,) in [-2, 2], RLConfig.action_division_num = 10 by default)."""
@@ -658,6 +696,8 @@ if __name__ == "__main__":
     only = set(sys.argv[1:])  # e.g. `make_golden.py worker` regenerates only worker_records.npz
     if not only or "spaces" in only:
         gen_spaces()
+    if not only or "rankbased" in only:
+        gen_rankbased()
     if not only or "ppo" in only:
         gen_ppo_returns()
     if not only or "r2d2" in only:

@@ -436,3 +436,40 @@ def test_r2d2_sequence_targets_equal_reference_trainer(name, golden_dir):
     # np.mean of the TD errors is numpy's pairwise sum / n: the restated summation order reproduces it exactly
     tds32 = np.random.default_rng(0).normal(size=80).astype(np.float32)
     assert o.np_pairwise_sum(tds32) == np.add.reduce(tds32) and o.np_pairwise_sum(tds32.astype(np.float64)) == np.add.reduce(tds32.astype(np.float64))
+
+
+# ---- rank-based replay: oracle/rankbased.py vs the reference's RankBasedMemory ------------------------------------
+def test_rankbased_oracle_matches_reference_golden(golden_dir):
+    """add / sample / update sequences of the reference class (np.random seeded) replayed on the stored uniform stream: sampled item
+    indices exact, float64 IS weights to 1e-12, priorities after the updates exact."""
+    from oracle import rankbased as orb
+
+    g = np.load(os.path.join(golden_dir, "rankbased.npz"))
+    for c in range(int(g["n_cases"])):
+        cap, alpha, beta0, bsteps, B, n_add = g[f"c{c}_cfg"]
+        cap, B, n_add = int(cap), int(B), int(n_add)
+        m = orb.RankBasedMemory(cap, alpha, beta0, bsteps)
+        for p in g[f"c{c}_pri0"]:
+            m.add(float(p))
+        for step in range(len(g[f"c{c}_idx"])):
+            idx, w, ranks, used = m.sample(B, step * 7, g[f"c{c}_u"][step])
+            np.testing.assert_array_equal(idx, g[f"c{c}_idx"][step])
+            np.testing.assert_allclose(w, g[f"c{c}_w"][step], rtol=1e-12)
+            assert len(set(idx.tolist())) == B and B <= used <= 4 * B
+            m.update(idx, g[f"c{c}_upd"][step])
+        np.testing.assert_array_equal(m.priorities, g[f"c{c}_pri_final"])
+
+
+def test_rankbased_choice_restatement_equals_numpy():
+    """oracle.rankbased.choice_without_replacement == np.random.choice(n, size, replace=False, p) for the same MT19937 stream, including
+    draws that need several rounds (few heavy ranks: the first round repeats indices)."""
+    from oracle import rankbased as orb
+
+    for seed, n, size, alpha in [(0, 50, 20, 2.0), (1, 400, 64, 1.5), (2, 33, 33, 0.3), (3, 1000, 10, 0.0)]:
+        p = (1.0 / np.arange(1, n + 1)) ** alpha
+        p /= p.sum()
+        np.random.seed(seed)
+        want = np.random.choice(n, size=size, replace=False, p=p)
+        got, used = orb.choice_without_replacement(p, size, np.random.RandomState(seed).random_sample(40 * size))
+        np.testing.assert_array_equal(got, want)
+        assert used >= size
