@@ -242,6 +242,19 @@ int srlx_tree_update(double* tree, uint64_t capacity, srlx_state* meta, const in
 int srlx_tree_retrieve(const double* tree, uint64_t capacity, const double* vals_dev, uint32_t n,
                        int64_t* out_tree_idx, uintptr_t cuda_stream);
 
+/* ---- large-batch Q-net inference on the tensor cores (csrc/qnet_tc.cu: tcgen05.mma + TMEM accumulators + TMA-staged operands) ------
+ * An explicit NON-parity mode of RLParameter.pred_q / pred_target_q (srl/algorithms/dqn/model_torch.py:58-70): bf16 operands, fp32
+ * accumulation; the fp32 seam (srlx_qnet_forward) stays the parity path.
+ * srlx_dense_bf16_tc: Y[M][N] = act(X[M][K] . W[N][K]^T + b); X / W bf16 with K contiguous (row strides ldx / ldw, multiples of 8),
+ * bias fp32 [N] or NULL, Y bf16 (out_f32 == 0) or fp32, relu != 0 applies max(., 0).
+ * srlx_qnet_forward_tc: the whole network (NoisyLinear draws and the dueling head included) for n states; workspace from
+ * srlx_qnet_tc_workspace_bytes. */
+int srlx_dense_bf16_tc(const void* x_dev, int ldx, const void* w_dev, int ldw, const float* bias_dev, void* y_dev, int ldy, int out_f32,
+                       int M, int N, int K, int relu, uintptr_t cuda_stream);
+size_t srlx_qnet_tc_workspace_bytes(const srlx_engine* eng, uint32_t n);
+int srlx_qnet_forward_tc(const srlx_engine* eng, int use_target, const float* obs_dev, uint32_t n, uint64_t noise_call_id, float* q_out_dev,
+                         void* workspace_dev, size_t workspace_bytes, uintptr_t cuda_stream);
+
 /* ---- rank-based prioritized replay (csrc/rankbased.cu) <- RankBasedMemory
  *      srl/rl/memories/priority_memories/rankbased_memory.py:15-77 behind the IPriorityMemory seam (imemory.py:7-34) --------------
  * priorities: float32 [capacity], item i's priority as the reference stores it (|td| as handed to update(); None -> NaN, sorted last).

@@ -117,6 +117,9 @@ SYMBOLS = [
     ("srlx_learner_info", C.c_int, [C.POINTER(SrlxEngine), C.POINTER(C.c_int), C.POINTER(C.c_size_t)]),
     ("srlx_tree_blk_bytes", _sz, [_u64]),
     ("srlx_qnet_forward", C.c_int, [C.POINTER(SrlxEngine), _i32, _P, _u32, _u64, _P, _uptr]),
+    ("srlx_dense_bf16_tc", C.c_int, [_P, _i32, _P, _i32, _P, _P, _i32, _i32, _i32, _i32, _i32, _i32, _uptr]),
+    ("srlx_qnet_tc_workspace_bytes", _sz, [C.POINTER(SrlxEngine), _u32]),
+    ("srlx_qnet_forward_tc", C.c_int, [C.POINTER(SrlxEngine), _i32, _P, _u32, _u64, _P, _P, _sz, _uptr]),
     ("srlx_rank_scratch_bytes", _sz, [_u64]),
     ("srlx_rank_sample", C.c_int, [_P, _u64, _u32, _dbl, _dbl, _u32, _P, _u32, _u64, _u64, _i32, _P, _P, _P, _P, _P, _uptr]),
     ("srlx_rank_update", C.c_int, [_P, _P, _P, _u32, _uptr]),

@@ -243,6 +243,23 @@ class DeviceEngine:
             _lib.check(self.lib.srlx_qnet_forward(C.byref(self.c), int(target), x.data_ptr(), x.shape[0], int(noise_call_id), q.data_ptr(), self._stream()))
         return q.cpu().numpy()
 
+    def pred_q_tc(self, obs, target=False, noise_call_id=0) -> torch.Tensor:
+        """pred_q / pred_target_q for LARGE batches on the tensor cores (csrc/qnet_tc.cu: tcgen05.mma, TMEM accumulators, TMA-staged
+        bf16 operands, fp32 accumulation).  An explicit non-parity mode: results agree with `pred_q` to bf16 resolution (~1e-2
+        relative), not to the 1e-4 of the fp32 path.  obs: [n, D] numpy array or CUDA tensor; returns a CUDA tensor [n, A]."""
+        x = obs if isinstance(obs, torch.Tensor) else torch.as_tensor(np.ascontiguousarray(obs, dtype=np.float32))
+        x = x.to(self.device, dtype=torch.float32).reshape(-1, self.D).contiguous()
+        n = x.shape[0]
+        q = torch.empty((n, self.A), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            need = int(self.lib.srlx_qnet_tc_workspace_bytes(C.byref(self.c), n))
+            ws = getattr(self, "_tc_ws", None)
+            if ws is None or ws.numel() < need:
+                ws = self._tc_ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+            _lib.check(self.lib.srlx_qnet_forward_tc(C.byref(self.c), int(target), x.data_ptr(), n, int(noise_call_id), q.data_ptr(),
+                                                     ws.data_ptr(), ws.numel(), self._stream()))
+        return q
+
     def noise(self, kind: int, call_id: int) -> np.ndarray:
         out = torch.empty(self.spec.n_params, dtype=torch.float32, device=self.device)
         with torch.cuda.device(self.device):
