@@ -403,6 +403,36 @@ def own_arm(args):
                    "checks and callbacks; L2 flushed once per bench step; envs are generated on device by design, so there is no "
                    "bulk host input on this path"}
 
+    # ---- the opt-in PRE-SAMPLED mode (EngineConfig.presample): batch t+1 is drawn before update t's priorities reach the tree, the
+    #      staleness the reference's own memory process has in distributed mode; the SumTree chain leaves the critical path ----------
+    presampled = None
+    if world == 1 and kw["mem_kind"] == 1 and eng.learner_info()[0] == "learner_fast_kernel" and not args.no_presample:
+        eng.c.presample = 1
+        for _ in range(2):
+            for _ in range(S):
+                eng.vec_step()
+                eng.learn(U)
+        barrier()
+        p0 = eng.read_state()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        Kp = max(2, K // 2)
+        flush.zero_()
+        a.record()
+        for _ in range(Kp):
+            for _ in range(S):
+                eng.vec_step()
+                eng.learn(U)
+        b.record()
+        barrier()
+        p1 = eng.read_state()
+        pms = a.elapsed_time(b)
+        pn = float(p1.train_count - p0.train_count)
+        presampled = {"env_steps_per_sec": Kp * S * E / (pms * 1e-3), "trainer_updates_per_sec": pn / (pms * 1e-3),
+                      "us_per_update_whole_pass": 1e3 * pms / pn, "steps": Kp,
+                      "what": "EngineConfig.presample = True: inside a launch batch t+1 is sampled before update t is applied (one update "
+                              "of staleness, srl/base/run/play_mp_memory.py:253-350); NOT the headline: `value` is the sequential order"}
+        eng.c.presample = 0
+
     # ---- N > 1: the SINGLE-LEARNER mode measured next to the replicas: every update is one Trainer.train() on the global
     #      batch (world x 32 items), gradients summed over NVLink inside the learner kernel, identical Adam on every rank ----------
     single = None
@@ -514,7 +544,7 @@ def own_arm(args):
             "data": "synthetic", "config": workload_config(args, world),
             "trainer_updates_per_sec": upd_rate, "wall_ms_per_step": 1e3 * t_wall / K,
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clk, "roofline": roofline,
-            "roofline_rollout": roofline_rollout, "cpu_baseline": cpu, "single_learner": single,
+            "roofline_rollout": roofline_rollout, "cpu_baseline": cpu, "single_learner": single, "presampled": presampled,
             "final_loss": float(st1.last_loss), "episodes": int(st1.episode_count),
             "mean_episode_len": float(st1.episode_len_sum) / max(1, st1.episode_count)}
     print(json.dumps(line), flush=True)
@@ -543,6 +573,7 @@ def main():
     ap.add_argument("--cpu-envs", type=int, default=64, help="env copies in the bounded sample of the oracle port (fallback CPU arm)")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-presample", action="store_true", help="skip the extra measurement of the opt-in pre-sampled mode")
     ap.add_argument("--force-port", action="store_true", help="CPU arms: use the oracle port even when baseline/_ref is present")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -113,7 +113,10 @@ typedef struct srlx_engine {
   int32_t target_update_interval;
   int32_t trunc_limit;     /* episode is truncated when step_num reaches this (CartPole 500; Grid 51 = max_episode_steps+1) */
   int32_t trunc_overrides_term; /* gymnasium TimeLimit semantics: truncated wins over terminated */
-  int32_t reserved_i;
+  int32_t presample;       /* 0: every batch is sampled after the previous update's priorities are in the tree (Trainer.train in sequence);
+                              1: batch t+1 is drawn BEFORE update t is applied (one update of staleness, as the reference's own memory
+                              process does in distributed mode, srl/base/run/play_mp_memory.py:253-350): the SumTree chain leaves the
+                              critical path (csrc/learner_fast.cu only) */
   uint64_t seed;
   uint64_t warmup_size;
   /* ---- hyper-parameters ---- */

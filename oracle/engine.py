@@ -42,6 +42,7 @@ class EngineConfig:
     enable_rescale: bool = False
     enable_reward_clip: bool = False
     has_duplicate: bool = True
+    presample: bool = False  # batch t+1 is drawn before update t lands (one launch = up to 256 updates), see learn()
     target_update_interval: int = 1000
     seed: int = 0
     warmup_size: int = 16
@@ -300,50 +301,63 @@ class OracleEngine:
         return g_lo, max(0, n_g)
 
     # ---- trainer updates ---------------------------------------------------------------------------------
-    def learn(self, n_updates=1):
+    def _sample(self, tc):
+        """(idx, slots, weights) of the batch of update `tc`, drawn from the memory as it is NOW."""
+        cfg, B = self.cfg, self.cfg.batch_size
+        if cfg.mem_kind == MEM_PROPORTIONAL:
+            beta_step = max(tc - 1, 0)  # PriorityReplayBuffer.step is the PREVIOUS update's train_count
+            idx, w, pri, retries = self.per.sample(B, beta_step, sumtree.philox_uniforms(cfg.seed, tc))
+            self.sample_retries += retries
+            return idx, idx - (self.cap - 1), w.astype(np.float32)
+        g_lo, n_g = self._valid_range()
+        pick = sumtree.uniform_sample_distinct(n_g * self.E, B, cfg.seed, tc)
+        slots = ((g_lo + pick // self.E) % self.R) * self.E + pick % self.E
+        return slots.copy(), slots, np.ones(B, dtype=np.float32)
+
+    def learn(self, n_updates=1, launch_updates=256):
+        """n_updates x Trainer.train().  presample=False: every batch is drawn after the previous update's priorities are in the
+        tree (the reference's sequential loop).  presample=True: inside one launch (<= launch_updates updates, the device's chunk)
+        batch t+1 is drawn BEFORE update t is applied -- one update of staleness, the order the reference's memory process
+        produces in distributed mode (srl/base/run/play_mp_memory.py:253-350); the first batch of a launch is drawn fresh."""
         cfg = self.cfg
         out = []
-        for _ in range(n_updates):
-            if self.mem_size < cfg.warmup_size:
-                continue
-            tc = self.train_count
-            B = cfg.batch_size
-            if cfg.mem_kind == MEM_PROPORTIONAL:
-                beta_step = max(tc - 1, 0)  # PriorityReplayBuffer.step is the PREVIOUS update's train_count
-                idx, w, pri, retries = self.per.sample(B, beta_step, sumtree.philox_uniforms(cfg.seed, tc))
-                self.sample_retries += retries
-                slots = idx - (self.cap - 1)
-                weights = w.astype(np.float32)
-            else:
-                g_lo, n_g = self._valid_range()
-                pick = sumtree.uniform_sample_distinct(n_g * self.E, B, cfg.seed, tc)
-                slots = ((g_lo + pick // self.E) % self.R) * self.E + pick % self.E
-                idx = slots.copy()
-                weights = np.ones(B, dtype=np.float32)
-            wins = [self.window(s) for s in slots]
-            states = np.stack([w_[0] for w_ in wins])
-            acts = np.stack([w_[1] for w_ in wins])
-            rews = np.stack([w_[2] for w_ in wins])
-            terms = np.stack([w_[3] for w_ in wins])
-            noise = (None, None, None)
-            if cfg.noisy:
-                noise = tuple(self.noise_fn(nets.NOISE_KIND_TRAIN, tc * 3 + p) for p in range(3))
-            res = nets.train_update(
-                self.spec, self.adam, self.tgt_mu, self.tgt_sigma, algo=cfg.algo, states=states, actions=acts,
-                rewards=rews, dones=terms, weights=weights, discount=cfg.discount, multisteps=self.M,
-                retrace_h=cfg.retrace_h, enable_double_dqn=cfg.enable_double_dqn, enable_rescale=cfg.enable_rescale,
-                noise=noise, sigma_mask=self.sigma_mask, huber_delta=cfg.huber_delta)
-            if cfg.mem_kind == MEM_PROPORTIONAL:
-                self.per.update(idx, res["priorities"])
-            if tc % cfg.target_update_interval == 0:
-                self.tgt_mu = self.mu.copy()
-                if self.tgt_sigma is not None:
-                    self.tgt_sigma = self.sigma.copy()
-                self.sync_count += 1
-            self.train_count += 1
-            self.last_loss = res["loss"]
-            res.update(idx=idx, slots=slots, weights=weights, states=states, actions=acts, rewards=rews, terms=terms)
-            out.append(res)
+        done = 0
+        while done < n_updates:
+            k = min(launch_updates, n_updates - done) if cfg.presample else n_updates - done
+            pending = None
+            for j in range(k):
+                if self.mem_size < cfg.warmup_size:
+                    continue
+                tc = self.train_count
+                idx, slots, weights = pending if pending is not None else self._sample(tc)
+                pending = None
+                wins = [self.window(s) for s in slots]
+                states = np.stack([w_[0] for w_ in wins])
+                acts = np.stack([w_[1] for w_ in wins])
+                rews = np.stack([w_[2] for w_ in wins])
+                terms = np.stack([w_[3] for w_ in wins])
+                noise = (None, None, None)
+                if cfg.noisy:
+                    noise = tuple(self.noise_fn(nets.NOISE_KIND_TRAIN, tc * 3 + p) for p in range(3))
+                res = nets.train_update(
+                    self.spec, self.adam, self.tgt_mu, self.tgt_sigma, algo=cfg.algo, states=states, actions=acts,
+                    rewards=rews, dones=terms, weights=weights, discount=cfg.discount, multisteps=self.M,
+                    retrace_h=cfg.retrace_h, enable_double_dqn=cfg.enable_double_dqn, enable_rescale=cfg.enable_rescale,
+                    noise=noise, sigma_mask=self.sigma_mask, huber_delta=cfg.huber_delta)
+                if cfg.presample and j + 1 < k:
+                    pending = self._sample(tc + 1)  # before this update's priorities reach the tree
+                if cfg.mem_kind == MEM_PROPORTIONAL:
+                    self.per.update(idx, res["priorities"])
+                if tc % cfg.target_update_interval == 0:
+                    self.tgt_mu = self.mu.copy()
+                    if self.tgt_sigma is not None:
+                        self.tgt_sigma = self.sigma.copy()
+                    self.sync_count += 1
+                self.train_count += 1
+                self.last_loss = res["loss"]
+                res.update(idx=idx, slots=slots, weights=weights, states=states, actions=acts, rewards=rews, terms=terms)
+                out.append(res)
+            done += k
         return out
 
     def run(self, n_steps, updates_per_step, training=True):

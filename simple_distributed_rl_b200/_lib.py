@@ -58,7 +58,7 @@ class SrlxEngine(C.Structure):
         ("ring_rows", C.c_int32), ("multisteps", C.c_int32), ("batch_size", C.c_int32), ("mem_kind", C.c_int32),
         ("enable_double_dqn", C.c_int32), ("enable_rescale", C.c_int32), ("enable_reward_clip", C.c_int32),
         ("has_duplicate", C.c_int32), ("target_update_interval", C.c_int32), ("trunc_limit", C.c_int32),
-        ("trunc_overrides_term", C.c_int32), ("reserved_i", C.c_int32),
+        ("trunc_overrides_term", C.c_int32), ("presample", C.c_int32),
         ("seed", C.c_uint64), ("warmup_size", C.c_uint64),
         ("epsilon", C.c_double), ("discount", C.c_double), ("lr", C.c_double),
         ("adam_beta1", C.c_double), ("adam_beta2", C.c_double), ("adam_eps", C.c_double),

@@ -140,7 +140,7 @@ __host__ __device__ inline FPlan make_fplan(const srlx_engine& eng, int C, long 
   p.off_samp_slot = take((size_t)2 * p.B4 * 4);
   p.off_samp_w = take((size_t)2 * p.B4 * 4);
   p.off_sdbl = take(2048);  // s_idx, s_att, sperm[4][32] (int), then s_pri, s_tmp (double)
-  p.off_plan = take(eng.mem_kind == SRLX_MEM_PROPORTIONAL ? (size_t)FNM * (5 * 8 + 2 * 9 * 4 + 5 * 4) : 0);  // old[5], node[9], end[9], blocked address[5]
+  p.off_plan = take(eng.mem_kind == SRLX_MEM_PROPORTIONAL ? (size_t)FNM * (5 * 8 + 2 * 9 * 4 + 5 * 4 + 4 + 8) : 0);  // old[5], node[9], end[9], blocked address[5], pad, old leaf
   p.n_cache = 0;
   if (eng.mem_kind == SRLX_MEM_PROPORTIONAL) {
     p.off_sub = take((size_t)kFMemWarps * 8 * kFSubLd * 8);
@@ -427,11 +427,13 @@ learner_fast_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_up
   double* s_tmp = s_pri + 32;
   double* s_wval = s_tmp + 32;                              // hand-over of the top-level walk: remaining value,
   int* s_widx = reinterpret_cast<int*>(s_wval + 32);        // node reached
+  double* s_tot = reinterpret_cast<double*>(s_widx + 32);   // tree total the current batch was sampled under
   double* sub = reinterpret_cast<double*>(smem + pl.off_sub);
   double* plan_old = reinterpret_cast<double*>(smem + pl.off_plan);
   int* plan_node = reinterpret_cast<int*>(smem + pl.off_plan + (size_t)FNM * 5 * 8);
   int* plan_end = plan_node + 9 * FNM;
   int* plan_baddr = plan_end + 9 * FNM;
+  double* plan_oldleaf = reinterpret_cast<double*>(plan_baddr + 6 * FNM);  // [FNM] the leaf's value before the update
   double* cache = reinterpret_cast<double*>(smem + pl.off_cache);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -444,6 +446,7 @@ learner_fast_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_up
   const int n_cache = pl.n_cache;
   const int u0 = rank * Us;
   const bool per = eng.mem_kind == SRLX_MEM_PROPORTIONAL;
+  const bool presample = eng.presample != 0;
   const bool noisy = net.noisy != 0;
   const bool need_online_next = FLAG ? true : (eng.enable_double_dqn || M > 1);
   // data-parallel learner (dp_world ranks, one engine each): gradients summed over the ranks every update
@@ -574,8 +577,31 @@ learner_fast_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_up
             // the peers' from this rank's mailboxes as they land
             const int tpar = (int)(tc_done & 1);
             const uint32_t tag = (uint32_t)(tc_done + 1);
-            for (int r = 0; r < G; ++r)
-              g += (r == dp_rank) ? part[i] : __uint_as_float(dp_load(dp_grad(dp_own, tpar, r, rank, PlPad) + i, tag, dp_dead));
+            // all peers' words polled together (one L2 round trip per attempt whatever the number of ranks)
+            float gv[kDpMaxWorld];
+            unsigned pend = ((1u << G) - 1u) & ~(1u << dp_rank);
+            long long t0 = 0;
+            for (int it = 0; pend; ++it) {
+              unsigned long long w[kDpMaxWorld];
+#pragma unroll
+              for (int r = 0; r < kDpMaxWorld; ++r) {
+                w[r] = 0;
+                if ((pend >> r) & 1u)
+                  asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(w[r]) : "l"(dp_grad(dp_own, tpar, r, rank, PlPad) + i) : "memory");
+              }
+#pragma unroll
+              for (int r = 0; r < kDpMaxWorld; ++r)
+                if (((pend >> r) & 1u) && (uint32_t)(w[r] >> 32) == tag) { gv[r] = __uint_as_float((uint32_t)w[r]); pend &= ~(1u << r); }
+              if (pend) {
+                if (*dp_dead) break;
+                __nanosleep(100);
+                if (it == 256) t0 = clock64();
+                if (it > 256 && clock64() - t0 > 2000000000ll) { *dp_dead = 1; break; }
+              }
+            }
+#pragma unroll
+            for (int r = 0; r < kDpMaxWorld; ++r)
+              if (r < G) g += (r == dp_rank) ? part[i] : ((pend >> r) & 1u ? 0.f : gv[r]);
             g *= 1.0f / (float)G;
           }
           float m = p_m1[i], v = p_v1[i];
@@ -993,6 +1019,7 @@ learner_fast_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_up
       int* p_end = plan_end + mt;     // [kLv][FNM] last lane of the leader's run
       int* p_baddr = plan_baddr + mt; // [kLu][FNM] where the uncached node lives in the blocked copy
       double* p_old = plan_old + mt;  // [kLu][FNM] old values of the uncached nodes, fetched while the forward pass runs
+      double* p_oldleaf = plan_oldleaf + mt;
       auto level_of = [&](int q) -> int { return q < kLc ? (mw - 1) + 3 * q : clev + (mw - 1) + 3 * (q - kLc); };
       auto level_ok = [&](int q, int a) -> bool { return q < kLc ? (a < clev && a < dmax) : (a < dmax); };
 
@@ -1024,6 +1051,7 @@ learner_fast_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_up
       auto sample_slots = [&](uint64_t tc, int pb, bool stamp) {
         if (per) {
           const double total = cache[0];
+          if (mt == 0) *s_tot = total;  // the IS weights of this batch use the total it was drawn under
           // (a) the cached top levels were walked by warp 0 for all B samples (walk_top) while warps 1..3 finished the
           //     deep levels of the update; each owner lane picks its sample's state up from shared memory
           int idx = 0;
@@ -1249,7 +1277,7 @@ learner_fast_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_up
       auto send_weights = [&](uint64_t tc, int pb) {
         double wv = 1.0;
         if (per) {
-          const double total = cache[0];  // the tree has not changed since the sample
+          const double total = *s_tot;  // the total the batch was drawn under (== cache[0] unless the batch was pre-sampled)
           // PriorityReplayBuffer.step is the train_count of the PREVIOUS update() call (priority_replay_buffer.py:232,250)
           const double stepd = (tc > 0) ? (double)(tc - 1) : 0.0;
           double beta = eng.per_beta_initial + (1.0 - eng.per_beta_initial) * stepd / eng.per_beta_steps;
@@ -1342,6 +1370,8 @@ learner_fast_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_up
         __syncwarp();
         s_valid = s_item < B;
         s_li = s_valid ? s_idx[s_item] : 0x7ffffffe;
+        // pre-sampled batches were drawn before the previous update: their leaves may have changed since, read them now
+        *p_oldleaf = s_valid ? (presample ? __ldcg(eng.tree + s_li) : s_pri[s_item]) : 0.0;
         const unsigned sip1 = (unsigned)s_li + 1u;
         const int sd = 31 - __clz(sip1);
 #pragma unroll 1
@@ -1394,7 +1424,7 @@ learner_fast_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_up
         const int prevli = __shfl_up_sync(FULL, s_li, 1), nextli = __shfl_down_sync(FULL, s_li, 1);
         const double prevp = __shfl_up_sync(FULL, pnew, 1);
         const bool dupprev = lane > 0 && prevli == s_li;  // duplicates of a leaf are consecutive, in batch order
-        const double chg = s_valid ? pnew - (dupprev ? prevp : s_pri[s_item]) : 0.0;
+        const double chg = s_valid ? pnew - (dupprev ? prevp : *p_oldleaf) : 0.0;
         if (mw == 1) {
           if (s_valid && (lane == 31 || nextli != s_li)) {  // the last item touching a leaf wins
             __stcg(eng.tree + s_li, pnew);
@@ -1578,6 +1608,14 @@ learner_fast_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_up
           if (per && mw == 0 && lane < B && upd + 1 < n_updates) u_next = draw(tc + 1, lane, 0);
           SRLX_FSTAMP(mt == 0, 26);
           SRLX_FSTAMP(mt == 32, 27);
+          if (presample && upd + 1 < n_updates) {
+            // pre-sampled mode: batch t+1 is drawn NOW, from the tree as updates <= t-1 left it; update t lands afterwards
+            if (per) {
+              if (mw == 0) walk_top(u_next);
+              named_bar_sync(FBAR_MEM, FNM);
+            }
+            sample_slots(tc + 1, parb ^ 1, upd + 2 == n_updates);
+          }
         }
         if (mw == 0) {
           if (rank == 0) {
@@ -1609,14 +1647,14 @@ learner_fast_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_up
               }
               named_bar_sync(FBAR_MB, FNM);  // cached levels of the tree are updated
               SRLX_FSTAMP(mt == 0, 28);
-              if (upd + 1 < n_updates) walk_top(u_next);
+              if (upd + 1 < n_updates && !presample) walk_top(u_next);
             }
             named_bar_sync(FBAR_MEM, FNM);  // deep levels written + top-level walk handed over
           } else {
             named_bar_sync(FBAR_MEM, FNM);
           }
           SRLX_FSTAMP(mt == 0, 20);
-          if (upd + 1 < n_updates) sample_slots(tc + 1, parb ^ 1, upd + 2 == n_updates);
+          if (upd + 1 < n_updates && !presample) sample_slots(tc + 1, parb ^ 1, upd + 2 == n_updates);
           SRLX_FSTAMP(mt == 0, 21);
         }
       }
@@ -1895,6 +1933,7 @@ extern "C" int srlx_learn(const srlx_engine* eng, uint32_t n_updates, uintptr_t 
   if (rc < 0) return rc;
   if (rc == 1) return learn_fast(eng, n_updates, cuda_stream, C, lev);
   SRLX_REQUIRE(eng->dp_world <= 1, "the data-parallel learner (dp_world = %d) exists for the single-hidden-layer cluster kernel only", eng->dp_world);
+  SRLX_REQUIRE(!eng->presample, "the pre-sampled mode exists for the single-hidden-layer cluster kernel only");
   if (small_pick(eng, &smem_bytes, &C) == 2) return learn_small(eng, n_updates, cuda_stream);
   return learn_generic(eng, n_updates, cuda_stream);
 }

@@ -38,6 +38,7 @@ class EngineConfig:
     enable_rescale: bool = False
     enable_reward_clip: bool = False
     has_duplicate: bool = True
+    presample: bool = False  # batch t+1 drawn before update t lands (include/srlx.h srlx_engine.presample)
     target_update_interval: int = 1000
     seed: int = 0
     warmup_size: int = 1000
@@ -137,6 +138,7 @@ class DeviceEngine:
         c.n_envs, c.ring_rows, c.multisteps, c.batch_size, c.mem_kind = self.E, self.R, self.M, self.B, cfg.mem_kind
         c.enable_double_dqn, c.enable_rescale, c.enable_reward_clip = int(cfg.enable_double_dqn), int(cfg.enable_rescale), int(cfg.enable_reward_clip)
         c.has_duplicate, c.target_update_interval = int(cfg.has_duplicate), int(cfg.target_update_interval)
+        c.presample = int(bool(getattr(cfg, 'presample', False)))
         c.seed, c.warmup_size = int(cfg.seed) & 0xFFFFFFFFFFFFFFFF, int(cfg.warmup_size)
         for k in ("epsilon", "discount", "lr", "adam_beta1", "adam_beta2", "adam_eps", "retrace_h", "per_alpha", "per_beta_initial",
                   "per_beta_steps", "per_epsilon", "reward_shift", "reward_scale", "huber_delta"):

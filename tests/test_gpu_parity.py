@@ -721,6 +721,70 @@ def test_unresynced_drift_over_20_updates():
         assert math.isclose(res[name]["loss_dev"], res[name]["loss_orc"], rel_tol=1e-4, abs_tol=1e-6), res[name]
 
 
+@pytest.mark.parametrize("name", ["cartpole_rainbow_default", "cartpole_rainbow_noisy_plain_m2_b24", "pendulum_rainbow_a3_fast",
+                                  "cartpole_dqn_uniform_h64", "cartpole_rainbow_naive_m4"])
+def test_presampled_mode_equals_oracle_in_that_order(name):
+    """EngineConfig.presample: inside a launch batch t+1 is drawn BEFORE update t's priorities reach the tree (the order the
+    reference's own memory process produces in distributed mode, play_mp_memory.py:253-350).  The oracle samples in the same
+    order (oracle/engine.py::learn); k updates in ONE launch are compared with the oracle's k updates from the same start:
+    the last batch's leaves (exact), its IS weights, the windows, target / loss, the parameters and the whole tree."""
+    from simple_distributed_rl_b200.engine import DeviceEngine, EngineConfig
+
+    for k in (1, 2, 3, 6, 11):
+        kw = dict(ENGINE_CASES[name], seed=3, target_update_interval=4, presample=True)
+        dev = DeviceEngine(EngineConfig(**kw), debug=True)
+        dev.run(kw["ring_rows"] + 2, 0)
+        orc = _oracle_from_device(dev, kw)
+        dev.learn(k)
+        outs = orc.learn(k)
+        st = dev.read_state()
+        assert len(outs) == k and st.train_count == k == orc.train_count
+        o = outs[-1]
+        cfg, B, M, D = orc.cfg, orc.cfg.batch_size, orc.cfg.multisteps, orc.D
+        np.testing.assert_array_equal(dev.t["dbg_sample_idx"].cpu().numpy(), o["idx"])
+        np.testing.assert_allclose(dev.t["dbg_weights"].cpu().numpy(), o["weights"], rtol=1e-6)
+        win = dev.t["dbg_windows"].cpu().numpy()
+        np.testing.assert_array_equal(win[:B * (M + 1) * D].reshape(B, M + 1, D), o["states"])
+        np.testing.assert_allclose(dev.t["dbg_target_q"].cpu().numpy(), o["target_q"], rtol=1e-4, atol=1e-5)
+        assert math.isclose(st.last_loss, o["loss"], rel_tol=1e-4, abs_tol=1e-6)
+        mu_d, sg_d = dev.get_params()
+        np.testing.assert_allclose(mu_d, orc.mu, rtol=1e-4, atol=2e-5)
+        if dev.per:
+            np.testing.assert_allclose(dev.t["tree"].cpu().numpy(), orc.per.tree.tree, rtol=1e-3, atol=1e-5)
+            assert math.isclose(st.max_priority, orc.per.max_priority, rel_tol=1e-3)
+    # and it is a different order from the sequential one whenever consecutive batches share a leaf or the total moves a walk
+    if dev.per:
+        kw2 = dict(ENGINE_CASES[name], seed=3, target_update_interval=4)
+        seq = DeviceEngine(EngineConfig(**kw2), debug=True)
+        seq.run(kw2["ring_rows"] + 2, 0)
+        seq.learn(11)
+        assert seq.read_state().train_count == 11
+        assert not torch.equal(seq.t["tree"], dev.t["tree"])
+
+
+def test_presampled_mode_full_size_properties_and_learning():
+    """BASELINE configs[2] sizes in the pre-sampled mode: the SumTree stays a sum tree through launches of 256 pre-sampled
+    updates (every leaf's change is taken against its CURRENT value, not the one seen at sampling time), and the mode learns
+    CartPole as the sequential one does."""
+    from simple_distributed_rl_b200.engine import DeviceEngine, EngineConfig
+    from simple_distributed_rl_b200.runner import VecRunner
+
+    kw = dict(FULL_SIZE["rainbow_8192x256_per"], presample=True)
+    dev = DeviceEngine(EngineConfig(**kw))
+    dev.run(kw["ring_rows"] + 3, 0)
+    dev.learn(700)
+    assert dev.read_state().train_count == 700
+    tree = dev.t["tree"].cpu().numpy()
+    cap = dev.cap
+    np.testing.assert_allclose(tree[: cap - 1], tree[1::2][: cap - 1] + tree[2::2][: cap - 1], rtol=1e-9, atol=1e-9)
+    np.testing.assert_allclose(tree[0], tree[cap - 1:].sum(), rtol=1e-9)
+    kw = dict(env="CartPole-v1", algo="rainbow", hidden=(512,), dueling="average", noisy=True, mem_kind=1, multisteps=3, n_envs=1024,
+              ring_rows=256, batch_size=32, warmup_size=1000, lr=1e-3, target_update_interval=1000, seed=1, presample=True)
+    r = VecRunner(EngineConfig(**kw))
+    r.train(max_steps=1024 * 400, train_interval=4, steps_per_call=16)
+    assert float(np.mean(r.evaluate(max_episodes=100, test_epsilon=0.0))) >= 150.0
+
+
 @pytest.mark.parametrize("path", learner_cases.PATHS, ids=learner_cases.IDS)
 def test_device_learner_equals_reference_trainer_on_frozen_memory(path):
     """The device learner against the REFERENCE ITSELF, no oracle in between: tests/golden/learner_*.npz hold what the reference's
