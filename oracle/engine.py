@@ -182,6 +182,28 @@ class OracleEngine:
             tree[pa : pb + 1] += pc
             a, b, change = pa, pb, pc
 
+    def _tree_set_const(self, leaf_lo, n, value):
+        """leaves [leaf_lo, leaf_lo+n) <- value.  When n is a power of two (>= 2) and the range is a ring row, those leaves are the
+        leaves of ONE complete subtree rooted at node leaf_lo / n + cap / n - 1: every node below that root is exactly value * (leaves
+        under it); the root takes value * n and its ancestors the root's change (device twin: csrc/rollout.cu::post_step_pow2_kernel).
+        Otherwise: the level-by-level bulk set."""
+        pow2 = n >= 2 and (n & (n - 1)) == 0 and leaf_lo % n == 0 and self.cap % n == 0 and self.cap // n >= 2
+        if not pow2:
+            return self._tree_set_range(leaf_lo, np.full(n, value, dtype=np.float64))
+        tree = self.per.tree.tree
+        root = leaf_lo // n + self.cap // n - 1
+        logn = n.bit_length() - 1
+        for k in range(1, logn + 1):
+            first = ((root + 1) << k) - 1
+            tree[first:first + (1 << k)] = value * float(1 << (logn - k))
+        nv = value * float(n)
+        delta = nv - tree[root]
+        tree[root] = nv
+        p = root
+        while p > 0:
+            p = (p - 1) // 2
+            tree[p] = tree[p] + delta
+
     # ---- one vector step ---------------------------------------------------------------------------------
     def epsilon_at(self, step):
         """Linear.update(step).to_float() (srl/rl/schedulers/schedulers/linear.py:11-21); phase 0 = Constant (constant.py)."""
@@ -252,11 +274,11 @@ class OracleEngine:
             M, R = self.M, self.R
             if cfg.mem_kind == MEM_PROPORTIONAL:
                 if M == 1:
-                    self._tree_set_range(row * E, np.full(E, self.per.max_priority))
+                    self._tree_set_const(row * E, E, self.per.max_priority)
                 else:
-                    self._tree_set_range(row * E, np.zeros(E))
+                    self._tree_set_const(row * E, E, 0.0)
                     if g >= M - 1:
-                        self._tree_set_range(((g - M + 1) % R) * E, np.full(E, self.per.max_priority))
+                        self._tree_set_const(((g - M + 1) % R) * E, E, self.per.max_priority)
             rows_added = max(0, g + 1 - (M - 1))
             self.mem_size = E * min(rows_added, R - (M - 1))
             self.per.size = self.mem_size

@@ -184,6 +184,58 @@ __device__ inline void tree_set_row(double* __restrict__ tree, int64_t cap, int6
   }
 }
 
+// ---- replay add of a whole row when E is a power of two (every BASELINE configuration): the E leaves of ring row `row` are the
+// leaves of ONE complete subtree, rooted at node row + R - 1 whatever R is (heap layout: the descendants of node r at relative depth k
+// are [(r + 1) 2^k - 1, (r + 1) 2^k - 1 + 2^k)).  Setting them all to the same value v therefore needs no read-modify-write below that
+// root: the node h levels above the leaves is exactly v * 2^h.  All CTAs fill the 2E - 2 nodes below the root with plain stores; one
+// thread rewrites the root (new = v * E) and adds new - old to its <= log2(2R) ancestors.  57 us (one CTA, a block barrier and an L2
+// round trip per level, twice for n-step windows) -> a few us.  CPU twin: oracle/engine.py::_tree_set_const.
+__device__ __forceinline__ void subtree_fill(double* __restrict__ tree, int64_t root, int logE, double v, int64_t t0, int64_t stride) {
+  // nodes at relative depth k = 1 .. logE below `root`, 2^k each: global thread index walks the 2E - 2 of them
+  const int64_t total = ((int64_t)2 << logE) - 2;
+  for (int64_t i = t0; i < total; i += stride) {
+    const int k = 63 - __clzll(i + 2);              // i + 2 in [2^k, 2^(k+1))
+    const int64_t j = i + 2 - ((int64_t)1 << k);
+    __stcg(tree + ((root + 1) << k) - 1 + j, v * (double)((int64_t)1 << (logE - k)));
+  }
+}
+__device__ inline void subtree_root_and_path(double* __restrict__ tree, int64_t root, int logE, double v) {
+  const double nv = v * (double)((int64_t)1 << logE);
+  const double delta = nv - __ldcg(tree + root);
+  __stcg(tree + root, nv);
+  int64_t p = root;
+  while (p > 0) {
+    p = (p - 1) / 2;
+    __stcg(tree + p, __ldcg(tree + p) + delta);
+  }
+}
+__global__ void __launch_bounds__(1024)
+post_step_pow2_kernel(const __grid_constant__ srlx_engine eng, const int logE) {
+  srlx_state* st = eng.state;
+  const uint64_t g = st->vec_steps;
+  const int E = eng.n_envs, R = eng.ring_rows, M = eng.multisteps;
+  const int row = (int)(g % (uint64_t)R);
+  const int64_t t0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (int64_t)gridDim.x * blockDim.x;
+  const double maxp = st->max_priority;
+  const bool add_row = M == 1 || g >= (uint64_t)(M - 1);
+  const int arow = M == 1 ? row : (int)((g - (uint64_t)(M - 1)) % (uint64_t)R);
+  if (eng.mem_kind == SRLX_MEM_PROPORTIONAL) {
+    if (M > 1) subtree_fill(eng.tree, (int64_t)row + R - 1, logE, 0.0, t0, stride);   // the row being overwritten leaves the sampleable set
+    if (add_row) subtree_fill(eng.tree, (int64_t)arow + R - 1, logE, maxp, t0, stride);  // its M-step windows are complete
+  }
+  if (t0 == 0) {
+    if (eng.mem_kind == SRLX_MEM_PROPORTIONAL) {
+      if (M > 1) subtree_root_and_path(eng.tree, (int64_t)row + R - 1, logE, 0.0);
+      if (add_row) subtree_root_and_path(eng.tree, (int64_t)arow + R - 1, logE, maxp);
+    }
+    const uint64_t rows_added = (g + 1 >= (uint64_t)(M - 1)) ? (g + 1 - (uint64_t)(M - 1)) : 0;
+    const uint64_t rows_cap = (uint64_t)(R - (M - 1));
+    st->mem_size = (uint64_t)E * (rows_added < rows_cap ? rows_added : rows_cap);
+    st->vec_steps = g + 1;
+    st->total_step += (uint64_t)E;
+  }
+}
+
 __global__ void __launch_bounds__(1024)
 post_step_kernel(const __grid_constant__ srlx_engine eng, double* __restrict__ scratch) {
   srlx_state* st = eng.state;
@@ -313,6 +365,22 @@ __global__ void engine_reset_kernel(const __grid_constant__ srlx_engine eng) {
 
 // ---- host side ---------------------------------------------------------------------------------------------------
 namespace srlx {
+// replay add of the row just written + counters: the complete-subtree kernel when E is a power of two (and the ring holds more than
+// one row, so that the two subtrees of an n-step add are distinct from the root), else the generic level-by-level kernel
+static void launch_post_step(const srlx_engine* eng, cudaStream_t st) {
+  const int E = eng->n_envs;
+  const bool pow2 = E >= 2 && (E & (E - 1)) == 0 && eng->ring_rows >= 2;
+  if (pow2) {
+    int logE = 0;
+    while ((1 << logE) < E) ++logE;
+    const long long nodes = 2ll * ((2ll << logE) - 2);
+    int grid = (int)((nodes + 1023) / 1024);
+    grid = grid < 1 ? 1 : (grid > 148 ? 148 : grid);
+    post_step_pow2_kernel<<<grid, 1024, 0, st>>>(*eng, logE);
+  } else {
+    post_step_kernel<<<1, 1024, 0, st>>>(*eng, eng->tree_scratch);
+  }
+}
 static int check_engine(const srlx_engine* eng) {
   SRLX_REQUIRE(eng != nullptr, "engine is NULL");
   SRLX_REQUIRE(eng->n_envs >= 1, "n_envs must be >= 1");
@@ -354,7 +422,7 @@ extern "C" int srlx_ext_step(const srlx_engine* eng, const float* obs_dev, const
   ext_row_write_kernel<<<grid, 256, 0, (cudaStream_t)cuda_stream>>>(*eng, obs_dev, next_obs_dev, action_dev, reward_dev, term_dev, done_dev);
   count_launch();
   SRLX_CHECK_CUDA(cudaGetLastError());
-  post_step_kernel<<<1, 1024, 0, (cudaStream_t)cuda_stream>>>(*eng, eng->tree_scratch);
+  launch_post_step(eng, (cudaStream_t)cuda_stream);
   count_launch();
   SRLX_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -422,7 +490,7 @@ extern "C" int srlx_vec_step(const srlx_engine* eng, int training, uintptr_t cud
   count_launch();
   SRLX_CHECK_CUDA(cudaGetLastError());
   if (training) {
-    post_step_kernel<<<1, 1024, 0, (cudaStream_t)cuda_stream>>>(*eng, eng->tree_scratch);
+    launch_post_step(eng, (cudaStream_t)cuda_stream);
   } else {
     eval_post_step_kernel<<<1, 1, 0, (cudaStream_t)cuda_stream>>>(eng->state, eng->n_envs);
   }

