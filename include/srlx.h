@@ -202,6 +202,64 @@ typedef struct srlx_engine {
   uint64_t dp_bytes;      /* size of every exchange buffer */
 } srlx_engine;
 
+/* ---- PPO (R15; BASELINE configs[4]) -- csrc/ppo.cu restates srl/algorithms/ppo/ppo.py for E vectorised env copies ------------------- */
+typedef struct srlx_ppo_state {
+  uint64_t train_count;  /* RLTrainer.train_count: minibatch updates done */
+  uint64_t adam_step;    /* optimizer.iterations */
+  double policy_loss, value_loss, entropy_loss; /* trainer.info of the last update (ppo.py:271-273) */
+  double grad_norm;      /* global gradient norm before clipping */
+  uint64_t reserved[2];
+} srlx_ppo_state;
+
+typedef struct srlx_ppo {
+  srlx_engine env;       /* env tables, env buffers, counters (`state`), seed, reward_shift / reward_scale; ring / tree / Q-net fields unused */
+  /* ActorCriticNetwork (ppo.py:55-101) as two dense stacks over ONE flat parameter buffer: value stack = trunk + value block + 1
+   * output, policy stack = trunk + policy block + outputs (continuous: loc, log_scale; discrete: logits); the trunk layers carry
+   * the same w_off / b_off in both.  ReLU between layers, last layer linear. */
+  srlx_net net_v, net_p;
+  int32_t n_params;
+  int32_t continuous;          /* 1: Normal policy on a 1-D Box action (Pendulum-v1); 0: Categorical over env.n_actions */
+  int32_t horizon;             /* T: rows of the rollout buffer */
+  int32_t batch_size;          /* <= 32 */
+  int32_t baseline_type;       /* 0 none, 1 "ave", 2 "std", 3 "normal", 4 "advantage" (ppo.py:220-232, :125-126) */
+  int32_t surrogate_clip;      /* 1 "clip", 0 "" */
+  int32_t enable_value_clip, state_normalized;
+  int32_t method;              /* SRLX_RETURNS_GAE / SRLX_RETURNS_MC */
+  int32_t reward_clip_enable;
+  uint64_t lr_decay_steps;     /* 0: constant lr; else keras ExponentialDecay(staircase=True): lr * rate^floor(step / steps) */
+  double discount, gae_discount, policy_clip_range, value_clip_range, lr, lr_decay_rate, value_loss_weight, entropy_weight, grad_clip_norm;
+  double adam_beta1, adam_beta2, adam_eps;  /* keras Adam: 0.9, 0.999, 1e-7 */
+  double log_scale_lo, log_scale_hi;        /* log of stable_gradients_scale_range (normal_dist_block.py:96-100,148-153) */
+  double action_low, action_high;           /* the env's Box: rescale_from [-1, 1] then clip (np_array.py:64-67,93-95) */
+  double reward_clip_lo, reward_clip_hi;
+  /* device buffers (caller-owned) */
+  float* params; float* adam_m; float* adam_v;  /* [n_params] */
+  float* buf_obs;          /* [T][E][D] worker batch["state"] */
+  float* buf_action;       /* [T][E] the policy's action (before rescaling) or the action index */
+  float* buf_v;            /* [T][E] batch["v"]: V(s) at acting time (old_v of the value clip) */
+  float* buf_logp;         /* [T][E] batch["log_prob"] */
+  float* buf_reward;       /* [T][E] */
+  unsigned char* buf_done; /* [T][E] */
+  float* buf_vnew;         /* [T+1][E] V(s) with the parameters at the end of the rollout (GAE) */
+  float* buf_ret;          /* [T][E] batch["discounted_reward"] */
+  unsigned char* buf_valid;/* [T][E] 1 where the reference would have emitted the step (its episode ended inside the buffer) */
+  srlx_ppo_state* pstate;
+  int32_t* dbg_idx;        /* optional [batch_size]: flat buffer indices of the last minibatch */
+  float* dbg_grads;        /* optional [n_params]: clipped gradient of the last update */
+  float* grad_scratch;     /* [n_params]: gradient accumulator of the update kernel when it does not fit shared memory (wide blocks) */
+} srlx_ppo;
+
+size_t srlx_sizeof_ppo(void);
+size_t srlx_sizeof_ppo_state(void);
+/* one vector step of all E env copies under the current policy (Worker.policy + env.step); training != 0 stores row vec_steps % T */
+int srlx_ppo_vec_step(const srlx_ppo* ppo, int training, uintptr_t cuda_stream);
+/* V(s) of n states [n][D] with the current parameters */
+int srlx_ppo_values(const srlx_ppo* ppo, const float* obs_dev, uint64_t n, float* out_dev, uintptr_t cuda_stream);
+/* Worker.on_step at episode end for the whole buffer (ppo.py:375-404): values with the current parameters, GAE / MC -> buf_ret, buf_valid */
+int srlx_ppo_finish_rollout(const srlx_ppo* ppo, uintptr_t cuda_stream);
+/* n_updates x Trainer._train (ppo.py:208-291) on the finished buffer */
+int srlx_ppo_learn(const srlx_ppo* ppo, uint32_t n_updates, uintptr_t cuda_stream);
+
 /* ---- library ------------------------------------------------------------------------------------------ */
 int srlx_version(void);
 const char* srlx_last_error(void);

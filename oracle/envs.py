@@ -283,8 +283,12 @@ class PendulumSpec:
         return np.array([cs, sn, st[1]], dtype=np.float64).astype(np.float32)
 
     def step(self, st, action, seed=None, e=None, g=None):
+        return self.step_torque(st, np.float64(self.action_table[action]))
+
+    def step_torque(self, st, u):
+        """One step with a continuous torque u (already inside [-max_torque, max_torque]): what the policy-gradient algorithms send."""
         th, thdot = np.float64(st[0]), np.float64(st[1])
-        u = np.float64(self.action_table[action])
+        u = np.float64(u)
         an = pend_angle_normalize(th)
         sn, _ = pend_sincos(an)
         costs = (an * an + np.float64(0.1) * (thdot * thdot)) + np.float64(0.001) * (u * u)

@@ -89,6 +89,30 @@ class SrlxEngine(C.Structure):
     ]
 
 
+class SrlxPpoState(C.Structure):
+    _fields_ = [("train_count", C.c_uint64), ("adam_step", C.c_uint64), ("policy_loss", C.c_double), ("value_loss", C.c_double),
+                ("entropy_loss", C.c_double), ("grad_norm", C.c_double), ("reserved", C.c_uint64 * 2)]
+
+
+class SrlxPpo(C.Structure):
+    _fields_ = [
+        ("env", SrlxEngine), ("net_v", SrlxNet), ("net_p", SrlxNet),
+        ("n_params", C.c_int32), ("continuous", C.c_int32), ("horizon", C.c_int32), ("batch_size", C.c_int32),
+        ("baseline_type", C.c_int32), ("surrogate_clip", C.c_int32), ("enable_value_clip", C.c_int32), ("state_normalized", C.c_int32),
+        ("method", C.c_int32), ("reward_clip_enable", C.c_int32),
+        ("lr_decay_steps", C.c_uint64),
+        ("discount", C.c_double), ("gae_discount", C.c_double), ("policy_clip_range", C.c_double), ("value_clip_range", C.c_double),
+        ("lr", C.c_double), ("lr_decay_rate", C.c_double), ("value_loss_weight", C.c_double), ("entropy_weight", C.c_double),
+        ("grad_clip_norm", C.c_double),
+        ("adam_beta1", C.c_double), ("adam_beta2", C.c_double), ("adam_eps", C.c_double),
+        ("log_scale_lo", C.c_double), ("log_scale_hi", C.c_double), ("action_low", C.c_double), ("action_high", C.c_double),
+        ("reward_clip_lo", C.c_double), ("reward_clip_hi", C.c_double),
+        ("params", _P), ("adam_m", _P), ("adam_v", _P),
+        ("buf_obs", _P), ("buf_action", _P), ("buf_v", _P), ("buf_logp", _P), ("buf_reward", _P), ("buf_done", _P), ("buf_vnew", _P),
+        ("buf_ret", _P), ("buf_valid", _P), ("pstate", _P), ("dbg_idx", _P), ("dbg_grads", _P), ("grad_scratch", _P),
+    ]
+
+
 class SrlxError(RuntimeError):
     pass
 
@@ -117,6 +141,12 @@ SYMBOLS = [
     ("srlx_learner_info", C.c_int, [C.POINTER(SrlxEngine), C.POINTER(C.c_int), C.POINTER(C.c_size_t)]),
     ("srlx_tree_blk_bytes", _sz, [_u64]),
     ("srlx_qnet_forward", C.c_int, [C.POINTER(SrlxEngine), _i32, _P, _u32, _u64, _P, _uptr]),
+    ("srlx_sizeof_ppo", _sz, []),
+    ("srlx_sizeof_ppo_state", _sz, []),
+    ("srlx_ppo_vec_step", C.c_int, [C.POINTER(SrlxPpo), _i32, _uptr]),
+    ("srlx_ppo_values", C.c_int, [C.POINTER(SrlxPpo), _P, _u64, _P, _uptr]),
+    ("srlx_ppo_finish_rollout", C.c_int, [C.POINTER(SrlxPpo), _uptr]),
+    ("srlx_ppo_learn", C.c_int, [C.POINTER(SrlxPpo), _u32, _uptr]),
     ("srlx_dense_bf16_tc", C.c_int, [_P, _i32, _P, _i32, _P, _P, _i32, _i32, _i32, _i32, _i32, _i32, _uptr]),
     ("srlx_qnet_tc_workspace_bytes", _sz, [C.POINTER(SrlxEngine), _u32]),
     ("srlx_qnet_forward_tc", C.c_int, [C.POINTER(SrlxEngine), _i32, _P, _u32, _u64, _P, _P, _sz, _uptr]),
@@ -155,6 +185,9 @@ def load():
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
+    if lib.srlx_sizeof_ppo() != C.sizeof(SrlxPpo) or lib.srlx_sizeof_ppo_state() != C.sizeof(SrlxPpoState):
+        raise SrlxError(f"ABI mismatch: C sizes ppo/ppo_state = {lib.srlx_sizeof_ppo()}/{lib.srlx_sizeof_ppo_state()}, "
+                        f"ctypes = {C.sizeof(SrlxPpo)}/{C.sizeof(SrlxPpoState)}")
     if lib.srlx_sizeof_engine() != C.sizeof(SrlxEngine) or lib.srlx_sizeof_state() != C.sizeof(SrlxState) or lib.srlx_sizeof_net() != C.sizeof(SrlxNet):
         raise SrlxError(
             f"ABI mismatch: C sizes engine/state/net = {lib.srlx_sizeof_engine()}/{lib.srlx_sizeof_state()}/{lib.srlx_sizeof_net()}, "

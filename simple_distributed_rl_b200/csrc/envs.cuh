@@ -170,10 +170,10 @@ __device__ inline void pendulum_reset(const srlx_engine& eng, uint32_t e, uint32
   st[2] = 0.0;
   st[3] = 0.0;
 }
-__device__ inline double pendulum_step(const srlx_engine& eng, int action, double* st, bool& terminated) {
+// continuous torque u (already inside [-max_torque, max_torque]): the policy-gradient algorithms act on the Box directly
+__device__ inline double pendulum_step_torque(const double u, double* st, bool& terminated) {
   const double dt = 0.05, max_speed = 8.0;
   const double th = st[0], thdot = st[1];
-  const double u = eng.act_tbl[action];  // already inside [-max_torque, max_torque]
   const double an = pend_angle_normalize(th);
   double sn, cs;
   pend_sincos(an, sn, cs);
@@ -184,6 +184,9 @@ __device__ inline double pendulum_step(const srlx_engine& eng, int action, doubl
   st[1] = newthdot;
   terminated = false;  // Pendulum only ever ends by the 200-step TimeLimit
   return -costs;
+}
+__device__ inline double pendulum_step(const srlx_engine& eng, int action, double* st, bool& terminated) {
+  return pendulum_step_torque(eng.act_tbl[action], st, terminated);  // the reference's discretised torques (value-based algorithms)
 }
 
 // ---- dispatch ---------------------------------------------------------------------------------------------------
