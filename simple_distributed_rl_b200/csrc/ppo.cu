@@ -19,7 +19,7 @@
 
 namespace srlx {
 
-constexpr int kPpoThreads = 256;
+constexpr int kPpoThreads = 256, kPpoUpdThreads = 512;
 
 struct PpoSmem {
   size_t wv, wp, av, ap, qv, qp, total;
@@ -42,9 +42,22 @@ __host__ __device__ inline PpoSmem ppo_smem(const srlx_ppo& p, const NetPlan& pv
 __device__ inline void ppo_load_weights(const srlx_net& net, const NetPlan& pl, const float* __restrict__ params, float* weff) {
   for (int l = 0; l < net.n_layers; ++l) {
     const int U = net.out_dim[l], K = net.k_dim[l];
-    for (int i = threadIdx.x; i < U * K; i += blockDim.x) {
-      const int u = i / K, k = i - u * K;
-      weff[pl.w_s[l] + u * pl.ldw[l] + k] = __ldcg(params + net.w_off[l] + i);
+    const int n = U * K, nt = blockDim.x;
+    for (int i0 = threadIdx.x; i0 < n; i0 += 4 * nt) {  // four independent L2 loads in flight per thread
+      float v[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int i = i0 + j * nt;
+        v[j] = i < n ? __ldcg(params + net.w_off[l] + i) : 0.f;
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int i = i0 + j * nt;
+        if (i < n) {
+          const int u = i / K, k = i - u * K;
+          weff[pl.w_s[l] + u * pl.ldw[l] + k] = v[j];
+        }
+      }
     }
     for (int u = threadIdx.x; u < U; u += blockDim.x) weff[pl.b_s[l] + u] = __ldcg(params + net.b_off[l] + u);
   }
@@ -245,7 +258,7 @@ __host__ __device__ inline PpoUpdSmem ppo_upd_smem(const srlx_ppo& p, const NetP
 
 // g_ext: the gradient accumulator in global memory (wide networks: two weight copies + activations already fill the shared memory);
 // NULL -> shared memory
-__global__ void __launch_bounds__(kPpoThreads)
+__global__ void __launch_bounds__(kPpoUpdThreads)
 ppo_update_kernel(const __grid_constant__ srlx_ppo ppo, const uint32_t n_updates, float* __restrict__ g_ext) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const NetPlan pv = make_plan(ppo.net_v), pp = make_plan(ppo.net_p);
@@ -456,15 +469,30 @@ ppo_update_kernel(const __grid_constant__ srlx_ppo ppo, const uint32_t n_updates
       const double t1 = (double)(step + 1);
       const float alpha = (float)(lr * sqrt(1.0 - pow(ppo.adam_beta2, t1)) / (1.0 - pow(ppo.adam_beta1, t1)));
       const float b1 = (float)ppo.adam_beta1, b2 = (float)ppo.adam_beta2, eps = (float)ppo.adam_eps;
-      for (int i = tid; i < P; i += nt) {
-        const float g = G[i] * scale;
-        float m = ppo.adam_m[i], v = ppo.adam_v[i];
-        m = m + (g - m) * (1.0f - b1);
-        v = v + (g * g - v) * (1.0f - b2);
-        ppo.adam_m[i] = m;
-        ppo.adam_v[i] = v;
-        ppo.params[i] = ppo.params[i] - alpha * m / (sqrtf(v) + eps);
-        if (ppo.dbg_grads) ppo.dbg_grads[i] = g;
+      for (int i0 = tid; i0 < P; i0 += 4 * nt) {  // four parameters per thread and pass: their loads are in flight together
+        float gg[4], mm[4], vv[4], pp4[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int i = i0 + j * nt;
+          const bool ok = i < P;
+          gg[j] = ok ? G[i] * scale : 0.f;
+          mm[j] = ok ? __ldcg(ppo.adam_m + i) : 0.f;
+          vv[j] = ok ? __ldcg(ppo.adam_v + i) : 0.f;
+          pp4[j] = ok ? __ldcg(ppo.params + i) : 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int i = i0 + j * nt;
+          if (i < P) {
+            const float g = gg[j];
+            const float m = mm[j] + (g - mm[j]) * (1.0f - b1);
+            const float v = vv[j] + (g * g - vv[j]) * (1.0f - b2);
+            ppo.adam_m[i] = m;
+            ppo.adam_v[i] = v;
+            ppo.params[i] = pp4[j] - alpha * m / (sqrtf(v) + eps);
+            if (ppo.dbg_grads) ppo.dbg_grads[i] = g;
+          }
+        }
       }
     }
     __syncthreads();
@@ -579,7 +607,7 @@ extern "C" int srlx_ppo_learn(const srlx_ppo* ppo, uint32_t n_updates, uintptr_t
   }
   SRLX_REQUIRE((long long)so.total + 1024 <= max_smem, "network too large for the PPO update kernel: needs %zu bytes of shared memory", so.total);
   SRLX_CHECK_CUDA(cudaFuncSetAttribute(ppo_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)so.total));
-  ppo_update_kernel<<<1, kPpoThreads, so.total, (cudaStream_t)cuda_stream>>>(*ppo, n_updates, g_ext);
+  ppo_update_kernel<<<1, kPpoUpdThreads, so.total, (cudaStream_t)cuda_stream>>>(*ppo, n_updates, g_ext);
   count_launch();
   SRLX_CHECK_CUDA(cudaGetLastError());
   return 0;
