@@ -260,6 +260,74 @@ int srlx_ppo_finish_rollout(const srlx_ppo* ppo, uintptr_t cuda_stream);
 /* n_updates x Trainer._train (ppo.py:208-291) on the finished buffer */
 int srlx_ppo_learn(const srlx_ppo* ppo, uint32_t n_updates, uintptr_t cuda_stream);
 
+/* ---- R2D2 (R14; BASELINE configs[3]) -- csrc/r2d2.cu restates srl/algorithms/r2d2/r2d2.py for E vectorised env copies --------------
+ * Q-network (r2d2.py:27-63): Flatten -> keras LSTM(lstm_units) -> hidden block (MLP + Dense(A), or MLP + dueling block).
+ * Parameter layout (one flat fp32 buffer; every dense map carries its bias as a LAST COLUMN, activations carry a trailing 1):
+ *   lstm   W[4u][in + u + 1]   row j = unit * 4 + gate (gate order i, f, c~, o as keras), columns [x (in) | h (u) | bias]
+ *   head l W[out_l][k_l + 1]   ReLU after every layer but the last; dueling: the last hidden layer is [value-hidden(H) ; advantage-
+ *          hidden(H)] (width 2H) and the output layer has 1 + A rows over 2H inputs whose off-branch blocks are structural zeros
+ *          (row 0 reads [0,H), rows 1..A read [H,2H)); duel_hidden = H tells the optimiser which entries never move.
+ * Replay: one ring COLUMN per env copy with its own cursor (slot(e, c) = (c % R) * E + e).  A row stores one step of the worker's
+ * recent_* lists (r2d2.py:232-283): state, next state, action, behaviour probability, reward, terminated, the LSTM state BEFORE the step,
+ * and the step's index in its episode; the seq_len-1 padded steps the reference appends at an episode's end (:285-303) are written as
+ * rows too, the padding in front of an episode's first step (:232-247) is rebuilt by index.  Item = anchor row = the newest
+ * transition of a (burnin + seq_len + 1)-state window, exactly one item per memory.add() of the reference. */
+typedef struct srlx_r2d2 {
+  srlx_engine env;  /* env tables + env buffers + `state` counters + seed, epsilon, discount, lr, adam_*, per_*, batch_size, mem_kind,
+                       has_duplicate, warmup_size, target_update_interval, enable_double_dqn, enable_rescale, retrace_h, ring_rows (R),
+                       tree ([2*R*E-1], proportional only); the Q-net / ring / learner fields of srlx_engine are unused */
+  int32_t lstm_units, burnin, seq_len, enable_retrace;
+  int32_t n_head, dueling;                 /* head layers (incl. the output layer); SRLX_DUEL_* */
+  int32_t head_out[SRLX_MAX_LAYERS], head_k[SRLX_MAX_LAYERS], head_off[SRLX_MAX_LAYERS]; /* rows, inputs (without the bias column), offset */
+  int32_t lstm_off, n_params;
+  int32_t duel_hidden, reserved_i32;       /* H of the dueling block (0: no dueling block) */
+  double test_epsilon;
+  /* parameters */
+  float* params; float* target; float* adam_m; float* adam_v; float* grads; /* [n_params] each */
+  /* replay ring, [R*E] rows */
+  uint32_t* cursor;        /* [E] rows written so far by env e */
+  float* ring_obs; float* ring_next_obs;   /* [R*E][D] */
+  int32_t* ring_action; double* ring_prob; double* ring_reward; unsigned char* ring_done; int32_t* ring_tstep; /* [R*E] */
+  float* ring_h; float* ring_c;            /* [R*E][u] */
+  /* rollout workspace */
+  float* roll_xh;          /* [E][in+u+1] the step's LSTM input [x | h_{t-1} | 1] (the library writes the trailing 1) */
+  float* roll_h;           /* [E][u+1] h_t carried to the next step, last column 1 (head input) */
+  float* roll_c;           /* [E][u] */
+  float* roll_act[SRLX_MAX_LAYERS]; /* [E][head_out[l] + 1] (last column 1); the last one [E][head_out] */
+  unsigned char* roll_reset; /* [E] */
+  uint32_t* new_c0; uint32_t* new_n;  /* [E] first new row / rows written by the last vector step */
+  int64_t* add_idx; double* add_pri;  /* [2*E*seq_len] replay-add list (proportional) */
+  /* learner workspace; z = 0 online, 1 target; W = burnin + seq_len; rows t-major */
+  float* xh;               /* [2][W+2][B][in+u+1], last column 1 */
+  float* cbuf;             /* [2][W+2][B][u] */
+  float* gates;            /* [W+1][B][4u] online gate activations */
+  float* dgates;           /* [W+1][B][4u] */
+  float* dc;               /* [B][u] */
+  float* act[SRLX_MAX_LAYERS];  /* [2][(seq_len+1)*B][head_out[l] + 1] (last column 1); last layer [2][rows][head_out] */
+  float* dact[SRLX_MAX_LAYERS]; /* [(seq_len+1)*B][head_out[l]] gradient wrt the layer's output */
+  float* dh;               /* [(seq_len+1)*B][u] gradient wrt the LSTM outputs */
+  float* q;                /* [2][B][seq_len+1][A] */
+  int64_t* sel;            /* [B] tree indices (proportional) or slots (uniform) of the batch */
+  float* weights;          /* [B] IS weights */
+  int32_t* b_actions; double* b_mu; double* b_rewards; unsigned char* b_dones; /* [B][seq_len] */
+  double* b_target; double* b_tdmean; unsigned char* b_tdkind;                 /* [B][seq_len], [B], [B] */
+} srlx_r2d2;
+
+size_t srlx_sizeof_r2d2(void);
+/* one vector step (Worker.policy + env.step + Worker.on_step, r2d2.py:249-318); training != 0 stores rows and adds items */
+int srlx_r2d2_vec_step(const srlx_r2d2* r, int training, uintptr_t cuda_stream);
+/* n_updates x Trainer.train (r2d2.py:90-215); no-op while mem_size < warmup_size */
+int srlx_r2d2_learn(const srlx_r2d2* r, uint32_t n_updates, uintptr_t cuda_stream);
+/* q_out[n][A] = Q of ONE step from the given LSTM state: obs [n][D], h / c [n][u] in, h_out / c_out [n][u] out (may alias h / c);
+ * test tap and evaluation helper: runs in the learner workspace (r->xh, r->cbuf, r->act), so n <= batch_size and never between the
+ * kernels of an update */
+int srlx_r2d2_forward(const srlx_r2d2* r, int use_target, const float* obs_dev, const float* h_dev, const float* c_dev, uint32_t n,
+                      float* q_out_dev, float* h_out_dev, float* c_out_dev, uintptr_t cuda_stream);
+/* C[M][N] = A . B with arbitrary strides (the fp32 GEMM every R2D2 layer runs on; test tap): A(m,k) = a[m*sa_m + k*sa_k],
+ * B(k,n) = b[k*sb_k + n*sb_n], C row stride ldc; relu != 0 clamps at 0; accumulate != 0 adds to C */
+int srlx_sgemm(const float* a_dev, long long sa_m, long long sa_k, const float* b_dev, long long sb_k, long long sb_n, float* c_dev,
+               long long ldc, int M, int N, int K, int relu, int accumulate, uintptr_t cuda_stream);
+
 /* ---- library ------------------------------------------------------------------------------------------ */
 int srlx_version(void);
 const char* srlx_last_error(void);

@@ -113,6 +113,25 @@ class SrlxPpo(C.Structure):
     ]
 
 
+class SrlxR2d2(C.Structure):
+    _fields_ = [
+        ("env", SrlxEngine),
+        ("lstm_units", C.c_int32), ("burnin", C.c_int32), ("seq_len", C.c_int32), ("enable_retrace", C.c_int32),
+        ("n_head", C.c_int32), ("dueling", C.c_int32),
+        ("head_out", C.c_int32 * SRLX_MAX_LAYERS), ("head_k", C.c_int32 * SRLX_MAX_LAYERS), ("head_off", C.c_int32 * SRLX_MAX_LAYERS),
+        ("lstm_off", C.c_int32), ("n_params", C.c_int32), ("duel_hidden", C.c_int32), ("reserved_i32", C.c_int32),
+        ("test_epsilon", C.c_double),
+        ("params", _P), ("target", _P), ("adam_m", _P), ("adam_v", _P), ("grads", _P),
+        ("cursor", _P), ("ring_obs", _P), ("ring_next_obs", _P), ("ring_action", _P), ("ring_prob", _P), ("ring_reward", _P),
+        ("ring_done", _P), ("ring_tstep", _P), ("ring_h", _P), ("ring_c", _P),
+        ("roll_xh", _P), ("roll_h", _P), ("roll_c", _P), ("roll_act", _P * SRLX_MAX_LAYERS), ("roll_reset", _P),
+        ("new_c0", _P), ("new_n", _P), ("add_idx", _P), ("add_pri", _P),
+        ("xh", _P), ("cbuf", _P), ("gates", _P), ("dgates", _P), ("dc", _P),
+        ("act", _P * SRLX_MAX_LAYERS), ("dact", _P * SRLX_MAX_LAYERS), ("dh", _P), ("q", _P), ("sel", _P), ("weights", _P),
+        ("b_actions", _P), ("b_mu", _P), ("b_rewards", _P), ("b_dones", _P), ("b_target", _P), ("b_tdmean", _P), ("b_tdkind", _P),
+    ]
+
+
 class SrlxError(RuntimeError):
     pass
 
@@ -147,6 +166,11 @@ SYMBOLS = [
     ("srlx_ppo_values", C.c_int, [C.POINTER(SrlxPpo), _P, _u64, _P, _uptr]),
     ("srlx_ppo_finish_rollout", C.c_int, [C.POINTER(SrlxPpo), _uptr]),
     ("srlx_ppo_learn", C.c_int, [C.POINTER(SrlxPpo), _u32, _uptr]),
+    ("srlx_sizeof_r2d2", _sz, []),
+    ("srlx_r2d2_vec_step", C.c_int, [C.POINTER(SrlxR2d2), _i32, _uptr]),
+    ("srlx_r2d2_learn", C.c_int, [C.POINTER(SrlxR2d2), _u32, _uptr]),
+    ("srlx_r2d2_forward", C.c_int, [C.POINTER(SrlxR2d2), _i32, _P, _P, _P, _u32, _P, _P, _P, _uptr]),
+    ("srlx_sgemm", C.c_int, [_P, C.c_longlong, C.c_longlong, _P, C.c_longlong, C.c_longlong, _P, C.c_longlong, _i32, _i32, _i32, _i32, _i32, _uptr]),
     ("srlx_dense_bf16_tc", C.c_int, [_P, _i32, _P, _i32, _P, _P, _i32, _i32, _i32, _i32, _i32, _i32, _uptr]),
     ("srlx_qnet_tc_workspace_bytes", _sz, [C.POINTER(SrlxEngine), _u32]),
     ("srlx_qnet_forward_tc", C.c_int, [C.POINTER(SrlxEngine), _i32, _P, _u32, _u64, _P, _P, _sz, _uptr]),
@@ -188,6 +212,8 @@ def load():
     if lib.srlx_sizeof_ppo() != C.sizeof(SrlxPpo) or lib.srlx_sizeof_ppo_state() != C.sizeof(SrlxPpoState):
         raise SrlxError(f"ABI mismatch: C sizes ppo/ppo_state = {lib.srlx_sizeof_ppo()}/{lib.srlx_sizeof_ppo_state()}, "
                         f"ctypes = {C.sizeof(SrlxPpo)}/{C.sizeof(SrlxPpoState)}")
+    if lib.srlx_sizeof_r2d2() != C.sizeof(SrlxR2d2):
+        raise SrlxError(f"ABI mismatch: C size r2d2 = {lib.srlx_sizeof_r2d2()}, ctypes = {C.sizeof(SrlxR2d2)}")
     if lib.srlx_sizeof_engine() != C.sizeof(SrlxEngine) or lib.srlx_sizeof_state() != C.sizeof(SrlxState) or lib.srlx_sizeof_net() != C.sizeof(SrlxNet):
         raise SrlxError(
             f"ABI mismatch: C sizes engine/state/net = {lib.srlx_sizeof_engine()}/{lib.srlx_sizeof_state()}/{lib.srlx_sizeof_net()}, "

@@ -1,0 +1,958 @@
+// r2d2.cu -- R2D2 on device (BASELINE configs[3]): srl/algorithms/r2d2/r2d2.py restated for E vectorised env copies.
+//   Worker.on_reset / policy / on_step (:221-318)  -> r2d2_pre_kernel, r2d2_hidden_kernel, lstm_fwd_kernel, sgemm (head), r2d2_act_kernel,
+//                                                     r2d2_add_kernel (proportional memory)
+//   Trainer.train / _train_on_batches (:90-215)    -> r2d2_sample_*_kernel, r2d2_gather_kernel, lstm_fwd_kernel x (burnin + seq_len + 1)
+//                                                     for both networks, head GEMMs, srlx_sequence_targets (the reference's own target loop,
+//                                                     bit-exact, csrc/sequence_targets.cu), r2d2_loss_kernel (keras Huber on target * w, q * w),
+//                                                     head backward GEMMs, lstm_bwd_kernel x seq_len (BPTT, burn-in outside the tape),
+//                                                     weight-gradient GEMMs, r2d2_adam_kernel (keras Adam), priority update, target sync
+// The reference's R2D2 is TensorFlow-only (r2d2.py:5); the CPU oracle (oracle/r2d2.py) is a torch RESTATEMENT of the keras model and says so.
+// Every dense map is one strided fp32 GEMM (sgemm_kernel) whose bias rides as the last weight column against a trailing 1 in the
+// activations, so forward, input gradient and weight gradient (bias included) are the same kernel with different strides.  The LSTM
+// step fuses the gate GEMM with the cell update (a thread owns the four gates of a unit); the BPTT step fuses dh = dgates . Wh^T with
+// the gate derivatives.  One launch per time step: consecutive steps are data dependent; the whole update is launch-ordered on one
+// stream and capturable in a CUDA graph (no host synchronisation, no allocation; the warm-up gate is evaluated on device).
+#include "envs.cuh"
+#include "tree.cuh"
+
+namespace srlx {
+
+constexpr uint32_t R2D2_PAD_TAIL = 0, R2D2_PAD_PRE = 1;
+
+struct Gate {  // kernels of an update return at once while the memory is below warmup_size (Trainer.train: `if batches is None: return`)
+  const srlx_state* st;
+  unsigned long long warmup;
+  __device__ __forceinline__ bool closed() const { return st != nullptr && st->mem_size < warmup; }
+};
+
+// ---- strided fp32 GEMM --------------------------------------------------------------------------------------------------------------
+struct GemmP {
+  const float* A; long long sa_m, sa_k;
+  const float* B; long long sb_k, sb_n;
+  float* C; long long ldc;
+  int M, N, K;
+  int relu, accumulate;
+  const float* mask; long long ldmask;  // C = mask > 0 ? C : 0 (ReLU backward against the layer's stored output)
+  long long zA, zB, zC;                 // blockIdx.z strides (floats)
+  const float* B1;                      // if set: blockIdx.z == 1 reads B1 instead of B + zB (online / target parameter buffers)
+  Gate gate;
+};
+
+template <int BM, int BN, int TM, int TN>
+__device__ __forceinline__ void gemm_mainloop(const float* __restrict__ A, long long sa_m, long long sa_k, const float* __restrict__ B,
+                                              long long sb_k, long long sb_n, int M, int N, int K, int m0, int n0, float (&acc)[TM][TN]) {
+  constexpr int BK = 16, NT = (BM / TM) * (BN / TN);
+  __shared__ float As[BK][BM + 4];
+  __shared__ float Bs[BK][BN + 4];
+  const int tid = threadIdx.x, tx = tid % (BN / TN), ty = tid / (BN / TN);
+#pragma unroll
+  for (int i = 0; i < TM; ++i)
+#pragma unroll
+    for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+  for (int k0 = 0; k0 < K; k0 += BK) {
+    for (int i = tid; i < BM * BK; i += NT) {
+      int mm, kk;
+      if (sa_k == 1) { kk = i % BK; mm = i / BK; } else { mm = i % BM; kk = i / BM; }
+      const int gm = m0 + mm, gk = k0 + kk;
+      As[kk][mm] = (gm < M && gk < K) ? __ldg(A + (long long)gm * sa_m + (long long)gk * sa_k) : 0.f;
+    }
+    for (int i = tid; i < BN * BK; i += NT) {
+      int nn, kk;
+      if (sb_n == 1) { nn = i % BN; kk = i / BN; } else { kk = i % BK; nn = i / BK; }
+      const int gn = n0 + nn, gk = k0 + kk;
+      Bs[kk][nn] = (gn < N && gk < K) ? __ldcg(B + (long long)gk * sb_k + (long long)gn * sb_n) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < BK; ++kk) {
+      float a[TM], b[TN];
+#pragma unroll
+      for (int i = 0; i < TM; ++i) a[i] = As[kk][ty * TM + i];
+#pragma unroll
+      for (int j = 0; j < TN; ++j) b[j] = Bs[kk][tx * TN + j];
+#pragma unroll
+      for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+}
+
+template <int BM, int BN, int TM, int TN>
+__global__ void __launch_bounds__((BM / TM) * (BN / TN)) sgemm_kernel(const GemmP p) {
+  if (p.gate.closed()) return;
+  const int z = blockIdx.z;
+  const float* A = p.A + (long long)z * p.zA;
+  const float* B = (z == 1 && p.B1) ? p.B1 : p.B + (long long)z * p.zB;
+  float* C = p.C + (long long)z * p.zC;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  float acc[TM][TN];
+  gemm_mainloop<BM, BN, TM, TN>(A, p.sa_m, p.sa_k, B, p.sb_k, p.sb_n, p.M, p.N, p.K, m0, n0, acc);
+  const int tx = threadIdx.x % (BN / TN), ty = threadIdx.x / (BN / TN);
+#pragma unroll
+  for (int i = 0; i < TM; ++i) {
+    const int m = m0 + ty * TM + i;
+    if (m >= p.M) continue;
+#pragma unroll
+    for (int j = 0; j < TN; ++j) {
+      const int n = n0 + tx * TN + j;
+      if (n >= p.N) continue;
+      float v = acc[i][j];
+      float* c = C + (long long)m * p.ldc + n;
+      if (p.accumulate) v += *c;
+      if (p.relu) v = fmaxf(v, 0.f);
+      if (p.mask && !(p.mask[(long long)m * p.ldmask + n] > 0.f)) v = 0.f;
+      *c = v;
+    }
+  }
+}
+
+static int launch_gemm(const GemmP& p, int nz, cudaStream_t s) {
+  if (p.M <= 0 || p.N <= 0) return 0;
+  if (p.M <= 32 || p.N <= 32) {
+    dim3 grid((p.N + 31) / 32, (p.M + 31) / 32, nz);
+    sgemm_kernel<32, 32, 2, 4><<<grid, 128, 0, s>>>(p);
+  } else {
+    dim3 grid((p.N + 63) / 64, (p.M + 63) / 64, nz);
+    sgemm_kernel<64, 64, 4, 4><<<grid, 256, 0, s>>>(p);
+  }
+  count_launch();
+  return 0;
+}
+
+// ---- LSTM step, forward: gates = [x_t | h_{t-1} | 1] . W^T, keras gate order (i, f, c~, o); c_t = f c_{t-1} + i c~; h_t = o tanh(c_t) -------
+struct LstmFwdP {
+  const float* xh; long long z_xh;   // [z][M][K]
+  const float* W0; const float* W1;  // per z: [4u][K]
+  const float* c_in; float* c_out; long long z_c;  // [z][M][u]
+  float* h_out; long long ld_h, z_h;               // h_t -> row m at h_out + z*z_h + m*ld_h
+  float* gates;                       // z == 0 only: [M][4u] activated gates (BPTT), or NULL
+  int M, u, K;
+  Gate gate;
+};
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+template <int BM, int TM>
+__global__ void __launch_bounds__((BM / TM) * 8) lstm_fwd_kernel(const LstmFwdP p) {
+  if (p.gate.closed()) return;
+  constexpr int BN = 32, TN = 4;
+  const int z = blockIdx.z;
+  const float* W = z ? p.W1 : p.W0;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  float acc[TM][TN];
+  gemm_mainloop<BM, BN, TM, TN>(p.xh + (long long)z * p.z_xh, p.K, 1, W, 1, p.K, p.M, 4 * p.u, p.K, m0, n0, acc);
+  const int tx = threadIdx.x % (BN / TN), ty = threadIdx.x / (BN / TN);
+  const int unit = (n0 >> 2) + tx;
+  if (unit >= p.u) return;
+#pragma unroll
+  for (int i = 0; i < TM; ++i) {
+    const int m = m0 + ty * TM + i;
+    if (m >= p.M) continue;
+    const float ig = sigmoidf_(acc[i][0]), fg = sigmoidf_(acc[i][1]), gg = tanhf(acc[i][2]), og = sigmoidf_(acc[i][3]);
+    const long long ci = (long long)z * p.z_c + (long long)m * p.u + unit;
+    const float c = fmaf(fg, p.c_in[ci], ig * gg);
+    p.c_out[ci] = c;
+    p.h_out[(long long)z * p.z_h + (long long)m * p.ld_h + unit] = og * tanhf(c);
+    if (p.gates && z == 0) *reinterpret_cast<float4*>(p.gates + ((long long)m * p.u + unit) * 4) = make_float4(ig, fg, gg, og);
+  }
+}
+
+// ---- LSTM step, backward (BPTT): dh_t = dgates_{t+1} . Wh + dL/dh_t (head); gate derivatives; dc carried in place ---------------------
+struct LstmBwdP {
+  const float* dg_next;  // [M][4u] or NULL (last step of the tape)
+  const float* W; int in; int K;
+  const float* dh_head;  // [M][u]
+  const float* gates;    // [M][4u] of step t
+  const float* c_prev;   // [M][u] c_{t-1}
+  const float* c_cur;    // [M][u] c_t
+  float* dc;             // [M][u] in: dL/dc_t from step t+1, out: dL/dc_{t-1}
+  float* dg;             // [M][4u] out: gradient wrt the pre-activation gates of step t
+  int M, u, first;       // first != 0: dc starts at 0
+  Gate gate;
+};
+
+template <int BM, int TM>
+__global__ void __launch_bounds__((BM / TM) * 8) lstm_bwd_kernel(const LstmBwdP p) {
+  if (p.gate.closed()) return;
+  constexpr int BN = 32, TN = 4;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  float acc[TM][TN];
+  if (p.dg_next) {
+    gemm_mainloop<BM, BN, TM, TN>(p.dg_next, 4LL * p.u, 1, p.W + p.in, p.K, 1, p.M, p.u, 4 * p.u, m0, n0, acc);
+  } else {
+#pragma unroll
+    for (int i = 0; i < TM; ++i)
+#pragma unroll
+      for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+  }
+  const int tx = threadIdx.x % (BN / TN), ty = threadIdx.x / (BN / TN);
+#pragma unroll
+  for (int i = 0; i < TM; ++i) {
+    const int m = m0 + ty * TM + i;
+    if (m >= p.M) continue;
+#pragma unroll
+    for (int j = 0; j < TN; ++j) {
+      const int unit = n0 + tx * TN + j;
+      if (unit >= p.u) continue;
+      const long long ui = (long long)m * p.u + unit;
+      const float4 g4 = *reinterpret_cast<const float4*>(p.gates + ui * 4);
+      const float ig = g4.x, fg = g4.y, gg = g4.z, og = g4.w;
+      const float tc = tanhf(p.c_cur[ui]);
+      const float dh = acc[i][j] + p.dh_head[ui];
+      const float dcv = (p.first ? 0.f : p.dc[ui]) + dh * og * (1.f - tc * tc);
+      float4 d;
+      d.x = dcv * gg * ig * (1.f - ig);
+      d.y = dcv * p.c_prev[ui] * fg * (1.f - fg);
+      d.z = dcv * ig * (1.f - gg * gg);
+      d.w = dh * tc * og * (1.f - og);
+      *reinterpret_cast<float4*>(p.dg + ui * 4) = d;
+      p.dc[ui] = dcv * fg;
+    }
+  }
+}
+
+// ---- ring geometry -------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ long long ring_slot(const srlx_r2d2& r, long long pos, int e) {
+  return (pos % r.env.ring_rows) * (long long)r.env.n_envs + e;
+}
+// position held by ring row `row` of column e, or -1 if the row has never been written
+__device__ __forceinline__ long long ring_pos_of_row(const srlx_r2d2& r, int row, long long cur) {
+  const int R = r.env.ring_rows;
+  if (cur <= R) return row < cur ? row : -1;
+  const long long last = cur - 1;
+  long long back = (last - row) % R;
+  if (back < 0) back += R;
+  return last - back;
+}
+// an anchor is sampleable while the burnin + seq_len rows in front of it have not been overwritten
+__device__ __forceinline__ bool ring_anchor_valid(const srlx_r2d2& r, long long pos, long long cur) {
+  if (pos < 0) return false;
+  const int R = r.env.ring_rows, W = r.burnin + r.seq_len;
+  return cur <= R || pos - (W - 1) >= cur - R;
+}
+
+// ---- rollout ---------------------------------------------------------------------------------------------------------------------------
+// Worker.on_reset + the state half of on_step: reset-if-needed, observation -> network input and ring row
+__global__ void r2d2_pre_kernel(const __grid_constant__ srlx_r2d2 r, const int training) {
+  const srlx_engine& eng = r.env;
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= eng.n_envs) return;
+  const int D = eng.obs_dim, K = D + r.lstm_units + 1;
+  double* st = eng.env_state + (size_t)e * 4;
+  unsigned char was_reset = 0;
+  if (eng.env_needs_reset[e]) {
+    const uint32_t ep = eng.env_episode[e];
+    env_reset(eng, (uint32_t)e, ep, st);
+    eng.env_episode[e] = ep + 1;
+    eng.env_step_num[e] = 0;
+    eng.env_ep_reward[e] = 0.0;
+    eng.env_needs_reset[e] = 0;
+    was_reset = 1;
+  }
+  r.roll_reset[e] = was_reset;
+  float obs[SRLX_MAX_OBS];
+  env_obs(eng, st, obs);
+  float* x = r.roll_xh + (size_t)e * K;
+  for (int d = 0; d < D; ++d) x[d] = obs[d];
+  x[K - 1] = 1.f;
+  if (training) {
+    const long long slot = ring_slot(r, r.cursor[e], e);
+    for (int d = 0; d < D; ++d) r.ring_obs[slot * D + d] = obs[d];
+    r.ring_tstep[slot] = eng.env_step_num[e];
+  }
+}
+
+// LSTM state: zero at an episode's first step (get_initial_state, r2d2.py:243), else the h_t / c_t the previous step left in roll_h /
+// roll_c; stored with the row BEFORE the step consumes the state (recent_hidden_states[i] belongs to _recent_states[i], :232-283)
+__global__ void r2d2_hidden_kernel(const __grid_constant__ srlx_r2d2 r, const int training) {
+  const srlx_engine& eng = r.env;
+  const int u = r.lstm_units, D = eng.obs_dim, K = D + u + 1;
+  const long long n = (long long)eng.n_envs * u;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int e = (int)(i / u), j = (int)(i - (long long)e * u);
+    float h = r.roll_h[(size_t)e * (u + 1) + j], c = r.roll_c[i];
+    if (r.roll_reset[e]) { h = 0.f; c = 0.f; r.roll_c[i] = 0.f; }
+    r.roll_xh[(size_t)e * K + D + j] = h;
+    if (j == 0) r.roll_h[(size_t)e * (u + 1) + u] = 1.f;
+    if (training) {
+      const long long slot = ring_slot(r, r.cursor[e], e);
+      r.ring_h[slot * u + j] = h;
+      r.ring_c[slot * u + j] = c;
+    }
+  }
+}
+
+__device__ __forceinline__ void dueling_combine(const float* o, int A, int dueling, float* q) {
+  if (dueling == SRLX_DUEL_NONE) {
+    for (int a = 0; a < A; ++a) q[a] = o[a];
+    return;
+  }
+  const float v = o[0];
+  float red = 0.f;
+  if (dueling == SRLX_DUEL_AVERAGE) {
+    for (int a = 0; a < A; ++a) red += o[1 + a];
+    red /= (float)A;
+  } else if (dueling == SRLX_DUEL_MAX) {
+    red = o[1];
+    for (int a = 1; a < A; ++a) red = fmaxf(red, o[1 + a]);
+  }
+  for (int a = 0; a < A; ++a) q[a] = v + o[1 + a] - red;
+}
+
+// Worker.policy (epsilon-greedy probabilities, funcs.calc_epsilon_greedy_probs / random_choice_by_probs, srl/rl/functions.py:188-214) +
+// env.step + the transition half of Worker.on_step, the padded tail at an episode's end included (r2d2.py:285-303)
+__global__ void r2d2_act_kernel(const __grid_constant__ srlx_r2d2 r, const int training) {
+  const srlx_engine& eng = r.env;
+  __shared__ unsigned long long s_episodes, s_eplen, s_rows;
+  __shared__ double s_epreward;
+  if (threadIdx.x == 0) { s_episodes = 0; s_eplen = 0; s_rows = 0; s_epreward = 0.0; }
+  __syncthreads();
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < eng.n_envs) {
+    const int A = eng.n_actions, D = eng.obs_dim, R = eng.ring_rows;
+    const int n_out = r.head_out[r.n_head - 1];
+    const uint64_t g = eng.state->vec_steps;
+    float q[SRLX_MAX_ACTIONS];
+    dueling_combine(r.roll_act[r.n_head - 1] + (size_t)e * n_out, A, r.dueling, q);
+    if (eng.dbg_q) for (int a = 0; a < A; ++a) eng.dbg_q[(size_t)e * A + a] = q[a];
+    const double eps = training ? eng.epsilon : r.test_epsilon;
+    float qmax = q[0];
+    for (int a = 1; a < A; ++a) qmax = fmaxf(qmax, q[a]);
+    int nmax = 0;
+    for (int a = 0; a < A; ++a) nmax += (q[a] == qmax);
+    double probs[SRLX_MAX_ACTIONS], total = 0.0;
+    for (int a = 0; a < A; ++a) {
+      double pr = __ddiv_rn(eps, (double)A);
+      if (q[a] == qmax) pr = __dadd_rn(pr, __ddiv_rn(__dsub_rn(1.0, eps), (double)nmax));
+      probs[a] = pr;
+      total = __dadd_rn(total, pr);
+    }
+    const uint4 w = philox(eng.seed, STREAM_POLICY, (uint32_t)e, (uint32_t)g, (uint32_t)(g >> 32));
+    const double rr = __dmul_rn(u01_f64(w.x, w.y), total);
+    int action = A - 1;
+    double num = 0.0;
+    for (int a = 0; a < A; ++a) {
+      num = __dadd_rn(num, probs[a]);
+      if (rr <= num) { action = a; break; }
+    }
+    if (eng.dbg_action) eng.dbg_action[e] = action;
+    double* st = eng.env_state + (size_t)e * 4;
+    bool terminated = false;
+    const double rew = env_step(eng, (uint32_t)e, g, action, st, terminated);
+    const int step_num = eng.env_step_num[e] + 1;
+    eng.env_step_num[e] = step_num;
+    bool truncated = step_num >= eng.trunc_limit;
+    if (eng.trunc_overrides_term) terminated = terminated && !truncated;
+    else truncated = truncated && !terminated;
+    const bool done = terminated || truncated;
+    const double ep_reward = eng.env_ep_reward[e] + rew;
+    eng.env_ep_reward[e] = ep_reward;
+    if (training) {
+      const uint32_t c0 = r.cursor[e];
+      float nobs[SRLX_MAX_OBS];
+      env_obs(eng, st, nobs);
+      long long slot = ring_slot(r, c0, e);
+      for (int d = 0; d < D; ++d) r.ring_next_obs[slot * D + d] = nobs[d];
+      r.ring_action[slot] = action;
+      r.ring_prob[slot] = probs[action];
+      r.ring_reward[slot] = (rew + eng.reward_shift) * eng.reward_scale;  // worker_run.py:348
+      r.ring_done[slot] = terminated ? 1 : 0;
+      uint32_t n_new = 1;
+      if (done) {
+        for (int m = 1; m < r.seq_len; ++m) {
+          slot = ring_slot(r, (long long)c0 + m, e);
+          for (int d = 0; d < D; ++d) {
+            r.ring_obs[slot * D + d] = (m == 1) ? nobs[d] : 0.f;
+            r.ring_next_obs[slot * D + d] = 0.f;
+          }
+          const uint4 pw = philox(eng.seed, STREAM_PAD_ACTION, (uint32_t)e, c0 + (uint32_t)m, R2D2_PAD_TAIL);
+          r.ring_action[slot] = (int)u_below(pw.x, (uint32_t)A);
+          r.ring_prob[slot] = 1.0 / (double)A;
+          r.ring_reward[slot] = 0.0;
+          r.ring_done[slot] = 1;
+          r.ring_tstep[slot] = step_num - 1 + m;
+        }
+        n_new = (uint32_t)r.seq_len;
+      }
+      r.cursor[e] = c0 + n_new;
+      r.new_c0[e] = c0;
+      r.new_n[e] = n_new;
+      const unsigned long long before = c0 < (uint32_t)R ? c0 : (uint32_t)R, after = (c0 + n_new) < (uint32_t)R ? (c0 + n_new) : (uint32_t)R;
+      if (after > before) atomicAdd(&s_rows, after - before);
+      atomicMax((unsigned long long*)&eng.state->reserved[0], (unsigned long long)(c0 + n_new));
+    }
+    if (done) {
+      eng.env_needs_reset[e] = 1;
+      if (eng.env_last_ep_len) {
+        if (eng.env_first_ep_reward && eng.env_last_ep_len[e] == 0) eng.env_first_ep_reward[e] = ep_reward;
+        eng.env_last_ep_len[e] = step_num;
+      }
+      atomicAdd(&s_episodes, 1ull);
+      atomicAdd(&s_eplen, (unsigned long long)step_num);
+      atomicAdd(&s_epreward, ep_reward);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (s_episodes) {
+      atomicAdd((unsigned long long*)&eng.state->episode_count, s_episodes);
+      atomicAdd((unsigned long long*)&eng.state->episode_len_sum, s_eplen);
+      atomicAdd(&eng.state->episode_reward_sum, s_epreward);
+    }
+    if (s_rows) atomicAdd((unsigned long long*)&eng.state->mem_size, s_rows);
+  }
+}
+
+__global__ void r2d2_step_count_kernel(srlx_state* st, int E) {
+  st->vec_steps += 1;
+  st->total_step += (uint64_t)E;
+}
+
+// ProportionalMemory.add for the rows of one vector step (proportional_memory.py:120-129): new leaves take max_priority; the anchor
+// whose window the new row cuts (pos - R + W - 1) drops to 0 so that the sampler's zero-priority rejection skips it.  Entries are laid
+// out env-major in row order and applied in that order (tree_update_batch: the reference's sequential fp64 association).
+__global__ void __launch_bounds__(1024) r2d2_add_kernel(const __grid_constant__ srlx_r2d2 r) {
+  extern __shared__ __align__(16) unsigned char tree_smem[];
+  TreeHashScratch* hs = reinterpret_cast<TreeHashScratch*>(tree_smem);
+  __shared__ int s_scan[1024];
+  __shared__ int s_base;
+  __shared__ int64_t s_idx[kTreeHashChunk];
+  __shared__ double s_pri[kTreeHashChunk];
+  const srlx_engine& eng = r.env;
+  const int E = eng.n_envs, R = eng.ring_rows, W = r.burnin + r.seq_len, tid = threadIdx.x;
+  const long long cap = (long long)R * E;
+  const double maxp = eng.state->max_priority;
+  if (tid == 0) s_base = 0;
+  __syncthreads();
+  for (int e0 = 0; e0 < E; e0 += 1024) {
+    const int e = e0 + tid;
+    int cnt = 0;
+    uint32_t c0 = 0, n = 0;
+    if (e < E) {
+      c0 = r.new_c0[e];
+      n = r.new_n[e];
+      for (uint32_t j = 0; j < n; ++j) cnt += 1 + ((long long)c0 + j >= R ? 1 : 0);
+    }
+    s_scan[tid] = cnt;
+    __syncthreads();
+    for (int off = 1; off < 1024; off <<= 1) {  // inclusive Hillis-Steele scan
+      const int v = tid >= off ? s_scan[tid - off] : 0;
+      __syncthreads();
+      s_scan[tid] += v;
+      __syncthreads();
+    }
+    int o = s_base + s_scan[tid] - cnt;
+    for (uint32_t j = 0; j < n; ++j) {
+      const long long pos = (long long)c0 + j;
+      if (pos >= R) {
+        r.add_idx[o] = ring_slot(r, pos - R + W - 1, e) + cap - 1;
+        r.add_pri[o] = 0.0;
+        ++o;
+      }
+      r.add_idx[o] = ring_slot(r, pos, e) + cap - 1;
+      r.add_pri[o] = maxp;
+      ++o;
+    }
+    __syncthreads();
+    if (tid == 1023) s_base += s_scan[1023];
+    __syncthreads();
+  }
+  const int total = s_base;
+  for (int base = 0; base < total; base += kTreeHashChunk) {
+    const int m = min(kTreeHashChunk, total - base);
+    if (tid < m) { s_idx[tid] = r.add_idx[base + tid]; s_pri[tid] = r.add_pri[base + tid]; }
+    __syncthreads();
+    tree_update_prepare(eng.tree, s_idx, m, hs);
+    tree_update_apply(eng.tree, s_pri, m, hs, nullptr, 0);
+  }
+}
+
+// ---- trainer: sample --------------------------------------------------------------------------------------------------------------------
+// ReplayBuffer.sample (replay_buffer.py:34-36: random.sample, distinct items): uniform (row, env) draws, rejected when the row is not a
+// valid anchor or was already picked, accepted in attempt order
+__global__ void __launch_bounds__(256) r2d2_sample_uniform_kernel(const __grid_constant__ srlx_r2d2 r, const Gate gate) {
+  if (gate.closed()) return;
+  const srlx_engine& eng = r.env;
+  __shared__ long long s_cand[256];
+  __shared__ int s_n;
+  const int B = eng.batch_size, E = eng.n_envs, R = eng.ring_rows, tid = threadIdx.x;
+  const uint64_t step = eng.state->train_count;
+  const unsigned long long maxc = eng.state->reserved[0];
+  const uint32_t rows = (uint32_t)(maxc < (unsigned long long)R ? maxc : (unsigned long long)R);
+  if (tid == 0) s_n = 0;
+  __syncthreads();
+  for (int round = 0; round < 256 && s_n < B; ++round) {
+    const uint32_t a = (uint32_t)round * 256u + (uint32_t)tid;
+    const uint4 w = philox(eng.seed, STREAM_UNIFORM_SAMPLE, a, (uint32_t)step, (uint32_t)(step >> 32));
+    const int row = (int)u_below(w.x, rows), e = (int)u_below(w.y, (uint32_t)E);
+    const long long cur = r.cursor[e];
+    const long long pos = ring_pos_of_row(r, row, cur);
+    s_cand[tid] = ring_anchor_valid(r, pos, cur) ? (long long)row * E + e : -1;
+    __syncthreads();
+    if (tid == 0) {
+      int n = s_n;
+      for (int i = 0; i < 256 && n < B; ++i) {
+        const long long c = s_cand[i];
+        if (c < 0) continue;
+        bool dup = false;
+        for (int j = 0; j < n; ++j) dup |= (r.sel[j] == c);
+        if (!dup) { r.sel[n] = c; r.weights[n] = 1.0f; ++n; }
+      }
+      s_n = n;
+    }
+    __syncthreads();
+  }
+}
+
+// ProportionalMemory.sample (proportional_memory.py:131-169) on the tree over all R*E rows
+__global__ void __launch_bounds__(1024) r2d2_sample_per_kernel(const __grid_constant__ srlx_r2d2 r, const Gate gate) {
+  if (gate.closed()) return;
+  const srlx_engine& eng = r.env;
+  __shared__ int64_t s_idx[SRLX_MAX_BATCH];
+  __shared__ double s_pri[SRLX_MAX_BATCH];
+  __shared__ double s_tmp[SRLX_MAX_BATCH];
+  __shared__ float s_w[SRLX_MAX_BATCH];
+  __shared__ unsigned long long retries;
+  if (threadIdx.x == 0) retries = 0;
+  __syncthreads();
+  const long long cap = (long long)eng.ring_rows * eng.n_envs;
+  const uint64_t step = eng.state->train_count;
+  const double total = __ldcg(eng.tree);
+  // PriorityReplayBuffer.step is the train_count the PREVIOUS update handed to memory.update (priority_replay_buffer.py:228-250)
+  const double beta_step = step > 0 ? (double)(step - 1) : 0.0;
+  double beta = eng.per_beta_initial + (1.0 - eng.per_beta_initial) * beta_step / eng.per_beta_steps;
+  if (beta > 1.0) beta = 1.0;
+  per_sample_block(eng.tree, 2 * cap - 1, total, eng.batch_size, eng.seed, step, nullptr, 10000, eng.has_duplicate, s_idx, s_pri, s_tmp, &retries);
+  per_weights_block(total, (double)eng.state->mem_size, beta, eng.batch_size, s_pri, s_tmp, s_w);
+  for (int i = threadIdx.x; i < eng.batch_size; i += blockDim.x) { r.sel[i] = s_idx[i]; r.weights[i] = s_w[i]; }
+  if (threadIdx.x == 0) eng.state->sample_retries += retries;
+}
+
+// the batch as _train_on_batches lays it out (r2d2.py:109-133): W + 1 states per item (padding in front of an episode's first step
+// rebuilt by index: dummy state 0, random action, probability 1/A, reward 0, not done, zero LSTM state), time-major for the unroll
+__global__ void __launch_bounds__(128) r2d2_gather_kernel(const __grid_constant__ srlx_r2d2 r, const Gate gate) {
+  if (gate.closed()) return;
+  const srlx_engine& eng = r.env;
+  const int b = blockIdx.x, B = eng.batch_size, E = eng.n_envs, D = eng.obs_dim, u = r.lstm_units, A = eng.n_actions;
+  const int W = r.burnin + r.seq_len, S = r.seq_len, K = D + u + 1, tid = threadIdx.x;
+  const long long cap = (long long)eng.ring_rows * E;
+  long long slot = r.sel[b];
+  if (eng.mem_kind == SRLX_MEM_PROPORTIONAL) slot -= cap - 1;
+  const int e = (int)(slot % E), row = (int)(slot / E);
+  const long long cur = r.cursor[e];
+  const long long p = ring_pos_of_row(r, row, cur);
+  const long long ep_start = p - r.ring_tstep[slot];
+  const size_t zx = (size_t)(W + 2) * B * K, zc = (size_t)(W + 2) * B * u;
+  for (int w = tid; w < (W + 1) * D; w += blockDim.x) {
+    const int i = w / D, d = w - i * D;
+    float v;
+    if (i == W) v = r.ring_next_obs[slot * D + d];
+    else {
+      const long long pos = p - (W - 1) + i;
+      v = pos < ep_start ? 0.f : r.ring_obs[ring_slot(r, pos, e) * D + d];
+    }
+    const size_t o = ((size_t)i * B + b) * K + d;
+    r.xh[o] = v;
+    r.xh[zx + o] = v;
+  }
+  const long long pos0 = p - (W - 1);
+  const bool pre0 = pos0 < ep_start;
+  const long long s0 = pre0 ? 0 : ring_slot(r, pos0, e);
+  for (int j = tid; j < u; j += blockDim.x) {
+    const float h = pre0 ? 0.f : r.ring_h[s0 * u + j], c = pre0 ? 0.f : r.ring_c[s0 * u + j];
+    r.xh[(size_t)b * K + D + j] = h;
+    r.xh[zx + (size_t)b * K + D + j] = h;
+    r.cbuf[(size_t)b * u + j] = c;
+    r.cbuf[zc + (size_t)b * u + j] = c;
+  }
+  for (int k = tid; k < S; k += blockDim.x) {
+    const long long pos = p - (S - 1) + k;
+    const size_t o = (size_t)b * S + k;
+    if (pos < ep_start) {
+      const uint4 pw = philox(eng.seed, STREAM_PAD_ACTION, (uint32_t)e, (uint32_t)pos, R2D2_PAD_PRE);
+      r.b_actions[o] = (int)u_below(pw.x, (uint32_t)A);
+      r.b_mu[o] = 1.0 / (double)A;
+      r.b_rewards[o] = 0.0;
+      r.b_dones[o] = 0;
+    } else {
+      const long long s = ring_slot(r, pos, e);
+      r.b_actions[o] = r.ring_action[s];
+      r.b_mu[o] = r.ring_prob[s];
+      r.b_rewards[o] = r.ring_reward[s];
+      r.b_dones[o] = r.ring_done[s];
+    }
+  }
+}
+
+// head output rows (t, b) -> Q [z][b][t][a] for the reference's per-sequence loop
+__global__ void r2d2_combine_kernel(const __grid_constant__ srlx_r2d2 r, const Gate gate) {
+  if (gate.closed()) return;
+  const int B = r.env.batch_size, S1 = r.seq_len + 1, A = r.env.n_actions, n_out = r.head_out[r.n_head - 1];
+  const int rows = S1 * B;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 2 * rows) return;
+  const int z = i / rows, row = i - z * rows, t = row / B, b = row - t * B;
+  float q[SRLX_MAX_ACTIONS];
+  dueling_combine(r.act[r.n_head - 1] + ((size_t)z * rows + row) * n_out, A, r.dueling, q);
+  float* out = r.q + (((size_t)z * B + b) * S1 + t) * A;
+  for (int a = 0; a < A; ++a) out[a] = q[a];
+}
+
+// keras.losses.Huber()(target * w, q_onehot * w) (r2d2.py:206-209): mean over (B, seq_len); gradient wrt the head outputs
+__global__ void __launch_bounds__(256) r2d2_loss_kernel(const __grid_constant__ srlx_r2d2 r, const Gate gate) {
+  if (gate.closed()) return;
+  __shared__ double s_sum[256];
+  const int B = r.env.batch_size, S = r.seq_len, S1 = S + 1, A = r.env.n_actions, n_out = r.head_out[r.n_head - 1], tid = threadIdx.x;
+  const float inv_n = 1.0f / (float)(B * S);
+  double part = 0.0;
+  for (int i = tid; i < B * S; i += blockDim.x) {
+    const int t = i / B, b = i - t * B;  // row (t, b) of the head
+    const int a = r.b_actions[(size_t)b * S + t];
+    const float w = r.weights[b];
+    const float* qrow = r.q + ((size_t)b * S1 + t) * A;
+    const float y_pred = qrow[a] * w;
+    const float y_true = (float)(r.b_target[(size_t)b * S + t] * (double)w);
+    const float err = y_pred - y_true, ae = fabsf(err);
+    part += (ae <= 1.0f) ? 0.5 * (double)err * (double)err : (double)ae - 0.5;
+    const float gq = w * fminf(fmaxf(err, -1.0f), 1.0f) * inv_n;
+    float* d = r.dact[r.n_head - 1] + (size_t)i * n_out;
+    if (r.dueling == SRLX_DUEL_NONE) {
+      for (int j = 0; j < A; ++j) d[j] = (j == a) ? gq : 0.f;
+    } else {
+      d[0] = gq;
+      int amax = 0;
+      if (r.dueling == SRLX_DUEL_MAX) {
+        const float* o = r.act[r.n_head - 1] + (size_t)i * n_out;
+        for (int j = 1; j < A; ++j) if (o[1 + j] > o[1 + amax]) amax = j;
+      }
+      for (int j = 0; j < A; ++j) {
+        float v = (j == a) ? gq : 0.f;
+        if (r.dueling == SRLX_DUEL_AVERAGE) v -= gq / (float)A;
+        else if (r.dueling == SRLX_DUEL_MAX && j == amax) v -= gq;
+        d[1 + j] = v;
+      }
+    }
+  }
+  s_sum[tid] = part;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (tid < s) s_sum[tid] += s_sum[tid + s];
+    __syncthreads();
+  }
+  if (tid == 0) {
+    const double loss = s_sum[0] / (double)(B * S);
+    r.env.state->last_loss = loss;
+    r.env.state->loss_sum += loss;
+  }
+}
+
+// keras Adam (optimizers.Adam defaults: beta 0.9 / 0.999, epsilon 1e-7 outside the root): alpha = lr sqrt(1 - b2^t) / (1 - b1^t)
+__global__ void r2d2_adam_kernel(const __grid_constant__ srlx_r2d2 r, const Gate gate) {
+  if (gate.closed()) return;
+  const srlx_engine& eng = r.env;
+  const double t1 = (double)(eng.state->adam_step + 1);
+  const float alpha = (float)(eng.lr * sqrt(1.0 - pow(eng.adam_beta2, t1)) / (1.0 - pow(eng.adam_beta1, t1)));
+  const float b1 = (float)eng.adam_beta1, b2 = (float)eng.adam_beta2, eps = (float)eng.adam_eps;
+  const int lo = r.head_off[r.n_head - 1], ld = r.head_k[r.n_head - 1] + 1, H = r.duel_hidden;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < r.n_params; i += gridDim.x * blockDim.x) {
+    if (H > 0 && i >= lo) {  // structural zeros of the dueling output layer: V reads [0, H), the advantages [H, 2H)
+      const int row = (i - lo) / ld, col = (i - lo) - row * ld;
+      if (row == 0 ? (col >= H && col < 2 * H) : col < H) continue;
+    }
+    const float g = r.grads[i];
+    const float m = r.adam_m[i] + (1.f - b1) * (g - r.adam_m[i]);
+    const float v = r.adam_v[i] + (1.f - b2) * (g * g - r.adam_v[i]);
+    r.adam_m[i] = m;
+    r.adam_v[i] = v;
+    r.params[i] -= alpha * m / (sqrtf(v) + eps);
+  }
+}
+
+// memory.update(update_args, td_errors, train_count) (r2d2.py:97; proportional_memory.py:171-177 on the mean TD error of a sequence)
+__global__ void __launch_bounds__(1024) r2d2_priority_kernel(const __grid_constant__ srlx_r2d2 r, const Gate gate) {
+  if (gate.closed()) return;
+  extern __shared__ __align__(16) unsigned char tree_smem[];
+  TreeHashScratch* hs = reinterpret_cast<TreeHashScratch*>(tree_smem);
+  __shared__ int64_t s_idx[SRLX_MAX_BATCH];
+  __shared__ double s_pri[SRLX_MAX_BATCH];
+  const srlx_engine& eng = r.env;
+  const int B = eng.batch_size;
+  for (int i = threadIdx.x; i < B; i += blockDim.x) {
+    s_idx[i] = r.sel[i];
+    s_pri[i] = pow(fabs(r.b_tdmean[i]) + eng.per_epsilon, eng.per_alpha);
+  }
+  __syncthreads();
+  tree_update_batch(eng.tree, s_idx, s_pri, B, hs);
+  if (threadIdx.x == 0) {
+    double mp = eng.state->max_priority;
+    for (int i = 0; i < B; ++i) mp = (mp < s_pri[i]) ? s_pri[i] : mp;
+    eng.state->max_priority = mp;
+  }
+}
+
+// hard target sync when train_count % interval == 0, evaluated BEFORE the increment (r2d2.py:100-104)
+__global__ void r2d2_sync_kernel(const __grid_constant__ srlx_r2d2 r, const Gate gate) {
+  if (gate.closed()) return;
+  if (r.env.state->train_count % (uint64_t)r.env.target_update_interval != 0) return;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < r.n_params; i += gridDim.x * blockDim.x) r.target[i] = r.params[i];
+}
+
+__global__ void r2d2_finish_kernel(const __grid_constant__ srlx_r2d2 r, const Gate gate) {
+  if (gate.closed()) return;
+  srlx_state* st = r.env.state;
+  if (st->train_count % (uint64_t)r.env.target_update_interval == 0) st->sync_count += 1;
+  st->train_count += 1;
+  st->adam_step += 1;
+}
+
+// copy rows [n][w] between strided buffers (srlx_r2d2_forward staging)
+__global__ void r2d2_copy_rows_kernel(const float* __restrict__ src, long long ld_s, float* __restrict__ dst, long long ld_d, long long n, int w) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n * w; i += (long long)gridDim.x * blockDim.x) {
+    const long long row = i / w;
+    const int j = (int)(i - row * w);
+    dst[row * ld_d + j] = src[row * ld_s + j];
+  }
+}
+__global__ void r2d2_combine_rows_kernel(const float* __restrict__ o, int n_out, int A, int dueling, long long n, float* __restrict__ q) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float qq[SRLX_MAX_ACTIONS];
+  dueling_combine(o + i * n_out, A, dueling, qq);
+  for (int a = 0; a < A; ++a) q[i * A + a] = qq[a];
+}
+
+
+// ---- host side ------------------------------------------------------------------------------------------------------------------------------
+static int r2d2_check(const srlx_r2d2* r) {
+  SRLX_REQUIRE(r != nullptr, "r2d2 is NULL");
+  const srlx_engine& e = r->env;
+  SRLX_REQUIRE(e.n_envs >= 1 && e.obs_dim >= 1 && e.obs_dim <= 4, "n_envs / obs_dim out of range");
+  SRLX_REQUIRE(e.env_id == SRLX_ENV_GRID || e.env_id == SRLX_ENV_CARTPOLE || e.env_id == SRLX_ENV_PENDULUM, "unknown env_id %d", e.env_id);
+  SRLX_REQUIRE(e.n_actions >= 1 && e.n_actions <= SRLX_MAX_ACTIONS, "n_actions out of range");
+  SRLX_REQUIRE(r->lstm_units >= 1 && r->burnin >= 0 && r->seq_len >= 1 && r->seq_len <= 128, "lstm_units / burnin / seq_len (<= 128) out of range");
+  SRLX_REQUIRE(r->n_head >= 1 && r->n_head <= SRLX_MAX_LAYERS, "head layers out of range");
+  SRLX_REQUIRE(r->head_k[0] == r->lstm_units, "the first head layer reads the LSTM output");
+  SRLX_REQUIRE(r->head_out[r->n_head - 1] == (r->dueling == SRLX_DUEL_NONE ? e.n_actions : 1 + e.n_actions), "output layer width does not match");
+  SRLX_REQUIRE(e.state && e.env_state && e.env_step_num && e.env_episode && e.env_ep_reward && e.env_needs_reset, "env buffer pointer is NULL");
+  SRLX_REQUIRE(r->params && r->target, "params / target pointer is NULL");
+  return 0;
+}
+
+// one LSTM step + head on n rows: xh_in [n][K] -> h into h_out (row stride ld_h, which must be followed by a 1 at column u: the head
+// reads [h | 1]), c in place, head activations -> acts[l]
+static int r2d2_net_step(const srlx_r2d2* r, const float* W, const float* xh_in, float* h_out, long long ld_h, float* c, float* const* acts,
+                         int n, cudaStream_t s) {
+  const int D = r->env.obs_dim, u = r->lstm_units, K = D + u + 1;
+  LstmFwdP lp{};
+  lp.xh = xh_in; lp.z_xh = 0; lp.W0 = W + r->lstm_off; lp.W1 = nullptr; lp.c_in = c; lp.c_out = c; lp.z_c = 0;
+  lp.h_out = h_out; lp.ld_h = ld_h; lp.z_h = 0; lp.gates = nullptr; lp.M = n; lp.u = u; lp.K = K; lp.gate = Gate{nullptr, 0};
+  if (n <= 32) lstm_fwd_kernel<32, 2><<<dim3((4 * u + 31) / 32, (n + 31) / 32, 1), 128, 0, s>>>(lp);
+  else lstm_fwd_kernel<64, 4><<<dim3((4 * u + 31) / 32, (n + 63) / 64, 1), 128, 0, s>>>(lp);
+  count_launch();
+  const float* in = h_out;
+  long long ld_in = ld_h;
+  for (int l = 0; l < r->n_head; ++l) {
+    const bool last = l == r->n_head - 1;
+    GemmP g{};
+    g.A = in; g.sa_m = ld_in; g.sa_k = 1;
+    g.B = W + r->head_off[l]; g.sb_k = 1; g.sb_n = r->head_k[l] + 1;
+    g.C = acts[l]; g.ldc = last ? r->head_out[l] : r->head_out[l] + 1;
+    g.M = n; g.N = r->head_out[l]; g.K = r->head_k[l] + 1; g.relu = last ? 0 : 1;
+    g.gate = Gate{nullptr, 0};
+    launch_gemm(g, 1, s);
+    in = acts[l];
+    ld_in = r->head_out[l] + 1;
+  }
+  return 0;
+}
+
+}  // namespace srlx
+
+using namespace srlx;
+
+extern "C" size_t srlx_sizeof_r2d2(void) { return sizeof(srlx_r2d2); }
+
+extern "C" int srlx_sgemm(const float* a_dev, long long sa_m, long long sa_k, const float* b_dev, long long sb_k, long long sb_n, float* c_dev,
+                          long long ldc, int M, int N, int K, int relu, int accumulate, uintptr_t cuda_stream) {
+  SRLX_REQUIRE(a_dev && b_dev && c_dev, "srlx_sgemm: NULL buffer");
+  SRLX_REQUIRE(M >= 0 && N >= 0 && K >= 0, "srlx_sgemm: negative size");
+  GemmP g{};
+  g.A = a_dev; g.sa_m = sa_m; g.sa_k = sa_k; g.B = b_dev; g.sb_k = sb_k; g.sb_n = sb_n; g.C = c_dev; g.ldc = ldc;
+  g.M = M; g.N = N; g.K = K; g.relu = relu; g.accumulate = accumulate; g.gate = Gate{nullptr, 0};
+  launch_gemm(g, 1, (cudaStream_t)cuda_stream);
+  SRLX_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int srlx_r2d2_vec_step(const srlx_r2d2* r, int training, uintptr_t cuda_stream) {
+  if (int rc = r2d2_check(r)) return rc;
+  const srlx_engine& eng = r->env;
+  cudaStream_t s = (cudaStream_t)cuda_stream;
+  SRLX_REQUIRE(r->roll_xh && r->roll_h && r->roll_c && r->roll_reset, "rollout workspace pointer is NULL");
+  for (int l = 0; l < r->n_head; ++l) SRLX_REQUIRE(r->roll_act[l] != nullptr, "roll_act[%d] is NULL", l);
+  const bool per = eng.mem_kind == SRLX_MEM_PROPORTIONAL;
+  if (training) {
+    SRLX_REQUIRE(r->cursor && r->ring_obs && r->ring_next_obs && r->ring_action && r->ring_prob && r->ring_reward && r->ring_done &&
+                 r->ring_tstep && r->ring_h && r->ring_c && r->new_c0 && r->new_n, "replay ring pointer is NULL");
+    SRLX_REQUIRE(eng.ring_rows >= 2 * (r->burnin + r->seq_len), "ring_rows must be >= 2 * (burnin + seq_len)");
+    SRLX_REQUIRE(!per || (eng.tree && r->add_idx && r->add_pri), "proportional memory needs tree / add_idx / add_pri");
+  }
+  const int E = eng.n_envs, u = r->lstm_units;
+  r2d2_pre_kernel<<<(E + 127) / 128, 128, 0, s>>>(*r, training);
+  const long long nh = (long long)E * u;
+  const long long hb = (nh + 255) / 256;
+  r2d2_hidden_kernel<<<(unsigned)(hb < 2368 ? hb : 2368), 256, 0, s>>>(*r, training);
+  count_launch(2);
+  r2d2_net_step(r, r->params, r->roll_xh, r->roll_h, u + 1, r->roll_c, r->roll_act, E, s);
+  r2d2_act_kernel<<<(E + 127) / 128, 128, 0, s>>>(*r, training);
+  count_launch();
+  if (training && per) {
+    SRLX_CHECK_CUDA(cudaFuncSetAttribute(r2d2_add_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TreeHashScratch)));
+    r2d2_add_kernel<<<1, 1024, sizeof(TreeHashScratch), s>>>(*r);
+    count_launch();
+  }
+  r2d2_step_count_kernel<<<1, 1, 0, s>>>(eng.state, E);
+  count_launch();
+  SRLX_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int srlx_r2d2_forward(const srlx_r2d2* r, int use_target, const float* obs_dev, const float* h_dev, const float* c_dev, uint32_t n,
+                                 float* q_out_dev, float* h_out_dev, float* c_out_dev, uintptr_t cuda_stream) {
+  if (int rc = r2d2_check(r)) return rc;
+  const srlx_engine& eng = r->env;
+  SRLX_REQUIRE(obs_dev && h_dev && c_dev && q_out_dev && h_out_dev && c_out_dev, "srlx_r2d2_forward: NULL buffer");
+  SRLX_REQUIRE(n >= 1 && n <= (uint32_t)eng.batch_size, "srlx_r2d2_forward: n = %u exceeds batch_size %d (the call runs in the learner workspace)", n, eng.batch_size);
+  SRLX_REQUIRE(r->xh && r->cbuf, "learner workspace pointer is NULL");
+  for (int l = 0; l < r->n_head; ++l) SRLX_REQUIRE(r->act[l] != nullptr, "act[%d] is NULL", l);
+  cudaStream_t s = (cudaStream_t)cuda_stream;
+  const int D = eng.obs_dim, u = r->lstm_units, K = D + u + 1, B = eng.batch_size;
+  float* x0 = r->xh;                      // time row 0: input
+  float* x1 = r->xh + (size_t)B * K;      // time row 1: receives h (followed by the row's trailing 1)
+  const unsigned nb = (unsigned)(((long long)n * (u > D ? u : D) + 255) / 256);
+  r2d2_copy_rows_kernel<<<nb, 256, 0, s>>>(obs_dev, D, x0, K, n, D);
+  r2d2_copy_rows_kernel<<<nb, 256, 0, s>>>(h_dev, u, x0 + D, K, n, u);
+  r2d2_copy_rows_kernel<<<nb, 256, 0, s>>>(c_dev, u, r->cbuf, u, n, u);
+  count_launch(3);
+  r2d2_net_step(r, use_target ? r->target : r->params, x0, x1 + D, K, r->cbuf, r->act, (int)n, s);
+  r2d2_copy_rows_kernel<<<nb, 256, 0, s>>>(x1 + D, K, h_out_dev, u, n, u);
+  r2d2_copy_rows_kernel<<<nb, 256, 0, s>>>(r->cbuf, u, c_out_dev, u, n, u);
+  const int n_out = r->head_out[r->n_head - 1];
+  r2d2_combine_rows_kernel<<<(n + 127) / 128, 128, 0, s>>>(r->act[r->n_head - 1], n_out, eng.n_actions, r->dueling, n, q_out_dev);
+  count_launch(3);
+  SRLX_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int srlx_r2d2_learn(const srlx_r2d2* r, uint32_t n_updates, uintptr_t cuda_stream) {
+  if (int rc = r2d2_check(r)) return rc;
+  const srlx_engine& eng = r->env;
+  cudaStream_t s = (cudaStream_t)cuda_stream;
+  const bool per = eng.mem_kind == SRLX_MEM_PROPORTIONAL;
+  SRLX_REQUIRE(eng.batch_size >= 1 && eng.batch_size <= SRLX_MAX_BATCH, "batch_size out of range");
+  SRLX_REQUIRE(eng.target_update_interval >= 1, "target_update_interval must be >= 1");
+  SRLX_REQUIRE(r->cursor && r->ring_obs && r->ring_next_obs && r->ring_action && r->ring_prob && r->ring_reward && r->ring_done &&
+               r->ring_tstep && r->ring_h && r->ring_c, "replay ring pointer is NULL");
+  SRLX_REQUIRE(r->adam_m && r->adam_v && r->grads && r->xh && r->cbuf && r->gates && r->dgates && r->dc && r->dh && r->q && r->sel && r->weights &&
+               r->b_actions && r->b_mu && r->b_rewards && r->b_dones && r->b_target && r->b_tdmean && r->b_tdkind, "learner workspace pointer is NULL");
+  for (int l = 0; l < r->n_head; ++l) SRLX_REQUIRE(r->act[l] && r->dact[l], "act / dact[%d] is NULL", l);
+  SRLX_REQUIRE(!per || eng.tree, "proportional memory needs the tree");
+  const int B = eng.batch_size, D = eng.obs_dim, u = r->lstm_units, K = D + u + 1, S = r->seq_len, W = r->burnin + S, A = eng.n_actions;
+  const int rows1 = (S + 1) * B, rowsS = S * B;
+  const size_t zx = (size_t)(W + 2) * B * K, zc = (size_t)(W + 2) * B * u;
+  const Gate gate{eng.state, (unsigned long long)eng.warmup_size};
+  if (per) SRLX_CHECK_CUDA(cudaFuncSetAttribute(r2d2_priority_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TreeHashScratch)));
+  for (uint32_t it = 0; it < n_updates; ++it) {
+    // memory.sample (r2d2.py:91) + the batch layout of _train_on_batches (:109-133)
+    if (per) r2d2_sample_per_kernel<<<1, 1024, 0, s>>>(*r, gate);
+    else r2d2_sample_uniform_kernel<<<1, 256, 0, s>>>(*r, gate);
+    r2d2_gather_kernel<<<B, 128, 0, s>>>(*r, gate);
+    count_launch(2);
+    // burn-in + unroll of both networks (:136-150): step t reads [x_t | h_{t-1} | 1] in time row t and leaves h_t in time row t + 1
+    for (int t = 0; t <= W; ++t) {
+      LstmFwdP lp{};
+      lp.xh = r->xh + (size_t)t * B * K; lp.z_xh = (long long)zx;
+      lp.W0 = r->params + r->lstm_off; lp.W1 = r->target + r->lstm_off;
+      lp.c_in = r->cbuf + (size_t)t * B * u; lp.c_out = r->cbuf + (size_t)(t + 1) * B * u; lp.z_c = (long long)zc;
+      lp.h_out = r->xh + (size_t)(t + 1) * B * K + D; lp.ld_h = K; lp.z_h = (long long)zx;
+      lp.gates = r->gates + (size_t)t * B * 4 * u; lp.M = B; lp.u = u; lp.K = K; lp.gate = gate;
+      if (B <= 32) lstm_fwd_kernel<32, 2><<<dim3((4 * u + 31) / 32, (B + 31) / 32, 2), 128, 0, s>>>(lp);
+      else lstm_fwd_kernel<64, 4><<<dim3((4 * u + 31) / 32, (B + 63) / 64, 2), 128, 0, s>>>(lp);
+      count_launch();
+    }
+    // hidden block on the S + 1 unrolled steps of both networks
+    for (int l = 0; l < r->n_head; ++l) {
+      const bool last = l == r->n_head - 1;
+      const int ldo = last ? r->head_out[l] : r->head_out[l] + 1;
+      GemmP g{};
+      if (l == 0) { g.A = r->xh + (size_t)(r->burnin + 1) * B * K + D; g.sa_m = K; g.zA = (long long)zx; }
+      else { g.A = r->act[l - 1]; g.sa_m = r->head_out[l - 1] + 1; g.zA = (long long)rows1 * (r->head_out[l - 1] + 1); }
+      g.sa_k = 1;
+      g.B = r->params + r->head_off[l]; g.B1 = r->target + r->head_off[l]; g.sb_k = 1; g.sb_n = r->head_k[l] + 1;
+      g.C = r->act[l]; g.ldc = ldo; g.zC = (long long)rows1 * ldo;
+      g.M = rows1; g.N = r->head_out[l]; g.K = r->head_k[l] + 1; g.relu = last ? 0 : 1; g.gate = gate;
+      launch_gemm(g, 2, s);
+    }
+    r2d2_combine_kernel<<<(2 * rows1 + 127) / 128, 128, 0, s>>>(*r, gate);
+    count_launch();
+    // the reference's own per-sequence loop (:158-202), bit-exact (csrc/sequence_targets.cu)
+    if (int rc = srlx_sequence_targets(r->q, r->q + (size_t)B * (S + 1) * A, r->b_actions, r->b_mu, r->b_rewards, r->b_dones, r->b_target,
+                                       r->b_tdmean, r->b_tdkind, (uint32_t)B, (uint32_t)S, (uint32_t)A, eng.discount, eng.retrace_h,
+                                       eng.enable_double_dqn, eng.enable_rescale, r->enable_retrace, cuda_stream)) return rc;
+    r2d2_loss_kernel<<<1, 256, 0, s>>>(*r, gate);
+    count_launch();
+    // hidden block backward over the S trained steps (rows (t, b), t < S, are the first S * B rows of every activation buffer)
+    for (int l = r->n_head - 1; l >= 0; --l) {
+      const float* in = l == 0 ? r->xh + (size_t)(r->burnin + 1) * B * K + D : r->act[l - 1];
+      const long long ld_in = l == 0 ? K : r->head_out[l - 1] + 1;
+      GemmP gw{};  // dW_l = dO_l^T . [in_l | 1]
+      gw.A = r->dact[l]; gw.sa_m = 1; gw.sa_k = r->head_out[l];
+      gw.B = in; gw.sb_k = ld_in; gw.sb_n = 1;
+      gw.C = r->grads + r->head_off[l]; gw.ldc = r->head_k[l] + 1;
+      gw.M = r->head_out[l]; gw.N = r->head_k[l] + 1; gw.K = rowsS; gw.gate = gate;
+      launch_gemm(gw, 1, s);
+      GemmP gi{};  // d in_l = dO_l . W_l[:, :k_l], through the ReLU of the layer below
+      gi.A = r->dact[l]; gi.sa_m = r->head_out[l]; gi.sa_k = 1;
+      gi.B = r->params + r->head_off[l]; gi.sb_k = r->head_k[l] + 1; gi.sb_n = 1;
+      gi.C = l == 0 ? r->dh : r->dact[l - 1]; gi.ldc = r->head_k[l];
+      gi.M = rowsS; gi.N = r->head_k[l]; gi.K = r->head_out[l]; gi.gate = gate;
+      if (l > 0) { gi.mask = r->act[l - 1]; gi.ldmask = r->head_out[l - 1] + 1; }
+      launch_gemm(gi, 1, s);
+    }
+    // BPTT over the S trained steps; the burn-in state is a constant of the tape (:136-138)
+    for (int t = S - 1; t >= 0; --t) {
+      LstmBwdP bp{};
+      bp.dg_next = t == S - 1 ? nullptr : r->dgates + (size_t)(t + 1) * B * 4 * u;
+      bp.W = r->params + r->lstm_off; bp.in = D; bp.K = K;
+      bp.dh_head = r->dh + (size_t)t * B * u;
+      bp.gates = r->gates + (size_t)(r->burnin + t) * B * 4 * u;
+      bp.c_prev = r->cbuf + (size_t)(r->burnin + t) * B * u;
+      bp.c_cur = r->cbuf + (size_t)(r->burnin + t + 1) * B * u;
+      bp.dc = r->dc; bp.dg = r->dgates + (size_t)t * B * 4 * u; bp.M = B; bp.u = u; bp.first = t == S - 1; bp.gate = gate;
+      if (B <= 32) lstm_bwd_kernel<32, 2><<<dim3((u + 31) / 32, (B + 31) / 32, 1), 128, 0, s>>>(bp);
+      else lstm_bwd_kernel<64, 4><<<dim3((u + 31) / 32, (B + 63) / 64, 1), 128, 0, s>>>(bp);
+      count_launch();
+    }
+    {
+      GemmP gw{};  // dW_lstm = sum_t dgates_t^T . [x_t | h_{t-1} | 1]
+      gw.A = r->dgates; gw.sa_m = 1; gw.sa_k = 4LL * u;
+      gw.B = r->xh + (size_t)r->burnin * B * K; gw.sb_k = K; gw.sb_n = 1;
+      gw.C = r->grads + r->lstm_off; gw.ldc = K;
+      gw.M = 4 * u; gw.N = K; gw.K = rowsS; gw.gate = gate;
+      launch_gemm(gw, 1, s);
+    }
+    r2d2_adam_kernel<<<(r->n_params + 255) / 256 < 1184 ? (r->n_params + 255) / 256 : 1184, 256, 0, s>>>(*r, gate);
+    count_launch();
+    if (per) {
+      r2d2_priority_kernel<<<1, 1024, sizeof(TreeHashScratch), s>>>(*r, gate);
+      count_launch();
+    }
+    r2d2_sync_kernel<<<(r->n_params + 255) / 256 < 1184 ? (r->n_params + 255) / 256 : 1184, 256, 0, s>>>(*r, gate);
+    r2d2_finish_kernel<<<1, 1, 0, s>>>(*r, gate);
+    count_launch(2);
+  }
+  SRLX_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
