@@ -296,7 +296,7 @@ typedef struct srlx_r2d2 {
   float* roll_act[SRLX_MAX_LAYERS]; /* [E][head_out[l] + 1] (last column 1); the last one [E][head_out] */
   unsigned char* roll_reset; /* [E] */
   uint32_t* new_c0; uint32_t* new_n;  /* [E] first new row / rows written by the last vector step */
-  int64_t* add_idx; double* add_pri;  /* [2*E*seq_len] replay-add list (proportional) */
+  int64_t* add_idx; double* add_pri;  /* [E*(2*seq_len+burnin+seq_len)] replay-add list (proportional) */
   /* learner workspace; z = 0 online, 1 target; W = burnin + seq_len; rows t-major */
   float* xh;               /* [2][W+2][B][in+u+1], last column 1 */
   float* cbuf;             /* [2][W+2][B][u] */

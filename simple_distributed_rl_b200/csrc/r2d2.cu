@@ -411,7 +411,8 @@ __global__ void r2d2_step_count_kernel(srlx_state* st, int E) {
 }
 
 // ProportionalMemory.add for the rows of one vector step (proportional_memory.py:120-129): new leaves take max_priority; the anchor
-// whose window the new row cuts (pos - R + W - 1) drops to 0 so that the sampler's zero-priority rejection skips it.  Entries are laid
+// whose window the new row cuts (pos - R + W - 1; at a column's first wrap all of 1 .. W - 1) drops to 0 so that the sampler's
+// zero-priority rejection skips it.  Entries are laid
 // out env-major in row order and applied in that order (tree_update_batch: the reference's sequential fp64 association).
 __global__ void __launch_bounds__(1024) r2d2_add_kernel(const __grid_constant__ srlx_r2d2 r) {
   extern __shared__ __align__(16) unsigned char tree_smem[];
@@ -433,7 +434,10 @@ __global__ void __launch_bounds__(1024) r2d2_add_kernel(const __grid_constant__ 
     if (e < E) {
       c0 = r.new_c0[e];
       n = r.new_n[e];
-      for (uint32_t j = 0; j < n; ++j) cnt += 1 + ((long long)c0 + j >= R ? 1 : 0);
+      for (uint32_t j = 0; j < n; ++j) {
+        const long long pos = (long long)c0 + j;
+        cnt += 1 + (pos >= R ? (W - 1) - (pos == R ? 1 : W - 1) + 1 : 0);
+      }
     }
     s_scan[tid] = cnt;
     __syncthreads();
@@ -446,10 +450,12 @@ __global__ void __launch_bounds__(1024) r2d2_add_kernel(const __grid_constant__ 
     int o = s_base + s_scan[tid] - cnt;
     for (uint32_t j = 0; j < n; ++j) {
       const long long pos = (long long)c0 + j;
-      if (pos >= R) {
-        r.add_idx[o] = ring_slot(r, pos - R + W - 1, e) + cap - 1;
-        r.add_pri[o] = 0.0;
-        ++o;
+      if (pos >= R) {  // the column's first wrap cuts every anchor that still reaches back to row 0; later rows cut one anchor each
+        for (int a = (pos == R ? 1 : W - 1); a <= W - 1; ++a) {
+          r.add_idx[o] = ring_slot(r, pos - R + a, e) + cap - 1;
+          r.add_pri[o] = 0.0;
+          ++o;
+        }
       }
       r.add_idx[o] = ring_slot(r, pos, e) + cap - 1;
       r.add_pri[o] = maxp;

@@ -266,8 +266,8 @@ class R2D2Engine:
                 self.t[f"dact{l}"] = z(((S + 1) * B, out), torch.float32)
             if self.per:
                 self.t["tree"] = z(2 * N - 1, torch.float64)
-                self.t["add_idx"] = z(2 * E * S, torch.int64)
-                self.t["add_pri"] = z(2 * E * S, torch.float64)
+                self.t["add_idx"] = z(E * (2 * S + W), torch.int64)
+                self.t["add_pri"] = z(E * (2 * S + W), torch.float64)
         self.c = self._build_struct()
         self.set_weights(self.spec.init_keras(cfg.seed) if weights is None else weights)
         if training and self.per:

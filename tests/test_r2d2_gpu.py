@@ -62,7 +62,7 @@ class _Twin:
     def __init__(self, eng):
         cfg = eng.cfg
         self.eng, self.cfg = eng, cfg
-        self.env = oenvs.make_spec(cfg.env)
+        self.env = oenvs.make_spec(cfg.env, **cfg.env_kwargs)
         E = eng.E
         self.state = [None] * E
         self.needs_reset = [True] * E
@@ -104,6 +104,7 @@ class _Twin:
                 h_before[e], c_before[e] = prev_h[e], prev_c[e]
             obs[e] = env.obs(self.state[e])
         eng.vec_step(True)
+        np.testing.assert_array_equal(eng.t["roll_xh"].cpu().numpy()[:, :eng.D], obs)  # env transitions + observation encoding, exact
         q_dev = eng.t["dbg_q"].cpu().numpy()
         a_dev = eng.t["dbg_action"].cpu().numpy()
         h_dev = eng.t["roll_h"].cpu().numpy()[:, :eng.u].copy()
