@@ -280,7 +280,8 @@ typedef struct srlx_r2d2 {
   int32_t n_head, dueling;                 /* head layers (incl. the output layer); SRLX_DUEL_* */
   int32_t head_out[SRLX_MAX_LAYERS], head_k[SRLX_MAX_LAYERS], head_off[SRLX_MAX_LAYERS]; /* rows, inputs (without the bias column), offset */
   int32_t lstm_off, n_params;
-  int32_t duel_hidden, reserved_i32;       /* H of the dueling block (0: no dueling block) */
+  int32_t duel_hidden;                     /* H of the dueling block (0: no dueling block) */
+  int32_t no_persistent;                   /* != 0: one launch per time step instead of the persistent unroll kernels (diagnostic) */
   double test_epsilon;
   /* parameters */
   float* params; float* target; float* adam_m; float* adam_v; float* grads; /* [n_params] each */
@@ -303,6 +304,9 @@ typedef struct srlx_r2d2 {
   float* gates;            /* [W+1][B][4u] online gate activations */
   float* dgates;           /* [W+1][B][4u] */
   float* dc;               /* [B][u] */
+  float* gemm_ws;          /* optional split-K workspace of the narrow weight-gradient maps (32 * max_l head_out[l] * (head_k[l] + 1) floats is enough) */
+  uint64_t gemm_ws_floats;
+  uint32_t* bar;           /* [4] barrier words of the persistent unroll kernels (NULL: one launch per time step) */
   float* act[SRLX_MAX_LAYERS];  /* [2][(seq_len+1)*B][head_out[l] + 1] (last column 1); last layer [2][rows][head_out] */
   float* dact[SRLX_MAX_LAYERS]; /* [(seq_len+1)*B][head_out[l]] gradient wrt the layer's output */
   float* dh;               /* [(seq_len+1)*B][u] gradient wrt the LSTM outputs */

@@ -119,14 +119,14 @@ class SrlxR2d2(C.Structure):
         ("lstm_units", C.c_int32), ("burnin", C.c_int32), ("seq_len", C.c_int32), ("enable_retrace", C.c_int32),
         ("n_head", C.c_int32), ("dueling", C.c_int32),
         ("head_out", C.c_int32 * SRLX_MAX_LAYERS), ("head_k", C.c_int32 * SRLX_MAX_LAYERS), ("head_off", C.c_int32 * SRLX_MAX_LAYERS),
-        ("lstm_off", C.c_int32), ("n_params", C.c_int32), ("duel_hidden", C.c_int32), ("reserved_i32", C.c_int32),
+        ("lstm_off", C.c_int32), ("n_params", C.c_int32), ("duel_hidden", C.c_int32), ("no_persistent", C.c_int32),
         ("test_epsilon", C.c_double),
         ("params", _P), ("target", _P), ("adam_m", _P), ("adam_v", _P), ("grads", _P),
         ("cursor", _P), ("ring_obs", _P), ("ring_next_obs", _P), ("ring_action", _P), ("ring_prob", _P), ("ring_reward", _P),
         ("ring_done", _P), ("ring_tstep", _P), ("ring_h", _P), ("ring_c", _P),
         ("roll_xh", _P), ("roll_h", _P), ("roll_c", _P), ("roll_act", _P * SRLX_MAX_LAYERS), ("roll_reset", _P),
         ("new_c0", _P), ("new_n", _P), ("add_idx", _P), ("add_pri", _P),
-        ("xh", _P), ("cbuf", _P), ("gates", _P), ("dgates", _P), ("dc", _P),
+        ("xh", _P), ("cbuf", _P), ("gates", _P), ("dgates", _P), ("dc", _P), ("gemm_ws", _P), ("gemm_ws_floats", C.c_uint64), ("bar", _P),
         ("act", _P * SRLX_MAX_LAYERS), ("dact", _P * SRLX_MAX_LAYERS), ("dh", _P), ("q", _P), ("sel", _P), ("weights", _P),
         ("b_actions", _P), ("b_mu", _P), ("b_rewards", _P), ("b_dones", _P), ("b_target", _P), ("b_tdmean", _P), ("b_tdkind", _P),
     ]

@@ -36,6 +36,7 @@ struct GemmP {
   long long zA, zB, zC;                 // blockIdx.z strides (floats)
   const float* B1;                      // if set: blockIdx.z == 1 reads B1 instead of B + zB (online / target parameter buffers)
   Gate gate;
+  float* ws; int ksplit, klen;          // split-K (narrow outputs over a long reduction): slice z of k -> ws[z][M][N], summed in slice order
 };
 
 template <int BM, int BN, int TM, int TN>
@@ -83,13 +84,26 @@ template <int BM, int BN, int TM, int TN>
 __global__ void __launch_bounds__((BM / TM) * (BN / TN)) sgemm_kernel(const GemmP p) {
   if (p.gate.closed()) return;
   const int z = blockIdx.z;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  const int tx = threadIdx.x % (BN / TN), ty = threadIdx.x / (BN / TN);
+  float acc[TM][TN];
+  if (p.ksplit > 1) {
+    const int kb = z * p.klen, kl = min(p.klen, p.K - kb);
+    gemm_mainloop<BM, BN, TM, TN>(p.A + (long long)kb * p.sa_k, p.sa_m, p.sa_k, p.B + (long long)kb * p.sb_k, p.sb_k, p.sb_n, p.M, p.N, kl, m0, n0, acc);
+    float* out = p.ws + (size_t)z * p.M * p.N;
+#pragma unroll
+    for (int i = 0; i < TM; ++i)
+#pragma unroll
+      for (int j = 0; j < TN; ++j) {
+        const int m = m0 + ty * TM + i, n = n0 + tx * TN + j;
+        if (m < p.M && n < p.N) out[(size_t)m * p.N + n] = acc[i][j];
+      }
+    return;
+  }
   const float* A = p.A + (long long)z * p.zA;
   const float* B = (z == 1 && p.B1) ? p.B1 : p.B + (long long)z * p.zB;
   float* C = p.C + (long long)z * p.zC;
-  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
-  float acc[TM][TN];
   gemm_mainloop<BM, BN, TM, TN>(A, p.sa_m, p.sa_k, B, p.sb_k, p.sb_n, p.M, p.N, p.K, m0, n0, acc);
-  const int tx = threadIdx.x % (BN / TN), ty = threadIdx.x / (BN / TN);
 #pragma unroll
   for (int i = 0; i < TM; ++i) {
     const int m = m0 + ty * TM + i;
@@ -108,11 +122,146 @@ __global__ void __launch_bounds__((BM / TM) * (BN / TN)) sgemm_kernel(const Gemm
   }
 }
 
-static int launch_gemm(const GemmP& p, int nz, cudaStream_t s) {
+// Register-tiled version for the large maps (hidden block over (S + 1) * B rows, weight gradients, the rollout's E-row steps): BM x BN
+// tile per CTA, 16-deep k slices double-buffered through registers, every thread an (BM/16) x (BN/16) micro-tile read as float4 from
+// k-major shared tiles.  Operand strides are arbitrary (row- or column-major A and B: forward, input-gradient and weight-gradient maps
+// are the same kernel); the bias columns make the leading dimensions odd, so global loads are scalar, with the lanes laid along
+// whichever dimension is contiguous.
+template <int BM, int BN>
+__global__ void __launch_bounds__(256) sgemm_tiled_kernel(const GemmP p) {
+  if (p.gate.closed()) return;
+  constexpr int BK = 16, TM = BM / 16, TN = BN / 16, NA = BM * BK / 256, NB = BN * BK / 256;
+  __shared__ __align__(16) float As[2][BK][BM + 4];
+  __shared__ __align__(16) float Bs[2][BK][BN + 4];
+  const int z = blockIdx.z;
+  const float* __restrict__ A = p.A + (long long)z * p.zA;
+  const float* __restrict__ B = (z == 1 && p.B1) ? p.B1 : p.B + (long long)z * p.zB;
+  float* C = p.C + (long long)z * p.zC;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN, tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const bool a_k = p.sa_k == 1, b_n = p.sb_n == 1;
+  float ra[NA], rb[NB];
+  auto load = [&](int k0) {
+#pragma unroll
+    for (int i = 0; i < NA; ++i) {
+      const int idx = tid + i * 256;
+      const int kk = a_k ? idx % BK : idx / BM, mm = a_k ? idx / BK : idx % BM;
+      const int gm = m0 + mm, gk = k0 + kk;
+      ra[i] = (gm < p.M && gk < p.K) ? __ldcg(A + (long long)gm * p.sa_m + (long long)gk * p.sa_k) : 0.f;
+    }
+#pragma unroll
+    for (int i = 0; i < NB; ++i) {
+      const int idx = tid + i * 256;
+      const int nn = b_n ? idx % BN : idx / BK, kk = b_n ? idx / BN : idx % BK;
+      const int gn = n0 + nn, gk = k0 + kk;
+      rb[i] = (gn < p.N && gk < p.K) ? __ldcg(B + (long long)gk * p.sb_k + (long long)gn * p.sb_n) : 0.f;
+    }
+  };
+  auto store = [&](int buf) {
+#pragma unroll
+    for (int i = 0; i < NA; ++i) {
+      const int idx = tid + i * 256;
+      const int kk = a_k ? idx % BK : idx / BM, mm = a_k ? idx / BK : idx % BM;
+      As[buf][kk][mm] = ra[i];
+    }
+#pragma unroll
+    for (int i = 0; i < NB; ++i) {
+      const int idx = tid + i * 256;
+      const int nn = b_n ? idx % BN : idx / BK, kk = b_n ? idx / BN : idx % BK;
+      Bs[buf][kk][nn] = rb[i];
+    }
+  };
+  float acc[TM][TN];
+#pragma unroll
+  for (int i = 0; i < TM; ++i)
+#pragma unroll
+    for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+  load(0);
+  store(0);
+  __syncthreads();
+  int buf = 0;
+  for (int k0 = 0; k0 < p.K; k0 += BK) {
+    const bool more = k0 + BK < p.K;
+    if (more) load(k0 + BK);
+#pragma unroll
+    for (int kk = 0; kk < BK; ++kk) {
+      float a[TM], b[TN];
+#pragma unroll
+      for (int i = 0; i < TM; i += 4) *reinterpret_cast<float4*>(&a[i]) = *reinterpret_cast<const float4*>(&As[buf][kk][(i / 4) * (BM / (TM / 4)) + ty * 4]);
+#pragma unroll
+      for (int j = 0; j < TN; j += 4) *reinterpret_cast<float4*>(&b[j]) = *reinterpret_cast<const float4*>(&Bs[buf][kk][(j / 4) * (BN / (TN / 4)) + tx * 4]);
+#pragma unroll
+      for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    if (more) {
+      store(buf ^ 1);
+      __syncthreads();
+      buf ^= 1;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < TM; ++i) {
+    const int m = m0 + (i / 4) * (BM / (TM / 4)) + ty * 4 + (i & 3);
+    if (m >= p.M) continue;
+#pragma unroll
+    for (int j = 0; j < TN; ++j) {
+      const int n = n0 + (j / 4) * (BN / (TN / 4)) + tx * 4 + (j & 3);
+      if (n >= p.N) continue;
+      float v = acc[i][j];
+      float* c = C + (long long)m * p.ldc + n;
+      if (p.accumulate) v += *c;
+      if (p.relu) v = fmaxf(v, 0.f);
+      if (p.mask && !(p.mask[(long long)m * p.ldmask + n] > 0.f)) v = 0.f;
+      *c = v;
+    }
+  }
+}
+
+__global__ void splitk_reduce_kernel(const GemmP p) {
+  if (p.gate.closed()) return;
+  const long long n_out = (long long)p.M * p.N;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_out; i += (long long)gridDim.x * blockDim.x) {
+    const int m = (int)(i / p.N), n = (int)(i - (long long)m * p.N);
+    float v = 0.f;
+    for (int z = 0; z < p.ksplit; ++z) v += p.ws[(size_t)z * n_out + i];
+    float* c = p.C + (long long)m * p.ldc + n;
+    if (p.accumulate) v += *c;
+    if (p.relu) v = fmaxf(v, 0.f);
+    if (p.mask && !(p.mask[(long long)m * p.ldmask + n] > 0.f)) v = 0.f;
+    *c = v;
+  }
+}
+
+static int launch_gemm(const GemmP& p_in, int nz, cudaStream_t s, float* ws = nullptr, size_t ws_floats = 0) {
+  GemmP p = p_in;
   if (p.M <= 0 || p.N <= 0) return 0;
+  if (nz == 1 && ws && (p.M <= 32 || p.N <= 32) && p.K >= 1024) {
+    int splits = p.K / 256;
+    if (splits > 32) splits = 32;
+    while (splits > 1 && (size_t)splits * p.M * p.N > ws_floats) --splits;
+    if (splits > 1) {
+      p.klen = ((p.K + splits - 1) / splits + 15) / 16 * 16;
+      p.ksplit = (p.K + p.klen - 1) / p.klen;
+      p.ws = ws;
+      dim3 grid((p.N + 31) / 32, (p.M + 31) / 32, p.ksplit);
+      sgemm_kernel<32, 32, 2, 4><<<grid, 128, 0, s>>>(p);
+      const long long n_out = (long long)p.M * p.N;
+      splitk_reduce_kernel<<<(unsigned)((n_out + 255) / 256 < 592 ? (n_out + 255) / 256 : 592), 256, 0, s>>>(p);
+      count_launch(2);
+      return 0;
+    }
+  }
+  const long long t128 = (long long)((p.M + 127) / 128) * ((p.N + 127) / 128) * nz, t64 = (long long)((p.M + 63) / 64) * ((p.N + 63) / 64) * nz;
   if (p.M <= 32 || p.N <= 32) {
     dim3 grid((p.N + 31) / 32, (p.M + 31) / 32, nz);
     sgemm_kernel<32, 32, 2, 4><<<grid, 128, 0, s>>>(p);
+  } else if (t128 >= 120) {  // enough 128 x 128 tiles for the 148 SMs
+    dim3 grid((p.N + 127) / 128, (p.M + 127) / 128, nz);
+    sgemm_tiled_kernel<128, 128><<<grid, 256, 0, s>>>(p);
+  } else if (t64 >= 32) {
+    dim3 grid((p.N + 63) / 64, (p.M + 63) / 64, nz);
+    sgemm_tiled_kernel<64, 64><<<grid, 256, 0, s>>>(p);
   } else {
     dim3 grid((p.N + 63) / 64, (p.M + 63) / 64, nz);
     sgemm_kernel<64, 64, 4, 4><<<grid, 256, 0, s>>>(p);
@@ -210,6 +359,305 @@ __global__ void __launch_bounds__((BM / TM) * 8) lstm_bwd_kernel(const LstmBwdP 
       *reinterpret_cast<float4*>(p.dg + ui * 4) = d;
       p.dc[ui] = dcv * fg;
     }
+  }
+}
+
+// ---- persistent unroll: all time steps of both networks in ONE cooperative launch -------------------------------------------------------
+// A recurrent step is a [B x K] . [K x 4u] map with B <= 64: far too small to fill the GPU per launch, and consecutive steps are data
+// dependent.  So the grid stays resident for the whole sequence: CTA (z, c) owns 8 LSTM units (32 gate rows) of network z and keeps
+// their weights in REGISTERS for all steps (lane = gate row, warp = one of 8 k slices: 65 floats per thread at K = 517); per step it
+// stages [x_t | h_{t-1} | 1] (B x K floats, L2 hits) into shared memory, every warp accumulates its k slice for all rows out of
+// warp-wide BROADCAST float4 reads (one shared-memory wavefront per 4 k values, no bank conflicts by construction), the 8 slices are
+// summed in slice order, the thread that owns (row, unit) applies the gates, keeps c in a register, writes h_t into the next step's
+// input row and the activated gates for BPTT, and the CTAs of one network meet at a counting barrier in global memory (release
+// fence + atomic add, acquire spin).  Weights are read from L2 once per launch instead of once per step.
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void grid_arrive(unsigned* bar) {
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) atomicAdd(bar, 1u);
+}
+// a CTA that waits longer than ~2 s gives up (the results are then garbage, bar[3] records it) instead of hanging the GPU: the launch
+// is cooperative, so every CTA is resident and this cannot happen unless a CTA died
+__device__ __forceinline__ void grid_wait(unsigned* bar_base, const unsigned* bar, unsigned target) {
+  if (threadIdx.x == 0) {
+    const long long t0 = clock64();
+    while (ld_acquire_u32(bar) < target) {
+      __nanosleep(20);
+      if (clock64() - t0 > 4000000000ll) { atomicExch(bar_base + 3, 0xDEADu); break; }
+    }
+  }
+  __syncthreads();
+}
+
+__device__ __forceinline__ void cp_async16(float* smem_dst, const float* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+__device__ __forceinline__ void cp_async4(float* smem_dst, const float* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+
+struct SeqFwdP {
+  const float* W0; const float* W1;  // LSTM weights of the online / target network: [4u][K]
+  float* xh; long long z_xh;         // [z][T + 1][B][K]
+  float* cbuf; long long z_c;        // [z][T + 1][B][u]
+  float* gates;                      // [T][B][4u] activated gates of network 0
+  unsigned* bar;                     // [4] arrival counters (forward: [z]; backward: [2]; [3] = time-out flag), zero at launch
+  int B, u, D, K, T, cpn;            // T steps; cpn CTAs per network
+  Gate gate;
+};
+
+// Thread layout of a forward CTA: lane = unit * 4 + ksub, slice = warp * 4 + ksub: 32 slices of 16 h columns (u <= 512); slice s also
+// takes "extra" column s of the [x | 1] part (D + 1 <= 32 columns).  A thread owns the FOUR gates of its unit over its slice: 64 + 4
+// weights in registers, and every h value it reads from shared memory feeds 4 FMAs (shared-memory wavefronts, not FMA issue, bound this
+// loop: a float4 read is served one quarter-warp at a time, and the slice offsets are skewed so that the 4 addresses of a quarter-warp
+// fall into different banks).  Rows go in passes of 16: partial sums -> shared [slice][row][gate row], summed in slice order by the
+// two threads that own (row, unit), which keep c in a register across all steps.
+constexpr int kFwdXS = 608, kFwdExtra = 576, kFwdRedStride = 16 * 32 + 8;
+__device__ __forceinline__ int fwd_hoff(int s) { return s * 16 + (s >> 1) * 4; }
+
+template <int ROWS>
+__global__ void __launch_bounds__(256, 1) lstm_seq_fwd_kernel(const SeqFwdP p) {
+  if (p.gate.closed()) return;
+  extern __shared__ __align__(16) float seq_smem[];
+  constexpr int XS = kFwdXS, RP = 16, NPASS = ROWS / RP, RSTR = kFwdRedStride;
+  float* xs = seq_smem;              // [ROWS][XS]
+  float* red = seq_smem + ROWS * XS; // [32 slices][RSTR]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, j = lane >> 2, ksub = lane & 3, sl = warp * 4 + ksub;
+  const int z = blockIdx.x / p.cpn, unit0 = (blockIdx.x % p.cpn) * 8;
+  const int B = p.B, u = p.u, D = p.D, K = p.K;
+  const float* __restrict__ W = z ? p.W1 : p.W0;
+  const int unit = unit0 + j;
+  float wh[4][16], we[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const float* wr = W + (size_t)(unit * 4 + q) * K;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) wh[q][i] = (unit < u && sl * 16 + i < u) ? __ldg(wr + D + sl * 16 + i) : 0.f;
+    we[q] = (unit < u && sl <= D) ? __ldg(wr + (sl < D ? sl : K - 1)) : 0.f;
+  }
+  for (int i = tid; i < ROWS * XS; i += 256) xs[i] = 0.f;
+  __syncthreads();
+  for (int m = tid; m < B; m += 256) xs[m * XS + kFwdExtra + D] = 1.f;  // the bias column's partner
+  float* xh = p.xh + (size_t)z * p.z_xh;
+  float* cb = p.cbuf + (size_t)z * p.z_c;
+  // finalising thread: half = which 16 slices it sums, (fm, fj) = row within the pass / unit
+  const int half = (tid >> 4) & 1, pair = (tid & 15) + (tid >> 5) * 16, fm = pair >> 3, fj = pair & 7, funit = unit0 + fj;
+  float c_reg[NPASS];
+#pragma unroll
+  for (int ps = 0; ps < NPASS; ++ps) {
+    const int m = ps * RP + fm;
+    c_reg[ps] = (m < B && funit < u) ? __ldcg(cb + (size_t)m * u + funit) : 0.f;
+  }
+  __syncthreads();
+  for (int t = 0; t < p.T; ++t) {
+    if (t > 0) grid_wait(p.bar, p.bar + z, (unsigned)t * (unsigned)p.cpn);
+    const float* src = xh + (size_t)t * B * K;
+    // The rows are K = D + u + 1 floats apart (odd: the bias column), so the copies are 4 bytes wide.  A load -> register -> store loop
+    // leaves the step bound by L2 latency (the weights take the registers a deep software pipeline would need), so the copies are
+    // cp.async: ~130 per thread, all in flight at once.  4-byte cp.async exists only as .ca (through L1): safe when no 128-byte line
+    // straddles two time rows (B * K * 4 bytes a multiple of 128, i.e. B a multiple of 32) -- every line is then fetched once per
+    // launch, after the step that wrote it.  Other batch sizes take plain ld.cg loads.
+    if ((B & 31) == 0) {
+      for (int m = warp; m < B; m += 8) {
+        const float* row = src + (size_t)m * K;
+        float* dst = xs + m * XS;
+        for (int k = lane; k < u; k += 32) cp_async4(dst + fwd_hoff(k >> 4) + (k & 15), row + D + k);
+        if (lane < D) cp_async4(dst + kFwdExtra + lane, row + lane);
+      }
+      cp_async_commit();
+      cp_async_wait<0>();
+    } else {
+      for (int m = warp; m < B; m += 8) {
+        const float* row = src + (size_t)m * K;
+        float* dst = xs + m * XS;
+        for (int k = lane; k < u; k += 32) dst[fwd_hoff(k >> 4) + (k & 15)] = __ldcg(row + D + k);
+        if (lane < D) dst[kFwdExtra + lane] = __ldcg(row + lane);
+      }
+    }
+    __syncthreads();
+#pragma unroll 1
+    for (int ps = 0; ps < NPASS; ++ps) {
+      const int r0 = ps * RP;
+      if (r0 < B) {
+        float acc[RP][4];
+#pragma unroll
+        for (int m = 0; m < RP; ++m) acc[m][0] = acc[m][1] = acc[m][2] = acc[m][3] = 0.f;
+        const float* xrow = xs + r0 * XS + fwd_hoff(sl);
+#pragma unroll
+        for (int i = 0; i < 16; i += 4) {
+#pragma unroll
+          for (int m = 0; m < RP; ++m) {
+            const float4 a = *reinterpret_cast<const float4*>(xrow + m * XS + i);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              acc[m][q] = fmaf(a.x, wh[q][i], acc[m][q]);
+              acc[m][q] = fmaf(a.y, wh[q][i + 1], acc[m][q]);
+              acc[m][q] = fmaf(a.z, wh[q][i + 2], acc[m][q]);
+              acc[m][q] = fmaf(a.w, wh[q][i + 3], acc[m][q]);
+            }
+          }
+        }
+#pragma unroll
+        for (int m = 0; m < RP; ++m) {
+          const float a = xs[(r0 + m) * XS + kFwdExtra + sl];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) acc[m][q] = fmaf(a, we[q], acc[m][q]);
+          *reinterpret_cast<float4*>(red + sl * RSTR + m * 32 + j * 4) = make_float4(acc[m][0], acc[m][1], acc[m][2], acc[m][3]);
+        }
+      }
+      __syncthreads();
+      if (r0 < B) {
+        float4 sg = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int s2 = 0; s2 < 16; ++s2) {
+          const float4 r = *reinterpret_cast<const float4*>(red + (half * 16 + s2) * RSTR + fm * 32 + fj * 4);
+          sg.x += r.x; sg.y += r.y; sg.z += r.z; sg.w += r.w;
+        }
+        // slices 0..15 + slices 16..31, in that order on both threads of the pair
+        const float ox = __shfl_xor_sync(0xffffffffu, sg.x, 16), oy = __shfl_xor_sync(0xffffffffu, sg.y, 16);
+        const float oz = __shfl_xor_sync(0xffffffffu, sg.z, 16), ow = __shfl_xor_sync(0xffffffffu, sg.w, 16);
+        if (half == 0) { sg.x += ox; sg.y += oy; sg.z += oz; sg.w += ow; }
+        else { sg.x = ox + sg.x; sg.y = oy + sg.y; sg.z = oz + sg.z; sg.w = ow + sg.w; }
+        const int m = r0 + fm;
+        if (m < B && funit < u) {
+          const float ig = sigmoidf_(sg.x), fg = sigmoidf_(sg.y), gg = tanhf(sg.z), og = sigmoidf_(sg.w);
+          const float c = fmaf(fg, c_reg[ps], ig * gg);
+          c_reg[ps] = c;
+          if (half == 0) {
+            __stcg(cb + ((size_t)(t + 1) * B + m) * u + funit, c);
+            __stcg(xh + ((size_t)(t + 1) * B + m) * K + D + funit, og * tanhf(c));
+            if (z == 0 && p.gates) __stcg(reinterpret_cast<float4*>(p.gates + (((size_t)t * B + m) * u + funit) * 4), make_float4(ig, fg, gg, og));
+          }
+        }
+      }
+      __syncthreads();
+    }
+    if (t + 1 < p.T) grid_arrive(p.bar + z);
+  }
+}
+
+// BPTT, persistent: CTA c owns 4 units; dh_t = dgates_{t+1} . Wh needs every gate row of the step before, so the CTA's 4u x 4 slice of
+// Wh sits in registers and the [B x 4u] gate gradients are streamed through shared memory in windows of 256 gate rows (cp.async,
+// double-buffered, so the L2 reads of window v + 1 overlap the FMAs of window v).  lane = gs * 4 + rg: the thread handles rows
+// rg, rg + 4, ... and, in every window, 4 gate rows (slice warp * 8 + gs) for all 4 units: each float4 it reads feeds 16 FMAs; row
+// stride 264 puts the 8 addresses of a quarter-warp into 8 different bank groups.  The 64 slices are summed in slice order by the
+// thread that owns (row, unit), which keeps dc in a register across all steps.
+struct SeqBwdP {
+  const float* W; int K, D;   // online LSTM weights [4u][K]
+  const float* dh_head;       // [S][B][u]
+  const float* gates;         // [S][B][4u] activated gates of the trained steps
+  const float* cbuf;          // [S + 1][B][u]: c before trained step 0, then after every trained step
+  float* dgates;              // [S][B][4u]
+  unsigned* bar;              // the same [4] words
+  int B, u, S, n_cta;
+  Gate gate;
+};
+
+constexpr int kBwdRow = 264, kBwdRedStride = 272;
+template <int ROWS>
+__global__ void __launch_bounds__(256, 1) lstm_seq_bwd_kernel(const SeqBwdP p) {
+  if (p.gate.closed()) return;
+  extern __shared__ __align__(16) float seq_smem[];
+  constexpr int RW = kBwdRow, NR = ROWS / 4, RSTR = kBwdRedStride, NWMAX = 8;
+  float* ds = seq_smem;                 // [2][ROWS][RW]
+  float* red = seq_smem + 2 * ROWS * RW;  // [64 slices][RSTR]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, rg = lane & 3, gs = lane >> 2, sl = warp * 8 + gs;
+  const int B = p.B, u = p.u, G = 4 * u, unit0 = blockIdx.x * 4;
+  const int nw = (G + 255) / 256;
+  float w[NWMAX][4][4];  // [window][gate row in the slice][unit]
+#pragma unroll
+  for (int v = 0; v < NWMAX; ++v)
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) {
+        const int g = v * 256 + sl * 4 + i;
+        w[v][i][jj] = (g < G && unit0 + jj < u) ? __ldg(p.W + (size_t)g * p.K + p.D + unit0 + jj) : 0.f;
+      }
+  for (int i = tid; i < 2 * ROWS * RW; i += 256) ds[i] = 0.f;
+  const int fm = tid >> 2, fj = tid & 3, funit = unit0 + fj;  // the (row, unit) this thread finalises (ROWS * 4 <= 256)
+  const bool fok = fm < B && funit < u && fm < ROWS;
+  float dc_reg = 0.f;
+  __syncthreads();
+  auto stage = [&](const float* dgn, int v, int buf) {
+    float* dst = ds + buf * ROWS * RW;
+#pragma unroll
+    for (int it = 0; it < ROWS * 64 / 256; ++it) {
+      const int idx = tid + it * 256, m = idx >> 6, g = v * 256 + (idx & 63) * 4;
+      if (m < B && g < G) cp_async16(dst + m * RW + (idx & 63) * 4, dgn + (size_t)m * G + g);
+    }
+    cp_async_commit();
+  };
+  for (int t = p.S - 1; t >= 0; --t) {
+    const bool have_next = t < p.S - 1;
+    if (have_next) {
+      grid_wait(p.bar, p.bar + 2, (unsigned)(p.S - 1 - t) * (unsigned)p.n_cta);
+      const float* dgn = p.dgates + (size_t)(t + 1) * B * G;
+      float acc[NR][4];
+#pragma unroll
+      for (int i = 0; i < NR; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
+      stage(dgn, 0, 0);
+#pragma unroll
+      for (int v = 0; v < NWMAX; ++v) {
+        if (v < nw) {
+          if (v + 1 < nw) {
+            stage(dgn, v + 1, (v + 1) & 1);
+            cp_async_wait<1>();
+          } else {
+            cp_async_wait<0>();
+          }
+          __syncthreads();
+          const float* base = ds + (v & 1) * ROWS * RW + rg * RW + sl * 4;
+#pragma unroll
+          for (int i = 0; i < NR; ++i) {
+            const float4 a = *reinterpret_cast<const float4*>(base + i * 4 * RW);
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+              acc[i][jj] = fmaf(a.x, w[v][0][jj], acc[i][jj]);
+              acc[i][jj] = fmaf(a.y, w[v][1][jj], acc[i][jj]);
+              acc[i][jj] = fmaf(a.z, w[v][2][jj], acc[i][jj]);
+              acc[i][jj] = fmaf(a.w, w[v][3][jj], acc[i][jj]);
+            }
+          }
+          __syncthreads();
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < NR; ++i)
+        *reinterpret_cast<float4*>(red + sl * RSTR + (i * 4 + rg) * 4) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+      __syncthreads();
+    }
+    if (fok) {
+      float dh = p.dh_head[((size_t)t * B + fm) * u + funit];
+      if (have_next) {
+        float sum = 0.f;
+#pragma unroll 8
+        for (int s2 = 0; s2 < 64; ++s2) sum += red[s2 * RSTR + fm * 4 + fj];
+        dh += sum;
+      }
+      const size_t ui = ((size_t)t * B + fm) * u + funit;
+      const float4 g4 = *reinterpret_cast<const float4*>(p.gates + ui * 4);
+      const float ig = g4.x, fg = g4.y, gg = g4.z, og = g4.w;
+      const float c_prev = p.cbuf[ui], tc = tanhf(p.cbuf[ui + (size_t)B * u]);
+      const float dcv = dc_reg + dh * og * (1.f - tc * tc);
+      float4 d;
+      d.x = dcv * gg * ig * (1.f - ig);
+      d.y = dcv * c_prev * fg * (1.f - fg);
+      d.z = dcv * ig * (1.f - gg * gg);
+      d.w = dh * tc * og * (1.f - og);
+      __stcg(reinterpret_cast<float4*>(p.dgates + ui * 4), d);
+      dc_reg = dcv * fg;
+    }
+    if (t > 0) grid_arrive(p.bar + 2);
   }
 }
 
@@ -412,19 +860,20 @@ __global__ void r2d2_step_count_kernel(srlx_state* st, int E) {
 
 // ProportionalMemory.add for the rows of one vector step (proportional_memory.py:120-129): new leaves take max_priority; the anchor
 // whose window the new row cuts (pos - R + W - 1; at a column's first wrap all of 1 .. W - 1) drops to 0 so that the sampler's
-// zero-priority rejection skips it.  Entries are laid
-// out env-major in row order and applied in that order (tree_update_batch: the reference's sequential fp64 association).
+// zero-priority rejection skips it.  A vector step touches a few leaves per env copy -- thousands per step -- so they are set in
+// bulk: every touched leaf is written, then the touched paths are rebuilt bottom-up, one level per block-wide barrier, every
+// ancestor as left child + right child (the value the reference's node holds up to the rounding of its `+= change` chain; the trainer's
+// priority updates keep the reference's sequential association, tree_update_batch).  The result is a pure function of the leaves:
+// deterministic, no atomics.  (In a tree whose leaves sit on two depths a node can be rebuilt once before its deeper child is final;
+// the deeper path rebuilds it again one level later.)
 __global__ void __launch_bounds__(1024) r2d2_add_kernel(const __grid_constant__ srlx_r2d2 r) {
-  extern __shared__ __align__(16) unsigned char tree_smem[];
-  TreeHashScratch* hs = reinterpret_cast<TreeHashScratch*>(tree_smem);
   __shared__ int s_scan[1024];
   __shared__ int s_base;
-  __shared__ int64_t s_idx[kTreeHashChunk];
-  __shared__ double s_pri[kTreeHashChunk];
   const srlx_engine& eng = r.env;
   const int E = eng.n_envs, R = eng.ring_rows, W = r.burnin + r.seq_len, tid = threadIdx.x;
   const long long cap = (long long)R * E;
   const double maxp = eng.state->max_priority;
+  double* tree = eng.tree;
   if (tid == 0) s_base = 0;
   __syncthreads();
   for (int e0 = 0; e0 < E; e0 += 1024) {
@@ -452,26 +901,32 @@ __global__ void __launch_bounds__(1024) r2d2_add_kernel(const __grid_constant__ 
       const long long pos = (long long)c0 + j;
       if (pos >= R) {  // the column's first wrap cuts every anchor that still reaches back to row 0; later rows cut one anchor each
         for (int a = (pos == R ? 1 : W - 1); a <= W - 1; ++a) {
-          r.add_idx[o] = ring_slot(r, pos - R + a, e) + cap - 1;
-          r.add_pri[o] = 0.0;
-          ++o;
+          const long long idx = ring_slot(r, pos - R + a, e) + cap - 1;
+          r.add_idx[o++] = idx;
+          __stcg(tree + idx, 0.0);
         }
       }
-      r.add_idx[o] = ring_slot(r, pos, e) + cap - 1;
-      r.add_pri[o] = maxp;
-      ++o;
+      const long long idx = ring_slot(r, pos, e) + cap - 1;
+      r.add_idx[o++] = idx;
+      __stcg(tree + idx, maxp);
     }
     __syncthreads();
     if (tid == 1023) s_base += s_scan[1023];
     __syncthreads();
   }
   const int total = s_base;
-  for (int base = 0; base < total; base += kTreeHashChunk) {
-    const int m = min(kTreeHashChunk, total - base);
-    if (tid < m) { s_idx[tid] = r.add_idx[base + tid]; s_pri[tid] = r.add_pri[base + tid]; }
+  __threadfence_block();
+  __syncthreads();
+  int depth = 0;
+  while (((2 * cap - 1) >> (depth + 1)) > 0) ++depth;  // levels above the deepest leaf
+  for (int lv = 1; lv <= depth; ++lv) {
+    for (int i = tid; i < total; i += 1024) {
+      const uint64_t ip1 = (uint64_t)r.add_idx[i] + 1;
+      if ((ip1 >> lv) == 0) continue;
+      const uint64_t node = (ip1 >> lv) - 1;
+      __stcg(tree + node, __ldcg(tree + 2 * node + 1) + __ldcg(tree + 2 * node + 2));
+    }
     __syncthreads();
-    tree_update_prepare(eng.tree, s_idx, m, hs);
-    tree_update_apply(eng.tree, s_pri, m, hs, nullptr, 0);
   }
 }
 
@@ -803,7 +1258,7 @@ extern "C" int srlx_r2d2_vec_step(const srlx_r2d2* r, int training, uintptr_t cu
     SRLX_REQUIRE(r->cursor && r->ring_obs && r->ring_next_obs && r->ring_action && r->ring_prob && r->ring_reward && r->ring_done &&
                  r->ring_tstep && r->ring_h && r->ring_c && r->new_c0 && r->new_n, "replay ring pointer is NULL");
     SRLX_REQUIRE(eng.ring_rows >= 2 * (r->burnin + r->seq_len), "ring_rows must be >= 2 * (burnin + seq_len)");
-    SRLX_REQUIRE(!per || (eng.tree && r->add_idx && r->add_pri), "proportional memory needs tree / add_idx / add_pri");
+    SRLX_REQUIRE(!per || (eng.tree && r->add_idx), "proportional memory needs tree / add_idx");
   }
   const int E = eng.n_envs, u = r->lstm_units;
   r2d2_pre_kernel<<<(E + 127) / 128, 128, 0, s>>>(*r, training);
@@ -815,8 +1270,7 @@ extern "C" int srlx_r2d2_vec_step(const srlx_r2d2* r, int training, uintptr_t cu
   r2d2_act_kernel<<<(E + 127) / 128, 128, 0, s>>>(*r, training);
   count_launch();
   if (training && per) {
-    SRLX_CHECK_CUDA(cudaFuncSetAttribute(r2d2_add_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TreeHashScratch)));
-    r2d2_add_kernel<<<1, 1024, sizeof(TreeHashScratch), s>>>(*r);
+    r2d2_add_kernel<<<1, 1024, 0, s>>>(*r);
     count_launch();
   }
   r2d2_step_count_kernel<<<1, 1, 0, s>>>(eng.state, E);
@@ -869,6 +1323,14 @@ extern "C" int srlx_r2d2_learn(const srlx_r2d2* r, uint32_t n_updates, uintptr_t
   const int rows1 = (S + 1) * B, rowsS = S * B;
   const size_t zx = (size_t)(W + 2) * B * K, zc = (size_t)(W + 2) * B * u;
   const Gate gate{eng.state, (unsigned long long)eng.warmup_size};
+  // the persistent unroll needs every CTA resident at once (cooperative launch) and the per-thread weight slices in registers
+  static int n_sm = 0;
+  if (n_sm == 0) {
+    int dev = 0;
+    SRLX_CHECK_CUDA(cudaGetDevice(&dev));
+    SRLX_CHECK_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+  }
+  const bool persistent = !r->no_persistent && r->bar != nullptr && B <= 64 && u <= 512 && D + 1 <= 32 && 2 * ((u + 7) / 8) <= n_sm && (u + 3) / 4 <= n_sm;
   if (per) SRLX_CHECK_CUDA(cudaFuncSetAttribute(r2d2_priority_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TreeHashScratch)));
   for (uint32_t it = 0; it < n_updates; ++it) {
     // memory.sample (r2d2.py:91) + the batch layout of _train_on_batches (:109-133)
@@ -877,16 +1339,31 @@ extern "C" int srlx_r2d2_learn(const srlx_r2d2* r, uint32_t n_updates, uintptr_t
     r2d2_gather_kernel<<<B, 128, 0, s>>>(*r, gate);
     count_launch(2);
     // burn-in + unroll of both networks (:136-150): step t reads [x_t | h_{t-1} | 1] in time row t and leaves h_t in time row t + 1
-    for (int t = 0; t <= W; ++t) {
-      LstmFwdP lp{};
-      lp.xh = r->xh + (size_t)t * B * K; lp.z_xh = (long long)zx;
-      lp.W0 = r->params + r->lstm_off; lp.W1 = r->target + r->lstm_off;
-      lp.c_in = r->cbuf + (size_t)t * B * u; lp.c_out = r->cbuf + (size_t)(t + 1) * B * u; lp.z_c = (long long)zc;
-      lp.h_out = r->xh + (size_t)(t + 1) * B * K + D; lp.ld_h = K; lp.z_h = (long long)zx;
-      lp.gates = r->gates + (size_t)t * B * 4 * u; lp.M = B; lp.u = u; lp.K = K; lp.gate = gate;
-      if (B <= 32) lstm_fwd_kernel<32, 2><<<dim3((4 * u + 31) / 32, (B + 31) / 32, 2), 128, 0, s>>>(lp);
-      else lstm_fwd_kernel<64, 4><<<dim3((4 * u + 31) / 32, (B + 63) / 64, 2), 128, 0, s>>>(lp);
+    if (persistent) {
+      SRLX_CHECK_CUDA(cudaMemsetAsync(r->bar, 0, 4 * sizeof(unsigned), s));
+      SeqFwdP fp{};
+      fp.W0 = r->params + r->lstm_off; fp.W1 = r->target + r->lstm_off;
+      fp.xh = r->xh; fp.z_xh = (long long)zx; fp.cbuf = r->cbuf; fp.z_c = (long long)zc; fp.gates = r->gates; fp.bar = r->bar;
+      fp.B = B; fp.u = u; fp.D = D; fp.K = K; fp.T = W + 1; fp.cpn = (u + 7) / 8; fp.gate = gate;
+      void* args[] = {&fp};
+      const dim3 grid(2 * fp.cpn), block(256);
+      const void* fn = B <= 32 ? (const void*)lstm_seq_fwd_kernel<32> : (const void*)lstm_seq_fwd_kernel<64>;
+      const size_t smem = ((size_t)(B <= 32 ? 32 : 64) * kFwdXS + (size_t)32 * kFwdRedStride) * sizeof(float);
+      SRLX_CHECK_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      SRLX_CHECK_CUDA(cudaLaunchCooperativeKernel(fn, grid, block, args, smem, s));
       count_launch();
+    } else {
+      for (int t = 0; t <= W; ++t) {
+        LstmFwdP lp{};
+        lp.xh = r->xh + (size_t)t * B * K; lp.z_xh = (long long)zx;
+        lp.W0 = r->params + r->lstm_off; lp.W1 = r->target + r->lstm_off;
+        lp.c_in = r->cbuf + (size_t)t * B * u; lp.c_out = r->cbuf + (size_t)(t + 1) * B * u; lp.z_c = (long long)zc;
+        lp.h_out = r->xh + (size_t)(t + 1) * B * K + D; lp.ld_h = K; lp.z_h = (long long)zx;
+        lp.gates = r->gates + (size_t)t * B * 4 * u; lp.M = B; lp.u = u; lp.K = K; lp.gate = gate;
+        if (B <= 32) lstm_fwd_kernel<32, 2><<<dim3((4 * u + 31) / 32, (B + 31) / 32, 2), 128, 0, s>>>(lp);
+        else lstm_fwd_kernel<64, 4><<<dim3((4 * u + 31) / 32, (B + 63) / 64, 2), 128, 0, s>>>(lp);
+        count_launch();
+      }
     }
     // hidden block on the S + 1 unrolled steps of both networks
     for (int l = 0; l < r->n_head; ++l) {
@@ -918,7 +1395,7 @@ extern "C" int srlx_r2d2_learn(const srlx_r2d2* r, uint32_t n_updates, uintptr_t
       gw.B = in; gw.sb_k = ld_in; gw.sb_n = 1;
       gw.C = r->grads + r->head_off[l]; gw.ldc = r->head_k[l] + 1;
       gw.M = r->head_out[l]; gw.N = r->head_k[l] + 1; gw.K = rowsS; gw.gate = gate;
-      launch_gemm(gw, 1, s);
+      launch_gemm(gw, 1, s, r->gemm_ws, (size_t)r->gemm_ws_floats);
       GemmP gi{};  // d in_l = dO_l . W_l[:, :k_l], through the ReLU of the layer below
       gi.A = r->dact[l]; gi.sa_m = r->head_out[l]; gi.sa_k = 1;
       gi.B = r->params + r->head_off[l]; gi.sb_k = r->head_k[l] + 1; gi.sb_n = 1;
@@ -928,18 +1405,31 @@ extern "C" int srlx_r2d2_learn(const srlx_r2d2* r, uint32_t n_updates, uintptr_t
       launch_gemm(gi, 1, s);
     }
     // BPTT over the S trained steps; the burn-in state is a constant of the tape (:136-138)
-    for (int t = S - 1; t >= 0; --t) {
-      LstmBwdP bp{};
-      bp.dg_next = t == S - 1 ? nullptr : r->dgates + (size_t)(t + 1) * B * 4 * u;
-      bp.W = r->params + r->lstm_off; bp.in = D; bp.K = K;
-      bp.dh_head = r->dh + (size_t)t * B * u;
-      bp.gates = r->gates + (size_t)(r->burnin + t) * B * 4 * u;
-      bp.c_prev = r->cbuf + (size_t)(r->burnin + t) * B * u;
-      bp.c_cur = r->cbuf + (size_t)(r->burnin + t + 1) * B * u;
-      bp.dc = r->dc; bp.dg = r->dgates + (size_t)t * B * 4 * u; bp.M = B; bp.u = u; bp.first = t == S - 1; bp.gate = gate;
-      if (B <= 32) lstm_bwd_kernel<32, 2><<<dim3((u + 31) / 32, (B + 31) / 32, 1), 128, 0, s>>>(bp);
-      else lstm_bwd_kernel<64, 4><<<dim3((u + 31) / 32, (B + 63) / 64, 1), 128, 0, s>>>(bp);
+    if (persistent) {
+      SeqBwdP bp{};
+      bp.W = r->params + r->lstm_off; bp.K = K; bp.D = D;
+      bp.dh_head = r->dh; bp.gates = r->gates + (size_t)r->burnin * B * 4 * u; bp.cbuf = r->cbuf + (size_t)r->burnin * B * u;
+      bp.dgates = r->dgates; bp.bar = r->bar; bp.B = B; bp.u = u; bp.S = S; bp.n_cta = (u + 3) / 4; bp.gate = gate;
+      void* args[] = {&bp};
+      const void* fn = B <= 32 ? (const void*)lstm_seq_bwd_kernel<32> : (const void*)lstm_seq_bwd_kernel<64>;
+      const size_t smem = ((size_t)2 * (B <= 32 ? 32 : 64) * kBwdRow + (size_t)64 * kBwdRedStride) * sizeof(float);
+      SRLX_CHECK_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      SRLX_CHECK_CUDA(cudaLaunchCooperativeKernel(fn, dim3(bp.n_cta), dim3(256), args, smem, s));
       count_launch();
+    } else {
+      for (int t = S - 1; t >= 0; --t) {
+        LstmBwdP bp{};
+        bp.dg_next = t == S - 1 ? nullptr : r->dgates + (size_t)(t + 1) * B * 4 * u;
+        bp.W = r->params + r->lstm_off; bp.in = D; bp.K = K;
+        bp.dh_head = r->dh + (size_t)t * B * u;
+        bp.gates = r->gates + (size_t)(r->burnin + t) * B * 4 * u;
+        bp.c_prev = r->cbuf + (size_t)(r->burnin + t) * B * u;
+        bp.c_cur = r->cbuf + (size_t)(r->burnin + t + 1) * B * u;
+        bp.dc = r->dc; bp.dg = r->dgates + (size_t)t * B * 4 * u; bp.M = B; bp.u = u; bp.first = t == S - 1; bp.gate = gate;
+        if (B <= 32) lstm_bwd_kernel<32, 2><<<dim3((u + 31) / 32, (B + 31) / 32, 1), 128, 0, s>>>(bp);
+        else lstm_bwd_kernel<64, 4><<<dim3((u + 31) / 32, (B + 63) / 64, 1), 128, 0, s>>>(bp);
+        count_launch();
+      }
     }
     {
       GemmP gw{};  // dW_lstm = sum_t dgates_t^T . [x_t | h_{t-1} | 1]

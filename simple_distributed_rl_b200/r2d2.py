@@ -199,7 +199,7 @@ class R2D2NetSpec:
 
 class R2D2Engine:
     def __init__(self, cfg: R2D2Config, device="cuda:0", debug: bool = False, weights=None, track_episodes: bool = False,
-                 training: bool = True):
+                 training: bool = True, persistent: bool = True):
         self.lib = _lib.load()
         if not torch.cuda.is_available():
             raise _lib.SrlxError("R2D2Engine needs a CUDA device (no CPU fallback)")
@@ -215,6 +215,7 @@ class R2D2Engine:
         self.spec = R2D2NetSpec(D, u, cfg.hidden_layers, cfg.dueling_type, A)
         self.K = K = self.spec.K
         self.per = cfg.memory == "Proportional"
+        self.persistent = bool(persistent)
         self.R = R = max(2 * W, -(-cfg.capacity // E) + W - 1) if training else 2 * W
         if training and cfg.warmup_size > E * (R - (W - 1)):
             raise ValueError(f"warmup_size {cfg.warmup_size} exceeds the reachable memory size {E * (R - (W - 1))}")
@@ -254,7 +255,8 @@ class R2D2Engine:
                 ring_tstep=z(N, torch.int32), ring_h=z((N, u), torch.float32), ring_c=z((N, u), torch.float32),
                 new_c0=z(E, torch.int32), new_n=z(E, torch.int32),
                 xh=ones_last((2, W + 2, B, K)), cbuf=z((2, W + 2, B, u), torch.float32),
-                gates=z((W + 1, B, 4 * u), torch.float32), dgates=z((W + 1, B, 4 * u), torch.float32), dc=z((B, u), torch.float32),
+                gates=z((W + 1, B, 4 * u), torch.float32), dgates=z((W + 1, B, 4 * u), torch.float32), dc=z((B, u), torch.float32), bar=z(4, torch.int32),
+                gemm_ws=z(32 * max(out * (k + 1) for out, k, _ in head if out <= 32 or k + 1 <= 32) if any(out <= 32 or k + 1 <= 32 for out, k, _ in head) else 1, torch.float32),
                 dh=z(((S + 1) * B, u), torch.float32), q=z((2, B, S + 1, A), torch.float32),
                 sel=z(B, torch.int64), weights=torch.ones(B, dtype=torch.float32, device=dev),
                 b_actions=z((B, S), torch.int32), b_mu=torch.ones((B, S), dtype=torch.float64, device=dev), b_rewards=z((B, S), torch.float64),
@@ -300,9 +302,12 @@ class R2D2Engine:
                     getattr(c, nm)[l] = self.t[f"{nm}{l}"].data_ptr()
         c.lstm_off, c.n_params, c.test_epsilon = self.spec.lstm_off, self.spec.n_params, float(cfg.test_epsilon)
         c.duel_hidden = self.spec.H if self.spec.zero_mask is not None else 0
+        c.no_persistent = int(not self.persistent)
+        if "gemm_ws" in self.t:
+            c.gemm_ws_floats = self.t["gemm_ws"].numel()
         for k in ("params", "target", "adam_m", "adam_v", "grads", "cursor", "ring_obs", "ring_next_obs", "ring_action", "ring_prob",
                   "ring_reward", "ring_done", "ring_tstep", "ring_h", "ring_c", "roll_xh", "roll_h", "roll_c", "roll_reset", "new_c0", "new_n",
-                  "add_idx", "add_pri", "xh", "cbuf", "gates", "dgates", "dc", "dh", "q", "sel", "weights", "b_actions", "b_mu", "b_rewards",
+                  "add_idx", "add_pri", "xh", "cbuf", "gates", "dgates", "dc", "gemm_ws", "bar", "dh", "q", "sel", "weights", "b_actions", "b_mu", "b_rewards",
                   "b_dones", "b_target", "b_tdmean", "b_tdkind"):
             if k in self.t:
                 setattr(c, k, self.t[k].data_ptr())

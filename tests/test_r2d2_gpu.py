@@ -193,6 +193,14 @@ CASES = {
     "grid_naive_per_nodup": dict(env="Grid", dueling_type="", memory="Proportional", per_has_duplicate=False, burnin=3, sequence_length=2,
                                  lstm_units=8, hidden_layers=(8,)),
     "cartpole_batch40_two_row_tiles": dict(batch_size=40, warmup_size=40, n_envs=9, lstm_units=40, hidden_layers=(70,), capacity=9 * 64),
+    # batch sizes that are multiples of 32 stage the recurrent input with cp.async
+    "cartpole_batch32_cp_async": dict(batch_size=32, warmup_size=32, n_envs=8, lstm_units=24, capacity=8 * 64, memory="Proportional"),
+    "pendulum_batch64_cp_async": dict(env="Pendulum-v1", batch_size=64, warmup_size=64, n_envs=12, lstm_units=40, hidden_layers=(20,),
+                                      dueling_type=None, capacity=12 * 64, enable_rescale=True),
+    # one launch per time step instead of the persistent unroll kernels (the path shapes outside their limits take)
+    "cartpole_step_launches": dict(_persistent=False),
+    "pendulum_per_step_launches_batch40": dict(env="Pendulum-v1", memory="Proportional", batch_size=40, warmup_size=40, n_envs=9, lstm_units=40,
+                                               capacity=9 * 64, _persistent=False),
 }
 
 
@@ -204,8 +212,10 @@ def test_lockstep_rollout_replay_and_updates(name):
     dones, hidden state, both kinds of padding), PER leaf selection and IS weights against the oracle memory on the device's tree
     (exact / 1e-6), Q / targets / loss / mean TD (1e-4), gradients (1e-3), parameters after keras Adam (1e-4), priorities in the
     tree (1e-12), target sync and counters."""
-    cfg = _cfg(**CASES[name])
-    eng = _engine(cfg)
+    kw = dict(CASES[name])
+    persistent = kw.pop("_persistent", True)
+    cfg = _cfg(**kw)
+    eng = _engine(cfg, persistent=persistent)
     twin = _Twin(eng)
     tr = _trainer(eng, eng.get_weights())
     n_upd = 0
@@ -368,3 +378,27 @@ def test_learning_pendulum_reference_acceptance_gate():
     r.train(max_train_count=200 * 35 * 2, train_interval=1)
     rewards = r.evaluate(max_episodes=10)
     assert np.mean(rewards) >= -500, rewards
+
+
+@pytest.mark.parametrize("M,N,K", [(7, 5, 3), (40, 33, 70), (200, 150, 37), (1300, 1100, 129), (64, 2048, 517), (2048, 517, 640)])
+@pytest.mark.parametrize("a_t,b_t", [(False, False), (True, False), (False, True), (True, True)])
+def test_strided_sgemm_every_tile_variant(M, N, K, a_t, b_t):
+    """srlx_sgemm (the map every R2D2 layer runs on) for row- and column-major operands, odd leading dimensions, ReLU and accumulate,
+    against torch fp64."""
+    from simple_distributed_rl_b200 import _lib
+
+    lib = _lib.load()
+    g = torch.Generator(device="cuda").manual_seed(M * 7 + N)
+    lda, ldb = (M + 3 if a_t else K + 1), (K + 5 if b_t else N + 2)
+    a = torch.randn((K, lda) if a_t else (M, lda), device="cuda", generator=g)
+    b = torch.randn((N, ldb) if b_t else (K, ldb), device="cuda", generator=g)
+    A = a[:, :M].T if a_t else a[:, :K]
+    Bm = b[:, :K].T if b_t else b[:, :N]
+    c = torch.randn(M, N + 1, device="cuda", generator=g)
+    want = torch.relu(c[:, :N].double() + A.double() @ Bm.double())
+    sa = (1, lda) if a_t else (lda, 1)
+    sb = (1, ldb) if b_t else (ldb, 1)
+    _lib.check(lib.srlx_sgemm(a.data_ptr(), sa[0], sa[1], b.data_ptr(), sb[0], sb[1], c.data_ptr(), N + 1, M, N, K, 1, 1,
+                              torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(c[:, :N].cpu().numpy(), want.float().cpu().numpy(), rtol=2e-5, atol=2e-5 * K ** 0.5)
