@@ -22,6 +22,37 @@ def timed(fn, n):
     return a.elapsed_time(b) / n
 
 
+def cpu_port(eng, n):
+    """oracle/r2d2.py (the torch restatement of Trainer._train_on_batches + keras Adam) on the host cores, same shapes, random batch"""
+    import time
+
+    import numpy as np
+
+    from oracle import r2d2 as orc
+
+    c = eng.cfg
+    tr = orc.Trainer(eng.get_weights(), len(c.hidden_layers) - (0 if c.dueling_type is None else 1), c.dueling_type, c.burnin,
+                     c.sequence_length, c.discount, c.lr, c.target_model_update_interval, c.enable_double_dqn, c.enable_rescale,
+                     c.enable_retrace, c.retrace_h)
+    rng = np.random.default_rng(0)
+    B, S, W1 = eng.B, eng.S, eng.W + 1
+    states = rng.normal(size=(B, W1, eng.D)).astype(np.float32)
+    actions = rng.integers(0, eng.A, size=(B, S)).tolist()
+    probs = np.full((B, S), 0.5).tolist()
+    rewards = rng.normal(size=(B, S)).tolist()
+    dones = np.zeros((B, S), bool).tolist()
+    h0 = np.zeros((B, eng.u), np.float32)
+    times = []
+    for i in range(n + 1):
+        t0 = time.perf_counter()
+        out = tr.train_on_batches(states, actions, probs, rewards, dones, h0, h0, np.ones(B, np.float32))
+        tr.apply(out["grads"])
+        times.append(time.perf_counter() - t0)
+    ms = 1e3 * float(np.mean(times[1:]))
+    return dict(kind="port", update_ms=ms, updates_per_s=1e3 / ms, cores=torch.get_num_threads(),
+                sample=f"{n} updates of oracle/r2d2.py (torch fp32 CPU) on a random batch of the same shape after 1 warm-up")
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--env", default="CartPole-v1")
@@ -33,6 +64,8 @@ def main():
     ap.add_argument("--rows", type=int, default=512)
     ap.add_argument("--memory", default="Proportional")
     ap.add_argument("--out", default="")
+    ap.add_argument("--cpu-baseline", type=int, default=0, help="time N updates of the CPU port (oracle/r2d2.py, torch fp32, all host threads) "
+                    "on a batch of the same shape: the reference's own R2D2 is TensorFlow-only and cannot run here")
     a = ap.parse_args()
     cfg = R2D2Config(env=a.env, n_envs=a.n_envs, lstm_units=a.units, hidden_layers=(512,), dueling_type="average", burnin=a.burnin,
                      sequence_length=a.seq, batch_size=a.batch, capacity=a.n_envs * a.rows, warmup_size=a.n_envs * 4, memory=a.memory,
@@ -62,6 +95,8 @@ def main():
                vec_step_ms=step_ms, env_steps_per_s=a.n_envs / step_ms * 1e3, update_ms_eager=learn_ms, update_ms_graph=graph_ms,
                updates_per_s_graph=1e3 / graph_ms, launches_per_update=int(launches), lstm_tflops_graph=flops / graph_ms / 1e9,
                train_count=int(st.train_count), loss=st.last_loss, mem_size=int(st.mem_size))
+    if a.cpu_baseline > 0:
+        out["cpu_baseline"] = cpu_port(eng, a.cpu_baseline)
     print(json.dumps(out))
     if a.out:
         json.dump(out, open(a.out, "w"), indent=1)
