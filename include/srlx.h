@@ -371,6 +371,28 @@ int srlx_tree_sample(const double* tree, uint64_t capacity, srlx_state* meta, ui
  * max_priority (proportional_memory.py:171-177). */
 int srlx_tree_update(double* tree, uint64_t capacity, srlx_state* meta, const int64_t* tree_idx_dev,
                      const float* priorities_dev, uint32_t n, double alpha, double epsilon, uintptr_t cuda_stream);
+/* The whole seam in one launch per sample(): the add / update calls made since the last sample (op list in program order; idx >= 0:
+ * update of that tree index with raw priority val; -1: add with raw priority; -2: add with priority None; -3: add with the stored
+ * priority, ProportionalMemory.restore) are applied with the reference's sequential association, then `batch` items are drawn
+ * (batch == 0: apply only).  ops_* / out_* / flag may be mapped pinned HOST memory (srlx_host_alloc): the kernel reads and writes it
+ * directly and stores `seq` into *flag last, so the host polls one word instead of synchronising the stream. */
+int srlx_tree_seam(double* tree_dev, uint64_t capacity, srlx_state* meta_dev, const int64_t* ops_idx, const double* ops_val, uint32_t n_ops,
+                   double alpha, double epsilon, uint32_t batch, uint64_t step, double beta_initial, double beta_steps, int has_duplicate,
+                   uint64_t seed, const double* u01_dev, uint32_t max_tries, int64_t* out_tree_idx, float* out_weights,
+                   unsigned long long* flag, unsigned long long seq, uintptr_t cuda_stream);
+/* the same call with its per-memory constants in a caller-owned HOST struct (fewer arguments to marshal per call) */
+typedef struct srlx_seam {
+  double* tree; srlx_state* meta; const int64_t* ops_idx; const double* ops_val; int64_t* out_tree_idx; float* out_weights;
+  unsigned long long* flag;
+  uint64_t capacity;
+  double alpha, epsilon, beta_initial, beta_steps;
+  int32_t has_duplicate, reserved;
+} srlx_seam;
+int srlx_tree_seam_desc(const srlx_seam* desc, uint32_t n_ops, uint32_t batch, uint64_t step, uint64_t seed, const double* u01_dev,
+                        uint32_t max_tries, unsigned long long seq, uintptr_t cuda_stream);
+/* mapped pinned host memory (zeroed): *host_ptr for the CPU, *dev_ptr for kernels */
+int srlx_host_alloc(size_t bytes, void** host_ptr, void** dev_ptr);
+int srlx_host_free(void* host_ptr);
 /* descend only: out_tree_idx[i] = SumTree._retrieve(tree, 0, vals[i]) (proportional_memory.py:57-66). */
 int srlx_tree_retrieve(const double* tree, uint64_t capacity, const double* vals_dev, uint32_t n,
                        int64_t* out_tree_idx, uintptr_t cuda_stream);

@@ -132,6 +132,12 @@ class SrlxR2d2(C.Structure):
     ]
 
 
+class SrlxSeam(C.Structure):
+    _fields_ = [("tree", _P), ("meta", _P), ("ops_idx", _P), ("ops_val", _P), ("out_tree_idx", _P), ("out_weights", _P), ("flag", _P),
+                ("capacity", C.c_uint64), ("alpha", C.c_double), ("epsilon", C.c_double), ("beta_initial", C.c_double),
+                ("beta_steps", C.c_double), ("has_duplicate", C.c_int32), ("reserved", C.c_int32)]
+
+
 class SrlxError(RuntimeError):
     pass
 
@@ -152,6 +158,10 @@ SYMBOLS = [
     ("srlx_tree_add", C.c_int, [_P, _u64, _P, _P, _u64, _dbl, _dbl, _i32, _uptr]),
     ("srlx_tree_sample", C.c_int, [_P, _u64, _P, _u32, _u64, _dbl, _dbl, _i32, _u64, _P, _u32, _P, _P, _P, _uptr]),
     ("srlx_tree_update", C.c_int, [_P, _u64, _P, _P, _P, _u32, _dbl, _dbl, _uptr]),
+    ("srlx_tree_seam", C.c_int, [_P, _u64, _P, _P, _P, _u32, _dbl, _dbl, _u32, _u64, _dbl, _dbl, _i32, _u64, _P, _u32, _P, _P, _P, _u64, _uptr]),
+    ("srlx_tree_seam_desc", C.c_int, [C.POINTER(SrlxSeam), _u32, _u32, _u64, _u64, _P, _u32, _u64, _uptr]),
+    ("srlx_host_alloc", C.c_int, [_sz, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
+    ("srlx_host_free", C.c_int, [_P]),
     ("srlx_tree_retrieve", C.c_int, [_P, _u64, _P, _u32, _P, _uptr]),
     ("srlx_engine_reset", C.c_int, [C.POINTER(SrlxEngine), _uptr]),
     ("srlx_engine_run", C.c_int, [C.POINTER(SrlxEngine), _u32, _u32, _i32, _uptr]),

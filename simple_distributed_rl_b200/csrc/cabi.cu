@@ -4,6 +4,7 @@
 
 #include <atomic>
 
+#include <string.h>
 #include "net.cuh"
 #include "tree.cuh"
 
@@ -127,6 +128,105 @@ tree_update_kernel(double* tree, srlx_state* meta, const int64_t* idx, const flo
     double mp = meta->max_priority;
     for (int i = 0; i < (int)n; ++i) mp = (mp < s_pri[i]) ? s_pri[i] : mp;
     meta->max_priority = mp;
+  }
+}
+
+// The IPriorityMemory seam in ONE launch per sample(): the add / update calls the host made since the last sample (an op list in
+// program order, read straight from mapped pinned host memory) are applied with the reference's sequential association, then the
+// batch is drawn and the results go straight back to mapped host memory, followed by a sequence word the host polls -- no stream
+// synchronisation, no staging copies.  op idx >= 0: update of that tree index with raw priority val; -1: add with raw priority val;
+// -2: add with priority None (takes max_priority AS OF that point of the sequence); -3: add with the stored priority val (restore).
+constexpr int64_t kOpAdd = -1, kOpAddNone = -2, kOpAddRaw = -3;
+__global__ void __launch_bounds__(kTreeThreads)
+tree_seam_kernel(double* tree, uint64_t capacity, srlx_state* meta, const int64_t* __restrict__ ops_idx, const double* __restrict__ ops_val,
+                 uint32_t n_ops, double alpha, double epsilon, uint32_t batch, uint64_t step, double beta_initial, double beta_steps,
+                 int has_duplicate, uint64_t seed, const double* u01, uint32_t max_tries, int64_t* out_idx, float* out_w,
+                 volatile unsigned long long* flag, unsigned long long seq) {
+  extern __shared__ __align__(16) unsigned char tree_smem[];
+  TreeHashScratch* hs = reinterpret_cast<TreeHashScratch*>(tree_smem);
+  __shared__ int64_t s_idx[kTreeMaxBatch];
+  __shared__ double s_pri[kTreeMaxBatch];
+  __shared__ double s_tmp[kTreeMaxBatch];
+  __shared__ float s_w[kTreeMaxBatch];
+  __shared__ unsigned long long retries;
+  __shared__ unsigned long long s_write, s_size;
+  __shared__ double s_maxp;
+  if (threadIdx.x == 0) {
+    retries = 0;
+    s_write = meta->vec_steps;
+    s_size = meta->mem_size;
+    s_maxp = meta->max_priority;
+  }
+  __syncthreads();
+  for (uint32_t base = 0; base < n_ops; base += kTreeHashChunk) {
+    const int m = (int)min((uint32_t)kTreeHashChunk, n_ops - base);
+    if ((int)threadIdx.x < m) {
+      const int64_t k = ops_idx[base + threadIdx.x];
+      const double v = ops_val[base + threadIdx.x];
+      s_idx[threadIdx.x] = k;
+      s_pri[threadIdx.x] = (k >= 0 || k == kOpAdd) ? pow(fabs(v) + epsilon, alpha) : v;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {  // cursor, size and max_priority advance in program order
+      unsigned long long w = s_write, sz = s_size;
+      double mp = s_maxp;
+      for (int i = 0; i < m; ++i) {
+        const int64_t k = s_idx[i];
+        if (k >= 0) {
+          mp = (mp < s_pri[i]) ? s_pri[i] : mp;
+        } else {
+          if (k == kOpAddNone) s_pri[i] = mp;
+          s_idx[i] = (int64_t)w + (int64_t)capacity - 1;
+          w = (w + 1) % capacity;
+          sz = sz < capacity ? sz + 1 : capacity;
+        }
+      }
+      s_write = w; s_size = sz; s_maxp = mp;
+    }
+    __syncthreads();
+    if (m <= 4) {  // a lone add between two samples: one warp, lane = level above the leaf, one L2 round trip per item
+      if (threadIdx.x < 32) {
+        for (int i = 0; i < m; ++i) {
+          const uint64_t ip1 = (uint64_t)s_idx[i] + 1;
+          const int l = threadIdx.x;
+          const bool on = (ip1 >> l) != 0;
+          const uint64_t node = on ? (ip1 >> l) - 1 : 0;
+          double v = on ? __ldcg(tree + node) : 0.0;
+          const double change = s_pri[i] - __shfl_sync(0xffffffffu, v, 0);
+          if (on) __stcg(tree + node, l == 0 ? s_pri[i] : v + change);
+          __syncwarp();
+        }
+      }
+      __syncthreads();
+    } else {
+      tree_update_batch(tree, s_idx, s_pri, m, hs);
+    }
+  }
+  if (threadIdx.x == 0 && n_ops) {
+    meta->vec_steps = s_write;
+    meta->mem_size = s_size;
+    meta->max_priority = s_maxp;
+  }
+  if (batch) {
+    __threadfence_block();
+    __syncthreads();
+    const double total = __ldcg(tree);
+    double beta = beta_initial + (1.0 - beta_initial) * (double)step / beta_steps;
+    if (beta > 1.0) beta = 1.0;
+    per_sample_block(tree, 2 * (int64_t)capacity - 1, total, (int)batch, seed, step, u01, (int)max_tries, has_duplicate, s_idx, s_pri,
+                     s_tmp, &retries);
+    per_weights_block(total, (double)s_size, beta, (int)batch, s_pri, s_tmp, s_w);
+    for (int i = threadIdx.x; i < (int)batch; i += blockDim.x) {
+      out_idx[i] = s_idx[i];
+      out_w[i] = s_w[i];
+    }
+    if (threadIdx.x == 0) meta->sample_retries += retries;
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0 && flag) {
+    *flag = seq;
+    __threadfence_system();
   }
 }
 
@@ -261,6 +361,49 @@ extern "C" int srlx_tree_update(double* tree, uint64_t capacity, srlx_state* met
                                                                                              alpha, epsilon);
   count_launch();
   SRLX_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int srlx_tree_seam(double* tree, uint64_t capacity, srlx_state* meta, const int64_t* ops_idx, const double* ops_val, uint32_t n_ops,
+                              double alpha, double epsilon, uint32_t batch, uint64_t step, double beta_initial, double beta_steps,
+                              int has_duplicate, uint64_t seed, const double* u01_dev, uint32_t max_tries, int64_t* out_tree_idx,
+                              float* out_weights, unsigned long long* flag, unsigned long long seq, uintptr_t cuda_stream) {
+  SRLX_REQUIRE(tree && meta && capacity >= 1, "srlx_tree_seam: bad arguments");
+  SRLX_REQUIRE(n_ops == 0 || (ops_idx && ops_val), "srlx_tree_seam: op list is NULL");
+  SRLX_REQUIRE(batch <= (uint32_t)kTreeMaxBatch, "srlx_tree_seam: batch %u > %d", batch, kTreeMaxBatch);
+  SRLX_REQUIRE(batch == 0 || (out_tree_idx && out_weights), "srlx_tree_seam: output buffer is NULL");
+  SRLX_REQUIRE(batch == 0 || (max_tries >= 1 && max_tries <= 9999), "srlx_tree_seam: max_tries %u out of range [1,9999]", max_tries);
+  SRLX_REQUIRE(capacity < (1ull << 30), "srlx_tree_seam: capacity %llu too large (node ids are 32-bit)", (unsigned long long)capacity);
+  static bool attr_set = false;
+  if (!attr_set) {
+    SRLX_CHECK_CUDA(cudaFuncSetAttribute(tree_seam_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TreeHashScratch)));
+    attr_set = true;
+  }
+  tree_seam_kernel<<<1, kTreeThreads, sizeof(TreeHashScratch), (cudaStream_t)cuda_stream>>>(
+      tree, capacity, meta, ops_idx, ops_val, n_ops, alpha, epsilon, batch, step, beta_initial, beta_steps, has_duplicate, seed, u01_dev,
+      max_tries, out_tree_idx, out_weights, flag, seq);
+  count_launch();
+  SRLX_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int srlx_tree_seam_desc(const srlx_seam* d, uint32_t n_ops, uint32_t batch, uint64_t step, uint64_t seed, const double* u01_dev,
+                                   uint32_t max_tries, unsigned long long seq, uintptr_t cuda_stream) {
+  SRLX_REQUIRE(d != nullptr, "srlx_tree_seam_desc: descriptor is NULL");
+  return srlx_tree_seam(d->tree, d->capacity, d->meta, d->ops_idx, d->ops_val, n_ops, d->alpha, d->epsilon, batch, step, d->beta_initial,
+                        d->beta_steps, d->has_duplicate, seed, u01_dev, max_tries, d->out_tree_idx, d->out_weights, d->flag, seq, cuda_stream);
+}
+
+extern "C" int srlx_host_alloc(size_t bytes, void** host_ptr, void** dev_ptr) {
+  SRLX_REQUIRE(host_ptr && dev_ptr && bytes > 0, "srlx_host_alloc: bad arguments");
+  SRLX_CHECK_CUDA(cudaHostAlloc(host_ptr, bytes, cudaHostAllocMapped | cudaHostAllocPortable));
+  SRLX_CHECK_CUDA(cudaHostGetDevicePointer(dev_ptr, *host_ptr, 0));
+  memset(*host_ptr, 0, bytes);
+  return 0;
+}
+
+extern "C" int srlx_host_free(void* host_ptr) {
+  if (host_ptr) SRLX_CHECK_CUDA(cudaFreeHost(host_ptr));
   return 0;
 }
 

@@ -22,6 +22,14 @@ from . import _lib
 
 
 class DeviceProportionalMemory:
+    """One kernel launch per `sample()`: `add` / `update` only append to an op list in mapped pinned host memory; the next `sample`
+    (or anything that reads the tree) launches `srlx_tree_seam`, which applies the list in program order with the reference's
+    sequential association, draws the batch, and writes indices, weights and a sequence word straight back into mapped host memory,
+    where the host polls the word -- no stream synchronisation, no staging copies, no per-call allocations."""
+
+    MAX_OPS = 4096
+    MAX_BATCH = 1024
+
     def __init__(self, capacity: int, alpha: float = 0.6, beta_initial: float = 0.4, beta_steps: int = 1_000_000,
                  has_duplicate: bool = True, epsilon: float = 0.0001, device="cuda:0", seed: int = 0):
         self.lib = _lib.load()
@@ -35,13 +43,86 @@ class DeviceProportionalMemory:
         self._tree = torch.zeros(2 * self.capacity - 1, dtype=torch.float64, device=self.device)
         self._meta = torch.zeros(C.sizeof(_lib.SrlxState), dtype=torch.uint8, device=self.device)
         self._draws = 0
+        # mapped pinned host memory: 2 x [ops_idx int64 x MAX_OPS | ops_val float64 x MAX_OPS] | out_idx int64 x MAX_BATCH | out_w float32 x
+        # MAX_BATCH | flag uint64.  Two op lists, so that a launch can be left running (`_launch(wait=False)`) while the host fills
+        # the other one.  (Launching the apply kernel eagerly from `update` was measured: the second launch per epoch costs more host time
+        # than the overlap saves, 63 vs 57 us per epoch of the reference's speed-test; `update` only appends.)
+        nb = 2 * self.MAX_OPS * 16 + self.MAX_BATCH * 12 + 8
+        hp, dp = C.c_void_p(), C.c_void_p()
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.srlx_host_alloc(nb, C.byref(hp), C.byref(dp)))
+        self._host_ptr, base = hp.value, dp.value
+        view = lambda ct, n, off: np.ctypeslib.as_array((ct * n).from_address(hp.value + off))  # noqa: E731
+        ob = self.MAX_OPS * 16  # bytes of one op list
+        o2, o3, o4 = 2 * ob, 2 * ob + self.MAX_BATCH * 8, 2 * ob + self.MAX_BATCH * 12
+        self._bufs = [(view(C.c_int64, self.MAX_OPS, k * ob), view(C.c_double, self.MAX_OPS, k * ob + self.MAX_OPS * 8)) for k in (0, 1)]
+        self._out_idx, self._out_w = view(C.c_int64, self.MAX_BATCH, o2), view(C.c_float, self.MAX_BATCH, o3)
+        self._flag = view(C.c_uint64, 1, o4)
+        self._n_ops, self._seq, self._cur, self._buf_seq = 0, 0, 0, [0, 0]
+        self._descs = []
+        for k in (0, 1):
+            d = _lib.SrlxSeam()
+            d.tree, d.meta, d.ops_idx, d.ops_val = self._tree.data_ptr(), self._meta.data_ptr(), base + k * ob, base + k * ob + self.MAX_OPS * 8
+            d.out_tree_idx, d.out_weights, d.flag, d.capacity = base + o2, base + o3, base + o4, self.capacity
+            d.alpha, d.epsilon, d.beta_initial, d.beta_steps = self.alpha, self.epsilon, self.beta_initial, self.beta_steps
+            d.has_duplicate = int(self.has_duplicate)
+            self._descs.append((d, C.byref(d)))
+        self._ops_idx, self._ops_val = self._bufs[0]
+        self._call, self._dev_index = self.lib.srlx_tree_seam_desc, self.device.index or 0
         self.clear()
+
+    def __del__(self):
+        try:
+            if getattr(self, "_host_ptr", None):
+                torch.cuda.synchronize(self.device)
+                self.lib.srlx_host_free(self._host_ptr)
+                self._host_ptr = None
+        except Exception:
+            pass
 
     # -- helpers
     def _s(self):
         return torch.cuda.current_stream(self.device).cuda_stream
 
+    def _launch(self, batch: int, step: int, u_ptr, max_tries: int, wait: bool = True):
+        """apply the pending ops of the current list, then draw `batch` items (0: apply only).  wait: return when the kernel's sequence
+        word has arrived; else return at once and continue in the other op list."""
+        self._seq += 1
+        self._draws += 1 if batch else 0
+        seed = (self.seed * 0x9E3779B97F4A7C15 + self._draws) & 0xFFFFFFFFFFFFFFFF
+        ref = self._descs[self._cur][1]
+        if torch.cuda.current_device() != self._dev_index:
+            with torch.cuda.device(self.device):
+                rc = self._call(ref, self._n_ops, batch, max(int(step), 0), seed, u_ptr, max_tries, self._seq, self._s())
+        else:
+            rc = self._call(ref, self._n_ops, batch, max(int(step), 0), seed, u_ptr, max_tries, self._seq, self._s())
+        if rc:
+            _lib.check(rc)
+        self._n_ops = 0
+        if wait:
+            self._wait(self._seq)
+        else:
+            self._buf_seq[self._cur] = self._seq
+            self._cur ^= 1
+            self._ops_idx, self._ops_val = self._bufs[self._cur]
+            self._wait(self._buf_seq[self._cur])  # the launch that read the list we are about to fill (long done)
+
+    def _wait(self, seq: int):
+        flag, spins = self._flag, 0
+        while flag[0] < seq:
+            spins += 1
+            if spins > 20_000_000:  # ~10 s: surface a dead kernel instead of spinning forever
+                torch.cuda.synchronize(self.device)
+                if flag[0] < seq:
+                    raise _lib.SrlxError("srlx_tree_seam did not complete")
+
+    def _flush(self):
+        if self._n_ops:
+            self._launch(0, 0, None, 1)
+        self._wait(self._seq)
+
     def _read_meta(self) -> "_lib.SrlxState":
+        self._flush()
         return _lib.SrlxState.from_buffer_copy(self._meta.cpu().numpy().tobytes())
 
     def _write_meta(self, st):
@@ -49,6 +130,8 @@ class DeviceProportionalMemory:
 
     # -- IPriorityMemory (imemory.py:7-34)
     def clear(self) -> None:
+        self._wait(self._seq)
+        self._n_ops = 0
         _lib.check(self.lib.srlx_tree_clear(self._tree.data_ptr(), self.capacity, self._meta.data_ptr(), self._s()))
         self.data: List[Any] = [None] * self.capacity
         self._write = 0
@@ -58,42 +141,47 @@ class DeviceProportionalMemory:
         return self._size
 
     def add(self, batch: Any, priority: Optional[float] = None, _restore_skip: bool = False) -> None:
-        pr = None
-        ptr = None
-        if priority is not None:
-            pr = torch.tensor([float(priority)], dtype=torch.float64, device=self.device)
-            ptr = pr.data_ptr()
-        _lib.check(self.lib.srlx_tree_add(self._tree.data_ptr(), self.capacity, self._meta.data_ptr(), ptr, 1, self.alpha,
-                                          self.epsilon, int(_restore_skip), self._s()))
-        self.data[self._write] = batch
-        self._write = (self._write + 1) % self.capacity
-        self._size = min(self._size + 1, self.capacity)
+        n = self._n_ops
+        if n == self.MAX_OPS:
+            self._flush()
+            n = 0
+        if priority is None:
+            self._ops_idx[n] = -2
+        else:
+            self._ops_idx[n] = -3 if _restore_skip else -1
+            self._ops_val[n] = priority
+        self._n_ops = n + 1
+        w = self._write
+        self.data[w] = batch
+        self._write = w + 1 if w + 1 < self.capacity else 0
+        if self._size < self.capacity:
+            self._size += 1
 
     def sample(self, batch_size: int, step: int, uniforms: Optional[np.ndarray] = None):
-        idx = torch.empty(batch_size, dtype=torch.int64, device=self.device)
-        w = torch.empty(batch_size, dtype=torch.float32, device=self.device)
+        if not 1 <= batch_size <= self.MAX_BATCH:
+            raise ValueError(f"batch_size {batch_size} out of range [1, {self.MAX_BATCH}]")
         u_ptr, max_tries = None, 9999
         if uniforms is not None:
             u = torch.as_tensor(np.ascontiguousarray(uniforms, dtype=np.float64)).to(self.device)
             u_ptr, max_tries = u.data_ptr(), int(u.shape[1])
         # the Philox stream is keyed by (seed, draw counter) so consecutive sample() calls are independent draws
-        self._draws += 1
-        seed = (self.seed * 0x9E3779B97F4A7C15 + self._draws) & 0xFFFFFFFFFFFFFFFF
-        _lib.check(self.lib.srlx_tree_sample(self._tree.data_ptr(), self.capacity, self._meta.data_ptr(), batch_size, max(int(step), 0),
-                                             self.beta_initial, self.beta_steps, int(self.has_duplicate), seed, u_ptr, max_tries,
-                                             idx.data_ptr(), w.data_ptr(), None, self._s()))
-        indices = idx.cpu().numpy().tolist()
-        batches = [self.data[i - (self.capacity - 1)] for i in indices]
-        return batches, w.cpu().numpy(), indices
+        self._launch(int(batch_size), step, u_ptr, max_tries)
+        indices = self._out_idx[:batch_size].tolist()
+        data, off = self.data, self.capacity - 1
+        return [data[i - off] for i in indices], self._out_w[:batch_size].copy(), indices
 
     def update(self, indices: List[Any], priorities: np.ndarray) -> None:
         n = len(indices)
         if n == 0:
             return
-        idx = torch.as_tensor(np.asarray(indices, dtype=np.int64)).to(self.device)
-        pr = torch.as_tensor(np.asarray(priorities, dtype=np.float32)).to(self.device)
-        _lib.check(self.lib.srlx_tree_update(self._tree.data_ptr(), self.capacity, self._meta.data_ptr(), idx.data_ptr(),
-                                             pr.data_ptr(), n, self.alpha, self.epsilon, self._s()))
+        if n > self.MAX_OPS:
+            raise ValueError(f"update of {n} items at once (max {self.MAX_OPS})")
+        if self._n_ops + n > self.MAX_OPS:
+            self._flush()
+        a = self._n_ops
+        self._ops_idx[a:a + n] = indices
+        self._ops_val[a:a + n] = np.asarray(priorities, dtype=np.float32)  # the trainer hands float32 TD errors
+        self._n_ops = a + n
 
     def backup(self):
         st = self._read_meta()
@@ -119,6 +207,7 @@ class DeviceProportionalMemory:
         return float(self._read_meta().max_priority)
 
     def tree_array(self) -> np.ndarray:
+        self._flush()
         return self._tree.cpu().numpy()
 
 

@@ -7,8 +7,9 @@ the figure is the wall time of the whole run.  Arms:
   python   the reference's ProportionalMemory (srl/rl/memories/priority_memories/proportional_memory.py), only where
            /root/reference is importable (the build container); elsewhere the oracle's restatement (oracle/sumtree.py) stands in
   cpp      the reference's pybind11 module compiled from its own sources (oracle/_ref, built by oracle/Makefile)
-  seam     DeviceProportionalMemory driven item by item through the IPriorityMemory methods, host lists in and out
-           (one launch + host round trips per call: the drop-in seam, latency-bound by design)
+  seam     DeviceProportionalMemory driven item by item through the IPriorityMemory methods, host lists in and out: add / update
+           append to an op list in mapped pinned host memory, every sample() is ONE launch (srlx_tree_seam) that applies the list,
+           draws the batch and writes the results + a sequence word back to mapped host memory, which the host polls
   device   the same three C-ABI calls (srlx_tree_add / _sample / _update) with every operand resident in HBM and no host
            synchronisation inside the loop: what a device-side consumer sees (3 launches per epoch)
   fused    for scale: the fused engine does add (8192 leaves) / sample / update inside rollout + learner kernels; its SumTree
@@ -93,7 +94,7 @@ def arm_cpp():
 def arm_seam():
     from simple_distributed_rl_b200.memory import DeviceProportionalMemory
 
-    return "DeviceProportionalMemory (IPriorityMemory seam)", DeviceProportionalMemory(CAPACITY, ALPHA, BETA0, BETA_STEPS, has_duplicate=True)
+    return "DeviceProportionalMemory (IPriorityMemory seam: one launch per sample, mapped host memory)", DeviceProportionalMemory(CAPACITY, ALPHA, BETA0, BETA_STEPS, has_duplicate=True)
 
 
 def run_device_resident(epochs=EPOCHS):
