@@ -200,6 +200,11 @@ typedef struct srlx_engine {
   void* dp_peer[8];       /* dp_peer[r]: the exchange buffer of rank r as addressable from this rank (own: srlx_dp_alloc or any
                              zeroed device buffer of srlx_dp_bytes(); peers: srlx_dp_open of their IPC handle, or a peer-enabled pointer) */
   uint64_t dp_bytes;      /* size of every exchange buffer */
+  /* ---- invalid-action masks (dqn.py:156-165 with its batch-minimum fill, rainbow_nomultisteps.py:19-31, rainbow.py:236-252 with
+   *      -inf per window step): bit a of ring_invalid[slot] = action a is invalid in that row's NEXT state.  NULL: the env has no
+   *      invalid actions (the device envs).  Rows enter through srlx_ext_step_masked; the generic learner (csrc/learner.cu) reads
+   *      them, and srlx_learn dispatches to it whenever the buffer is present ---- */
+  uint32_t* ring_invalid; /* [R*E] or NULL */
 } srlx_engine;
 
 /* ---- PPO (R15; BASELINE configs[4]) -- csrc/ppo.cu restates srl/algorithms/ppo/ppo.py for E vectorised env copies ------------------- */
@@ -477,6 +482,10 @@ int srlx_learn(const srlx_engine* eng, uint32_t n_updates, uintptr_t cuda_stream
  *                  -> (next observation [E][D] float32, raw reward f64, terminated, truncated at trunc_limit).  No policy, no ring. */
 int srlx_ext_step(const srlx_engine* eng, const float* obs_dev, const float* next_obs_dev, const int32_t* action_dev,
                   const float* reward_dev, const unsigned char* term_dev, const unsigned char* done_dev, uintptr_t cuda_stream);
+/* srlx_ext_step with the next state's invalid-action mask of every record (bit a = action a invalid; NULL = none) */
+int srlx_ext_step_masked(const srlx_engine* eng, const float* obs_dev, const float* next_obs_dev, const int32_t* action_dev,
+                         const float* reward_dev, const unsigned char* term_dev, const unsigned char* done_dev,
+                         const uint32_t* next_invalid_dev, uintptr_t cuda_stream);
 int srlx_env_reset_obs(const srlx_engine* eng, int force, float* out_obs_dev, uintptr_t cuda_stream);
 int srlx_env_step_actions(const srlx_engine* eng, const int32_t* actions_dev, float* out_obs_dev, double* out_reward_dev,
                           unsigned char* out_term_dev, unsigned char* out_trunc_dev, uintptr_t cuda_stream);

@@ -116,6 +116,7 @@ class OracleEngine:
         self.ring_reward = np.zeros(self.cap, dtype=np.float32)
         self.ring_term = np.zeros(self.cap, dtype=np.uint8)
         self.ring_done = np.zeros(self.cap, dtype=np.uint8)
+        self.ring_invalid = None  # uint32 [cap] bit masks of the next state's invalid actions (external envs; ext_step)
         # memory
         self.per = sumtree.ProportionalMemory(self.cap, cfg.per_alpha, cfg.per_beta_initial, cfg.per_beta_steps,
                                               cfg.has_duplicate, cfg.per_epsilon)
@@ -316,6 +317,42 @@ class OracleEngine:
                 states[k + 1] = states[k]
         return states, acts, rews, terms
 
+    def window_invalid(self, slot):
+        """bool [M, A]: invalid actions of the window's M next states; padded records carry none (rainbow.py:366)"""
+        E, R, M = self.E, self.R, self.M
+        rho, e = divmod(int(slot), E)
+        out = np.zeros((M, self.A), dtype=bool)
+        for k in range(M):
+            sk = ((rho + k) % R) * E + e
+            out[k] = [(int(self.ring_invalid[sk]) >> a) & 1 for a in range(self.A)]
+            if self.ring_done[sk]:
+                break
+        return out
+
+    def ext_step(self, obs, next_obs, action, reward, term, done, next_invalid=None):
+        """One row of E records from a host loop (csrc/rollout.cu: srlx_ext_step_masked) + the replay add of vec_step."""
+        cfg, E = self.cfg, self.E
+        g = self.vec_steps
+        row = g % self.R
+        sl = slice(row * E, (row + 1) * E)
+        self.ring_obs[sl], self.ring_next_obs[sl] = obs, next_obs
+        self.ring_action[sl], self.ring_reward[sl] = action, np.asarray(reward, np.float32)
+        self.ring_term[sl], self.ring_done[sl] = term, done
+        if self.ring_invalid is not None:
+            self.ring_invalid[sl] = 0 if next_invalid is None else next_invalid
+        M, R = self.M, self.R
+        if cfg.mem_kind == MEM_PROPORTIONAL:
+            if M == 1:
+                self._tree_set_const(row * E, E, self.per.max_priority)
+            else:
+                self._tree_set_const(row * E, E, 0.0)
+                if g >= M - 1:
+                    self._tree_set_const(((g - M + 1) % R) * E, E, self.per.max_priority)
+        self.mem_size = E * min(max(0, g + 1 - (M - 1)), R - (M - 1))
+        self.per.size = self.mem_size
+        self.vec_steps += 1
+        self.total_step += E
+
     def _valid_range(self):
         g_next, R, M = self.vec_steps, self.R, self.M
         g_lo = max(0, g_next - R)
@@ -358,6 +395,7 @@ class OracleEngine:
                 acts = np.stack([w_[1] for w_ in wins])
                 rews = np.stack([w_[2] for w_ in wins])
                 terms = np.stack([w_[3] for w_ in wins])
+                inv = None if self.ring_invalid is None else np.stack([self.window_invalid(s) for s in slots])
                 noise = (None, None, None)
                 if cfg.noisy:
                     noise = tuple(self.noise_fn(nets.NOISE_KIND_TRAIN, tc * 3 + p) for p in range(3))
@@ -365,7 +403,7 @@ class OracleEngine:
                     self.spec, self.adam, self.tgt_mu, self.tgt_sigma, algo=cfg.algo, states=states, actions=acts,
                     rewards=rews, dones=terms, weights=weights, discount=cfg.discount, multisteps=self.M,
                     retrace_h=cfg.retrace_h, enable_double_dqn=cfg.enable_double_dqn, enable_rescale=cfg.enable_rescale,
-                    noise=noise, sigma_mask=self.sigma_mask, huber_delta=cfg.huber_delta)
+                    noise=noise, sigma_mask=self.sigma_mask, huber_delta=cfg.huber_delta, next_invalid=inv)
                 if cfg.presample and j + 1 < k:
                     pending = self._sample(tc + 1)  # before this update's priorities reach the tree
                 if cfg.mem_kind == MEM_PROPORTIONAL:

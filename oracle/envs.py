@@ -298,7 +298,18 @@ class PendulumSpec:
         return np.array([newth, newthdot, 0.0, 0.0], dtype=np.float64), float(-costs), False
 
 
+class ExternalSpec:
+    """An env stepped by a host loop (the reference's core_play.play through the plug-in classes): only the shapes matter."""
+
+    trunc_limit, trunc_overrides_term = 2**31 - 1, 0
+
+    def __init__(self, obs_dim, n_actions):
+        self.obs_dim, self.n_actions = int(obs_dim), int(n_actions)
+
+
 def make_spec(env_id, **kw):
+    if env_id in (3, "external"):
+        return ExternalSpec(**kw)
     if env_id in (0, "Grid", "grid"):
         return GridSpec(**kw)
     if env_id in (1, "CartPole-v1", "cartpole"):

@@ -203,8 +203,9 @@ def train_update(
     noise=(None, None, None),
     sigma_mask=None,
     huber_delta=1.0,
+    next_invalid=None,
 ):
-    """One Trainer.train() given an already-sampled batch.
+    """One Trainer.train() given an already-sampled batch.  next_invalid: optional bool [B, M, A], invalid actions of the M next states.
 
     states [B, M+1, D]; actions/rewards/dones [B, M] where dones = "terminated" (so undone = 1 - dones for the 1-step
     algorithms, dqn.py:243).  noise = (online(s) draw, online(s') draw, target(s') draw), flat, or None when not noisy.
@@ -226,11 +227,11 @@ def train_update(
     if algo == "rainbow" and multisteps > 1:
         target_q, state, act = targets.rainbow_target(
             pred_q, pred_target_q, states, actions, rewards, dones, discount, multisteps, retrace_h,
-            enable_double_dqn, enable_rescale, n_actions=spec.n_actions)
+            enable_double_dqn, enable_rescale, n_actions=spec.n_actions, next_invalid=next_invalid)
     else:
         target_q = targets.dqn_target(
             pred_q, pred_target_q, states[:, 1, :], rewards[:, 0].astype(np.float32), (1 - dones[:, 0]).astype(np.int64),
-            discount, enable_double_dqn, enable_rescale)
+            discount, enable_double_dqn, enable_rescale, next_invalid=None if next_invalid is None else next_invalid[:, 0, :])
         state, act = states[:, 0, :], actions[:, 0]
 
     onehot = torch.as_tensor(np.eye(spec.n_actions, dtype=np.float32)[act])

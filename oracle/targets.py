@@ -48,12 +48,13 @@ def dqn_target(pred_q, pred_target_q, n_state, reward, undone, discount, enable_
 
 
 def rainbow_target(pred_q, pred_target_q, states, actions, rewards, dones, discount, multisteps, retrace_h=1.0,
-                   enable_double_dqn=True, enable_rescale=False, n_actions=None, np_dtype=np.float32):
+                   enable_double_dqn=True, enable_rescale=False, n_actions=None, np_dtype=np.float32, next_invalid=None):
     """rainbow.py:185-287.
 
     states  [B, M+1, D]   tracking "state" of the M+1 window entries
     actions [B, M] int    action index of entries 1..M (one-hot in the reference)
     rewards [B, M], dones [B, M]  entries 1..M ("terminated")
+    next_invalid optional bool [B, M, A]: invalid actions of entries 1..M (rainbow.py:236-249: -inf before the argmax)
     Returns (target_q [B], state [B,D], action_idx [B]).
     """
     B, M = actions.shape
@@ -90,8 +91,12 @@ def rainbow_target(pred_q, pred_target_q, states, actions, rewards, dones, disco
     q = np.insert(q, 0, 0, axis=1)
 
     if enable_double_dqn:
+        if next_invalid is not None and next_invalid.any():
+            q_online[next_invalid] = -np.inf
         n_act_idx = np.argmax(q_online, axis=2)
     else:
+        if next_invalid is not None and next_invalid.any():
+            q_target[next_invalid] = -np.inf
         n_act_idx = np.argmax(q_target, axis=2)
     maxq = np.take_along_axis(q_target, np.expand_dims(n_act_idx, axis=2), axis=2)
     maxq = np.squeeze(maxq, axis=2)

@@ -86,6 +86,7 @@ class SrlxEngine(C.Structure):
         ("tree_blk", _P), ("tree_blk_bytes", C.c_uint64),
         ("eps_end", C.c_double), ("eps_phase_steps", C.c_uint64),
         ("learner_seed", C.c_uint64), ("dp_world", C.c_int32), ("dp_rank", C.c_int32), ("dp_peer", _P * 8), ("dp_bytes", C.c_uint64),
+        ("ring_invalid", _P),
     ]
 
 
@@ -195,6 +196,7 @@ SYMBOLS = [
     ("srlx_dp_free", C.c_int, [_P]),
     ("srlx_dp_enable_peer", C.c_int, [_i32, _i32]),
     ("srlx_ext_step", C.c_int, [C.POINTER(SrlxEngine), _P, _P, _P, _P, _P, _P, _uptr]),
+    ("srlx_ext_step_masked", C.c_int, [C.POINTER(SrlxEngine), _P, _P, _P, _P, _P, _P, _P, _uptr]),
     ("srlx_env_reset_obs", C.c_int, [C.POINTER(SrlxEngine), _i32, _P, _uptr]),
     ("srlx_env_step_actions", C.c_int, [C.POINTER(SrlxEngine), _P, _P, _P, _P, _P, _uptr]),
     ("srlx_sequence_targets", C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _u32, _u32, _u32, _dbl, _dbl, _i32, _i32, _i32, _uptr]),

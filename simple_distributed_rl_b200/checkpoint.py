@@ -98,6 +98,7 @@ class RingView:
         self.reward = np.zeros(cap, dtype=np.float32)
         self.term = np.zeros(cap, dtype=np.uint8)
         self.done = np.zeros(cap, dtype=np.uint8)
+        self.invalid: Optional[np.ndarray] = None  # [cap] uint32 bit masks: invalid actions of the row's NEXT state (None: no masks)
         self.leaf_priority: Optional[np.ndarray] = None  # [cap] float64 (proportional memory), by slot
         self.max_priority = 1.0
 
@@ -146,6 +147,7 @@ def export_items(ring: RingView, pad_action=None, compress: bool = False) -> Tup
     terminated step's successor, whose gain is masked by terminated=1, rainbow.py:257)."""
     E, R, M, A = ring.E, ring.R, ring.M, ring.A
     g_lo, n_g = ring.valid_rows()
+    inv = (lambda sl: [a for a in range(A) if (int(ring.invalid[sl]) >> a) & 1]) if ring.invalid is not None else (lambda sl: [])
     items: List[Any] = []
     pri = [] if ring.leaf_priority is not None else None
     for e in range(E):
@@ -153,7 +155,7 @@ def export_items(ring: RingView, pad_action=None, compress: bool = False) -> Tup
             slot = (g % R) * E + e
             if M == 1:
                 item = [ring.obs[slot].copy(), ring.next_obs[slot].copy(), _onehot(ring.action[slot], A), float(ring.reward[slot]),
-                        int(not ring.term[slot]), []]
+                        int(not ring.term[slot]), inv(slot)]
             else:
                 item = [[ring.obs[slot].copy(), None, None, None, None]]
                 ended, last_state = False, None
@@ -161,7 +163,7 @@ def export_items(ring: RingView, pad_action=None, compress: bool = False) -> Tup
                     if not ended:
                         sk = ((g + k) % R) * E + e
                         last_state = ring.next_obs[sk].copy()
-                        item.append([last_state, _onehot(ring.action[sk], A), float(ring.reward[sk]), int(ring.term[sk]), []])
+                        item.append([last_state, _onehot(ring.action[sk], A), float(ring.reward[sk]), int(ring.term[sk]), inv(sk)])
                         ended = bool(ring.done[sk])
                     else:
                         a = int(pad_action(e, g + k)) if pad_action is not None else 0
@@ -203,14 +205,16 @@ def _first_transition(item: Any, M: int):
     """(state, next_state, action, reward, terminated, done, tail) of the first step of a reference item; tail = the later
     (state', action, reward, terminated, done) steps a multistep window carries."""
     it = _unpack(item)
+    bits = lambda lst: sum(1 << int(a) for a in (lst or []))  # noqa: E731
     if M == 1:
         s, ns, oh, r, undone = it[0], it[1], it[2], it[3], it[4]
         term = 0 if undone else 1
-        return np.asarray(s, np.float32), np.asarray(ns, np.float32), int(np.argmax(oh)), float(r), term, term, []
+        return (np.asarray(s, np.float32), np.asarray(ns, np.float32), int(np.argmax(oh)), float(r), term, term, [],
+                bits(it[5] if len(it) > 5 else None))
     steps = []
     for k in range(1, M + 1):
         ns, oh, r, t = it[k][0], it[k][1], it[k][2], it[k][3]
-        steps.append([np.asarray(ns, np.float32), int(np.argmax(oh)), float(r), int(t), int(t)])
+        steps.append([np.asarray(ns, np.float32), int(np.argmax(oh)), float(r), int(t), int(t), bits(it[k][4] if len(it[k]) > 4 else None)])
     for k in range(M - 1):  # step k ended its episode when step k+1 is padding: same state, reward 0, terminated 1
         nxt = steps[k + 1]
         if nxt[3] == 1 and nxt[2] == 0.0 and np.array_equal(nxt[0], steps[k][0]):
@@ -222,7 +226,7 @@ def _first_transition(item: Any, M: int):
         real.append(st)
         ended = bool(st[4])
     f = real[0]
-    return np.asarray(it[0][0], np.float32), f[0], f[1], f[2], f[3], f[4], real[1:]
+    return np.asarray(it[0][0], np.float32), f[0], f[1], f[2], f[3], f[4], real[1:], f[5]
 
 
 def _ordered_items(inner: list, proportional: bool) -> Tuple[List[Any], Optional[np.ndarray], float]:
@@ -268,7 +272,11 @@ def memory_restore(data: list, n_envs: int, ring_rows: int, multisteps: int, n_a
         tail = []
         prev_ns, prev_done = None, True
         for j in range(n_g):
-            s, ns, a, r, term, done, tail = _first_transition(items[e * n_g + j], M)
+            s, ns, a, r, term, done, tail, mask = _first_transition(items[e * n_g + j], M)
+            if mask:
+                if ring.invalid is None:
+                    ring.invalid = np.zeros(ring.capacity, dtype=np.uint32)
+                ring.invalid[j * E + e] = mask
             if check_continuity and M > 1 and not prev_done and not np.array_equal(s, prev_ns):
                 raise DiscontinuousMemoryError(
                     f"memory_restore: item {e * n_g + j} does not continue the trajectory of the item before it (its state is not the "
@@ -285,7 +293,11 @@ def memory_restore(data: list, n_envs: int, ring_rows: int, multisteps: int, n_a
         for k in range(M - 1):  # rows after the last window start: real steps carried by the last item, else a cut
             slot = (n_g + k) * E + e
             if k < len(tail):
-                ns, a, r, term, done = tail[k]
+                ns, a, r, term, done, mask = tail[k]
+                if mask:
+                    if ring.invalid is None:
+                        ring.invalid = np.zeros(ring.capacity, dtype=np.uint32)
+                    ring.invalid[slot] = mask
                 ring.obs[slot], ring.next_obs[slot] = prev_next, ns
                 ring.action[slot], ring.reward[slot], ring.term[slot], ring.done[slot] = a, r, term, done
                 prev_next = ns

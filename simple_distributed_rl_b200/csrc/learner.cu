@@ -147,7 +147,7 @@ __host__ __device__ inline LPlan make_lplan(const srlx_engine& eng, int C, int m
   p.off_samp_slot = take((size_t)2 * p.B * 4);
   p.off_samp_w = take((size_t)2 * p.B * 4);
   p.off_g = take((size_t)4 * p.BM * 4);    // gathered action / reward / term / done
-  p.off_win = take((size_t)3 * p.BM * 4);  // window action / reward / term after padding
+  p.off_win = take((size_t)4 * p.BM * 4);  // window action / reward / term / next-state invalid-action mask after padding
   p.off_tq = take((size_t)2 * p.B * 4);    // target_q, q(s,a)
   p.off_draw = take((size_t)p.B * p.NOP * 4);
   p.off_sidx = take((size_t)p.B * 8);
@@ -327,6 +327,7 @@ learner_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_updates
   int* w_act = reinterpret_cast<int*>(smem + pl.off_win);
   float* w_rew = reinterpret_cast<float*>(smem + pl.off_win) + pl.BM;
   float* w_term = w_rew + pl.BM;
+  uint32_t* w_inv = reinterpret_cast<uint32_t*>(w_term + pl.BM);
   float* tq = reinterpret_cast<float*>(smem + pl.off_tq);
   float* qsa = tq + pl.B;
   float* dRaw = reinterpret_cast<float*>(smem + pl.off_draw);  // [B][NOP]
@@ -890,6 +891,7 @@ learner_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_updates
         g_rew[w] = rw;
         g_term[w] = (float)tm;
         g_done[w] = (int)dn;
+        w_inv[w] = eng.ring_invalid ? __ldcg(eng.ring_invalid + sk) : 0u;
         float* xr = x_cur + (size_t)(B + w) * pl.ldx0;
 #pragma unroll
         for (int d = 0; d < SRLX_MAX_OBS; ++d)
@@ -922,6 +924,7 @@ learner_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_updates
             w_act[w] = (int)u_below(pw.x, (uint32_t)A);
             w_rew[w] = 0.f;
             w_term[w] = 1.f;
+            w_inv[w] = 0u;  // padded records carry no invalid actions (rainbow.py:366)
             const float* src = x_cur + (size_t)(B + i * M + last_k) * pl.ldx0;
             float* dst = x_cur + (size_t)(B + w) * pl.ldx0;
             for (int d = 0; d < D; ++d) dst[d] = src[d];
@@ -974,6 +977,21 @@ learner_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_updates
       {
         const float* qon = Q + B * A;          // online(s')  [BM][A]
         const float* qtg = Q + (B + BM) * A;   // target(s')  [BM][A]
+        // invalid actions, one-step targets (dqn.py:156-165, rainbow_nomultisteps.py:19-31): the masked entries take the MINIMUM OF THE
+        // WHOLE BATCH'S Q matrix (online with double DQN, else target), not -inf
+        float gmin = 0.f;
+        if (eng.ring_invalid && M == 1) {
+          __shared__ float s_gmin[kLearnThreads / 32];
+          const float* qm = eng.enable_double_dqn ? qon : qtg;
+          float m = INFINITY;
+          for (int w = at; w < B * A; w += NA) m = fminf(m, qm[w]);
+          for (int sft = 16; sft > 0; sft >>= 1) m = fminf(m, __shfl_xor_sync(0xffffffffu, m, sft));
+          if ((at & 31) == 0) s_gmin[at >> 5] = m;
+          named_bar_sync(BAR_AUX, NA);
+          gmin = s_gmin[0];
+          for (int w = 1; w < NA / 32; ++w) gmin = fminf(gmin, s_gmin[w]);
+          named_bar_sync(BAR_AUX, NA);
+        }
         float lsum = 0.f;
         for (int i = at; i < B; i += NA) {
           const float gamma = (float)eng.discount;
@@ -982,13 +1000,19 @@ learner_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_updates
             const float* qo = qon + (size_t)(i * M + k) * A;
             const float* qt = qtg + (size_t)(i * M + k) * A;
             const float* qsel = eng.enable_double_dqn ? qo : qt;
+            const uint32_t inv = w_inv[i * M + k];
+            // masked value: the batch minimum (one-step) or -inf (n-step, rainbow.py:244-249)
+            const float fill = M == 1 ? gmin : -INFINITY;
             int am = 0;
-            float best = qsel[0];
-            for (int a = 1; a < A; ++a)
-              if (qsel[a] > best) { best = qsel[a]; am = a; }  // np.argmax: first max wins
+            float best = (inv & 1u) ? fill : qsel[0];
+            for (int a = 1; a < A; ++a) {
+              const float v = ((inv >> a) & 1u) ? fill : qsel[a];
+              if (v > best) { best = v; am = a; }  // np.argmax: first max wins
+            }
             // Retrace with the reference's index shift (rainbow.py:267): action taken at s_k vs greedy action at s_{k+1}
             if (k >= 1) retrace = retrace * ((float)eng.retrace_h * ((w_act[i * M + k] == am) ? 1.f : 0.f));
-            float maxq = qt[am];
+            // the value comes from the TARGET net; without double DQN the target matrix itself was overwritten at the masked entries
+            float maxq = (!eng.enable_double_dqn && ((inv >> am) & 1u)) ? fill : qt[am];
             if (eng.enable_rescale) maxq = inverse_rescaling_f(maxq);
             float gain = w_rew[i * M + k] + ((1.0f - w_term[i * M + k]) * gamma) * maxq;
             if (eng.enable_rescale) gain = rescaling_f(gain);

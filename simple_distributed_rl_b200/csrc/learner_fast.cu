@@ -1844,7 +1844,7 @@ extern "C" int srlx_dbg_pow(const double* x_dev, double a, double* out_dev, size
 static int fast_choose(const srlx_engine* eng, int* C_out, int* lev_out, size_t* smem_out) {
   using namespace srlx;
   const char* force = getenv("SRLX_LEARNER");
-  if ((force && force[0] == 'g') || !fast_shape_ok(*eng)) return 0;
+  if ((force && force[0] == 'g') || !fast_shape_ok(*eng) || eng->ring_invalid) return 0;  // masks: the generic learner
   int want = 0;
   if (const char* e = getenv("SRLX_CLUSTER")) want = atoi(e);
   int dev = 0, max_smem = 0;
@@ -1880,7 +1880,7 @@ int learn_small(const srlx_engine* eng, uint32_t n_updates, uintptr_t cuda_strea
 // 2 when the row-split kernel (learner_small.cu: uniform replay, no NoisyNet, batch rows over a small cluster) is the one to run
 static int small_pick(const srlx_engine* eng, size_t* smem_out, int* C_out) {
   const char* force = getenv("SRLX_LEARNER");
-  if (force && force[0] == 'g') return 0;
+  if ((force && force[0] == 'g') || eng->ring_invalid) return 0;
   return srlx::small_choose(eng, smem_out, C_out) == 1 ? 2 : 0;
 }
 

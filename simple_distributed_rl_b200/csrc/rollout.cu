@@ -276,7 +276,8 @@ __global__ void eval_post_step_kernel(srlx_state* st, int E) {
 //      simple_distributed_rl_b200/srl_classes.py) enter the ring as one row of E records; post_step_kernel then does the replay add
 __global__ void ext_row_write_kernel(const __grid_constant__ srlx_engine eng, const float* __restrict__ obs, const float* __restrict__ next_obs,
                                      const int32_t* __restrict__ action, const float* __restrict__ reward,
-                                     const uint8_t* __restrict__ term, const uint8_t* __restrict__ done) {
+                                     const uint8_t* __restrict__ term, const uint8_t* __restrict__ done,
+                                     const uint32_t* __restrict__ next_invalid) {
   const int E = eng.n_envs, D = eng.obs_dim;
   const int row = (int)(eng.state->vec_steps % (uint64_t)eng.ring_rows);
   for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < E; e += gridDim.x * blockDim.x) {
@@ -289,6 +290,7 @@ __global__ void ext_row_write_kernel(const __grid_constant__ srlx_engine eng, co
     eng.ring_reward[slot] = reward[e];
     eng.ring_term[slot] = term[e] ? 1 : 0;
     eng.ring_done[slot] = done[e] ? 1 : 0;
+    if (eng.ring_invalid) eng.ring_invalid[slot] = next_invalid ? next_invalid[e] : 0u;
   }
 }
 
@@ -410,7 +412,15 @@ extern "C" int srlx_engine_reset(const srlx_engine* eng, uintptr_t cuda_stream) 
 
 extern "C" int srlx_ext_step(const srlx_engine* eng, const float* obs_dev, const float* next_obs_dev, const int32_t* action_dev,
                              const float* reward_dev, const unsigned char* term_dev, const unsigned char* done_dev, uintptr_t cuda_stream) {
+  return srlx_ext_step_masked(eng, obs_dev, next_obs_dev, action_dev, reward_dev, term_dev, done_dev, nullptr, cuda_stream);
+}
+
+extern "C" int srlx_ext_step_masked(const srlx_engine* eng, const float* obs_dev, const float* next_obs_dev, const int32_t* action_dev,
+                                    const float* reward_dev, const unsigned char* term_dev, const unsigned char* done_dev,
+                                    const uint32_t* next_invalid_dev, uintptr_t cuda_stream) {
   using namespace srlx;
+  SRLX_REQUIRE(eng != nullptr, "engine is NULL");
+  SRLX_REQUIRE(next_invalid_dev == nullptr || eng->ring_invalid != nullptr, "invalid-action masks need the ring_invalid buffer");
   SRLX_REQUIRE(eng != nullptr, "engine is NULL");
   SRLX_REQUIRE(eng->n_envs >= 1 && eng->obs_dim >= 1 && eng->obs_dim <= SRLX_MAX_OBS, "n_envs / obs_dim out of range");
   SRLX_REQUIRE(eng->ring_rows >= eng->multisteps && eng->multisteps >= 1, "ring_rows (%d) must be >= multisteps (%d)", eng->ring_rows, eng->multisteps);
@@ -419,7 +429,8 @@ extern "C" int srlx_ext_step(const srlx_engine* eng, const float* obs_dev, const
   SRLX_REQUIRE(eng->mem_kind == SRLX_MEM_UNIFORM || (eng->tree && eng->tree_scratch), "proportional memory needs tree + tree_scratch");
   SRLX_REQUIRE(obs_dev && next_obs_dev && action_dev && reward_dev && term_dev && done_dev, "record pointer is NULL");
   const int grid = (eng->n_envs + 255) / 256 < 296 ? (eng->n_envs + 255) / 256 : 296;
-  ext_row_write_kernel<<<grid, 256, 0, (cudaStream_t)cuda_stream>>>(*eng, obs_dev, next_obs_dev, action_dev, reward_dev, term_dev, done_dev);
+  ext_row_write_kernel<<<grid, 256, 0, (cudaStream_t)cuda_stream>>>(*eng, obs_dev, next_obs_dev, action_dev, reward_dev, term_dev, done_dev,
+                                                                       next_invalid_dev);
   count_launch();
   SRLX_CHECK_CUDA(cudaGetLastError());
   launch_post_step(eng, (cudaStream_t)cuda_stream);

@@ -61,6 +61,7 @@ class EngineConfig:
     hidden: tuple = (64, 64)
     dueling: Optional[str] = None
     noisy: bool = False
+    invalid_actions: bool = False  # keep the next state's invalid-action mask per row (external envs; generic learner only)
     env_kwargs: dict = field(default_factory=dict)
 
 
@@ -104,6 +105,8 @@ class DeviceEngine:
             self.t["tree_scratch"] = z(2 * (self.E + 2), torch.float64)
             # blocked copy of the deep SumTree levels for the learner's sampler (csrc/learner_fast.cu), rebuilt per learn call
             self.t["tree_blk"] = z(max(64, self.lib.srlx_tree_blk_bytes(self.cap) // 8), torch.float64)
+        if cfg.invalid_actions:
+            self.t["ring_invalid"] = z(self.cap, torch.int32)
         if track_episodes:
             self.t["env_first_ep_reward"] = z(self.E, torch.float64)
             self.t["env_last_ep_len"] = z(self.E, torch.int32)
@@ -158,6 +161,29 @@ class DeviceEngine:
             if name in self.t:
                 setattr(c, name, self.t[name].data_ptr())
         return c
+
+    def enable_invalid_actions(self):
+        """Start keeping invalid-action masks (include/srlx.h srlx_engine.ring_invalid): rows written so far had none.  From here on
+        srlx_learn runs the generic learner, which applies them (dqn.py:156-165, rainbow.py:236-249)."""
+        if "ring_invalid" not in self.t:
+            self.t["ring_invalid"] = torch.zeros(self.cap, dtype=torch.int32, device=self.device)
+            self.c = self._build_struct()
+
+    def ext_step(self, obs, next_obs, action, reward, term, done, next_invalid=None):
+        """One row of E records produced by a host loop (srlx_ext_step_masked): float32 [E][D] x 2, int32 [E], float32 [E], uint8 [E] x 2,
+        optional uint32 bit masks [E] of the next state's invalid actions."""
+        f = lambda x, dt: torch.as_tensor(np.asarray(x)).to(self.device, dtype=dt).contiguous()  # noqa: E731
+        bufs = [f(obs, torch.float32).reshape(self.E, self.D), f(next_obs, torch.float32).reshape(self.E, self.D), f(action, torch.int32),
+                f(reward, torch.float32), f(term, torch.uint8), f(done, torch.uint8)]
+        inv = None
+        if next_invalid is not None:
+            self.enable_invalid_actions()
+            inv = f(np.asarray(next_invalid, dtype=np.int64), torch.int32)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.srlx_ext_step_masked(self.c, *[b.data_ptr() for b in bufs], None if inv is None else inv.data_ptr(),
+                                                     self._stream()))
+        self._holds_data = True
+        self._keep_ext = (bufs, inv)
 
     def set_data_parallel(self, world: int, rank: int, peer_ptrs, nbytes: int, learner_seed: int):
         """Make this engine rank `rank` of a `world`-rank data-parallel learner: peer_ptrs[r] = the exchange buffer of rank r as
@@ -316,6 +342,8 @@ class DeviceEngine:
         v.reward[:] = self.t["ring_reward"].cpu().numpy().reshape(-1)
         v.term[:] = self.t["ring_term"].cpu().numpy().reshape(-1)
         v.done[:] = self.t["ring_done"].cpu().numpy().reshape(-1)
+        if "ring_invalid" in self.t:
+            v.invalid = self.t["ring_invalid"].cpu().numpy().reshape(-1).astype(np.uint32)
         if self.per:
             cap = self.E * self.R
             v.leaf_priority = self.t["tree"][cap - 1:].cpu().numpy().astype(np.float64)
@@ -333,6 +361,11 @@ class DeviceEngine:
                           ("ring_term", v.term), ("ring_done", v.done)):
             t = self.t[name]
             t.copy_(torch.as_tensor(np.ascontiguousarray(arr)).reshape(t.shape).to(t.dtype))
+        if getattr(v, "invalid", None) is not None:
+            self.enable_invalid_actions()
+            self.t["ring_invalid"].copy_(torch.as_tensor(np.ascontiguousarray(v.invalid).astype(np.int64)).to(torch.int32))
+        elif "ring_invalid" in self.t:
+            self.t["ring_invalid"].zero_()
         st = self.read_state()
         g_lo, n_g = v.valid_rows()
         st.vec_steps, st.total_step, st.mem_size = v.vec_steps, v.vec_steps * self.E, n_g * self.E

@@ -99,7 +99,8 @@ class DeviceMemory(RLMemory):
         D = self.engine.D
         # pinned staging of the records a host loop hands over, copied to the device in one go at flush()
         self._cap_stage = 256
-        self._stage = torch.zeros((self._cap_stage, 2 * D + 4), dtype=torch.float32).pin_memory()
+        self._stage = torch.zeros((self._cap_stage, 2 * D + 5), dtype=torch.float32).pin_memory()  # ... + invalid-action bit mask
+        self._masks = False  # a record with invalid actions has been seen
         self._n_stage = 0
         self._steps = 0  # rows ever added (== the device's vec_steps once flushed)
         self.step = 0    # PriorityReplayBuffer.step (priority_replay_buffer.py:247-250): kept for interface parity
@@ -109,18 +110,25 @@ class DeviceMemory(RLMemory):
 
     # ---- worker side ------------------------------------------------------------------------------------------------
     def add(self, batch: Any, priority: Optional[float] = None, serialized: bool = False) -> None:
-        """batch = one env step (state, next_state, action index, reward, terminated, done) -- what DeviceWorker.on_step hands over.
-        n-step windows are rebuilt from consecutive rows at sample time, so records must arrive in trajectory order."""
+        """batch = one env step (state, next_state, action index, reward, terminated, done[, next_invalid_actions]) -- what
+        DeviceWorker.on_step hands over.  n-step windows are rebuilt from consecutive rows at sample time, so records must arrive in
+        trajectory order."""
         if serialized:
             import pickle
 
             batch = pickle.loads(batch)
-        s, ns, a, r, term, done = batch
+        s, ns, a, r, term, done = batch[:6]
+        mask = 0
+        if len(batch) > 6 and batch[6]:
+            for ia in batch[6]:
+                mask |= 1 << int(ia)
+            self._masks = True
         D = self.engine.D
         row = self._stage[self._n_stage]
         row[:D] = torch.as_tensor(np.asarray(s, dtype=np.float32).reshape(-1))
         row[D:2 * D] = torch.as_tensor(np.asarray(ns, dtype=np.float32).reshape(-1))
         row[2 * D], row[2 * D + 1], row[2 * D + 2], row[2 * D + 3] = float(a), float(r), float(bool(term)), float(bool(done))
+        row[2 * D + 4] = float(mask)  # <= 16 actions: exact in float32
         self._n_stage += 1
         self._steps += 1
         if self._n_stage == self._cap_stage:
@@ -142,12 +150,17 @@ class DeviceMemory(RLMemory):
         act = d[:, 2 * D].to(torch.int32).contiguous()
         rew = d[:, 2 * D + 1].contiguous()
         term, done = d[:, 2 * D + 2].to(torch.uint8).contiguous(), d[:, 2 * D + 3].to(torch.uint8).contiguous()
+        inv = None
+        if self._masks:  # from the first record with invalid actions on: masks are kept and the generic learner applies them
+            eng.enable_invalid_actions()
+            inv = d[:, 2 * D + 4].to(torch.int32).contiguous()
         s = eng._stream()
         with torch.cuda.device(self.device):
             for i in range(n):
-                _lib.check(eng.lib.srlx_ext_step(eng.c, obs[i].data_ptr(), nobs[i].data_ptr(), act[i:i + 1].data_ptr(), rew[i:i + 1].data_ptr(),
-                                                 term[i:i + 1].data_ptr(), done[i:i + 1].data_ptr(), s))
-        self._keep = (obs, nobs, act, rew, term, done)  # alive until the next flush (the launches are asynchronous)
+                _lib.check(eng.lib.srlx_ext_step_masked(eng.c, obs[i].data_ptr(), nobs[i].data_ptr(), act[i:i + 1].data_ptr(),
+                                                        rew[i:i + 1].data_ptr(), term[i:i + 1].data_ptr(), done[i:i + 1].data_ptr(),
+                                                        None if inv is None else inv[i:i + 1].data_ptr(), s))
+        self._keep = (obs, nobs, act, rew, term, done, inv)  # alive until the next flush (the launches are asynchronous)
         eng._holds_data = True
         self._n_stage = 0
 
@@ -299,14 +312,13 @@ class DeviceWorker(RLWorker):
 
     def policy(self, worker) -> int:
         invalid_actions = worker.invalid_actions
-        if invalid_actions:
-            raise NotImplementedError("invalid actions are not supported on the device path")
         if not self.noisy:
             epsilon = self.epsilon_sch.update(self.step_in_training).to_float() if self.training else self.config.test_epsilon
             self.info["epsilon"] = epsilon
             if random.random() < epsilon:
-                return random.choice(list(range(self.n_actions)))
+                return random.choice([a for a in range(self.n_actions) if a not in invalid_actions])
         q = self.parameter.pred_q(worker.state[np.newaxis, ...])[0]
+        q[invalid_actions] = -np.inf  # dqn.py:207, rainbow.py:307,325
         return int(np.argmax(q))
 
     def on_step(self, worker) -> None:
@@ -315,7 +327,8 @@ class DeviceWorker(RLWorker):
         reward = worker.reward
         if self.config.enable_reward_clip:
             reward = -1 if reward < 0 else (1 if reward > 0 else 0)
-        self.memory.add((worker.state, worker.next_state, int(worker.action), float(reward), bool(worker.terminated), bool(worker.done)))
+        self.memory.add((worker.state, worker.next_state, int(worker.action), float(reward), bool(worker.terminated), bool(worker.done),
+                         list(worker.next_invalid_actions)))
 
     def render_terminal(self, worker, **kwargs) -> None:
         q = self.parameter.pred_q(worker.state[np.newaxis, ...])[0]

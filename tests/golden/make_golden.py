@@ -177,7 +177,7 @@ def _noise_schedule(spec, model):
 
 
 def gen_trainer(case, algo, hidden, dueling, noisy, multisteps, double, rescale, B=8, n_updates=2, retrace_h=1.0,
-                seed=0):
+                seed=0, invalid_p=0.0):
     torch.manual_seed(seed)
     rng = np.random.default_rng(seed)
     if algo == "dqn":
@@ -212,6 +212,10 @@ def gen_trainer(case, algo, hidden, dueling, noisy, multisteps, double, rescale,
     rewards = rng.normal(0, 1, size=(n_updates, B, M)).astype(np.float32)
     terms = (rng.random((n_updates, B, M)) < 0.25).astype(np.int64)
     weights = rng.uniform(0.3, 1.0, size=(n_updates, B)).astype(np.float32)
+    # invalid actions of the M next states (never all of them): dqn.py:156-165, rainbow_nomultisteps.py:19-31, rainbow.py:236-249
+    invalid = rng.random((n_updates, B, M, A)) < invalid_p
+    invalid[..., 0] &= ~invalid.all(axis=-1)
+    inv_list = lambda u, i, k: [int(a) for a in np.nonzero(invalid[u, i, k])[0]]  # noqa: E731
     # make a few windows greedy-consistent is not needed: random actions already hit both retrace branches for A=4
     batches_list = []
     for u in range(n_updates):
@@ -221,11 +225,11 @@ def gen_trainer(case, algo, hidden, dueling, noisy, multisteps, double, rescale,
                 steps = [[states[u, i, 0], None, None, None, None]]
                 for k in range(M):
                     steps.append([states[u, i, k + 1], np.eye(A, dtype=np.float32)[actions[u, i, k]].tolist(),
-                                  float(rewards[u, i, k]), int(terms[u, i, k]), []])
+                                  float(rewards[u, i, k]), int(terms[u, i, k]), inv_list(u, i, k)])
                 bl.append(steps)
             else:
                 bl.append([states[u, i, 0], states[u, i, 1], np.eye(A, dtype=np.float32)[actions[u, i, 0]].tolist(),
-                           float(rewards[u, i, 0]), int(1 - terms[u, i, 0]), []])
+                           float(rewards[u, i, 0]), int(1 - terms[u, i, 0]), inv_list(u, i, 0)])
         batches_list.append(bl)
     memory = _StubMemory(batches_list, [w for w in weights])
     trainer = cfg.make_trainer(parameter, memory)
@@ -302,6 +306,7 @@ def gen_trainer(case, algo, hidden, dueling, noisy, multisteps, double, rescale,
         mu0=mu0, sigma0=sig0 if sig0 is not None else np.zeros(0, np.float32),
         tmu0=tmu0, tsigma0=tsig0 if tsig0 is not None else np.zeros(0, np.float32),
         states=states, actions=actions, rewards=rewards, terms=terms, weights=weights, noise=noise if noisy else np.zeros(0),
+        invalid=invalid,
         target_q=np.array(captured), losses=np.array(losses), priorities=np.array([p for p, s in memory.updates]),
         update_steps=np.array([s for p, s in memory.updates]), mu_after=np.array(mus), sigma_after=np.array(sigs),
         tmu_after=np.array(tmus), train_count=trainer.train_count, sync_count=trainer.sync_count,
@@ -704,6 +709,12 @@ if __name__ == "__main__":
         gen_r2d2_targets()
     if not only or "worker" in only:
         gen_worker_records()
+    if not only or "invalid" in only:  # the same trainer steps with invalid-action lists in the records
+        gen_trainer("dqn_mlp32_invalid_double", "dqn", (32,), None, False, 1, True, False, invalid_p=0.35, seed=3)
+        gen_trainer("dqn_mlp32_invalid_nodouble_rescale", "dqn", (32,), None, False, 1, False, True, invalid_p=0.35, seed=4)
+        gen_trainer("rainbow_duel32_invalid_m1", "rainbow", (32,), "average", False, 1, True, False, invalid_p=0.35, seed=5)
+        gen_trainer("rainbow_duel32_invalid_m3", "rainbow", (32,), "average", False, 3, True, False, invalid_p=0.35, seed=6)
+        gen_trainer("rainbow_mlp32_invalid_m2_nodouble", "rainbow", (32,), None, False, 2, False, False, invalid_p=0.35, seed=7, retrace_h=0.9)
     if not only or "base" in only:
         gen_grid()
         gen_sumtree()

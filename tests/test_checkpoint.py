@@ -347,3 +347,30 @@ def test_interleaved_trajectories_are_refused_for_multistep_memories():
     ck.memory_restore([[inter, 0], None], E, R, M, A, D, False, check_continuity=False)  # explicit opt-out still works
     one_step, _ = ck.export_items(ck.RingView(E, R, 1, A, D, vec_steps=R))
     ck.memory_restore([[one_step[::-1], 0], None], E, R, 1, A, D, False)  # 1-step items are self-contained: any order imports
+
+
+@pytest.mark.parametrize("M", [1, 3])
+def test_invalid_action_masks_round_trip_through_the_reference_item_format(M):
+    """ring_invalid <-> the next_invalid_actions lists of the reference's records (dqn.py:229-246, rainbow.py:341-351)."""
+    from simple_distributed_rl_b200 import checkpoint as ck
+
+    E, R, A, D = 2, 12, 5, 3
+    rng = np.random.default_rng(0)
+    ring = ck.RingView(E, R, M, A, D, vec_steps=9)
+    n = 9 * E
+    ring.obs[:n] = rng.normal(size=(n, D))
+    ring.next_obs[:n] = rng.normal(size=(n, D))
+    for g in range(8):  # one contiguous trajectory per column
+        ring.obs[(g + 1) * E:(g + 2) * E] = ring.next_obs[g * E:(g + 1) * E]
+    ring.action[:n] = rng.integers(0, A, n)
+    ring.reward[:n] = rng.normal(size=n)
+    ring.invalid = np.zeros(ring.capacity, dtype=np.uint32)
+    ring.invalid[:n] = rng.integers(0, 1 << A, n)
+    items, _ = ck.export_items(ring)
+    first = items[0]
+    lst = first[5] if M == 1 else first[1][4]
+    assert lst == [a for a in range(A) if (int(ring.invalid[0]) >> a) & 1]
+    back = ck.memory_restore([list(items), 0], E, R, M, A, D, proportional=False)
+    g_lo, n_g = ring.valid_rows()
+    assert back.invalid is not None
+    np.testing.assert_array_equal(back.invalid[: (n_g + M - 1) * E], ring.invalid[: (n_g + M - 1) * E])

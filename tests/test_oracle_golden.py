@@ -173,7 +173,7 @@ def test_trainer_update_matches_reference(path):
             spec, st, tmu, tsig, algo=algo, states=g["states"][u], actions=g["actions"][u], rewards=g["rewards"][u],
             dones=g["terms"][u], weights=g["weights"][u], discount=float(g["discount"]), multisteps=int(g["multisteps"]),
             retrace_h=float(g["retrace_h"]), enable_double_dqn=bool(g["double"]), enable_rescale=bool(g["rescale"]),
-            noise=noise, sigma_mask=mask)
+            noise=noise, sigma_mask=mask, next_invalid=g["invalid"][u] if "invalid" in g.files and g["invalid"].any() else None)
         np.testing.assert_allclose(res["target_q"], g["target_q"][u], rtol=1e-6, atol=1e-6)
         assert abs(res["loss"] - g["losses"][u]) <= 1e-6 * max(1, abs(g["losses"][u]))
         np.testing.assert_allclose(res["priorities"], g["priorities"][u], rtol=1e-5, atol=1e-6)

@@ -25,6 +25,8 @@ def main():
     if os.environ.get("PC_WORKLOAD") == "dqn_per":  # DQN MLP[64,64] on proportional replay: the generic learner_kernel
         kw = dict(env="CartPole-v1", algo="dqn", hidden=(64, 64), mem_kind=1, multisteps=1, n_envs=E, ring_rows=R, batch_size=32,
                   warmup_size=1000, seed=1, epsilon=0.1)
+    if os.environ.get("PC_PRESAMPLE"):
+        kw["presample"] = True
     d = DeviceEngine(EngineConfig(**kw), debug=True)
     for f in ("dbg_q", "dbg_action", "dbg_sample_idx", "dbg_weights", "dbg_target_q", "dbg_q_sa", "dbg_grads", "dbg_windows"):
         setattr(d.c, f, None)  # only the clock tap stays on: the other taps cost time inside the learner
