@@ -12,6 +12,8 @@
 // step fuses the gate GEMM with the cell update (a thread owns the four gates of a unit); the BPTT step fuses dh = dgates . Wh^T with
 // the gate derivatives.  One launch per time step: consecutive steps are data dependent; the whole update is launch-ordered on one
 // stream and capturable in a CUDA graph (no host synchronisation, no allocation; the warm-up gate is evaluated on device).
+#include <stdlib.h>
+
 #include "envs.cuh"
 #include "tree.cuh"
 
@@ -218,6 +220,125 @@ __global__ void __launch_bounds__(256) sgemm_tiled_kernel(const GemmP p) {
   }
 }
 
+// Tensor-core version of the tiled GEMM at fp32 accuracy: 3 x TF32.  Every operand is split into hi = tf32(x) and lo = tf32(x - hi)
+// and a product is formed as hi*hi + hi*lo + lo*hi on mma.sync.m16n8k8 (fp32 accumulate): the dropped lo*lo term is 2^-22 relative, so
+// the result sits within a few fp32 ulps of the FMA chain -- the 1e-4 parity bar holds with two orders of magnitude to spare -- at
+// several times the SIMT rate.  Same tiles, strides and epilogue as sgemm_tiled_kernel; 8 warps as 2 x 4, k-major shared tiles padded
+// to a stride of 8 mod 32 so that the 32 fragment loads of a warp fall into 32 different banks.
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
+  const float rest = x - __uint_as_float(hi);
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(rest));
+}
+__device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+
+template <int BM, int BN>
+__global__ void __launch_bounds__(256) sgemm_mma_kernel(const GemmP p) {
+  if (p.gate.closed()) return;
+  constexpr int BK = 16, NA = BM * BK / 256, NB = BN * BK / 256, WM = BM / 2, WN = BN / 4, MT = WM / 16, NT = WN / 8;
+  constexpr int LDA = BM + 8, LDB = BN + 8;
+  __shared__ __align__(16) float As[2][BK][LDA];
+  __shared__ __align__(16) float Bs[2][BK][LDB];
+  const int z = blockIdx.z;
+  const float* __restrict__ A = p.A + (long long)z * p.zA;
+  const float* __restrict__ B = (z == 1 && p.B1) ? p.B1 : p.B + (long long)z * p.zB;
+  float* C = p.C + (long long)z * p.zC;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wm = (warp >> 2) * WM, wn = (warp & 3) * WN, g = lane >> 2, t = lane & 3;
+  const bool a_k = p.sa_k == 1, b_n = p.sb_n == 1;
+  float ra[NA], rb[NB];
+  auto load = [&](int k0) {
+#pragma unroll
+    for (int i = 0; i < NA; ++i) {
+      const int idx = tid + i * 256;
+      const int kk = a_k ? idx % BK : idx / BM, mm = a_k ? idx / BK : idx % BM;
+      const int gm = m0 + mm, gk = k0 + kk;
+      ra[i] = (gm < p.M && gk < p.K) ? __ldcg(A + (long long)gm * p.sa_m + (long long)gk * p.sa_k) : 0.f;
+    }
+#pragma unroll
+    for (int i = 0; i < NB; ++i) {
+      const int idx = tid + i * 256;
+      const int nn = b_n ? idx % BN : idx / BK, kk = b_n ? idx / BN : idx % BK;
+      const int gn = n0 + nn, gk = k0 + kk;
+      rb[i] = (gn < p.N && gk < p.K) ? __ldcg(B + (long long)gk * p.sb_k + (long long)gn * p.sb_n) : 0.f;
+    }
+  };
+  auto store = [&](int buf) {
+#pragma unroll
+    for (int i = 0; i < NA; ++i) {
+      const int idx = tid + i * 256;
+      const int kk = a_k ? idx % BK : idx / BM, mm = a_k ? idx / BK : idx % BM;
+      As[buf][kk][mm] = ra[i];
+    }
+#pragma unroll
+    for (int i = 0; i < NB; ++i) {
+      const int idx = tid + i * 256;
+      const int nn = b_n ? idx % BN : idx / BK, kk = b_n ? idx / BN : idx % BK;
+      Bs[buf][kk][nn] = rb[i];
+    }
+  };
+  float acc[MT][NT][4];
+#pragma unroll
+  for (int i = 0; i < MT; ++i)
+#pragma unroll
+    for (int j = 0; j < NT; ++j) acc[i][j][0] = acc[i][j][1] = acc[i][j][2] = acc[i][j][3] = 0.f;
+  load(0);
+  store(0);
+  __syncthreads();
+  int buf = 0;
+  for (int k0 = 0; k0 < p.K; k0 += BK) {
+    const bool more = k0 + BK < p.K;
+    if (more) load(k0 + BK);
+#pragma unroll
+    for (int ks = 0; ks < BK; ks += 8) {
+      uint32_t bh[NT][2], bl[NT][2];
+#pragma unroll
+      for (int j = 0; j < NT; ++j) {
+        split_tf32(Bs[buf][ks + t][wn + j * 8 + g], bh[j][0], bl[j][0]);
+        split_tf32(Bs[buf][ks + t + 4][wn + j * 8 + g], bh[j][1], bl[j][1]);
+      }
+#pragma unroll
+      for (int i = 0; i < MT; ++i) {
+        uint32_t ah[4], al[4];
+        split_tf32(As[buf][ks + t][wm + i * 16 + g], ah[0], al[0]);
+        split_tf32(As[buf][ks + t][wm + i * 16 + g + 8], ah[1], al[1]);
+        split_tf32(As[buf][ks + t + 4][wm + i * 16 + g], ah[2], al[2]);
+        split_tf32(As[buf][ks + t + 4][wm + i * 16 + g + 8], ah[3], al[3]);
+#pragma unroll
+        for (int j = 0; j < NT; ++j) {
+          mma_tf32(acc[i][j], al, bh[j]);  // small terms first
+          mma_tf32(acc[i][j], ah, bl[j]);
+          mma_tf32(acc[i][j], ah, bh[j]);
+        }
+      }
+    }
+    if (more) {
+      store(buf ^ 1);
+      __syncthreads();
+      buf ^= 1;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < MT; ++i)
+#pragma unroll
+    for (int j = 0; j < NT; ++j)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int m = m0 + wm + i * 16 + g + (q >> 1) * 8, n = n0 + wn + j * 8 + 2 * t + (q & 1);
+        if (m >= p.M || n >= p.N) continue;
+        float v = acc[i][j][q];
+        float* c = C + (long long)m * p.ldc + n;
+        if (p.accumulate) v += *c;
+        if (p.relu) v = fmaxf(v, 0.f);
+        if (p.mask && !(p.mask[(long long)m * p.ldmask + n] > 0.f)) v = 0.f;
+        *c = v;
+      }
+}
+
 __global__ void splitk_reduce_kernel(const GemmP p) {
   if (p.gate.closed()) return;
   const long long n_out = (long long)p.M * p.N;
@@ -232,6 +353,8 @@ __global__ void splitk_reduce_kernel(const GemmP p) {
     *c = v;
   }
 }
+
+static bool g_gemm_simt = getenv("SRLX_GEMM_SIMT") != nullptr;  // diagnostic: FMA tiles instead of 3 x TF32 tensor-core tiles
 
 static int launch_gemm(const GemmP& p_in, int nz, cudaStream_t s, float* ws = nullptr, size_t ws_floats = 0) {
   GemmP p = p_in;
@@ -258,10 +381,12 @@ static int launch_gemm(const GemmP& p_in, int nz, cudaStream_t s, float* ws = nu
     sgemm_kernel<32, 32, 2, 4><<<grid, 128, 0, s>>>(p);
   } else if (t128 >= 120) {  // enough 128 x 128 tiles for the 148 SMs
     dim3 grid((p.N + 127) / 128, (p.M + 127) / 128, nz);
-    sgemm_tiled_kernel<128, 128><<<grid, 256, 0, s>>>(p);
+    if (g_gemm_simt) sgemm_tiled_kernel<128, 128><<<grid, 256, 0, s>>>(p);
+    else sgemm_mma_kernel<128, 128><<<grid, 256, 0, s>>>(p);
   } else if (t64 >= 32) {
     dim3 grid((p.N + 63) / 64, (p.M + 63) / 64, nz);
-    sgemm_tiled_kernel<64, 64><<<grid, 256, 0, s>>>(p);
+    if (g_gemm_simt) sgemm_tiled_kernel<64, 64><<<grid, 256, 0, s>>>(p);
+    else sgemm_mma_kernel<64, 64><<<grid, 256, 0, s>>>(p);
   } else {
     dim3 grid((p.N + 63) / 64, (p.M + 63) / 64, nz);
     sgemm_kernel<64, 64, 4, 4><<<grid, 256, 0, s>>>(p);
@@ -665,6 +790,11 @@ __global__ void __launch_bounds__(256, 1) lstm_seq_bwd_kernel(const SeqBwdP p) {
 __device__ __forceinline__ long long ring_slot(const srlx_r2d2& r, long long pos, int e) {
   return (pos % r.env.ring_rows) * (long long)r.env.n_envs + e;
 }
+// SumTree leaf of ring row (pos % R) of column e: ENV-major, so that the rows one env writes in a step (up to seq_len at an episode's
+// end) are adjacent leaves and share their ancestors -- the bulk add rebuilds ~2 nodes per row instead of one per row and level
+__device__ __forceinline__ long long ring_leaf(const srlx_r2d2& r, long long pos, int e) {
+  return (long long)e * r.env.ring_rows + (pos % r.env.ring_rows);
+}
 // position held by ring row `row` of column e, or -1 if the row has never been written
 __device__ __forceinline__ long long ring_pos_of_row(const srlx_r2d2& r, int row, long long cur) {
   const int R = r.env.ring_rows;
@@ -901,12 +1031,12 @@ __global__ void __launch_bounds__(1024) r2d2_add_kernel(const __grid_constant__ 
       const long long pos = (long long)c0 + j;
       if (pos >= R) {  // the column's first wrap cuts every anchor that still reaches back to row 0; later rows cut one anchor each
         for (int a = (pos == R ? 1 : W - 1); a <= W - 1; ++a) {
-          const long long idx = ring_slot(r, pos - R + a, e) + cap - 1;
+          const long long idx = ring_leaf(r, pos - R + a, e) + cap - 1;
           r.add_idx[o++] = idx;
           __stcg(tree + idx, 0.0);
         }
       }
-      const long long idx = ring_slot(r, pos, e) + cap - 1;
+      const long long idx = ring_leaf(r, pos, e) + cap - 1;
       r.add_idx[o++] = idx;
       __stcg(tree + idx, maxp);
     }
@@ -919,12 +1049,29 @@ __global__ void __launch_bounds__(1024) r2d2_add_kernel(const __grid_constant__ 
   __syncthreads();
   int depth = 0;
   while (((2 * cap - 1) >> (depth + 1)) > 0) ++depth;  // levels above the deepest leaf
+  // entries of one env are neighbours in the list and (env-major leaves) in the tree: an entry whose ancestor at this level equals its
+  // list predecessor's leaves the node to that entry; the survivors go four at a time so that their loads overlap
   for (int lv = 1; lv <= depth; ++lv) {
-    for (int i = tid; i < total; i += 1024) {
-      const uint64_t ip1 = (uint64_t)r.add_idx[i] + 1;
-      if ((ip1 >> lv) == 0) continue;
-      const uint64_t node = (ip1 >> lv) - 1;
-      __stcg(tree + node, __ldcg(tree + 2 * node + 1) + __ldcg(tree + 2 * node + 2));
+    for (int i0 = tid; i0 < total; i0 += 4 * 1024) {
+      uint64_t node[4];
+      double a[4], b[4];
+      bool on[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int i = i0 + j * 1024;
+        on[j] = false;
+        if (i < total) {
+          const uint64_t ip1 = (uint64_t)r.add_idx[i] + 1;
+          if ((ip1 >> lv) != 0) {
+            node[j] = (ip1 >> lv) - 1;
+            on[j] = i == 0 || (((uint64_t)r.add_idx[i - 1] + 1) >> lv) != (ip1 >> lv);
+          }
+        }
+        if (on[j]) { a[j] = __ldcg(tree + 2 * node[j] + 1); b[j] = __ldcg(tree + 2 * node[j] + 2); }
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (on[j]) __stcg(tree + node[j], a[j] + b[j]);
     }
     __syncthreads();
   }
@@ -1000,7 +1147,10 @@ __global__ void __launch_bounds__(128) r2d2_gather_kernel(const __grid_constant_
   const int W = r.burnin + r.seq_len, S = r.seq_len, K = D + u + 1, tid = threadIdx.x;
   const long long cap = (long long)eng.ring_rows * E;
   long long slot = r.sel[b];
-  if (eng.mem_kind == SRLX_MEM_PROPORTIONAL) slot -= cap - 1;
+  if (eng.mem_kind == SRLX_MEM_PROPORTIONAL) {  // tree leaves are env-major (ring_leaf), ring slots row-major
+    const long long leaf = slot - (cap - 1);
+    slot = (leaf % eng.ring_rows) * E + leaf / eng.ring_rows;
+  }
   const int e = (int)(slot % E), row = (int)(slot / E);
   const long long cur = r.cursor[e];
   const long long p = ring_pos_of_row(r, row, cur);

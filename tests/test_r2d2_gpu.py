@@ -142,8 +142,11 @@ class _Twin:
         """device batch entry (tree index or slot) -> (env, item)"""
         eng = self.eng
         E, R = eng.E, eng.R
-        slot = int(sel) - (R * E - 1 if eng.per else 0)
-        e, row = slot % E, slot // E
+        if eng.per:  # tree leaves are env-major (csrc/r2d2.cu: ring_leaf)
+            leaf = int(sel) - (R * E - 1)
+            e, row = leaf // R, leaf % R
+        else:
+            e, row = int(sel) % E, int(sel) // E
         cur = int(eng.t["cursor"][e].item())
         assert cur == len(self.workers[e].items)
         pos = row if cur <= R else (cur - 1) - ((cur - 1 - row) % R)
@@ -289,7 +292,7 @@ def test_per_selection_and_weights_equal_the_oracle_memory(has_dup):
                 c = int(cur[e])
                 pos = row if c <= R else (c - 1) - ((c - 1 - row) % R)
                 valid = pos < c and (c <= R or pos - (W - 1) >= c - R)
-                assert (tree[cap - 1 + row * E + e] > 0) == valid, (g, e, row)
+                assert (tree[cap - 1 + e * R + row] > 0) == valid, (g, e, row)
         mem = osum.ProportionalMemory(cap, cfg.per_alpha, cfg.per_beta_initial, cfg.per_beta_steps, has_dup, cfg.per_epsilon)
         mem.tree.tree[:] = tree
         mem.size = int(st.mem_size)
@@ -380,7 +383,7 @@ def test_learning_pendulum_reference_acceptance_gate():
     assert np.mean(rewards) >= -500, rewards
 
 
-@pytest.mark.parametrize("M,N,K", [(7, 5, 3), (40, 33, 70), (200, 150, 37), (1300, 1100, 129), (64, 2048, 517), (2048, 517, 640)])
+@pytest.mark.parametrize("M,N,K", [(7, 5, 3), (40, 33, 70), (200, 150, 37), (1300, 1100, 129), (64, 2048, 517), (2048, 517, 640), (2048, 1700, 70)])
 @pytest.mark.parametrize("a_t,b_t", [(False, False), (True, False), (False, True), (True, True)])
 def test_strided_sgemm_every_tile_variant(M, N, K, a_t, b_t):
     """srlx_sgemm (the map every R2D2 layer runs on) for row- and column-major operands, odd leading dimensions, ReLU and accumulate,
