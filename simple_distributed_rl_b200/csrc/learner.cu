@@ -774,7 +774,10 @@ learner_kernel(const __grid_constant__ srlx_engine eng, const uint32_t n_updates
               any |= (2 * idx[g] + 1 < n_nodes);
             }
           }
-          // leaf priorities; a zero-priority leaf is re-drawn (proportional_memory.py:150-152), sequentially
+          // leaf priorities; a zero-priority leaf is re-drawn (proportional_memory.py:150-152), sequentially.  Every lane of the warp read
+          // s_idx / s_val of this group above; lane g overwrites them below: order the two (compute-sanitizer racecheck reported the
+          // intra-warp read -> write pair, profiles/sanitizer/r1_o_racecheck.tail.txt)
+          __syncwarp();
 #pragma unroll
           for (int g = 0; g < kSampleGroup; ++g) {
             if (lane == g && g0 + g < B) {
