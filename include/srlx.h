@@ -327,6 +327,10 @@ size_t srlx_sizeof_r2d2(void);
 int srlx_r2d2_vec_step(const srlx_r2d2* r, int training, uintptr_t cuda_stream);
 /* n_updates x Trainer.train (r2d2.py:90-215); no-op while mem_size < warmup_size */
 int srlx_r2d2_learn(const srlx_r2d2* r, uint32_t n_updates, uintptr_t cuda_stream);
+/* the same update in two halves, for a data-parallel trainer over several GPUs: phases = 1 runs sample .. backward and leaves the
+ * gradient of this rank's batch in r->grads (the caller all-reduces it: NCCL over NVLink), phases = 2 runs Adam, the priority update,
+ * the target sync and the counters; phases = 3 = srlx_r2d2_learn.  One update per call when split. */
+int srlx_r2d2_learn_phase(const srlx_r2d2* r, uint32_t n_updates, int phases, uintptr_t cuda_stream);
 /* q_out[n][A] = Q of ONE step from the given LSTM state: obs [n][D], h / c [n][u] in, h_out / c_out [n][u] out (may alias h / c);
  * test tap and evaluation helper: runs in the learner workspace (r->xh, r->cbuf, r->act), so n <= batch_size and never between the
  * kernels of an update */

@@ -180,6 +180,7 @@ SYMBOLS = [
     ("srlx_sizeof_r2d2", _sz, []),
     ("srlx_r2d2_vec_step", C.c_int, [C.POINTER(SrlxR2d2), _i32, _uptr]),
     ("srlx_r2d2_learn", C.c_int, [C.POINTER(SrlxR2d2), _u32, _uptr]),
+    ("srlx_r2d2_learn_phase", C.c_int, [C.POINTER(SrlxR2d2), _u32, _i32, _uptr]),
     ("srlx_r2d2_forward", C.c_int, [C.POINTER(SrlxR2d2), _i32, _P, _P, _P, _u32, _P, _P, _P, _uptr]),
     ("srlx_sgemm", C.c_int, [_P, C.c_longlong, C.c_longlong, _P, C.c_longlong, C.c_longlong, _P, C.c_longlong, _i32, _i32, _i32, _i32, _i32, _uptr]),
     ("srlx_dense_bf16_tc", C.c_int, [_P, _i32, _P, _i32, _P, _P, _i32, _i32, _i32, _i32, _i32, _i32, _uptr]),

@@ -1457,7 +1457,13 @@ extern "C" int srlx_r2d2_forward(const srlx_r2d2* r, int use_target, const float
 }
 
 extern "C" int srlx_r2d2_learn(const srlx_r2d2* r, uint32_t n_updates, uintptr_t cuda_stream) {
+  return srlx_r2d2_learn_phase(r, n_updates, 3, cuda_stream);
+}
+
+extern "C" int srlx_r2d2_learn_phase(const srlx_r2d2* r, uint32_t n_updates, int phases, uintptr_t cuda_stream) {
   if (int rc = r2d2_check(r)) return rc;
+  SRLX_REQUIRE(phases >= 1 && phases <= 3, "srlx_r2d2_learn_phase: phases must be 1 (gradients), 2 (apply) or 3 (both)");
+  SRLX_REQUIRE(phases == 3 || n_updates == 1, "srlx_r2d2_learn_phase: one update per call when the phases are split");
   const srlx_engine& eng = r->env;
   cudaStream_t s = (cudaStream_t)cuda_stream;
   const bool per = eng.mem_kind == SRLX_MEM_PROPORTIONAL;
@@ -1483,6 +1489,7 @@ extern "C" int srlx_r2d2_learn(const srlx_r2d2* r, uint32_t n_updates, uintptr_t
   const bool persistent = !r->no_persistent && r->bar != nullptr && B <= 64 && u <= 512 && D + 1 <= 32 && 2 * ((u + 7) / 8) <= n_sm && (u + 3) / 4 <= n_sm;
   if (per) SRLX_CHECK_CUDA(cudaFuncSetAttribute(r2d2_priority_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TreeHashScratch)));
   for (uint32_t it = 0; it < n_updates; ++it) {
+    if (phases & 1) {
     // memory.sample (r2d2.py:91) + the batch layout of _train_on_batches (:109-133)
     if (per) r2d2_sample_per_kernel<<<1, 1024, 0, s>>>(*r, gate);
     else r2d2_sample_uniform_kernel<<<1, 256, 0, s>>>(*r, gate);
@@ -1589,6 +1596,8 @@ extern "C" int srlx_r2d2_learn(const srlx_r2d2* r, uint32_t n_updates, uintptr_t
       gw.M = 4 * u; gw.N = K; gw.K = rowsS; gw.gate = gate;
       launch_gemm(gw, 1, s);
     }
+    }  // phase 1: r->grads holds the gradient of this rank's batch
+    if (!(phases & 2)) continue;
     r2d2_adam_kernel<<<(r->n_params + 255) / 256 < 1184 ? (r->n_params + 255) / 256 : 1184, 256, 0, s>>>(*r, gate);
     count_launch();
     if (per) {

@@ -271,6 +271,7 @@ class R2D2Engine:
                 self.t["add_idx"] = z(E * (2 * S + W), torch.int64)
                 self.t["add_pri"] = z(E * (2 * S + W), torch.float64)
         self.c = self._build_struct()
+        self._dp_world, self._dp_group, self._dp_ready = 1, None, False
         self.set_weights(self.spec.init_keras(cfg.seed) if weights is None else weights)
         if training and self.per:
             self._write_state(max_priority=1.0)  # ProportionalMemory.max_priority starts at 1 (proportional_memory.py:116)
@@ -323,7 +324,38 @@ class R2D2Engine:
 
     def learn(self, n_updates: int = 1):
         with torch.cuda.device(self.device):
-            _lib.check(self.lib.srlx_r2d2_learn(C.byref(self.c), int(n_updates), self._s()))
+            if self._dp_world <= 1:
+                _lib.check(self.lib.srlx_r2d2_learn(C.byref(self.c), int(n_updates), self._s()))
+                return
+            import torch.distributed as dist
+
+            if not self._dp_ready:  # the warm-up gate is per shard on the device: open it for all ranks in the same update
+                ok = torch.tensor([int(self.read_state().mem_size >= self.cfg.warmup_size)], device=self.device)
+                dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self._dp_group)
+                if not int(ok.item()):
+                    return
+                self._dp_ready = True
+            for _ in range(int(n_updates)):  # ONE trainer over all shards: the gradient of the global batch, the same Adam step everywhere
+                _lib.check(self.lib.srlx_r2d2_learn_phase(C.byref(self.c), 1, 1, self._s()))
+                dist.all_reduce(self.t["grads"], op=dist.ReduceOp.SUM, group=self._dp_group)
+                self.t["grads"].mul_(1.0 / self._dp_world)
+                _lib.check(self.lib.srlx_r2d2_learn_phase(C.byref(self.c), 1, 2, self._s()))
+
+    def link_data_parallel(self, group=None):
+        """Actor shards + ONE learner (BASELINE configs[3]; the reference's distributed mode has one trainer fed by all actors,
+        srl/base/run/play_mp.py:352-462): every rank keeps its env copies and its replay shard, samples batch_size sequences from it,
+        and every update applies the gradient of the GLOBAL batch (world x batch_size sequences: keras' mean over all of them) --
+        an NCCL all-reduce of the flat gradient over NVLink between the backward pass and Adam (6 MB at LSTM 512: tens of
+        microseconds against milliseconds of update).  Parameters, target network and Adam state start from rank 0's and stay
+        bit-identical.  IS weights use the shard's own N / total / max.  All ranks must pass the warm-up gate together (same
+        warmup_size and env count per rank)."""
+        import torch.distributed as dist
+
+        world = dist.get_world_size(group)
+        if world > 1:
+            for k in ("params", "target", "adam_m", "adam_v"):
+                dist.broadcast(self.t[k], src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        self._dp_world, self._dp_group, self._dp_ready = world, group, False
 
     def forward(self, obs, h, c, use_target=False):
         """(q [n][A], h' [n][u], c' [n][u]) of one step (n <= batch_size; runs in the learner workspace)."""

@@ -179,3 +179,26 @@ def test_data_parallel_learning_gate_cartpole():
     assert st.train_count > 40_000
     for r in runners:
         assert float(np.mean(r.evaluate(max_episodes=50, test_epsilon=0.0))) >= 150.0
+
+
+def test_r2d2_actor_shards_one_learner_under_torchrun():
+    """BASELINE configs[3]'s layout in small: two ranks (torchrun, NCCL), each with its own env copies and replay shard, ONE trainer step
+    per update on the global batch (gradient all-reduce between backward and Adam, simple_distributed_rl_b200/r2d2.py::
+    link_data_parallel): parameters, target network and Adam state stay bit-identical on both ranks while they keep acting and learning."""
+    import json
+    import os
+    import subprocess
+    import sys
+
+    _need_gpus(2)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, R2D2_SMALL="1")
+    for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "MASTER_ADDR", "MASTER_PORT"):
+        env.pop(k, None)
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29531", os.path.join(root, "tools", "r2d2_dp_check.py")], capture_output=True, text=True, env=env,
+                       timeout=600)
+    line = [ln for ln in r.stdout.splitlines() if ln.startswith("R2D2DP ")]
+    assert r.returncode == 0 and line, r.stdout[-2000:] + r.stderr[-2000:]
+    out = json.loads(line[-1][len("R2D2DP "):])
+    assert out["world"] == 2 and out["replicas_bit_identical"] is True and out["train_count"] >= 20 and out["global_batch"] == 64
