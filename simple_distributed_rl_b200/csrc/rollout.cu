@@ -386,7 +386,8 @@ static void launch_post_step(const srlx_engine* eng, cudaStream_t st) {
 static int check_engine(const srlx_engine* eng) {
   SRLX_REQUIRE(eng != nullptr, "engine is NULL");
   SRLX_REQUIRE(eng->n_envs >= 1, "n_envs must be >= 1");
-  SRLX_REQUIRE(eng->obs_dim >= 1 && eng->obs_dim <= SRLX_MAX_OBS && eng->obs_dim <= 4, "obs_dim %d unsupported", eng->obs_dim);
+  // the device envs have <= 4 observation floats; an external env (host loop) may hand over up to SRLX_MAX_OBS (stacked states)
+  SRLX_REQUIRE(eng->obs_dim >= 1 && eng->obs_dim <= (eng->env_id == SRLX_ENV_EXTERNAL ? SRLX_MAX_OBS : 4), "obs_dim %d unsupported", eng->obs_dim);
   SRLX_REQUIRE(eng->n_actions >= 1 && eng->n_actions <= SRLX_MAX_ACTIONS, "n_actions %d out of range", eng->n_actions);
   SRLX_REQUIRE(eng->net.n_layers >= 1 && eng->net.n_layers <= SRLX_MAX_LAYERS, "n_layers %d out of range", eng->net.n_layers);
   SRLX_REQUIRE(eng->net.in_dim == eng->obs_dim, "net.in_dim != obs_dim");

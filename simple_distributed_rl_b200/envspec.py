@@ -97,8 +97,8 @@ def make_env_spec(name: str, **kw) -> EnvSpec:
     if name == "external":
         # stepped by a HOST loop (the reference's core_play.play through the plug-in classes, srl_classes.py): only the shapes matter
         D, A = int(kw["obs_dim"]), int(kw["n_actions"])
-        if not (1 <= D <= 4 and 1 <= A <= 16):
-            raise NotImplementedError(f"the device learners take <= 4 observation floats and <= 16 discrete actions (got {D}, {A})")
+        if not (1 <= D <= 16 and 1 <= A <= 16):  # SRLX_MAX_OBS / SRLX_MAX_ACTIONS; more than 4 floats: the generic learner
+            raise NotImplementedError(f"the device learners take <= 16 observation floats and <= 16 discrete actions (got {D}, {A})")
         return EnvSpec(name, _lib.ENV_EXTERNAL, D, A, 2**31 - 1, 0, 0, reward_baseline={})
     raise ValueError(f"environment {name!r} is not available on device (supported: Grid, EasyGrid, CartPole-v1, Pendulum-v1)")
 

@@ -77,10 +77,12 @@ def _engine_config(config) -> EngineConfig:
         return cached
     assert config.is_setup(), "RLConfig.setup(env) must have run (make_memory / make_parameter do it)"
     obs, act = config.observation_space, config.action_space
-    if len(obs.shape) != 1 or not hasattr(act, "n"):
-        raise NotImplementedError(f"device path: a flat observation vector and a discrete action are needed (got {obs}, {act})")
+    if len(obs.shape) < 1 or not hasattr(act, "n"):
+        raise NotImplementedError(f"device path: a vector observation and a discrete action are needed (got {obs}, {act})")
+    # window_length > 1: WorkerRun stacks the last states itself (worker_run.py:318-322) and the reference's MLP input block flattens
+    # them; the device sees the flattened stack as one observation vector
     ecfg = engine_config_from_srl("external", config, num_envs=1, seed=int(getattr(config, "b200_seed", 0)),
-                                  env_kwargs=dict(obs_dim=int(obs.shape[0]), n_actions=int(act.n)))
+                                  env_kwargs=dict(obs_dim=int(np.prod(obs.shape)), n_actions=int(act.n)), allow_window=True)
     object.__setattr__(config, "_b200_engine_config", ecfg)
     return ecfg
 

@@ -46,7 +46,7 @@ def _algo_of(rl_config) -> str:
 
 
 def engine_config_from_srl(env: Any, rl_config: Any, num_envs: int, seed: int = 0, ring_rows: Optional[int] = None,
-                           env_kwargs: Optional[dict] = None) -> EngineConfig:
+                           env_kwargs: Optional[dict] = None, allow_window: bool = False) -> EngineConfig:
     """Map (env id or EnvConfig, dqn/rainbow Config) -> EngineConfig.  Unsupported settings raise.  env = "external" (with
     env_kwargs = {obs_dim, n_actions}) describes an env stepped by a host loop (srl_classes.py)."""
     env_name = env if isinstance(env, str) else _get(env, "name", _get(env, "id", None))
@@ -55,8 +55,9 @@ def engine_config_from_srl(env: Any, rl_config: Any, num_envs: int, seed: int = 
     if env_name == "Pendulum-v1":  # continuous action Box: the value-based worker sees RLConfig.action_division_num torques
         env_kwargs.setdefault("action_division_num", int(_get(rl_config, "action_division_num", 10)))
     # ---- things the device path does not implement: refuse loudly
-    if _get(rl_config, "window_length", 1) not in (0, 1):
-        raise NotImplementedError("window_length > 1 is not supported on the device path")
+    if _get(rl_config, "window_length", 1) not in (0, 1) and not allow_window:
+        # the plug-in classes get the stacked state from the reference's own WorkerRun (allow_window); the device rollout does not stack
+        raise NotImplementedError("window_length > 1 is not supported by the device rollout (it is through srl_classes)")
     if _get(rl_config, "frameskip", 0) not in (0, None):
         raise NotImplementedError("frameskip is not supported on the device path")
     eps_sched = _schedule_of(rl_config, "epsilon_scheduler", float(_get(rl_config, "epsilon", 0.1)), allow_linear=True)

@@ -175,3 +175,38 @@ def test_reference_runner_on_an_env_with_invalid_actions(masked_env, srl_mod, al
     assert not np.any(acts == 1 + obs % 3)  # never the forbidden action of the state it was chosen in
     assert np.isfinite(state.trainer.info["loss"])
     assert len(runner.evaluate(max_episodes=3)) == 3
+
+
+@pytest.mark.parametrize("force", ["", "generic"])
+def test_learners_with_wide_observations_equal_the_oracle(force, monkeypatch):
+    """observation vectors of more than 4 floats (stacked states, window_length > 1) run on learner_small_kernel (+ its replay CTA) or
+    the generic learner (SRLX_LEARNER=generic): 7 floats, PER, 3-step Rainbow, no masks, against the oracle update by update."""
+    from simple_distributed_rl_b200.engine import DeviceEngine, EngineConfig
+
+    if force:
+        monkeypatch.setenv("SRLX_LEARNER", force)
+    D, A, E, R = 7, 3, 4, 24
+    kw = dict(env="external", env_kwargs=dict(obs_dim=D, n_actions=A), n_envs=E, ring_rows=R, batch_size=8, warmup_size=8, seed=5,
+              algo="rainbow", hidden=(32,), dueling="average", multisteps=3, mem_kind=1)
+    dev = DeviceEngine(EngineConfig(**kw), debug=True)
+    assert dev.learner_info()[0] == ("learner_kernel" if force else "learner_small_kernel")
+    mu, sigma = dev.get_params()
+    orc = oeng.OracleEngine(oeng.EngineConfig(**kw), mu, sigma)
+    rng = np.random.default_rng(4)
+    n_upd = 0
+    for g in range(40):
+        rec = _records(rng, E, D, A)
+        dev.ext_step(*rec[:6])
+        orc.ext_step(*rec[:6])
+        if g < 6:
+            continue
+        dev.learn(1)
+        out = orc.learn(1)[0]
+        n_upd += 1
+        np.testing.assert_array_equal(dev.t["dbg_sample_idx"].cpu().numpy(), out["idx"])
+        np.testing.assert_allclose(dev.t["dbg_target_q"].cpu().numpy(), out["target_q"], rtol=1e-4, atol=2e-5)
+        mu_d, _ = dev.get_params()
+        np.testing.assert_allclose(mu_d, orc.mu, rtol=1e-4, atol=2e-5)
+        orc.adam.mu.data.copy_(torch.as_tensor(mu_d))
+        orc.tgt_mu = dev.get_target()[0].copy()
+    assert n_upd >= 30

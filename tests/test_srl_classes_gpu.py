@@ -226,3 +226,24 @@ def test_reference_runner_trains_on_the_device_proportional_memory(srl_mod):
     cap = mem.capacity
     assert mem.length() >= 60 and abs(tree[0] - tree[cap - 1:].sum()) <= 1e-9 * tree[0]
     assert mem.max_priority >= 1.0 and type(state.trainer).__module__.startswith("srl.")
+
+
+def test_reference_runner_with_window_length(plug, srl_mod):
+    """RLConfig.window_length > 1: WorkerRun stacks the last states (worker_run.py:318-322), the device sees the flattened stack as
+    one observation (Grid: 3 x 2 = 6 floats: learner_small_kernel or the generic learner); consecutive rows of the ring are shifted copies of each other."""
+    import srl
+
+    dqn, rainbow = srl_mod
+    cfg = _small_dqn(dqn, window_length=3)
+    runner = srl.Runner("Grid", cfg)
+    state = runner.train(max_train_count=80)
+    eng = state.memory.engine
+    assert eng.D == 6 and eng.learner_info()[0] in ("learner_kernel", "learner_small_kernel") and state.trainer.get_train_count() == 80
+    n = min(int(eng.read_state().vec_steps), eng.R)
+    obs = eng.t["ring_obs"][:n].cpu().numpy()
+    nobs = eng.t["ring_next_obs"][:n].cpu().numpy()
+    np.testing.assert_array_equal(obs[:, 2:], nobs[:, :4])  # the stack moves on by one state per step
+    done = eng.t["ring_done"][:n].cpu().numpy().astype(bool)
+    keep = ~done[:-1]
+    np.testing.assert_array_equal(nobs[:-1][keep], obs[1:][keep])  # the next row starts from this row's next state within an episode
+    assert np.isfinite(state.trainer.info["loss"]) and len(runner.evaluate(max_episodes=2)) == 2
