@@ -546,6 +546,10 @@ struct SeqFwdP {
 // loop: a float4 read is served one quarter-warp at a time, and the slice offsets are skewed so that the 4 addresses of a quarter-warp
 // fall into different banks).  Rows go in passes of 16: partial sums -> shared [slice][row][gate row], summed in slice order by the
 // two threads that own (row, unit), which keep c in a register across all steps.
+#ifndef SRLX_FWD_RP
+#define SRLX_FWD_RP 16
+#endif
+constexpr int kFwdRP = SRLX_FWD_RP;  // rows per pass of the forward unroll
 constexpr int kFwdXS = 608, kFwdExtra = 576, kFwdRedStride = 16 * 32 + 8;
 __device__ __forceinline__ int fwd_hoff(int s) { return s * 16 + (s >> 1) * 4; }
 
@@ -553,7 +557,7 @@ template <int ROWS>
 __global__ void __launch_bounds__(256, 1) lstm_seq_fwd_kernel(const SeqFwdP p) {
   if (p.gate.closed()) return;
   extern __shared__ __align__(16) float seq_smem[];
-  constexpr int XS = kFwdXS, RP = 16, NPASS = ROWS / RP, RSTR = kFwdRedStride;
+  constexpr int XS = kFwdXS, RP = kFwdRP, NPASS = ROWS / RP, RSTR = kFwdRedStride;
   float* xs = seq_smem;              // [ROWS][XS]
   float* red = seq_smem + ROWS * XS; // [32 slices][RSTR]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, j = lane >> 2, ksub = lane & 3, sl = warp * 4 + ksub;
@@ -640,7 +644,7 @@ __global__ void __launch_bounds__(256, 1) lstm_seq_fwd_kernel(const SeqFwdP p) {
         }
       }
       __syncthreads();
-      if (r0 < B) {
+      if (r0 < B && pair < RP * 8) {
         float4 sg = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
         for (int s2 = 0; s2 < 16; ++s2) {
