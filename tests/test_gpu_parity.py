@@ -1205,3 +1205,45 @@ def test_vec_runner_stop_conditions_counters_and_callbacks():
     h2 = Hooks(stop_after=3)
     st = r.train(max_steps=1000 * E, callbacks=[h2])                                   # a True from on_step_end stops the run
     assert h2.calls.count("step_end") == 3 and st.total_step == 3 * E and st.end_reason == "callback.on_step_end"
+
+
+@pytest.mark.parametrize("has_dup,capacity", [(True, 64), (False, 37), (True, 1000)])
+def test_seam_random_call_sequences_equal_the_oracle_memory(has_dup, capacity):
+    """DeviceProportionalMemory (one launch per sample over an op list in mapped host memory) against oracle/sumtree.py's
+    ProportionalMemory on long random sequences of add(None) / add(p) / sample / update in every interleaving, more ops between two
+    samples than one hash pass holds, the ring wrapping: tree arrays bit for bit, max_priority, size, leaf selection for injected
+    uniforms, weights to 1e-6.  (Leaf selection can only be compared while the two trees agree in every bit the walk looks at; with
+    1e-13 pow differences a draw that lands within that distance of a node boundary would differ -- none does in these seeds.)"""
+    from oracle import sumtree as osum
+
+    from simple_distributed_rl_b200.memory import DeviceProportionalMemory
+
+    rng = np.random.default_rng(capacity)
+    dev = DeviceProportionalMemory(capacity, 0.7, 0.5, 50, has_duplicate=has_dup)
+    orc = osum.ProportionalMemory(capacity, 0.7, 0.5, 50, has_dup, 0.0001)
+    last_idx = None
+    for it in range(400):
+        kind = rng.integers(0, 10)
+        if kind < 5 or orc.size < 12:
+            n = int(rng.integers(1, 90 if kind == 0 else 4))
+            for _ in range(n):
+                p = None if rng.random() < 0.3 else float(rng.random() * 3)
+                dev.add(it, p)
+                orc.add(p)
+        elif kind < 8:
+            B = int(rng.integers(1, 9))
+            u = rng.random((B, 64))
+            _, w, idx = dev.sample(B, it, uniforms=u)
+            oi, ow, _, _ = orc.sample(B, it, lambda i, k: u[i, k])
+            assert idx == oi.tolist()
+            np.testing.assert_allclose(w, ow, rtol=1e-6)
+            last_idx = idx
+        elif last_idx is not None:
+            pr = rng.random(len(last_idx)).astype(np.float32) * 2
+            dev.update(last_idx, pr)
+            orc.update(np.asarray(last_idx), pr)
+        if it % 37 == 0:  # (CUDA's pow and libm's may differ in the last bit: 1e-13, as in test_tree_golden_sequences)
+            np.testing.assert_allclose(dev.tree_array(), orc.tree.tree, rtol=1e-13, atol=1e-15)
+            assert math.isclose(dev.max_priority, orc.max_priority, rel_tol=1e-13) and dev.length() == orc.size
+    np.testing.assert_allclose(dev.tree_array(), orc.tree.tree, rtol=1e-13, atol=1e-15)
+    assert math.isclose(dev.max_priority, orc.max_priority, rel_tol=1e-13)
