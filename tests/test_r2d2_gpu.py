@@ -405,3 +405,23 @@ def test_strided_sgemm_every_tile_variant(M, N, K, a_t, b_t):
                               torch.cuda.current_stream().cuda_stream))
     torch.cuda.synchronize()
     np.testing.assert_allclose(c[:, :N].cpu().numpy(), want.float().cpu().numpy(), rtol=2e-5, atol=2e-5 * K ** 0.5)
+
+
+def test_runner_max_steps_on_grid_and_weight_round_trip():
+    """R2D2Runner.train(max_steps=...) (counters polled every 8th vector step), Grid (2 observation ints, 4 actions, LSTM units not a
+    multiple of 8), Parameter.call_backup / call_restore in keras order through the device."""
+    from simple_distributed_rl_b200.r2d2 import R2D2Engine, R2D2Runner
+
+    cfg = _cfg(env="Grid", n_envs=24, lstm_units=20, hidden_layers=(16,), dueling_type="max", capacity=24 * 60, warmup_size=48,
+               batch_size=16, memory="Proportional", burnin=1, sequence_length=4)
+    r = R2D2Runner(cfg)
+    st = r.train(max_steps=24 * 40, updates_per_vec_step=2)
+    assert st.end_reason == "max_steps over." and st.total_step == 24 * 40 and st.vec_steps == 40
+    s = r.engine.read_state()
+    assert st.train_count == s.train_count and 60 <= s.train_count <= 80 and s.episode_count > 0
+    w = r.engine.get_weights()
+    assert [x.shape for x in w] == [(2, 80), (20, 80), (80,), (20, 16), (16,), (16, 1), (1,), (20, 16), (16,), (16, 4), (4,)]
+    other = R2D2Engine(cfg, weights=w)
+    assert torch.equal(other.t["params"], r.engine.t["params"]) and torch.equal(other.t["target"], other.t["params"])
+    rewards = r.evaluate(max_episodes=4)
+    assert len(rewards) == 4 and all(-3.0 <= x <= 1.0 for x in rewards)
