@@ -205,6 +205,11 @@ typedef struct srlx_engine {
    *      invalid actions (the device envs).  Rows enter through srlx_ext_step_masked; the generic learner (csrc/learner.cu) reads
    *      them, and srlx_learn dispatches to it whenever the buffer is present ---- */
   uint32_t* ring_invalid; /* [R*E] or NULL */
+  /* ---- any epsilon schedule (SchedulerConfig with several phases / cosine / polynomial ..., srl/rl/schedulers/scheduler.py:232-345) as
+   *      a table: training rollouts of vector step g use eps_table[min(g, eps_table_len - 1)] (the host fills it by stepping the
+   *      reference's own scheduler object 0, 1, 2, ... until it is constant).  NULL: `epsilon` / the linear phase above ---- */
+  const double* eps_table;
+  uint64_t eps_table_len;
 } srlx_engine;
 
 /* ---- PPO (R15; BASELINE configs[4]) -- csrc/ppo.cu restates srl/algorithms/ppo/ppo.py for E vectorised env copies ------------------- */

@@ -49,6 +49,7 @@ class EngineConfig:
     epsilon: float = 0.1
     eps_end: float = 0.1  # linear schedule epsilon -> eps_end over eps_phase_steps steps (0 = constant epsilon)
     eps_phase_steps: int = 0
+    eps_table: Optional[tuple] = None  # epsilon per vector step, held at its last entry (any scheduler, tabulated)
     discount: float = 0.99
     lr: float = 1e-3
     adam_beta1: float = 0.9
@@ -209,6 +210,8 @@ class OracleEngine:
     def epsilon_at(self, step):
         """Linear.update(step).to_float() (srl/rl/schedulers/schedulers/linear.py:11-21); phase 0 = Constant (constant.py)."""
         cfg = self.cfg
+        if cfg.eps_table is not None and len(cfg.eps_table):
+            return float(cfg.eps_table[min(int(step), len(cfg.eps_table) - 1)])
         if not cfg.eps_phase_steps:
             return cfg.epsilon
         if step >= cfg.eps_phase_steps:

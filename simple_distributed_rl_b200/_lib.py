@@ -86,7 +86,7 @@ class SrlxEngine(C.Structure):
         ("tree_blk", _P), ("tree_blk_bytes", C.c_uint64),
         ("eps_end", C.c_double), ("eps_phase_steps", C.c_uint64),
         ("learner_seed", C.c_uint64), ("dp_world", C.c_int32), ("dp_rank", C.c_int32), ("dp_peer", _P * 8), ("dp_bytes", C.c_uint64),
-        ("ring_invalid", _P),
+        ("ring_invalid", _P), ("eps_table", _P), ("eps_table_len", C.c_uint64),
     ]
 
 

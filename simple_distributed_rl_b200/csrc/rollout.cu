@@ -47,7 +47,9 @@ rollout_kernel(const __grid_constant__ srlx_engine eng, const int envs_per_cta, 
   const bool noisy = net.noisy != 0;
   // Linear.update(step_in_training).to_float() (schedulers/linear.py:16-21); evaluation passes test_epsilon in eng.epsilon
   double eps_d = eng.epsilon;
-  if (training && eng.eps_phase_steps)
+  if (training && eng.eps_table && eng.eps_table_len)
+    eps_d = eng.eps_table[g < eng.eps_table_len ? g : eng.eps_table_len - 1];  // any scheduler, tabulated by the host
+  else if (training && eng.eps_phase_steps)
     eps_d = g >= eng.eps_phase_steps ? eng.eps_end : eng.epsilon - ((eng.epsilon - eng.eps_end) / (double)eng.eps_phase_steps) * (double)g;
   const float eps = (float)eps_d;
 

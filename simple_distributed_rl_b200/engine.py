@@ -45,6 +45,7 @@ class EngineConfig:
     epsilon: float = 0.1
     eps_end: float = 0.1  # linear schedule epsilon -> eps_end over eps_phase_steps vector steps (0 = constant epsilon)
     eps_phase_steps: int = 0
+    eps_table: Optional[tuple] = None  # any other schedule, tabulated per vector step (include/srlx.h srlx_engine.eps_table)
     discount: float = 0.99
     lr: float = 1e-3
     adam_beta1: float = 0.9
@@ -107,6 +108,8 @@ class DeviceEngine:
             self.t["tree_blk"] = z(max(64, self.lib.srlx_tree_blk_bytes(self.cap) // 8), torch.float64)
         if cfg.invalid_actions:
             self.t["ring_invalid"] = z(self.cap, torch.int32)
+        if cfg.eps_table is not None and len(cfg.eps_table):
+            self.t["eps_table"] = torch.as_tensor(np.asarray(cfg.eps_table, dtype=np.float64)).to(dev)
         if track_episodes:
             self.t["env_first_ep_reward"] = z(self.E, torch.float64)
             self.t["env_last_ep_len"] = z(self.E, torch.int32)
@@ -157,6 +160,8 @@ class DeviceEngine:
             c.noise_scratch_bytes = self.t["noise_scratch"].numel() * 4
         if "tree_blk" in self.t:
             c.tree_blk_bytes = self.t["tree_blk"].numel() * 8
+        if "eps_table" in self.t:
+            c.eps_table_len = self.t["eps_table"].numel()
         for name, _ in _lib.SrlxEngine._fields_:
             if name in self.t:
                 setattr(c, name, self.t[name].data_ptr())

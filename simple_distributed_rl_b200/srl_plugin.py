@@ -109,7 +109,8 @@ def engine_config_from_srl(env: Any, rl_config: Any, num_envs: int, seed: int = 
         mem_kind=mem_kind, algo=algo, enable_double_dqn=bool(rl_config.enable_double_dqn),
         enable_rescale=bool(rl_config.enable_rescale), enable_reward_clip=bool(rl_config.enable_reward_clip),
         target_update_interval=int(rl_config.target_model_update_interval), seed=int(seed),
-        warmup_size=int(mem.warmup_size), epsilon=eps_sched[0], eps_end=eps_sched[1], eps_phase_steps=eps_sched[2], discount=float(rl_config.discount),
+        warmup_size=int(mem.warmup_size), epsilon=eps_sched[0], eps_end=eps_sched[1], eps_phase_steps=eps_sched[2],
+        eps_table=eps_sched[3] if len(eps_sched) > 3 else None, discount=float(rl_config.discount),
         lr=float(rl_config.lr), retrace_h=float(_get(rl_config, "retrace_h", 1.0)),
         reward_shift=float(_get(rl_config, "reward_shift", 0.0) or 0.0), reward_scale=float(_get(rl_config, "reward_scale", 1.0) or 1.0),
         hidden=hidden, dueling=dueling, noisy=noisy, env_kwargs=env_kwargs, **per)
@@ -130,8 +131,18 @@ def _schedule_of(rl_config: Any, field: str, val: float, allow_linear: bool = Tr
         if int(ph["phase_steps"]) <= 0:
             raise ValueError(f"{field}: linear phase_steps must be > 0")
         return (float(ph["start_rate"]), float(ph["end_rate"]), int(ph["phase_steps"]))
-    raise NotImplementedError(f"{field}: only a constant rate" + (" or one linear phase" if allow_linear else "")
-                              + " is supported on the device path")
+    if not allow_linear:
+        raise NotImplementedError(f"{field}: only a constant rate is supported on the device path")
+    # anything else (several phases, cosine, polynomial, ...): step the reference's own scheduler object 0, 1, 2, ... as a worker
+    # would (ListScheduler is stateful, scheduler.py:319-345) and tabulate until every phase is over and the value stands still
+    total = sum(int(ph.get("phase_steps", 0) or 0) for ph in phases)
+    if total > 8_000_000:
+        raise NotImplementedError(f"{field}: a schedule of {total} steps is too long to tabulate")
+    sch = s.create(val)
+    table = [float(sch.update(g).to_float()) for g in range(total + 2)]
+    if float(sch.update(total + 1000).to_float()) != table[-1]:
+        raise NotImplementedError(f"{field}: the schedule does not settle after its phases; not supported on the device path")
+    return (table[0], table[-1], 0, tuple(table))
 
 
 class DeviceRunner(VecRunner):

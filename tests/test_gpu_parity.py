@@ -281,6 +281,11 @@ ENGINE_CASES = {
     # linear epsilon schedule (DQN/Rainbow .setup_from_atari style: 1.0 -> 0.1), phase ends inside the run
     "cartpole_dqn_linear_epsilon": dict(env="CartPole-v1", algo="dqn", hidden=(32,), mem_kind=0, multisteps=1, n_envs=48, ring_rows=8,
                                         batch_size=16, warmup_size=48, epsilon=1.0, eps_end=0.1, eps_phase_steps=12),
+    # any other epsilon schedule as a table per vector step (several phases / cosine / polynomial; the host steps the reference's own
+    # scheduler object): here linear 1.0 -> 0.4 over 5 steps, cosine 0.4 -> 0.1 over 6, then constant, shorter than the run
+    "cartpole_dqn_epsilon_table": dict(env="CartPole-v1", algo="dqn", hidden=(32,), mem_kind=0, multisteps=1, n_envs=48, ring_rows=8,
+                                       batch_size=16, warmup_size=48, epsilon=1.0,
+                                       eps_table=(1.0, 0.88, 0.76, 0.64, 0.52, 0.4, 0.3897777, 0.3598076, 0.3121320, 0.25, 0.1776457, 0.1, 0.1)),
     # uniform replay + plain weights + more than one hidden layer: learner_small_kernel (one thread block, learner_small.cu)
     "cartpole_dqn_uniform_64x64": dict(env="CartPole-v1", algo="dqn", hidden=(64, 64), mem_kind=0, multisteps=1, n_envs=64,
                                        ring_rows=8, batch_size=32, warmup_size=64, epsilon=0.2),  # BASELINE configs[1] shape

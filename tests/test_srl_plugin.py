@@ -41,7 +41,10 @@ def test_dqn_config_maps_and_unsupported_raises(srl_mod):
     with pytest.raises(NotImplementedError):
         engine_config_from_srl("Grid", cfg, num_envs=64)
     cfg2 = rainbow.Config()
-    cfg2.epsilon_scheduler.add_linear(1.0, 0.1, 1000).add_linear(0.1, 0.01, 1000)  # ListScheduler: not on the device
+    cfg2.epsilon_scheduler.add_linear(1.0, 0.1, 1000).add_linear(0.1, 0.01, 1000)  # ListScheduler: tabulated per vector step
+    e2 = engine_config_from_srl("Grid", cfg2, num_envs=64)
+    assert len(e2.eps_table) == 2002 and e2.eps_table[0] == 1.0 and e2.eps_table[-1] == 0.01
+    cfg2.epsilon_scheduler.add_linear(0.01, 0.001, 9_000_000)  # too long to tabulate: refused, not silently ignored
     with pytest.raises(NotImplementedError):
         engine_config_from_srl("Grid", cfg2, num_envs=64)
     cfg3 = dqn.Config()
@@ -77,6 +80,33 @@ def test_epsilon_scheduler_maps_and_oracle_follows_reference_linear(srl_mod):
     e = engine_config_from_srl("Grid", at, num_envs=8)
     assert (e.epsilon, e.eps_end, e.eps_phase_steps) == (1.0, 0.1, 1_000_000)
     assert (e.hidden, e.enable_reward_clip, e.enable_double_dqn, e.target_update_interval) == ((512,), True, False, 10000)
+
+
+def test_multi_phase_epsilon_schedule_is_tabulated_from_the_reference_scheduler(srl_mod):
+    """Several phases / cosine / polynomial (scheduler.py:232-345, ListScheduler is stateful): the table handed to the device is the
+    reference's own scheduler stepped 0, 1, 2, ... as a worker does (rainbow.py:312); the oracle reads the same table."""
+    from oracle import engine as oeng
+    from simple_distributed_rl_b200.srl_plugin import engine_config_from_srl
+
+    dqn, rainbow = srl_mod
+    cfg = rainbow.Config()
+    cfg.epsilon_scheduler.clear()
+    cfg.epsilon_scheduler.add_linear(1.0, 0.4, 5)
+    cfg.epsilon_scheduler.add_cosine(0.4, 0.1, 6)
+    cfg.epsilon_scheduler.add_polynomial(0.1, 0.02, 7, power=2.0)
+    e = engine_config_from_srl("Grid", cfg, num_envs=8)
+    assert e.eps_table is not None and len(e.eps_table) == 5 + 6 + 7 + 2 and e.eps_phase_steps == 0
+    fresh = cfg.epsilon_scheduler.create(cfg.epsilon)
+    want = [fresh.update(g).to_float() for g in range(40)]
+    o = oeng.OracleEngine.__new__(oeng.OracleEngine)
+    o.cfg = oeng.EngineConfig(env="Grid", epsilon=e.epsilon, eps_table=e.eps_table)
+    assert [o.epsilon_at(g) for g in range(40)] == want
+    assert want[0] == 1.0 and want[-1] == 0.02 and len(set(want)) > 12
+    one = dqn.Config()
+    one.epsilon_scheduler.set_cosine(0.9, 0.05, 11)
+    e1 = engine_config_from_srl("Grid", one, num_envs=8)
+    s1 = one.epsilon_scheduler.create(one.epsilon)
+    assert list(e1.eps_table[:12]) == [s1.update(g).to_float() for g in range(12)] and e1.eps_table[-1] == 0.05
 
 
 def test_register_memory_uses_reference_custom_seam(srl_mod):
