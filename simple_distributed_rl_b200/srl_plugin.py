@@ -62,6 +62,8 @@ def engine_config_from_srl(env: Any, rl_config: Any, num_envs: int, seed: int = 
         raise NotImplementedError("frameskip is not supported on the device path")
     eps_sched = _schedule_of(rl_config, "epsilon_scheduler", float(_get(rl_config, "epsilon", 0.1)), allow_linear=True)
     if getattr(_get(rl_config, "lr_scheduler"), "schedule_type", "") not in ("", None):  # LRSchedulerConfig (rl/schedulers/lr_scheduler.py)
+        # (the reference's own torch trainers cannot run one either: apply_torch_scheduler returns the torch LR-scheduler object and
+        # the trainer then calls zero_grad() / step() on IT, dqn/model_torch.py:79,117-119 -- there is no behaviour to match)
         raise NotImplementedError("lr_scheduler: only the constant learning rate is supported on the device path")
     mem = rl_config.memory
     if _get(mem, "enable_demo_memory", False):

@@ -425,3 +425,44 @@ def test_runner_max_steps_on_grid_and_weight_round_trip():
     assert torch.equal(other.t["params"], r.engine.t["params"]) and torch.equal(other.t["target"], other.t["params"])
     rewards = r.evaluate(max_episodes=4)
     assert len(rewards) == 4 and all(-3.0 <= x <= 1.0 for x in rewards)
+
+
+def test_full_size_update_equals_the_oracle_and_the_per_step_path():
+    """The shape tools/r2d2_bench.py times (BASELINE configs[3]: LSTM 512, dueling 512, burn-in 40, sequence 80, batch 64, proportional
+    sequence replay; 256 env copies here): one update of the persistent unroll kernels + tensor-core GEMM tiles against (a) the oracle
+    trainer on the batch the device gathered (Q, targets, loss 1e-4; gradients 2e-3 of their scale; parameters after Adam) and (b) the
+    same update through one launch per time step (the path the small lockstep cases pin item by item)."""
+    cfg = _cfg(env="CartPole-v1", n_envs=256, lstm_units=512, hidden_layers=(512,), dueling_type="average", burnin=40, sequence_length=80,
+               batch_size=64, capacity=256 * 300, warmup_size=256 * 4, memory="Proportional", enable_rescale=True, enable_retrace=False,
+               lr=1e-4, epsilon=0.4, seed=2)
+    a, b = _engine(cfg), _engine(cfg, persistent=False)
+    for _ in range(130):
+        a.vec_step(True)
+        b.vec_step(True)
+    assert torch.equal(a.t["tree"], b.t["tree"]) and torch.equal(a.t["ring_h"], b.t["ring_h"])
+    w0 = a.get_weights()
+    a.learn(1)
+    b.learn(1)
+    torch.cuda.synchronize()
+    assert torch.equal(a.t["sel"], b.t["sel"]) and torch.equal(a.t["b_actions"], b.t["b_actions"])
+    for k, tol in (("q", 2e-4), ("b_target", 2e-4), ("grads", 2e-3), ("params", 1e-5)):
+        x, y = a.t[k].double(), b.t[k].double()
+        assert float((x - y).abs().max()) <= tol * max(1e-3, float(y.abs().max())), k
+    # (a) the oracle on the gathered batch
+    D, u, W, S, B = a.D, a.u, a.W, a.S, a.B
+    xh = a.t["xh"].cpu().numpy()
+    states = np.transpose(xh[0, :W + 1, :, :D], (1, 0, 2))                      # [B, W + 1, D]
+    tr = _trainer(a, w0)
+    out = tr.train_on_batches(states, a.t["b_actions"].cpu().numpy().tolist(), a.t["b_mu"].cpu().numpy().tolist(),
+                              a.t["b_rewards"].cpu().numpy().tolist(), a.t["b_dones"].cpu().numpy().astype(bool).tolist(),
+                              xh[0, 0, :, D:D + u], a.t["cbuf"].cpu().numpy()[0, 0], a.t["weights"].cpu().numpy())
+    q = a.t["q"].cpu().numpy()
+    np.testing.assert_allclose(q[0], out["q"], rtol=1e-4, atol=1e-4)
+    np.testing.assert_allclose(q[1], out["q_target"], rtol=1e-4, atol=1e-4)
+    np.testing.assert_allclose(a.t["b_target"].cpu().numpy(), out["target"], rtol=1e-4, atol=1e-4)
+    assert abs(a.read_state().last_loss - out["loss"]) <= 1e-4 * max(1.0, abs(out["loss"]))
+    for gd, go in zip(a.spec.to_keras(a.t["grads"].cpu().numpy()), out["grads"]):
+        assert float(np.abs(gd - go).max()) <= 2e-3 * max(1e-6, float(np.abs(go).max()))
+    tr.apply(out["grads"])
+    for wd, wo in zip(a.get_weights(), tr.weights()):
+        np.testing.assert_allclose(wd, wo, rtol=1e-4, atol=2e-5)

@@ -1,2 +1,2 @@
 set -x
-timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -q --timeout 300 -k "lockstep" 2>&1 | tail -8
+timeout 900 python -m pytest tests/test_r2d2_gpu.py -m gpu -q --timeout 600 -k "full_size" 2>&1 | tail -30
