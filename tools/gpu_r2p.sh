@@ -1,2 +1,2 @@
 set -x
-timeout 900 python -m pytest tests/test_r2d2_gpu.py -m gpu -q --timeout 600 -k "full_size" 2>&1 | tail -30
+timeout 600 python tools/quickstart_check.py 2>&1 | grep -v "WARNING\|^###\|st/s" | tail -12
