@@ -304,6 +304,7 @@ typedef struct srlx_r2d2 {
   float* roll_xh;          /* [E][in+u+1] the step's LSTM input [x | h_{t-1} | 1] (the library writes the trailing 1) */
   float* roll_h;           /* [E][u+1] h_t carried to the next step, last column 1 (head input) */
   float* roll_c;           /* [E][u] */
+  float* roll_gates;       /* optional [E][4u]: gate pre-activations of the step (E > 64: the step runs as tiled GEMM + cell update) */
   float* roll_act[SRLX_MAX_LAYERS]; /* [E][head_out[l] + 1] (last column 1); the last one [E][head_out] */
   unsigned char* roll_reset; /* [E] */
   uint32_t* new_c0; uint32_t* new_n;  /* [E] first new row / rows written by the last vector step */
@@ -316,7 +317,8 @@ typedef struct srlx_r2d2 {
   float* dc;               /* [B][u] */
   float* gemm_ws;          /* optional split-K workspace of the narrow weight-gradient maps (32 * max_l head_out[l] * (head_k[l] + 1) floats is enough) */
   uint64_t gemm_ws_floats;
-  uint32_t* bar;           /* [4] barrier words of the persistent unroll kernels (NULL: one launch per time step) */
+  uint32_t* bar;           /* [8] barrier words of the persistent unroll kernels ([0..3]; NULL: one launch per time step) and of the
+                              cooperative replay add ([4], [5]; required with proportional replay) */
   float* act[SRLX_MAX_LAYERS];  /* [2][(seq_len+1)*B][head_out[l] + 1] (last column 1); last layer [2][rows][head_out] */
   float* dact[SRLX_MAX_LAYERS]; /* [(seq_len+1)*B][head_out[l]] gradient wrt the layer's output */
   float* dh;               /* [(seq_len+1)*B][u] gradient wrt the LSTM outputs */

@@ -125,7 +125,7 @@ class SrlxR2d2(C.Structure):
         ("params", _P), ("target", _P), ("adam_m", _P), ("adam_v", _P), ("grads", _P),
         ("cursor", _P), ("ring_obs", _P), ("ring_next_obs", _P), ("ring_action", _P), ("ring_prob", _P), ("ring_reward", _P),
         ("ring_done", _P), ("ring_tstep", _P), ("ring_h", _P), ("ring_c", _P),
-        ("roll_xh", _P), ("roll_h", _P), ("roll_c", _P), ("roll_act", _P * SRLX_MAX_LAYERS), ("roll_reset", _P),
+        ("roll_xh", _P), ("roll_h", _P), ("roll_c", _P), ("roll_gates", _P), ("roll_act", _P * SRLX_MAX_LAYERS), ("roll_reset", _P),
         ("new_c0", _P), ("new_n", _P), ("add_idx", _P), ("add_pri", _P),
         ("xh", _P), ("cbuf", _P), ("gates", _P), ("dgates", _P), ("dc", _P), ("gemm_ws", _P), ("gemm_ws_floats", C.c_uint64), ("bar", _P),
         ("act", _P * SRLX_MAX_LAYERS), ("dact", _P * SRLX_MAX_LAYERS), ("dh", _P), ("q", _P), ("sel", _P), ("weights", _P),

@@ -339,6 +339,46 @@ __global__ void __launch_bounds__(256) sgemm_mma_kernel(const GemmP p) {
       }
 }
 
+// Narrow outputs (the Q head: N = A or 1 + A columns over a K of several hundred): a tile kernel would run one column of CTAs with a
+// long serial k loop.  Here a warp owns a row: the lanes stride over k (coalesced in A and, for a row-major weight, in B), keep N
+// partial sums each and meet in a shuffle tree -- one pass over A at memory speed.
+template <int NMAX>
+__global__ void __launch_bounds__(256) sgemm_narrow_kernel(const GemmP p) {
+  if (p.gate.closed()) return;
+  const int z = blockIdx.z;
+  const float* __restrict__ A = p.A + (long long)z * p.zA;
+  const float* __restrict__ B = (z == 1 && p.B1) ? p.B1 : p.B + (long long)z * p.zB;
+  float* C = p.C + (long long)z * p.zC;
+  const int lane = threadIdx.x & 31;
+  const long long m = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (m >= p.M) return;
+  float acc[NMAX];
+#pragma unroll
+  for (int n = 0; n < NMAX; ++n) acc[n] = 0.f;
+  const float* a = A + m * p.sa_m;
+  for (int k = lane; k < p.K; k += 32) {
+    const float av = __ldcg(a + (long long)k * p.sa_k);
+#pragma unroll
+    for (int n = 0; n < NMAX; ++n)
+      if (n < p.N) acc[n] = fmaf(av, __ldg(B + (long long)k * p.sb_k + (long long)n * p.sb_n), acc[n]);
+  }
+#pragma unroll
+  for (int n = 0; n < NMAX; ++n)
+    for (int sft = 16; sft > 0; sft >>= 1) acc[n] += __shfl_xor_sync(0xffffffffu, acc[n], sft);
+  if (lane == 0) {
+#pragma unroll
+    for (int n = 0; n < NMAX; ++n) {
+      if (n >= p.N) break;
+      float v = acc[n];
+      float* c = C + m * p.ldc + n;
+      if (p.accumulate) v += *c;
+      if (p.relu) v = fmaxf(v, 0.f);
+      if (p.mask && !(p.mask[m * p.ldmask + n] > 0.f)) v = 0.f;
+      *c = v;
+    }
+  }
+}
+
 __global__ void splitk_reduce_kernel(const GemmP p) {
   if (p.gate.closed()) return;
   const long long n_out = (long long)p.M * p.N;
@@ -376,7 +416,10 @@ static int launch_gemm(const GemmP& p_in, int nz, cudaStream_t s, float* ws = nu
     }
   }
   const long long t128 = (long long)((p.M + 127) / 128) * ((p.N + 127) / 128) * nz, t64 = (long long)((p.M + 63) / 64) * ((p.N + 63) / 64) * nz;
-  if (p.M <= 32 || p.N <= 32) {
+  if (p.N <= 8 && p.M >= 256 && p.K >= 64) {  // a narrow head over many rows: warp per row
+    dim3 grid((unsigned)((p.M + 7) / 8), 1, nz);
+    sgemm_narrow_kernel<8><<<grid, 256, 0, s>>>(p);
+  } else if (p.M <= 32 || p.N <= 32) {
     dim3 grid((p.N + 31) / 32, (p.M + 31) / 32, nz);
     sgemm_kernel<32, 32, 2, 4><<<grid, 128, 0, s>>>(p);
   } else if (t128 >= 120) {  // enough 128 x 128 tiles for the 148 SMs
@@ -430,6 +473,20 @@ __global__ void __launch_bounds__((BM / TM) * 8) lstm_fwd_kernel(const LstmFwdP 
     p.c_out[ci] = c;
     p.h_out[(long long)z * p.z_h + (long long)m * p.ld_h + unit] = og * tanhf(c);
     if (p.gates && z == 0) *reinterpret_cast<float4*>(p.gates + ((long long)m * p.u + unit) * 4) = make_float4(ig, fg, gg, og);
+  }
+}
+
+// cell update on pre-activations a tiled GEMM left in `pre` [M][4u] (the rollout's E-row step: the GEMM runs on the tensor-core tiles)
+__global__ void lstm_pointwise_kernel(const float* __restrict__ pre, float* __restrict__ c, float* __restrict__ h_out, long long ld_h, int M, int u) {
+  const long long n = (long long)M * u;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const long long m = i / u;
+    const int unit = (int)(i - m * u);
+    const float4 g4 = *reinterpret_cast<const float4*>(pre + i * 4);
+    const float ig = sigmoidf_(g4.x), fg = sigmoidf_(g4.y), gg = tanhf(g4.z), og = sigmoidf_(g4.w);
+    const float cn = fmaf(fg, c[i], ig * gg);
+    c[i] = cn;
+    h_out[m * ld_h + unit] = og * tanhf(cn);
   }
 }
 
@@ -1001,74 +1058,83 @@ __global__ void r2d2_step_count_kernel(srlx_state* st, int E) {
 // deterministic, no atomics.  (In a tree whose leaves sit on two depths a node can be rebuilt once before its deeper child is final;
 // the deeper path rebuilds it again one level later.)
 __global__ void __launch_bounds__(1024) r2d2_add_kernel(const __grid_constant__ srlx_r2d2 r) {
+  // cooperative launch over a few CTAs: CTA 0 builds the entry list and writes the leaves, then all CTAs rebuild the touched paths,
+  // one level per grid barrier (bar[4] = arrival counter, bar[5] = number of entries; zeroed by the host before the launch)
   __shared__ int s_scan[1024];
   __shared__ int s_base;
   const srlx_engine& eng = r.env;
   const int E = eng.n_envs, R = eng.ring_rows, W = r.burnin + r.seq_len, tid = threadIdx.x;
   const long long cap = (long long)R * E;
-  const double maxp = eng.state->max_priority;
   double* tree = eng.tree;
-  if (tid == 0) s_base = 0;
-  __syncthreads();
-  for (int e0 = 0; e0 < E; e0 += 1024) {
-    const int e = e0 + tid;
-    int cnt = 0;
-    uint32_t c0 = 0, n = 0;
-    if (e < E) {
-      c0 = r.new_c0[e];
-      n = r.new_n[e];
-      for (uint32_t j = 0; j < n; ++j) {
-        const long long pos = (long long)c0 + j;
-        cnt += 1 + (pos >= R ? (W - 1) - (pos == R ? 1 : W - 1) + 1 : 0);
-      }
-    }
-    s_scan[tid] = cnt;
+  unsigned* bar = r.bar + 4;
+  volatile unsigned* n_entries = r.bar + 5;
+  if (blockIdx.x == 0) {
+    const double maxp = eng.state->max_priority;
+    if (tid == 0) s_base = 0;
     __syncthreads();
-    for (int off = 1; off < 1024; off <<= 1) {  // inclusive Hillis-Steele scan
-      const int v = tid >= off ? s_scan[tid - off] : 0;
-      __syncthreads();
-      s_scan[tid] += v;
-      __syncthreads();
-    }
-    int o = s_base + s_scan[tid] - cnt;
-    for (uint32_t j = 0; j < n; ++j) {
-      const long long pos = (long long)c0 + j;
-      if (pos >= R) {  // the column's first wrap cuts every anchor that still reaches back to row 0; later rows cut one anchor each
-        for (int a = (pos == R ? 1 : W - 1); a <= W - 1; ++a) {
-          const long long idx = ring_leaf(r, pos - R + a, e) + cap - 1;
-          r.add_idx[o++] = idx;
-          __stcg(tree + idx, 0.0);
+    for (int e0 = 0; e0 < E; e0 += 1024) {
+      const int e = e0 + tid;
+      int cnt = 0;
+      uint32_t c0 = 0, n = 0;
+      if (e < E) {
+        c0 = r.new_c0[e];
+        n = r.new_n[e];
+        for (uint32_t j = 0; j < n; ++j) {
+          const long long pos = (long long)c0 + j;
+          cnt += 1 + (pos >= R ? (W - 1) - (pos == R ? 1 : W - 1) + 1 : 0);
         }
       }
-      const long long idx = ring_leaf(r, pos, e) + cap - 1;
-      r.add_idx[o++] = idx;
-      __stcg(tree + idx, maxp);
+      s_scan[tid] = cnt;
+      __syncthreads();
+      for (int off = 1; off < 1024; off <<= 1) {  // inclusive Hillis-Steele scan
+        const int v = tid >= off ? s_scan[tid - off] : 0;
+        __syncthreads();
+        s_scan[tid] += v;
+        __syncthreads();
+      }
+      int o = s_base + s_scan[tid] - cnt;
+      for (uint32_t j = 0; j < n; ++j) {
+        const long long pos = (long long)c0 + j;
+        if (pos >= R) {  // the column's first wrap cuts every anchor that still reaches back to row 0; later rows cut one anchor each
+          for (int a = (pos == R ? 1 : W - 1); a <= W - 1; ++a) {
+            const long long idx = ring_leaf(r, pos - R + a, e) + cap - 1;
+            r.add_idx[o++] = idx;
+            __stcg(tree + idx, 0.0);
+          }
+        }
+        const long long idx = ring_leaf(r, pos, e) + cap - 1;
+        r.add_idx[o++] = idx;
+        __stcg(tree + idx, maxp);
+      }
+      __syncthreads();
+      if (tid == 1023) s_base += s_scan[1023];
+      __syncthreads();
     }
-    __syncthreads();
-    if (tid == 1023) s_base += s_scan[1023];
-    __syncthreads();
+    if (tid == 0) *n_entries = (unsigned)s_base;
   }
-  const int total = s_base;
-  __threadfence_block();
-  __syncthreads();
+  unsigned phase = 1;
+  grid_arrive(bar);
+  grid_wait(r.bar, bar, phase * gridDim.x);
+  const int total = (int)*n_entries;
   int depth = 0;
   while (((2 * cap - 1) >> (depth + 1)) > 0) ++depth;  // levels above the deepest leaf
   // entries of one env are neighbours in the list and (env-major leaves) in the tree: an entry whose ancestor at this level equals its
   // list predecessor's leaves the node to that entry; the survivors go four at a time so that their loads overlap
+  const int nthr = gridDim.x * 1024, gtid = blockIdx.x * 1024 + tid;
   for (int lv = 1; lv <= depth; ++lv) {
-    for (int i0 = tid; i0 < total; i0 += 4 * 1024) {
+    for (int i0 = gtid; i0 < total; i0 += 4 * nthr) {
       uint64_t node[4];
       double a[4], b[4];
       bool on[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const int i = i0 + j * 1024;
+        const int i = i0 + j * nthr;
         on[j] = false;
         if (i < total) {
-          const uint64_t ip1 = (uint64_t)r.add_idx[i] + 1;
+          const uint64_t ip1 = (uint64_t)__ldcg(r.add_idx + i) + 1;
           if ((ip1 >> lv) != 0) {
             node[j] = (ip1 >> lv) - 1;
-            on[j] = i == 0 || (((uint64_t)r.add_idx[i - 1] + 1) >> lv) != (ip1 >> lv);
+            on[j] = i == 0 || (((uint64_t)__ldcg(r.add_idx + i - 1) + 1) >> lv) != (ip1 >> lv);
           }
         }
         if (on[j]) { a[j] = __ldcg(tree + 2 * node[j] + 1); b[j] = __ldcg(tree + 2 * node[j] + 2); }
@@ -1077,7 +1143,9 @@ __global__ void __launch_bounds__(1024) r2d2_add_kernel(const __grid_constant__ 
       for (int j = 0; j < 4; ++j)
         if (on[j]) __stcg(tree + node[j], a[j] + b[j]);
     }
-    __syncthreads();
+    ++phase;
+    grid_arrive(bar);
+    grid_wait(r.bar, bar, phase * gridDim.x);
   }
 }
 
@@ -1358,14 +1426,25 @@ static int r2d2_check(const srlx_r2d2* r) {
 // one LSTM step + head on n rows: xh_in [n][K] -> h into h_out (row stride ld_h, which must be followed by a 1 at column u: the head
 // reads [h | 1]), c in place, head activations -> acts[l]
 static int r2d2_net_step(const srlx_r2d2* r, const float* W, const float* xh_in, float* h_out, long long ld_h, float* c, float* const* acts,
-                         int n, cudaStream_t s) {
+                         int n, cudaStream_t s, float* pre = nullptr) {
   const int D = r->env.obs_dim, u = r->lstm_units, K = D + u + 1;
-  LstmFwdP lp{};
-  lp.xh = xh_in; lp.z_xh = 0; lp.W0 = W + r->lstm_off; lp.W1 = nullptr; lp.c_in = c; lp.c_out = c; lp.z_c = 0;
-  lp.h_out = h_out; lp.ld_h = ld_h; lp.z_h = 0; lp.gates = nullptr; lp.M = n; lp.u = u; lp.K = K; lp.gate = Gate{nullptr, 0};
-  if (n <= 32) lstm_fwd_kernel<32, 2><<<dim3((4 * u + 31) / 32, (n + 31) / 32, 1), 128, 0, s>>>(lp);
-  else lstm_fwd_kernel<64, 4><<<dim3((4 * u + 31) / 32, (n + 63) / 64, 1), 128, 0, s>>>(lp);
-  count_launch();
+  if (n > 64 && pre != nullptr) {  // many rows: gate pre-activations on the tiled GEMM, then the cell update
+    GemmP g{};
+    g.A = xh_in; g.sa_m = K; g.sa_k = 1;
+    g.B = W + r->lstm_off; g.sb_k = 1; g.sb_n = K;
+    g.C = pre; g.ldc = 4 * u; g.M = n; g.N = 4 * u; g.K = K; g.gate = Gate{nullptr, 0};
+    launch_gemm(g, 1, s);
+    const long long nb = ((long long)n * u + 255) / 256;
+    lstm_pointwise_kernel<<<(unsigned)(nb < 2368 ? nb : 2368), 256, 0, s>>>(pre, c, h_out, ld_h, n, u);
+    count_launch();
+  } else {
+    LstmFwdP lp{};
+    lp.xh = xh_in; lp.z_xh = 0; lp.W0 = W + r->lstm_off; lp.W1 = nullptr; lp.c_in = c; lp.c_out = c; lp.z_c = 0;
+    lp.h_out = h_out; lp.ld_h = ld_h; lp.z_h = 0; lp.gates = nullptr; lp.M = n; lp.u = u; lp.K = K; lp.gate = Gate{nullptr, 0};
+    if (n <= 32) lstm_fwd_kernel<32, 2><<<dim3((4 * u + 31) / 32, (n + 31) / 32, 1), 128, 0, s>>>(lp);
+    else lstm_fwd_kernel<64, 4><<<dim3((4 * u + 31) / 32, (n + 63) / 64, 1), 128, 0, s>>>(lp);
+    count_launch();
+  }
   const float* in = h_out;
   long long ld_in = ld_h;
   for (int l = 0; l < r->n_head; ++l) {
@@ -1420,11 +1499,15 @@ extern "C" int srlx_r2d2_vec_step(const srlx_r2d2* r, int training, uintptr_t cu
   const long long hb = (nh + 255) / 256;
   r2d2_hidden_kernel<<<(unsigned)(hb < 2368 ? hb : 2368), 256, 0, s>>>(*r, training);
   count_launch(2);
-  r2d2_net_step(r, r->params, r->roll_xh, r->roll_h, u + 1, r->roll_c, r->roll_act, E, s);
+  r2d2_net_step(r, r->params, r->roll_xh, r->roll_h, u + 1, r->roll_c, r->roll_act, E, s, r->roll_gates);
   r2d2_act_kernel<<<(E + 127) / 128, 128, 0, s>>>(*r, training);
   count_launch();
   if (training && per) {
-    r2d2_add_kernel<<<1, 1024, 0, s>>>(*r);
+    SRLX_REQUIRE(r->bar != nullptr, "proportional replay add needs the barrier words (bar)");
+    SRLX_CHECK_CUDA(cudaMemsetAsync(r->bar + 4, 0, 2 * sizeof(unsigned), s));
+    void* args[] = {(void*)r};
+    const int n_cta = E >= 1024 ? 32 : (E >= 64 ? 8 : 1);
+    SRLX_CHECK_CUDA(cudaLaunchCooperativeKernel((const void*)r2d2_add_kernel, dim3(n_cta), dim3(1024), args, 0, s));
     count_launch();
   }
   r2d2_step_count_kernel<<<1, 1, 0, s>>>(eng.state, E);

@@ -235,6 +235,7 @@ class R2D2Engine:
             env_ep_reward=z(E, torch.float64), env_needs_reset=torch.ones(E, dtype=torch.uint8, device=dev),
             params=z(P, torch.float32), target=z(P, torch.float32),
             roll_xh=ones_last((E, K)), roll_h=ones_last((E, u + 1)), roll_c=z((E, u), torch.float32), roll_reset=z(E, torch.uint8),
+            roll_gates=z((E, 4 * u) if E > 64 else (1,), torch.float32),
         )
         head = self.spec.head
         for l, (out, k, off) in enumerate(head):
@@ -255,7 +256,7 @@ class R2D2Engine:
                 ring_tstep=z(N, torch.int32), ring_h=z((N, u), torch.float32), ring_c=z((N, u), torch.float32),
                 new_c0=z(E, torch.int32), new_n=z(E, torch.int32),
                 xh=ones_last((2, W + 2, B, K)), cbuf=z((2, W + 2, B, u), torch.float32),
-                gates=z((W + 1, B, 4 * u), torch.float32), dgates=z((W + 1, B, 4 * u), torch.float32), dc=z((B, u), torch.float32), bar=z(4, torch.int32),
+                gates=z((W + 1, B, 4 * u), torch.float32), dgates=z((W + 1, B, 4 * u), torch.float32), dc=z((B, u), torch.float32), bar=z(8, torch.int32),
                 gemm_ws=z(32 * max(out * (k + 1) for out, k, _ in head if out <= 32 or k + 1 <= 32) if any(out <= 32 or k + 1 <= 32 for out, k, _ in head) else 1, torch.float32),
                 dh=z(((S + 1) * B, u), torch.float32), q=z((2, B, S + 1, A), torch.float32),
                 sel=z(B, torch.int64), weights=torch.ones(B, dtype=torch.float32, device=dev),
@@ -307,7 +308,7 @@ class R2D2Engine:
         if "gemm_ws" in self.t:
             c.gemm_ws_floats = self.t["gemm_ws"].numel()
         for k in ("params", "target", "adam_m", "adam_v", "grads", "cursor", "ring_obs", "ring_next_obs", "ring_action", "ring_prob",
-                  "ring_reward", "ring_done", "ring_tstep", "ring_h", "ring_c", "roll_xh", "roll_h", "roll_c", "roll_reset", "new_c0", "new_n",
+                  "ring_reward", "ring_done", "ring_tstep", "ring_h", "ring_c", "roll_xh", "roll_h", "roll_c", "roll_gates", "roll_reset", "new_c0", "new_n",
                   "add_idx", "add_pri", "xh", "cbuf", "gates", "dgates", "dc", "gemm_ws", "bar", "dh", "q", "sel", "weights", "b_actions", "b_mu", "b_rewards",
                   "b_dones", "b_target", "b_tdmean", "b_tdkind"):
             if k in self.t:

@@ -200,6 +200,8 @@ CASES = {
     "cartpole_batch32_cp_async": dict(batch_size=32, warmup_size=32, n_envs=8, lstm_units=24, capacity=8 * 64, memory="Proportional"),
     "pendulum_batch64_cp_async": dict(env="Pendulum-v1", batch_size=64, warmup_size=64, n_envs=12, lstm_units=40, hidden_layers=(20,),
                                       dueling_type=None, capacity=12 * 64, enable_rescale=True),
+    # more than 64 env copies: the rollout's LSTM step runs as tiled GEMM + cell update
+    "cartpole_80_envs_gemm_rollout": dict(n_envs=80, lstm_units=24, capacity=80 * 24, warmup_size=64, batch_size=16, memory="Proportional"),
     # one launch per time step instead of the persistent unroll kernels (the path shapes outside their limits take)
     "cartpole_step_launches": dict(_persistent=False),
     "pendulum_per_step_launches_batch40": dict(env="Pendulum-v1", memory="Proportional", batch_size=40, warmup_size=40, n_envs=9, lstm_units=40,
@@ -383,7 +385,7 @@ def test_learning_pendulum_reference_acceptance_gate():
     assert np.mean(rewards) >= -500, rewards
 
 
-@pytest.mark.parametrize("M,N,K", [(7, 5, 3), (40, 33, 70), (200, 150, 37), (1300, 1100, 129), (64, 2048, 517), (2048, 517, 640), (2048, 1700, 70)])
+@pytest.mark.parametrize("M,N,K", [(7, 5, 3), (40, 33, 70), (200, 150, 37), (1300, 1100, 129), (64, 2048, 517), (2048, 517, 640), (2048, 1700, 70), (5184, 3, 1025), (300, 8, 70)])
 @pytest.mark.parametrize("a_t,b_t", [(False, False), (True, False), (False, True), (True, True)])
 def test_strided_sgemm_every_tile_variant(M, N, K, a_t, b_t):
     """srlx_sgemm (the map every R2D2 layer runs on) for row- and column-major operands, odd leading dimensions, ReLU and accumulate,
