@@ -515,6 +515,67 @@ int srlx_dp_enable_peer(int device_a, int device_b);
 int srlx_qnet_forward(const srlx_engine* eng, int use_target, const float* obs_dev, uint32_t n, uint64_t noise_call_id,
                       float* q_out_dev, uintptr_t cuda_stream);
 
+/* ---- Image observation pipeline + conv Q-network -- csrc/imageq.cu -------------------------------------------
+ * srlx_image_process <- ImageProcessor.remap_observation (srl/rl/processors/image_processor.py:104-154) for a BATCH of uint8 frames:
+ *   colour conversion (cv2.cvtColor COLOR_RGB2GRAY, or gray -> 3 equal channels), trimming, cv2.resize (INTER_LINEAR, the 11-bit
+ *   fixed-point form OpenCV uses for uint8) and the normalisation, in ONE pass over the frames (read uint8 once, write once).
+ *   Bit-exact with cv2 4.13 / the reference class (tests/golden/image_processor.npz).
+ * srlx_image_linear_table: the per-axis index / coefficient table of cv2.resize (host; border_reset = 1 for x, 0 for y). */
+typedef struct srlx_image_proc {
+  int32_t src_h, src_w, src_c;        /* source frames uint8 [n][src_h][src_w][src_c], src_c = 1 or 3 */
+  int32_t top, left, trim_h, trim_w;  /* trimming window (0, 0, src_h, src_w: none) */
+  int32_t out_h, out_w, out_c;        /* out_c = 1 or 3; out_c != src_c converts */
+  int32_t resize;                     /* != 0: through the tables; 0: out_h == trim_h and out_w == trim_w */
+  int32_t normalize;                  /* 0: uint8 out; 1: float32 v / max_val ("0to1"); 2: float32 v * 2 / max_val - 1 ("-1to1") */
+  float max_val;
+  const int32_t* x_idx; const int32_t* x_coef; const int32_t* y_idx; const int32_t* y_coef; /* device [out_w], [out_w][2], [out_h], [out_h][2] */
+} srlx_image_proc;
+int srlx_image_linear_table(int32_t dst, int32_t src, int border_reset, int32_t* idx_out_host, int32_t* coef_out_host);
+/* out_dev: uint8 or float32 [n][out_h][out_w][out_c], frame f at out_dev + f * out_frame_stride elements */
+int srlx_image_process(const srlx_image_proc* p, const unsigned char* src_dev, uint32_t n, void* out_dev, uint64_t out_frame_stride,
+                       uintptr_t cuda_stream);
+
+/* Conv Q-network of the image configs: InputImageBlock (reshape + DQNImageBlock: Conv2d layers with replicate padding and ReLU,
+ * srl/rl/torch_/blocks/dqn_image_block.py:10-62, input_image_block.py:42-75) -> Flatten -> MLP hidden block -> Linear(A)
+ * (srl/algorithms/dqn/model_torch.py:17-29), and its trainer (model_torch.py:75-131 with dqn.py:143-173 calc_target_q): double DQN,
+ * rescaling, Huber loss with the IS weight inside, torch Adam, priorities |target - q|, target sync at train_count % interval == 0.
+ * Every map is im2col (replicate padding = index clamp) + the strided GEMM family of csrc/gemm.cuh (3 x TF32 tensor-core tiles at
+ * fp32 accuracy).  Parameter layout (one flat fp32 buffer, bias = LAST COLUMN of every block):
+ *   conv l   W[F_l][k*k*C + 1]   column order (kh, kw, c) when the layer's input is channel-fastest (NHWC: every layer after the
+ *                                first, and a first layer fed NHWC frames), (c, kh, kw) when it is NCHW (a stack of gray frames)
+ *   dense l  W[out_l][k_l + 1]   dense 0 reads the last conv output flattened as (h, w, c)
+ * (netspec.ImageNetSpec converts from / to the reference's state_dict.)  Activations are NHWC. */
+#define SRLX_MAX_CONV 4
+typedef struct srlx_imageq {
+  int32_t in_c, in_h, in_w;
+  int64_t in_sb, in_sc, in_sh, in_sw;   /* element strides of a state batch */
+  int32_t in_u8; float in_max_val;      /* != 0: states are uint8 frames, value = v / in_max_val formed on the fly (the "0to1" normalisation) */
+  int32_t n_conv;
+  int32_t conv_f[SRLX_MAX_CONV], conv_k[SRLX_MAX_CONV], conv_s[SRLX_MAX_CONV], conv_p[SRLX_MAX_CONV];
+  int32_t conv_oh[SRLX_MAX_CONV], conv_ow[SRLX_MAX_CONV], conv_off[SRLX_MAX_CONV];
+  int32_t n_dense;                      /* hidden layers + the output layer */
+  int32_t dense_out[SRLX_MAX_LAYERS], dense_k[SRLX_MAX_LAYERS], dense_off[SRLX_MAX_LAYERS];
+  int32_t n_actions, n_params, batch_cap;
+  int32_t enable_double_dqn, enable_rescale;
+  uint32_t target_update_interval;
+  double discount, lr, adam_beta1, adam_beta2, adam_eps;
+  float* params; float* target; float* adam_m; float* adam_v; float* grads;  /* [n_params] each */
+  uint64_t* counters;                   /* device [4]: train_count, adam_step, sync_count, reserved */
+  float* ws; uint64_t ws_floats;        /* workspace, srlx_imageq_ws_floats(q) floats */
+} srlx_imageq;
+size_t srlx_sizeof_imageq(void);
+uint64_t srlx_imageq_ws_floats(const srlx_imageq* q);
+/* write the constant columns of the workspace (run once after allocation, and after any foreign write to ws) */
+int srlx_imageq_init(const srlx_imageq* q, uintptr_t cuda_stream);
+/* q_out[n][A] = Q(state[n]) with `params` (pred_q) or `target` (pred_target_q); n <= batch_cap */
+int srlx_imageq_forward(const srlx_imageq* q, int use_target, const void* state_dev, uint32_t n, float* q_out_dev, uintptr_t cuda_stream);
+/* one Trainer.train() on a batch in device memory: action int32 [B], reward / undone / weights float32 [B] ->
+ * priorities_out [B] (|target_q - q|), loss_out [1], target_q_out [B] (may be NULL).  phases: 1 = forward + backward (gradient left
+ * in q->grads), 2 = Adam + target sync + counters, 3 = both. */
+int srlx_imageq_train(const srlx_imageq* q, const void* state_dev, const void* n_state_dev, const int32_t* action_dev,
+                      const float* reward_dev, const float* undone_dev, const float* weights_dev, uint32_t batch,
+                      float* priorities_out_dev, float* loss_out_dev, float* target_q_out_dev, int phases, uintptr_t cuda_stream);
+
 #ifdef __cplusplus
 }
 #endif

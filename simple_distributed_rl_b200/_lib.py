@@ -133,6 +133,36 @@ class SrlxR2d2(C.Structure):
     ]
 
 
+SRLX_MAX_CONV = 4
+
+
+class SrlxImageProc(C.Structure):
+    _fields_ = [("src_h", C.c_int32), ("src_w", C.c_int32), ("src_c", C.c_int32),
+                ("top", C.c_int32), ("left", C.c_int32), ("trim_h", C.c_int32), ("trim_w", C.c_int32),
+                ("out_h", C.c_int32), ("out_w", C.c_int32), ("out_c", C.c_int32),
+                ("resize", C.c_int32), ("normalize", C.c_int32), ("max_val", C.c_float),
+                ("x_idx", _P), ("x_coef", _P), ("y_idx", _P), ("y_coef", _P)]
+
+
+class SrlxImageQ(C.Structure):
+    _fields_ = [
+        ("in_c", C.c_int32), ("in_h", C.c_int32), ("in_w", C.c_int32),
+        ("in_sb", C.c_int64), ("in_sc", C.c_int64), ("in_sh", C.c_int64), ("in_sw", C.c_int64),
+        ("in_u8", C.c_int32), ("in_max_val", C.c_float),
+        ("n_conv", C.c_int32),
+        ("conv_f", C.c_int32 * SRLX_MAX_CONV), ("conv_k", C.c_int32 * SRLX_MAX_CONV), ("conv_s", C.c_int32 * SRLX_MAX_CONV),
+        ("conv_p", C.c_int32 * SRLX_MAX_CONV), ("conv_oh", C.c_int32 * SRLX_MAX_CONV), ("conv_ow", C.c_int32 * SRLX_MAX_CONV),
+        ("conv_off", C.c_int32 * SRLX_MAX_CONV),
+        ("n_dense", C.c_int32),
+        ("dense_out", C.c_int32 * SRLX_MAX_LAYERS), ("dense_k", C.c_int32 * SRLX_MAX_LAYERS), ("dense_off", C.c_int32 * SRLX_MAX_LAYERS),
+        ("n_actions", C.c_int32), ("n_params", C.c_int32), ("batch_cap", C.c_int32),
+        ("enable_double_dqn", C.c_int32), ("enable_rescale", C.c_int32), ("target_update_interval", C.c_uint32),
+        ("discount", C.c_double), ("lr", C.c_double), ("adam_beta1", C.c_double), ("adam_beta2", C.c_double), ("adam_eps", C.c_double),
+        ("params", _P), ("target", _P), ("adam_m", _P), ("adam_v", _P), ("grads", _P),
+        ("counters", _P), ("ws", _P), ("ws_floats", C.c_uint64),
+    ]
+
+
 class SrlxSeam(C.Structure):
     _fields_ = [("tree", _P), ("meta", _P), ("ops_idx", _P), ("ops_val", _P), ("out_tree_idx", _P), ("out_weights", _P), ("flag", _P),
                 ("capacity", C.c_uint64), ("alpha", C.c_double), ("epsilon", C.c_double), ("beta_initial", C.c_double),
@@ -201,6 +231,13 @@ SYMBOLS = [
     ("srlx_env_reset_obs", C.c_int, [C.POINTER(SrlxEngine), _i32, _P, _uptr]),
     ("srlx_env_step_actions", C.c_int, [C.POINTER(SrlxEngine), _P, _P, _P, _P, _P, _uptr]),
     ("srlx_sequence_targets", C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _u32, _u32, _u32, _dbl, _dbl, _i32, _i32, _i32, _uptr]),
+    ("srlx_image_linear_table", C.c_int, [_i32, _i32, _i32, _P, _P]),
+    ("srlx_image_process", C.c_int, [C.POINTER(SrlxImageProc), _P, _u32, _P, _u64, _uptr]),
+    ("srlx_sizeof_imageq", _sz, []),
+    ("srlx_imageq_ws_floats", _u64, [C.POINTER(SrlxImageQ)]),
+    ("srlx_imageq_init", C.c_int, [C.POINTER(SrlxImageQ), _uptr]),
+    ("srlx_imageq_forward", C.c_int, [C.POINTER(SrlxImageQ), _i32, _P, _u32, _P, _uptr]),
+    ("srlx_imageq_train", C.c_int, [C.POINTER(SrlxImageQ), _P, _P, _P, _P, _P, _P, _u32, _P, _P, _P, _i32, _uptr]),
     ("srlx_returns_scan", C.c_int, [_P, _P, _P, _P, _P, _P, _P, _u32, _u32, _dbl, _dbl, _i32, _i32, _i32, _dbl, _dbl, _uptr]),
 ]
 
@@ -225,6 +262,8 @@ def load():
     if lib.srlx_sizeof_ppo() != C.sizeof(SrlxPpo) or lib.srlx_sizeof_ppo_state() != C.sizeof(SrlxPpoState):
         raise SrlxError(f"ABI mismatch: C sizes ppo/ppo_state = {lib.srlx_sizeof_ppo()}/{lib.srlx_sizeof_ppo_state()}, "
                         f"ctypes = {C.sizeof(SrlxPpo)}/{C.sizeof(SrlxPpoState)}")
+    if lib.srlx_sizeof_imageq() != C.sizeof(SrlxImageQ):
+        raise SrlxError(f"ABI mismatch: C size imageq = {lib.srlx_sizeof_imageq()}, ctypes = {C.sizeof(SrlxImageQ)}")
     if lib.srlx_sizeof_r2d2() != C.sizeof(SrlxR2d2):
         raise SrlxError(f"ABI mismatch: C size r2d2 = {lib.srlx_sizeof_r2d2()}, ctypes = {C.sizeof(SrlxR2d2)}")
     if lib.srlx_sizeof_engine() != C.sizeof(SrlxEngine) or lib.srlx_sizeof_state() != C.sizeof(SrlxState) or lib.srlx_sizeof_net() != C.sizeof(SrlxNet):

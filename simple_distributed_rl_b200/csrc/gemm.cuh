@@ -368,7 +368,7 @@ __global__ void __launch_bounds__(256) sgemm_narrow_kernel(const GemmP p) {
   }
 }
 
-__global__ void splitk_reduce_kernel(const GemmP p) {
+static __global__ void splitk_reduce_kernel(const GemmP p) {
   if (p.gate.closed()) return;
   const long long n_out = (long long)p.M * p.N;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_out; i += (long long)gridDim.x * blockDim.x) {
@@ -385,10 +385,13 @@ __global__ void splitk_reduce_kernel(const GemmP p) {
 
 static const bool g_gemm_simt = getenv("SRLX_GEMM_SIMT") != nullptr;  // diagnostic: FMA tiles instead of 3 x TF32 tensor-core tiles
 
-static int launch_gemm(const GemmP& p_in, int nz, cudaStream_t s, float* ws = nullptr, size_t ws_floats = 0) {
+// wide_split: split-K whenever the output has fewer 64 x 64 tiles than the GPU has SMs (the convolution weight gradients: a few tiles
+// over a reduction of batch x positions rows)
+static int launch_gemm(const GemmP& p_in, int nz, cudaStream_t s, float* ws = nullptr, size_t ws_floats = 0, bool wide_split = false) {
   GemmP p = p_in;
   if (p.M <= 0 || p.N <= 0) return 0;
-  if (nz == 1 && ws && (p.M <= 32 || p.N <= 32) && p.K >= 1024) {
+  const bool few_tiles = wide_split && (long long)((p.M + 63) / 64) * ((p.N + 63) / 64) < 148;
+  if (nz == 1 && ws && (p.M <= 32 || p.N <= 32 || few_tiles) && p.K >= 1024) {
     int splits = p.K / 256;
     if (splits > 32) splits = 32;
     while (splits > 1 && (size_t)splits * p.M * p.N > ws_floats) --splits;

@@ -1,0 +1,95 @@
+"""CPU: host logic of the image path -- layout <-> reference state_dict, the demo memory's mixing rules, loud failure without CUDA."""
+import numpy as np
+import pytest
+import torch
+
+from simple_distributed_rl_b200 import _lib, image
+
+
+def test_spec_layout_round_trip_every_input_kind():
+    for shape, t in [((28, 36, 4), "IMAGE_MAP"), ((4, 28, 36), "GRAY_HW"), ((28, 36), "GRAY_HW"), ((28, 36, 1), "GRAY_HW1"),
+                     ((3, 28, 36, 1), "GRAY_HW1"), ((20, 24, 3), "RGB")]:
+        sp = image.ImageNetSpec(shape, t, 5, filters=8, hidden=(16, 8))
+        sd = sp.init_state_dict(1)
+        assert list(sd.keys()) == sp.keys()
+        flat = sp.from_state_dict(sd)
+        assert flat.shape == (sp.n_params,) and sp.n_params == sum(v.numel() for v in sd.values())
+        back = sp.to_state_dict(flat)
+        assert all(torch.equal(sd[k], back[k]) for k in sd)
+    # the DQN block's shapes for an Atari stack (dqn_image_block.py:25-27: 84 -> 21 -> 11 -> 11)
+    sp = image.ImageNetSpec((84, 84, 4), "IMAGE_MAP", 6)
+    assert [(g[6], g[7], g[8]) for g in sp.conv_geo] == [(21, 21, 32), (11, 11, 64), (11, 11, 64)] and sp.flat == 64 * 11 * 11
+
+
+class _Mem:
+    def __init__(self):
+        self.items, self.updates = [], []
+
+    def length(self):
+        return len(self.items)
+
+    def add(self, batch, priority=None):
+        self.items.append(batch)
+
+    def sample(self, batch_size, step):
+        return self.items[:batch_size], [0.5] * batch_size, list(range(batch_size))
+
+    def update(self, update_args, priorities):
+        self.updates.append((list(update_args), np.array(priorities)))
+
+    def backup(self):
+        return list(self.items)
+
+    def restore(self, data):
+        self.items = list(data)
+
+
+def test_demo_memory_mixing_rules():
+    """priority_replay_buffer.py:177-246: demo_batch_size = max(1, int(B * ratio)); main batch = B - demo; ONE weight of 1.0 appended;
+    update() trims the priorities to the main batch."""
+    m = image.DemoMixMemory(_Mem(), batch_size=32, demo_ratio=1 / 16, capacity=100, warmup_size=40, seed=0)
+    assert m.demo_batch_size == 2 and m.batch_size == 30
+    m.select_memory = "demo"
+    for i in range(5):
+        m.add(("demo", i))
+    m.select_memory = "main"
+    for i in range(39):
+        m.add(("main", i))
+    assert m.sample() is None and m.is_warmup_needed() and m.length() == 44
+    m.add(("main", 39))
+    batches, weights, args = m.sample()
+    assert len(batches) == 32 and [b[0] for b in batches].count("demo") == 2 and all(b[0] == "main" for b in batches[:30])
+    assert weights.dtype == np.float32 and len(weights) == 31 and weights[-1] == 1.0  # the reference's np.append(weights, 1.0)
+    m.update(args, np.arange(32, dtype=np.float32), 7)
+    assert len(m.memory.updates[-1][1]) == 30 and m.step == 7
+    data = m.call_backup()
+    m2 = image.DemoMixMemory(_Mem(), batch_size=32, demo_ratio=1 / 16, capacity=100, warmup_size=40)
+    m2.call_restore(data)
+    assert m2.length() == m.length() and m2.demo == m.demo
+    # demo ring wraps at capacity
+    m3 = image.DemoMixMemory(_Mem(), batch_size=4, demo_ratio=0.25, capacity=3, warmup_size=3)
+    m3.select_memory = "demo"
+    for i in range(5):
+        m3.add(i)
+    assert m3.demo == [3, 4, 2]
+    with pytest.raises(ValueError):
+        image.DemoMixMemory(_Mem(), batch_size=1, demo_ratio=1.0, capacity=10, warmup_size=5)  # nothing left for the main batch
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU behaviour")
+def test_no_cpu_fallback():
+    with pytest.raises(_lib.SrlxError):
+        image.DeviceImagePipeline((10, 10, 3), "RGB", device="cpu")
+    with pytest.raises(_lib.SrlxError):
+        image.ImageQNet(image.ImageNetSpec((28, 36, 1), "GRAY_HW1", 3, filters=8, hidden=(16,)))
+
+
+def test_linear_table_is_a_host_function_and_matches_the_oracle():
+    from oracle import image as oimg
+
+    lib = _lib.load()
+    for dst, src, border in [(84, 210, 1), (84, 160, 0), (96, 64, 1), (72, 48, 0), (5, 5, 1), (1, 7, 0), (77, 3, 1)]:
+        idx, coef = np.zeros(dst, np.int32), np.zeros((dst, 2), np.int32)
+        _lib.check(lib.srlx_image_linear_table(dst, src, border, idx.ctypes.data, coef.ctypes.data))
+        oi, oc = oimg.linear_table(dst, src, bool(border))
+        assert np.array_equal(idx, oi) and np.array_equal(coef, oc), (dst, src, border)
