@@ -8,6 +8,8 @@
 // family of gemm.cuh; the input gradient of a convolution is the GEMM dOut x W followed by a GATHER col2im (every input pixel sums the
 // window slots that read it, in a fixed order: deterministic, no atomics).  Activations are NHWC, so a conv layer's output is the next
 // layer's im2col source and the last one IS the flattened input of the first dense layer.
+#include <algorithm>
+
 #include "gemm.cuh"
 #include "net.cuh"
 
@@ -54,6 +56,85 @@ __global__ void __launch_bounds__(256) image_process_kernel(const __grid_constan
   }
 }
 
+// Staged version (the usual case: the frame, as gray bytes when the output is gray, fits in shared memory and its size is a multiple of
+// 16 bytes): one CTA per frame.  Phase 1 streams the frame in with 16-byte loads -- 48 bytes = 16 RGB pixels per step, converted to 16
+// gray bytes and stored as one 16-byte word -- so every source byte crosses the memory system exactly once and no lane issues byte
+// loads to global memory; phase 2 forms the outputs from shared memory (4 taps each) and writes them coalesced.  The resize tables sit
+// in shared memory too.
+__device__ __forceinline__ uint32_t gray3(uint32_t r, uint32_t g, uint32_t b) { return (r * 9798u + g * 19235u + b * 3735u + 16384u) >> 15; }
+
+template <typename OutT>
+__global__ void __launch_bounds__(256) image_process_staged_kernel(const __grid_constant__ srlx_image_proc p, const unsigned char* __restrict__ src,
+                                                                   const uint32_t n, OutT* __restrict__ out, const uint64_t out_stride,
+                                                                   const int to_gray) {
+  extern __shared__ __align__(16) unsigned char sm_raw[];
+  int* xi = reinterpret_cast<int*>(sm_raw);
+  int* xc = xi + p.out_w;
+  int* yi = xc + 2 * p.out_w;
+  int* yc = yi + p.out_h;
+  unsigned char* fr = sm_raw + (((size_t)(3 * p.out_w + 3 * p.out_h) * 4 + 15) / 16) * 16;
+  const int tid = threadIdx.x;
+  if (p.resize) {
+    for (int i = tid; i < p.out_w; i += 256) { xi[i] = p.x_idx[i]; xc[2 * i] = p.x_coef[2 * i]; xc[2 * i + 1] = p.x_coef[2 * i + 1]; }
+    for (int i = tid; i < p.out_h; i += 256) { yi[i] = p.y_idx[i]; yc[2 * i] = p.y_coef[2 * i]; yc[2 * i + 1] = p.y_coef[2 * i + 1]; }
+  }
+  const size_t frame_bytes = (size_t)p.src_h * p.src_w * p.src_c;
+  const int sc = to_gray ? 1 : p.src_c;  // channels of the staged frame
+  const int per = p.out_h * p.out_w * p.out_c;
+  for (uint32_t f = blockIdx.x; f < n; f += gridDim.x) {
+    const uint4* g = reinterpret_cast<const uint4*>(src + (size_t)f * frame_bytes);
+    if (to_gray) {
+      const int groups = p.src_h * p.src_w / 16;
+      for (int i = tid; i < groups; i += 256) {
+        uint32_t w[12];
+        const uint4 a = __ldcs(g + 3 * i), b = __ldcs(g + 3 * i + 1), c = __ldcs(g + 3 * i + 2);
+        w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w; w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w; w[8] = c.x; w[9] = c.y; w[10] = c.z; w[11] = c.w;
+        uint32_t o[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const int k = 3 * j;
+          const uint32_t r_ = (w[k >> 2] >> (8 * (k & 3))) & 0xffu, g_ = (w[(k + 1) >> 2] >> (8 * ((k + 1) & 3))) & 0xffu,
+                         b_ = (w[(k + 2) >> 2] >> (8 * ((k + 2) & 3))) & 0xffu;
+          o[j >> 2] |= gray3(r_, g_, b_) << (8 * (j & 3));
+        }
+        reinterpret_cast<uint4*>(fr)[i] = make_uint4(o[0], o[1], o[2], o[3]);
+      }
+    } else {
+      const int words = (int)(frame_bytes / 16);
+      for (int i = tid; i < words; i += 256) reinterpret_cast<uint4*>(fr)[i] = __ldcs(g + i);
+    }
+    __syncthreads();
+    OutT* of = out + (size_t)f * out_stride;
+    for (int i = tid; i < per; i += 256) {
+      int r = i;
+      const int c = r % p.out_c;
+      r /= p.out_c;
+      const int ox = r % p.out_w, oy = r / p.out_w;
+      const int cs = sc == 1 ? 0 : c;
+      auto px = [&](int y, int x) -> int { return fr[((y + p.top) * p.src_w + (x + p.left)) * sc + cs]; };
+      int v;
+      if (p.resize) {
+        const int x0 = xi[ox], x1 = min(x0 + 1, p.trim_w - 1), a0 = xc[2 * ox], a1 = xc[2 * ox + 1];
+        const int yr = yi[oy], y0 = min(max(yr, 0), p.trim_h - 1), y1 = min(max(yr + 1, 0), p.trim_h - 1);
+        const int b0 = yc[2 * oy], b1 = yc[2 * oy + 1];
+        const int r0 = px(y0, x0) * a0 + px(y0, x1) * a1;
+        const int r1 = px(y1, x0) * a0 + px(y1, x1) * a1;
+        v = (((b0 * (r0 >> 4)) >> 16) + ((b1 * (r1 >> 4)) >> 16) + 2) >> 2;
+        v = min(max(v, 0), 255);
+      } else {
+        v = px(oy, ox);
+      }
+      if constexpr (sizeof(OutT) == 1) {
+        of[i] = (OutT)v;
+      } else {
+        const float x = (float)v;
+        __stcs(of + i, p.normalize == 1 ? __fdiv_rn(x, p.max_val) : __fsub_rn(__fdiv_rn(__fmul_rn(x, 2.f), p.max_val), 1.f));
+      }
+    }
+    __syncthreads();
+  }
+}
+
 // ---- im2col / col2im ----------------------------------------------------------------------------------------------------------------
 struct ConvG {
   int C, H, W, k, s, p, OH, OW, K;       // K = C * k * k
@@ -64,28 +145,6 @@ struct ConvG {
 __device__ __forceinline__ void col_split(const ConvG& g, int j, int& c, int& kh, int& kw) {
   if (g.c_fast) { c = j % g.C; j /= g.C; kw = j % g.k; kh = j / g.k; }
   else { kw = j % g.k; j /= g.k; kh = j % g.k; c = j / g.k; }
-}
-
-template <typename InT>
-__global__ void __launch_bounds__(256) im2col_kernel(const ConvG g, const InT* __restrict__ in, const float inv_div, float* __restrict__ col,
-                                                     const long long rows) {
-  const int ld = g.K + 1;
-  const long long total = rows * ld;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const long long row = i / ld;
-    const int j = (int)(i - row * ld);
-    float v = 1.f;  // the bias column
-    if (j < g.K) {
-      int c, kh, kw;
-      col_split(g, j, c, kh, kw);
-      const int ow = (int)(row % g.OW), oh = (int)((row / g.OW) % g.OH);
-      const long long b = row / ((long long)g.OW * g.OH);
-      const int ih = min(max(oh * g.s - g.p + kh, 0), g.H - 1), iw = min(max(ow * g.s - g.p + kw, 0), g.W - 1);  // padding_mode="replicate"
-      const InT x = in[b * g.sb + c * g.sc + ih * g.sh + iw * g.sw];
-      if constexpr (sizeof(InT) == 1) v = __fdiv_rn((float)x, inv_div); else v = x;
-    }
-    col[i] = v;
-  }
 }
 
 // dIn[b][ih][iw][c] = (act > 0) * sum over the window slots (oh, kh, ow, kw) whose clamped source is (ih, iw) of dcol[(b, oh, ow)][(kh, kw, c)]
@@ -114,6 +173,253 @@ __global__ void __launch_bounds__(256) col2im_kernel(const ConvG g, const float*
     }
     din[i] = sum;
   }
+}
+
+// ---- implicit-GEMM tiles ------------------------------------------------------------------------------------------------------------
+// The convolution maps without a materialised im2col matrix: the tile loader GATHERS the operand from the NHWC / NCHW source (replicate
+// padding = clamped index, the bias column = 1), as the A operand of a forward map (rows = output positions) or as the B operand of a
+// weight-gradient map (reduction over output positions).  Same 3 x TF32 mma.sync tiles, register double buffering and epilogue as
+// sgemm_mma_kernel; plus split-K over blockIdx.z (partials to ws[z][M][N], summed in slice order by splitk_reduce_kernel) so that a map
+// with few output tiles still fills the 148 SMs.  Plain strided operands go through the same kernel (gather = 0).
+struct IGemmP {
+  GemmP g;
+  ConvG cv;
+  const void* src;
+  int src_u8;
+  float src_div;
+  int gather;  // 0: none; 1: A = im2col(src) [M = positions][K = cv.K + 1]; 2: B = im2col(src) [K = positions][N = cv.K + 1]
+};
+
+__device__ __forceinline__ float igemm_src(const IGemmP& q, long long off) {
+  if (q.src_u8) return __fdiv_rn((float)__ldg(reinterpret_cast<const unsigned char*>(q.src) + off), q.src_div);
+  return __ldcg(reinterpret_cast<const float*>(q.src) + off);
+}
+
+template <int BM, int BN>
+__global__ void __launch_bounds__(256) igemm_kernel(const IGemmP q) {
+  const GemmP& p = q.g;
+  const ConvG& cv = q.cv;
+  constexpr int BK = 16, NA = BM * BK / 256, NB = BN * BK / 256, WM = BM / 2, WN = BN / 4, MT = WM / 16, NT = WN / 8;
+  constexpr int LDA = BM + 8, LDB = BN + 8;
+  __shared__ __align__(16) float As[2][BK][LDA];
+  __shared__ __align__(16) float Bs[2][BK][LDB];
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wm = (warp >> 2) * WM, wn = (warp & 3) * WN, g = lane >> 2, t = lane & 3;
+  const int kb = p.ksplit > 1 ? blockIdx.z * p.klen : 0, ke = p.ksplit > 1 ? min(p.K, kb + p.klen) : p.K;
+  const bool a_k = q.gather == 1 || p.sa_k == 1, b_n = q.gather == 2 || p.sb_n == 1;
+  // Everything about a tile slot that does not change along k is decoded ONCE (the loop is issue-bound on index arithmetic otherwise):
+  // per A slot its shared-memory offset and either (row base, ih0, iw0) of a gathered row or the element offset of a strided one; per B
+  // slot likewise with (c, kh, kw) of a gathered column.  Along k the offsets advance by additions: 16 columns of the im2col matrix are
+  // walked as (c, kw, kh) counters, 16 positions as (ow, oh, image) counters.  Offsets are 32-bit (the launcher checks the extents).
+  int sa[NA], sb[NB];                 // shared-memory offsets
+  int a0[NA], a1[NA], a2[NA];         // gather A: row base (-1: no row), ih0, iw0   | strided A: element offset (-1: no row), k index, -
+  int b0[NB], b1[NB], b2[NB], b3[NB]; // gather B: c (-1 bias, -2 none), kh, kw, -    | strided B: element offset (-1: no column), k index, -, -
+  int kc = 0, kkw = 0, kkh = 0, kg = 0;     // gather A: this thread's column kg = (kkh, kkw, kc)
+  int rw[NB], rh[NB], rbase[NB], rrow[NB];  // gather B: this slot's position (ow, oh, image base offset, row)
+#pragma unroll
+  for (int i = 0; i < NA; ++i) {
+    const int idx = tid + i * 256;
+    const int kk = a_k ? idx % BK : idx / BM, mm = a_k ? idx / BK : idx % BM;
+    sa[i] = kk * LDA + mm;
+    const long long row = m0 + mm;
+    if (q.gather == 1) {
+      a0[i] = -1; a1[i] = 0; a2[i] = 0;
+      if (row < p.M) {
+        const int ow = (int)(row % cv.OW), oh = (int)((row / cv.OW) % cv.OH);
+        a0[i] = (int)((row / ((long long)cv.OW * cv.OH)) * cv.sb);
+        a1[i] = oh * cv.s - cv.p;
+        a2[i] = ow * cv.s - cv.p;
+      }
+    } else {
+      a0[i] = row < p.M ? (int)(row * p.sa_m + (long long)(kb + kk) * p.sa_k) : -1;
+      a1[i] = kb + kk; a2[i] = 0;
+    }
+  }
+  if (q.gather == 1) {
+    kg = kb + (tid & (BK - 1));
+    if (kg < cv.K) col_split(cv, kg, kc, kkh, kkw);
+  }
+#pragma unroll
+  for (int i = 0; i < NB; ++i) {
+    const int idx = tid + i * 256;
+    const int nn = b_n ? idx % BN : idx / BK, kk = b_n ? idx / BN : idx % BK;
+    sb[i] = kk * LDB + nn;
+    const int j = n0 + nn;
+    b1[i] = 0; b2[i] = 0; b3[i] = 0; rw[i] = 0; rh[i] = 0; rbase[i] = 0; rrow[i] = 0;
+    if (q.gather == 2) {
+      b0[i] = j < cv.K ? 0 : (j == cv.K ? -1 : -2);
+      if (j < cv.K) col_split(cv, j, b0[i], b1[i], b2[i]);
+      const long long row = kb + kk;
+      rrow[i] = (int)row;
+      rw[i] = (int)(row % cv.OW); rh[i] = (int)((row / cv.OW) % cv.OH);
+      rbase[i] = (int)((row / ((long long)cv.OW * cv.OH)) * cv.sb);
+    } else {
+      b0[i] = j < p.N ? (int)((long long)(kb + kk) * p.sb_k + (long long)j * p.sb_n) : -1;
+      b1[i] = kb + kk;
+    }
+  }
+  const int a_step = (int)(BK * p.sa_k), b_step = (int)(BK * p.sb_k), img = (int)cv.sb;
+  const int csc = (int)cv.sc, csh = (int)cv.sh, csw = (int)cv.sw;
+  float ra[NA], rb[NB];
+  auto load = [&]() {  // fetches the NEXT k slice of this thread's slots and advances the counters
+    if (q.gather == 1) {
+      const bool in_k = kg < ke, bias = kg >= cv.K;
+#pragma unroll
+      for (int i = 0; i < NA; ++i) {
+        float v = 0.f;
+        if (a0[i] >= 0 && in_k) {
+          if (bias) v = 1.f;
+          else {
+            const int ih = min(max(a1[i] + kkh, 0), cv.H - 1), iw = min(max(a2[i] + kkw, 0), cv.W - 1);
+            v = igemm_src(q, a0[i] + kc * csc + ih * csh + iw * csw);
+          }
+        }
+        ra[i] = v;
+      }
+      kg += BK;
+      if (cv.c_fast) {
+        kc += BK;
+        while (kc >= cv.C) { kc -= cv.C; if (++kkw == cv.k) { kkw = 0; ++kkh; } }
+      } else {
+        kkw += BK;
+        while (kkw >= cv.k) { kkw -= cv.k; if (++kkh == cv.k) { kkh = 0; ++kc; } }
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < NA; ++i) {
+        ra[i] = (a0[i] >= 0 && a1[i] < ke) ? __ldcg(p.A + a0[i]) : 0.f;
+        a0[i] += a0[i] >= 0 ? a_step : 0;
+        a1[i] += BK;
+      }
+    }
+    if (q.gather == 2) {
+#pragma unroll
+      for (int i = 0; i < NB; ++i) {
+        float v = 0.f;
+        if (rrow[i] < ke && b0[i] != -2) {
+          if (b0[i] == -1) v = 1.f;
+          else {
+            const int ih = min(max(rh[i] * cv.s - cv.p + b1[i], 0), cv.H - 1), iw = min(max(rw[i] * cv.s - cv.p + b2[i], 0), cv.W - 1);
+            v = igemm_src(q, rbase[i] + b0[i] * csc + ih * csh + iw * csw);
+          }
+        }
+        rb[i] = v;
+        rrow[i] += BK;
+        rw[i] += BK;
+        while (rw[i] >= cv.OW) { rw[i] -= cv.OW; if (++rh[i] == cv.OH) { rh[i] = 0; rbase[i] += img; } }
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < NB; ++i) {
+        rb[i] = (b0[i] >= 0 && b1[i] < ke) ? __ldcg(p.B + b0[i]) : 0.f;
+        b0[i] += b0[i] >= 0 ? b_step : 0;
+        b1[i] += BK;
+      }
+    }
+  };
+  auto store = [&](int buf) {
+#pragma unroll
+    for (int i = 0; i < NA; ++i) (&As[buf][0][0])[sa[i]] = ra[i];
+#pragma unroll
+    for (int i = 0; i < NB; ++i) (&Bs[buf][0][0])[sb[i]] = rb[i];
+  };
+  float acc[MT][NT][4];
+#pragma unroll
+  for (int i = 0; i < MT; ++i)
+#pragma unroll
+    for (int j = 0; j < NT; ++j) acc[i][j][0] = acc[i][j][1] = acc[i][j][2] = acc[i][j][3] = 0.f;
+  load();
+  store(0);
+  __syncthreads();
+  int buf = 0;
+  for (int k0 = kb; k0 < ke; k0 += BK) {
+    const bool more = k0 + BK < ke;
+    if (more) load();
+#pragma unroll
+    for (int ks = 0; ks < BK; ks += 8) {
+      uint32_t bh[NT][2], bl[NT][2];
+#pragma unroll
+      for (int j = 0; j < NT; ++j) {
+        split_tf32(Bs[buf][ks + t][wn + j * 8 + g], bh[j][0], bl[j][0]);
+        split_tf32(Bs[buf][ks + t + 4][wn + j * 8 + g], bh[j][1], bl[j][1]);
+      }
+#pragma unroll
+      for (int i = 0; i < MT; ++i) {
+        uint32_t ah[4], al[4];
+        split_tf32(As[buf][ks + t][wm + i * 16 + g], ah[0], al[0]);
+        split_tf32(As[buf][ks + t][wm + i * 16 + g + 8], ah[1], al[1]);
+        split_tf32(As[buf][ks + t + 4][wm + i * 16 + g], ah[2], al[2]);
+        split_tf32(As[buf][ks + t + 4][wm + i * 16 + g + 8], ah[3], al[3]);
+#pragma unroll
+        for (int j = 0; j < NT; ++j) {
+          mma_tf32(acc[i][j], al, bh[j]);
+          mma_tf32(acc[i][j], ah, bl[j]);
+          mma_tf32(acc[i][j], ah, bh[j]);
+        }
+      }
+    }
+    if (more) {
+      store(buf ^ 1);
+      __syncthreads();
+      buf ^= 1;
+    }
+  }
+  float* part = p.ksplit > 1 ? p.ws + (size_t)blockIdx.z * p.M * p.N : nullptr;
+#pragma unroll
+  for (int i = 0; i < MT; ++i)
+#pragma unroll
+    for (int j = 0; j < NT; ++j)
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const int m = m0 + wm + i * 16 + g + (r >> 1) * 8, n = n0 + wn + j * 8 + 2 * t + (r & 1);
+        if (m >= p.M || n >= p.N) continue;
+        float v = acc[i][j][r];
+        if (part) { part[(size_t)m * p.N + n] = v; continue; }
+        float* c = p.C + (long long)m * p.ldc + n;
+        if (p.accumulate) v += *c;
+        if (p.relu) v = fmaxf(v, 0.f);
+        if (p.mask && !(p.mask[(long long)m * p.ldmask + n] > 0.f)) v = 0.f;
+        *c = v;
+      }
+}
+
+static int launch_igemm(IGemmP q, cudaStream_t s, float* ws, size_t ws_floats) {
+  GemmP& p = q.g;
+  if (p.M <= 0 || p.N <= 0) return 0;
+  p.gate = Gate{nullptr, 0};
+  const long long lim = (1LL << 31) - 1;  // 32-bit element offsets inside the kernel
+  SRLX_REQUIRE((q.gather == 1 || (long long)p.M * llabs(p.sa_m) + (long long)p.K * llabs(p.sa_k) < lim) &&
+                   (q.gather == 2 || (long long)p.K * llabs(p.sb_k) + (long long)p.N * llabs(p.sb_n) < lim) &&
+                   (q.gather == 0 || (long long)(q.gather == 1 ? p.M : p.K) / ((long long)q.cv.OH * q.cv.OW) * q.cv.sb < lim),
+               "imageq: an operand of a map exceeds 2^31 elements (batch too large for one launch)");
+  const bool n32 = p.N <= 32, m32 = !n32 && p.M <= 32;
+  const int BM = m32 ? 32 : 64, BN = n32 ? 32 : 64;
+  const long long tiles = (long long)((p.M + BM - 1) / BM) * ((p.N + BN - 1) / BN);
+  if (q.gather == 0 && tiles >= 4 * 148 && p.M >= 128 && p.N >= 128) return launch_gemm(p, 1, s);  // large plain maps: the 128 x 128 tiles
+  int splits = 1;
+  if (tiles < 148 && p.K >= 128 && ws) {
+    splits = (int)((2 * 148 + tiles - 1) / tiles);
+    if (splits > p.K / 64) splits = p.K / 64;
+    if (splits > 64) splits = 64;
+    while (splits > 1 && (size_t)splits * p.M * p.N > ws_floats) --splits;
+  }
+  p.ksplit = 1;
+  if (splits > 1) {
+    p.klen = ((p.K + splits - 1) / splits + 15) / 16 * 16;
+    p.ksplit = (p.K + p.klen - 1) / p.klen;
+    p.ws = ws;
+  }
+  dim3 grid((p.N + BN - 1) / BN, (p.M + BM - 1) / BM, p.ksplit);
+  if (n32) igemm_kernel<64, 32><<<grid, 256, 0, s>>>(q);
+  else if (m32) igemm_kernel<32, 64><<<grid, 256, 0, s>>>(q);
+  else igemm_kernel<64, 64><<<grid, 256, 0, s>>>(q);
+  count_launch();
+  if (p.ksplit > 1) {
+    const long long n_out = (long long)p.M * p.N;
+    splitk_reduce_kernel<<<(unsigned)((n_out + 255) / 256 < 592 ? (n_out + 255) / 256 : 592), 256, 0, s>>>(p);
+    count_launch();
+  }
+  return 0;
 }
 
 // ---- loss, Adam ---------------------------------------------------------------------------------------------------------------------
@@ -203,7 +509,7 @@ __global__ void fill_kernel(float* p, const long long n, const long long stride,
 struct ImageQPlan {
   ConvG g[SRLX_MAX_CONV];
   long long rows[SRLX_MAX_CONV];          // per sample: OH * OW
-  size_t col[SRLX_MAX_CONV], cact[SRLX_MAX_CONV], dcact[SRLX_MAX_CONV], dcol;
+  size_t cact[SRLX_MAX_CONV], dcact[SRLX_MAX_CONV], dcol;
   size_t act[SRLX_MAX_LAYERS], dact[SRLX_MAX_LAYERS];
   size_t ones, qbuf, dq, tq, split;
   size_t split_floats, total;
@@ -229,7 +535,6 @@ static int imageq_plan(const srlx_imageq* q, ImageQPlan& pl) {
     g.c_fast = g.sc == 1;
     pl.rows[l] = (long long)g.OH * g.OW;
     const int F = q->conv_f[l];
-    pl.col[l] = take((size_t)B * pl.rows[l] * (g.K + 1));
     pl.cact[l] = take((size_t)B * pl.rows[l] * F);
     pl.dcact[l] = take((size_t)B * pl.rows[l] * F);
     if (l > 0 && (size_t)B * pl.rows[l] * g.K > dcol_max) dcol_max = (size_t)B * pl.rows[l] * g.K;
@@ -238,6 +543,7 @@ static int imageq_plan(const srlx_imageq* q, ImageQPlan& pl) {
     C = F; H = g.OH; W = g.OW;
   }
   pl.flat = C * H * W;
+  if ((size_t)B * pl.flat > split_max && (size_t)B * pl.flat <= ((size_t)1 << 21)) split_max = (size_t)B * pl.flat;
   pl.dcol = take(dcol_max);
   int k = pl.flat;
   for (int l = 0; l < q->n_dense; ++l) {
@@ -245,7 +551,7 @@ static int imageq_plan(const srlx_imageq* q, ImageQPlan& pl) {
     const int out = q->dense_out[l], last = l == q->n_dense - 1;
     pl.act[l] = take((size_t)B * (out + (last ? 0 : 1)));
     pl.dact[l] = take((size_t)B * out);
-    if ((size_t)out > split_max) split_max = out;
+    if ((size_t)B * out > split_max) split_max = (size_t)B * out;  // forward / input-gradient maps of a small batch over a long reduction
     if (l > 0 && (size_t)out * (k + 1) > split_max) split_max = (size_t)out * (k + 1);
     off_p += out * (k + 1);
     k = out;
@@ -255,7 +561,7 @@ static int imageq_plan(const srlx_imageq* q, ImageQPlan& pl) {
   pl.qbuf = take((size_t)3 * B * q->n_actions);
   pl.dq = take((size_t)B * q->n_actions);
   pl.tq = take((size_t)B + 4);
-  pl.split_floats = 32 * split_max;
+  pl.split_floats = std::min<size_t>(64 * split_max, (size_t)16 << 20);  // launch_igemm takes fewer slices when they do not fit
   pl.split = take(pl.split_floats);
   pl.total = off;
   return 0;
@@ -266,36 +572,35 @@ static unsigned grid_for(long long n) { const long long g = (n + 255) / 256; ret
 // forward of n samples with parameter buffer P; leaves col / cact / act of the pass in the workspace, Q in qout [n][A]
 static int imageq_forward(const srlx_imageq* q, const ImageQPlan& pl, const float* P, const void* state, int n, float* qout, cudaStream_t s) {
   float* ws = q->ws;
-  const Gate open{nullptr, 0};
+  float* sws = ws + pl.split;
   for (int l = 0; l < q->n_conv; ++l) {
     const ConvG& g = pl.g[l];
-    const long long rows = (long long)n * pl.rows[l];
-    if (l == 0 && q->in_u8) im2col_kernel<unsigned char><<<grid_for(rows * (g.K + 1)), 256, 0, s>>>(g, (const unsigned char*)state, q->in_max_val, ws + pl.col[l], rows);
-    else im2col_kernel<float><<<grid_for(rows * (g.K + 1)), 256, 0, s>>>(g, l == 0 ? (const float*)state : ws + pl.cact[l - 1], 1.f, ws + pl.col[l], rows);
-    count_launch();
-    GemmP p{};
-    p.A = ws + pl.col[l]; p.sa_m = g.K + 1; p.sa_k = 1;
+    IGemmP c{};
+    c.cv = g; c.gather = 1;
+    c.src = l == 0 ? state : (const void*)(ws + pl.cact[l - 1]); c.src_u8 = l == 0 && q->in_u8; c.src_div = q->in_max_val;
+    GemmP& p = c.g;
     p.B = P + q->conv_off[l]; p.sb_k = 1; p.sb_n = g.K + 1;
     p.C = ws + pl.cact[l]; p.ldc = q->conv_f[l];
-    p.M = (int)rows; p.N = q->conv_f[l]; p.K = g.K + 1; p.relu = 1; p.gate = open;
-    if (launch_gemm(p, 1, s)) return -1;
+    p.M = (int)((long long)n * pl.rows[l]); p.N = q->conv_f[l]; p.K = g.K + 1; p.relu = 1;
+    if (launch_igemm(c, s, sws, pl.split_floats)) return -1;
   }
   for (int l = 0; l < q->n_dense; ++l) {
     const int k = q->dense_k[l], out = q->dense_out[l], last = l == q->n_dense - 1;
     const float* Wl = P + q->dense_off[l];
-    GemmP p{};
+    IGemmP d{};
+    GemmP& p = d.g;
     p.B = Wl; p.sb_k = 1; p.sb_n = k + 1;
     p.C = last ? qout : ws + pl.act[l]; p.ldc = last ? out : out + 1;
-    p.M = n; p.N = out; p.gate = open;
+    p.M = n; p.N = out;
     if (l == 0) {  // the flattened conv output has no constant column: bias as a second, K = 1 map against the ones vector
       p.A = ws + pl.cact[q->n_conv - 1]; p.sa_m = k; p.sa_k = 1; p.K = k;
-      if (launch_gemm(p, 1, s)) return -1;
-      GemmP b = p;
-      b.A = ws + pl.ones; b.sa_m = 1; b.sa_k = 1; b.B = Wl + k; b.K = 1; b.accumulate = 1; b.relu = !last;
-      if (launch_gemm(b, 1, s)) return -1;
+      if (launch_igemm(d, s, sws, pl.split_floats)) return -1;
+      IGemmP b = d;
+      b.g.A = ws + pl.ones; b.g.sa_m = 1; b.g.sa_k = 1; b.g.B = Wl + k; b.g.K = 1; b.g.accumulate = 1; b.g.relu = !last;
+      if (launch_igemm(b, s, sws, pl.split_floats)) return -1;
     } else {
       p.A = ws + pl.act[l - 1]; p.sa_m = k + 1; p.sa_k = 1; p.K = k + 1; p.relu = !last;
-      if (launch_gemm(p, 1, s)) return -1;
+      if (launch_igemm(d, s, sws, pl.split_floats)) return -1;
     }
   }
   return 0;
@@ -345,7 +650,27 @@ int srlx_image_process(const srlx_image_proc* p, const unsigned char* src, uint3
   if (n == 0) return 0;
   const long long total = (long long)n * p->out_h * p->out_w * p->out_c;
   cudaStream_t s = (cudaStream_t)stream;
-  if (p->normalize == 0) image_process_kernel<unsigned char><<<grid_for(total), 256, 0, s>>>(*p, src, n, (unsigned char*)out, out_stride);
+  // staged path: whole frame (gray bytes when the output is gray) in shared memory, 16-byte loads
+  const int to_gray = p->src_c == 3 && p->out_c == 1;
+  const size_t frame_bytes = (size_t)p->src_h * p->src_w * p->src_c, staged = to_gray ? frame_bytes / 3 : frame_bytes;
+  const size_t smem = (((size_t)(3 * p->out_w + 3 * p->out_h) * 4 + 15) / 16) * 16 + staged;
+  static const bool no_staged = getenv("SRLX_IMAGE_SCALAR") != nullptr;  // diagnostic: the one-thread-per-output kernel for every shape
+  const bool can_stage = !no_staged && frame_bytes % 16 == 0 && (!to_gray || ((size_t)p->src_h * p->src_w) % 16 == 0) && smem <= 200 * 1024 &&
+                         ((uintptr_t)src & 15) == 0;
+  if (can_stage) {
+    int per_sm = 0;
+    if (p->normalize == 0) {
+      SRLX_CHECK_CUDA(cudaFuncSetAttribute(image_process_staged_kernel<unsigned char>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      SRLX_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, image_process_staged_kernel<unsigned char>, 256, smem));
+      const unsigned grid = (unsigned)std::min<long long>(n, 148LL * std::max(per_sm, 1));
+      image_process_staged_kernel<unsigned char><<<grid, 256, smem, s>>>(*p, src, n, (unsigned char*)out, out_stride, to_gray);
+    } else {
+      SRLX_CHECK_CUDA(cudaFuncSetAttribute(image_process_staged_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      SRLX_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, image_process_staged_kernel<float>, 256, smem));
+      const unsigned grid = (unsigned)std::min<long long>(n, 148LL * std::max(per_sm, 1));
+      image_process_staged_kernel<float><<<grid, 256, smem, s>>>(*p, src, n, (float*)out, out_stride, to_gray);
+    }
+  } else if (p->normalize == 0) image_process_kernel<unsigned char><<<grid_for(total), 256, 0, s>>>(*p, src, n, (unsigned char*)out, out_stride);
   else image_process_kernel<float><<<grid_for(total), 256, 0, s>>>(*p, src, n, (float*)out, out_stride);
   count_launch();
   SRLX_CHECK_CUDA(cudaGetLastError());
@@ -391,7 +716,6 @@ int srlx_imageq_train(const srlx_imageq* q, const void* state, const void* n_sta
   cudaStream_t s = (cudaStream_t)stream;
   float* ws = q->ws;
   const int B = (int)batch, A = q->n_actions;
-  const Gate open{nullptr, 0};
   if (phases & 1) {
     SRLX_REQUIRE(state && n_state && action && reward && undone && weights && pri_out && loss_out, "imageq_train: null batch array");
     float* qb = ws + pl.qbuf;
@@ -404,29 +728,32 @@ int srlx_imageq_train(const srlx_imageq* q, const void* state, const void* n_sta
                                          loss_out, tq_out);
     count_launch();
     // dense layers, last to first
+    float* sws = ws + pl.split;
     const float* dout = ws + pl.dq;
     int ld_dout = A;
     for (int l = q->n_dense - 1; l >= 0; --l) {
       const int k = q->dense_k[l], out = q->dense_out[l];
       const float* X = l == 0 ? ws + pl.cact[q->n_conv - 1] : ws + pl.act[l - 1];
       const int ldx = l == 0 ? k : k + 1;
-      GemmP w{};  // dW[out][k (+1)] = dOut^T x X
+      IGemmP wq{};  // dW[out][k (+1)] = dOut^T x X
+      GemmP& w = wq.g;
       w.A = dout; w.sa_m = 1; w.sa_k = ld_dout;
       w.B = X; w.sb_k = ldx; w.sb_n = 1;
       w.C = q->grads + q->dense_off[l]; w.ldc = k + 1;
-      w.M = out; w.N = l == 0 ? k : k + 1; w.K = B; w.gate = open;
-      if (launch_gemm(w, 1, s, ws + pl.split, pl.split_floats, true)) return -1;
+      w.M = out; w.N = l == 0 ? k : k + 1; w.K = B;
+      if (launch_igemm(wq, s, sws, pl.split_floats)) return -1;
       if (l == 0) {
-        GemmP b = w;
-        b.B = ws + pl.ones; b.sb_k = 1; b.sb_n = 1; b.C = q->grads + q->dense_off[l] + k; b.N = 1;
-        if (launch_gemm(b, 1, s, ws + pl.split, pl.split_floats)) return -1;
+        IGemmP bq = wq;
+        bq.g.B = ws + pl.ones; bq.g.sb_k = 1; bq.g.sb_n = 1; bq.g.C = q->grads + q->dense_off[l] + k; bq.g.N = 1;
+        if (launch_igemm(bq, s, sws, pl.split_floats)) return -1;
       }
-      GemmP x{};  // dX[B][k] = (X > 0) * dOut x W[:, :k]
+      IGemmP xq{};  // dX[B][k] = (X > 0) * dOut x W[:, :k]
+      GemmP& x = xq.g;
       x.A = dout; x.sa_m = ld_dout; x.sa_k = 1;
       x.B = q->params + q->dense_off[l]; x.sb_k = k + 1; x.sb_n = 1;
       x.C = l == 0 ? ws + pl.dcact[q->n_conv - 1] : ws + pl.dact[l - 1]; x.ldc = k;
-      x.M = B; x.N = k; x.K = out; x.mask = X; x.ldmask = ldx; x.gate = open;
-      if (launch_gemm(x, 1, s)) return -1;
+      x.M = B; x.N = k; x.K = out; x.mask = X; x.ldmask = ldx;
+      if (launch_igemm(xq, s, sws, pl.split_floats)) return -1;
       dout = x.C;
       ld_dout = k;
     }
@@ -435,19 +762,22 @@ int srlx_imageq_train(const srlx_imageq* q, const void* state, const void* n_sta
       const ConvG& g = pl.g[l];
       const int F = q->conv_f[l];
       const long long rows = (long long)B * pl.rows[l];
-      GemmP w{};  // dW[F][K+1] = dOut^T x col
+      IGemmP wq{};  // dW[F][K+1] = dOut^T x im2col(input of the layer), the im2col matrix gathered by the tile loader
+      wq.cv = g; wq.gather = 2;
+      wq.src = l == 0 ? state : (const void*)(ws + pl.cact[l - 1]); wq.src_u8 = l == 0 && q->in_u8; wq.src_div = q->in_max_val;
+      GemmP& w = wq.g;
       w.A = ws + pl.dcact[l]; w.sa_m = 1; w.sa_k = F;
-      w.B = ws + pl.col[l]; w.sb_k = g.K + 1; w.sb_n = 1;
       w.C = q->grads + q->conv_off[l]; w.ldc = g.K + 1;
-      w.M = F; w.N = g.K + 1; w.K = (int)rows; w.gate = open;
-      if (launch_gemm(w, 1, s, ws + pl.split, pl.split_floats, true)) return -1;
+      w.M = F; w.N = g.K + 1; w.K = (int)rows;
+      if (launch_igemm(wq, s, sws, pl.split_floats)) return -1;
       if (l == 0) break;
-      GemmP x{};  // dcol[rows][K] = dOut x W[:, :K]
+      IGemmP xq{};  // dcol[rows][K] = dOut x W[:, :K]
+      GemmP& x = xq.g;
       x.A = ws + pl.dcact[l]; x.sa_m = F; x.sa_k = 1;
       x.B = q->params + q->conv_off[l]; x.sb_k = g.K + 1; x.sb_n = 1;
       x.C = ws + pl.dcol; x.ldc = g.K;
-      x.M = (int)rows; x.N = g.K; x.K = F; x.gate = open;
-      if (launch_gemm(x, 1, s)) return -1;
+      x.M = (int)rows; x.N = g.K; x.K = F;
+      if (launch_igemm(xq, s, sws, pl.split_floats)) return -1;
       const long long n_in = (long long)B * g.H * g.W * g.C;
       col2im_kernel<<<grid_for(n_in), 256, 0, s>>>(g, ws + pl.dcol, ws + pl.cact[l - 1], ws + pl.dcact[l - 1], n_in);
       count_launch();

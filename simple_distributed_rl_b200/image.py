@@ -89,6 +89,8 @@ class DeviceImagePipeline:
             raise ValueError(f"frames must be a CUDA uint8 tensor [n, {self.src_shape}], got {frames.dtype} {tuple(frames.shape)} on {frames.device}")
         frames = frames.contiguous()
         n = frames.shape[0]
+        if n == 0:
+            return torch.empty((0,) + self.out_shape, dtype=self.out_dtype, device=self.device)
         if out is None:
             out = torch.empty((n,) + self.out_shape, dtype=self.out_dtype, device=self.device)
         elif out.dtype != self.out_dtype or tuple(out.shape) != (n,) + self.out_shape or not out.is_contiguous():
@@ -300,6 +302,8 @@ class ImageQNet:
     def _states(self, x) -> torch.Tensor:
         want = torch.uint8 if self.uint8_states else torch.float32
         if isinstance(x, np.ndarray):
+            if self.uint8_states and x.dtype != np.uint8:
+                raise ValueError(f"this network takes uint8 frames, got {x.dtype}")
             x = torch.from_numpy(np.ascontiguousarray(x, dtype=np.uint8 if self.uint8_states else np.float32)).to(self.device, non_blocking=True)
         if not x.is_cuda or x.dtype != want or tuple(x.shape[1:]) != self.spec.obs_shape:
             raise ValueError(f"states must be a CUDA {want} tensor [n, {self.spec.obs_shape}], got {x.dtype} {tuple(x.shape)} on {x.device}")

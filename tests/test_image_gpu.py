@@ -43,8 +43,10 @@ def test_processor_random_shapes_against_the_oracle_and_strided_output(im):
     from oracle import image as oimg
 
     rng = np.random.default_rng(3)
-    for _ in range(25):
+    for it in range(40):
         H, W, h, w = (int(v) for v in rng.integers(2, 200, size=4))
+        if it % 2:
+            W = 16 * int(rng.integers(1, 13))  # frame size a multiple of 16 bytes: the shared-memory staged kernel; else one thread per output
         src_t = ("RGB", "GRAY_HW")[int(rng.integers(2))]
         img_t = ("RGB", "GRAY_HW", "GRAY_HW1")[int(rng.integers(3))]
         norm = ("", "0to1", "-1to1")[int(rng.integers(3))]
@@ -145,12 +147,17 @@ def test_imageq_lockstep_with_the_oracle_unresynced(im, obs_shape, stype, filter
         np.testing.assert_allclose(tq.cpu().numpy(), otq, rtol=2e-4, atol=2e-5)
         np.testing.assert_allclose(float(loss), oloss, rtol=2e-4, atol=1e-7)
         np.testing.assert_allclose(pri.cpu().numpy(), opri, rtol=2e-3, atol=2e-5)
-    sd, osd = net.state_dict(), ora.state_dict()
-    for k in spec.keys():  # 5 Adam steps of lr = 1e-3 move a weight by at most 5e-3; agree to 2 % of one step
-        np.testing.assert_allclose(sd[k].numpy(), osd[k], rtol=1e-3, atol=2e-5, err_msg=k)
-    tsd = net.state_dict(target=True)
+    # 5 Adam steps of lr = 1e-3 move a weight by at most 5e-3.  Bar: 2 % of ONE step (2e-5) on all but 1e-4 of the entries -- a weight whose
+    # gradient is rounding noise takes +-lr whatever its size, so its sign can differ -- and never more than half a step anywhere.
+    def close(a, b, what):
+        d = np.abs(a - b)
+        bad = d > 2e-5 + 1e-3 * np.abs(b)
+        assert bad.mean() <= 1e-4 and d.max() <= 5e-4, (what, float(bad.mean()), float(d.max()))
+
+    sd, osd, tsd = net.state_dict(), ora.state_dict(), net.state_dict(target=True)
     for k in spec.keys():
-        np.testing.assert_allclose(tsd[k].numpy(), ora.t[k].numpy(), rtol=1e-3, atol=2e-5, err_msg="target " + k)
+        close(sd[k].numpy(), osd[k], k)
+        close(tsd[k].numpy(), ora.t[k].numpy(), "target " + k)
     assert net.train_count == 5 and net.sync_count == ora.sync_count == 2
 
 
@@ -259,4 +266,4 @@ def test_reference_runner_trains_image_dqn_on_device(srl_mod, tmp_path):
     ref_runner.load_parameter(path)
     par = ref_runner.make_parameter()
     assert type(par).__module__.startswith("srl.")
-    np.testing.assert_allclose(par.pred_q(np.zeros((1, 28, 36, 2), np.float32) + 0.25), q_dev, rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(par.pred_q(np.zeros((1, 28, 36, 2), np.float32) + 0.25), q_dev, rtol=1e-4, atol=5e-5)  # torch CPU conv vs device
