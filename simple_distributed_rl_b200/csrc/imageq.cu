@@ -184,25 +184,33 @@ __global__ void __launch_bounds__(256) col2im_kernel(const ConvG g, const float*
 struct IGemmP {
   GemmP g;
   ConvG cv;
-  const void* src;
-  int src_u8;
-  float src_div;
-  int gather;  // 0: none; 1: A = im2col(src) [M = positions][K = cv.K + 1]; 2: B = im2col(src) [K = positions][N = cv.K + 1]
+  const float* src;  // gather source (fp32: uint8 states are converted once per pass, u8_to_f32_kernel)
+  const float* one;  // a 1.0f in global memory: the source of the bias column
+  int gather;        // 0: none; 1: A = im2col(src) [M = positions][K = cv.K + 1]; 2: B = im2col(src) [K = positions][N = cv.K + 1]
 };
 
-__device__ __forceinline__ float igemm_src(const IGemmP& q, long long off) {
-  if (q.src_u8) return __fdiv_rn((float)__ldg(reinterpret_cast<const unsigned char*>(q.src) + off), q.src_div);
-  return __ldcg(reinterpret_cast<const float*>(q.src) + off);
+__device__ __forceinline__ void cp_async4(float* smem_dst, const float* gsrc, int bytes) {  // bytes = 0: zero fill
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc), "r"(bytes));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N)); }
+
+__global__ void u8_to_f32_kernel(const unsigned char* __restrict__ in, const long long n, const float div, float* __restrict__ out) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) out[i] = __fdiv_rn((float)in[i], div);
 }
 
+// The k loop is a STAGES-deep cp.async pipeline: every thread copies its 4-byte tile slots of slice it + STAGES - 1 straight into shared
+// memory (zero fill outside the operand, the bias column from a constant 1) while the tensor cores work on slice it -- no register
+// staging, one __syncthreads per slice, global latency covered by STAGES - 1 slices in flight.
 template <int BM, int BN>
 __global__ void __launch_bounds__(256) igemm_kernel(const IGemmP q) {
   const GemmP& p = q.g;
   const ConvG& cv = q.cv;
-  constexpr int BK = 16, NA = BM * BK / 256, NB = BN * BK / 256, WM = BM / 2, WN = BN / 4, MT = WM / 16, NT = WN / 8;
+  constexpr int BK = 16, STAGES = 4, NA = BM * BK / 256, NB = BN * BK / 256, WM = BM / 2, WN = BN / 4, MT = WM / 16, NT = WN / 8;
   constexpr int LDA = BM + 8, LDB = BN + 8;
-  __shared__ __align__(16) float As[2][BK][LDA];
-  __shared__ __align__(16) float Bs[2][BK][LDB];
+  __shared__ __align__(16) float As[STAGES][BK][LDA];
+  __shared__ __align__(16) float Bs[STAGES][BK][LDB];
   const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int wm = (warp >> 2) * WM, wn = (warp & 3) * WN, g = lane >> 2, t = lane & 3;
   const int kb = p.ksplit > 1 ? blockIdx.z * p.klen : 0, ke = p.ksplit > 1 ? min(p.K, kb + p.klen) : p.K;
@@ -213,7 +221,7 @@ __global__ void __launch_bounds__(256) igemm_kernel(const IGemmP q) {
   // walked as (c, kw, kh) counters, 16 positions as (ow, oh, image) counters.  Offsets are 32-bit (the launcher checks the extents).
   int sa[NA], sb[NB];                 // shared-memory offsets
   int a0[NA], a1[NA], a2[NA];         // gather A: row base (-1: no row), ih0, iw0   | strided A: element offset (-1: no row), k index, -
-  int b0[NB], b1[NB], b2[NB], b3[NB]; // gather B: c (-1 bias, -2 none), kh, kw, -    | strided B: element offset (-1: no column), k index, -, -
+  int b0[NB], b1[NB], b2[NB];         // gather B: c (-1 bias, -2 none), kh, kw      | strided B: element offset (-1: no column), k index, -
   int kc = 0, kkw = 0, kkh = 0, kg = 0;     // gather A: this thread's column kg = (kkh, kkw, kc)
   int rw[NB], rh[NB], rbase[NB], rrow[NB];  // gather B: this slot's position (ow, oh, image base offset, row)
 #pragma unroll
@@ -245,7 +253,7 @@ __global__ void __launch_bounds__(256) igemm_kernel(const IGemmP q) {
     const int nn = b_n ? idx % BN : idx / BK, kk = b_n ? idx / BN : idx % BK;
     sb[i] = kk * LDB + nn;
     const int j = n0 + nn;
-    b1[i] = 0; b2[i] = 0; b3[i] = 0; rw[i] = 0; rh[i] = 0; rbase[i] = 0; rrow[i] = 0;
+    b1[i] = 0; b2[i] = 0; rw[i] = 0; rh[i] = 0; rbase[i] = 0; rrow[i] = 0;
     if (q.gather == 2) {
       b0[i] = j < cv.K ? 0 : (j == cv.K ? -1 : -2);
       if (j < cv.K) col_split(cv, j, b0[i], b1[i], b2[i]);
@@ -260,21 +268,23 @@ __global__ void __launch_bounds__(256) igemm_kernel(const IGemmP q) {
   }
   const int a_step = (int)(BK * p.sa_k), b_step = (int)(BK * p.sb_k), img = (int)cv.sb;
   const int csc = (int)cv.sc, csh = (int)cv.sh, csw = (int)cv.sw;
-  float ra[NA], rb[NB];
-  auto load = [&]() {  // fetches the NEXT k slice of this thread's slots and advances the counters
+  auto issue = [&](int buf) {  // copies the NEXT k slice of this thread's slots into stage `buf` and advances the counters
+    float* as = &As[buf][0][0];
+    float* bs = &Bs[buf][0][0];
     if (q.gather == 1) {
       const bool in_k = kg < ke, bias = kg >= cv.K;
 #pragma unroll
       for (int i = 0; i < NA; ++i) {
-        float v = 0.f;
+        const float* src = q.one;
+        int bytes = 0;
         if (a0[i] >= 0 && in_k) {
-          if (bias) v = 1.f;
-          else {
+          bytes = 4;
+          if (!bias) {
             const int ih = min(max(a1[i] + kkh, 0), cv.H - 1), iw = min(max(a2[i] + kkw, 0), cv.W - 1);
-            v = igemm_src(q, a0[i] + kc * csc + ih * csh + iw * csw);
+            src = q.src + (a0[i] + kc * csc + ih * csh + iw * csw);
           }
         }
-        ra[i] = v;
+        cp_async4(as + sa[i], src, bytes);
       }
       kg += BK;
       if (cv.c_fast) {
@@ -287,7 +297,8 @@ __global__ void __launch_bounds__(256) igemm_kernel(const IGemmP q) {
     } else {
 #pragma unroll
       for (int i = 0; i < NA; ++i) {
-        ra[i] = (a0[i] >= 0 && a1[i] < ke) ? __ldcg(p.A + a0[i]) : 0.f;
+        const bool ok = a0[i] >= 0 && a1[i] < ke;
+        cp_async4(as + sa[i], ok ? p.A + a0[i] : p.A, ok ? 4 : 0);
         a0[i] += a0[i] >= 0 ? a_step : 0;
         a1[i] += BK;
       }
@@ -295,15 +306,16 @@ __global__ void __launch_bounds__(256) igemm_kernel(const IGemmP q) {
     if (q.gather == 2) {
 #pragma unroll
       for (int i = 0; i < NB; ++i) {
-        float v = 0.f;
+        const float* src = q.one;
+        int bytes = 0;
         if (rrow[i] < ke && b0[i] != -2) {
-          if (b0[i] == -1) v = 1.f;
-          else {
+          bytes = 4;
+          if (b0[i] != -1) {
             const int ih = min(max(rh[i] * cv.s - cv.p + b1[i], 0), cv.H - 1), iw = min(max(rw[i] * cv.s - cv.p + b2[i], 0), cv.W - 1);
-            v = igemm_src(q, rbase[i] + b0[i] * csc + ih * csh + iw * csw);
+            src = q.src + (rbase[i] + b0[i] * csc + ih * csh + iw * csw);
           }
         }
-        rb[i] = v;
+        cp_async4(bs + sb[i], src, bytes);
         rrow[i] += BK;
         rw[i] += BK;
         while (rw[i] >= cv.OW) { rw[i] -= cv.OW; if (++rh[i] == cv.OH) { rh[i] = 0; rbase[i] += img; } }
@@ -311,30 +323,30 @@ __global__ void __launch_bounds__(256) igemm_kernel(const IGemmP q) {
     } else {
 #pragma unroll
       for (int i = 0; i < NB; ++i) {
-        rb[i] = (b0[i] >= 0 && b1[i] < ke) ? __ldcg(p.B + b0[i]) : 0.f;
+        const bool ok = b0[i] >= 0 && b1[i] < ke;
+        cp_async4(bs + sb[i], ok ? p.B + b0[i] : p.B, ok ? 4 : 0);
         b0[i] += b0[i] >= 0 ? b_step : 0;
         b1[i] += BK;
       }
     }
-  };
-  auto store = [&](int buf) {
-#pragma unroll
-    for (int i = 0; i < NA; ++i) (&As[buf][0][0])[sa[i]] = ra[i];
-#pragma unroll
-    for (int i = 0; i < NB; ++i) (&Bs[buf][0][0])[sb[i]] = rb[i];
   };
   float acc[MT][NT][4];
 #pragma unroll
   for (int i = 0; i < MT; ++i)
 #pragma unroll
     for (int j = 0; j < NT; ++j) acc[i][j][0] = acc[i][j][1] = acc[i][j][2] = acc[i][j][3] = 0.f;
-  load();
-  store(0);
-  __syncthreads();
-  int buf = 0;
-  for (int k0 = kb; k0 < ke; k0 += BK) {
-    const bool more = k0 + BK < ke;
-    if (more) load();
+  const int nk = (ke - kb + BK - 1) / BK;
+#pragma unroll
+  for (int st = 0; st < STAGES - 1; ++st) {
+    if (st < nk) issue(st);
+    cp_async_commit();
+  }
+  for (int it = 0; it < nk; ++it) {
+    cp_async_wait<STAGES - 2>();  // slice `it` has landed (for this thread; the barrier makes it so for all)
+    __syncthreads();              // ... and everybody is done with slice it - 1, whose stage the next copy overwrites
+    if (it + STAGES - 1 < nk) issue((it + STAGES - 1) % STAGES);
+    cp_async_commit();
+    const int buf = it % STAGES;
 #pragma unroll
     for (int ks = 0; ks < BK; ks += 8) {
       uint32_t bh[NT][2], bl[NT][2];
@@ -357,11 +369,6 @@ __global__ void __launch_bounds__(256) igemm_kernel(const IGemmP q) {
           mma_tf32(acc[i][j], ah, bh[j]);
         }
       }
-    }
-    if (more) {
-      store(buf ^ 1);
-      __syncthreads();
-      buf ^= 1;
     }
   }
   float* part = p.ksplit > 1 ? p.ws + (size_t)blockIdx.z * p.M * p.N : nullptr;
@@ -511,7 +518,7 @@ struct ImageQPlan {
   long long rows[SRLX_MAX_CONV];          // per sample: OH * OW
   size_t cact[SRLX_MAX_CONV], dcact[SRLX_MAX_CONV], dcol;
   size_t act[SRLX_MAX_LAYERS], dact[SRLX_MAX_LAYERS];
-  size_t ones, qbuf, dq, tq, split;
+  size_t ones, qbuf, dq, tq, split, in_f32;
   size_t split_floats, total;
   int flat;                               // inputs of dense 0
 };
@@ -563,6 +570,7 @@ static int imageq_plan(const srlx_imageq* q, ImageQPlan& pl) {
   pl.tq = take((size_t)B + 4);
   pl.split_floats = std::min<size_t>(64 * split_max, (size_t)16 << 20);  // launch_igemm takes fewer slices when they do not fit
   pl.split = take(pl.split_floats);
+  pl.in_f32 = take(q->in_u8 ? (size_t)B * q->in_sb : 0);
   pl.total = off;
   return 0;
 }
@@ -573,11 +581,18 @@ static unsigned grid_for(long long n) { const long long g = (n + 255) / 256; ret
 static int imageq_forward(const srlx_imageq* q, const ImageQPlan& pl, const float* P, const void* state, int n, float* qout, cudaStream_t s) {
   float* ws = q->ws;
   float* sws = ws + pl.split;
+  const float* in = (const float*)state;
+  if (q->in_u8) {  // uint8 frames -> "0to1" floats once per pass (the tile loaders copy 4-byte words straight into shared memory)
+    const long long n_in = (long long)n * q->in_sb;
+    u8_to_f32_kernel<<<grid_for(n_in), 256, 0, s>>>((const unsigned char*)state, n_in, q->in_max_val, ws + pl.in_f32);
+    count_launch();
+    in = ws + pl.in_f32;
+  }
   for (int l = 0; l < q->n_conv; ++l) {
     const ConvG& g = pl.g[l];
     IGemmP c{};
-    c.cv = g; c.gather = 1;
-    c.src = l == 0 ? state : (const void*)(ws + pl.cact[l - 1]); c.src_u8 = l == 0 && q->in_u8; c.src_div = q->in_max_val;
+    c.cv = g; c.gather = 1; c.one = ws + pl.ones;
+    c.src = l == 0 ? in : ws + pl.cact[l - 1];
     GemmP& p = c.g;
     p.B = P + q->conv_off[l]; p.sb_k = 1; p.sb_n = g.K + 1;
     p.C = ws + pl.cact[l]; p.ldc = q->conv_f[l];
@@ -764,7 +779,7 @@ int srlx_imageq_train(const srlx_imageq* q, const void* state, const void* n_sta
       const long long rows = (long long)B * pl.rows[l];
       IGemmP wq{};  // dW[F][K+1] = dOut^T x im2col(input of the layer), the im2col matrix gathered by the tile loader
       wq.cv = g; wq.gather = 2;
-      wq.src = l == 0 ? state : (const void*)(ws + pl.cact[l - 1]); wq.src_u8 = l == 0 && q->in_u8; wq.src_div = q->in_max_val;
+      wq.src = l == 0 ? (q->in_u8 ? ws + pl.in_f32 : (const float*)state) : ws + pl.cact[l - 1]; wq.one = ws + pl.ones;
       GemmP& w = wq.g;
       w.A = ws + pl.dcact[l]; w.sa_m = 1; w.sa_k = F;
       w.C = q->grads + q->conv_off[l]; w.ldc = g.K + 1;
