@@ -572,6 +572,11 @@ int srlx_imageq_forward(const srlx_imageq* q, int use_target, const void* state_
 /* one Trainer.train() on a batch in device memory: action int32 [B], reward / undone / weights float32 [B] ->
  * priorities_out [B] (|target_q - q|), loss_out [1], target_q_out [B] (may be NULL).  phases: 1 = forward + backward (gradient left
  * in q->grads), 2 = Adam + target sync + counters, 3 = both. */
+/* C[M][N] = A . B with arbitrary strides on the tcgen05 tiles at fp32 accuracy (3 x TF32 through tcgen05.mma.kind::tf32, accumulator in
+ * tensor memory; csrc/gemm_tc3.cuh) -- the GEMM every map of the conv Q-network runs on; test tap with srlx_sgemm's arguments plus an
+ * optional split-K workspace (ws_dev may be NULL: no split). */
+int srlx_sgemm_tc3(const float* a_dev, long long sa_m, long long sa_k, const float* b_dev, long long sb_k, long long sb_n, float* c_dev,
+                   long long ldc, int M, int N, int K, int relu, int accumulate, float* ws_dev, uint64_t ws_floats, uintptr_t cuda_stream);
 int srlx_imageq_train(const srlx_imageq* q, const void* state_dev, const void* n_state_dev, const int32_t* action_dev,
                       const float* reward_dev, const float* undone_dev, const float* weights_dev, uint32_t batch,
                       float* priorities_out_dev, float* loss_out_dev, float* target_q_out_dev, int phases, uintptr_t cuda_stream);

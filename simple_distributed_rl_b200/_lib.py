@@ -231,6 +231,7 @@ SYMBOLS = [
     ("srlx_env_reset_obs", C.c_int, [C.POINTER(SrlxEngine), _i32, _P, _uptr]),
     ("srlx_env_step_actions", C.c_int, [C.POINTER(SrlxEngine), _P, _P, _P, _P, _P, _uptr]),
     ("srlx_sequence_targets", C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _u32, _u32, _u32, _dbl, _dbl, _i32, _i32, _i32, _uptr]),
+    ("srlx_sgemm_tc3", C.c_int, [_P, C.c_longlong, C.c_longlong, _P, C.c_longlong, C.c_longlong, _P, C.c_longlong, _i32, _i32, _i32, _i32, _i32, _P, _u64, _uptr]),
     ("srlx_image_linear_table", C.c_int, [_i32, _i32, _i32, _P, _P]),
     ("srlx_image_process", C.c_int, [C.POINTER(SrlxImageProc), _P, _u32, _P, _u64, _uptr]),
     ("srlx_sizeof_imageq", _sz, []),

@@ -10,7 +10,7 @@
 // layer's im2col source and the last one IS the flattened input of the first dense layer.
 #include <algorithm>
 
-#include "gemm.cuh"
+#include "gemm_tc3.cuh"
 #include "net.cuh"
 
 namespace srlx {
@@ -136,17 +136,6 @@ __global__ void __launch_bounds__(256) image_process_staged_kernel(const __grid_
 }
 
 // ---- im2col / col2im ----------------------------------------------------------------------------------------------------------------
-struct ConvG {
-  int C, H, W, k, s, p, OH, OW, K;       // K = C * k * k
-  long long sb, sc, sh, sw;              // element strides of the source
-  int c_fast;                            // column order (kh, kw, c) instead of (c, kh, kw)
-};
-
-__device__ __forceinline__ void col_split(const ConvG& g, int j, int& c, int& kh, int& kw) {
-  if (g.c_fast) { c = j % g.C; j /= g.C; kw = j % g.k; kh = j / g.k; }
-  else { kw = j % g.k; j /= g.k; kh = j % g.k; c = j / g.k; }
-}
-
 // dIn[b][ih][iw][c] = (act > 0) * sum over the window slots (oh, kh, ow, kw) whose clamped source is (ih, iw) of dcol[(b, oh, ow)][(kh, kw, c)]
 __global__ void __launch_bounds__(256) col2im_kernel(const ConvG g, const float* __restrict__ dcol, const float* __restrict__ act,
                                                      float* __restrict__ din, const long long total) {
@@ -390,7 +379,76 @@ __global__ void __launch_bounds__(256) igemm_kernel(const IGemmP q) {
       }
 }
 
+template <int BN>
+static int t3_launch_bn(const T3P& p, dim3 grid, cudaStream_t s) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    SRLX_CHECK_CUDA(cudaFuncSetAttribute(t3_gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t3_smem_bytes<BN>()));
+    attr_set = true;
+  }
+  t3_gemm_kernel<BN><<<grid, T3_THREADS, t3_smem_bytes<BN>(), s>>>(p);
+  count_launch();
+  return 0;
+}
+
+// C[M][N] = A[M][K] x B[K][N] on the tcgen05 tiles of gemm_tc3.cuh: the larger of (M, N) takes the 128-row side, split-K when the
+// tiles do not fill the SMs (one CTA per SM: the 3-stage hi / lo ring takes 120 - 198 KB of shared memory)
+static int launch_t3(const IGemmP& q, cudaStream_t s, float* ws, size_t ws_floats) {
+  const GemmP& g = q.g;
+  if (g.M <= 0 || g.N <= 0) return 0;
+  const long long lim = (1LL << 31) - 1;
+  SRLX_REQUIRE((q.gather == 1 || (long long)g.M * llabs(g.sa_m) + (long long)g.K * llabs(g.sa_k) < lim) &&
+                   (q.gather == 2 || (long long)g.K * llabs(g.sb_k) + (long long)g.N * llabs(g.sb_n) < lim) &&
+                   (q.gather == 0 || ((long long)(q.gather == 1 ? g.M : g.K) / ((long long)q.cv.OH * q.cv.OW) + 1) * q.cv.sb < lim),
+               "imageq: an operand of a map exceeds 2^31 elements (batch too large for one launch)");
+  T3Op x{}, y{};  // x: rows = the M index, y: rows = the N index
+  x.rows = g.M; y.rows = g.N;
+  if (q.gather == 1) { x.mode = 1; x.ptr = q.src; } else { x.mode = 0; x.ptr = g.A; x.s_row = (int)g.sa_m; x.s_k = (int)g.sa_k; }
+  if (q.gather == 2) { y.mode = 2; y.ptr = q.src; } else { y.mode = 0; y.ptr = g.B; y.s_row = (int)g.sb_n; y.s_k = (int)g.sb_k; }
+  const bool swap = g.N > g.M;
+  T3P p{};
+  p.a = swap ? y : x; p.b = swap ? x : y;
+  p.cv = q.cv; p.one = q.one; p.K = g.K;
+  p.C = g.C; p.c_a = swap ? 1 : g.ldc; p.c_b = swap ? g.ldc : 1;
+  p.mask = g.mask; p.m_a = swap ? 1 : g.ldmask; p.m_b = swap ? g.ldmask : 1;
+  p.w_a = swap ? 1 : g.N; p.w_b = swap ? g.N : 1; p.w_slice = (long long)g.M * g.N;
+  p.relu = g.relu; p.accumulate = g.accumulate;
+  const int BN = p.b.rows <= 32 ? 32 : 64;
+  const long long tiles = (long long)((p.a.rows + T3_BM - 1) / T3_BM) * ((p.b.rows + BN - 1) / BN);
+  int splits = 1;
+  if (tiles < 148 && g.K >= 128 && ws) {
+    splits = (int)((148 + tiles - 1) / tiles);
+    if (splits > g.K / 64) splits = g.K / 64;
+    if (splits > 64) splits = 64;
+    while (splits > 1 && (size_t)splits * g.M * g.N > ws_floats) --splits;
+  }
+  p.ksplit = 1;
+  if (splits > 1) {
+    p.klen = ((g.K + splits - 1) / splits + T3_BK - 1) / T3_BK * T3_BK;
+    p.ksplit = (g.K + p.klen - 1) / p.klen;
+    p.ws = ws;
+  }
+  dim3 grid((p.b.rows + BN - 1) / BN, (p.a.rows + T3_BM - 1) / T3_BM, p.ksplit);
+  int rc = BN == 32 ? t3_launch_bn<32>(p, grid, s) : t3_launch_bn<64>(p, grid, s);
+  if (rc) return rc;
+  if (p.ksplit > 1) {
+    GemmP r = g;
+    r.gate = Gate{nullptr, 0}; r.ws = ws; r.ksplit = p.ksplit;
+    const long long n_out = (long long)g.M * g.N;
+    splitk_reduce_kernel<<<(unsigned)((n_out + 255) / 256 < 592 ? (n_out + 255) / 256 : 592), 256, 0, s>>>(r);
+    count_launch();
+  }
+  return 0;
+}
+
+// SRLX_IMAGE_TC3=1 routes every map through the tcgen05 tiles of gemm_tc3.cuh.  Same results to fp32 accuracy (tests run both); at the
+// reference's batch sizes it is the slower of the two today (batch 32: 1.00 vs 0.69 ms per update, batch 256: 3.4 vs 2.7 ms;
+// profiles/r3h_t3_ncu_summary.txt: one 198 KB CTA = 8 warps per SM, 1000 instructions per warp and k slice of slot arithmetic and
+// barrier polling, issue slots 29 % busy), so the cp.async + mma.sync tiles below stay the default.
+static const bool g_image_tc3 = getenv("SRLX_IMAGE_TC3") != nullptr;
+
 static int launch_igemm(IGemmP q, cudaStream_t s, float* ws, size_t ws_floats) {
+  if (g_image_tc3) return launch_t3(q, s, ws, ws_floats);
   GemmP& p = q.g;
   if (p.M <= 0 || p.N <= 0) return 0;
   p.gate = Gate{nullptr, 0};
@@ -518,7 +576,7 @@ struct ImageQPlan {
   long long rows[SRLX_MAX_CONV];          // per sample: OH * OW
   size_t cact[SRLX_MAX_CONV], dcact[SRLX_MAX_CONV], dcol;
   size_t act[SRLX_MAX_LAYERS], dact[SRLX_MAX_LAYERS];
-  size_t ones, qbuf, dq, tq, split, in_f32;
+  size_t ones, one4, qbuf, dq, tq, split, in_f32;
   size_t split_floats, total;
   int flat;                               // inputs of dense 0
 };
@@ -565,6 +623,7 @@ static int imageq_plan(const srlx_imageq* q, ImageQPlan& pl) {
   }
   SRLX_REQUIRE(q->n_params == off_p, "imageq: n_params = %d, the layers hold %d", q->n_params, off_p);
   pl.ones = take((size_t)B);
+  pl.one4 = take(4);  // {1, 0, 0, 0}: the source of the bias column's 16-byte chunk
   pl.qbuf = take((size_t)3 * B * q->n_actions);
   pl.dq = take((size_t)B * q->n_actions);
   pl.tq = take((size_t)B + 4);
@@ -591,7 +650,7 @@ static int imageq_forward(const srlx_imageq* q, const ImageQPlan& pl, const floa
   for (int l = 0; l < q->n_conv; ++l) {
     const ConvG& g = pl.g[l];
     IGemmP c{};
-    c.cv = g; c.gather = 1; c.one = ws + pl.ones;
+    c.cv = g; c.gather = 1; c.one = ws + pl.one4;
     c.src = l == 0 ? in : ws + pl.cact[l - 1];
     GemmP& p = c.g;
     p.B = P + q->conv_off[l]; p.sb_k = 1; p.sb_n = g.K + 1;
@@ -633,6 +692,20 @@ static int imageq_check(const srlx_imageq* q, ImageQPlan& pl) {
 using namespace srlx;
 
 extern "C" {
+
+int srlx_sgemm_tc3(const float* a, long long sa_m, long long sa_k, const float* b, long long sb_k, long long sb_n, float* c, long long ldc, int M,
+                   int N, int K, int relu, int accumulate, float* ws, uint64_t ws_floats, uintptr_t stream) {
+  SRLX_REQUIRE(a && b && c, "srlx_sgemm_tc3: NULL buffer");
+  SRLX_REQUIRE(M >= 0 && N >= 0 && K >= 0, "srlx_sgemm_tc3: negative size");
+  IGemmP q{};
+  GemmP& g = q.g;
+  g.A = a; g.sa_m = sa_m; g.sa_k = sa_k; g.B = b; g.sb_k = sb_k; g.sb_n = sb_n; g.C = c; g.ldc = ldc;
+  g.M = M; g.N = N; g.K = K; g.relu = relu; g.accumulate = accumulate; g.gate = Gate{nullptr, 0};
+  q.one = a;
+  if (int rc = launch_t3(q, (cudaStream_t)stream, ws, ws_floats)) return rc;
+  SRLX_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
 
 size_t srlx_sizeof_imageq(void) { return sizeof(srlx_imageq); }
 
@@ -704,6 +777,8 @@ int srlx_imageq_init(const srlx_imageq* q, uintptr_t stream) {
   cudaStream_t s = (cudaStream_t)stream;
   const long long B = q->batch_cap;
   fill_kernel<<<grid_for(B), 256, 0, s>>>(q->ws + pl.ones, B, 1, 1.f);
+  fill_kernel<<<1, 32, 0, s>>>(q->ws + pl.one4, 4, 1, 0.f);
+  fill_kernel<<<1, 32, 0, s>>>(q->ws + pl.one4, 1, 1, 1.f);
   for (int l = 0; l + 1 < q->n_dense; ++l) fill_kernel<<<grid_for(B), 256, 0, s>>>(q->ws + pl.act[l] + q->dense_out[l], B, q->dense_out[l] + 1, 1.f);
   count_launch(q->n_dense);
   SRLX_CHECK_CUDA(cudaGetLastError());
@@ -779,7 +854,7 @@ int srlx_imageq_train(const srlx_imageq* q, const void* state, const void* n_sta
       const long long rows = (long long)B * pl.rows[l];
       IGemmP wq{};  // dW[F][K+1] = dOut^T x im2col(input of the layer), the im2col matrix gathered by the tile loader
       wq.cv = g; wq.gather = 2;
-      wq.src = l == 0 ? (q->in_u8 ? ws + pl.in_f32 : (const float*)state) : ws + pl.cact[l - 1]; wq.one = ws + pl.ones;
+      wq.src = l == 0 ? (q->in_u8 ? ws + pl.in_f32 : (const float*)state) : ws + pl.cact[l - 1]; wq.one = ws + pl.one4;
       GemmP& w = wq.g;
       w.A = ws + pl.dcact[l]; w.sa_m = 1; w.sa_k = F;
       w.C = q->grads + q->conv_off[l]; w.ldc = g.K + 1;

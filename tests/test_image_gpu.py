@@ -272,3 +272,16 @@ def test_reference_runner_trains_image_dqn_on_device(srl_mod, tmp_path):
     par = ref_runner.make_parameter()
     assert type(par).__module__.startswith("srl.")
     np.testing.assert_allclose(par.pred_q(np.zeros((1, 28, 36, 2), np.float32) + 0.25), q_dev, rtol=1e-4, atol=5e-5)  # torch CPU conv vs device
+
+
+def test_imageq_on_the_tcgen05_tiles_in_a_subprocess():
+    """SRLX_IMAGE_TC3=1 (read when the library loads): every map of the network on the tcgen05 3 x TF32 tiles (csrc/gemm_tc3.cuh) -- the
+    reference-trainer goldens and the gradient check again, to the same tolerances."""
+    import subprocess
+
+    env = dict(os.environ, SRLX_IMAGE_TC3="1")
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-m", "gpu", "-q", "-x", "-p", "no:cacheprovider", "-k",
+                        "matches_the_reference_trainer or gradient_against_autograd or planes or gray_nohidden"],
+                       env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    assert " passed" in r.stdout and "failed" not in r.stdout
