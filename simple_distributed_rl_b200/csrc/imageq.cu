@@ -80,7 +80,13 @@ __global__ void __launch_bounds__(256) image_process_staged_kernel(const __grid_
   }
   const size_t frame_bytes = (size_t)p.src_h * p.src_w * p.src_c;
   const int sc = to_gray ? 1 : p.src_c;  // channels of the staged frame
-  const int per = p.out_h * p.out_w * p.out_c;
+  const int n_pix = p.out_h * p.out_w, dx = 256 % p.out_w, dy = 256 / p.out_w;
+  __shared__ float lut[256];  // image_processor.py:141-146 for every byte value, float32 arithmetic
+  {
+    const float x = (float)tid;
+    lut[tid] = p.normalize == 1 ? __fdiv_rn(x, p.max_val) : __fsub_rn(__fdiv_rn(__fmul_rn(x, 2.f), p.max_val), 1.f);
+  }
+  __syncthreads();
   for (uint32_t f = blockIdx.x; f < n; f += gridDim.x) {
     const uint4* g = reinterpret_cast<const uint4*>(src + (size_t)f * frame_bytes);
     if (to_gray) {
@@ -105,31 +111,33 @@ __global__ void __launch_bounds__(256) image_process_staged_kernel(const __grid_
     }
     __syncthreads();
     OutT* of = out + (size_t)f * out_stride;
-    for (int i = tid; i < per; i += 256) {
-      int r = i;
-      const int c = r % p.out_c;
-      r /= p.out_c;
-      const int ox = r % p.out_w, oy = r / p.out_w;
-      const int cs = sc == 1 ? 0 : c;
-      auto px = [&](int y, int x) -> int { return fr[((y + p.top) * p.src_w + (x + p.left)) * sc + cs]; };
-      int v;
+    // thread per output PIXEL, (ox, oy) carried as counters (no division in the loop), the normalisation through a 256-entry table
+    int ox = tid % p.out_w, oy = tid / p.out_w;
+    for (int pix = tid; pix < n_pix; pix += 256) {
+      int x0 = ox, x1 = ox, a0 = 0, a1 = 0, y0 = oy, y1 = oy, b0 = 0, b1 = 0;
       if (p.resize) {
-        const int x0 = xi[ox], x1 = min(x0 + 1, p.trim_w - 1), a0 = xc[2 * ox], a1 = xc[2 * ox + 1];
-        const int yr = yi[oy], y0 = min(max(yr, 0), p.trim_h - 1), y1 = min(max(yr + 1, 0), p.trim_h - 1);
-        const int b0 = yc[2 * oy], b1 = yc[2 * oy + 1];
-        const int r0 = px(y0, x0) * a0 + px(y0, x1) * a1;
-        const int r1 = px(y1, x0) * a0 + px(y1, x1) * a1;
-        v = (((b0 * (r0 >> 4)) >> 16) + ((b1 * (r1 >> 4)) >> 16) + 2) >> 2;
-        v = min(max(v, 0), 255);
-      } else {
-        v = px(oy, ox);
+        x0 = xi[ox]; x1 = min(x0 + 1, p.trim_w - 1); a0 = xc[2 * ox]; a1 = xc[2 * ox + 1];
+        const int yr = yi[oy];
+        y0 = min(max(yr, 0), p.trim_h - 1); y1 = min(max(yr + 1, 0), p.trim_h - 1); b0 = yc[2 * oy]; b1 = yc[2 * oy + 1];
       }
-      if constexpr (sizeof(OutT) == 1) {
-        of[i] = (OutT)v;
-      } else {
-        const float x = (float)v;
-        __stcs(of + i, p.normalize == 1 ? __fdiv_rn(x, p.max_val) : __fsub_rn(__fdiv_rn(__fmul_rn(x, 2.f), p.max_val), 1.f));
+      const int o00 = ((y0 + p.top) * p.src_w + (x0 + p.left)) * sc, o01 = ((y0 + p.top) * p.src_w + (x1 + p.left)) * sc;
+      const int o10 = ((y1 + p.top) * p.src_w + (x0 + p.left)) * sc, o11 = ((y1 + p.top) * p.src_w + (x1 + p.left)) * sc;
+      for (int c = 0; c < p.out_c; ++c) {
+        const int cs = sc == 1 ? 0 : c;
+        int v;
+        if (p.resize) {
+          const int r0 = fr[o00 + cs] * a0 + fr[o01 + cs] * a1;
+          const int r1 = fr[o10 + cs] * a0 + fr[o11 + cs] * a1;
+          v = (((b0 * (r0 >> 4)) >> 16) + ((b1 * (r1 >> 4)) >> 16) + 2) >> 2;
+          v = min(max(v, 0), 255);
+        } else {
+          v = fr[o00 + cs];
+        }
+        if constexpr (sizeof(OutT) == 1) of[pix * p.out_c + c] = (OutT)v;
+        else __stcs(of + pix * p.out_c + c, lut[v]);
       }
+      ox += dx; oy += dy;
+      if (ox >= p.out_w) { ox -= p.out_w; ++oy; }
     }
     __syncthreads();
   }
