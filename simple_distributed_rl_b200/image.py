@@ -345,6 +345,27 @@ class ImageQNet:
         return self._loss, self._pri[:B], self._tq[:B]
 
 
+    def apply_gradients(self):
+        """The optimiser half of an update (phases = 2): Adam on whatever sits in `self.grads`, target sync, counters."""
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.srlx_imageq_train(C.byref(self.c), None, None, None, None, None, None, 1, None, None, None, 2, _stream()))
+
+    def train_data_parallel(self, state, n_state, action, reward, undone, weights, group=None):
+        """One Trainer.train() of ONE trainer over the ranks of a torch.distributed group (the reference's distributed mode has a single
+        trainer, srl/base/run/play_mp.py:352-462): every rank runs forward / backward on ITS shard of the batch (equal shard sizes), the
+        flat gradient is averaged with one NCCL all-reduce over NVLink -- the Huber loss is a mean over the global batch -- and every rank
+        applies the same Adam step, so parameters, moments and target network stay identical on all ranks.  Returns this rank's
+        (loss of its shard, priorities, target_q)."""
+        import torch.distributed as dist
+
+        out = self.train(state, n_state, action, reward, undone, weights, phases=1)
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+            dist.all_reduce(self.grads, op=dist.ReduceOp.SUM, group=group)
+            self.grads.div_(dist.get_world_size(group))
+        self.apply_gradients()
+        return out
+
+
 # =====================================================================================================================
 class DemoMixMemory:
     """PriorityReplayBuffer's demo memory (srl/rl/memories/priority_replay_buffer.py:177-240) over any IPriorityMemory (the device

@@ -202,3 +202,40 @@ def test_r2d2_actor_shards_one_learner_under_torchrun():
     assert r.returncode == 0 and line, r.stdout[-2000:] + r.stderr[-2000:]
     out = json.loads(line[-1][len("R2D2DP "):])
     assert out["world"] == 2 and out["replicas_bit_identical"] is True and out["train_count"] >= 20 and out["global_batch"] == 64
+
+
+def test_image_trainer_data_parallel_equals_one_trainer_on_the_global_batch():
+    """The conv Q-network's trainer over 2 GPUs (image.ImageQNet.train(phases=1) -> gradient average -> apply_gradients(), what
+    train_data_parallel does with an NCCL all-reduce under torchrun): two ranks with half the batch each == one network on the whole
+    batch, update after update, and the ranks stay bit-identical."""
+    _need_gpus(2)
+    from simple_distributed_rl_b200 import image as im
+
+    obs, A, B = (84, 84, 4), 6, 16
+    spec = im.ImageNetSpec(obs, "IMAGE_MAP", A)
+    one = im.ImageQNet(spec, batch_size=2 * B, seed=3, target_model_update_interval=2, device="cuda:0")
+    ranks = [im.ImageQNet(spec, batch_size=B, seed=3, target_model_update_interval=2, device=f"cuda:{r}") for r in range(2)]
+    rng = np.random.default_rng(0)
+    for u in range(4):
+        fr = rng.integers(0, 256, size=(2, 2 * B) + obs, dtype=np.uint8)
+        st = (fr / np.float32(255)).astype(np.float32)
+        a, r_ = rng.integers(0, A, 2 * B), rng.normal(0, 1, 2 * B).astype(np.float32)
+        ud, w = (rng.random(2 * B) > 0.2).astype(np.float32), rng.uniform(0.3, 1, 2 * B).astype(np.float32)
+        loss1, pri1, tq1 = one.train(st[0], st[1], a, r_, ud, w)
+        outs = []
+        for k, net in enumerate(ranks):
+            sl = slice(k * B, (k + 1) * B)
+            outs.append(net.train(st[0][sl], st[1][sl], a[sl], r_[sl], ud[sl], w[sl], phases=1))
+        g = (ranks[0].grads + ranks[1].grads.to("cuda:0")) / 2  # = dist.all_reduce(SUM) / world
+        ranks[0].grads.copy_(g)
+        ranks[1].grads.copy_(g.to("cuda:1"))
+        for net in ranks:
+            net.apply_gradients()
+        assert torch.equal(ranks[0].params.cpu(), ranks[1].params.cpu()) and torch.equal(ranks[0].target.cpu(), ranks[1].target.cpu())
+        np.testing.assert_allclose(torch.cat([o[2].cpu() for o in outs]).numpy(), tq1.cpu().numpy(), rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose(torch.cat([o[1].cpu() for o in outs]).numpy(), pri1.cpu().numpy(), rtol=1e-4, atol=1e-6)
+        np.testing.assert_allclose(float(outs[0][0] + outs[1][0].cpu().to(outs[0][0].device)) / 2, float(loss1), rtol=1e-5)
+        d = (ranks[0].params - one.params).abs()
+        # Adam's +-lr steps on entries whose gradient is rounding noise (see test_image_gpu.py): statistical bar on the parameters
+        assert float((d > 2e-5).float().mean()) <= 0.02 and float(d.max()) <= 5e-4, (u, float((d > 2e-5).float().mean()), float(d.max()))
+    assert ranks[0].train_count == ranks[1].train_count == one.train_count == 4 and ranks[0].sync_count == one.sync_count == 2
