@@ -300,13 +300,17 @@ class ImageQNet:
 
     # ---- batches ------------------------------------------------------------------------------------------------------
     def _states(self, x) -> torch.Tensor:
-        want = torch.uint8 if self.uint8_states else torch.float32
+        """uint8 frames (only on a network built with uint8_states=True: its workspace holds the normalised copy) or float32 states;
+        sets the struct's in_u8 for the call that follows."""
         if isinstance(x, np.ndarray):
-            if self.uint8_states and x.dtype != np.uint8:
-                raise ValueError(f"this network takes uint8 frames, got {x.dtype}")
-            x = torch.from_numpy(np.ascontiguousarray(x, dtype=np.uint8 if self.uint8_states else np.float32)).to(self.device, non_blocking=True)
-        if not x.is_cuda or x.dtype != want or tuple(x.shape[1:]) != self.spec.obs_shape:
-            raise ValueError(f"states must be a CUDA {want} tensor [n, {self.spec.obs_shape}], got {x.dtype} {tuple(x.shape)} on {x.device}")
+            x = np.ascontiguousarray(x if x.dtype == np.uint8 else x.astype(np.float32, copy=False))
+            x = torch.from_numpy(x).to(self.device, non_blocking=True)
+        u8 = x.dtype == torch.uint8
+        if u8 and not self.uint8_states:
+            raise ValueError("uint8 states need a network built with uint8_states=True")
+        if not x.is_cuda or x.dtype not in (torch.uint8, torch.float32) or tuple(x.shape[1:]) != self.spec.obs_shape:
+            raise ValueError(f"states must be a CUDA uint8 / float32 tensor [n, {self.spec.obs_shape}], got {x.dtype} {tuple(x.shape)} on {x.device}")
+        self.c.in_u8 = int(u8)
         return x.contiguous()
 
     def _vec(self, x, dtype) -> torch.Tensor:
@@ -334,6 +338,8 @@ class ImageQNet:
         """One Trainer.train() on the batch.  Returns (loss [1], priorities [B], target_q [B]) as device tensors (views of buffers that
         the next call overwrites)."""
         s, ns = self._states(state), self._states(n_state)
+        if s.dtype != ns.dtype:
+            raise ValueError("state and n_state must have the same dtype")
         B = s.shape[0]
         a, r = self._vec(action, torch.int32), self._vec(reward, torch.float32)
         u, w = self._vec(undone, torch.float32), self._vec(weights, torch.float32)

@@ -196,8 +196,9 @@ def test_imageq_uint8_states_equal_float_states_bitwise_and_chunked_forward(im):
     fr, st, a, r, ud, w = _batch(np.random.default_rng(4), B, obs_shape, A)
     qf, qu = net_f.pred_q(st[:, 0]), net_u.pred_q(fr[:, 0])  # cap = 3: 8 states in chunks of 3, 3, 2
     assert torch.equal(qf, qu)
+    assert torch.equal(net_u.pred_q(st[:, 0]), qu)  # a uint8-capable network takes float32 states too (the worker's policy does)
     with pytest.raises(ValueError):
-        net_u.pred_q(st[:, 0])  # float states to a uint8 network
+        net_f.pred_q(fr[:, 0])  # uint8 frames need a network built with uint8_states=True
     with pytest.raises(Exception):
         net_u.train(fr[:, 0], fr[:, 1], a, r, ud, w)  # batch 8 > batch_cap 3
 
@@ -244,6 +245,37 @@ def test_reference_runner_trains_image_dqn_on_device(srl_mod, tmp_path):
         cfg.memory.capacity, cfg.memory.warmup_size, cfg.memory.compress = 500, 32, False
         return cfg
 
+    # (a) device memory: uint8 frames resident in HBM, uniform and proportional; file round trip in the reference's item format
+    for mem_kind in ("uniform", "per"):
+        srl_image.register(device_memory=True)
+        try:
+            cfg = make_cfg(srl_image.DeviceImageProcessor)
+            if mem_kind == "per":
+                cfg.memory.set_proportional()
+            runner = srl.Runner("PixelGrid-b200", cfg)
+            state = runner.train(max_train_count=40)
+            mem = state.memory
+            assert type(mem).__name__ == "DeviceImageMemory" and mem.S.dtype == torch.uint8 and mem.S.is_cuda
+            assert state.trainer.get_train_count() == 40 and np.isfinite(state.trainer.info["loss"]) and mem.length() >= 32 + 40 - 2
+            # what sits in HBM is what the reference's processor + window stacking produced, as bytes: a frame's background is blue = 40,
+            # gray = (40 * 3735 + 16384) >> 15 = 5 after cv2's conversion
+            mem.flush()
+            assert int(mem.S[:mem.length()].min()) >= 0 and 5 in mem.S[:mem.length()].unique().tolist()
+            if mem_kind == "per":
+                assert mem.per.length() == mem.length() and mem.per.max_priority > 0
+            path_m = str(tmp_path / f"m_{mem_kind}.dat")
+            runner.save_memory(path_m)
+            n_before, s_before = mem.length(), mem.S[:mem.length()].clone()
+            runner2 = srl.Runner("PixelGrid-b200", cfg)
+            runner2.load_memory(path_m)
+            mem2 = runner2.make_memory()
+            mem2.flush()
+            assert mem2.length() == n_before and torch.equal(mem2.S[:n_before], s_before)
+            item = mem2._item(0)
+            assert len(item) == 6 and item[0].dtype == np.float32 and item[0].shape == (28, 36, 2)  # the worker's record (dqn.py:229-246)
+        finally:
+            srl_image.unregister()
+    # (b) the reference's own Memory (host lists), device processor / network / trainer
     srl_image.register()
     try:
         runner = srl.Runner("PixelGrid-b200", make_cfg(srl_image.DeviceImageProcessor))
