@@ -8,11 +8,12 @@
 //
 // One CTA = one 128 x BN output tile (BN = 32 / 64), 256 threads, all of them PRODUCERS: operands are not plain matrices (strided views,
 // and the im2col matrix of a convolution gathered on the fly with replicate padding), so instead of TMA the threads copy their fixed
-// tile slots with cp.async (16-byte chunks where 4 consecutive k are contiguous, else 4-byte words), two k slices (32 columns each)
-// ahead, straight into the canonical K-major 128-byte-swizzle layout (row r, 16-byte chunk c at r * 128 + ((c ^ (r & 7)) << 4)); when
+// tile slots with cp.async (16-byte chunks where 4 consecutive k are contiguous, else 4-byte words), one k slice (32 columns) ahead,
+// straight into the canonical K-major 128-byte-swizzle layout (row r, 16-byte chunk c at r * 128 + ((c ^ (r & 7)) << 4)); when
 // a slice has landed each thread splits its own slots in place (hi) and into a second tile (lo).  fence.proxy.async + barrier, then
-// ONE thread issues 4 k-steps x 3 tcgen05.mma (M = 128, N = BN, K = 8) and commits the stage's "empty" mbarrier; a 4-stage ring keeps
-// the tensor cores busy while the next slices are on their way.  Epilogue: tcgen05.ld (32 lanes x 32 columns) of every k chunk's
+// ONE thread issues 4 k-steps x 3 tcgen05.mma (M = 128, N = BN, K = 8) and commits the stage's "empty" mbarrier.  Two stages of
+// (hi + lo) tiles = 97 KB and 256 TMEM columns per CTA, so TWO CTAs share an SM and cover each other's copy latency (measured: 1.00 ->
+// 0.91 ms per update against one CTA with a 4-stage ring, batch-256 forward 0.56 -> 0.40 ms).  Epilogue: tcgen05.ld (32 lanes x 32 columns) of every k chunk's
 // accumulator (see t3_gemm_kernel), fp32 sum, then the same accumulate / ReLU / mask epilogue as gemm.cuh, or split-K partials
 // (ws[z][M][N], summed in slice order by splitk_reduce_kernel).
 // The larger of (M, N) rides on the 128-row side; element addresses of C / mask / partials are (row_a * c_a + row_b * c_b).
@@ -33,7 +34,12 @@ __device__ __forceinline__ void col_split(const ConvG& g, int j, int& c, int& kh
   else { kw = j % g.k; j /= g.k; kh = j % g.k; c = j / g.k; }
 }
 
-constexpr int T3_BM = 128, T3_BK = 32, T3_STAGES = 4, T3_THREADS = 256;
+#ifndef T3_STAGES_N
+#define T3_STAGES_N 2
+#endif
+// T3_STAGES / T3_AHEAD: shared-memory ring depth and how many k slices the copies run ahead; T3_TMEM: accumulator columns per CTA
+// (2 stages = 97 KB and 256 columns let TWO CTAs share an SM: 16 warps to hide the copy latency instead of 8)
+constexpr int T3_BM = 128, T3_BK = 32, T3_STAGES = T3_STAGES_N, T3_AHEAD = T3_STAGES_N > 2 ? 2 : 1, T3_TMEM = T3_STAGES_N > 2 ? 512 : 256, T3_THREADS = 256;
 
 struct T3Op {      // one operand as a source of K-major tiles: element (r, k)
   const float* ptr;
@@ -288,12 +294,12 @@ struct T3Producer {
 
 // The tensor cores add into the fp32 accumulator by truncation: over n tcgen05.mma the error grows like n * 2^-24 of the running sum
 // (measured: K = 4096 in one accumulator is 2.7e-6 of sum |a||b|, 40 x an fp32 FMA chain).  So the k range of a CTA is cut into up to
-// 512 / BN CHUNKS, each with its own accumulator in tensor memory (all 512 columns are allocated: one CTA per SM), and the epilogue
+// T3_TMEM / BN CHUNKS, each with its own accumulator in tensor memory (256 columns per CTA: two CTAs share an SM), and the epilogue
 // adds the chunks in fp32 with round-to-nearest.
 template <int BN>
-__global__ void __launch_bounds__(T3_THREADS, 1) t3_gemm_kernel(const T3P p) {
+__global__ void __launch_bounds__(T3_THREADS, T3_STAGES_N > 2 ? 1 : 2) t3_gemm_kernel(const T3P p) {
   constexpr uint32_t TILE_A = T3_BM * 128, TILE_B = BN * 128, STAGE = 2 * TILE_A + 2 * TILE_B;
-  constexpr int NCH = 512 / BN;
+  constexpr int NCH = T3_TMEM / BN;
   extern __shared__ unsigned char t3_smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)t3_smem_raw + 1023) & ~(uintptr_t)1023);
   uint64_t* empty = reinterpret_cast<uint64_t*>(smem + T3_STAGES * STAGE);
@@ -312,7 +318,7 @@ __global__ void __launch_bounds__(T3_THREADS, 1) t3_gemm_kernel(const T3P p) {
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(t3_smem_u32(tmem_base_p)), "n"(512) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(t3_smem_u32(tmem_base_p)), "n"(T3_TMEM) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -325,19 +331,19 @@ __global__ void __launch_bounds__(T3_THREADS, 1) t3_gemm_kernel(const T3P p) {
   const uint32_t idesc = t3_instr_desc(BN);
   auto stage_ptr = [&](int it) { return smem + (it % T3_STAGES) * STAGE; };
 #pragma unroll
-  for (int it = 0; it < 2; ++it) {  // two slices ahead
+  for (int it = 0; it < T3_AHEAD; ++it) {  // T3_AHEAD slices ahead
     if (it < nk) { pa.issue(stage_ptr(it)); pb.issue(stage_ptr(it) + 2 * TILE_A); }
     asm volatile("cp.async.commit_group;" ::: "memory");
   }
   for (int it = 0; it < nk; ++it) {
-    if (it + 2 < nk) {
-      const int nx = it + 2;
+    if (it + T3_AHEAD < nk) {
+      const int nx = it + T3_AHEAD;
       if (nx >= T3_STAGES) t3_mbar_wait(&empty[nx % T3_STAGES], ((nx / T3_STAGES) - 1) & 1);  // the MMAs that read that stage are done
       pa.issue(stage_ptr(nx));
       pb.issue(stage_ptr(nx) + 2 * TILE_A);
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
-    asm volatile("cp.async.wait_group 2;" ::: "memory");  // slice `it` of THIS thread has landed
+    asm volatile("cp.async.wait_group %0;" ::"n"(T3_AHEAD) : "memory");  // slice `it` of THIS thread has landed
     unsigned char* st = stage_ptr(it);
     pa.fixup(st, st + TILE_A);
     pb.fixup(st + 2 * TILE_A, st + 2 * TILE_A + TILE_B);
@@ -407,7 +413,7 @@ __global__ void __launch_bounds__(T3_THREADS, 1) t3_gemm_kernel(const T3P p) {
   __syncthreads();
   if (warp == 0) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(T3_TMEM) : "memory");
   }
 }
 

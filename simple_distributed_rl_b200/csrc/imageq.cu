@@ -449,14 +449,18 @@ static int launch_t3(const IGemmP& q, cudaStream_t s, float* ws, size_t ws_float
   return 0;
 }
 
-// SRLX_IMAGE_TC3=1 routes every map through the tcgen05 tiles of gemm_tc3.cuh.  Same results to fp32 accuracy (tests run both); at the
-// reference's batch sizes it is the slower of the two today (batch 32: 1.00 vs 0.69 ms per update, batch 256: 3.4 vs 2.7 ms;
-// profiles/r3h_t3_ncu_summary.txt: one 198 KB CTA = 8 warps per SM, 1000 instructions per warp and k slice of slot arithmetic and
-// barrier polling, issue slots 29 % busy), so the cp.async + mma.sync tiles below stay the default.
+// Which tile engine runs a map.  Measured per map at the Atari setting (profiles/r3e_* mma.sync, r3m_* tcgen05): the tcgen05 tiles win
+// where a gathered forward map has enough 128-row tiles to put two CTAs on every SM (batch 256: conv 2 / 3 forward 83 vs 117 us,
+// conv 1 forward 114 vs 139 us) and lose on small grids and on the weight-gradient maps (row-fast 4-byte gathers: 353 vs 230 us), so the
+// default is a HYBRID: tcgen05 for forward convolutions with >= 200 tiles, the cp.async + mma.sync tiles for everything else.
+// SRLX_IMAGE_TC3=1 forces every map onto tcgen05 (tests run the whole suite of parity checks that way), SRLX_IMAGE_MMA_SYNC=1 onto
+// mma.sync.
 static const bool g_image_tc3 = getenv("SRLX_IMAGE_TC3") != nullptr;
+static const bool g_image_mma_sync = getenv("SRLX_IMAGE_MMA_SYNC") != nullptr;
 
 static int launch_igemm(IGemmP q, cudaStream_t s, float* ws, size_t ws_floats) {
   if (g_image_tc3) return launch_t3(q, s, ws, ws_floats);
+  if (!g_image_mma_sync && q.gather == 1 && (long long)((q.g.M + T3_BM - 1) / T3_BM) * ((q.g.N + 63) / 64) >= 200) return launch_t3(q, s, ws, ws_floats);
   GemmP& p = q.g;
   if (p.M <= 0 || p.N <= 0) return 0;
   p.gate = Gate{nullptr, 0};
