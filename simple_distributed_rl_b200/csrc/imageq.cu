@@ -161,18 +161,22 @@ __global__ void __launch_bounds__(256) col2im_kernel(const ConvG g, const float*
     if (act[i] > 0.f) {
       const int oh_lo = ih == 0 ? 0 : max(0, (ih + g.p - g.k + 1 + g.s - 1) / g.s), oh_hi = ih == g.H - 1 ? g.OH - 1 : min(g.OH - 1, (ih + g.p) / g.s);
       const int ow_lo = iw == 0 ? 0 : max(0, (iw + g.p - g.k + 1 + g.s - 1) / g.s), ow_hi = iw == g.W - 1 ? g.OW - 1 : min(g.OW - 1, (iw + g.p) / g.s);
-      for (int oh = oh_lo; oh <= oh_hi; ++oh)
-        for (int kh = 0; kh < g.k; ++kh) {
-          if (min(max(oh * g.s - g.p + kh, 0), g.H - 1) != ih) continue;
+      const bool in_h = ih > 0 && ih < g.H - 1, in_w = iw > 0 && iw < g.W - 1;  // an interior pixel is read by exactly ONE kh (kw) per oh (ow)
+      for (int oh = oh_lo; oh <= oh_hi; ++oh) {
+        const int kh0 = in_h ? ih + g.p - oh * g.s : 0, kh1 = in_h ? kh0 : g.k - 1;
+        for (int kh = kh0; kh <= kh1; ++kh) {
+          if (!in_h && min(max(oh * g.s - g.p + kh, 0), g.H - 1) != ih) continue;
           for (int ow = ow_lo; ow <= ow_hi; ++ow) {
             const float* row = dcol + ((b * g.OH + oh) * g.OW + ow) * (long long)g.K;
-            for (int kw = 0; kw < g.k; ++kw) {
-              if (min(max(ow * g.s - g.p + kw, 0), g.W - 1) != iw) continue;
+            const int kw0 = in_w ? iw + g.p - ow * g.s : 0, kw1 = in_w ? kw0 : g.k - 1;
+            for (int kw = kw0; kw <= kw1; ++kw) {
+              if (!in_w && min(max(ow * g.s - g.p + kw, 0), g.W - 1) != iw) continue;
               const int j = g.c_fast ? (kh * g.k + kw) * g.C + c : (c * g.k + kh) * g.k + kw;
               sum += row[j];
             }
           }
         }
+      }
     }
     din[i] = sum;
   }
