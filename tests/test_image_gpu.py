@@ -317,3 +317,21 @@ def test_imageq_on_the_tcgen05_tiles_in_a_subprocess():
                        env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
     assert " passed" in r.stdout and "failed" not in r.stdout
+
+
+def test_image_dqn_learns_through_the_reference_runner(srl_mod):
+    """Learning gate of the image path: srl.Runner on PixelGrid (optimal return 0.94) over the device processor / conv Q-network / trainer
+    / uint8 replay reaches >= 0.85 after 3000 updates (tools/image_learning_check.py: 0.94 on seeds 1, 2, 3, ~3 s of training each)."""
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    sys.path.insert(0, os.path.dirname(__file__))
+    import image_env
+    import image_learning_check as lc
+    from simple_distributed_rl_b200 import srl_image
+
+    image_env.register()
+    srl_image.register(device_memory=True)
+    try:
+        reward, _ = lc.run(seed=1, n_train=3000)
+    finally:
+        srl_image.unregister()
+    assert reward >= 0.85, reward
