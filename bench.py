@@ -552,15 +552,186 @@ def own_arm(args):
         dist.destroy_process_group()
 
 
+# ---------------------------------------------------------------------------------------------------------------------
+# --workload image: the observation pipeline of the image configs, an HBM-bound byte kernel.  A step = one pass of
+# ImageProcessor.remap_observation (srl/rl/processors/image_processor.py:104-154: RGB -> gray, cv2 linear resize 210 x 160 -> 84 x 84,
+# "0to1" normalisation: the InputImageBlockConfig "DQN" default, input_block.py:205) over a batch of --frames synthetic Atari frames
+# (826 MB at the default 8192: larger than L2).  Metric frames/s; every rank processes its own frames (weak scaling, no collective).
+# ---------------------------------------------------------------------------------------------------------------------
+IMG_SRC, IMG_DST = (210, 160, 3), (84, 84)
+IMG_BYTES = IMG_SRC[0] * IMG_SRC[1] * IMG_SRC[2] + IMG_DST[0] * IMG_DST[1] * 4  # algorithmic bytes per frame: uint8 in, float32 out
+
+
+def image_config(args):
+    return {"workload": "ImageProcessor RGB 210x160x3 uint8 -> GRAY_HW1 84x84 float32 '0to1' (InputImageBlockConfig DQN default; SURVEY 8f rank 4)",
+            "frames_per_launch": args.frames, "launches_per_step": args.launches_per_step, "frames_per_step": args.frames * args.launches_per_step,
+            "l2": "inputs larger than L2 (frames_per_launch x 100.8 KB in, x 28.2 KB out)"}
+
+
+def _image_cpu_worker(a):
+    kind, n_frames, seed = a
+    import numpy as np
+    rng = np.random.default_rng(seed)
+    frames = rng.integers(0, 256, size=(64,) + IMG_SRC, dtype=np.uint8)
+    if kind == "reference":  # the reference's own class (cv2 underneath), from baseline/_ref
+        sys.path.insert(0, REF_DIR)
+        from srl.base.define import SpaceTypes
+        from srl.base.spaces.box import BoxSpace
+        from srl.rl.processors.image_processor import ImageProcessor
+        sp = BoxSpace(IMG_SRC, 0, 255, np.uint8, SpaceTypes.RGB)
+        proc = ImageProcessor(SpaceTypes.GRAY_HW1, (IMG_DST[1], IMG_DST[0]), normalize_type="0to1")
+        ns = proc.remap_observation_space(sp)
+        fn = lambda f: proc.remap_observation(f, sp, ns)  # noqa: E731
+    else:
+        from oracle import image as oimg
+        fn = lambda f: oimg.process(f, "RGB", "GRAY_HW1", (IMG_DST[1], IMG_DST[0]), "0to1")  # noqa: E731
+    fn(frames[0])
+    t0 = time.perf_counter()
+    for i in range(n_frames):
+        fn(frames[i & 63])
+    return n_frames, time.perf_counter() - t0
+
+
+def image_cpu_run(n_procs, n_frames):
+    kind = "reference"
+    try:
+        import cv2  # noqa: F401
+        assert os.path.isfile(os.path.join(REF_DIR, "srl", "__init__.py"))
+    except Exception:
+        kind = "port"
+        n_frames = max(50, n_frames // 40)  # the numpy port is ~40 x slower than cv2
+    if n_procs == 1:
+        res = [_image_cpu_worker((kind, n_frames, 1))]
+    else:
+        import multiprocessing as mp
+        with mp.get_context("spawn").Pool(n_procs) as pool:
+            res = pool.map(_image_cpu_worker, [(kind, n_frames, 1 + i) for i in range(n_procs)])
+    total, t = sum(r[0] for r in res), max(r[1] for r in res)
+    what = ("srl ImageProcessor(GRAY_HW1, (84, 84), '0to1').remap_observation (cv2 cvtColor + resize) from baseline/_ref" if kind == "reference"
+            else "oracle/image.py (numpy restatement of the cv2 fixed-point algorithms; cv2 or baseline/_ref absent)")
+    return {"value": total / t, "kind": kind, "cores": n_procs, "sample": f"{what}: {n_frames} synthetic 210x160x3 frames per process, {n_procs} process(es)"}
+
+
+def image_reference_arm(args):
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    K, W = args.steps, max(3, args.warmup)
+    cores = os.cpu_count() or 1
+    image_cpu_run(cores, 200 * W)
+    t0 = time.perf_counter()
+    r = image_cpu_run(cores, 2000 * K)
+    line = {"impl": "reference", "metric": "frames_per_sec", "value": r["value"], "unit": "frames/s", "n_gpus": int(os.environ.get("WORLD_SIZE", "1")),
+            "steps": K, "warmup": W, "ms_per_step": 1e3 * (time.perf_counter() - t0) / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u8", "data": "synthetic", "config": image_config(args),
+            "cpu_baseline": {"value": r["value"], "unit": "frames/s", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]},
+            "e2e": {"value": r["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def image_arm(args):
+    import torch
+    import torch.distributed as dist
+
+    from simple_distributed_rl_b200 import _lib, image
+
+    rank, world, local_rank = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback; use --impl reference for the CPU path)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device(f"cuda:{local_rank}")
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.load()
+    n, K, W, R = args.frames, args.steps, max(3, args.warmup), args.launches_per_step
+    pipe = image.DeviceImagePipeline(IMG_SRC, "RGB", "GRAY_HW1", (IMG_DST[1], IMG_DST[0]), "0to1", device=str(dev))
+    gen = torch.Generator(device=dev).manual_seed(1 + rank)
+    frames = torch.randint(0, 256, (n,) + IMG_SRC, dtype=torch.uint8, device=dev, generator=gen)
+    out = torch.empty((n,) + IMG_DST + (1,), dtype=torch.float32, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(W * R):
+        pipe(frames, out=out)
+    clk = ClockSampler("GPU-" + str(torch.cuda.get_device_properties(dev).uuid).replace("GPU-", ""))
+    barrier()
+    clk.start()
+    l0 = lib.srlx_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(K * R):
+        pipe(frames, out=out)  # inputs (826 MB) and outputs (231 MB) are larger than L2: every launch streams from HBM
+    e1.record()
+    barrier()
+    launches = lib.srlx_launch_count() - l0
+    clocks = clk.stop()
+    t_dev = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_dev, op=dist.ReduceOp.MAX)
+    t_dev = float(t_dev[0])
+    value = n * K * R * world / (t_dev * 1e-3)
+    # end to end through the public API with HOST buffers: pinned uint8 frames -> device, the kernel, float32 states -> pinned host memory
+    n_e = min(n, 2048)
+    h_in = torch.empty((n_e,) + IMG_SRC, dtype=torch.uint8).pin_memory()
+    h_in.copy_(frames[:n_e].cpu())
+    h_out = torch.empty((n_e,) + IMG_DST + (1,), dtype=torch.float32).pin_memory()
+    for _ in range(2):
+        h_out.copy_(pipe(h_in.to(dev, non_blocking=True)), non_blocking=True)
+    barrier()
+    e0.record()
+    for _ in range(K):
+        h_out.copy_(pipe(h_in.to(dev, non_blocking=True)), non_blocking=True)
+    e1.record()
+    barrier()
+    t_e = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
+    e2e = {"value": n_e * K * world / (float(t_e[0]) * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": int(h_in.numel()), "d2h_bytes_per_step": int(h_out.numel() * 4),
+           "frames_per_step": n_e, "note": "DeviceImagePipeline(frames) on pinned host uint8 frames, float32 states copied back to pinned host memory: PCIe-bound"}
+    if rank == 0:
+        peak, peak_src = 6543.1, "fallback"
+        try:
+            peak, peak_src = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]), "measured"
+        except Exception:
+            pass
+        traffic, traffic_src = None, None
+        try:
+            d = json.load(open(os.path.join(ROOT, "profiles", "r3o_image_process_ncu_summary.json")))[0]
+            traffic, traffic_src = d["dram_bytes"] * n / 8192.0, "profiles/r3o_image_process_ncu_summary.json (8192 frames per launch)"
+        except Exception:
+            pass
+        achieved = IMG_BYTES * n * K * R / (t_dev * 1e-3) / 1e9
+        roofline = {"kernel": "image_process_staged_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                    "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "algorithmic_bytes_per_frame": IMG_BYTES,
+                    "frames_per_launch": n, "launch_ms": t_dev / (K * R), "formula": "achieved = algorithmic_bytes_per_frame * frames_per_launch / launch duration"}
+        cpu = None
+        if not args.no_cpu_baseline:
+            r = image_cpu_run(1, 20000)
+            cpu = {"value": r["value"], "unit": "frames/s", "cores": 1, "kind": r["kind"], "sample": r["sample"]}
+        line = {"metric": "frames_per_sec", "value": value, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": t_dev / K,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": image_config(args),
+                "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="own", choices=["own", "reference"])
-    ap.add_argument("--workload", default="rainbow", choices=sorted(WORKLOADS),
+    ap.add_argument("--workload", default="rainbow", choices=sorted(WORKLOADS) + ["image"],
                     help="rainbow = BASELINE configs[2] (the headline, default); dqn = configs[1] (use --envs 4096) and dqn_default = "
-                         "the reference's default DQN config: side measurements")
+                         "the reference's default DQN config: side measurements; image = the observation pipeline of the image configs "
+                         "(SURVEY 8f rank 4; metric frames/s)")
+    ap.add_argument("--frames", type=int, default=8192, help="--workload image: frames per launch")
+    ap.add_argument("--launches-per-step", type=int, default=100, help="--workload image: launches in one bench step (100 x 0.27 ms: a 0.5 s timed region)")
     ap.add_argument("--envs", type=int, default=8192)
     ap.add_argument("--ring-rows", type=int, default=256)
     ap.add_argument("--train-interval", type=int, default=10,
@@ -576,6 +747,8 @@ def main():
     ap.add_argument("--no-presample", action="store_true", help="skip the extra measurement of the opt-in pre-sampled mode")
     ap.add_argument("--force-port", action="store_true", help="CPU arms: use the oracle port even when baseline/_ref is present")
     args = ap.parse_args()
+    if args.workload == "image":
+        return image_reference_arm(args) if args.impl == "reference" else image_arm(args)
     if args.impl == "reference":
         reference_arm(args)
     else:
