@@ -558,6 +558,12 @@ typedef struct srlx_imageq {
   int32_t n_actions, n_params, batch_cap;
   int32_t enable_double_dqn, enable_rescale;
   uint32_t target_update_interval;
+  int32_t dueling, duel_hidden;         /* SRLX_DUEL_*; != NONE: the rainbow head (srl/rl/torch_/blocks/dueling_network.py:8-59) as the last two
+                                           dense layers -- [value-hidden (H) ; advantage-hidden (H)] of width 2H, then 1 + A rows over 2H inputs whose
+                                           off-branch blocks are structural zeros (row 0 reads [0, H), rows 1..A read [H, 2H); Adam never moves them)
+                                           -- followed by Q = V + Adv - mean / max / nothing */
+  int32_t target_f32;                   /* != 0: the target arithmetic of rainbow_nomultisteps.py:10-43 (float32 throughout); 0: dqn.py:143-173
+                                           (numpy promotes reward + undone * discount * maxq to float64) */
   double discount, lr, adam_beta1, adam_beta2, adam_eps;
   float* params; float* target; float* adam_m; float* adam_v; float* grads;  /* [n_params] each */
   uint64_t* counters;                   /* device [4]: train_count, adam_step, sync_count, reserved */

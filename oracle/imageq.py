@@ -7,6 +7,8 @@ Follows
   srl/rl/torch_/blocks/mlp_block.py, srl/algorithms/dqn/model_torch.py:17-29   Flatten -> Linear + ReLU ... -> Linear(A)
   srl/algorithms/dqn/dqn.py:143-173                         calc_target_q (double DQN, rescaling; no invalid actions)
   srl/algorithms/dqn/model_torch.py:75-131                  Trainer.train: HuberLoss(target * w, q * w), Adam, priorities, target sync
+  srl/rl/torch_/blocks/dueling_network.py:8-59, srl/algorithms/rainbow/model_torch.py:15-29,85-122, rainbow_nomultisteps.py:10-43
+                                                            rainbow (multisteps = 1) over the same image block: dueling head, float32 targets
 written over a plain dict of arrays under the reference's state_dict keys (torch.nn.functional calls, no reference module).
 Pinned by tests/golden/imageq_*.npz -- the reference's own Trainer.train on frozen batches (tests/golden/make_golden_image.py).
 """
@@ -39,7 +41,7 @@ def inverse_rescaling(x, eps=0.001):
 
 
 class ImageQ:
-    def __init__(self, sd, obs_shape, stype, double=True, rescale=False, discount=0.99, lr=0.001, sync_interval=1000, target_sd=None):
+    def __init__(self, sd, obs_shape, stype, double=True, rescale=False, discount=0.99, lr=0.001, sync_interval=1000, target_sd=None, dueling=None):
         self.obs_shape, self.stype = tuple(obs_shape), stype
         self.p = {k: torch.tensor(np.asarray(v), dtype=torch.float32, requires_grad=True) for k, v in sd.items()}
         tsd = sd if target_sd is None else target_sd
@@ -48,7 +50,9 @@ class ImageQ:
         self.opt = torch.optim.Adam(list(self.p.values()), lr=lr)
         self.train_count = 0
         self.sync_count = 0
-        self.n_hidden = sum(1 for k in sd if k.startswith("hidden_block.hidden_layers.") and k.endswith(".weight"))
+        self.n_hidden = sum(1 for k in sd if k.startswith("hidden_block.hidden_layers.") and k.endswith(".weight") and "_layers." not in k[27:])
+        self.dueling = dueling  # None | "average" | "max" | "": the block sits at hidden_block.hidden_layers.{2 * n_hidden}
+        self.target_f32 = dueling is not None
 
     def forward(self, params, x: torch.Tensor) -> torch.Tensor:
         x = to_nchw(x, self.obs_shape, self.stype)
@@ -58,7 +62,18 @@ class ImageQ:
         x = x.flatten(1)
         for i in range(self.n_hidden):
             x = F.relu(F.linear(x, params[f"hidden_block.hidden_layers.{2 * i}.weight"], params[f"hidden_block.hidden_layers.{2 * i}.bias"]))
-        return F.linear(x, params["out_layer.weight"], params["out_layer.bias"])
+        if self.dueling is None:
+            return F.linear(x, params["out_layer.weight"], params["out_layer.bias"])
+        base = f"hidden_block.hidden_layers.{2 * self.n_hidden}."
+        v = F.linear(F.relu(F.linear(x, params[base + "v_layers.0.weight"], params[base + "v_layers.0.bias"])), params[base + "v_layers.2.weight"],
+                     params[base + "v_layers.2.bias"])
+        adv = F.linear(F.relu(F.linear(x, params[base + "adv_layers.0.weight"], params[base + "adv_layers.0.bias"])), params[base + "adv_layers.2.weight"],
+                       params[base + "adv_layers.2.bias"])
+        if self.dueling == "average":
+            return v + adv - torch.mean(adv, dim=-1, keepdim=True)
+        if self.dueling == "max":
+            return v + adv - torch.max(adv, dim=-1, keepdim=True)[0]
+        return v + adv
 
     def pred_q(self, state, target=False):
         with torch.no_grad():
@@ -73,7 +88,10 @@ class ImageQ:
             maxq = np.max(n_q_target, axis=1)
         if self.rescale:
             maxq = inverse_rescaling(maxq)
-        target_q = np.asarray(reward, np.float32) + np.asarray(undone, np.int64) * self.discount * maxq
+        if self.target_f32:  # rainbow_nomultisteps.py:13-17,36: every array float32
+            target_q = np.asarray(reward, np.float32) + np.asarray(undone, np.float32) * self.discount * maxq
+        else:  # dqn.py: undone stays an int array -> float64
+            target_q = np.asarray(reward, np.float32) + np.asarray(undone, np.int64) * self.discount * maxq
         if self.rescale:
             target_q = rescaling(target_q)
         return target_q.astype(np.float32)

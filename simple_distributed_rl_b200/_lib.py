@@ -157,6 +157,7 @@ class SrlxImageQ(C.Structure):
         ("dense_out", C.c_int32 * SRLX_MAX_LAYERS), ("dense_k", C.c_int32 * SRLX_MAX_LAYERS), ("dense_off", C.c_int32 * SRLX_MAX_LAYERS),
         ("n_actions", C.c_int32), ("n_params", C.c_int32), ("batch_cap", C.c_int32),
         ("enable_double_dqn", C.c_int32), ("enable_rescale", C.c_int32), ("target_update_interval", C.c_uint32),
+        ("dueling", C.c_int32), ("duel_hidden", C.c_int32), ("target_f32", C.c_int32),
         ("discount", C.c_double), ("lr", C.c_double), ("adam_beta1", C.c_double), ("adam_beta2", C.c_double), ("adam_eps", C.c_double),
         ("params", _P), ("target", _P), ("adam_m", _P), ("adam_v", _P), ("grads", _P),
         ("counters", _P), ("ws", _P), ("ws_floats", C.c_uint64),

@@ -539,10 +539,15 @@ __global__ void __launch_bounds__(256) imageq_loss_kernel(const srlx_imageq q, c
       for (int a = 1; a < A; ++a) maxq = fmaxf(maxq, nt[a]);
     }
     if (q.enable_rescale) maxq = inverse_rescaling_f(maxq);
-    // reward (f32) + undone (int array) * discount (python float) * maxq (f32): numpy promotes to float64, then .astype(float32)
-    double t = (double)reward[b] + ((double)undone[b] * q.discount) * (double)maxq;
-    if (q.enable_rescale) t = rescaling_d(t);
-    const float tq = (float)t;
+    float tq;
+    if (q.target_f32) {  // rainbow_nomultisteps.py:36-41: every array is float32, the python-float discount is a weak scalar
+      tq = __fadd_rn(reward[b], __fmul_rn(__fmul_rn(undone[b], (float)q.discount), maxq));
+      if (q.enable_rescale) tq = rescaling_f(tq);
+    } else {  // dqn.py:166-171: reward (f32) + undone (int array) * discount (python float) * maxq (f32) -> float64, then .astype(float32)
+      double t = (double)reward[b] + ((double)undone[b] * q.discount) * (double)maxq;
+      if (q.enable_rescale) t = rescaling_d(t);
+      tq = (float)t;
+    }
     const int a_sel = action[b];
     const float qv = q0[(size_t)b * A + a_sel], w = weights[b];
     const float x = __fsub_rn(__fmul_rn(qv, w), __fmul_rn(tq, w));
@@ -569,7 +574,12 @@ __global__ void __launch_bounds__(256) imageq_adam_kernel(const srlx_imageq q) {
   const float step_size = (float)(q.lr / (1.0 - pow(q.adam_beta1, t))), bc2_sqrt = (float)sqrt(1.0 - pow(q.adam_beta2, t));
   const float b1 = (float)q.adam_beta1, b2 = (float)q.adam_beta2, eps = (float)q.adam_eps;
   const bool sync = tc % (uint64_t)q.target_update_interval == 0;
+  const int h_off = q.dense_off[q.n_dense - 1], H = q.duel_hidden, h_ld = 2 * H + 1;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < q.n_params; i += gridDim.x * blockDim.x) {
+    if (q.dueling && i >= h_off) {  // the off-branch blocks of the dueling output layer are not parameters
+      const int r = (i - h_off) / h_ld, c = (i - h_off) - r * h_ld;
+      if (r == 0 ? (c >= H && c < 2 * H) : c < H) continue;
+    }
     const float g = q.grads[i];
     float p = q.params[i], m = q.adam_m[i], v = q.adam_v[i];
     m = m + (g - m) * (1.0f - b1);
@@ -588,6 +598,39 @@ __global__ void imageq_count_kernel(const srlx_imageq q) {
   q.counters[1] += 1;
 }
 
+// dueling_network.py:51-58: y = [V, Adv_0..Adv_{A-1}] -> Q = V + Adv - mean(Adv) | - max(Adv) | nothing
+__global__ void duel_combine_kernel(const float* __restrict__ y, const int n, const int A, const int kind, float* __restrict__ qout) {
+  for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < n; b += gridDim.x * blockDim.x) {
+    const float* yb = y + (size_t)b * (1 + A);
+    float sub = 0.f;
+    if (kind == SRLX_DUEL_AVERAGE) {
+      for (int a = 0; a < A; ++a) sub += yb[1 + a];
+      sub /= (float)A;
+    } else if (kind == SRLX_DUEL_MAX) {
+      sub = yb[1];
+      for (int a = 1; a < A; ++a) sub = fmaxf(sub, yb[1 + a]);
+    }
+    for (int a = 0; a < A; ++a) qout[(size_t)b * A + a] = yb[0] + yb[1 + a] - sub;
+  }
+}
+// its backward: dV = sum_a dQ_a; dAdv_a = dQ_a - mean_a dQ (average) | dQ_a - [a == argmax Adv] sum_a dQ (max) | dQ_a (naive)
+__global__ void duel_backward_kernel(const float* __restrict__ dq, const float* __restrict__ y, const int n, const int A, const int kind,
+                                     float* __restrict__ dy) {
+  for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < n; b += gridDim.x * blockDim.x) {
+    const float* d = dq + (size_t)b * A;
+    const float* yb = y + (size_t)b * (1 + A);
+    float sum = 0.f;
+    for (int a = 0; a < A; ++a) sum += d[a];
+    int arg = 0;
+    for (int a = 1; a < A; ++a)
+      if (yb[1 + a] > yb[1 + arg]) arg = a;  // torch.max: the first maximum takes the gradient
+    float* o = dy + (size_t)b * (1 + A);
+    o[0] = sum;
+    for (int a = 0; a < A; ++a)
+      o[1 + a] = kind == SRLX_DUEL_AVERAGE ? d[a] - sum / (float)A : (kind == SRLX_DUEL_MAX ? d[a] - (a == arg ? sum : 0.f) : d[a]);
+  }
+}
+
 __global__ void fill_kernel(float* p, const long long n, const long long stride, const float v) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) p[i * stride] = v;
 }
@@ -598,14 +641,19 @@ struct ImageQPlan {
   long long rows[SRLX_MAX_CONV];          // per sample: OH * OW
   size_t cact[SRLX_MAX_CONV], dcact[SRLX_MAX_CONV], dcol;
   size_t act[SRLX_MAX_LAYERS], dact[SRLX_MAX_LAYERS];
-  size_t ones, one4, qbuf, dq, tq, split, in_f32;
+  size_t ones, one4, qbuf, dq, tq, split, in_f32, y, dy;
   size_t split_floats, total;
   int flat;                               // inputs of dense 0
 };
 
 static int imageq_plan(const srlx_imageq* q, ImageQPlan& pl) {
   SRLX_REQUIRE(q->n_conv >= 1 && q->n_conv <= SRLX_MAX_CONV && q->n_dense >= 1 && q->n_dense <= SRLX_MAX_LAYERS, "imageq: 1..%d conv layers, 1..%d dense layers", SRLX_MAX_CONV, SRLX_MAX_LAYERS);
-  SRLX_REQUIRE(q->batch_cap >= 1 && q->n_actions >= 1 && q->dense_out[q->n_dense - 1] == q->n_actions, "imageq: the last dense layer has n_actions rows");
+  const int duel = q->dueling != SRLX_DUEL_NONE;
+  SRLX_REQUIRE(q->batch_cap >= 1 && q->n_actions >= 1 && q->dense_out[q->n_dense - 1] == q->n_actions + duel,
+               "imageq: the last dense layer has n_actions rows (1 + n_actions with a dueling head)");
+  SRLX_REQUIRE(!duel || (q->dueling >= SRLX_DUEL_AVERAGE && q->dueling <= SRLX_DUEL_NAIVE && q->n_dense >= 2 && q->duel_hidden >= 1 &&
+                         q->dense_out[q->n_dense - 2] == 2 * q->duel_hidden),
+               "imageq: a dueling head is the last two dense layers, [2 * duel_hidden] then [1 + n_actions]");
   const long long B = q->batch_cap;
   size_t off = 0;
   auto take = [&](size_t n) { const size_t o = off; off += (n + 3) / 4 * 4; return o; };
@@ -652,6 +700,8 @@ static int imageq_plan(const srlx_imageq* q, ImageQPlan& pl) {
   pl.split_floats = std::min<size_t>(64 * split_max, (size_t)16 << 20);  // launch_igemm takes fewer slices when they do not fit
   pl.split = take(pl.split_floats);
   pl.in_f32 = take(q->in_u8 ? (size_t)B * q->in_sb : 0);
+  pl.y = take(duel ? (size_t)B * (1 + q->n_actions) : 0);
+  pl.dy = take(duel ? (size_t)B * (1 + q->n_actions) : 0);
   pl.total = off;
   return 0;
 }
@@ -686,7 +736,7 @@ static int imageq_forward(const srlx_imageq* q, const ImageQPlan& pl, const floa
     IGemmP d{};
     GemmP& p = d.g;
     p.B = Wl; p.sb_k = 1; p.sb_n = k + 1;
-    p.C = last ? qout : ws + pl.act[l]; p.ldc = last ? out : out + 1;
+    p.C = last ? (q->dueling ? ws + pl.y : qout) : ws + pl.act[l]; p.ldc = last ? out : out + 1;
     p.M = n; p.N = out;
     if (l == 0) {  // the flattened conv output has no constant column: bias as a second, K = 1 map against the ones vector
       p.A = ws + pl.cact[q->n_conv - 1]; p.sa_m = k; p.sa_k = 1; p.K = k;
@@ -698,6 +748,10 @@ static int imageq_forward(const srlx_imageq* q, const ImageQPlan& pl, const floa
       p.A = ws + pl.act[l - 1]; p.sa_m = k + 1; p.sa_k = 1; p.K = k + 1; p.relu = !last;
       if (launch_igemm(d, s, sws, pl.split_floats)) return -1;
     }
+  }
+  if (q->dueling) {
+    duel_combine_kernel<<<grid_for(n), 256, 0, s>>>(ws + pl.y, n, q->n_actions, q->dueling, qout);
+    count_launch();
   }
   return 0;
 }
@@ -848,6 +902,12 @@ int srlx_imageq_train(const srlx_imageq* q, const void* state, const void* n_sta
     float* sws = ws + pl.split;
     const float* dout = ws + pl.dq;
     int ld_dout = A;
+    if (q->dueling) {  // pl.y still holds [V, Adv] of the online pass on `state` (the last forward)
+      duel_backward_kernel<<<grid_for(B), 256, 0, s>>>(ws + pl.dq, ws + pl.y, B, A, q->dueling, ws + pl.dy);
+      count_launch();
+      dout = ws + pl.dy;
+      ld_dout = 1 + A;
+    }
     for (int l = q->n_dense - 1; l >= 0; --l) {
       const int k = q->dense_k[l], out = q->dense_out[l];
       const float* X = l == 0 ? ws + pl.cact[q->n_conv - 1] : ws + pl.act[l - 1];

@@ -118,6 +118,7 @@ class ImageNetSpec:
     hidden: Tuple[int, ...] = (512,)
     conv: Tuple[Tuple[int, int, int], ...] = DQN_CONV
     conv_filters: Optional[Tuple[int, ...]] = None
+    dueling: Optional[str] = None  # None: Linear(A) (dqn); "average" | "max" | "" (naive): rainbow's DuelingNetworkBlock, hidden[-1] = its units
 
     def __post_init__(self):
         s, t = tuple(int(v) for v in self.obs_shape), self.obs_type
@@ -155,7 +156,20 @@ class ImageNetSpec:
         self.last_chw = (c, h, w)
         self.dense = []  # (out, k, off)
         kk = self.flat
-        for out in tuple(int(v) for v in self.hidden) + (int(self.n_actions),):
+        hid = tuple(int(v) for v in self.hidden)
+        self.duel = {None: _lib.DUEL_NONE, "none": _lib.DUEL_NONE, "average": _lib.DUEL_AVERAGE, "max": _lib.DUEL_MAX, "": _lib.DUEL_NAIVE,
+                     "naive": _lib.DUEL_NAIVE}[self.dueling]
+        if self.duel != _lib.DUEL_NONE:
+            if len(hid) < 1:
+                raise ValueError("a dueling head needs at least one layer size (its hidden units)")
+            self.duel_hidden = hid[-1]
+            outs = hid[:-1] + (2 * hid[-1], 1 + int(self.n_actions))  # [value-hidden ; advantage-hidden], then [V ; Adv]
+        else:
+            self.duel_hidden = 0
+            outs = hid + (int(self.n_actions),)
+        if len(outs) > _lib.SRLX_MAX_LAYERS:
+            raise ValueError("too many layers")
+        for out in outs:
             self.dense.append((out, kk, off))
             off += out * (kk + 1)
             kk = out
@@ -168,12 +182,28 @@ class ImageNetSpec:
     def _dense_key(self, l):
         return "out_layer." if l == len(self.dense) - 1 else f"hidden_block.hidden_layers.{2 * l}."
 
+    def _dense_parts(self):
+        """[(layer l, row0, rows, col0, cols, key prefix)]: which Linear of the reference fills which sub-block of dense layer l."""
+        n, parts = len(self.dense), []
+        if self.duel == _lib.DUEL_NONE:
+            for l, (out, kk, off) in enumerate(self.dense):
+                parts.append((l, 0, out, 0, kk, self._dense_key(l)))
+            return parts
+        for l in range(n - 2):
+            out, kk, off = self.dense[l]
+            parts.append((l, 0, out, 0, kk, f"hidden_block.hidden_layers.{2 * l}."))
+        base, H, A = f"hidden_block.hidden_layers.{2 * (n - 2)}.", self.duel_hidden, int(self.n_actions)
+        kk = self.dense[n - 2][1]
+        parts += [(n - 2, 0, H, 0, kk, base + "v_layers.0."), (n - 1, 0, 1, 0, H, base + "v_layers.2."),
+                  (n - 2, H, H, 0, kk, base + "adv_layers.0."), (n - 1, 1, A, H, H, base + "adv_layers.2.")]
+        return parts
+
     def keys(self) -> List[str]:
         ks = []
         for l in range(len(self.conv_geo)):
             ks += [self._conv_key(l) + "weight", self._conv_key(l) + "bias"]
-        for l in range(len(self.dense)):
-            ks += [self._dense_key(l) + "weight", self._dense_key(l) + "bias"]
+        for (_, _, _, _, _, key) in self._dense_parts():
+            ks += [key + "weight", key + "bias"]
         return ks
 
     def from_state_dict(self, sd) -> np.ndarray:
@@ -185,14 +215,17 @@ class ImageNetSpec:
                 raise ValueError(f"state_dict[{self._conv_key(l)}weight] has shape {W_.shape}, expected {(f, c, k, k)}")
             cols = W_.transpose(0, 2, 3, 1).reshape(f, -1) if c_fast else W_.reshape(f, -1)
             flat[off:off + f * (c * k * k + 1)] = np.concatenate([cols, b.reshape(f, 1)], axis=1).reshape(-1)
-        for l, (out, kk, off) in enumerate(self.dense):
-            W_, b = arr(sd[self._dense_key(l) + "weight"]), arr(sd[self._dense_key(l) + "bias"])
-            if W_.shape != (out, kk):
-                raise ValueError(f"state_dict[{self._dense_key(l)}weight] has shape {W_.shape}, expected {(out, kk)}")
+        for (l, r0, rows, c0, cols, key) in self._dense_parts():
+            out, kk, off = self.dense[l]
+            W_, b = arr(sd[key + "weight"]), arr(sd[key + "bias"])
+            if W_.shape != (rows, cols):
+                raise ValueError(f"state_dict[{key}weight] has shape {W_.shape}, expected {(rows, cols)}")
             if l == 0:  # torch flattens (c, h, w); the device's conv output is (h, w, c)
                 c, h, w = self.last_chw
-                W_ = W_.reshape(out, c, h, w).transpose(0, 2, 3, 1).reshape(out, kk)
-            flat[off:off + out * (kk + 1)] = np.concatenate([W_, b.reshape(out, 1)], axis=1).reshape(-1)
+                W_ = W_.reshape(rows, c, h, w).transpose(0, 2, 3, 1).reshape(rows, cols)
+            blk = flat[off:off + out * (kk + 1)].reshape(out, kk + 1)  # a view: off-branch blocks of a dueling head stay zero
+            blk[r0:r0 + rows, c0:c0 + cols] = W_
+            blk[r0:r0 + rows, kk] = b
         return flat
 
     def to_state_dict(self, flat: np.ndarray):
@@ -203,14 +236,15 @@ class ImageNetSpec:
             W_ = cols.reshape(f, k, k, c).transpose(0, 3, 1, 2) if c_fast else cols.reshape(f, c, k, k)
             sd[self._conv_key(l) + "weight"] = torch.from_numpy(np.ascontiguousarray(W_).copy())
             sd[self._conv_key(l) + "bias"] = torch.from_numpy(blk[:, -1].copy())
-        for l, (out, kk, off) in enumerate(self.dense):
+        for (l, r0, rows, c0, cols, key) in self._dense_parts():
+            out, kk, off = self.dense[l]
             blk = np.asarray(flat[off:off + out * (kk + 1)]).reshape(out, kk + 1)
-            W_ = blk[:, :-1]
+            W_ = blk[r0:r0 + rows, c0:c0 + cols]
             if l == 0:
                 c, h, w = self.last_chw
-                W_ = W_.reshape(out, h, w, c).transpose(0, 3, 1, 2).reshape(out, kk)
-            sd[self._dense_key(l) + "weight"] = torch.from_numpy(np.ascontiguousarray(W_).copy())
-            sd[self._dense_key(l) + "bias"] = torch.from_numpy(blk[:, -1].copy())
+                W_ = W_.reshape(rows, h, w, c).transpose(0, 3, 1, 2).reshape(rows, cols)
+            sd[key + "weight"] = torch.from_numpy(np.ascontiguousarray(W_).copy())
+            sd[key + "bias"] = torch.from_numpy(blk[r0:r0 + rows, kk].copy())
         return sd
 
     def init_state_dict(self, seed: int = 0):
@@ -222,14 +256,14 @@ class ImageNetSpec:
             bound = 1.0 / math.sqrt(c * k * k)
             sd[self._conv_key(l) + "weight"] = (torch.rand(f, c, k, k, generator=gen) * 2 - 1) * bound
             sd[self._conv_key(l) + "bias"] = (torch.rand(f, generator=gen) * 2 - 1) * bound
-        for l, (out, kk, off) in enumerate(self.dense):
-            if l < len(self.dense) - 1:
-                sd[self._dense_key(l) + "weight"] = torch.randn(out, kk, generator=gen) * math.sqrt(2.0 / kk)
-                sd[self._dense_key(l) + "bias"] = torch.zeros(out)
-            else:
-                bound = 1.0 / math.sqrt(kk)
-                sd[self._dense_key(l) + "weight"] = (torch.rand(out, kk, generator=gen) * 2 - 1) * bound
-                sd[self._dense_key(l) + "bias"] = (torch.rand(out, generator=gen) * 2 - 1) * bound
+        for (l, r0, rows, c0, cols, key) in self._dense_parts():
+            if "hidden_block.hidden_layers" in key and "_layers." not in key.split("hidden_layers.")[1]:  # MLPBlock Linear: he_normal, zero bias
+                sd[key + "weight"] = torch.randn(rows, cols, generator=gen) * math.sqrt(2.0 / cols)
+                sd[key + "bias"] = torch.zeros(rows)
+            else:  # out_layer and the dueling block's Linear layers: torch defaults
+                bound = 1.0 / math.sqrt(cols)
+                sd[key + "weight"] = (torch.rand(rows, cols, generator=gen) * 2 - 1) * bound
+                sd[key + "bias"] = (torch.rand(rows, generator=gen) * 2 - 1) * bound
         return sd
 
 
@@ -242,7 +276,8 @@ class ImageQNet:
     def __init__(self, spec: ImageNetSpec, batch_size: int = 32, enable_double_dqn: bool = True, enable_rescale: bool = False,
                  discount: float = 0.99, lr: float = 0.001, target_model_update_interval: int = 1000, adam_beta1: float = 0.9,
                  adam_beta2: float = 0.999, adam_eps: float = 1e-8, uint8_states: bool = False, max_val: float = 255.0, seed: int = 0,
-                 device: str = "cuda:0", batch_cap: Optional[int] = None):
+                 device: str = "cuda:0", batch_cap: Optional[int] = None, target_f32: Optional[bool] = None):
+        """target_f32: the float32 target arithmetic of rainbow_nomultisteps.py (default: on with a dueling head, i.e. for rainbow specs)"""
         self.lib = _lib.load()
         self.device = torch.device(device)
         if self.device.type != "cuda" or not torch.cuda.is_available():
@@ -261,6 +296,8 @@ class ImageQNet:
             q.dense_out[l], q.dense_k[l], q.dense_off[l] = out, kk, off
         q.n_actions, q.n_params, q.batch_cap = spec.n_actions, spec.n_params, cap
         q.enable_double_dqn, q.enable_rescale, q.target_update_interval = int(enable_double_dqn), int(enable_rescale), int(target_model_update_interval)
+        q.dueling, q.duel_hidden = spec.duel, spec.duel_hidden
+        q.target_f32 = int(spec.duel != _lib.DUEL_NONE if target_f32 is None else target_f32)
         q.discount, q.lr, q.adam_beta1, q.adam_beta2, q.adam_eps = discount, lr, adam_beta1, adam_beta2, adam_eps
         f32 = dict(dtype=torch.float32, device=self.device)
         self.params, self.target = torch.zeros(spec.n_params, **f32), torch.zeros(spec.n_params, **f32)

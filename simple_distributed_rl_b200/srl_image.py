@@ -20,7 +20,10 @@ What plugs in where:
   srl/algorithms/dqn/model_torch.py:75-131                ImageTrainer.train(): memory.sample() (the reference's own replay, host
                                                           lists) -> one batch upload -> srlx_imageq_train -> memory.update()
 Memory and Worker stay the reference's classes (dqn.Memory, dqn.Worker): the worker's policy calls ImageParameter.pred_q.
-Not covered (raises): activation other than relu, image blocks other than "DQN" (R2D3 / AlphaZero / MuZero blocks), invalid actions.
+Rainbow with multisteps = 1 ("Rainbow_no_multisteps:torch": the dueling head of srl/rl/torch_/blocks/dueling_network.py, average / max / naive,
+float32 targets of rainbow_nomultisteps.py) runs through the same classes.
+Not covered (raises): activation other than relu, image blocks other than "DQN" (R2D3 / AlphaZero / MuZero blocks), invalid actions,
+NoisyNet and n-step Retrace targets over image states.
 """
 from dataclasses import dataclass
 from typing import Any, cast
@@ -77,12 +80,27 @@ def spec_from_config(config) -> ImageNetSpec:
     if str(img.kwargs.get("activation", "relu")).lower() != "relu":
         raise NotImplementedError("image block activation other than relu")
     hk = dict(getattr(config.hidden_block, "kwargs", {}) or {})
-    if config.hidden_block.name != "MLP" or str(hk.get("activation", "relu")).lower() != "relu":
-        raise NotImplementedError(f"hidden block {config.hidden_block.name!r} / activation {hk.get('activation')!r}")
-    return ImageNetSpec(tuple(obs.shape), obs.stype.name, int(act.n), filters=int(img.kwargs.get("filters", 32)), hidden=tuple(hk["layer_sizes"]))
+    rainbow = hasattr(config, "multisteps")
+    if rainbow and (int(config.multisteps) != 1 or bool(getattr(config, "enable_noisy_dense", False))):
+        raise NotImplementedError("rainbow over image states: multisteps = 1 without NoisyNet is built on the device (Rainbow_no_multisteps)")
+    filters = int(img.kwargs.get("filters", 32))
+    if config.hidden_block.name == "MLP" and not rainbow:
+        if str(hk.get("activation", "relu")).lower() != "relu":
+            raise NotImplementedError(f"hidden block activation {hk.get('activation')!r}")
+        return ImageNetSpec(tuple(obs.shape), obs.stype.name, int(act.n), filters=filters, hidden=tuple(hk["layer_sizes"]))
+    if config.hidden_block.name == "DuelingNetwork" and rainbow:
+        acts = (hk.get("mlp_kwargs", {}).get("activation", "relu"), hk.get("dueling_kwargs", {}).get("activation", "relu"))
+        if any(str(a).lower() != "relu" for a in acts):
+            raise NotImplementedError(f"dueling network activations {acts!r}")
+        return ImageNetSpec(tuple(obs.shape), obs.stype.name, int(act.n), filters=filters, hidden=tuple(hk["layer_sizes"]),
+                            dueling=hk.get("dueling_kwargs", {}).get("dueling_type", "average"))
+    raise NotImplementedError(f"hidden block {config.hidden_block.name!r} for {'rainbow' if rainbow else 'dqn'} over image states "
+                              "(dqn: MLP; rainbow: DuelingNetwork)")
 
 
-class ImageParameter(CommonInterfaceParameter):
+class _ImageParameterMixin:
+    """setup / backup / restore / pred_q over ImageQNet, shared by the dqn and the rainbow parameter classes"""
+
     def setup(self) -> None:
         super().setup()
         cfg = self.config
@@ -116,6 +134,22 @@ class ImageParameter(CommonInterfaceParameter):
 
     def pred_target_q(self, state) -> np.ndarray:
         return self.net.pred_target_q(np.asarray(state, dtype=np.float32)).cpu().numpy().astype(self.np_dtype, copy=False)
+
+
+class ImageParameter(_ImageParameterMixin, CommonInterfaceParameter):
+    """srl/algorithms/dqn/model_torch.py:34-72"""
+
+
+def _rainbow_parameter_class():
+    from srl.algorithms.rainbow.rainbow import CommonInterfaceParameter as RainbowParameterBase
+
+    class ImageRainbowParameter(_ImageParameterMixin, RainbowParameterBase):
+        """srl/algorithms/rainbow/model_torch.py:32-72 (multisteps = 1: rainbow_nomultisteps.py)"""
+
+    return ImageRainbowParameter
+
+
+ImageRainbowParameter = _rainbow_parameter_class()
 
 
 class DeviceImageMemory(RLMemory):
@@ -326,16 +360,19 @@ _saved = {}
 
 
 def register(device_memory: bool = False) -> None:
-    """Take over "DQN:torch": the reference's Worker, the device Parameter / Trainer, and either the reference's Memory (host lists,
+    """Take over "DQN:torch" and "Rainbow_no_multisteps:torch": the reference's Worker, the device Parameter / Trainer, and either the reference's Memory (host lists,
     the batch uploaded per update) or DeviceImageMemory (uint8 frames resident in HBM, device_memory=True)."""
     from srl.algorithms import dqn
 
+    from srl.algorithms import rainbow
+
     reg = rl_registration._registry
-    key = rl_registration._create_registry_key(dqn.Config().set_torch())
-    if key not in _saved:
-        _saved[key] = list(reg[key])
-    mem_ep, _, _, worker_ep = _saved[key]
-    reg[key] = [f"{_MOD}:DeviceImageMemory" if device_memory else mem_ep, f"{_MOD}:ImageParameter", f"{_MOD}:ImageTrainer", worker_ep]
+    for cfg, par in ((dqn.Config().set_torch(), "ImageParameter"), (rainbow.Config(multisteps=1).set_torch(), "ImageRainbowParameter")):
+        key = rl_registration._create_registry_key(cfg)
+        if key not in _saved:
+            _saved[key] = list(reg[key])
+        mem_ep, _, _, worker_ep = _saved[key]
+        reg[key] = [f"{_MOD}:DeviceImageMemory" if device_memory else mem_ep, f"{_MOD}:{par}", f"{_MOD}:ImageTrainer", worker_ep]
 
 
 def unregister() -> None:

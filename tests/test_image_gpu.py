@@ -76,7 +76,9 @@ def test_processor_at_atari_batch_size_property(im):
 
 # ---- conv Q-network vs the reference's trainer ------------------------------------------------------------------------------
 def _net_from_golden(im, g, uint8=False, cap=None):
-    spec = im.ImageNetSpec(tuple(g["obs_shape"]), str(g["obs_stype"]), int(g["n_actions"]), filters=int(g["filters"]), hidden=tuple(g["hidden"]))
+    duel = str(g["dueling"]) if "dueling" in g.files else "none"  # rainbow (multisteps = 1) files carry the dueling type
+    spec = im.ImageNetSpec(tuple(g["obs_shape"]), str(g["obs_stype"]), int(g["n_actions"]), filters=int(g["filters"]), hidden=tuple(g["hidden"]),
+                           dueling=None if duel == "none" else duel)
     net = im.ImageQNet(spec, batch_size=g["frames"].shape[1], enable_double_dqn=bool(g["double"]), enable_rescale=bool(g["rescale"]),
                        discount=float(g["discount"]), lr=float(g["lr"]), target_model_update_interval=1000, uint8_states=uint8, batch_cap=cap)
     keys = [str(k) for k in g["keys"]]
@@ -335,3 +337,55 @@ def test_image_dqn_learns_through_the_reference_runner(srl_mod):
     finally:
         srl_image.unregister()
     assert reward >= 0.85, reward
+
+
+def test_reference_runner_trains_image_rainbow_dueling_on_device(srl_mod, tmp_path):
+    """Rainbow with multisteps = 1 ("Rainbow_no_multisteps:torch") and the dueling block over the DQN image block: the reference's loop,
+    Memory (proportional) and Worker; network / trainer on the device; the parameter file loads into the reference's torch Parameter."""
+    import srl
+    from srl.base.define import SpaceTypes
+    from srl.rl.processors.image_processor import ImageProcessor
+
+    sys.path.insert(0, os.path.dirname(__file__))
+    import image_env
+    from simple_distributed_rl_b200 import srl_image
+
+    _, rainbow = srl_mod
+    image_env.register()
+
+    def make_cfg():
+        cfg = rainbow.Config(batch_size=16, lr=1e-3, epsilon=0.3, target_model_update_interval=25, multisteps=1, enable_noisy_dense=False)
+        cfg.input_block.image.set_dqn_block(filters=8)
+        cfg.input_block.image.processors = [ImageProcessor(SpaceTypes.GRAY_HW1, (36, 28), normalize_type="0to1")]
+        cfg.hidden_block.set_dueling_network((24, 16), dueling_type="average")
+        cfg.window_length = 2
+        cfg.memory.set_proportional()
+        cfg.memory.capacity, cfg.memory.warmup_size, cfg.memory.compress = 500, 32, False
+        return cfg
+
+    for device_memory in (False, True):
+        srl_image.register(device_memory=device_memory)
+        try:
+            runner = srl.Runner("PixelGrid-b200", make_cfg())
+            state = runner.train(max_train_count=50)
+            assert type(state.trainer).__name__ == "ImageTrainer" and type(state.parameter).__name__ == "ImageRainbowParameter"
+            assert type(state.worker.worker).__module__ == "srl.algorithms.rainbow.rainbow_nomultisteps"
+            assert type(state.memory).__name__ == ("DeviceImageMemory" if device_memory else "Memory")
+            net = state.parameter.net
+            assert net.train_count == 50 and net.sync_count == 2 and np.isfinite(state.trainer.info["loss"]) and net.c.target_f32 == 1
+            # the off-branch blocks of the dueling output layer never move
+            out, kk, off = net.spec.dense[-1]
+            blk = net.params[off:off + out * (kk + 1)].reshape(out, kk + 1).cpu().numpy()
+            H = net.spec.duel_hidden
+            assert np.all(blk[0, H:2 * H] == 0) and np.all(blk[1:, :H] == 0) and np.any(blk[0, :H] != 0) and np.any(blk[1:, H:2 * H] != 0)
+            path = str(tmp_path / f"p_{int(device_memory)}.dat")
+            runner.save_parameter(path)
+            q_dev = state.parameter.pred_q(np.zeros((1, 28, 36, 2), np.float32) + 0.25)
+        finally:
+            srl_image.unregister()
+        ref_runner = srl.Runner("PixelGrid-b200", make_cfg())
+        ref_runner.set_device("CPU")
+        ref_runner.load_parameter(path)
+        par = ref_runner.make_parameter()
+        assert type(par).__module__.startswith("srl.")
+        np.testing.assert_allclose(par.pred_q(np.zeros((1, 28, 36, 2), np.float32) + 0.25), q_dev, rtol=1e-4, atol=5e-5)
