@@ -17,8 +17,9 @@ for shape, st, it, rs, nm in [((64, 48, 3), "RGB", "GRAY_HW1", (28, 36), "0to1")
     out = pipe(rng.integers(0, 256, size=(5,) + shape, dtype=np.uint8))
     torch.cuda.synchronize()
     print("pipe ok", tuple(out.shape), out.dtype)
-for obs, stype, u8, hidden in [((28, 36, 4), "IMAGE_MAP", True, (32,)), ((3, 30, 26), "GRAY_HW", False, ()), ((20, 24, 3), "RGB", False, (24, 16))]:
-    spec = image.ImageNetSpec(obs, stype, 5, filters=8, hidden=hidden)
+for obs, stype, u8, hidden, duel in [((28, 36, 4), "IMAGE_MAP", True, (32,), None), ((3, 30, 26), "GRAY_HW", False, (), None),
+                                     ((20, 24, 3), "RGB", False, (24, 16), None), ((28, 36, 2), "IMAGE_MAP", True, (24, 16), "max")]:
+    spec = image.ImageNetSpec(obs, stype, 5, filters=8, hidden=hidden, dueling=duel)
     net = image.ImageQNet(spec, batch_size=6, uint8_states=u8, target_model_update_interval=2)
     fr = rng.integers(0, 256, size=(2, 6) + obs, dtype=np.uint8)
     x = fr if u8 else (fr / 255.0).astype(np.float32)
