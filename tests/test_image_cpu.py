@@ -93,3 +93,21 @@ def test_linear_table_is_a_host_function_and_matches_the_oracle():
         _lib.check(lib.srlx_image_linear_table(dst, src, border, idx.ctypes.data, coef.ctypes.data))
         oi, oc = oimg.linear_table(dst, src, bool(border))
         assert np.array_equal(idx, oi) and np.array_equal(coef, oc), (dst, src, border)
+
+
+def test_bench_image_reference_arm_prints_the_contract_line():
+    """bench.py --workload image --impl reference: the reference's ImageProcessor (or the numpy port without cv2 / baseline/_ref) on the host
+    cores, one JSON line with the contract's keys."""
+    import json
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--workload", "image", "--impl", "reference", "--steps", "1", "--warmup", "1"],
+                       capture_output=True, text=True, timeout=600, cwd=root)
+    assert r.returncode == 0, r.stderr[-2000:]
+    d = json.loads(r.stdout.strip().splitlines()[-1])
+    assert d["impl"] == "reference" and d["metric"] == "frames_per_sec" and d["unit"] == "frames/s" and d["higher_is_better"] is True
+    assert d["value"] > 0 and d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and "workload" in d["config"]
