@@ -700,8 +700,8 @@ def image_arm(args):
             pass
         traffic, traffic_src = None, None
         try:
-            d = json.load(open(os.path.join(ROOT, "profiles", "r3o_image_process_ncu_summary.json")))[0]
-            traffic, traffic_src = d["dram_bytes"] * n / 8192.0, "profiles/r3o_image_process_ncu_summary.json (8192 frames per launch)"
+            d = json.load(open(os.path.join(ROOT, "profiles", "r3u_image_process_ncu_summary.json")))[0]
+            traffic, traffic_src = d["dram_bytes"] * n / 8192.0, "profiles/r3u_image_process_ncu_summary.json (8192 frames per launch)"
         except Exception:
             pass
         achieved = IMG_BYTES * n * K * R / (t_dev * 1e-3) / 1e9

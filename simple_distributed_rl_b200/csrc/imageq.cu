@@ -78,13 +78,16 @@ __global__ void __launch_bounds__(256) image_process_staged_kernel(const __grid_
   int* yc = yi + p.out_h;
   unsigned char* fr = sm_raw + (((size_t)(3 * p.out_w + 3 * p.out_h) * 4 + 15) / 16) * 16;
   const int tid = threadIdx.x;
-  if (RESIZE) {
-    for (int i = tid; i < p.out_w; i += 256) { xi[i] = p.x_idx[i]; xc[2 * i] = p.x_coef[2 * i]; xc[2 * i + 1] = p.x_coef[2 * i + 1]; }
+  if (RESIZE) {  // x: both tap offsets in one word and both coefficients in one word (offsets < 2^16, coefficients <= 2048)
+    for (int i = tid; i < p.out_w; i += 256) {
+      const int x0 = p.x_idx[i], x1 = min(x0 + 1, p.trim_w - 1);
+      xi[i] = ((x0 + p.left) * SC) | (((x1 + p.left) * SC) << 16);
+      xc[i] = p.x_coef[2 * i] | (p.x_coef[2 * i + 1] << 16);
+    }
     for (int i = tid; i < p.out_h; i += 256) { yi[i] = p.y_idx[i]; yc[2 * i] = p.y_coef[2 * i]; yc[2 * i + 1] = p.y_coef[2 * i + 1]; }
   }
   const size_t frame_bytes = (size_t)p.src_h * p.src_w * p.src_c;
   constexpr int sc = SC;  // channels of the staged frame
-  const int n_pix = p.out_h * p.out_w, dx = 256 % p.out_w, dy = 256 / p.out_w;
   __shared__ float lut[256];  // image_processor.py:141-146 for every byte value, float32 arithmetic
   {
     const float x = (float)tid;
@@ -116,34 +119,51 @@ __global__ void __launch_bounds__(256) image_process_staged_kernel(const __grid_
     }
     __syncthreads();
     OutT* of = out + (size_t)f * out_stride;
-    // thread per output PIXEL, (ox, oy) carried as counters (no division in the loop), the normalisation through a 256-entry table
-    int ox = tid % p.out_w, oy = tid / p.out_w;
-    for (int pix = tid; pix < n_pix; pix += 256) {
-      int x0 = ox, x1 = ox, a0 = 0, a1 = 0, y0 = oy, y1 = oy, b0 = 0, b1 = 0;
-      if (RESIZE) {
-        x0 = xi[ox]; x1 = min(x0 + 1, p.trim_w - 1); a0 = xc[2 * ox]; a1 = xc[2 * ox + 1];
-        const int yr = yi[oy];
-        y0 = min(max(yr, 0), p.trim_h - 1); y1 = min(max(yr + 1, 0), p.trim_h - 1); b0 = yc[2 * oy]; b1 = yc[2 * oy + 1];
-      }
-      const int o00 = ((y0 + p.top) * p.src_w + (x0 + p.left)) * sc, o01 = ((y0 + p.top) * p.src_w + (x1 + p.left)) * sc;
-      const int o10 = ((y1 + p.top) * p.src_w + (x0 + p.left)) * sc, o11 = ((y1 + p.top) * p.src_w + (x1 + p.left)) * sc;
+    // lanes own output COLUMNS (3 per lane and block of 96: their tap offsets and coefficients stay in registers), warps own rows: a
+    // row's two source rows and vertical coefficients are warp-uniform, a pixel costs four byte taps and the fixed-point blend; the
+    // normalisation is a 256-entry table
+    const int warp = tid >> 5, lane = tid & 31;
+    for (int xb = 0; xb < p.out_w; xb += 96) {
+      int o0[3], o1[3], a0[3], a1[3];
 #pragma unroll
-      for (int c = 0; c < OC; ++c) {
-        const int cs = sc == 1 ? 0 : c;
-        int v;
+      for (int k = 0; k < 3; ++k) {
+        const int ox = min(xb + lane + 32 * k, p.out_w - 1);
+        o0[k] = o1[k] = (ox + p.left) * SC; a0[k] = a1[k] = 0;
         if (RESIZE) {
-          const int r0 = fr[o00 + cs] * a0 + fr[o01 + cs] * a1;
-          const int r1 = fr[o10 + cs] * a0 + fr[o11 + cs] * a1;
-          v = (((b0 * (r0 >> 4)) >> 16) + ((b1 * (r1 >> 4)) >> 16) + 2) >> 2;
-          v = min(max(v, 0), 255);
-        } else {
-          v = fr[o00 + cs];
+          const uint32_t xo = (uint32_t)xi[ox], xa = (uint32_t)xc[ox];
+          o0[k] = xo & 0xffff; o1[k] = xo >> 16; a0[k] = xa & 0xffff; a1[k] = xa >> 16;
         }
-        if constexpr (sizeof(OutT) == 1) of[pix * OC + c] = (OutT)v;
-        else __stcs(of + pix * OC + c, lut[v]);
       }
-      ox += dx; oy += dy;
-      if (ox >= p.out_w) { ox -= p.out_w; ++oy; }
+      for (int oy = warp; oy < p.out_h; oy += 8) {
+        int r0 = (oy + p.top) * p.src_w * SC, r1 = r0, b0 = 0, b1 = 0;
+        if (RESIZE) {
+          const int yr = yi[oy];
+          r0 = (min(max(yr, 0), p.trim_h - 1) + p.top) * p.src_w * SC;
+          r1 = (min(max(yr + 1, 0), p.trim_h - 1) + p.top) * p.src_w * SC;
+          b0 = yc[2 * oy]; b1 = yc[2 * oy + 1];
+        }
+        OutT* orow = of + (size_t)oy * p.out_w * OC;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          const int ox = xb + lane + 32 * k;
+          if (ox >= p.out_w) break;
+#pragma unroll
+          for (int c = 0; c < OC; ++c) {
+            const int cs = SC == 1 ? 0 : c;
+            int v;
+            if (RESIZE) {
+              const int t0 = fr[r0 + o0[k] + cs] * a0[k] + fr[r0 + o1[k] + cs] * a1[k];
+              const int t1 = fr[r1 + o0[k] + cs] * a0[k] + fr[r1 + o1[k] + cs] * a1[k];
+              v = (((b0 * (t0 >> 4)) >> 16) + ((b1 * (t1 >> 4)) >> 16) + 2) >> 2;
+              v = min(max(v, 0), 255);
+            } else {
+              v = fr[r0 + o0[k] + cs];
+            }
+            if constexpr (sizeof(OutT) == 1) orow[ox * OC + c] = (OutT)v;
+            else __stcs(orow + ox * OC + c, lut[v]);
+          }
+        }
+      }
     }
     __syncthreads();
   }
