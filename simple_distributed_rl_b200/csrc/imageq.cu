@@ -662,6 +662,8 @@ struct ImageQPlan {
   size_t cact[SRLX_MAX_CONV], dcact[SRLX_MAX_CONV], dcol;
   size_t act[SRLX_MAX_LAYERS], dact[SRLX_MAX_LAYERS];
   size_t ones, one4, qbuf, dq, tq, split, in_f32, y, dy;
+  size_t cact2[SRLX_MAX_CONV], act2[SRLX_MAX_LAYERS], y2, split2, in_f32b;  // second and third forward sets: the two passes over n_state run
+  size_t cact3[SRLX_MAX_CONV], act3[SRLX_MAX_LAYERS], y3, split3;           // beside the online pass over state
   size_t split_floats, total;
   int flat;                               // inputs of dense 0
 };
@@ -691,6 +693,8 @@ static int imageq_plan(const srlx_imageq* q, ImageQPlan& pl) {
     pl.rows[l] = (long long)g.OH * g.OW;
     const int F = q->conv_f[l];
     pl.cact[l] = take((size_t)B * pl.rows[l] * F);
+    pl.cact2[l] = take((size_t)B * pl.rows[l] * F);
+    pl.cact3[l] = take((size_t)B * pl.rows[l] * F);
     pl.dcact[l] = take((size_t)B * pl.rows[l] * F);
     if (l > 0 && (size_t)B * pl.rows[l] * g.K > dcol_max) dcol_max = (size_t)B * pl.rows[l] * g.K;
     if ((size_t)F * (g.K + 1) > split_max) split_max = (size_t)F * (g.K + 1);
@@ -705,6 +709,8 @@ static int imageq_plan(const srlx_imageq* q, ImageQPlan& pl) {
     SRLX_REQUIRE(q->dense_k[l] == k && q->dense_off[l] == off_p, "imageq: dense layer %d: dense_k / dense_off do not follow from the shapes (%d at %d expected)", l, k, off_p);
     const int out = q->dense_out[l], last = l == q->n_dense - 1;
     pl.act[l] = take((size_t)B * (out + (last ? 0 : 1)));
+    pl.act2[l] = take((size_t)B * (out + (last ? 0 : 1)));
+    pl.act3[l] = take((size_t)B * (out + (last ? 0 : 1)));
     pl.dact[l] = take((size_t)B * out);
     if ((size_t)B * out > split_max) split_max = (size_t)B * out;  // forward / input-gradient maps of a small batch over a long reduction
     if (l > 0 && (size_t)out * (k + 1) > split_max) split_max = (size_t)out * (k + 1);
@@ -719,8 +725,13 @@ static int imageq_plan(const srlx_imageq* q, ImageQPlan& pl) {
   pl.tq = take((size_t)B + 4);
   pl.split_floats = std::min<size_t>(64 * split_max, (size_t)16 << 20);  // launch_igemm takes fewer slices when they do not fit
   pl.split = take(pl.split_floats);
+  pl.split2 = take(pl.split_floats);
+  pl.split3 = take(pl.split_floats);
   pl.in_f32 = take(q->in_u8 ? (size_t)B * q->in_sb : 0);
+  pl.in_f32b = take(q->in_u8 ? (size_t)B * q->in_sb : 0);
   pl.y = take(duel ? (size_t)B * (1 + q->n_actions) : 0);
+  pl.y2 = take(duel ? (size_t)B * (1 + q->n_actions) : 0);
+  pl.y3 = take(duel ? (size_t)B * (1 + q->n_actions) : 0);
   pl.dy = take(duel ? (size_t)B * (1 + q->n_actions) : 0);
   pl.total = off;
   return 0;
@@ -728,25 +739,32 @@ static int imageq_plan(const srlx_imageq* q, ImageQPlan& pl) {
 
 static unsigned grid_for(long long n) { const long long g = (n + 255) / 256; return (unsigned)(g < 148 * 8 ? (g < 1 ? 1 : g) : 148 * 8); }
 
-// forward of n samples with parameter buffer P; leaves col / cact / act of the pass in the workspace, Q in qout [n][A]
-static int imageq_forward(const srlx_imageq* q, const ImageQPlan& pl, const float* P, const void* state, int n, float* qout, cudaStream_t s) {
+// uint8 frames -> "0to1" floats once per pass (the tile loaders copy 4-byte words straight into shared memory); float states pass through
+static const float* imageq_input(const srlx_imageq* q, const ImageQPlan& pl, const void* state, int n, int which, cudaStream_t s) {
+  if (!q->in_u8) return (const float*)state;
+  float* dst = q->ws + (which ? pl.in_f32b : pl.in_f32);
+  const long long n_in = (long long)n * q->in_sb;
+  u8_to_f32_kernel<<<grid_for(n_in), 256, 0, s>>>((const unsigned char*)state, n_in, q->in_max_val, dst);
+  count_launch();
+  return dst;
+}
+
+// forward of n samples (float states `in`) with parameter buffer P on stream s, in forward-buffer set `set`; leaves cact / act / y of the
+// pass in that set, Q in qout [n][A]
+static int imageq_forward(const srlx_imageq* q, const ImageQPlan& pl, const float* P, const float* in, int n, float* qout, cudaStream_t s, int set) {
   float* ws = q->ws;
-  float* sws = ws + pl.split;
-  const float* in = (const float*)state;
-  if (q->in_u8) {  // uint8 frames -> "0to1" floats once per pass (the tile loaders copy 4-byte words straight into shared memory)
-    const long long n_in = (long long)n * q->in_sb;
-    u8_to_f32_kernel<<<grid_for(n_in), 256, 0, s>>>((const unsigned char*)state, n_in, q->in_max_val, ws + pl.in_f32);
-    count_launch();
-    in = ws + pl.in_f32;
-  }
+  float* sws = ws + (set == 0 ? pl.split : (set == 1 ? pl.split2 : pl.split3));
+  const size_t* cact = set == 0 ? pl.cact : (set == 1 ? pl.cact2 : pl.cact3);
+  const size_t* act = set == 0 ? pl.act : (set == 1 ? pl.act2 : pl.act3);
+  const size_t ybuf = set == 0 ? pl.y : (set == 1 ? pl.y2 : pl.y3);
   for (int l = 0; l < q->n_conv; ++l) {
     const ConvG& g = pl.g[l];
     IGemmP c{};
     c.cv = g; c.gather = 1; c.one = ws + pl.one4;
-    c.src = l == 0 ? in : ws + pl.cact[l - 1];
+    c.src = l == 0 ? in : ws + cact[l - 1];
     GemmP& p = c.g;
     p.B = P + q->conv_off[l]; p.sb_k = 1; p.sb_n = g.K + 1;
-    p.C = ws + pl.cact[l]; p.ldc = q->conv_f[l];
+    p.C = ws + cact[l]; p.ldc = q->conv_f[l];
     p.M = (int)((long long)n * pl.rows[l]); p.N = q->conv_f[l]; p.K = g.K + 1; p.relu = 1;
     if (launch_igemm(c, s, sws, pl.split_floats)) return -1;
   }
@@ -756,24 +774,44 @@ static int imageq_forward(const srlx_imageq* q, const ImageQPlan& pl, const floa
     IGemmP d{};
     GemmP& p = d.g;
     p.B = Wl; p.sb_k = 1; p.sb_n = k + 1;
-    p.C = last ? (q->dueling ? ws + pl.y : qout) : ws + pl.act[l]; p.ldc = last ? out : out + 1;
+    p.C = last ? (q->dueling ? ws + ybuf : qout) : ws + act[l]; p.ldc = last ? out : out + 1;
     p.M = n; p.N = out;
     if (l == 0) {  // the flattened conv output has no constant column: bias as a second, K = 1 map against the ones vector
-      p.A = ws + pl.cact[q->n_conv - 1]; p.sa_m = k; p.sa_k = 1; p.K = k;
+      p.A = ws + cact[q->n_conv - 1]; p.sa_m = k; p.sa_k = 1; p.K = k;
       if (launch_igemm(d, s, sws, pl.split_floats)) return -1;
       IGemmP b = d;
       b.g.A = ws + pl.ones; b.g.sa_m = 1; b.g.sa_k = 1; b.g.B = Wl + k; b.g.K = 1; b.g.accumulate = 1; b.g.relu = !last;
       if (launch_igemm(b, s, sws, pl.split_floats)) return -1;
     } else {
-      p.A = ws + pl.act[l - 1]; p.sa_m = k + 1; p.sa_k = 1; p.K = k + 1; p.relu = !last;
+      p.A = ws + act[l - 1]; p.sa_m = k + 1; p.sa_k = 1; p.K = k + 1; p.relu = !last;
       if (launch_igemm(d, s, sws, pl.split_floats)) return -1;
     }
   }
   if (q->dueling) {
-    duel_combine_kernel<<<grid_for(n), 256, 0, s>>>(ws + pl.y, n, q->n_actions, q->dueling, qout);
+    duel_combine_kernel<<<grid_for(n), 256, 0, s>>>(ws + ybuf, n, q->n_actions, q->dueling, qout);
     count_launch();
   }
   return 0;
+}
+
+// side stream + fork / join events, one set per device (created on first use, kept for the life of the process)
+struct ImageAux { cudaStream_t side, side2; cudaEvent_t fork, join, join2, evb[SRLX_MAX_CONV + SRLX_MAX_LAYERS]; bool ok; };
+static const bool g_image_one_stream = getenv("SRLX_IMAGE_ONE_STREAM") != nullptr;
+static ImageAux* image_aux() {
+  static ImageAux aux[64] = {};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  ImageAux& a = aux[dev];
+  if (!a.ok) {
+    if (cudaStreamCreateWithFlags(&a.side, cudaStreamNonBlocking) != cudaSuccess || cudaStreamCreateWithFlags(&a.side2, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&a.fork, cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&a.join, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&a.join2, cudaEventDisableTiming) != cudaSuccess)
+      return nullptr;
+    for (int i = 0; i < SRLX_MAX_CONV + SRLX_MAX_LAYERS; ++i)
+      if (cudaEventCreateWithFlags(&a.evb[i], cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    a.ok = true;
+  }
+  return &a;
 }
 
 static int imageq_check(const srlx_imageq* q, ImageQPlan& pl) {
@@ -880,7 +918,11 @@ int srlx_imageq_init(const srlx_imageq* q, uintptr_t stream) {
   fill_kernel<<<grid_for(B), 256, 0, s>>>(q->ws + pl.ones, B, 1, 1.f);
   fill_kernel<<<1, 32, 0, s>>>(q->ws + pl.one4, 4, 1, 0.f);
   fill_kernel<<<1, 32, 0, s>>>(q->ws + pl.one4, 1, 1, 1.f);
-  for (int l = 0; l + 1 < q->n_dense; ++l) fill_kernel<<<grid_for(B), 256, 0, s>>>(q->ws + pl.act[l] + q->dense_out[l], B, q->dense_out[l] + 1, 1.f);
+  for (int l = 0; l + 1 < q->n_dense; ++l) {
+    fill_kernel<<<grid_for(B), 256, 0, s>>>(q->ws + pl.act[l] + q->dense_out[l], B, q->dense_out[l] + 1, 1.f);
+    fill_kernel<<<grid_for(B), 256, 0, s>>>(q->ws + pl.act2[l] + q->dense_out[l], B, q->dense_out[l] + 1, 1.f);
+    fill_kernel<<<grid_for(B), 256, 0, s>>>(q->ws + pl.act3[l] + q->dense_out[l], B, q->dense_out[l] + 1, 1.f);
+  }
   count_launch(q->n_dense);
   SRLX_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -890,7 +932,7 @@ int srlx_imageq_forward(const srlx_imageq* q, int use_target, const void* state,
   ImageQPlan pl;
   if (int rc = imageq_check(q, pl)) return rc;
   SRLX_REQUIRE(state && q_out && n >= 1 && n <= (uint32_t)q->batch_cap, "imageq_forward: 1 <= n <= batch_cap (%d), got %u", q->batch_cap, n);
-  if (imageq_forward(q, pl, use_target ? q->target : q->params, state, (int)n, q_out, (cudaStream_t)stream)) return -1;
+  if (imageq_forward(q, pl, use_target ? q->target : q->params, imageq_input(q, pl, state, (int)n, 0, (cudaStream_t)stream), (int)n, q_out, (cudaStream_t)stream, 0)) return -1;
   SRLX_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -912,14 +954,47 @@ int srlx_imageq_train(const srlx_imageq* q, const void* state, const void* n_sta
     float* qb = ws + pl.qbuf;
     // calc_target_q: pred_target_q(n_state), pred_q(n_state) for double DQN (dqn.py:154-162), then the online pass whose activations the
     // backward pass reads
-    if (imageq_forward(q, pl, q->target, n_state, B, qb + (size_t)2 * B * A, s)) return -1;
-    if (q->enable_double_dqn && imageq_forward(q, pl, q->params, n_state, B, qb + (size_t)B * A, s)) return -1;
-    if (imageq_forward(q, pl, q->params, state, B, qb, s)) return -1;
+    // The three forward passes are independent until the loss: the two over n_state run on side streams in their own forward-buffer
+    // sets beside the online pass over state (at batch 32 no map fills the GPU, so the passes overlap); SRLX_IMAGE_ONE_STREAM=1 keeps
+    // one stream.
+    const float* in_n = imageq_input(q, pl, n_state, B, 1, s);
+    const float* in_s = imageq_input(q, pl, state, B, 0, s);
+    ImageAux* ax = g_image_one_stream ? nullptr : image_aux();
+    if (ax) {
+      SRLX_CHECK_CUDA(cudaEventRecord(ax->fork, s));
+      SRLX_CHECK_CUDA(cudaStreamWaitEvent(ax->side, ax->fork, 0));
+      if (imageq_forward(q, pl, q->target, in_n, B, qb + (size_t)2 * B * A, ax->side, 1)) return -1;
+      SRLX_CHECK_CUDA(cudaEventRecord(ax->join, ax->side));
+      if (q->enable_double_dqn) {
+        SRLX_CHECK_CUDA(cudaStreamWaitEvent(ax->side2, ax->fork, 0));
+        if (imageq_forward(q, pl, q->params, in_n, B, qb + (size_t)B * A, ax->side2, 2)) return -1;
+        SRLX_CHECK_CUDA(cudaEventRecord(ax->join2, ax->side2));
+      }
+    } else {
+      if (imageq_forward(q, pl, q->target, in_n, B, qb + (size_t)2 * B * A, s, 1)) return -1;
+      if (q->enable_double_dqn && imageq_forward(q, pl, q->params, in_n, B, qb + (size_t)B * A, s, 2)) return -1;
+    }
+    if (imageq_forward(q, pl, q->params, in_s, B, qb, s, 0)) return -1;
+    if (ax) {
+      SRLX_CHECK_CUDA(cudaStreamWaitEvent(s, ax->join, 0));
+      if (q->enable_double_dqn) SRLX_CHECK_CUDA(cudaStreamWaitEvent(s, ax->join2, 0));
+    }
     imageq_loss_kernel<<<1, 256, 0, s>>>(*q, qb, qb + (size_t)B * A, qb + (size_t)2 * B * A, action, reward, undone, weights, B, ws + pl.dq, pri_out,
                                          loss_out, tq_out);
     count_launch();
-    // dense layers, last to first
+    // dense layers, last to first.  A layer's weight gradient (dW = dOut^T x X) is off the critical path -- only the input gradient feeds
+    // the next layer down -- so every dW map goes to the side stream (own split-K workspace), forked after its dOut is complete and joined
+    // before the optimiser step.
     float* sws = ws + pl.split;
+    float* sws_w = ws + (ax ? pl.split2 : pl.split);
+    int n_fork = 0;
+    auto dw_stream = [&]() -> cudaStream_t {
+      if (!ax) return s;
+      cudaEventRecord(ax->evb[n_fork], s);
+      cudaStreamWaitEvent(ax->side, ax->evb[n_fork], 0);
+      ++n_fork;
+      return ax->side;
+    };
     const float* dout = ws + pl.dq;
     int ld_dout = A;
     if (q->dueling) {  // pl.y still holds [V, Adv] of the online pass on `state` (the last forward)
@@ -938,11 +1013,12 @@ int srlx_imageq_train(const srlx_imageq* q, const void* state, const void* n_sta
       w.B = X; w.sb_k = ldx; w.sb_n = 1;
       w.C = q->grads + q->dense_off[l]; w.ldc = k + 1;
       w.M = out; w.N = l == 0 ? k : k + 1; w.K = B;
-      if (launch_igemm(wq, s, sws, pl.split_floats)) return -1;
+      const cudaStream_t sw = dw_stream();
+      if (launch_igemm(wq, sw, sws_w, pl.split_floats)) return -1;
       if (l == 0) {
         IGemmP bq = wq;
         bq.g.B = ws + pl.ones; bq.g.sb_k = 1; bq.g.sb_n = 1; bq.g.C = q->grads + q->dense_off[l] + k; bq.g.N = 1;
-        if (launch_igemm(bq, s, sws, pl.split_floats)) return -1;
+        if (launch_igemm(bq, sw, sws_w, pl.split_floats)) return -1;
       }
       IGemmP xq{};  // dX[B][k] = (X > 0) * dOut x W[:, :k]
       GemmP& x = xq.g;
@@ -961,12 +1037,12 @@ int srlx_imageq_train(const srlx_imageq* q, const void* state, const void* n_sta
       const long long rows = (long long)B * pl.rows[l];
       IGemmP wq{};  // dW[F][K+1] = dOut^T x im2col(input of the layer), the im2col matrix gathered by the tile loader
       wq.cv = g; wq.gather = 2;
-      wq.src = l == 0 ? (q->in_u8 ? ws + pl.in_f32 : (const float*)state) : ws + pl.cact[l - 1]; wq.one = ws + pl.one4;
+      wq.src = l == 0 ? in_s : ws + pl.cact[l - 1]; wq.one = ws + pl.one4;
       GemmP& w = wq.g;
       w.A = ws + pl.dcact[l]; w.sa_m = 1; w.sa_k = F;
       w.C = q->grads + q->conv_off[l]; w.ldc = g.K + 1;
       w.M = F; w.N = g.K + 1; w.K = (int)rows;
-      if (launch_igemm(wq, s, sws, pl.split_floats)) return -1;
+      if (launch_igemm(wq, dw_stream(), sws_w, pl.split_floats)) return -1;
       if (l == 0) break;
       IGemmP xq{};  // dcol[rows][K] = dOut x W[:, :K]
       GemmP& x = xq.g;
@@ -978,6 +1054,10 @@ int srlx_imageq_train(const srlx_imageq* q, const void* state, const void* n_sta
       const long long n_in = (long long)B * g.H * g.W * g.C;
       col2im_kernel<<<grid_for(n_in), 256, 0, s>>>(g, ws + pl.dcol, ws + pl.cact[l - 1], ws + pl.dcact[l - 1], n_in);
       count_launch();
+    }
+    if (ax) {  // the gradient is complete once the side stream has drained
+      SRLX_CHECK_CUDA(cudaEventRecord(ax->join, ax->side));
+      SRLX_CHECK_CUDA(cudaStreamWaitEvent(s, ax->join, 0));
     }
   }
   if (phases & 2) {
