@@ -9,6 +9,7 @@
 // window slots that read it, in a fixed order: deterministic, no atomics).  Activations are NHWC, so a conv layer's output is the next
 // layer's im2col source and the last one IS the flattened input of the first dense layer.
 #include <algorithm>
+#include <mutex>
 #include <type_traits>
 
 #include "gemm_tc3.cuh"
@@ -419,10 +420,12 @@ __global__ void __launch_bounds__(256) igemm_kernel(const IGemmP q) {
 
 template <int BN>
 static int t3_launch_bn(const T3P& p, dim3 grid, cudaStream_t s) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[64] = {};  // function attributes are per device: one process may drive several (tests/test_multi_gpu.py)
+  int dev = 0;
+  SRLX_CHECK_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64 || !attr_set[dev]) {
     SRLX_CHECK_CUDA(cudaFuncSetAttribute(t3_gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t3_smem_bytes<BN>()));
-    attr_set = true;
+    if (dev >= 0 && dev < 64) attr_set[dev] = true;
   }
   t3_gemm_kernel<BN><<<grid, T3_THREADS, t3_smem_bytes<BN>(), s>>>(p);
   count_launch();
@@ -799,8 +802,10 @@ struct ImageAux { cudaStream_t side, side2; cudaEvent_t fork, join, join2, evb[S
 static const bool g_image_one_stream = getenv("SRLX_IMAGE_ONE_STREAM") != nullptr;
 static ImageAux* image_aux() {
   static ImageAux aux[64] = {};
+  static std::mutex mu;  // first use from two host threads at once
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  std::lock_guard<std::mutex> lock(mu);
   ImageAux& a = aux[dev];
   if (!a.ok) {
     if (cudaStreamCreateWithFlags(&a.side, cudaStreamNonBlocking) != cudaSuccess || cudaStreamCreateWithFlags(&a.side2, cudaStreamNonBlocking) != cudaSuccess ||

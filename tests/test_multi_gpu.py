@@ -239,3 +239,18 @@ def test_image_trainer_data_parallel_equals_one_trainer_on_the_global_batch():
         # Adam's +-lr steps on entries whose gradient is rounding noise (see test_image_gpu.py): statistical bar on the parameters
         assert float((d > 2e-5).float().mean()) <= 0.02 and float(d.max()) <= 5e-4, (u, float((d > 2e-5).float().mean()), float(d.max()))
     assert ranks[0].train_count == ranks[1].train_count == one.train_count == 4 and ranks[0].sync_count == one.sync_count == 2
+
+
+def test_image_network_on_the_tcgen05_tiles_on_the_second_device():
+    """Function attributes (the tcgen05 tiles' 97 KB of dynamic shared memory) are per device: a network on cuda:1 of a process that already
+    ran one on cuda:0 must still launch -- forward maps of 256 states go to the tcgen05 engine by the default rule."""
+    _need_gpus(2)
+    from simple_distributed_rl_b200 import image as im
+
+    spec = im.ImageNetSpec((84, 84, 4), "IMAGE_MAP", 6)
+    x = np.random.default_rng(0).integers(0, 256, size=(256, 84, 84, 4), dtype=np.uint8)
+    qs = []
+    for d in (0, 1):
+        net = im.ImageQNet(spec, batch_size=256, uint8_states=True, seed=3, device=f"cuda:{d}")
+        qs.append(net.pred_q(x).cpu())
+    assert torch.equal(qs[0], qs[1])
