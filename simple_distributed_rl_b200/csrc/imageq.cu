@@ -63,8 +63,6 @@ __global__ void __launch_bounds__(256) image_process_kernel(const __grid_constan
 // gray bytes and stored as one 16-byte word -- so every source byte crosses the memory system exactly once and no lane issues byte
 // loads to global memory; phase 2 forms the outputs from shared memory (4 taps each) and writes them coalesced.  The resize tables sit
 // in shared memory too.
-__device__ __forceinline__ uint32_t gray3(uint32_t r, uint32_t g, uint32_t b) { return (r * 9798u + g * 19235u + b * 3735u + 16384u) >> 15; }
-
 // OC = output channels, SC = channels of the staged frame (1: gray bytes or a gray source; 3: RGB kept), RESIZE: through the tables --
 // compile-time so that the per-pixel loop has no branches and the channel loop unrolls (37.8 k -> 20.6 k warp instructions per Atari
 // frame together with the dp2a gray conversion below)
