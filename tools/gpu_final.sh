@@ -15,6 +15,8 @@ python tools/ncu_summary.py gpurun_out/${TAG}_learner_small.ncu-rep > gpurun_out
 timeout 300 python tools/sumtree_speedtest.py --skip python --out gpurun_out/${TAG}_sumtree_speedtest.json > gpurun_out/${TAG}_sumtree.log 2>&1; tail -3 gpurun_out/${TAG}_sumtree.log | cut -c1-250
 timeout 600 python tools/r2d2_bench.py --cpu-baseline 2 --out gpurun_out/${TAG}_r2d2_bench.json 2>&1 | tail -2 | cut -c1-1500
 timeout 400 python tools/image_bench.py --out gpurun_out/${TAG}_image_bench.json 2>&1 | tail -1 | cut -c1-300
+timeout 400 python bench.py --workload image > gpurun_out/${TAG}_bench_image.json 2>/dev/null; cut -c1-300 gpurun_out/${TAG}_bench_image.json
+timeout 400 python bench.py --workload image --impl reference > gpurun_out/${TAG}_bench_image_reference.json 2>/dev/null; cut -c1-200 gpurun_out/${TAG}_bench_image_reference.json
 python - <<PY
 import json
 for f in ('gpurun_out/${TAG}_bench.json','gpurun_out/${TAG}_bench_dqn.json','gpurun_out/${TAG}_bench_reference.json'):
