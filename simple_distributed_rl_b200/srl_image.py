@@ -56,6 +56,14 @@ def _device_of(config) -> str:
 class DeviceImageProcessor(ImageProcessor):
     """Drop-in for srl.rl.processors.image_processor.ImageProcessor: same fields, same spaces, pixels on the device."""
 
+    def __getstate__(self):
+        # the reference deep-copies / pickles configs (RLConfig.copy, train_mp): the cached device pipeline (CUDA tensors, a ctypes handle)
+        # stays behind and is rebuilt on first use
+        d = dict(self.__dict__)
+        d.pop("_pipe", None)
+        d.pop("_pipe_key", None)
+        return d
+
     def remap_observation(self, state, prev_space: SpaceBase, new_space: SpaceBase, **kwargs):
         state = np.asarray(state)
         if "float" in str(state.dtype):  # the reference neither converts nor resizes float frames (:126-137): nothing for the device to do
@@ -299,14 +307,24 @@ class DeviceImageMemory(RLMemory):
         data[5] = items + [None] * (self.capacity - n)
         return [data, None]
 
+    @staticmethod
+    def _decode(item):
+        """an item as the reference stores it with memory.compress = True (zlib over pickle, priority_replay_buffer.py:205-214)"""
+        if isinstance(item, (bytes, bytearray)):
+            import pickle
+            import zlib
+
+            return pickle.loads(zlib.decompress(item))
+        return item
+
     def call_restore(self, data: Any, **kwargs) -> None:
         if self.per is None:
-            items, write = list(data[0])[-self.capacity:], int(data[1])
+            items, write = [self._decode(it) for it in list(data[0])[-self.capacity:]], int(data[1])
         else:
             pd = list(data[0])
             if int(pd[0]) != self.capacity:
                 raise NotImplementedError(f"restoring a proportional image memory of capacity {pd[0]} into one of {self.capacity}")
-            items, write = [it for it in pd[5][:int(pd[2])]], int(pd[3])
+            items, write = [self._decode(it) for it in pd[5][:int(pd[2])]], int(pd[3])
         self._n_stage, self._count = 0, 0
         saved, self.per = self.per, None  # refill the rings in slot order without touching the tree
         try:

@@ -111,3 +111,34 @@ def test_bench_image_reference_arm_prints_the_contract_line():
     assert d["impl"] == "reference" and d["metric"] == "frames_per_sec" and d["unit"] == "frames/s" and d["higher_is_better"] is True
     assert d["value"] > 0 and d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and "workload" in d["config"]
+
+
+def test_device_image_processor_copies_and_pickles_without_its_device_cache():
+    """the reference deep-copies configs (RLConfig.copy) and pickles them for train_mp: the processor must survive both with a cached
+    pipeline attached"""
+    import copy
+    import pickle
+
+    import os
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    ref = next((p for p in ("/root/reference", os.path.join(root, "baseline", "_ref")) if os.path.isfile(os.path.join(p, "srl", "__init__.py"))), None)
+    if ref is None:
+        pytest.skip("reference not present")
+    if ref not in sys.path:
+        sys.path.insert(0, ref)
+    from srl.base.define import SpaceTypes
+
+    from simple_distributed_rl_b200 import srl_image
+
+    p = srl_image.DeviceImageProcessor(SpaceTypes.GRAY_HW1, (84, 84), normalize_type="0to1")
+    p._pipe, p._pipe_key = _lib.load(), ("not", "copyable")  # a ctypes handle, as the cached pipeline holds
+    for q in (copy.deepcopy(p), pickle.loads(pickle.dumps(p))):
+        assert q == p and not hasattr(q, "_pipe") and q.resize == (84, 84) and q.normalize_type == "0to1"
+    # decode of compressed items (memory.compress = True files of the reference)
+    import zlib
+
+    item = [np.zeros((2, 2), np.float32), np.ones((2, 2), np.float32), [1.0, 0.0], 0.5, 1, []]
+    got = srl_image.DeviceImageMemory._decode(zlib.compress(pickle.dumps(item)))
+    assert np.array_equal(got[1], item[1]) and got[3] == 0.5 and srl_image.DeviceImageMemory._decode(item) is item
